@@ -1,0 +1,67 @@
+/* xo_csr.c — ORACLE (test infrastructure): sparsity graph and element-matrix scatter.
+ * Restates utils/restrictedblf.cpp:142-163 (GetGraph: table of dof rows of the active entities
+ * handed to NGSolve's MatrixGraph = union of the row cliques, columns sorted ascending, explicit
+ * zeros kept, full non-symmetric storage) and NGSolve's SparseMatrix::AddElementMatrix
+ * (third party; binary search of the column in the sorted row).
+ */
+#include "xoracle.h"
+#include <stdlib.h>
+#include <string.h>
+
+static int cmp_i32(const void* a, const void* b)
+{
+  int32_t x = *(const int32_t*)a, y = *(const int32_t*)b;
+  return (x > y) - (x < y);
+}
+
+int64_t xo_graph(int64_t ndof, int64_t nrows, int width, const int32_t* table,
+                 int64_t* rowptr, int32_t* colidx)
+{
+  /* transposed table: dof -> table rows */
+  int64_t* cnt = (int64_t*)calloc(ndof + 1, sizeof(int64_t));
+  for (int64_t r = 0; r < nrows; r++)
+    for (int k = 0; k < width; k++) { int32_t d = table[r * width + k]; if (d >= 0) cnt[d + 1]++; }
+  for (int64_t d = 0; d < ndof; d++) cnt[d + 1] += cnt[d];
+  int64_t* pos = (int64_t*)malloc(sizeof(int64_t) * (ndof + 1));
+  memcpy(pos, cnt, sizeof(int64_t) * (ndof + 1));
+  int64_t* adj = (int64_t*)malloc(sizeof(int64_t) * (cnt[ndof] > 0 ? cnt[ndof] : 1));
+  for (int64_t r = 0; r < nrows; r++)
+    for (int k = 0; k < width; k++) { int32_t d = table[r * width + k]; if (d >= 0) adj[pos[d]++] = r; }
+  int32_t* buf = NULL;
+  int64_t bufcap = 0, nnz = 0;
+  rowptr[0] = 0;
+  for (int64_t d = 0; d < ndof; d++) {
+    int64_t need = (cnt[d + 1] - cnt[d]) * width;
+    if (need > bufcap) { bufcap = need * 2 + 64; buf = (int32_t*)realloc(buf, sizeof(int32_t) * bufcap); }
+    int64_t m = 0;
+    for (int64_t a = cnt[d]; a < cnt[d + 1]; a++)
+      for (int k = 0; k < width; k++) { int32_t c = table[adj[a] * width + k]; if (c >= 0) buf[m++] = c; }
+    qsort(buf, m, sizeof(int32_t), cmp_i32);
+    int64_t u = 0;
+    for (int64_t i = 0; i < m; i++) if (i == 0 || buf[i] != buf[i - 1]) { if (colidx) colidx[nnz + u] = buf[i]; u++; }
+    nnz += u;
+    rowptr[d + 1] = nnz;
+  }
+  free(buf); free(adj); free(pos); free(cnt);
+  return nnz;
+}
+
+void xo_scatter(int64_t ndof, int64_t nrows, int width, const int32_t* table, const double* mats,
+                const int64_t* rowptr, const int32_t* colidx, double* vals)
+{
+  (void)ndof;
+  for (int64_t r = 0; r < nrows; r++) {
+    const int32_t* dn = table + r * width;
+    const double* m = mats + r * (int64_t)width * width;
+    for (int i = 0; i < width; i++) {
+      if (dn[i] < 0) continue;
+      int64_t lo0 = rowptr[dn[i]], hi0 = rowptr[dn[i] + 1];
+      for (int j = 0; j < width; j++) {
+        if (dn[j] < 0) continue;
+        int64_t lo = lo0, hi = hi0;
+        while (lo < hi) { int64_t mid = (lo + hi) / 2; if (colidx[mid] < dn[j]) lo = mid + 1; else hi = mid; }
+        vals[lo] += m[i * width + j];
+      }
+    }
+  }
+}

@@ -1,0 +1,305 @@
+"""ctypes binding of the CPU restatement ORACLE (oracle/libxoracle.so).
+
+TEST INFRASTRUCTURE ONLY: imported by tests/, __graft_entry__.smoke() and the cpu_baseline /
+--impl reference legs of bench.py.  The product package ngsxfem_b200 never imports this.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+NEG, POS, IF = 0, 1, 2
+OP_ID, OP_GRAD, OP_DN = 0, 1, 2
+
+
+class Term(C.Structure):
+    _fields_ = [("op_trial", C.c_int), ("op_test", C.c_int), ("coef", C.c_double), ("hpow", C.c_int)]
+
+
+class Trafo(C.Structure):
+    _fields_ = [("dim", C.c_int), ("vtx", (C.c_double * 3) * 4), ("vnum", C.c_int * 4),
+                ("def_order", C.c_int), ("deform", C.POINTER(C.c_double))]
+
+
+def build(force=False):
+    so = os.path.join(_HERE, "libxoracle.so")
+    srcs = [os.path.join(_HERE, f) for f in os.listdir(_HERE) if f.endswith((".c", ".h", ".inc"))]
+    if force or not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
+        subprocess.check_call(["make", "-C", _HERE, "libxoracle.so"], stdout=subprocess.DEVNULL)
+    return so
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        _LIB = C.CDLL(build())
+        L = _LIB
+        L.xo_integrate_monomial.restype = C.c_double
+        L.xo_simplex_volume.restype = C.c_double
+        L.xo_graph.restype = C.c_int64
+        L.xo_batch_cut_rules.restype = C.c_int64
+    return _LIB
+
+
+def _p(a, t=C.c_double):
+    if a is None:
+        return None
+    return a.ctypes.data_as(C.POINTER(t))
+
+
+def _f64(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def _i32(a):
+    return np.ascontiguousarray(a, dtype=np.int32)
+
+
+def make_trafo(vtx, vnum=None, def_order=0, deform=None):
+    vtx = np.asarray(vtx, dtype=np.float64)
+    dim = vtx.shape[1]
+    T = Trafo()
+    T.dim = dim
+    for k in range(dim + 1):
+        for i in range(dim):
+            T.vtx[k][i] = vtx[k, i]
+        T.vnum[k] = int(vnum[k]) if vnum is not None else k
+    T.def_order = def_order
+    if deform is not None:
+        d = _f64(deform)
+        T._keep = d
+        T.deform = _p(d)
+    return T
+
+
+def ref_trafo(dim):
+    vt = np.zeros((dim + 1, dim))
+    for i in range(dim):
+        vt[i, i] = 1.0
+    return make_trafo(vt)
+
+
+def select_rule(dim, order):
+    L = lib()
+    n = L.xo_rule_size(dim, order)
+    pts = np.zeros((n, 3)); wts = np.zeros(n)
+    L.xo_select_rule(dim, order, _p(pts), _p(wts))
+    return pts, wts
+
+
+def gauss_jacobi01(n, alpha):
+    x = np.zeros(n); w = np.zeros(n)
+    lib().xo_gauss_jacobi01(n, alpha, _p(x), _p(w))
+    return x, w
+
+
+def check_if_straight_cut(v, eps=0.0):
+    v = _f64(v)
+    return lib().xo_check_if_straight_cut(_p(v), C.c_int(len(v)), C.c_double(eps))
+
+
+def straight_cut_rule(T, lsetvals, dt, order, cap=20000):
+    v = _f64(lsetvals)
+    pts = np.zeros((cap, 3)); wts = np.zeros(cap)
+    std = C.c_int(0)
+    n = lib().xo_straight_cut_rule(C.byref(T), _p(v), dt, order, _p(pts), _p(wts), cap, C.byref(std))
+    if n < 0:
+        raise RuntimeError(f"oracle error {n}")
+    return pts[:n].copy(), wts[:n].copy(), bool(std.value)
+
+
+def mlset_cut_rule(T, lsets, dts, order, cap=200000):
+    lsets = _f64(lsets)  # (dim+1) x M
+    M = lsets.shape[1]
+    dts = np.ascontiguousarray(np.atleast_2d(dts), dtype=np.int32)
+    pts = np.zeros((cap, 3)); wts = np.zeros(cap)
+    n = lib().xo_mlset_cut_rule(C.byref(T), _p(lsets), M, _p(dts, C.c_int), dts.shape[0], order,
+                                _p(pts), _p(wts), cap)
+    if n < 0:
+        raise RuntimeError(f"oracle error {n}")
+    return pts[:n].copy(), wts[:n].copy()
+
+
+def spacetime_cut_rule(T, lset_st, time_fe_order, dt, order_time, order_space, cap=200000):
+    l = _f64(lset_st)
+    pts = np.zeros((cap, 3)); tv = np.zeros(cap); wts = np.zeros(cap)
+    n = lib().xo_spacetime_cut_rule(C.byref(T), _p(l), time_fe_order, dt, order_time, order_space,
+                                    _p(pts), _p(tv), _p(wts), cap)
+    if n < 0:
+        raise RuntimeError(f"oracle error {n}")
+    return pts[:n].copy(), tv[:n].copy(), wts[:n].copy()
+
+
+def cutinfo_update(dim, el_vtx, phi):
+    el_vtx = _i32(el_vtx); phi = _f64(phi)
+    ne = el_vtx.shape[0]
+    nb = (ne + 7) // 8
+    bn = np.zeros(nb, np.uint8); bp = np.zeros(nb, np.uint8); bi = np.zeros(nb, np.uint8)
+    cr = np.zeros(ne)
+    err_el = C.c_int64(-1)
+    err = lib().xo_cutinfo_update(dim, C.c_int64(ne), _p(el_vtx, C.c_int32), _p(phi), _p(bn, C.c_uint8),
+                                  _p(bp, C.c_uint8), _p(bi, C.c_uint8), _p(cr), C.byref(err_el))
+    return bn, bp, bi, cr, err, err_el.value
+
+
+def ml_elements_of_type(dim, el_vtx, phis, dts):
+    el_vtx = _i32(el_vtx); phis = _f64(phis)
+    dts = np.ascontiguousarray(np.atleast_2d(dts), dtype=np.int32)
+    ne = el_vtx.shape[0]
+    bits = np.zeros((ne + 7) // 8, np.uint8)
+    lib().xo_ml_elements_of_type(dim, C.c_int64(ne), _p(el_vtx, C.c_int32), _p(phis), C.c_int64(phis.shape[1]),
+                                 phis.shape[0], _p(dts, C.c_int), dts.shape[0], _p(bits, C.c_uint8))
+    return bits
+
+
+def ml_elements_with_contribution(dim, el_vtx, vtx_xyz, phis, dts):
+    el_vtx = _i32(el_vtx); phis = _f64(phis); vtx_xyz = _f64(vtx_xyz)
+    dts = np.ascontiguousarray(np.atleast_2d(dts), dtype=np.int32)
+    ne = el_vtx.shape[0]
+    bits = np.zeros((ne + 7) // 8, np.uint8)
+    err = lib().xo_ml_elements_with_contribution(dim, C.c_int64(ne), _p(el_vtx, C.c_int32), _p(vtx_xyz), _p(phis),
+                                                 C.c_int64(phis.shape[1]), phis.shape[0], _p(dts, C.c_int),
+                                                 dts.shape[0], _p(bits, C.c_uint8))
+    if err:
+        raise RuntimeError(f"oracle error {err}")
+    return bits
+
+
+def facets_with_neighbor_types(facet_els, a, b, bnd_val_a=True, bnd_val_b=True, use_and=True):
+    fe = _i32(facet_els)
+    nf = fe.shape[0]
+    out = np.zeros((nf + 7) // 8, np.uint8)
+    lib().xo_facets_with_neighbor_types(C.c_int64(nf), _p(fe, C.c_int32), _p(a, C.c_uint8), _p(b, C.c_uint8),
+                                        int(bnd_val_a), int(bnd_val_b), int(use_and), _p(out, C.c_uint8))
+    return out
+
+
+def elements_with_neighbor_facets(facet_els, facets, ne):
+    fe = _i32(facet_els)
+    out = np.zeros((ne + 7) // 8, np.uint8)
+    lib().xo_elements_with_neighbor_facets(C.c_int64(fe.shape[0]), _p(fe, C.c_int32), _p(facets, C.c_uint8),
+                                           C.c_int64(ne), _p(out, C.c_uint8))
+    return out
+
+
+def dofs_of_elements(el_dofs, elems, ndof):
+    ed = _i32(el_dofs)
+    out = np.zeros((ndof + 7) // 8, np.uint8)
+    lib().xo_dofs_of_elements(C.c_int64(ed.shape[0]), ed.shape[1], _p(ed, C.c_int32), _p(elems, C.c_uint8),
+                              C.c_int64(ndof), _p(out, C.c_uint8))
+    return out
+
+
+def h1_ndof(dim, order):
+    return lib().xo_h1_ndof(dim, order)
+
+
+def h1_shapes(dim, order, vnum, xhat):
+    nd = h1_ndof(dim, order)
+    sh = np.zeros(nd); dsh = np.zeros((nd, dim))
+    vn = np.ascontiguousarray(vnum, dtype=np.int32)
+    x = np.zeros(3); x[:len(xhat)] = xhat
+    lib().xo_h1_shapes(dim, order, _p(vn, C.c_int), _p(x), _p(sh), _p(dsh))
+    return sh, dsh
+
+
+def terms_array(terms):
+    arr = (Term * len(terms))()
+    for i, (ou, ot, c, hp) in enumerate(terms):
+        arr[i].op_trial = ou; arr[i].op_test = ot; arr[i].coef = c; arr[i].hpow = hp
+    return arr
+
+
+def cut_elmat(T, fe_order, lsetvals, dt, order, terms):
+    nd = h1_ndof(T.dim, fe_order)
+    m = np.zeros((nd, nd))
+    v = _f64(lsetvals)
+    ta = terms_array(terms)
+    n = lib().xo_cut_elmat(C.byref(T), fe_order, _p(v), dt, order, ta, len(terms), _p(m))
+    if n < 0:
+        raise RuntimeError(f"oracle error {n}")
+    return m, n
+
+
+def facet_patch_elmat(T1, T2, fe_order, order, coef, hpow):
+    nd = h1_ndof(T1.dim, fe_order)
+    m = np.zeros((2 * nd, 2 * nd))
+    nfail = lib().xo_facet_patch_elmat(C.byref(T1), C.byref(T2), fe_order, order, C.c_double(coef), hpow, _p(m))
+    return m, nfail
+
+
+def graph(ndof, table):
+    t = _i32(table)
+    nrows, width = t.shape
+    rowptr = np.zeros(ndof + 1, np.int64)
+    nnz = lib().xo_graph(C.c_int64(ndof), C.c_int64(nrows), width, _p(t, C.c_int32), _p(rowptr, C.c_int64), None)
+    col = np.zeros(nnz, np.int32)
+    lib().xo_graph(C.c_int64(ndof), C.c_int64(nrows), width, _p(t, C.c_int32), _p(rowptr, C.c_int64), _p(col, C.c_int32))
+    return rowptr, col
+
+
+def scatter(ndof, table, mats, rowptr, col, vals=None):
+    t = _i32(table); m = _f64(mats)
+    if vals is None:
+        vals = np.zeros(len(col))
+    lib().xo_scatter(C.c_int64(ndof), C.c_int64(t.shape[0]), t.shape[1], _p(t, C.c_int32), _p(m),
+                     _p(rowptr, C.c_int64), _p(col, C.c_int32), _p(vals))
+    return vals
+
+
+def batch_cut_rules(dim, elems, el_vtx, vtx_xyz, phi, dt, order):
+    el_vtx = _i32(el_vtx); vtx_xyz = _f64(vtx_xyz); phi = _f64(phi)
+    el = None if elems is None else _i32(elems)
+    n = el_vtx.shape[0] if el is None else len(el)
+    off = np.zeros(n + 1, np.int64)
+    tot = lib().xo_batch_cut_rules(dim, C.c_int64(n), _p(el, C.c_int32), _p(el_vtx, C.c_int32), _p(vtx_xyz), _p(phi),
+                                   dt, order, _p(off, C.c_int64), None, None)
+    if tot < 0:
+        raise RuntimeError(f"oracle error {tot}")
+    pts = np.zeros((tot, 3)); wts = np.zeros(tot)
+    lib().xo_batch_cut_rules(dim, C.c_int64(n), _p(el, C.c_int32), _p(el_vtx, C.c_int32), _p(vtx_xyz), _p(phi),
+                             dt, order, _p(off, C.c_int64), _p(pts), _p(wts))
+    return off, pts, wts
+
+
+def batch_cut_elmats(dim, fe_order, elems, el_vtx, vtx_xyz, phi, dt, order, terms, def_order=0, deform=None):
+    el_vtx = _i32(el_vtx); vtx_xyz = _f64(vtx_xyz); phi = _f64(phi)
+    el = None if elems is None else _i32(elems)
+    n = el_vtx.shape[0] if el is None else len(el)
+    nd = h1_ndof(dim, fe_order)
+    mats = np.zeros((n, nd, nd))
+    ta = terms_array(terms)
+    d = None if deform is None else _f64(deform)
+    err = lib().xo_batch_cut_elmats(dim, fe_order, C.c_int64(n), _p(el, C.c_int32), _p(el_vtx, C.c_int32), _p(vtx_xyz),
+                                    _p(phi), dt, order, ta, len(terms), def_order, _p(d), _p(mats))
+    if err:
+        raise RuntimeError(f"oracle error {err}")
+    return mats
+
+
+def batch_facet_patch(dim, fe_order, facets, facet_els, el_vtx, vtx_xyz, order, coef, hpow, def_order=0, deform=None):
+    el_vtx = _i32(el_vtx); vtx_xyz = _f64(vtx_xyz); fe = _i32(facet_els)
+    fl = None if facets is None else _i32(facets)
+    n = fe.shape[0] if fl is None else len(fl)
+    nd = h1_ndof(dim, fe_order)
+    mats = np.zeros((n, 2 * nd, 2 * nd))
+    d = None if deform is None else _f64(deform)
+    nfail = lib().xo_batch_facet_patch(dim, fe_order, C.c_int64(n), _p(fl, C.c_int32), _p(fe, C.c_int32),
+                                       _p(el_vtx, C.c_int32), _p(vtx_xyz), order, C.c_double(coef), hpow,
+                                       def_order, _p(d), _p(mats))
+    return mats, nfail
+
+
+def integrate_monomial(dim, el_vtx, vtx_xyz, phi, dt, order, expo):
+    el_vtx = _i32(el_vtx); vtx_xyz = _f64(vtx_xyz); phi = _f64(phi)
+    ex = np.ascontiguousarray(expo, dtype=np.int32)
+    err = C.c_int(0)
+    v = lib().xo_integrate_monomial(dim, C.c_int64(el_vtx.shape[0]), _p(el_vtx, C.c_int32), _p(vtx_xyz), _p(phi),
+                                    dt, order, _p(ex, C.c_int), C.byref(err))
+    if err.value:
+        raise RuntimeError(f"oracle error {err.value}")
+    return v
