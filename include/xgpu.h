@@ -1,0 +1,189 @@
+/* xgpu.h — C ABI of libxgpu.so: the B200 (sm_100a) cut-element assembly path behind ngsxfem's
+ * CutInfo / dCut / SymbolicCutBFI / dFacetPatch / RestrictedBilinearForm.Assemble surface.
+ *
+ * Conventions
+ *   - plain C, no torch / NGSolve types.  Every array pointer is a DEVICE pointer unless the
+ *     parameter name ends in `_host`.  All arrays are caller owned; the library allocates only
+ *     its private scratch (inside xgpu_ctx / xgpu_plan).
+ *   - every call returns 0 (XGPU_OK) or a negative error code and never throws; the message of
+ *     the last error is available through xgpu_last_error().  Geometry errors that the
+ *     reference reports by throwing per element (straightcutrule.cpp:45-49,144-149,190-194)
+ *     are recorded on the device and fetched with xgpu_get_status() (first failing element).
+ *   - work is enqueued on the context's stream (xgpu_set_stream, a cudaStream_t); calls whose
+ *     result is a host scalar (`*_host` out-parameters) synchronise that stream.
+ *   - reference element conventions are those pinned by cutint/straightcutrule.cpp:506-514,
+ *     straightcutrule.hpp:56-60: TET v0=(1,0,0) v1=(0,1,0) v2=(0,0,1) v3=(0,0,0) etc.
+ *   - bitsets are arrays of uint32 words, bit i = word i>>5, bit i&31 — byte-identical to
+ *     NGSolve's BitArray (bit i = byte i>>3, bit i&7) on little-endian hosts.
+ *
+ * Each entry point cites the reference interface it replaces (paths relative to ngsxfem).
+ */
+#ifndef XGPU_H
+#define XGPU_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* utils/ngsxstd.hpp:16-19 */
+enum { XGPU_NEG = 0, XGPU_POS = 1, XGPU_IF = 2 };
+
+enum {
+  XGPU_OK = 0,
+  XGPU_ERR_CUDA = -1,
+  XGPU_ERR_ARG = -2,
+  XGPU_ERR_UNSUPPORTED = -3,   /* the reference's legacy paths (subdivlvl>0, quads/hexes, ...) */
+  XGPU_ERR_GEOM_PLAIN = -11,   /* straightcutrule.cpp:45-49 (zero vertex value on a cut element) */
+  XGPU_ERR_GEOM_SCUT = -12,    /* straightcutrule.cpp:144-149 */
+  XGPU_ERR_GEOM_NOTIMPL = -13, /* straightcutrule.cpp:190-194 */
+  XGPU_ERR_CAPACITY = -14
+};
+
+typedef struct xgpu_ctx xgpu_ctx;
+typedef struct xgpu_plan xgpu_plan;
+
+/* ---------------------------------------------------------------- context */
+int xgpu_create(int device, xgpu_ctx** ctx_out);
+void xgpu_destroy(xgpu_ctx* ctx);
+int xgpu_set_stream(xgpu_ctx* ctx, void* cuda_stream);
+int xgpu_sync(xgpu_ctx* ctx);
+const char* xgpu_last_error(xgpu_ctx* ctx);
+/* per-element geometry error recorded by kernels since the last xgpu_clear_status; syncs. */
+int xgpu_get_status(xgpu_ctx* ctx, int* code_host, int64_t* elem_host);
+int xgpu_clear_status(xgpu_ctx* ctx);
+/* number of kernels this context has launched so far (bench: gpu_launches) */
+int64_t xgpu_launch_count(xgpu_ctx* ctx);
+const char* xgpu_version(void);
+
+/* ---------------------------------------------------------------- tables (host side)
+ * NGSolve's SelectIntegrationRule / H1HighOrderFE are third party; defaults restate their
+ * published construction, xgpu_set_rule injects the exact tables when an adapter has them
+ * (call sites: straightcutrule.cpp:87-90,673; symboliccutbfi.cpp:2009-2012). */
+int xgpu_rule_size(xgpu_ctx* ctx, int dim, int order);
+int xgpu_get_rule(xgpu_ctx* ctx, int dim, int order, double* pts_host /* n x 3 */, double* wts_host);
+int xgpu_set_rule(xgpu_ctx* ctx, int dim, int order, int n, const double* pts_host, const double* wts_host);
+int xgpu_h1_ndof(int dim, int order);
+/* host evaluation of the device basis (tests / adapters): shape[nd], dshape[nd x dim] */
+int xgpu_h1_shapes_host(int dim, int order, const int32_t* vnum_host, const double* xhat_host,
+                        double* shape_host, double* dshape_host);
+
+/* ---------------------------------------------------------------- (a) CutInfo
+ * CutInformation::Update, VOL/BND loop (xfem/cutinfo.cpp:61-133): classification of simplices
+ * of dimension `dim` from nodal P1 level-set values.  cut_ratio may be NULL. */
+int xgpu_classify(xgpu_ctx* ctx, int dim, int64_t ne, const int32_t* el_vtx, const double* phi,
+                  uint32_t* bits_neg, uint32_t* bits_pos, uint32_t* bits_if, double* cut_ratio);
+/* BitArray algebra used by cutinfo.cpp:127-132 (UNCUT/HASNEG/HASPOS) and by user code.
+ * op: 0 OR, 1 AND, 2 ANDNOT (a & ~b), 3 NOT a, 4 COPY a, 5 CLEAR, 6 SET (tail bits stay 0) */
+int xgpu_bitset_op(xgpu_ctx* ctx, int op, const uint32_t* a, const uint32_t* b, uint32_t* out, int64_t nbits);
+int xgpu_bitset_count(xgpu_ctx* ctx, const uint32_t* bits, int64_t nbits, int64_t* count_host);
+/* ascending list of set bits; list must hold xgpu_bitset_count entries */
+int xgpu_bitset_to_list(xgpu_ctx* ctx, const uint32_t* bits, int64_t nbits, int32_t* list);
+/* CutInformation::GetElementsWithThresholdContribution (cutinfo.cpp:263-284) */
+int xgpu_threshold_elements(xgpu_ctx* ctx, int64_t ne, const double* cut_ratio, int dt, double threshold,
+                            uint32_t* bits_out);
+/* MultiLevelsetCutInformation::UpdateElementsOfDomainType (cutinfo.cpp:356-398).
+ * phis: M x nv (row j = level set j); dts_host: ntuples x M */
+int xgpu_classify_ml(xgpu_ctx* ctx, int dim, int64_t ne, const int32_t* el_vtx, const double* phis,
+                     int64_t nv, int M, const int* dts_host, int ntuples, uint32_t* bits_out);
+/* GetFacetsWithNeighborTypes (cutinfo.cpp:476-538); facet_els: nf x 2, -1 = boundary */
+int xgpu_facets_with_neighbor_types(xgpu_ctx* ctx, int64_t nf, const int32_t* facet_els,
+                                    const uint32_t* a, const uint32_t* b, int bnd_val_a, int bnd_val_b,
+                                    int use_and, uint32_t* bits_out);
+/* GetElementsWithNeighborFacets (cutinfo.cpp:540-566) */
+int xgpu_elements_with_neighbor_facets(xgpu_ctx* ctx, int64_t nf, const int32_t* facet_els,
+                                       const uint32_t* facet_bits, int64_t ne, uint32_t* bits_out);
+/* GetDofsOfElements (cutinfo.cpp:599-622); el_dofs: ne x nd, -1 = no dof */
+int xgpu_dofs_of_elements(xgpu_ctx* ctx, int64_t ne, int nd, const int32_t* el_dofs,
+                          const uint32_t* el_bits, int64_t ndof, uint32_t* bits_out);
+/* RestrictedFESpace / CompressedFESpace numbering (utils/restrictedfespace.cpp:23-51):
+ * map[d] = rank of d among the set bits, -1 if unset; *nactive_host = number of set bits */
+int xgpu_bitset_rank(xgpu_ctx* ctx, const uint32_t* bits, int64_t nbits, int32_t* map, int64_t* nactive_host);
+/* out[i][k] = map ? map[table[list[i]][k]] : table[list[i]][k]   (list==NULL: identity) */
+int xgpu_gather_rows(xgpu_ctx* ctx, int64_t n, const int32_t* list, int width, const int32_t* table,
+                     const int32_t* map, int32_t* out);
+
+/* ---------------------------------------------------------------- (b) cut quadrature
+ * StraightCutIntegrationRule (cutint/straightcutrule.cpp:582-677) for a list of simplices
+ * (elems==NULL: 0..n-1).  Points are reference coordinates of the background element
+ * (3 doubles per point, unused coordinates 0); weights follow the reference convention
+ * (w*|det F| is the physical measure, also for dt=IF).  Two calls: _count fills offsets[n+1]
+ * (device, int64) and returns the total; _fill writes pts[total x 3], wts[total]. */
+int xgpu_cutquad_count(xgpu_ctx* ctx, int dim, int64_t n, const int32_t* elems, const int32_t* el_vtx,
+                       const double* phi, int dt, int order, int64_t* offsets, int64_t* total_host);
+int xgpu_cutquad_fill(xgpu_ctx* ctx, int dim, int64_t n, const int32_t* elems, const int32_t* el_vtx,
+                      const double* vtx_xyz, const double* phi, int dt, int order,
+                      const int64_t* offsets, double* pts, double* wts);
+/* CreateMultiLevelsetCutIntegrationRule (cutint/mlsetintegration.cpp:6-186,
+ * straightcutrule.cpp:679-812): phis M x nv, dts_host ntuples x M */
+int xgpu_cutquad_ml_count(xgpu_ctx* ctx, int dim, int64_t n, const int32_t* elems, const int32_t* el_vtx,
+                          const double* phis, int64_t nv, int M, const int* dts_host, int ntuples,
+                          int order, int64_t* offsets, int64_t* total_host);
+int xgpu_cutquad_ml_fill(xgpu_ctx* ctx, int dim, int64_t n, const int32_t* elems, const int32_t* el_vtx,
+                         const double* vtx_xyz, const double* phis, int64_t nv, int M,
+                         const int* dts_host, int ntuples, int order, const int64_t* offsets,
+                         double* pts, double* wts);
+/* SpaceTimeCutIntegrationRule (cutint/spacetimecutrule.cpp:104-244): phi_st is time-major,
+ * (time_fe_order+1) x nv nodal values; tvals receives the reference time of every point. */
+int xgpu_cutquad_st_count(xgpu_ctx* ctx, int dim, int64_t n, const int32_t* elems, const int32_t* el_vtx,
+                          const double* phi_st, int64_t nv, int time_fe_order, int dt, int order_time,
+                          int order_space, int64_t* offsets, int64_t* total_host);
+int xgpu_cutquad_st_fill(xgpu_ctx* ctx, int dim, int64_t n, const int32_t* elems, const int32_t* el_vtx,
+                         const double* vtx_xyz, const double* phi_st, int64_t nv, int time_fe_order,
+                         int dt, int order_time, int order_space, const int64_t* offsets,
+                         double* pts, double* tvals, double* wts);
+/* Integrate (cutint/cutintegral.cpp:126-212) of a monomial prod x_i^expo[i] over a rule batch:
+ * sum_q w_q |det F| f(x_q).  result_host receives the sum (fixed-order reduction). */
+int xgpu_integrate_monomial(xgpu_ctx* ctx, int dim, int64_t n, const int32_t* elems, const int32_t* el_vtx,
+                            const double* vtx_xyz, const int64_t* offsets, const double* pts,
+                            const double* wts, const int* expo_host, double* result_host);
+
+/* ---------------------------------------------------------------- (c) element matrices
+ * SymbolicCutBilinearFormIntegrator::T_CalcElementMatrixAdd (xfem/symboliccutbfi.cpp:76-486)
+ * for a closed menu of integrands: sum of terms  coef * h^hpow * op_test(v) * op_trial(u),
+ * ops: 0 = ID, 1 = GRAD (GRADxGRAD is the dot product), 2 = DN = grad . n with
+ * n = grad(lset_p1)/|grad(lset_p1)|; h = |det F|^(1/dim).  mats: n x nd x nd, row-major,
+ * rows = test, cols = trial.  accumulate!=0 ADDS into mats (CalcElementMatrixAdd).  slots (nullable):
+ * matrix i is written to mats[slots[i]] instead of mats[i] (several integrators, one batch). */
+typedef struct { int op_trial, op_test; double coef; int hpow; } xgpu_term;
+/* per-element rules (cut elements): offsets/pts/wts from xgpu_cutquad_* */
+int xgpu_elmat_rule(xgpu_ctx* ctx, int dim, int fe_order, int64_t n, const int32_t* elems,
+                    const int32_t* el_vtx, const double* vtx_xyz, const double* phi,
+                    const int64_t* offsets, const double* pts, const double* wts,
+                    const xgpu_term* terms_host, int nterms, int accumulate, const int32_t* slots,
+                    double* mats);
+/* uncut elements: the shared standard rule of `order` on every listed element */
+int xgpu_elmat_std(xgpu_ctx* ctx, int dim, int fe_order, int64_t n, const int32_t* elems,
+                   const int32_t* el_vtx, const double* vtx_xyz, const double* phi, int order,
+                   const xgpu_term* terms_host, int nterms, int accumulate, const int32_t* slots,
+                   double* mats);
+
+/* ---------------------------------------------------------------- (d) ghost penalty
+ * SymbolicFacetPatchBilinearFormIntegrator::T_CalcFacetMatrix (xfem/symboliccutbfi.cpp:
+ * 1982-2377) for coef*h^hpow*(u-u.Other())*(v-v.Other()); order<0 -> 2*fe_order (:2004-2012).
+ * mats: n x (2nd) x (2nd), layout [el1 dofs ; el2 dofs] (:2207-2230). */
+int xgpu_facetpatch(xgpu_ctx* ctx, int dim, int fe_order, int64_t n, const int32_t* facets,
+                    const int32_t* facet_els, const int32_t* el_vtx, const double* vtx_xyz,
+                    int order, double coef, int hpow, double* mats);
+
+/* ---------------------------------------------------------------- (e) sparse assembly
+ * RestrictedBilinearForm::GetGraph (utils/restrictedblf.cpp:142-163) + NGSolve MatrixGraph /
+ * SparseMatrix::AddElementMatrix.  A batch is a table of dof rows (nrows x width, -1 = unused)
+ * with one width x width matrix per row.  The pattern is the union of the row cliques of all
+ * batches, columns ascending, explicit zeros kept; values are summed in a fixed order
+ * (batch, then row index) so results are bit-reproducible run to run. */
+typedef struct { const int32_t* table; const double* mats; int64_t nrows; int width; } xgpu_batch;
+int xgpu_csr_plan(xgpu_ctx* ctx, int64_t ndof, const xgpu_batch* batches_host, int nbatches,
+                  xgpu_plan** plan_out, int64_t* nnz_host);
+int xgpu_csr_pattern(xgpu_ctx* ctx, xgpu_plan* plan, int64_t* rowptr, int32_t* colidx);
+int xgpu_csr_scatter(xgpu_ctx* ctx, xgpu_plan* plan, const xgpu_batch* batches_host, int nbatches,
+                     const int64_t* rowptr, const int32_t* colidx, double* vals);
+void xgpu_plan_destroy(xgpu_plan* plan);
+/* y = A x for checks (CSR SpMV, one warp per row) */
+int xgpu_csr_spmv(xgpu_ctx* ctx, int64_t nrows, const int64_t* rowptr, const int32_t* colidx,
+                  const double* vals, const double* x, double* y);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,179 @@
+"""ctypes loader of libxgpu.so (the C ABI declared in include/xgpu.h).
+
+There is NO fallback: if the CUDA library is missing or a call fails, an exception is raised.
+torch is used only as the device allocator / stream provider; tensors are passed as raw pointers.
+"""
+import ctypes as C
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libxgpu.so")
+
+c_i32p = C.POINTER(C.c_int32)
+c_u32p = C.POINTER(C.c_uint32)
+c_i64p = C.POINTER(C.c_int64)
+c_f64p = C.POINTER(C.c_double)
+c_intp = C.POINTER(C.c_int)
+VP = C.c_void_p
+
+
+class XgpuError(RuntimeError):
+    """raised where the reference raises ngcore::Exception / NgException"""
+
+
+class Term(C.Structure):
+    _fields_ = [("op_trial", C.c_int), ("op_test", C.c_int), ("coef", C.c_double), ("hpow", C.c_int)]
+
+
+class Batch(C.Structure):
+    _fields_ = [("table", VP), ("mats", VP), ("nrows", C.c_int64), ("width", C.c_int)]
+
+
+_SIGS = {
+    "xgpu_create": (C.c_int, [C.c_int, C.POINTER(VP)]),
+    "xgpu_destroy": (None, [VP]),
+    "xgpu_set_stream": (C.c_int, [VP, VP]),
+    "xgpu_sync": (C.c_int, [VP]),
+    "xgpu_last_error": (C.c_char_p, [VP]),
+    "xgpu_get_status": (C.c_int, [VP, c_intp, c_i64p]),
+    "xgpu_clear_status": (C.c_int, [VP]),
+    "xgpu_launch_count": (C.c_int64, [VP]),
+    "xgpu_version": (C.c_char_p, []),
+    "xgpu_rule_size": (C.c_int, [VP, C.c_int, C.c_int]),
+    "xgpu_get_rule": (C.c_int, [VP, C.c_int, C.c_int, c_f64p, c_f64p]),
+    "xgpu_set_rule": (C.c_int, [VP, C.c_int, C.c_int, C.c_int, c_f64p, c_f64p]),
+    "xgpu_h1_ndof": (C.c_int, [C.c_int, C.c_int]),
+    "xgpu_h1_shapes_host": (C.c_int, [C.c_int, C.c_int, c_i32p, c_f64p, c_f64p, c_f64p]),
+    "xgpu_classify": (C.c_int, [VP, C.c_int, C.c_int64, VP, VP, VP, VP, VP, VP]),
+    "xgpu_bitset_op": (C.c_int, [VP, C.c_int, VP, VP, VP, C.c_int64]),
+    "xgpu_bitset_count": (C.c_int, [VP, VP, C.c_int64, c_i64p]),
+    "xgpu_bitset_to_list": (C.c_int, [VP, VP, C.c_int64, VP]),
+    "xgpu_threshold_elements": (C.c_int, [VP, C.c_int64, VP, C.c_int, C.c_double, VP]),
+    "xgpu_classify_ml": (C.c_int, [VP, C.c_int, C.c_int64, VP, VP, C.c_int64, C.c_int, c_intp, C.c_int, VP]),
+    "xgpu_facets_with_neighbor_types": (C.c_int, [VP, C.c_int64, VP, VP, VP, C.c_int, C.c_int, C.c_int, VP]),
+    "xgpu_elements_with_neighbor_facets": (C.c_int, [VP, C.c_int64, VP, VP, C.c_int64, VP]),
+    "xgpu_dofs_of_elements": (C.c_int, [VP, C.c_int64, C.c_int, VP, VP, C.c_int64, VP]),
+    "xgpu_bitset_rank": (C.c_int, [VP, VP, C.c_int64, VP, c_i64p]),
+    "xgpu_gather_rows": (C.c_int, [VP, C.c_int64, VP, C.c_int, VP, VP, VP]),
+    "xgpu_cutquad_count": (C.c_int, [VP, C.c_int, C.c_int64, VP, VP, VP, C.c_int, C.c_int, VP, c_i64p]),
+    "xgpu_cutquad_fill": (C.c_int, [VP, C.c_int, C.c_int64, VP, VP, VP, VP, C.c_int, C.c_int, VP, VP, VP]),
+    "xgpu_cutquad_ml_count": (C.c_int, [VP, C.c_int, C.c_int64, VP, VP, VP, C.c_int64, C.c_int, c_intp, C.c_int,
+                                        C.c_int, VP, c_i64p]),
+    "xgpu_cutquad_ml_fill": (C.c_int, [VP, C.c_int, C.c_int64, VP, VP, VP, VP, C.c_int64, C.c_int, c_intp, C.c_int,
+                                       C.c_int, VP, VP, VP]),
+    "xgpu_cutquad_st_count": (C.c_int, [VP, C.c_int, C.c_int64, VP, VP, VP, C.c_int64, C.c_int, C.c_int, C.c_int,
+                                        C.c_int, VP, c_i64p]),
+    "xgpu_cutquad_st_fill": (C.c_int, [VP, C.c_int, C.c_int64, VP, VP, VP, VP, C.c_int64, C.c_int, C.c_int, C.c_int,
+                                       C.c_int, VP, VP, VP, VP]),
+    "xgpu_integrate_monomial": (C.c_int, [VP, C.c_int, C.c_int64, VP, VP, VP, VP, VP, VP, c_intp, c_f64p]),
+    "xgpu_elmat_rule": (C.c_int, [VP, C.c_int, C.c_int, C.c_int64, VP, VP, VP, VP, VP, VP, VP, C.POINTER(Term),
+                                  C.c_int, C.c_int, VP, VP]),
+    "xgpu_elmat_std": (C.c_int, [VP, C.c_int, C.c_int, C.c_int64, VP, VP, VP, VP, C.c_int, C.POINTER(Term),
+                                 C.c_int, C.c_int, VP, VP]),
+    "xgpu_facetpatch": (C.c_int, [VP, C.c_int, C.c_int, C.c_int64, VP, VP, VP, VP, C.c_int, C.c_double, C.c_int, VP]),
+    "xgpu_csr_plan": (C.c_int, [VP, C.c_int64, C.POINTER(Batch), C.c_int, C.POINTER(VP), c_i64p]),
+    "xgpu_csr_pattern": (C.c_int, [VP, VP, VP, VP]),
+    "xgpu_csr_scatter": (C.c_int, [VP, VP, C.POINTER(Batch), C.c_int, VP, VP, VP]),
+    "xgpu_plan_destroy": (None, [VP]),
+    "xgpu_csr_spmv": (C.c_int, [VP, C.c_int64, VP, VP, VP, VP, VP]),
+}
+
+_LIB = None
+
+
+def exported_symbols():
+    return sorted(_SIGS)
+
+
+def load():
+    """dlopen libxgpu.so; raises if it has not been built (python -m ngsxfem_b200.build)."""
+    global _LIB
+    if _LIB is None:
+        if not os.path.exists(LIB_PATH):
+            raise XgpuError(f"{LIB_PATH} not found: build it with `python -m ngsxfem_b200.build` "
+                            "(there is no CPU fallback)")
+        lib = C.CDLL(LIB_PATH)
+        for name, (res, args) in _SIGS.items():
+            fn = getattr(lib, name)
+            fn.restype = res
+            fn.argtypes = args
+        _LIB = lib
+    return _LIB
+
+
+def ptr(t):
+    """device (or host) pointer of a tensor, None -> NULL"""
+    if t is None:
+        return None
+    assert t.is_contiguous()
+    return t.data_ptr()
+
+
+class Ctx:
+    """one xgpu_ctx per (device, stream)"""
+
+    def __init__(self, device=None):
+        if not torch.cuda.is_available():
+            raise XgpuError("no CUDA device: the cut-element assembly path has no CPU fallback")
+        self.lib = load()
+        if device is None:
+            device = torch.cuda.current_device()
+        self.device = torch.device("cuda", device if isinstance(device, int) else torch.device(device).index or 0)
+        h = VP()
+        rc = self.lib.xgpu_create(self.device.index, C.byref(h))
+        if rc != 0:
+            raise XgpuError(f"xgpu_create failed ({rc})")
+        self.h = h
+        self.use_current_stream()
+
+    def use_current_stream(self):
+        s = torch.cuda.current_stream(self.device).cuda_stream
+        self.check(self.lib.xgpu_set_stream(self.h, VP(s)))
+
+    def check(self, rc):
+        if rc != 0:
+            msg = self.lib.xgpu_last_error(self.h)
+            raise XgpuError(f"xgpu error {rc}: {msg.decode() if msg else ''}")
+
+    def status(self):
+        code = C.c_int(0)
+        el = C.c_int64(-1)
+        self.check(self.lib.xgpu_get_status(self.h, C.byref(code), C.byref(el)))
+        return code.value, el.value
+
+    def raise_on_geometry_error(self):
+        code, el = self.status()
+        if code != 0:
+            self.check(self.lib.xgpu_clear_status(self.h))
+            msgs = {-11: "You tried to cut a simplex with a plain geometry lset function",
+                    -12: "Bad length of s_cut!",
+                    -13: "Cutting this part of a tetraeder is not implemented yet!"}
+            raise XgpuError(f"{msgs.get(code, 'geometry error')} (element {el}, code {code})")
+
+    @property
+    def launches(self):
+        return self.lib.xgpu_launch_count(self.h)
+
+    def __del__(self):
+        try:
+            if getattr(self, "h", None):
+                self.lib.xgpu_destroy(self.h)
+                self.h = None
+        except Exception:
+            pass
+
+
+_CTX = {}
+
+
+def default_ctx(device=None):
+    if device is None:
+        device = torch.cuda.current_device() if torch.cuda.is_available() else 0
+    idx = device if isinstance(device, int) else (torch.device(device).index or 0)
+    if idx not in _CTX:
+        _CTX[idx] = Ctx(idx)
+    c = _CTX[idx]
+    c.use_current_stream()
+    return c

@@ -1,0 +1,87 @@
+// common.cuh — context, error handling, scratch arena, device-wide scan used by all kernels.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+#include <vector>
+#include <map>
+#include "../../include/xgpu.h"
+
+#define XGPU_NSM 148  // B200: 2 dies x 74 SMs
+
+struct xgpu_rule_host {
+  int n = 0;
+  std::vector<double> pts;  // n x 3
+  std::vector<double> wts;
+  double* d_pts = nullptr;  // device copies (n x 3, n)
+  double* d_wts = nullptr;
+};
+
+struct xgpu_ctx {
+  int device = 0;
+  cudaStream_t stream = 0;
+  std::string err;
+  int64_t launches = 0;
+  // device status: [0] = code, [1] = pad ; elem as unsigned long long min
+  int* d_status = nullptr;               // 2 ints
+  unsigned long long* d_status_elem = nullptr;
+  // grow-only scratch arena (slots by index so independent temporaries do not alias)
+  void* scratch[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  size_t scratch_bytes[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  int64_t* h_pinned = nullptr;  // 16 x int64 pinned staging for host scalars
+  std::map<std::pair<int, int>, xgpu_rule_host> rules;  // (dim, order) -> rule
+  std::map<int, void*> reftensors;                     // cached reference tensors (device)
+};
+
+inline int xgpu_fail(xgpu_ctx* ctx, int code, const char* msg)
+{
+  if (ctx) ctx->err = msg;
+  return code;
+}
+
+#define XGPU_CUDA(ctx, call)                                                          \
+  do {                                                                                \
+    cudaError_t e__ = (call);                                                         \
+    if (e__ != cudaSuccess) {                                                         \
+      char buf__[512];                                                                \
+      snprintf(buf__, sizeof(buf__), "%s:%d: %s", __FILE__, __LINE__, cudaGetErrorString(e__)); \
+      return xgpu_fail(ctx, XGPU_ERR_CUDA, buf__);                                    \
+    }                                                                                 \
+  } while (0)
+
+#define XGPU_LAUNCH_CHECK(ctx)        \
+  do {                                \
+    (ctx)->launches++;                \
+    XGPU_CUDA(ctx, cudaGetLastError()); \
+  } while (0)
+
+inline int xgpu_scratch(xgpu_ctx* ctx, int slot, size_t bytes, void** out)
+{
+  if (bytes > ctx->scratch_bytes[slot]) {
+    if (ctx->scratch[slot]) {
+      XGPU_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+      XGPU_CUDA(ctx, cudaFree(ctx->scratch[slot]));
+      ctx->scratch[slot] = nullptr; ctx->scratch_bytes[slot] = 0;
+    }
+    size_t want = bytes + bytes / 8 + 256;
+    XGPU_CUDA(ctx, cudaMalloc(&ctx->scratch[slot], want));
+    ctx->scratch_bytes[slot] = want;
+  }
+  *out = ctx->scratch[slot];
+  return XGPU_OK;
+}
+
+// record a per-element geometry error: keep the smallest failing element and its code
+__device__ __forceinline__ void xgpu_record_error(int* status, unsigned long long* status_elem, int code, long long elem)
+{
+  unsigned long long old = atomicMin(status_elem, (unsigned long long)elem);
+  if ((unsigned long long)elem <= old) atomicExch(status, code);
+}
+
+// ---- device-wide exclusive scan (int32 counts -> int64 offsets), out has n+1 entries ----
+int xgpu_exclusive_scan_i32(xgpu_ctx* ctx, const int32_t* in, int64_t n, int64_t* out);
+// the same with 32-bit output offsets (n+1 entries)
+int xgpu_exclusive_scan_i32_o32(xgpu_ctx* ctx, const int32_t* in, int64_t n, int32_t* out);
+
+const xgpu_rule_host* xgpu_rule_lookup(xgpu_ctx* ctx, int dim, int order);

@@ -1,0 +1,271 @@
+// cutquad.cu — StraightCutIntegrationRule on the GPU (cutint/straightcutrule.cpp:582-677).
+//
+//   k_cq_count<D>  one thread per listed element: #points from the sign pattern only
+//                  (1 / 2 / 3 sub-simplices, Decompose :131-196) -> device scan -> CSR-of-points.
+//   k_cq_fill<D>   one WARP per element: the decomposition (<= 4 cut points, <= 3 sub-simplices)
+//                  is computed redundantly per lane in registers/local memory, the reference rule
+//                  is staged in shared memory once per block, lanes stride over the
+//                  (sub-simplex, rule point) pairs so that the 32 B/point output is written
+//                  coalesced.  HBM bound: 16 B + 32 B (+ vertex coords for IF) in, 32 B/point out.
+//   k_integrate<D> sum_q w_q |det F| x^e over a rule batch (cutint/cutintegral.cpp:126-212),
+//                  fixed-order reductions (bit reproducible).
+#include "common.cuh"
+#include "cutgeom.cuh"
+
+namespace {
+
+inline unsigned nblk(int64_t n, int t) { return (unsigned)((n + t - 1) / t); }
+
+template <int D>
+__device__ __forceinline__ void load_el(const int32_t* __restrict__ el_vtx, const double* __restrict__ phi, int64_t el,
+                                        int* v, double* l)
+{
+#pragma unroll
+  for (int k = 0; k < D + 1; k++) { v[k] = __ldg(el_vtx + el * (D + 1) + k); l[k] = __ldg(phi + v[k]); }
+}
+
+template <int D>
+__global__ void __launch_bounds__(256) k_cq_count(int64_t n, const int32_t* __restrict__ elems,
+                                                  const int32_t* __restrict__ el_vtx, const double* __restrict__ phi,
+                                                  int dt, int np_vol, int np_sub, int32_t* __restrict__ counts)
+{
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int64_t el = elems ? (int64_t)elems[i] : i;
+  int v[D + 1]; double l[D + 1];
+  load_el<D>(el_vtx, phi, el, v, l);
+  const int dom = xg_check_cut(l, D + 1);
+  int cnt;
+  if (dom != XGPU_IF) cnt = (dom == dt) ? np_vol : 0;
+  else {
+    int nneg = 0;
+#pragma unroll
+    for (int k = 0; k < D + 1; k++) nneg += (l[k] < 0.0);
+    cnt = xg_nsub(D, nneg, dt) * np_sub;
+  }
+  counts[i] = cnt;
+}
+
+template <int D>
+__global__ void __launch_bounds__(128) k_cq_fill(int64_t n, const int32_t* __restrict__ elems,
+                                                 const int32_t* __restrict__ el_vtx, const double* __restrict__ vtx_xyz,
+                                                 const double* __restrict__ phi, int dt,
+                                                 const double* __restrict__ rv_p, const double* __restrict__ rv_w, int np_vol,
+                                                 const double* __restrict__ rs_p, const double* __restrict__ rs_w, int np_sub,
+                                                 const int64_t* __restrict__ offsets, double* __restrict__ pts,
+                                                 double* __restrict__ wts, int* status, unsigned long long* status_elem)
+{
+  extern __shared__ double smem[];  // sub rule: np_sub x 4 (xi0, xi1, xi2, w)
+  for (int t = threadIdx.x; t < np_sub; t += blockDim.x) {
+    smem[4 * t + 0] = rs_p[3 * t + 0]; smem[4 * t + 1] = rs_p[3 * t + 1]; smem[4 * t + 2] = rs_p[3 * t + 2];
+    smem[4 * t + 3] = rs_w[t];
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t i = warp0; i < n; i += nwarps) {
+    const int64_t el = elems ? (int64_t)elems[i] : i;
+    const int64_t off = offsets[i];
+    const int cnt = (int)(offsets[i + 1] - off);
+    if (cnt == 0) continue;
+    int v[D + 1]; double l[D + 1];
+    load_el<D>(el_vtx, phi, el, v, l);
+    const int dom = xg_check_cut(l, D + 1);
+    if (dom != XGPU_IF) {  // uncut, matching: the standard rule (:669-674)
+      for (int q = lane; q < cnt; q += 32) {
+        pts[3 * (off + q) + 0] = rv_p[3 * q + 0]; pts[3 * (off + q) + 1] = rv_p[3 * q + 1]; pts[3 * (off + q) + 2] = rv_p[3 * q + 2];
+        wts[off + q] = rv_w[q];
+      }
+      continue;
+    }
+    XgSimplex ref, sub[3];
+    xg_ref_simplex(D, ref);
+    const int ns = xg_decompose(ref, l, dt, sub);
+    if (ns < 0) {
+      if (lane == 0) xgpu_record_error(status, status_elem, ns, el);
+      for (int q = lane; q < cnt; q += 32) {
+        pts[3 * (off + q) + 0] = 0.0; pts[3 * (off + q) + 1] = 0.0; pts[3 * (off + q) + 2] = 0.0; wts[off + q] = 0.0;
+      }
+      continue;
+    }
+    double vol[3];
+    for (int s = 0; s < 3; s++) vol[s] = (s < ns) ? xg_volume(sub[s]) : 0.0;
+    double iffac = 1.0;
+    if (dt == XGPU_IF) {  // w <- w * ||F^{-T} n_ref||  (:558-578); affine F from the vertices
+      double vx[D + 1][3], F[D * D], Fi[D * D];
+#pragma unroll
+      for (int k = 0; k < D + 1; k++)
+#pragma unroll
+        for (int c = 0; c < 3; c++) vx[k][c] = (c < D) ? __ldg(vtx_xyz + (int64_t)v[k] * D + c) : 0.0;
+      xg_affine_jac<D>(vx, F);
+      xg_inv<D>(F, Fi);
+      iffac = xg_if_weight_factor<D>(Fi, l);
+    }
+    for (int idx = lane; idx < cnt; idx += 32) {
+      const int s = idx / np_sub, q = idx - s * np_sub;
+      double x[3];
+      const XgSimplex& S = (s == 0) ? sub[0] : ((s == 1) ? sub[1] : sub[2]);
+      xg_map_point(S, &smem[4 * q], x);
+      const double vs = (s == 0) ? vol[0] : ((s == 1) ? vol[1] : vol[2]);
+      pts[3 * (off + idx) + 0] = x[0]; pts[3 * (off + idx) + 1] = x[1]; pts[3 * (off + idx) + 2] = x[2];
+      wts[off + idx] = smem[4 * q + 3] * vs * iffac;
+    }
+  }
+}
+
+template <int D>
+__global__ void __launch_bounds__(128) k_integrate(int64_t n, const int32_t* __restrict__ elems,
+                                                   const int32_t* __restrict__ el_vtx, const double* __restrict__ vtx_xyz,
+                                                   const int64_t* __restrict__ offsets, const double* __restrict__ pts,
+                                                   const double* __restrict__ wts, int e0, int e1, int e2,
+                                                   double* __restrict__ elsum)
+{
+  const int lane = threadIdx.x & 31;
+  const int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (i >= n) return;
+  const int64_t el = elems ? (int64_t)elems[i] : i;
+  double vx[D + 1][3], F[D * D], Fi[D * D];
+#pragma unroll
+  for (int k = 0; k < D + 1; k++) {
+    const int v = __ldg(el_vtx + el * (D + 1) + k);
+#pragma unroll
+    for (int c = 0; c < 3; c++) vx[k][c] = (c < D) ? __ldg(vtx_xyz + (int64_t)v * D + c) : 0.0;
+  }
+  xg_affine_jac<D>(vx, F);
+  const double meas = fabs(xg_inv<D>(F, Fi));
+  const int ex[3] = {e0, e1, e2};
+  double s = 0.0;
+  for (int64_t q = offsets[i] + lane; q < offsets[i + 1]; q += 32) {
+    double lam[D + 1], sl = 1.0;
+#pragma unroll
+    for (int k = 0; k < D; k++) { lam[k] = pts[3 * q + k]; sl -= lam[k]; }
+    lam[D] = sl;
+    double f = 1.0;
+#pragma unroll
+    for (int c = 0; c < D; c++) {
+      double xc = 0.0;
+#pragma unroll
+      for (int k = 0; k < D + 1; k++) xc += lam[k] * vx[k][c];
+      for (int e = 0; e < ex[c]; e++) f *= xc;
+    }
+    s += wts[q] * meas * f;
+  }
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) s += __shfl_down_sync(0xffffffffu, s, d);
+  if (lane == 0) elsum[i] = s;
+}
+
+// fixed-order sum: each block reduces a contiguous tile with a shared-memory tree
+__global__ void __launch_bounds__(256) k_sum_tiles(const double* __restrict__ in, int64_t n, double* __restrict__ out)
+{
+  __shared__ double sm[256];
+  const int64_t tile = 256 * 16;
+  const int64_t base = (int64_t)blockIdx.x * tile;
+  double s = 0.0;
+  for (int k = 0; k < 16; k++) {
+    const int64_t i = base + (int64_t)k * 256 + threadIdx.x;
+    if (i < n) s += in[i];
+  }
+  sm[threadIdx.x] = s;
+  __syncthreads();
+  for (int d = 128; d > 0; d >>= 1) {
+    if ((int)threadIdx.x < d) sm[threadIdx.x] += sm[threadIdx.x + d];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) out[blockIdx.x] = sm[0];
+}
+
+}  // namespace
+
+int xgpu_sum_f64(xgpu_ctx* ctx, double* buf_a, int64_t n, double* buf_b, double* result_host)
+{
+  // ping-pong tiles until one value is left; buf_b must hold ceil(n/4096) doubles
+  double* in = buf_a; double* out = buf_b;
+  if (n == 0) { *result_host = 0.0; return XGPU_OK; }
+  while (n > 1) {
+    const int64_t nb = (n + 4095) / 4096;
+    k_sum_tiles<<<(unsigned)nb, 256, 0, ctx->stream>>>(in, n, out);
+    XGPU_LAUNCH_CHECK(ctx);
+    double* t = in; in = out; out = t;
+    n = nb;
+  }
+  XGPU_CUDA(ctx, cudaMemcpyAsync(ctx->h_pinned, in, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  XGPU_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  *result_host = *(double*)ctx->h_pinned;
+  return XGPU_OK;
+}
+
+extern "C" int xgpu_cutquad_count(xgpu_ctx* ctx, int dim, int64_t n, const int32_t* elems, const int32_t* el_vtx,
+                                  const double* phi, int dt, int order, int64_t* offsets, int64_t* total_host)
+{
+  if (!ctx || dim < 1 || dim > 3 || dt < 0 || dt > 2) return xgpu_fail(ctx, XGPU_ERR_ARG, "xgpu_cutquad_count: bad argument");
+  if (total_host) *total_host = 0;
+  const xgpu_rule_host* rv = xgpu_rule_lookup(ctx, dim, order);
+  const xgpu_rule_host* rs = (dt == XGPU_IF) ? xgpu_rule_lookup(ctx, dim - 1, order) : rv;
+  if (!rv || !rs) return xgpu_fail(ctx, XGPU_ERR_ARG, "xgpu_cutquad_count: no rule");
+  void* p;
+  int rc = xgpu_scratch(ctx, 0, sizeof(int32_t) * (n + 1), &p);
+  if (rc) return rc;
+  int32_t* counts = (int32_t*)p;
+  if (n > 0) {
+    if (dim == 3) k_cq_count<3><<<nblk(n, 256), 256, 0, ctx->stream>>>(n, elems, el_vtx, phi, dt, rv->n, rs->n, counts);
+    else if (dim == 2) k_cq_count<2><<<nblk(n, 256), 256, 0, ctx->stream>>>(n, elems, el_vtx, phi, dt, rv->n, rs->n, counts);
+    else k_cq_count<1><<<nblk(n, 256), 256, 0, ctx->stream>>>(n, elems, el_vtx, phi, dt, rv->n, rs->n, counts);
+    XGPU_LAUNCH_CHECK(ctx);
+  }
+  rc = xgpu_exclusive_scan_i32(ctx, counts, n, offsets);
+  if (rc) return rc;
+  if (total_host) {
+    XGPU_CUDA(ctx, cudaMemcpyAsync(ctx->h_pinned, offsets + n, sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
+    XGPU_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    *total_host = ctx->h_pinned[0];
+  }
+  return XGPU_OK;
+}
+
+extern "C" int xgpu_cutquad_fill(xgpu_ctx* ctx, int dim, int64_t n, const int32_t* elems, const int32_t* el_vtx,
+                                 const double* vtx_xyz, const double* phi, int dt, int order,
+                                 const int64_t* offsets, double* pts, double* wts)
+{
+  if (!ctx || dim < 1 || dim > 3 || dt < 0 || dt > 2) return xgpu_fail(ctx, XGPU_ERR_ARG, "xgpu_cutquad_fill: bad argument");
+  if (n == 0) return XGPU_OK;
+  const xgpu_rule_host* rv = xgpu_rule_lookup(ctx, dim, order);
+  const xgpu_rule_host* rs = (dt == XGPU_IF) ? xgpu_rule_lookup(ctx, dim - 1, order) : rv;
+  if (!rv || !rs) return xgpu_fail(ctx, XGPU_ERR_ARG, "xgpu_cutquad_fill: no rule");
+  const size_t sm = sizeof(double) * 4 * rs->n;
+  unsigned grid = nblk(n, 4);  // 4 warps (elements) per block
+  if (grid > XGPU_NSM * 16) grid = XGPU_NSM * 16;
+#define XG_FILL(DD)                                                                                                  \
+  {                                                                                                                  \
+    if (sm > 48 * 1024) XGPU_CUDA(ctx, cudaFuncSetAttribute(k_cq_fill<DD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm)); \
+    k_cq_fill<DD><<<grid, 128, sm, ctx->stream>>>(n, elems, el_vtx, vtx_xyz, phi, dt, rv->d_pts, rv->d_wts, rv->n,   \
+                                                  rs->d_pts, rs->d_wts, rs->n, offsets, pts, wts, ctx->d_status,     \
+                                                  ctx->d_status_elem);                                               \
+  }
+  if (dim == 3) XG_FILL(3) else if (dim == 2) XG_FILL(2) else XG_FILL(1)
+#undef XG_FILL
+  XGPU_LAUNCH_CHECK(ctx);
+  return XGPU_OK;
+}
+
+extern "C" int xgpu_integrate_monomial(xgpu_ctx* ctx, int dim, int64_t n, const int32_t* elems, const int32_t* el_vtx,
+                                       const double* vtx_xyz, const int64_t* offsets, const double* pts,
+                                       const double* wts, const int* expo_host, double* result_host)
+{
+  if (!ctx || dim < 1 || dim > 3 || !result_host) return xgpu_fail(ctx, XGPU_ERR_ARG, "xgpu_integrate_monomial: bad argument");
+  *result_host = 0.0;
+  if (n == 0) return XGPU_OK;
+  void* p;
+  const int64_t nb = (n + 4095) / 4096;
+  int rc = xgpu_scratch(ctx, 1, sizeof(double) * (n + nb + 2), &p);
+  if (rc) return rc;
+  double* elsum = (double*)p;
+  const int e0 = expo_host[0], e1 = dim > 1 ? expo_host[1] : 0, e2 = dim > 2 ? expo_host[2] : 0;
+  const unsigned grid = nblk(n * 32, 128);
+  if (dim == 3) k_integrate<3><<<grid, 128, 0, ctx->stream>>>(n, elems, el_vtx, vtx_xyz, offsets, pts, wts, e0, e1, e2, elsum);
+  else if (dim == 2) k_integrate<2><<<grid, 128, 0, ctx->stream>>>(n, elems, el_vtx, vtx_xyz, offsets, pts, wts, e0, e1, e2, elsum);
+  else k_integrate<1><<<grid, 128, 0, ctx->stream>>>(n, elems, el_vtx, vtx_xyz, offsets, pts, wts, e0, e1, e2, elsum);
+  XGPU_LAUNCH_CHECK(ctx);
+  return xgpu_sum_f64(ctx, elsum, n, elsum + n, result_host);
+}

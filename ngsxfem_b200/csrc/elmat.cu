@@ -1,0 +1,392 @@
+// elmat.cu — batched cut / uncut element matrices  B^T diag(w D) B
+// (SymbolicCutBilinearFormIntegrator::T_CalcElementMatrixAdd, xfem/symboliccutbfi.cpp:76-486).
+//
+//   k_elmat_points<D,MAXB>  general path, one WARP per element: (1) every lane evaluates the H1
+//        basis, physical gradients (F^{-T}) and normal derivatives at one quadrature point of the
+//        current chunk and stages them in shared memory, (2) the lanes own 2x2 register blocks of
+//        the element matrix and contract over the staged points.  Used for cut elements
+//        (per-element rules from cutquad) and for uncut elements with a shared standard rule
+//        when the fast path does not apply.
+//   k_elmat_affine<D>       fast path for uncut AFFINE elements and ID*ID / GRAD.GRAD terms:
+//        sum_q w_q (F^{-T} dphi_i).(F^{-T} dphi_j) = sum_ab G_ab sum_q w_q d_a phi_i d_b phi_j is the
+//        same sum re-associated, so the matrix is  |det F| (c_m M_ref + c_s sum_ab G_ab K_ref^ab)
+//        with reference tensors contracted once on the host from the same rule.  Each lane
+//        prepares the 1 + D(D+1)/2 geometry coefficients of one element, then the warp streams
+//        the 32 matrices out with fully coalesced 256 B stores: HBM-write bound
+//        (nd^2 * 8 B out per element, 16 B + vertex gathers in).
+#include "common.cuh"
+#include "cutgeom.cuh"
+#include <vector>
+
+namespace {
+
+inline unsigned nblk(int64_t n, int t) { return (unsigned)((n + t - 1) / t); }
+
+#define XG_MAXTERMS 8
+struct TermsDev {
+  int n;
+  int op_trial[XG_MAXTERMS], op_test[XG_MAXTERMS], hpow[XG_MAXTERMS];
+  double coef[XG_MAXTERMS];
+};
+
+__device__ __forceinline__ double ipow(double h, int p)
+{
+  if (p == 0) return 1.0;
+  double r = 1.0;
+  const int ap = p < 0 ? -p : p;
+  for (int i = 0; i < ap; i++) r *= h;
+  return p < 0 ? 1.0 / r : r;
+}
+
+// staging sink: values, physical gradients and normal derivative of shape i at one point
+template <int D>
+struct StageSink {
+  double* B;         // this point's slab: [val | g0 | g1 | g2 | dn], each ndp long
+  int ndp;
+  const double* Fi;  // D x D inverse Jacobian
+  const double* nrm; // unit normal (physical) or zeros
+  __device__ __forceinline__ void operator()(int i, const AD<D>& a)
+  {
+    B[i] = a.v;
+    double dn = 0.0;
+#pragma unroll
+    for (int c = 0; c < D; c++) {
+      double g = 0.0;
+#pragma unroll
+      for (int j = 0; j < D; j++) g += Fi[j * D + c] * a.d[j];
+      B[(1 + c) * ndp + i] = g;
+      dn += g * nrm[c];
+    }
+    B[(1 + D) * ndp + i] = dn;
+  }
+};
+
+template <int D, int MAXB>
+__global__ void __launch_bounds__(128) k_elmat_points(
+    int64_t n, const int32_t* __restrict__ elems, const int32_t* __restrict__ el_vtx,
+    const double* __restrict__ vtx_xyz, const double* __restrict__ phi,
+    const int64_t* __restrict__ offsets, const double* __restrict__ pts, const double* __restrict__ wts, int np_shared,
+    int p, int nd, int CH, TermsDev T, int accumulate, const int32_t* __restrict__ slots, double* __restrict__ mats)
+{
+  extern __shared__ double smem[];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const int ndp = (nd + 1) & ~1, nbk = ndp >> 1;
+  const int PS = ndp * (2 + D) + XG_MAXTERMS;  // per point: val, D grads, dn, term weights
+  double* Bw = smem + (size_t)wib * CH * PS;
+  const int64_t warp0 = (int64_t)blockIdx.x * (blockDim.x >> 5) + wib;
+  const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
+  const int nblocks = nbk * nbk;
+  for (int64_t e = warp0; e < n; e += nwarps) {
+    const int64_t el = elems ? (int64_t)elems[e] : e;
+    int v[D + 1];
+    double vx[D + 1][3], l[D + 1], F[D * D], Fi[D * D], nrm[3] = {0, 0, 0};
+#pragma unroll
+    for (int k = 0; k < D + 1; k++) {
+      v[k] = __ldg(el_vtx + el * (D + 1) + k);
+      l[k] = phi ? __ldg(phi + v[k]) : 0.0;
+#pragma unroll
+      for (int c = 0; c < 3; c++) vx[k][c] = (c < D) ? __ldg(vtx_xyz + (int64_t)v[k] * D + c) : 0.0;
+    }
+    xg_affine_jac<D>(vx, F);
+    const double meas = fabs(xg_inv<D>(F, Fi));
+    const double h = (D == 1) ? meas : ((D == 2) ? sqrt(meas) : cbrt(meas));
+    if (phi) {  // n = F^{-T} grad_ref(lset) normalised (Normalize(grad(lsetp1)))
+      double nn = 0.0;
+#pragma unroll
+      for (int c = 0; c < D; c++) {
+        double s = 0.0;
+#pragma unroll
+        for (int j = 0; j < D; j++) s += Fi[j * D + c] * (l[j] - l[D]);
+        nrm[c] = s; nn += s * s;
+      }
+      nn = sqrt(nn);
+      if (nn > 0.0) { for (int c = 0; c < D; c++) nrm[c] /= nn; }
+    }
+    const int64_t q0 = offsets ? offsets[e] : 0;
+    const int npe = offsets ? (int)(offsets[e + 1] - q0) : np_shared;
+    double acc[MAXB][4];
+#pragma unroll
+    for (int b = 0; b < MAXB; b++) { acc[b][0] = acc[b][1] = acc[b][2] = acc[b][3] = 0.0; }
+    for (int c0 = 0; c0 < npe; c0 += CH) {
+      const int cs = min(CH, npe - c0);
+      __syncwarp();
+      if (lane < cs) {
+        double* B = Bw + (size_t)lane * PS;
+        const double* xq = pts + 3 * (q0 + c0 + lane);
+        double xh[3] = {xq[0], xq[1], xq[2]};
+        for (int i = nd; i < ndp; i++) for (int k = 0; k < 2 + D; k++) B[k * ndp + i] = 0.0;
+        StageSink<D> sink{B, ndp, Fi, nrm};
+        xg_h1_shapes_rt<D>(p, v, xh, sink);
+        const double fac = wts[q0 + c0 + lane] * meas;
+        for (int t = 0; t < T.n; t++) B[(2 + D) * ndp + t] = T.coef[t] * ipow(h, T.hpow[t]) * fac;
+      }
+      __syncwarp();
+#pragma unroll
+      for (int b = 0; b < MAXB; b++) {
+        const int blk = lane + 32 * b;
+        if (blk < nblocks) {
+          const int i0 = 2 * (blk / nbk), j0 = 2 * (blk % nbk);
+          for (int q = 0; q < cs; q++) {
+            const double* B = Bw + (size_t)q * PS;
+            for (int t = 0; t < T.n; t++) {
+              const double cw = B[(2 + D) * ndp + t];
+              if (T.op_test[t] == 1 && T.op_trial[t] == 1) {
+                double s00 = 0, s01 = 0, s10 = 0, s11 = 0;
+#pragma unroll
+                for (int c = 0; c < D; c++) {
+                  const double a0 = B[(1 + c) * ndp + i0], a1 = B[(1 + c) * ndp + i0 + 1];
+                  const double b0 = B[(1 + c) * ndp + j0], b1 = B[(1 + c) * ndp + j0 + 1];
+                  s00 += a0 * b0; s01 += a0 * b1; s10 += a1 * b0; s11 += a1 * b1;
+                }
+                acc[b][0] += cw * s00; acc[b][1] += cw * s01; acc[b][2] += cw * s10; acc[b][3] += cw * s11;
+              } else {
+                const int ot = (T.op_test[t] == 0) ? 0 : (1 + D), ou = (T.op_trial[t] == 0) ? 0 : (1 + D);
+                const double a0 = cw * B[ot * ndp + i0], a1 = cw * B[ot * ndp + i0 + 1];
+                const double b0 = B[ou * ndp + j0], b1 = B[ou * ndp + j0 + 1];
+                acc[b][0] += a0 * b0; acc[b][1] += a0 * b1; acc[b][2] += a1 * b0; acc[b][3] += a1 * b1;
+              }
+            }
+          }
+        }
+      }
+    }
+    double* M = mats + (size_t)(slots ? (int64_t)slots[e] : e) * nd * nd;
+#pragma unroll
+    for (int b = 0; b < MAXB; b++) {
+      const int blk = lane + 32 * b;
+      if (blk < nblocks) {
+        const int i0 = 2 * (blk / nbk), j0 = 2 * (blk % nbk);
+#pragma unroll
+        for (int a = 0; a < 2; a++)
+#pragma unroll
+          for (int c = 0; c < 2; c++) {
+            const int i = i0 + a, j = j0 + c;
+            if (i < nd && j < nd) {
+              if (accumulate) M[i * nd + j] += acc[b][2 * a + c];
+              else M[i * nd + j] = acc[b][2 * a + c];
+            }
+          }
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------- affine fast path
+template <int D>
+__global__ void __launch_bounds__(256) k_elmat_affine(
+    int64_t n, const int32_t* __restrict__ elems, const int32_t* __restrict__ el_vtx,
+    const double* __restrict__ vtx_xyz, int nd, const double* __restrict__ Tref, TermsDev T, int accumulate,
+    const int32_t* __restrict__ slots, double* __restrict__ mats)
+{
+  constexpr int NG = D * (D + 1) / 2;
+  constexpr int NC = 1 + NG;
+  const int lane = threadIdx.x & 31;
+  const int nn = nd * nd;
+  const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  // reference tensor entries owned by this lane (idx = lane + 32 k), k < 4 kept in registers
+  double tr[4][NC];
+#pragma unroll
+  for (int k = 0; k < 4; k++) {
+    const int idx = lane + 32 * k;
+#pragma unroll
+    for (int m = 0; m < NC; m++) tr[k][m] = (idx < nn) ? __ldg(Tref + m * nn + idx) : 0.0;
+  }
+  const int64_t ngroups = (n + 31) >> 5;
+  for (int64_t g = warp0; g < ngroups; g += nwarps) {
+    const int64_t e = (g << 5) + lane;
+    double coef[NC];
+#pragma unroll
+    for (int m = 0; m < NC; m++) coef[m] = 0.0;
+    if (e < n) {
+      const int64_t el = elems ? (int64_t)elems[e] : e;
+      double vx[D + 1][3], F[D * D], Fi[D * D];
+#pragma unroll
+      for (int k = 0; k < D + 1; k++) {
+        const int v = __ldg(el_vtx + el * (D + 1) + k);
+#pragma unroll
+        for (int c = 0; c < 3; c++) vx[k][c] = (c < D) ? __ldg(vtx_xyz + (int64_t)v * D + c) : 0.0;
+      }
+      xg_affine_jac<D>(vx, F);
+      const double meas = fabs(xg_inv<D>(F, Fi));
+      const double h = (D == 1) ? meas : ((D == 2) ? sqrt(meas) : cbrt(meas));
+      double cm = 0.0, cs = 0.0;
+      for (int t = 0; t < T.n; t++) {
+        const double c = T.coef[t] * ipow(h, T.hpow[t]) * meas;
+        if (T.op_test[t] == 0) cm += c; else cs += c;
+      }
+      coef[0] = cm;
+      int m = 1;
+#pragma unroll
+      for (int a = 0; a < D; a++)
+#pragma unroll
+        for (int b = a; b < D; b++) {
+          double gab = 0.0;
+#pragma unroll
+          for (int c = 0; c < D; c++) gab += Fi[a * D + c] * Fi[b * D + c];
+          coef[m++] = cs * gab;
+        }
+    }
+    const int cnt = (int)min((int64_t)32, n - (g << 5));
+    for (int s = 0; s < cnt; s++) {
+      double cc[NC];
+#pragma unroll
+      for (int m = 0; m < NC; m++) cc[m] = __shfl_sync(0xffffffffu, coef[m], s);
+      const int64_t me = (g << 5) + s;
+      double* M = mats + (size_t)(slots ? (int64_t)slots[me] : me) * nn;
+      if (nn <= 128) {
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+          const int idx = lane + 32 * k;
+          if (idx < nn) {
+            double r = 0.0;
+#pragma unroll
+            for (int m = 0; m < NC; m++) r += cc[m] * tr[k][m];
+            if (accumulate) M[idx] += r; else M[idx] = r;
+          }
+        }
+      } else {
+        for (int idx = lane; idx < nn; idx += 32) {
+          double r = 0.0;
+#pragma unroll
+          for (int m = 0; m < NC; m++) r += cc[m] * __ldg(Tref + m * nn + idx);
+          if (accumulate) M[idx] += r; else M[idx] = r;
+        }
+      }
+    }
+  }
+}
+
+int make_terms(xgpu_ctx* ctx, const xgpu_term* th, int nt, TermsDev& T, bool* only_mass_stiff)
+{
+  if (nt < 0 || nt > XG_MAXTERMS) return xgpu_fail(ctx, XGPU_ERR_ARG, "elmat: too many terms (max 8)");
+  T.n = nt;
+  *only_mass_stiff = true;
+  for (int t = 0; t < nt; t++) {
+    const int ou = th[t].op_trial, ot = th[t].op_test;
+    if (ou < 0 || ou > 2 || ot < 0 || ot > 2 || ((ou == 1) != (ot == 1)))
+      return xgpu_fail(ctx, XGPU_ERR_UNSUPPORTED, "elmat: unsupported operator pair (menu: ID/DN x ID/DN, GRAD.GRAD)");
+    T.op_trial[t] = ou; T.op_test[t] = ot; T.hpow[t] = th[t].hpow; T.coef[t] = th[t].coef;
+    if (!((ou == 0 && ot == 0) || (ou == 1 && ot == 1))) *only_mass_stiff = false;
+  }
+  return XGPU_OK;
+}
+
+template <int D>
+int launch_points(xgpu_ctx* ctx, int64_t n, const int32_t* elems, const int32_t* el_vtx, const double* vtx_xyz,
+                  const double* phi, const int64_t* offsets, const double* pts, const double* wts, int np_shared,
+                  int p, const TermsDev& T, int accumulate, const int32_t* slots, double* mats)
+{
+  const int nd = xg_h1_ndof(D, p);
+  const int ndp = (nd + 1) & ~1;
+  const int PS = ndp * (2 + D) + XG_MAXTERMS;
+  int CH = 32;
+  while (CH > 4 && (size_t)4 * CH * PS * sizeof(double) > 56 * 1024) CH >>= 1;
+  const size_t sm = (size_t)4 * CH * PS * sizeof(double);
+  const int nblocks = (ndp / 2) * (ndp / 2);
+  unsigned grid = nblk(n, 4);
+  if (grid > XGPU_NSM * 8) grid = XGPU_NSM * 8;
+#define XG_LP(MB)                                                                                                   \
+  {                                                                                                                 \
+    XGPU_CUDA(ctx, cudaFuncSetAttribute(k_elmat_points<D, MB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm)); \
+    k_elmat_points<D, MB><<<grid, 128, sm, ctx->stream>>>(n, elems, el_vtx, vtx_xyz, phi, offsets, pts, wts, np_shared, \
+                                                          p, nd, CH, T, accumulate, slots, mats);                   \
+  }
+  if (nblocks <= 32) XG_LP(1) else if (nblocks <= 128) XG_LP(4) else if (nblocks <= 352) XG_LP(11)
+  else return xgpu_fail(ctx, XGPU_ERR_UNSUPPORTED, "elmat: element too large");
+#undef XG_LP
+  XGPU_LAUNCH_CHECK(ctx);
+  return XGPU_OK;
+}
+
+// reference tensors  M_ref, K_ref^{ab}+K_ref^{ba} (a<b), K_ref^{aa}  on the device, cached per (dim,p,order)
+int get_reftensor(xgpu_ctx* ctx, int dim, int p, int order, const double** out)
+{
+  const int key = dim * 10000 + p * 100 + (order < 0 ? 0 : order);
+  auto it = ctx->reftensors.find(key);
+  if (it != ctx->reftensors.end()) { *out = (const double*)it->second; return XGPU_OK; }
+  const xgpu_rule_host* r = xgpu_rule_lookup(ctx, dim, order);
+  if (!r) return xgpu_fail(ctx, XGPU_ERR_ARG, "elmat: no rule");
+  const int nd = xg_h1_ndof(dim, p), nn = nd * nd, ng = dim * (dim + 1) / 2;
+  std::vector<double> Tm((size_t)(1 + ng) * nn, 0.0), sh(nd), dsh(nd * dim);
+  for (int q = 0; q < r->n; q++) {
+    xgpu_h1_shapes_host(dim, p, nullptr, &r->pts[3 * q], sh.data(), dsh.data());
+    const double w = r->wts[q];
+    for (int i = 0; i < nd; i++)
+      for (int j = 0; j < nd; j++) {
+        Tm[i * nd + j] += w * sh[i] * sh[j];
+        int m = 1;
+        for (int a = 0; a < dim; a++)
+          for (int b = a; b < dim; b++, m++) {
+            double k = dsh[i * dim + a] * dsh[j * dim + b];
+            if (a != b) k += dsh[i * dim + b] * dsh[j * dim + a];
+            Tm[(size_t)m * nn + i * nd + j] += w * k;
+          }
+      }
+  }
+  void* d;
+  XGPU_CUDA(ctx, cudaMalloc(&d, sizeof(double) * Tm.size()));
+  XGPU_CUDA(ctx, cudaMemcpyAsync(d, Tm.data(), sizeof(double) * Tm.size(), cudaMemcpyHostToDevice, ctx->stream));
+  XGPU_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  ctx->reftensors[key] = d;
+  *out = (const double*)d;
+  return XGPU_OK;
+}
+
+}  // namespace
+
+extern "C" int xgpu_elmat_rule(xgpu_ctx* ctx, int dim, int fe_order, int64_t n, const int32_t* elems,
+                               const int32_t* el_vtx, const double* vtx_xyz, const double* phi,
+                               const int64_t* offsets, const double* pts, const double* wts,
+                               const xgpu_term* terms_host, int nterms, int accumulate, const int32_t* slots, double* mats)
+{
+  if (!ctx || dim < 1 || dim > 3 || fe_order < 1 || fe_order > XG_MAX_ORDER || !offsets)
+    return xgpu_fail(ctx, XGPU_ERR_ARG, "xgpu_elmat_rule: bad argument (orders 1..4)");
+  if (n == 0) return XGPU_OK;
+  TermsDev T; bool ms;
+  int rc = make_terms(ctx, terms_host, nterms, T, &ms);
+  if (rc) return rc;
+  if (dim == 3) return launch_points<3>(ctx, n, elems, el_vtx, vtx_xyz, phi, offsets, pts, wts, 0, fe_order, T, accumulate, slots, mats);
+  if (dim == 2) return launch_points<2>(ctx, n, elems, el_vtx, vtx_xyz, phi, offsets, pts, wts, 0, fe_order, T, accumulate, slots, mats);
+  return launch_points<1>(ctx, n, elems, el_vtx, vtx_xyz, phi, offsets, pts, wts, 0, fe_order, T, accumulate, slots, mats);
+}
+
+extern "C" int xgpu_elmat_std(xgpu_ctx* ctx, int dim, int fe_order, int64_t n, const int32_t* elems,
+                              const int32_t* el_vtx, const double* vtx_xyz, const double* phi, int order,
+                              const xgpu_term* terms_host, int nterms, int accumulate, const int32_t* slots, double* mats)
+{
+  if (!ctx || dim < 1 || dim > 3 || fe_order < 1 || fe_order > XG_MAX_ORDER)
+    return xgpu_fail(ctx, XGPU_ERR_ARG, "xgpu_elmat_std: bad argument (orders 1..4)");
+  if (n == 0) return XGPU_OK;
+  TermsDev T; bool ms;
+  int rc = make_terms(ctx, terms_host, nterms, T, &ms);
+  if (rc) return rc;
+  if (order < 0) {  // symboliccutbfi.cpp:100-118
+    int dtr = 99, dte = 99;
+    for (int t = 0; t < nterms; t++) {
+      dtr = std::min(dtr, terms_host[t].op_trial == 0 ? 0 : 1);
+      dte = std::min(dte, terms_host[t].op_test == 0 ? 0 : 1);
+    }
+    if (nterms == 0) dtr = dte = 0;
+    order = 2 * fe_order - (dtr + dte);
+  }
+  // fast path: orientation independent bases (P1, P2) and mass / stiffness terms only
+  if (ms && fe_order <= 2) {
+    const double* Tref;
+    rc = get_reftensor(ctx, dim, fe_order, order, &Tref);
+    if (rc) return rc;
+    const int nd = xg_h1_ndof(dim, fe_order);
+    unsigned grid = nblk((n + 31) / 32, 8);
+    if (grid > XGPU_NSM * 8) grid = XGPU_NSM * 8;
+    if (dim == 3) k_elmat_affine<3><<<grid, 256, 0, ctx->stream>>>(n, elems, el_vtx, vtx_xyz, nd, Tref, T, accumulate, slots, mats);
+    else if (dim == 2) k_elmat_affine<2><<<grid, 256, 0, ctx->stream>>>(n, elems, el_vtx, vtx_xyz, nd, Tref, T, accumulate, slots, mats);
+    else k_elmat_affine<1><<<grid, 256, 0, ctx->stream>>>(n, elems, el_vtx, vtx_xyz, nd, Tref, T, accumulate, slots, mats);
+    XGPU_LAUNCH_CHECK(ctx);
+    return XGPU_OK;
+  }
+  const xgpu_rule_host* r = xgpu_rule_lookup(ctx, dim, order);
+  if (!r) return xgpu_fail(ctx, XGPU_ERR_ARG, "xgpu_elmat_std: no rule");
+  if (dim == 3) return launch_points<3>(ctx, n, elems, el_vtx, vtx_xyz, phi, nullptr, r->d_pts, r->d_wts, r->n, fe_order, T, accumulate, slots, mats);
+  if (dim == 2) return launch_points<2>(ctx, n, elems, el_vtx, vtx_xyz, phi, nullptr, r->d_pts, r->d_wts, r->n, fe_order, T, accumulate, slots, mats);
+  return launch_points<1>(ctx, n, elems, el_vtx, vtx_xyz, phi, nullptr, r->d_pts, r->d_wts, r->n, fe_order, T, accumulate, slots, mats);
+}

@@ -1,0 +1,187 @@
+// facetpatch.cu — ghost-penalty facet-patch matrices
+// (SymbolicFacetPatchBilinearFormIntegrator::T_CalcFacetMatrix, xfem/symboliccutbfi.cpp:1982-2377,
+//  point mapping MapPatchIntegrationPoint :1747-1846) for the integrand
+//      coef * h^hpow * (u - u.Other()) * (v - v.Other()).
+// One WARP per facet.  The patch rule is [rule on el1 ; rule on el2]; every lane maps one patch
+// point into the other element's reference coordinates (affine elements: the affine solve the
+// reference uses as Newton start is already exact, Newton exits after its first step),
+// evaluates both bases and stages the jump vector J = [phi^1(x1) ; -phi^2(x2)] in shared memory;
+// lanes own 2x2 blocks of the (2nd)^2 matrix and accumulate c_q J J^T over the staged points.
+#include "common.cuh"
+#include "cutgeom.cuh"
+
+namespace {
+
+inline unsigned nblk(int64_t n, int t) { return (unsigned)((n + t - 1) / t); }
+
+struct ValSink {
+  double* J; double sgn;
+  template <int D> __device__ __forceinline__ void operator()(int i, const AD<D>& a) { J[i] = sgn * a.v; }
+};
+
+template <int D>
+__device__ __forceinline__ void load_geom(const int32_t* __restrict__ el_vtx, const double* __restrict__ vtx_xyz, int64_t el,
+                                          int* v, double (*vx)[3], double* F, double* Fi, double* meas)
+{
+#pragma unroll
+  for (int k = 0; k < D + 1; k++) {
+    v[k] = __ldg(el_vtx + el * (D + 1) + k);
+#pragma unroll
+    for (int c = 0; c < 3; c++) vx[k][c] = (c < D) ? __ldg(vtx_xyz + (int64_t)v[k] * D + c) : 0.0;
+  }
+  xg_affine_jac<D>(vx, F);
+  *meas = fabs(xg_inv<D>(F, Fi));
+}
+
+template <int D>
+__device__ __forceinline__ void map_fwd(const double (*vx)[3], const double* xh, double* x)
+{
+  double s = 1.0;
+#pragma unroll
+  for (int k = 0; k < D; k++) s -= xh[k];
+#pragma unroll
+  for (int c = 0; c < D; c++) {
+    double t = s * vx[D][c];
+#pragma unroll
+    for (int k = 0; k < D; k++) t += xh[k] * vx[k][c];
+    x[c] = t;
+  }
+}
+
+template <int D>
+__device__ __forceinline__ void map_inv(const double (*vx)[3], const double* Fi, const double* x, double* xh)
+{
+#pragma unroll
+  for (int i = 0; i < D; i++) {
+    double t = 0.0;
+#pragma unroll
+    for (int j = 0; j < D; j++) t += Fi[i * D + j] * (x[j] - vx[D][j]);
+    xh[i] = t;
+  }
+  for (int i = D; i < 3; i++) xh[i] = 0.0;
+}
+
+constexpr int FP_MAXB = 13;
+
+template <int D>
+__global__ void __launch_bounds__(128) k_facetpatch(
+    int64_t n, const int32_t* __restrict__ facets, const int32_t* __restrict__ facet_els,
+    const int32_t* __restrict__ el_vtx, const double* __restrict__ vtx_xyz,
+    const double* __restrict__ rp, const double* __restrict__ rw, int np,
+    int p, int nd, int CH, double coef, int hpow, double* __restrict__ mats)
+{
+  extern __shared__ double smem[];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const int N = 2 * nd, Np = (N + 1) & ~1, nbk = Np >> 1, nblocks = nbk * nbk;
+  const int PS = Np + 1;
+  double* Bw = smem + (size_t)wib * CH * PS;
+  const int64_t warp0 = (int64_t)blockIdx.x * (blockDim.x >> 5) + wib;
+  const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
+  const int npatch = 2 * np;
+  for (int64_t f = warp0; f < n; f += nwarps) {
+    const int64_t fac = facets ? (int64_t)facets[f] : f;
+    const int e1 = __ldg(facet_els + 2 * fac), e2 = __ldg(facet_els + 2 * fac + 1);
+    double* M = mats + (size_t)f * N * N;
+    if (e2 < 0) {  // the reference throws for LocalFacetNr2==-1 (:1992); boundary facets yield zero
+      for (int k = lane; k < N * N; k += 32) M[k] = 0.0;
+      continue;
+    }
+    int v1[D + 1], v2[D + 1];
+    double vx1[D + 1][3], vx2[D + 1][3], F1[D * D], Fi1[D * D], F2[D * D], Fi2[D * D], meas1, meas2;
+    load_geom<D>(el_vtx, vtx_xyz, e1, v1, vx1, F1, Fi1, &meas1);
+    load_geom<D>(el_vtx, vtx_xyz, e2, v2, vx2, F2, Fi2, &meas2);
+    const double h = (D == 1) ? meas1 : ((D == 2) ? sqrt(meas1) : cbrt(meas1));
+    double hp = 1.0;
+    { const int ap = hpow < 0 ? -hpow : hpow; for (int i = 0; i < ap; i++) hp *= h; if (hpow < 0) hp = 1.0 / hp; }
+    for (int panel = 0; panel * FP_MAXB * 32 < nblocks; panel++) {
+      double acc[FP_MAXB][4];
+#pragma unroll
+      for (int b = 0; b < FP_MAXB; b++) { acc[b][0] = acc[b][1] = acc[b][2] = acc[b][3] = 0.0; }
+      for (int c0 = 0; c0 < npatch; c0 += CH) {
+        const int cs = min(CH, npatch - c0);
+        __syncwarp();
+        if (lane < cs) {
+          const int l = c0 + lane;
+          double* B = Bw + (size_t)lane * PS;
+          double x1[3], x2[3], x[3], w;
+          if (l < np) {
+            x1[0] = rp[3 * l]; x1[1] = rp[3 * l + 1]; x1[2] = rp[3 * l + 2];
+            map_fwd<D>(vx1, x1, x);
+            map_inv<D>(vx2, Fi2, x, x2);
+            w = rw[l] * meas1;
+          } else {
+            const int q = l - np;
+            x2[0] = rp[3 * q]; x2[1] = rp[3 * q + 1]; x2[2] = rp[3 * q + 2];
+            map_fwd<D>(vx2, x2, x);
+            map_inv<D>(vx1, Fi1, x, x1);
+            w = rw[q] * meas2;
+          }
+          for (int i = N; i < Np; i++) B[i] = 0.0;
+          ValSink s1{B, 1.0}, s2{B + nd, -1.0};
+          xg_h1_shapes_rt<D>(p, v1, x1, s1);
+          xg_h1_shapes_rt<D>(p, v2, x2, s2);
+          B[Np] = coef * hp * w;
+        }
+        __syncwarp();
+#pragma unroll
+        for (int b = 0; b < FP_MAXB; b++) {
+          const int blk = (panel * FP_MAXB + b) * 32 + lane;
+          if (blk < nblocks) {
+            const int i0 = 2 * (blk / nbk), j0 = 2 * (blk % nbk);
+            for (int q = 0; q < cs; q++) {
+              const double* B = Bw + (size_t)q * PS;
+              const double cw = B[Np];
+              const double a0 = cw * B[i0], a1 = cw * B[i0 + 1], b0 = B[j0], b1 = B[j0 + 1];
+              acc[b][0] += a0 * b0; acc[b][1] += a0 * b1; acc[b][2] += a1 * b0; acc[b][3] += a1 * b1;
+            }
+          }
+        }
+      }
+#pragma unroll
+      for (int b = 0; b < FP_MAXB; b++) {
+        const int blk = (panel * FP_MAXB + b) * 32 + lane;
+        if (blk < nblocks) {
+          const int i0 = 2 * (blk / nbk), j0 = 2 * (blk % nbk);
+#pragma unroll
+          for (int a = 0; a < 2; a++)
+#pragma unroll
+            for (int c = 0; c < 2; c++) {
+              const int i = i0 + a, j = j0 + c;
+              if (i < N && j < N) M[i * N + j] = acc[b][2 * a + c];
+            }
+        }
+      }
+    }
+  }
+}
+
+}  // namespace
+
+extern "C" int xgpu_facetpatch(xgpu_ctx* ctx, int dim, int fe_order, int64_t n, const int32_t* facets,
+                               const int32_t* facet_els, const int32_t* el_vtx, const double* vtx_xyz,
+                               int order, double coef, int hpow, double* mats)
+{
+  if (!ctx || dim < 1 || dim > 3 || fe_order < 1 || fe_order > XG_MAX_ORDER)
+    return xgpu_fail(ctx, XGPU_ERR_ARG, "xgpu_facetpatch: bad argument (orders 1..4)");
+  if (n == 0) return XGPU_OK;
+  if (order < 0) order = 2 * fe_order;  // symboliccutbfi.cpp:2004-2012
+  const xgpu_rule_host* r = xgpu_rule_lookup(ctx, dim, order);
+  if (!r) return xgpu_fail(ctx, XGPU_ERR_ARG, "xgpu_facetpatch: no rule");
+  const int nd = xg_h1_ndof(dim, fe_order);
+  const int Np = (2 * nd + 1) & ~1, PS = Np + 1;
+  int CH = 32;
+  while (CH > 4 && (size_t)4 * CH * PS * sizeof(double) > 56 * 1024) CH >>= 1;
+  const size_t sm = (size_t)4 * CH * PS * sizeof(double);
+  unsigned grid = nblk(n, 4);
+  if (grid > XGPU_NSM * 8) grid = XGPU_NSM * 8;
+#define XG_FP(DD)                                                                                                   \
+  {                                                                                                                 \
+    XGPU_CUDA(ctx, cudaFuncSetAttribute(k_facetpatch<DD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));   \
+    k_facetpatch<DD><<<grid, 128, sm, ctx->stream>>>(n, facets, facet_els, el_vtx, vtx_xyz, r->d_pts, r->d_wts, r->n, \
+                                                     fe_order, nd, CH, coef, hpow, mats);                           \
+  }
+  if (dim == 3) XG_FP(3) else if (dim == 2) XG_FP(2) else XG_FP(1)
+#undef XG_FP
+  XGPU_LAUNCH_CHECK(ctx);
+  return XGPU_OK;
+}

@@ -1,0 +1,506 @@
+"""dCut / dFacetPatch / SymbolicCutBFI-style integrators and (Restricted)BilinearForm.Assemble —
+the Python mirror of ngsxfem's form surface (python/__init__.py:749-864, 973-1037;
+cutint/python_cutint.cpp:359-392, 447-483; cutint/cutintegral.cpp:12-66, 233-265;
+utils/restrictedblf.cpp) driving the batched CUDA path.
+
+NGSolve interprets arbitrary CoefficientFunction trees per quadrature point
+(xfem/symboliccutbfi.cpp:174-193).  The accelerated path supports a closed menu and raises for
+anything else (no silent fallback):  sums of  c * h^k * A(u) * B(v)  with A, B in
+{u, grad(u)., grad(u)*n}, n = Normalize(grad(lsetp1)), h = specialcf.mesh_size, and on facet
+patches  c * h^k * (u-u.Other())*(v-v.Other()).
+"""
+import numbers
+
+import torch
+
+from . import ops
+from ._lib import XgpuError, default_ctx
+from .cutinfo import BitArray, GridFunction, NEG, POS, IF, _lset_vec, _normalize_dtlist
+
+OP_ID, OP_GRAD, OP_DN, OP_JUMP = 0, 1, 2, 3
+
+
+# ------------------------------------------------------------------ tiny symbolic layer
+class MeshSize:
+    """specialcf.mesh_size and its integer powers"""
+
+    def __init__(self, power=1):
+        self.power = power
+
+    def __pow__(self, k):
+        if not isinstance(k, int):
+            raise XgpuError("only integer powers of the mesh size are supported")
+        return MeshSize(self.power * k)
+
+    def __rtruediv__(self, c):
+        return Scalar(float(c), -self.power)
+
+    def __mul__(self, o):
+        return Scalar(1.0, self.power) * o
+
+    __rmul__ = __mul__
+
+
+class specialcf:
+    mesh_size = MeshSize()
+
+
+class Scalar:
+    """c * h^k"""
+
+    def __init__(self, c, hpow=0):
+        self.c, self.hpow = float(c), int(hpow)
+
+    def __mul__(self, o):
+        if isinstance(o, numbers.Number):
+            return Scalar(self.c * o, self.hpow)
+        if isinstance(o, Scalar):
+            return Scalar(self.c * o.c, self.hpow + o.hpow)
+        if isinstance(o, MeshSize):
+            return Scalar(self.c, self.hpow + o.power)
+        return o.__rmul__(self)
+
+    __rmul__ = __mul__
+
+    def __truediv__(self, o):
+        if isinstance(o, MeshSize):
+            return Scalar(self.c, self.hpow - o.power)
+        return Scalar(self.c / float(o), self.hpow)
+
+
+class Normal:
+    """n = Normalize(grad(lsetp1))"""
+
+    def __init__(self, lset):
+        self.lset = lset
+
+
+class GradLset:
+    def __init__(self, lset):
+        self.lset = lset
+
+
+def Normalize(g):
+    if isinstance(g, GradLset):
+        return Normal(g.lset)
+    raise XgpuError("Normalize: only Normalize(grad(lsetp1)) is supported")
+
+
+class Proxy:
+    """trial / test function with an operator"""
+
+    def __init__(self, space, is_test, op=OP_ID, scal=None, other=False):
+        self.space, self.is_test, self.op, self.other = space, is_test, op, other
+        self.scal = scal or Scalar(1.0)
+
+    def Other(self):
+        if self.op != OP_ID:
+            raise XgpuError(".Other() is supported on u / v only")
+        return Proxy(self.space, self.is_test, OP_ID, self.scal, other=True)
+
+    def _with(self, op=None, scal=None):
+        return Proxy(self.space, self.is_test, self.op if op is None else op, scal or self.scal, self.other)
+
+    def __neg__(self):
+        return self._with(scal=self.scal * -1.0)
+
+    def __sub__(self, o):
+        if isinstance(o, Proxy) and o.other and not self.other and self.op == OP_ID and o.op == OP_ID \
+                and o.is_test == self.is_test:
+            return Proxy(self.space, self.is_test, OP_JUMP, self.scal)
+        raise XgpuError("unsupported difference of proxies (menu: u - u.Other())")
+
+    def __mul__(self, o):
+        if isinstance(o, (numbers.Number, Scalar, MeshSize)):
+            s = o if isinstance(o, Scalar) else (Scalar(float(o)) if isinstance(o, numbers.Number) else Scalar(1.0, o.power))
+            return self._with(scal=self.scal * s)
+        if isinstance(o, Normal):
+            if self.op != OP_GRAD:
+                raise XgpuError("only grad(u)*n is supported with the level-set normal")
+            return self._with(op=OP_DN)
+        if isinstance(o, Proxy):
+            return Form.from_pair(self, o)
+        if isinstance(o, Form):
+            return o.__rmul__(self)
+        return NotImplemented
+
+    __rmul__ = __mul__
+
+
+def TrialFunction(space):
+    return Proxy(space, False)
+
+
+def TestFunction(space):
+    return Proxy(space, True)
+
+
+def grad(u):
+    if isinstance(u, Proxy):
+        if u.op != OP_ID or u.other:
+            raise XgpuError("grad of this proxy is not supported")
+        return u._with(op=OP_GRAD)
+    if isinstance(u, GridFunction):
+        return GradLset(u)
+    raise XgpuError("grad: unsupported argument")
+
+
+class Form:
+    """sum of monomials (op_trial, op_test, coef, hpow)"""
+
+    def __init__(self, terms, space):
+        self.terms, self.space = terms, space
+
+    @staticmethod
+    def from_pair(a, b):
+        if a.is_test == b.is_test:
+            raise XgpuError("a bilinear form needs one trial and one test function per term")
+        u, v = (b, a) if a.is_test else (a, b)
+        if (u.op == OP_GRAD) != (v.op == OP_GRAD):
+            raise XgpuError("grad(u) must be paired with grad(v) (dot product) or the normal n")
+        if (u.op == OP_JUMP) != (v.op == OP_JUMP):
+            raise XgpuError("jump terms must pair (u-u.Other()) with (v-v.Other())")
+        s = u.scal * v.scal
+        return Form([(u.op, v.op, s.c, s.hpow)], u.space)
+
+    def __add__(self, o):
+        if isinstance(o, Form):
+            return Form(self.terms + o.terms, self.space)
+        return NotImplemented
+
+    def __sub__(self, o):
+        return self + (-1.0) * o
+
+    def __neg__(self):
+        return (-1.0) * self
+
+    def __mul__(self, o):
+        if isinstance(o, (numbers.Number, Scalar, MeshSize)):
+            s = o if isinstance(o, Scalar) else (Scalar(float(o)) if isinstance(o, numbers.Number) else Scalar(1.0, o.power))
+            return Form([(a, b, c * s.c, hp + s.hpow) for a, b, c, hp in self.terms], self.space)
+        if isinstance(o, (CutDifferentialSymbol, FacetPatchDifferentialSymbol)):
+            return Integral(self, o)
+        return NotImplemented
+
+    __rmul__ = __mul__
+
+
+# ------------------------------------------------------------------ differential symbols
+class CutDifferentialSymbol:
+    def __init__(self, levelset, domain_type, order, definedonelements, deformation, time_order=-1, tref=None):
+        self.levelset, self.domain_type, self.order = levelset, domain_type, order
+        self.definedonelements, self.deformation = definedonelements, deformation
+        self.time_order, self.tref = time_order, tref
+
+
+def dCut(levelset, domain_type, order=None, subdivlvl=None, time_order=-1, levelset_domain=None,
+         definedonelements=None, deformation=None, definedon=None, vb=0, element_boundary=False,
+         element_vb=0, skeleton=False, tref=None, **kwargs):
+    """python/__init__.py:781-864"""
+    if subdivlvl not in (None, 0):
+        raise XgpuError("subdivlvl > 0 selects ngsxfem's legacy subdivision path: not provided")
+    if element_boundary or skeleton or element_vb != 0 or vb != 0:
+        raise XgpuError("element-boundary / skeleton / BND cut integrals are not on the accelerated path yet")
+    if deformation is not None:
+        raise XgpuError("isoparametric deformation is not on the accelerated path yet")
+    if time_order >= 0 or tref is not None:
+        raise XgpuError("space-time forms are not assembled on the accelerated path yet (rules: ops.cutquad_st)")
+    if kwargs:
+        raise XgpuError(f"unsupported dCut arguments: {sorted(kwargs)}")
+    return CutDifferentialSymbol(levelset, domain_type, -1 if order is None else int(order), definedonelements, deformation)
+
+
+class FacetPatchDifferentialSymbol:
+    def __init__(self, definedonelements, order):
+        self.definedonelements, self.order = definedonelements, order
+
+
+def dFacetPatch(definedonelements=None, deformation=None, time_order=-1, tref=None, downscale=None,
+                bonus_intorder=0, **kwargs):
+    """python/__init__.py:749-778; bonus_intorder is accepted and ignored as in the reference"""
+    if deformation is not None or time_order >= 0 or tref is not None or downscale not in (None, 1, 1.0):
+        raise XgpuError("dFacetPatch: deformation / space-time / downscale are not on the accelerated path yet")
+    if definedonelements is None:
+        raise XgpuError("dFacetPatch needs definedonelements (a BitArray over the facets)")
+    return FacetPatchDifferentialSymbol(definedonelements, -1)
+
+
+class Integral:
+    def __init__(self, form, dx):
+        self.form, self.dx = form, dx
+
+    def __add__(self, o):
+        return SumOfIntegrals([self]) + o
+
+
+class SumOfIntegrals:
+    def __init__(self, ints):
+        self.ints = ints
+
+    def __add__(self, o):
+        if isinstance(o, Integral):
+            return SumOfIntegrals(self.ints + [o])
+        return SumOfIntegrals(self.ints + o.ints)
+
+
+# ------------------------------------------------------------------ sparse matrix result
+class SparseMatrixCSR:
+    def __init__(self, ndof, rowptr, col, vals):
+        self.ndof, self.rowptr, self.col, self.vals = ndof, rowptr, col, vals
+
+    @property
+    def nze(self):
+        return self.col.numel()
+
+    def CSR(self):
+        return self.vals, self.col, self.rowptr
+
+    def to_scipy(self):
+        import scipy.sparse as sp
+        return sp.csr_matrix((self.vals.cpu().numpy(), self.col.cpu().numpy(), self.rowptr.cpu().numpy()),
+                             shape=(self.ndof, self.ndof))
+
+    def __mul__(self, x):
+        return ops.csr_spmv(self.rowptr, self.col, self.vals, x)
+
+
+# ------------------------------------------------------------------ bilinear forms
+class BilinearForm:
+    """BilinearForm(space) / RestrictedBilinearForm(space, element_restriction, facet_restriction)
+
+    Assemble() = graph (GetGraph) + batched element / facet-patch matrices + deterministic
+    scatter, everything on the GPU.  Sparsity: union of the dof cliques of the active elements
+    (element_restriction, else the elements carrying dofs) and, if the space has dgjumps, of the
+    dof unions across the active facets (facet_restriction, else all interior facets between
+    active elements) — utils/restrictedblf.cpp:8-163, SURVEY.md §9.14."""
+
+    def __init__(self, space, symmetric=False, check_unused=True, element_restriction=None, facet_restriction=None,
+                 name="bfa", **flags):
+        if symmetric:
+            raise XgpuError("symmetric storage is not provided (the cut BFI never symmetrises, symboliccutbfi.cpp:56)")
+        self.space = space
+        self.element_restriction, self.facet_restriction = element_restriction, facet_restriction
+        self.integrals = []
+        self.mat = None
+        self.timings = {}
+
+    def __iadd__(self, o):
+        if isinstance(o, Integral):
+            self.integrals.append(o)
+        elif isinstance(o, SumOfIntegrals):
+            self.integrals.extend(o.ints)
+        else:
+            raise XgpuError("BilinearForm += expects form * dCut(...) or form * dFacetPatch(...)")
+        return self
+
+    # ---- helpers
+    def _active_elements(self):
+        if self.element_restriction is not None:
+            return self.element_restriction
+        act = getattr(self.space, "active_elements", None)
+        if act is not None:
+            return BitArray(self.space.mesh.ne, words=act)
+        return BitArray(self.space.mesh.ne, self.space.mesh.device).Set()
+
+    def _rows(self, elem_list):
+        sp = self.space
+        if hasattr(sp, "rows"):
+            return sp.rows(elem_list)
+        return ops.gather_rows(sp.el_dofs, elem_list, None)
+
+    def Assemble(self):
+        sp = self.space
+        mesh = sp.mesh
+        dim, p = mesh.dim, sp.order
+        ctx = default_ctx(mesh.device.index)
+        dev = mesh.device
+        ne = mesh.ne
+        nd = sp.nd
+        active = self._active_elements()
+
+        # ---- volume (cut) integrators: group per level set; per element ONE matrix summing all integrators
+        vol = [i for i in self.integrals if isinstance(i.dx, CutDifferentialSymbol)]
+        fac = [i for i in self.integrals if isinstance(i.dx, FacetPatchDifferentialSymbol)]
+        tables, mats = [], []
+        # two batches: U = uncut active elements, C = cut active elements (w.r.t. the level set of the
+        # integrators); every integrator accumulates into its elements' slot, so each element has ONE
+        # matrix as in NGSolve's element loop (CalcElementMatrixAdd over all integrators, then one
+        # AddElementMatrix).  A batch whose first integrator covers it completely is written without
+        # a prior memset (write-only traffic).
+        phi0 = None
+        for integ in vol:
+            if isinstance(integ.dx.levelset, (list, tuple)):
+                raise XgpuError("multi-level-set forms: use ops.cutquad_ml + ops.elmat_rule (assembly wrapper pending)")
+            phi = _lset_vec(integ.dx.levelset, mesh)
+            if phi0 is None:
+                phi0 = phi
+            elif phi.data_ptr() != phi0.data_ptr() and not torch.equal(phi, phi0):
+                raise XgpuError("all cut integrators of one BilinearForm must use the same level set")
+        if phi0 is not None:
+            bn, bp, bi, _ = ops.classify(dim, mesh.elements, phi0, want_ratio=False, ctx=ctx)
+            ctx.raise_on_geometry_error()
+            b_unc = ops.bitset_op(ops.BIT_OR, bn, bp, ne, ctx=ctx)
+            U = BitArray(ne, words=ops.bitset_op(ops.BIT_AND, b_unc, active.bits, ne, ctx=ctx))
+            Cc = BitArray(ne, words=ops.bitset_op(ops.BIT_AND, bi, active.bits, ne, ctx=ctx))
+        else:
+            U, Cc = active, BitArray(ne, dev)
+        l_U, l_C = U.indices(), Cc.indices()
+        slot_U = ops.bitset_rank(U.bits, ne, ctx=ctx)[0] if l_U.numel() else None
+        slot_C = ops.bitset_rank(Cc.bits, ne, ctx=ctx)[0] if l_C.numel() else None
+        m_U = torch.empty((l_U.numel(), nd, nd), dtype=torch.float64, device=dev)
+        m_C = torch.empty((l_C.numel(), nd, nd), dtype=torch.float64, device=dev)
+        init_U = init_C = False
+        for integ in vol:
+            dx = integ.dx
+            terms = list(integ.form.terms)
+            if any(t[0] == OP_JUMP for t in terms):
+                raise XgpuError("jump terms belong on dFacetPatch")
+            dt = int(dx.domain_type)
+            order = dx.order
+            if order < 0:  # symboliccutbfi.cpp:100-118
+                dtr = min(0 if t[0] == OP_ID else 1 for t in terms)
+                dte = min(0 if t[1] == OP_ID else 1 for t in terms)
+                order = 2 * p - (dtr + dte)
+            don = dx.definedonelements
+            if dt != IF and l_U.numel():
+                sel = ops.bitset_op(ops.BIT_AND, bn if dt == NEG else bp, U.bits, ne, ctx=ctx)
+                if don is not None:
+                    sel = ops.bitset_op(ops.BIT_AND, sel, don.bits, ne, ctx=ctx)
+                l = ops.bitset_to_list(sel, ne, ctx=ctx)
+                if l.numel():
+                    full = l.numel() == l_U.numel()
+                    if not init_U and not full:
+                        m_U.zero_()
+                    ops.elmat_std(dim, p, l, mesh.elements, mesh.points, phi0, order, terms, out=m_U,
+                                  accumulate=init_U or not full, slots=None if full else slot_U[l.long()].contiguous(), ctx=ctx)
+                    init_U = True
+            if l_C.numel():
+                sel = Cc.bits if don is None else ops.bitset_op(ops.BIT_AND, Cc.bits, don.bits, ne, ctx=ctx)
+                l = ops.bitset_to_list(sel, ne, ctx=ctx)
+                if l.numel():
+                    full = l.numel() == l_C.numel()
+                    if not init_C and not full:
+                        m_C.zero_()
+                    off, q, w = ops.cutquad(dim, l, mesh.elements, mesh.points, phi0, dt, order, ctx=ctx)
+                    ctx.raise_on_geometry_error()
+                    ops.elmat_rule(dim, p, l, mesh.elements, mesh.points, phi0, off, q, w, terms, out=m_C,
+                                   accumulate=init_C or not full, slots=None if full else slot_C[l.long()].contiguous(), ctx=ctx)
+                    init_C = True
+        if not init_U:
+            m_U.zero_()
+        if not init_C:
+            m_C.zero_()
+        if l_U.numel():
+            tables.append(self._rows(l_U)); mats.append(m_U)
+        if l_C.numel():
+            tables.append(self._rows(l_C)); mats.append(m_C)
+
+        # ---- facet patch integrators
+        _, _, fe = mesh.facets() if (fac or sp.dgjumps or self.facet_restriction is not None) else (None, None, None)
+        graph_facets = None
+        if self.facet_restriction is not None:
+            graph_facets = self.facet_restriction
+        elif sp.dgjumps and mesh.dim > 1:
+            # plain BilinearForm on a dgjumps space: couple across every facet between active elements
+            graph_facets = BitArray(mesh.nfacet, words=ops.facets_with_neighbor_types(fe, active.bits, active.bits, False, False, True, ctx=ctx))
+        facet_mats = {}
+        for integ in fac:
+            terms = integ.form.terms
+            if not all(t[0] == OP_JUMP and t[1] == OP_JUMP for t in terms):
+                raise XgpuError("dFacetPatch: only c*h^k*(u-u.Other())*(v-v.Other()) is supported")
+            l_f = integ.dx.definedonelements.indices()
+            key = id(integ.dx.definedonelements)
+            for (_, _, c, hp) in terms:
+                mm = ops.facetpatch(dim, p, l_f, fe, mesh.elements, mesh.points, integ.dx.order, c, hp, ctx=ctx)
+                if key in facet_mats:
+                    facet_mats[key] = (l_f, facet_mats[key][1] + mm)
+                else:
+                    facet_mats[key] = (l_f, mm)
+        covered = None
+        for key, (l_f, mm) in facet_mats.items():
+            fel = fe[l_f.long()]
+            t_f = torch.cat([self._rows(fel[:, 0].contiguous()), self._rows(fel[:, 1].contiguous())], dim=1).contiguous()
+            tables.append(t_f); mats.append(mm)
+            fb = BitArray(mesh.nfacet, mesh.device)
+            fb.bits.copy_(BitArray.from_numpy(_mask_from_list(l_f, mesh.nfacet), mesh.device).bits)
+            covered = fb if covered is None else (covered | fb)
+        if graph_facets is not None:
+            # facets that only contribute sparsity (explicit zeros kept)
+            rest = graph_facets if covered is None else BitArray(mesh.nfacet, words=ops.bitset_op(ops.BIT_ANDNOT, graph_facets.bits, covered.bits, mesh.nfacet, ctx=ctx))
+            l_g = rest.indices()
+            if l_g.numel():
+                fel = fe[l_g.long()]
+                inner = fel[:, 1] >= 0
+                fel = fel[inner]
+                if fel.shape[0]:
+                    t_g = torch.cat([self._rows(fel[:, 0].contiguous()), self._rows(fel[:, 1].contiguous())], dim=1).contiguous()
+                    tables.append(t_g)
+                    mats.append(torch.zeros((t_g.shape[0], 2 * nd, 2 * nd), dtype=torch.float64, device=dev))
+
+        plan = ops.csr_plan(sp.ndof, tables, ctx=ctx)
+        rowptr, col = ops.csr_pattern(plan, dev)
+        vals = ops.csr_scatter(plan, list(zip(tables, mats)), rowptr, col)
+        self.mat = SparseMatrixCSR(sp.ndof, rowptr, col, vals)
+        return self
+
+
+def _mask_from_list(lst, n):
+    import numpy as np
+    m = np.zeros(n, dtype=bool)
+    m[lst.cpu().numpy()] = True
+    return m
+
+
+def RestrictedBilinearForm(space, name="blf", element_restriction=None, facet_restriction=None, check_unused=True, **flags):
+    """python/__init__.py:973-1037 -> utils/python_utils.cpp:62-130"""
+    return BilinearForm(space, element_restriction=element_restriction, facet_restriction=facet_restriction,
+                        check_unused=check_unused, name=name, **flags)
+
+
+# ------------------------------------------------------------------ Integrate
+class CoordMonomial:
+    """x**a * y**b * z**c  (the only coefficient functions Integrate supports besides constants)"""
+
+    def __init__(self, expo, coef=1.0):
+        self.expo, self.coef = tuple(expo), float(coef)
+
+    def __mul__(self, o):
+        if isinstance(o, numbers.Number):
+            return CoordMonomial(self.expo, self.coef * o)
+        return CoordMonomial(tuple(a + b for a, b in zip(self.expo, o.expo)), self.coef * o.coef)
+
+    __rmul__ = __mul__
+
+    def __pow__(self, k):
+        return CoordMonomial(tuple(a * k for a in self.expo), self.coef ** k)
+
+
+x = CoordMonomial((1, 0, 0))
+y = CoordMonomial((0, 1, 0))
+z = CoordMonomial((0, 0, 1))
+
+
+def Integrate(levelset_domain=None, mesh=None, cf=1.0, order=5, time_order=-1, deformation=None, heapsize=1000000):
+    """python/__init__.py:361-439 -> cutint/python_cutint.cpp:21-163: sum_q w_q |det F| cf(x_q)."""
+    if deformation is not None or time_order >= 0:
+        raise XgpuError("Integrate: deformation / space-time are not on the accelerated path yet")
+    if isinstance(cf, numbers.Number):
+        cf = CoordMonomial((0, 0, 0), cf)
+    if not isinstance(cf, CoordMonomial):
+        raise XgpuError("Integrate: cf must be a constant or a coordinate monomial")
+    ld = levelset_domain
+    if ld.get("subdivlvl", 0) != 0:
+        raise XgpuError("subdivlvl != 0: legacy path not provided")
+    if "order" in ld and ld["order"] is not None and ld["order"] >= 0:
+        order = ld["order"]
+    dim = mesh.dim
+    ctx = default_ctx(mesh.device.index)
+    ls, dt = ld["levelset"], ld["domain_type"]
+    if isinstance(ls, (list, tuple)):
+        phis = torch.stack([_lset_vec(l, mesh) for l in ls]).contiguous()
+        dts = _normalize_dtlist(dt, len(ls))
+        off, p, w = ops.cutquad_ml(dim, None, mesh.elements, mesh.points, phis, dts, order, ctx=ctx)
+    else:
+        off, p, w = ops.cutquad(dim, None, mesh.elements, mesh.points, _lset_vec(ls, mesh), int(dt), order, ctx=ctx)
+    ctx.raise_on_geometry_error()
+    return cf.coef * ops.integrate_monomial(dim, None, mesh.elements, mesh.points, off, p, w, cf.expo[:dim], ctx=ctx)

@@ -1,0 +1,333 @@
+"""Thin tensor-level wrappers of the C ABI (one function per xgpu_* entry point).
+
+Tensors live on the CUDA device of the context; outputs are allocated with torch (device memory
+plumbing only) and filled by the hand-written kernels in libxgpu.so.
+"""
+import ctypes as C
+
+import torch
+
+from . import _lib
+from ._lib import Batch, Term, default_ctx, ptr
+
+NEG, POS, IF = 0, 1, 2
+OP_ID, OP_GRAD, OP_DN = 0, 1, 2
+BIT_OR, BIT_AND, BIT_ANDNOT, BIT_NOT, BIT_COPY, BIT_CLEAR, BIT_SET = range(7)
+
+
+def nwords(nbits):
+    return (int(nbits) + 31) // 32
+
+
+def _i32(t):
+    assert t.dtype == torch.int32 and t.is_cuda and t.is_contiguous(), "int32 contiguous CUDA tensor expected"
+    return t
+
+
+def _f64(t):
+    assert t.dtype == torch.float64 and t.is_cuda and t.is_contiguous(), "float64 contiguous CUDA tensor expected"
+    return t
+
+
+def new_bits(nbits, device):
+    return torch.zeros(nwords(nbits), dtype=torch.int32, device=device)
+
+
+def terms_array(terms):
+    arr = (Term * max(1, len(terms)))()
+    for i, (ou, ot, c, hp) in enumerate(terms):
+        arr[i].op_trial = int(ou); arr[i].op_test = int(ot); arr[i].coef = float(c); arr[i].hpow = int(hp)
+    return arr
+
+
+# ---------------------------------------------------------------- rules / basis (host tables)
+def get_rule(dim, order, ctx=None):
+    ctx = ctx or default_ctx()
+    n = ctx.lib.xgpu_rule_size(ctx.h, dim, order)
+    if n < 0:
+        ctx.check(n)
+    pts = torch.zeros((n, 3), dtype=torch.float64)
+    wts = torch.zeros(n, dtype=torch.float64)
+    rc = ctx.lib.xgpu_get_rule(ctx.h, dim, order, C.cast(pts.data_ptr(), _lib.c_f64p), C.cast(wts.data_ptr(), _lib.c_f64p))
+    if rc < 0:
+        ctx.check(rc)
+    return pts, wts
+
+
+def set_rule(dim, order, pts, wts, ctx=None):
+    ctx = ctx or default_ctx()
+    pts = pts.to(torch.float64).cpu().contiguous(); wts = wts.to(torch.float64).cpu().contiguous()
+    ctx.check(ctx.lib.xgpu_set_rule(ctx.h, dim, order, wts.numel(), C.cast(pts.data_ptr(), _lib.c_f64p),
+                                    C.cast(wts.data_ptr(), _lib.c_f64p)))
+
+
+def h1_ndof(dim, order):
+    return _lib.load().xgpu_h1_ndof(dim, order)
+
+
+def h1_shapes_host(dim, order, vnum, xhat):
+    lib = _lib.load()
+    nd = lib.xgpu_h1_ndof(dim, order)
+    sh = torch.zeros(nd, dtype=torch.float64); dsh = torch.zeros((nd, dim), dtype=torch.float64)
+    vn = torch.as_tensor(vnum, dtype=torch.int32).contiguous()
+    xh = torch.zeros(3, dtype=torch.float64); xh[:len(xhat)] = torch.as_tensor(xhat, dtype=torch.float64)
+    rc = lib.xgpu_h1_shapes_host(dim, order, C.cast(vn.data_ptr(), _lib.c_i32p), C.cast(xh.data_ptr(), _lib.c_f64p),
+                                 C.cast(sh.data_ptr(), _lib.c_f64p), C.cast(dsh.data_ptr(), _lib.c_f64p))
+    if rc < 0:
+        raise _lib.XgpuError(f"h1_shapes_host failed ({rc})")
+    return sh, dsh
+
+
+# ---------------------------------------------------------------- (a) CutInfo
+def classify(dim, el_vtx, phi, want_ratio=True, ctx=None, out=None):
+    ctx = ctx or default_ctx()
+    ne = el_vtx.shape[0]
+    dev = el_vtx.device
+    if out is None:
+        bn, bp, bi = new_bits(ne, dev), new_bits(ne, dev), new_bits(ne, dev)
+        cr = torch.empty(ne, dtype=torch.float64, device=dev) if want_ratio else None
+    else:
+        bn, bp, bi, cr = out
+    ctx.check(ctx.lib.xgpu_classify(ctx.h, dim, ne, ptr(_i32(el_vtx)), ptr(_f64(phi)), ptr(bn), ptr(bp), ptr(bi), ptr(cr)))
+    return bn, bp, bi, cr
+
+
+def bitset_op(op, a, b, nbits, out=None, ctx=None):
+    ctx = ctx or default_ctx()
+    if out is None:
+        out = torch.empty_like(a)
+    ctx.check(ctx.lib.xgpu_bitset_op(ctx.h, op, ptr(a), ptr(b), ptr(out), nbits))
+    return out
+
+
+def bitset_count(bits, nbits, ctx=None):
+    ctx = ctx or default_ctx()
+    c = C.c_int64(0)
+    ctx.check(ctx.lib.xgpu_bitset_count(ctx.h, ptr(bits), nbits, C.byref(c)))
+    return c.value
+
+
+def bitset_to_list(bits, nbits, ctx=None, count=None):
+    ctx = ctx or default_ctx()
+    if count is None:
+        count = bitset_count(bits, nbits, ctx)
+    lst = torch.empty(count, dtype=torch.int32, device=bits.device)
+    ctx.check(ctx.lib.xgpu_bitset_to_list(ctx.h, ptr(bits), nbits, ptr(lst)))
+    return lst
+
+
+def threshold_elements(cut_ratio, dt, threshold, ctx=None):
+    ctx = ctx or default_ctx()
+    ne = cut_ratio.numel()
+    out = new_bits(ne, cut_ratio.device)
+    ctx.check(ctx.lib.xgpu_threshold_elements(ctx.h, ne, ptr(_f64(cut_ratio)), dt, float(threshold), ptr(out)))
+    return out
+
+
+def _dts_array(dts):
+    flat = [int(d) for tup in dts for d in tup]
+    return (C.c_int * max(1, len(flat)))(*flat)
+
+
+def classify_ml(dim, el_vtx, phis, dts, ctx=None, out=None):
+    ctx = ctx or default_ctx()
+    ne = el_vtx.shape[0]
+    M, nv = phis.shape
+    if out is None:
+        out = new_bits(ne, el_vtx.device)
+    ctx.check(ctx.lib.xgpu_classify_ml(ctx.h, dim, ne, ptr(_i32(el_vtx)), ptr(_f64(phis)), nv, M, _dts_array(dts),
+                                       len(dts), ptr(out)))
+    return out
+
+
+def facets_with_neighbor_types(facet_els, a, b, bnd_val_a=True, bnd_val_b=True, use_and=True, ctx=None):
+    ctx = ctx or default_ctx()
+    nf = facet_els.shape[0]
+    out = new_bits(nf, facet_els.device)
+    ctx.check(ctx.lib.xgpu_facets_with_neighbor_types(ctx.h, nf, ptr(_i32(facet_els)), ptr(a), ptr(b), int(bnd_val_a),
+                                                      int(bnd_val_b), int(use_and), ptr(out)))
+    return out
+
+
+def elements_with_neighbor_facets(facet_els, facet_bits, ne, ctx=None):
+    ctx = ctx or default_ctx()
+    out = new_bits(ne, facet_els.device)
+    ctx.check(ctx.lib.xgpu_elements_with_neighbor_facets(ctx.h, facet_els.shape[0], ptr(_i32(facet_els)), ptr(facet_bits),
+                                                         ne, ptr(out)))
+    return out
+
+
+def dofs_of_elements(el_dofs, el_bits, ndof, ctx=None):
+    ctx = ctx or default_ctx()
+    out = new_bits(ndof, el_dofs.device)
+    ctx.check(ctx.lib.xgpu_dofs_of_elements(ctx.h, el_dofs.shape[0], el_dofs.shape[1], ptr(_i32(el_dofs)), ptr(el_bits),
+                                            ndof, ptr(out)))
+    return out
+
+
+def bitset_rank(bits, nbits, ctx=None):
+    ctx = ctx or default_ctx()
+    mp = torch.empty(nbits, dtype=torch.int32, device=bits.device)
+    n = C.c_int64(0)
+    ctx.check(ctx.lib.xgpu_bitset_rank(ctx.h, ptr(bits), nbits, ptr(mp), C.byref(n)))
+    return mp, n.value
+
+
+def gather_rows(table, lst=None, mp=None, ctx=None):
+    ctx = ctx or default_ctx()
+    n = table.shape[0] if lst is None else lst.numel()
+    out = torch.empty((n, table.shape[1]), dtype=torch.int32, device=table.device)
+    ctx.check(ctx.lib.xgpu_gather_rows(ctx.h, n, ptr(lst), table.shape[1], ptr(_i32(table)), ptr(mp), ptr(out)))
+    return out
+
+
+# ---------------------------------------------------------------- (b) cut quadrature
+def cutquad(dim, elems, el_vtx, vtx_xyz, phi, dt, order, ctx=None):
+    """returns (offsets int64 [n+1], pts [total,3], wts [total])"""
+    ctx = ctx or default_ctx()
+    n = el_vtx.shape[0] if elems is None else elems.numel()
+    dev = el_vtx.device
+    off = torch.empty(n + 1, dtype=torch.int64, device=dev)
+    tot = C.c_int64(0)
+    ctx.check(ctx.lib.xgpu_cutquad_count(ctx.h, dim, n, ptr(elems), ptr(_i32(el_vtx)), ptr(_f64(phi)), dt, order,
+                                         ptr(off), C.byref(tot)))
+    pts = torch.empty((tot.value, 3), dtype=torch.float64, device=dev)
+    wts = torch.empty(tot.value, dtype=torch.float64, device=dev)
+    ctx.check(ctx.lib.xgpu_cutquad_fill(ctx.h, dim, n, ptr(elems), ptr(el_vtx), ptr(_f64(vtx_xyz)), ptr(phi), dt, order,
+                                        ptr(off), ptr(pts), ptr(wts)))
+    return off, pts, wts
+
+
+def cutquad_ml(dim, elems, el_vtx, vtx_xyz, phis, dts, order, ctx=None):
+    ctx = ctx or default_ctx()
+    n = el_vtx.shape[0] if elems is None else elems.numel()
+    dev = el_vtx.device
+    M, nv = phis.shape
+    off = torch.empty(n + 1, dtype=torch.int64, device=dev)
+    tot = C.c_int64(0)
+    da = _dts_array(dts)
+    ctx.check(ctx.lib.xgpu_cutquad_ml_count(ctx.h, dim, n, ptr(elems), ptr(_i32(el_vtx)), ptr(_f64(phis)), nv, M, da,
+                                            len(dts), order, ptr(off), C.byref(tot)))
+    pts = torch.empty((tot.value, 3), dtype=torch.float64, device=dev)
+    wts = torch.empty(tot.value, dtype=torch.float64, device=dev)
+    ctx.check(ctx.lib.xgpu_cutquad_ml_fill(ctx.h, dim, n, ptr(elems), ptr(el_vtx), ptr(_f64(vtx_xyz)), ptr(phis), nv, M, da,
+                                           len(dts), order, ptr(off), ptr(pts), ptr(wts)))
+    return off, pts, wts
+
+
+def cutquad_st(dim, elems, el_vtx, vtx_xyz, phi_st, time_fe_order, dt, order_time, order_space, ctx=None):
+    ctx = ctx or default_ctx()
+    n = el_vtx.shape[0] if elems is None else elems.numel()
+    dev = el_vtx.device
+    nv = phi_st.shape[1]
+    off = torch.empty(n + 1, dtype=torch.int64, device=dev)
+    tot = C.c_int64(0)
+    ctx.check(ctx.lib.xgpu_cutquad_st_count(ctx.h, dim, n, ptr(elems), ptr(_i32(el_vtx)), ptr(_f64(phi_st)), nv,
+                                            time_fe_order, dt, order_time, order_space, ptr(off), C.byref(tot)))
+    pts = torch.empty((tot.value, 3), dtype=torch.float64, device=dev)
+    tv = torch.empty(tot.value, dtype=torch.float64, device=dev)
+    wts = torch.empty(tot.value, dtype=torch.float64, device=dev)
+    ctx.check(ctx.lib.xgpu_cutquad_st_fill(ctx.h, dim, n, ptr(elems), ptr(el_vtx), ptr(_f64(vtx_xyz)), ptr(phi_st), nv,
+                                           time_fe_order, dt, order_time, order_space, ptr(off), ptr(pts), ptr(tv), ptr(wts)))
+    return off, pts, tv, wts
+
+
+def integrate_monomial(dim, elems, el_vtx, vtx_xyz, off, pts, wts, expo, ctx=None):
+    ctx = ctx or default_ctx()
+    n = el_vtx.shape[0] if elems is None else elems.numel()
+    ex = (C.c_int * 3)(*([int(e) for e in expo] + [0] * (3 - len(expo))))
+    res = C.c_double(0.0)
+    ctx.check(ctx.lib.xgpu_integrate_monomial(ctx.h, dim, n, ptr(elems), ptr(_i32(el_vtx)), ptr(_f64(vtx_xyz)), ptr(off),
+                                              ptr(pts), ptr(wts), ex, C.byref(res)))
+    return res.value
+
+
+# ---------------------------------------------------------------- (c,d) matrices
+def elmat_rule(dim, fe_order, elems, el_vtx, vtx_xyz, phi, off, pts, wts, terms, out=None, accumulate=False, slots=None, ctx=None):
+    ctx = ctx or default_ctx()
+    n = el_vtx.shape[0] if elems is None else elems.numel()
+    nd = h1_ndof(dim, fe_order)
+    if out is None:
+        out = torch.empty((n, nd, nd), dtype=torch.float64, device=el_vtx.device)
+        accumulate = False
+    ctx.check(ctx.lib.xgpu_elmat_rule(ctx.h, dim, fe_order, n, ptr(elems), ptr(_i32(el_vtx)), ptr(_f64(vtx_xyz)), ptr(phi),
+                                      ptr(off), ptr(pts), ptr(wts), terms_array(terms), len(terms), int(accumulate), ptr(slots), ptr(out)))
+    return out
+
+
+def elmat_std(dim, fe_order, elems, el_vtx, vtx_xyz, phi, order, terms, out=None, accumulate=False, slots=None, ctx=None):
+    ctx = ctx or default_ctx()
+    n = el_vtx.shape[0] if elems is None else elems.numel()
+    nd = h1_ndof(dim, fe_order)
+    if out is None:
+        out = torch.empty((n, nd, nd), dtype=torch.float64, device=el_vtx.device)
+        accumulate = False
+    ctx.check(ctx.lib.xgpu_elmat_std(ctx.h, dim, fe_order, n, ptr(elems), ptr(_i32(el_vtx)), ptr(_f64(vtx_xyz)), ptr(phi),
+                                     order, terms_array(terms), len(terms), int(accumulate), ptr(slots), ptr(out)))
+    return out
+
+
+def facetpatch(dim, fe_order, facets, facet_els, el_vtx, vtx_xyz, order, coef, hpow, out=None, ctx=None):
+    ctx = ctx or default_ctx()
+    n = facet_els.shape[0] if facets is None else facets.numel()
+    nd = h1_ndof(dim, fe_order)
+    if out is None:
+        out = torch.empty((n, 2 * nd, 2 * nd), dtype=torch.float64, device=el_vtx.device)
+    ctx.check(ctx.lib.xgpu_facetpatch(ctx.h, dim, fe_order, n, ptr(facets), ptr(_i32(facet_els)), ptr(_i32(el_vtx)),
+                                      ptr(_f64(vtx_xyz)), order, float(coef), int(hpow), ptr(out)))
+    return out
+
+
+# ---------------------------------------------------------------- (e) sparse assembly
+class CsrPlan:
+    def __init__(self, ctx, handle, nnz, ndof, nb):
+        self.ctx, self.h, self.nnz, self.ndof, self.nb = ctx, handle, nnz, ndof, nb
+
+    def __del__(self):
+        try:
+            if self.h:
+                self.ctx.lib.xgpu_plan_destroy(self.h)
+                self.h = None
+        except Exception:
+            pass
+
+
+def _batches(batches):
+    arr = (Batch * len(batches))()
+    for i, (table, mats) in enumerate(batches):
+        arr[i].table = ptr(_i32(table))
+        arr[i].mats = ptr(mats) if mats is not None else None
+        arr[i].nrows = table.shape[0]
+        arr[i].width = table.shape[1]
+    return arr
+
+
+def csr_plan(ndof, tables, ctx=None):
+    ctx = ctx or default_ctx()
+    arr = _batches([(t, None) for t in tables])
+    h = _lib.VP()
+    nnz = C.c_int64(0)
+    ctx.check(ctx.lib.xgpu_csr_plan(ctx.h, ndof, arr, len(tables), C.byref(h), C.byref(nnz)))
+    return CsrPlan(ctx, h, nnz.value, ndof, len(tables))
+
+
+def csr_pattern(plan, device):
+    rowptr = torch.empty(plan.ndof + 1, dtype=torch.int64, device=device)
+    col = torch.empty(plan.nnz, dtype=torch.int32, device=device)
+    plan.ctx.check(plan.ctx.lib.xgpu_csr_pattern(plan.ctx.h, plan.h, ptr(rowptr), ptr(col)))
+    return rowptr, col
+
+
+def csr_scatter(plan, batches, rowptr, col, vals=None):
+    if vals is None:
+        vals = torch.zeros(plan.nnz, dtype=torch.float64, device=rowptr.device)
+    arr = _batches(batches)
+    plan.ctx.check(plan.ctx.lib.xgpu_csr_scatter(plan.ctx.h, plan.h, arr, len(batches), ptr(rowptr), ptr(col), ptr(vals)))
+    return vals
+
+
+def csr_spmv(rowptr, col, vals, x, ctx=None):
+    ctx = ctx or default_ctx()
+    y = torch.empty(rowptr.numel() - 1, dtype=torch.float64, device=x.device)
+    ctx.check(ctx.lib.xgpu_csr_spmv(ctx.h, y.numel(), ptr(rowptr), ptr(col), ptr(vals), ptr(_f64(x)), ptr(y)))
+    return y
