@@ -1,0 +1,154 @@
+"""The config-2 hot path as ONE host-side call sequence (BASELINE.json configs[1]):
+
+    ci   = CutInfo(mesh, lsetp1)                                   xfem/cutinfo.cpp:61-133
+    Vh   = Restrict(H1(mesh, order=p), ci.GetElementsOfType(HASNEG)) utils/restrictedfespace.cpp:23-73
+    a    = RestrictedBilinearForm(Vh, element_restriction=hasneg)   utils/restrictedblf.cpp:142-163
+    a   += (grad(u)*grad(v) + u*v) * dCut(lsetp1, NEG, definedonelements=hasneg)
+    a   += u*v * dCut(lsetp1, IF, definedonelements=ci.GetElementsOfType(IF))
+    a.Assemble()                                                   xfem/symboliccutbfi.cpp:76-486
+
+`CutAssembly.step()` runs exactly that through the C ABI (ngsxfem_b200.ops) on device-resident
+inputs; `step_host()` runs it from pinned HOST buffers with the host<->device copies inside
+(the e2e leg of bench.py).  Used by bench.py, __graft_entry__.smoke() and the parity tests.
+"""
+import torch
+
+from . import ops
+from ._lib import default_ctx
+
+TERMS_VOL = [(ops.OP_GRAD, ops.OP_GRAD, 1.0, 0), (ops.OP_ID, ops.OP_ID, 1.0, 0)]
+TERMS_IF = [(ops.OP_ID, ops.OP_ID, 1.0, 0)]
+
+
+class PhaseTimer:
+    """CUDA-event stopwatch per phase on the current stream (the stream the kernels run on)."""
+
+    def __init__(self, enabled=True):
+        self.enabled = enabled
+        self.marks = []
+
+    def mark(self, name):
+        if self.enabled:
+            ev = torch.cuda.Event(enable_timing=True)
+            ev.record()
+            self.marks.append((name, ev))
+
+    def result(self):
+        """{phase: ms}; call after a synchronize"""
+        out = {}
+        for (n0, e0), (n1, e1) in zip(self.marks[:-1], self.marks[1:]):
+            out[n1] = out.get(n1, 0.0) + e0.elapsed_time(e1)
+        return out
+
+
+class CutAssembly:
+    """device-resident mesh / space tables + one assembly pass"""
+
+    def __init__(self, dim, el_vtx, vtx_xyz, el_dofs, ndof_full, fe_order, ctx=None):
+        self.dim, self.p = dim, fe_order
+        self.el_vtx, self.vtx_xyz, self.el_dofs, self.ndof_full = el_vtx, vtx_xyz, el_dofs, int(ndof_full)
+        self.ne = el_vtx.shape[0]
+        self.dev = el_vtx.device
+        self.ctx = ctx or default_ctx(self.dev.index)
+        self.nd = ops.h1_ndof(dim, fe_order)
+
+    def step(self, phi, timer=None, keep=False):
+        """one pass of the hot path; returns a dict with the CSR matrix and the unit counts"""
+        t = timer or PhaseTimer(False)
+        ctx, dim, p, ne = self.ctx, self.dim, self.p, self.ne
+        els, xyz = self.el_vtx, self.vtx_xyz
+        t.mark("start")
+        # (a) CutInfo.Update
+        bn, bp, bi, cr = ops.classify(dim, els, phi, ctx=ctx)
+        t.mark("classify")
+        has = ops.bitset_op(ops.BIT_OR, bn, bi, ne, ctx=ctx)
+        l_neg = ops.bitset_to_list(bn, ne, ctx=ctx)
+        l_if = ops.bitset_to_list(bi, ne, ctx=ctx)
+        t.mark("lists")
+        # Restrict(H1, hasneg): active dofs, compressed numbering, dof rows of the two batches
+        act = ops.dofs_of_elements(self.el_dofs, has, self.ndof_full, ctx=ctx)
+        dofmap, ndof = ops.bitset_rank(act, self.ndof_full, ctx=ctx)
+        t_neg = ops.gather_rows(self.el_dofs, l_neg, dofmap, ctx=ctx)
+        t_if = ops.gather_rows(self.el_dofs, l_if, dofmap, ctx=ctx)
+        t.mark("restrict")
+        order = 2 * p  # symboliccutbfi.cpp:100-118 (ID*ID present: min diff order 0)
+        # (c) uncut NEG elements: shared standard rule
+        m_neg = ops.elmat_std(dim, p, l_neg, els, xyz, phi, order, TERMS_VOL, ctx=ctx)
+        t.mark("elmat_uncut")
+        # (b) cut quadrature + (c) cut element matrices: NEG part, then the IF integrator added
+        off, q, w = ops.cutquad(dim, l_if, els, xyz, phi, ops.NEG, order, ctx=ctx)
+        t.mark("cutquad")
+        m_if = ops.elmat_rule(dim, p, l_if, els, xyz, phi, off, q, w, TERMS_VOL, ctx=ctx)
+        t.mark("elmat_cut")
+        off2, q2, w2 = ops.cutquad(dim, l_if, els, xyz, phi, ops.IF, order, ctx=ctx)
+        t.mark("cutquad")
+        ops.elmat_rule(dim, p, l_if, els, xyz, phi, off2, q2, w2, TERMS_IF, out=m_if, accumulate=True, ctx=ctx)
+        t.mark("elmat_cut")
+        ctx.raise_on_geometry_error()
+        # (e) graph + scatter
+        tables = [t_neg, t_if]
+        plan = ops.csr_plan(ndof, tables, ctx=ctx)
+        t.mark("csr_plan")
+        rowptr, col = ops.csr_pattern(plan, self.dev)
+        t.mark("csr_pattern")
+        vals = ops.csr_scatter(plan, [(t_neg, m_neg), (t_if, m_if)], rowptr, col)
+        t.mark("csr_scatter")
+        out = dict(ndof=ndof, nnz=plan.nnz, n_neg=l_neg.numel(), n_if=l_if.numel(),
+                   units=l_neg.numel() + l_if.numel(), rowptr=rowptr, col=col, vals=vals,
+                   bits=(bn, bp, bi), cut_ratio=cr, npts=(w.numel(), w2.numel()))
+        if keep:
+            out.update(l_neg=l_neg, l_if=l_if, t_neg=t_neg, t_if=t_if, m_neg=m_neg, m_if=m_if)
+        return out
+
+
+class HostBuffers:
+    """pinned host copies of the inputs and pinned landing buffers for the outputs (e2e leg)"""
+
+    def __init__(self, el_vtx, vtx_xyz, el_dofs, phi):
+        self.el_vtx = el_vtx.cpu().pin_memory()
+        self.vtx_xyz = vtx_xyz.cpu().pin_memory()
+        self.el_dofs = el_dofs.cpu().pin_memory()
+        self.phi = phi.cpu().pin_memory()
+        self.out = {}
+
+    def h2d_bytes(self):
+        return sum(t.numel() * t.element_size() for t in (self.el_vtx, self.vtx_xyz, self.el_dofs, self.phi))
+
+    def land(self, name, t):
+        """device tensor -> pinned host buffer (grown on demand); returns bytes copied"""
+        buf = self.out.get(name)
+        if buf is None or buf.numel() < t.numel() or buf.dtype != t.dtype:
+            buf = torch.empty(int(t.numel() * 1.05) + 16, dtype=t.dtype).pin_memory()
+            self.out[name] = buf
+        buf[:t.numel()].copy_(t.reshape(-1), non_blocking=True)
+        return t.numel() * t.element_size()
+
+
+def step_host(hb, dim, ndof_full, fe_order, device, ctx=None):
+    """the same pass starting from HOST buffers: H2D of every input, assembly, D2H of the CutInfo
+    BitArrays / cut ratios and of the CSR matrix.  returns (result dict, h2d bytes, d2h bytes)"""
+    els = hb.el_vtx.to(device, non_blocking=True)
+    xyz = hb.vtx_xyz.to(device, non_blocking=True)
+    eld = hb.el_dofs.to(device, non_blocking=True)
+    phi = hb.phi.to(device, non_blocking=True)
+    prob = CutAssembly(dim, els, xyz, eld, ndof_full, fe_order, ctx=ctx)
+    r = prob.step(phi)
+    d2h = 0
+    for i, b in enumerate(r["bits"]):
+        d2h += hb.land(f"bits{i}", b)
+    d2h += hb.land("cut_ratio", r["cut_ratio"])
+    d2h += hb.land("rowptr", r["rowptr"])
+    d2h += hb.land("col", r["col"])
+    d2h += hb.land("vals", r["vals"])
+    torch.cuda.current_stream().synchronize()
+    return r, hb.h2d_bytes(), d2h
+
+
+def sphere_levelset(points, centers, radius, eps=1e-14):
+    """nodal P1 values of min_k |x - c_k| - r with the InterpolateToP1 perturbation
+    (utils/p1interpol.cpp:105-107: |v| < eps -> +eps)"""
+    phi = None
+    for c in centers:
+        d = torch.sqrt(sum((points[:, i] - c[i]) ** 2 for i in range(points.shape[1]))) - radius
+        phi = d if phi is None else torch.minimum(phi, d)
+    return torch.where(phi.abs() < eps, torch.full_like(phi, eps), phi).contiguous()

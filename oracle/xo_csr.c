@@ -14,6 +14,18 @@ static int cmp_i32(const void* a, const void* b)
   return (x > y) - (x < y);
 }
 
+/* ascending sort of a short candidate list: binary insertion for short rows, qsort otherwise */
+static void sort_i32(int32_t* a, int64_t n)
+{
+  if (n > 256) { qsort(a, n, sizeof(int32_t), cmp_i32); return; }
+  for (int64_t i = 1; i < n; i++) {
+    int32_t key = a[i];
+    int64_t j = i - 1;
+    while (j >= 0 && a[j] > key) { a[j + 1] = a[j]; j--; }
+    a[j + 1] = key;
+  }
+}
+
 int64_t xo_graph(int64_t ndof, int64_t nrows, int width, const int32_t* table,
                  int64_t* rowptr, int32_t* colidx)
 {
@@ -27,23 +39,33 @@ int64_t xo_graph(int64_t ndof, int64_t nrows, int width, const int32_t* table,
   int64_t* adj = (int64_t*)malloc(sizeof(int64_t) * (cnt[ndof] > 0 ? cnt[ndof] : 1));
   for (int64_t r = 0; r < nrows; r++)
     for (int k = 0; k < width; k++) { int32_t d = table[r * width + k]; if (d >= 0) adj[pos[d]++] = r; }
-  int32_t* buf = NULL;
-  int64_t bufcap = 0, nnz = 0;
+  /* rows are independent: pass 0 counts the unique columns of every row, pass 1 writes them
+   * (the result does not depend on the thread count) */
   rowptr[0] = 0;
-  for (int64_t d = 0; d < ndof; d++) {
-    int64_t need = (cnt[d + 1] - cnt[d]) * width;
-    if (need > bufcap) { bufcap = need * 2 + 64; buf = (int32_t*)realloc(buf, sizeof(int32_t) * bufcap); }
-    int64_t m = 0;
-    for (int64_t a = cnt[d]; a < cnt[d + 1]; a++)
-      for (int k = 0; k < width; k++) { int32_t c = table[adj[a] * width + k]; if (c >= 0) buf[m++] = c; }
-    qsort(buf, m, sizeof(int32_t), cmp_i32);
-    int64_t u = 0;
-    for (int64_t i = 0; i < m; i++) if (i == 0 || buf[i] != buf[i - 1]) { if (colidx) colidx[nnz + u] = buf[i]; u++; }
-    nnz += u;
-    rowptr[d + 1] = nnz;
+  for (int pass = 0; pass < (colidx ? 2 : 1); pass++) {
+#pragma omp parallel
+    {
+      int32_t* buf = NULL;
+      int64_t bufcap = 0;
+#pragma omp for schedule(static)
+      for (int64_t d = 0; d < ndof; d++) {
+        int64_t need = (cnt[d + 1] - cnt[d]) * width;
+        if (need > bufcap) { bufcap = need * 2 + 64; buf = (int32_t*)realloc(buf, sizeof(int32_t) * bufcap); }
+        int64_t m = 0;
+        for (int64_t a = cnt[d]; a < cnt[d + 1]; a++)
+          for (int k = 0; k < width; k++) { int32_t c = table[adj[a] * width + k]; if (c >= 0) buf[m++] = c; }
+        sort_i32(buf, m);
+        int64_t u = 0;
+        for (int64_t i = 0; i < m; i++)
+          if (i == 0 || buf[i] != buf[i - 1]) { if (pass == 1) colidx[rowptr[d] + u] = buf[i]; u++; }
+        if (pass == 0) rowptr[d + 1] = u;
+      }
+      free(buf);
+    }
+    if (pass == 0) for (int64_t d = 0; d < ndof; d++) rowptr[d + 1] += rowptr[d];
   }
-  free(buf); free(adj); free(pos); free(cnt);
-  return nnz;
+  free(adj); free(pos); free(cnt);
+  return rowptr[ndof];
 }
 
 void xo_scatter(int64_t ndof, int64_t nrows, int width, const int32_t* table, const double* mats,
@@ -60,6 +82,32 @@ void xo_scatter(int64_t ndof, int64_t nrows, int width, const int32_t* table, co
         if (dn[j] < 0) continue;
         int64_t lo = lo0, hi = hi0;
         while (lo < hi) { int64_t mid = (lo + hi) / 2; if (colidx[mid] < dn[j]) lo = mid + 1; else hi = mid; }
+        vals[lo] += m[i * width + j];
+      }
+    }
+  }
+}
+
+/* the same scatter with the table rows distributed over the host threads (atomic adds): the
+ * summation order is not fixed, so this variant is used for CPU baseline TIMING only — the
+ * checker is the serial xo_scatter above.  (NGSolve itself assembles in parallel, by element
+ * colouring.) */
+void xo_scatter_threads(int64_t ndof, int64_t nrows, int width, const int32_t* table, const double* mats,
+                        const int64_t* rowptr, const int32_t* colidx, double* vals)
+{
+  (void)ndof;
+#pragma omp parallel for schedule(static)
+  for (int64_t r = 0; r < nrows; r++) {
+    const int32_t* dn = table + r * width;
+    const double* m = mats + r * (int64_t)width * width;
+    for (int i = 0; i < width; i++) {
+      if (dn[i] < 0) continue;
+      int64_t lo0 = rowptr[dn[i]], hi0 = rowptr[dn[i] + 1];
+      for (int j = 0; j < width; j++) {
+        if (dn[j] < 0) continue;
+        int64_t lo = lo0, hi = hi0;
+        while (lo < hi) { int64_t mid = (lo + hi) / 2; if (colidx[mid] < dn[j]) lo = mid + 1; else hi = mid; }
+#pragma omp atomic
         vals[lo] += m[i * width + j];
       }
     }

@@ -17,70 +17,73 @@
 #include <string.h>
 #include "xo_rule_tables.inc"
 
-/* Jacobi polynomial P_n^{(a,0)}(x) and derivative by the three-term recurrence */
-static void jacobi_a0(int n, double a, double x, double* P, double* dP)
+/* Jacobi polynomial P_n^{(a,0)}(x) and derivative by the three-term recurrence.
+ * Extended precision: the weight formula 1/((1-x^2) P'^2) amplifies root errors near the
+ * end points, and rule weights enter every parity comparison at 1e-13. */
+typedef long double xo_ld;
+static void jacobi_a0(int n, xo_ld a, xo_ld x, xo_ld* P, xo_ld* dP)
 {
-  double p0 = 1.0, p1 = 0.5 * (a + (a + 2.0) * x);
-  double d0 = 0.0, d1 = 0.5 * (a + 2.0);
+  xo_ld p0 = 1.0L, p1 = 0.5L * (a + (a + 2.0L) * x);
+  xo_ld d0 = 0.0L, d1 = 0.5L * (a + 2.0L);
   if (n == 0) { *P = p0; *dP = d0; return; }
   for (int k = 2; k <= n; k++) {
-    double kk = k, b = 0.0;
-    double c1 = 2.0 * kk * (kk + a + b) * (2.0 * kk + a + b - 2.0);
-    double c2 = (2.0 * kk + a + b - 1.0) * (a * a - b * b);
-    double c3 = (2.0 * kk + a + b - 1.0) * (2.0 * kk + a + b) * (2.0 * kk + a + b - 2.0);
-    double c4 = 2.0 * (kk + a - 1.0) * (kk + b - 1.0) * (2.0 * kk + a + b);
-    double p2 = ((c2 + c3 * x) * p1 - c4 * p0) / c1;
-    double d2 = ((c2 + c3 * x) * d1 + c3 * p1 - c4 * d0) / c1;
+    xo_ld kk = k, b = 0.0L;
+    xo_ld c1 = 2.0L * kk * (kk + a + b) * (2.0L * kk + a + b - 2.0L);
+    xo_ld c2 = (2.0L * kk + a + b - 1.0L) * (a * a - b * b);
+    xo_ld c3 = (2.0L * kk + a + b - 1.0L) * (2.0L * kk + a + b) * (2.0L * kk + a + b - 2.0L);
+    xo_ld c4 = 2.0L * (kk + a - 1.0L) * (kk + b - 1.0L) * (2.0L * kk + a + b);
+    xo_ld p2 = ((c2 + c3 * x) * p1 - c4 * p0) / c1;
+    xo_ld d2 = ((c2 + c3 * x) * d1 + c3 * p1 - c4 * d0) / c1;
     p0 = p1; p1 = p2; d0 = d1; d1 = d2;
   }
   *P = p1; *dP = d1;
 }
 
 /* roots of P_n^{(a,0)} by interlacing brackets + safeguarded Newton */
-static void jacobi_roots(int n, double a, double* r)
+static void jacobi_roots(int n, xo_ld a, xo_ld* r)
 {
-  double prev[64], cur[64];
+  xo_ld prev[64], cur[64];
   int np = 0;
   for (int m = 1; m <= n; m++) {
     for (int i = 0; i < m; i++) {
-      double lo = (i == 0) ? -1.0 : prev[i - 1];
-      double hi = (i == m - 1) ? 1.0 : prev[i];
-      double flo, fhi, d;
+      xo_ld lo = (i == 0) ? -1.0L : prev[i - 1];
+      xo_ld hi = (i == m - 1) ? 1.0L : prev[i];
+      xo_ld flo, fhi, d;
       jacobi_a0(m, a, lo, &flo, &d);
       jacobi_a0(m, a, hi, &fhi, &d);
-      double x = 0.5 * (lo + hi);
+      xo_ld x = 0.5L * (lo + hi);
       for (int it = 0; it < 200; it++) {
-        double f, df;
+        xo_ld f, df;
         jacobi_a0(m, a, x, &f, &df);
-        if (f == 0.0) break;
+        if (f == 0.0L) break;
         if ((f < 0) == (flo < 0)) { lo = x; flo = f; } else { hi = x; fhi = f; }
-        double xn = x - f / df;
-        if (!(xn > lo && xn < hi)) xn = 0.5 * (lo + hi);
-        if (fabs(xn - x) < 1e-17 * (1.0 + fabs(x))) { x = xn; break; }
+        xo_ld xn = x - f / df;
+        if (!(xn > lo && xn < hi)) xn = 0.5L * (lo + hi);
+        if (fabsl(xn - x) < 1e-20L * (1.0L + fabsl(x))) { x = xn; break; }
         x = xn;
       }
       /* two polishing Newton steps */
-      for (int it = 0; it < 2; it++) { double f, df; jacobi_a0(m, a, x, &f, &df); x -= f / df; }
+      for (int it = 0; it < 2; it++) { xo_ld f, df; jacobi_a0(m, a, x, &f, &df); x -= f / df; }
       cur[i] = x;
     }
     np = m;
-    memcpy(prev, cur, sizeof(double) * np);
+    memcpy(prev, cur, sizeof(xo_ld) * np);
   }
-  memcpy(r, prev, sizeof(double) * n);
+  memcpy(r, prev, sizeof(xo_ld) * n);
 }
 
 void xo_gauss_jacobi01(int n, int alpha, double* x, double* w)
 {
-  double r[64];
-  double a = (double)alpha;
+  xo_ld r[64];
+  xo_ld a = (xo_ld)alpha;
   jacobi_roots(n, a, r);
   for (int i = 0; i < n; i++) {
-    double P, dP;
+    xo_ld P, dP;
     jacobi_a0(n, a, r[i], &P, &dP);
-    /* weight on [-1,1] for (1-x)^a: 2^{a+1}/((1-x^2) P'^2) (b = 0, integer a) */
-    double wi = pow(2.0, a + 1.0) / ((1.0 - r[i] * r[i]) * dP * dP);
-    x[i] = 0.5 * (1.0 + r[i]);
-    w[i] = wi / pow(2.0, a + 1.0);
+    /* weight on [-1,1] for (1-x)^a: 2^{a+1}/((1-x^2) P'^2) (b = 0, integer a); mapped to
+     * [0,1] with weight (1-x)^a the factor 2^{a+1} cancels */
+    x[i] = (double)(0.5L * (1.0L + r[i]));
+    w[i] = (double)(1.0L / ((1.0L - r[i] * r[i]) * dP * dP));
   }
 }
 

@@ -147,6 +147,9 @@ int64_t xo_graph(int64_t ndof, int64_t nrows, int width, const int32_t* table,
 /* vals += scatter of `mats` (nrows x width x width) by table rows (AddElementMatrix) */
 void xo_scatter(int64_t ndof, int64_t nrows, int width, const int32_t* table, const double* mats,
                 const int64_t* rowptr, const int32_t* colidx, double* vals);
+/* timing-only variant: table rows spread over the host threads, atomic adds (order not fixed) */
+void xo_scatter_threads(int64_t ndof, int64_t nrows, int width, const int32_t* table, const double* mats,
+                        const int64_t* rowptr, const int32_t* colidx, double* vals);
 
 #ifdef __cplusplus
 }

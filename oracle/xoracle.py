@@ -242,11 +242,14 @@ def graph(ndof, table):
     return rowptr, col
 
 
-def scatter(ndof, table, mats, rowptr, col, vals=None):
+def scatter(ndof, table, mats, rowptr, col, vals=None, threads=False):
+    """threads=True: timing-only variant (atomic adds over the host threads, order not fixed)"""
     t = _i32(table); m = _f64(mats)
     if vals is None:
         vals = np.zeros(len(col))
-    lib().xo_scatter(C.c_int64(ndof), C.c_int64(t.shape[0]), t.shape[1], _p(t, C.c_int32), _p(m),
+    fn = lib().xo_scatter_threads if threads else lib().xo_scatter
+    fn.restype = None
+    fn(C.c_int64(ndof), C.c_int64(t.shape[0]), t.shape[1], _p(t, C.c_int32), _p(m),
                      _p(rowptr, C.c_int64), _p(col, C.c_int32), _p(vals))
     return vals
 
