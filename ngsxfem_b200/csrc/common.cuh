@@ -9,6 +9,7 @@
 #include "../../include/xgpu.h"
 
 #define XGPU_NSM 148  // B200: 2 dies x 74 SMs
+#define XGPU_NSCRATCH 12
 
 struct xgpu_rule_host {
   int n = 0;
@@ -27,8 +28,9 @@ struct xgpu_ctx {
   int* d_status = nullptr;               // 2 ints
   unsigned long long* d_status_elem = nullptr;
   // grow-only scratch arena (slots by index so independent temporaries do not alias)
-  void* scratch[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-  size_t scratch_bytes[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  void* scratch[XGPU_NSCRATCH] = {};
+  size_t scratch_bytes[XGPU_NSCRATCH] = {};
+  int64_t epoch = 0;  // bumped whenever a plan takes over the shared pattern scratch (slot 8)
   int64_t* h_pinned = nullptr;  // 16 x int64 pinned staging for host scalars
   std::map<std::pair<int, int>, xgpu_rule_host> rules;  // (dim, order) -> rule
   std::map<int, void*> reftensors;                     // cached reference tensors (device)
@@ -56,16 +58,19 @@ inline int xgpu_fail(xgpu_ctx* ctx, int code, const char* msg)
     XGPU_CUDA(ctx, cudaGetLastError()); \
   } while (0)
 
+// Device memory of the library comes from the device's stream-ordered pool (cudaMallocAsync):
+// xgpu_create raises the pool's release threshold so freed blocks stay cached, which makes the
+// per-assembly plan buffers (hundreds of MB, sizes known only after a device-side count) cost
+// microseconds instead of the ~5 ms a cudaMalloc/cudaFree pair costs.
 inline int xgpu_scratch(xgpu_ctx* ctx, int slot, size_t bytes, void** out)
 {
   if (bytes > ctx->scratch_bytes[slot]) {
     if (ctx->scratch[slot]) {
-      XGPU_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-      XGPU_CUDA(ctx, cudaFree(ctx->scratch[slot]));
+      XGPU_CUDA(ctx, cudaFreeAsync(ctx->scratch[slot], ctx->stream));
       ctx->scratch[slot] = nullptr; ctx->scratch_bytes[slot] = 0;
     }
     size_t want = bytes + bytes / 8 + 256;
-    XGPU_CUDA(ctx, cudaMalloc(&ctx->scratch[slot], want));
+    XGPU_CUDA(ctx, cudaMallocAsync(&ctx->scratch[slot], want, ctx->stream));
     ctx->scratch_bytes[slot] = want;
   }
   *out = ctx->scratch[slot];

@@ -3,19 +3,28 @@
 //  SparseMatrix::AddElementMatrix.)
 //
 // The reference scatters element by element with a binary search per entry (and relies on
-// element colouring for thread safety).  Here assembly is a ROW-WISE GATHER:
+// element colouring for thread safety).  Here assembly is a ROW-WISE GATHER, one warp per
+// matrix row, everything staged in shared memory:
 //   plan    : transposed table  dof -> [(table row, local index)], built by histogram + scan +
 //             atomic-cursor fill, then each segment is sorted so the order is deterministic.
-//   pattern : one warp per matrix row gathers the dofs of all adjacent table rows into shared
-//             memory, bitonic-sorts, uniques: "union of cliques, ascending columns, explicit
-//             zeros kept" — bit-exact pattern.  Count pass -> scan -> fill pass.
-//   scatter : one warp per matrix row, each lane owns nonzeros of the row and sums the matching
-//             element-matrix entries in (batch, row) order: no atomics, bit-reproducible.
+//             Then ONE pattern pass: the warp inserts the dofs of all adjacent table rows into a
+//             shared-memory hash set (duplicates vanish, ~60 % of the candidates), compacts it and
+//             rank-sorts the survivors (all distinct -> rank = #smaller) straight into a candidate-
+//             offset scratch; a scan of the unique counts gives rowptr.
+//             "union of cliques, ascending columns, explicit zeros kept" — bit-exact pattern.
+//   pattern : compaction of the scratch rows into the caller's colidx (pure copy).
+//   scatter : the warp stages the row's columns and FP64 accumulators in shared memory, walks the
+//             sorted adjacency, reads each element-matrix row exactly once (contiguous w doubles),
+//             finds the column slot by binary search in shared memory and adds in (batch, table
+//             row, local index) order: no atomics, bit-reproducible, every matrix entry is read
+//             once and every value written once (write-only: no memset of vals needed).
 // All kernels are HBM/L2-gather bound; algorithmic bytes are stated in DESIGN.md.
 #include "common.cuh"
+#include <algorithm>
 #include <vector>
 
 #define XG_MAXBATCH 8
+#define XG_EMPTY 0x7fffffff
 
 struct BatchDev {
   int nb;
@@ -26,13 +35,16 @@ struct BatchDev {
 };
 
 struct xgpu_plan {
-  int64_t ndof = 0, nadj = 0, nnz = 0;
-  int maxcand = 0;
+  int64_t ndof = 0, nadj = 0, nnz = 0, ncand = 0;
+  int maxcand = 0, maxnr = 0, wmax = 0, dups = 0;
+  int64_t epoch = -1;             // ctx->epoch at which the pattern scratch (slot 8) was filled
   BatchDev bd;
   long long* adj_ptr = nullptr;   // ndof+1
   long long* adj = nullptr;       // nadj entries: (global table row << 8) | local index
   long long* rowptr = nullptr;    // ndof+1
-  int32_t* tmp32 = nullptr;       // ndof+1 counters
+  long long* candoff = nullptr;   // ndof+1: offsets of the rows in the candidate scratch
+  int32_t* tmp32 = nullptr;       // ndof+2 counters
+  cudaStream_t stream = 0;        // the buffers are stream-ordered allocations on this stream
 };
 
 namespace {
@@ -67,13 +79,14 @@ __global__ void k_adj_fill(const int32_t* __restrict__ table, int64_t nent, int 
   adj[adj_ptr[d] + pos] = ((rowoff + r) << 8) | (long long)loc;
 }
 
-// sort every adjacency segment ascending (insertion sort, segments are short) and compute the
-// candidate count of each row = sum of the widths of the adjacent table rows
+// sort every adjacency segment ascending (insertion sort, segments are short), compute the
+// candidate count of each row = sum of the widths of the adjacent table rows, and note whether
+// any dof occurs twice inside one table row (facet-patch rows [dofs(el1) ; dofs(el2)] do)
 __global__ void k_adj_sort(int64_t ndof, const long long* __restrict__ adj_ptr, long long* __restrict__ adj,
-                           BatchDev bd, int32_t* __restrict__ cand, int* __restrict__ maxcand)
+                           BatchDev bd, int32_t* __restrict__ cand, int* __restrict__ stats)
 {
   const int64_t d = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  int c = 0;
+  int c = 0, dup = 0;
   if (d < ndof) {
     const long long a = adj_ptr[d], b = adj_ptr[d + 1];
     for (long long i = a + 1; i < b; i++) {
@@ -82,116 +95,210 @@ __global__ void k_adj_sort(int64_t ndof, const long long* __restrict__ adj_ptr, 
       while (j >= a && adj[j] > key) { adj[j + 1] = adj[j]; j--; }
       adj[j + 1] = key;
     }
-    for (long long i = a; i < b; i++) c += bd.width[find_batch(bd, adj[i] >> 8)];
+    long long prev = -1;
+    for (long long i = a; i < b; i++) {
+      const long long g = adj[i] >> 8;
+      dup |= (g == prev);
+      prev = g;
+      c += bd.width[find_batch(bd, g)];
+    }
     cand[d] = c;
   }
   for (int s = 16; s > 0; s >>= 1) c = max(c, __shfl_down_sync(0xffffffffu, c, s));
-  if ((threadIdx.x & 31) == 0 && c > 0) atomicMax(maxcand, c);
+  dup = __any_sync(0xffffffffu, dup);
+  if ((threadIdx.x & 31) == 0) {
+    if (c > 0) atomicMax(stats, c);
+    if (dup) atomicOr(stats + 1, 1);
+  }
 }
 
-// gather + sort + unique of one row's candidate columns; returns #unique (valid in all lanes).
-// buf: CAP ints of shared memory owned by this warp.
-__device__ __forceinline__ int row_unique(int64_t d, const long long* __restrict__ adj_ptr,
-                                          const long long* __restrict__ adj, const BatchDev& bd, int* buf, int lane)
-{
-  const long long a = adj_ptr[d], b = adj_ptr[d + 1];
-  int m = 0;
-  long long prev = -1;
-  for (long long i = a; i < b; i++) {
-    const long long grow = adj[i] >> 8;
-    if (grow == prev) continue;  // the same table row twice (a dof repeated inside one row)
-    prev = grow;
-    const int bi = find_batch(bd, grow);
-    const int w = bd.width[bi];
-    const int32_t* row = bd.table[bi] + (grow - bd.rowoff[bi]) * w;
-    for (int k = lane; k < w; k += 32) {
-      const int32_t c = __ldg(row + k);
-      buf[m + k] = (c >= 0) ? c : 0x7fffffff;
-    }
-    m += w;
-  }
-  int P = 32;
-  while (P < m) P <<= 1;
-  for (int k = m + lane; k < P; k += 32) buf[k] = 0x7fffffff;
-  __syncwarp();
-  for (int size = 2; size <= P; size <<= 1)
-    for (int stride = size >> 1; stride > 0; stride >>= 1) {
-      for (int t = lane; t < (P >> 1); t += 32) {
-        const int lo = 2 * t - (t & (stride - 1));
-        const int hi = lo + stride;
-        const bool up = ((lo & size) == 0);
-        const int x = buf[lo], y = buf[hi];
-        if ((x > y) == up) { buf[lo] = y; buf[hi] = x; }
-      }
-      __syncwarp();
-    }
-  // unique (in place compaction, ascending): count and positions by ballot prefix
-  int nuniq = 0;
-  for (int base = 0; base < P; base += 32) {
-    const int k = base + lane;
-    const int x = buf[k];
-    const bool keep = (x != 0x7fffffff) && (k == 0 || buf[k - 1] != x);
-    __syncwarp();
-    const unsigned bal = __ballot_sync(0xffffffffu, keep);
-    if (keep) buf[nuniq + __popc(bal & ((1u << lane) - 1u))] = x;  // nuniq + rank <= k: safe
-    nuniq += __popc(bal);
-    __syncwarp();
-  }
-  return nuniq;
-}
-
-template <bool FILL>
-__global__ void __launch_bounds__(128) k_pattern(int64_t ndof, const long long* __restrict__ adj_ptr,
-                                                 const long long* __restrict__ adj, BatchDev bd, int CAP,
-                                                 int32_t* __restrict__ rowcnt, const long long* __restrict__ rowptr,
-                                                 int32_t* __restrict__ colidx)
+// ---- one pattern pass: hash-set dedupe + rank sort, one warp per matrix row
+__global__ void __launch_bounds__(256) k_pattern(int64_t ndof, const long long* __restrict__ adj_ptr,
+                                                 const long long* __restrict__ adj, BatchDev bd, int HCAP, int SL, int G,
+                                                 int trips, const long long* __restrict__ candoff,
+                                                 int32_t* __restrict__ tmpcol, int32_t* __restrict__ rowcnt,
+                                                 int* __restrict__ stats)
 {
   extern __shared__ int sbuf[];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-  int* buf = sbuf + (size_t)wib * CAP;
+  int* tab = sbuf + (size_t)wib * (HCAP + 4);
   const int64_t warp0 = (int64_t)blockIdx.x * (blockDim.x >> 5) + wib;
   const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
+  const int g = lane / SL, ls = lane - g * SL;
+  int mymax = 0;
   for (int64_t d = warp0; d < ndof; d += nwarps) {
-    const int nu = row_unique(d, adj_ptr, adj, bd, buf, lane);
-    if (!FILL) { if (lane == 0) rowcnt[d] = nu; }
-    else {
-      const long long o = rowptr[d];
-      for (int k = lane; k < nu; k += 32) colidx[o + k] = buf[k];
+    const long long o = candoff[d];
+    const int cand = (int)(candoff[d + 1] - o);
+    if (cand == 0) { if (lane == 0) rowcnt[d] = 0; continue; }
+    int H = 64, shift = 26;
+    while (H < 2 * cand) { H <<= 1; shift--; }
+    for (int k = lane; k < H; k += 32) tab[k] = XG_EMPTY;
+    __syncwarp();
+    const long long a = adj_ptr[d], b = adj_ptr[d + 1];
+    for (long long t0 = a; t0 < b; t0 += G) {
+      const long long t = t0 + g;
+      if (g < G && t < b) {
+        const long long grow = adj[t] >> 8;
+        if (t == a || (adj[t - 1] >> 8) != grow) {  // the same table row twice: insert once
+          const int bi = find_batch(bd, grow);
+          const int w = bd.width[bi];
+          const int32_t* row = bd.table[bi] + (grow - bd.rowoff[bi]) * w;
+          for (int lj = ls; lj < w; lj += SL) {
+            const int c = __ldg(row + lj);
+            if (c >= 0) {
+              unsigned h = ((unsigned)c * 2654435761u) >> shift;
+              while (true) {
+                const int old = atomicCAS(&tab[h], XG_EMPTY, c);
+                if (old == XG_EMPTY || old == c) break;
+                h = (h + 1) & (H - 1);
+              }
+            }
+          }
+        }
+      }
+    }
+    __syncwarp();
+    // in-place compaction of the occupied slots (write index <= read index)
+    int nu = 0;
+    for (int base = 0; base < H; base += 32) {
+      const int x = tab[base + lane];
+      const bool keep = (x != XG_EMPTY);
+      __syncwarp();
+      const unsigned bal = __ballot_sync(0xffffffffu, keep);
+      if (keep) tab[nu + __popc(bal & ((1u << lane) - 1u))] = x;
+      nu += __popc(bal);
+      __syncwarp();
+    }
+    if (lane == 0) rowcnt[d] = nu;
+    mymax = max(mymax, nu);
+    if (nu <= 128) {
+      // rank sort: all values distinct, rank = number of smaller values (broadcast reads)
+      if (lane < 4) tab[nu + lane] = XG_EMPTY;  // pad for the int4 reads (slots exist: HCAP + 4)
+      __syncwarp();
+      int x[4], r[4];
+#pragma unroll
+      for (int k = 0; k < 4; k++) { const int i = lane + 32 * k; x[k] = (i < nu) ? tab[i] : XG_EMPTY; r[k] = 0; }
+      for (int j = 0; j < nu; j += 4) {
+        const int4 v = *reinterpret_cast<const int4*>(tab + j);
+#pragma unroll
+        for (int k = 0; k < 4; k++) r[k] += (v.x < x[k]) + (v.y < x[k]) + (v.z < x[k]) + (v.w < x[k]);
+      }
+#pragma unroll
+      for (int k = 0; k < 4; k++) if (lane + 32 * k < nu) tmpcol[o + r[k]] = x[k];
+    } else {
+      int P = 256;
+      while (P < nu) P <<= 1;
+      for (int k = nu + lane; k < P; k += 32) tab[k] = XG_EMPTY;  // P <= H <= HCAP (nu <= cand <= H/2)
+      __syncwarp();
+      for (int size = 2; size <= P; size <<= 1)
+        for (int stride = size >> 1; stride > 0; stride >>= 1) {
+          for (int t = lane; t < (P >> 1); t += 32) {
+            const int lo = 2 * t - (t & (stride - 1));
+            const int hi = lo + stride;
+            const bool up = ((lo & size) == 0);
+            const int xa = tab[lo], xb = tab[hi];
+            if ((xa > xb) == up) { tab[lo] = xb; tab[hi] = xa; }
+          }
+          __syncwarp();
+        }
+      for (int k = lane; k < nu; k += 32) tmpcol[o + k] = tab[k];
     }
     __syncwarp();
   }
+  for (int s = 16; s > 0; s >>= 1) mymax = max(mymax, __shfl_down_sync(0xffffffffu, mymax, s));
+  if (lane == 0 && mymax > 0) atomicMax(stats + 2, mymax);
 }
 
-// row-wise gather of the element matrices (see header comment)
-__global__ void __launch_bounds__(256) k_scatter(int64_t ndof, const long long* __restrict__ adj_ptr,
-                                                 const long long* __restrict__ adj, BatchDev bd,
-                                                 const long long* __restrict__ rowptr, const int32_t* __restrict__ colidx,
-                                                 double* __restrict__ vals)
+// copy the unique columns of every row from the candidate-offset scratch to the final CSR
+__global__ void __launch_bounds__(256) k_compact(int64_t ndof, const long long* __restrict__ candoff,
+                                                 const long long* __restrict__ rowptr, const int32_t* __restrict__ tmpcol,
+                                                 int32_t* __restrict__ colidx)
 {
   const int lane = threadIdx.x & 31;
   const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
   for (int64_t d = warp0; d < ndof; d += nwarps) {
-    const long long r0 = rowptr[d], r1 = rowptr[d + 1];
+    const long long r0 = rowptr[d];
+    const int nr = (int)(rowptr[d + 1] - r0);
+    const long long o = candoff[d];
+    for (int k = lane; k < nr; k += 32) colidx[r0 + k] = tmpcol[o + k];
+  }
+}
+
+// row-wise gather of the element matrices (see header comment)
+template <bool DUPS>
+__global__ void __launch_bounds__(256) k_scatter(int64_t ndof, const long long* __restrict__ adj_ptr,
+                                                 const long long* __restrict__ adj, BatchDev bd, int RCAP, int SL, int G,
+                                                 int trips, const long long* __restrict__ rowptr,
+                                                 const int32_t* __restrict__ colidx, double* __restrict__ vals)
+{
+  extern __shared__ double sacc[];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, nwb = blockDim.x >> 5;
+  double* acc = sacc + (size_t)wib * RCAP;
+  int* cols = reinterpret_cast<int*>(sacc + (size_t)nwb * RCAP) + (size_t)wib * RCAP;
+  const int64_t warp0 = (int64_t)blockIdx.x * nwb + wib;
+  const int64_t nwarps = (int64_t)gridDim.x * nwb;
+  const int g = lane / SL, ls = lane - g * SL;
+  for (int64_t d = warp0; d < ndof; d += nwarps) {
+    const long long r0 = rowptr[d];
+    const int nr = (int)(rowptr[d + 1] - r0);
+    if (nr == 0) continue;
+    for (int k = lane; k < nr; k += 32) { cols[k] = __ldg(colidx + r0 + k); acc[k] = 0.0; }
+    __syncwarp();
     const long long a = adj_ptr[d], b = adj_ptr[d + 1];
-    for (long long cb = r0; cb < r1; cb += 32) {
-      const long long k = cb + lane;
-      const int32_t mycol = (k < r1) ? __ldg(colidx + k) : -2;
-      double acc = 0.0;
-      for (long long i = a; i < b; i++) {
-        const long long e = adj[i];
+    for (long long t0 = a; t0 < b; t0 += G) {
+      const long long t = t0 + g;
+      int w = 0;
+      const int32_t* row = nullptr;
+      const double* mrow = nullptr;
+      if (g < G && t < b) {
+        const long long e = adj[t];
         const long long grow = e >> 8;
         const int li = (int)(e & 255);
         const int bi = find_batch(bd, grow);
-        const int w = bd.width[bi];
         const long long lr = grow - bd.rowoff[bi];
-        const int32_t* row = bd.table[bi] + lr * w;
-        const double* mrow = bd.mats[bi] + ((size_t)lr * w + li) * w;
-        for (int lj = 0; lj < w; lj++)
-          if (__ldg(row + lj) == mycol) acc += __ldg(mrow + lj);
+        if (bd.mats[bi]) {  // a batch without matrices only contributes sparsity (explicit zeros)
+          w = bd.width[bi];
+          row = bd.table[bi] + lr * w;
+          mrow = bd.mats[bi] + ((size_t)lr * w + li) * w;
+        }
       }
-      if (k < r1) vals[k] += acc;
+      for (int it = 0; it < trips; it++) {
+        const int lj = it * SL + ls;
+        int pos = -1;
+        double m = 0.0;
+        if (lj < w) {
+          const int c = __ldg(row + lj);
+          if (c >= 0) {
+            m = __ldg(mrow + lj);
+            int lo = 0, hi = nr;
+            while (lo < hi) { const int mid = (lo + hi) >> 1; if (cols[mid] < c) lo = mid + 1; else hi = mid; }
+            pos = (lo < nr && cols[lo] == c) ? lo : -1;
+          }
+        }
+        // ordered adds: entry by entry (ascending adjacency), so the summation order is fixed
+        for (int gg = 0; gg < G; gg++) {
+          const bool mine = (g == gg) && (pos >= 0);
+          if (DUPS) {
+            // a dof may occur twice in one table row: sum the duplicates in lane order, leader adds
+            const unsigned peers = __match_any_sync(0xffffffffu, mine ? pos : (-1 - lane));
+            unsigned rem = mine ? peers : 0u;
+            double s = 0.0;
+            while (__any_sync(0xffffffffu, rem != 0u)) {
+              const int src = rem ? (__ffs(rem) - 1) : lane;
+              const double v = __shfl_sync(0xffffffffu, m, src);
+              if (rem) { s += v; rem &= rem - 1; }
+            }
+            if (mine && lane == __ffs(peers) - 1) acc[pos] += s;
+          } else {
+            if (mine) acc[pos] += m;
+          }
+          __syncwarp();
+        }
+      }
     }
+    for (int k = lane; k < nr; k += 32) vals[r0 + k] = acc[k];
+    __syncwarp();
   }
 }
 
@@ -225,12 +332,51 @@ int fill_bd(xgpu_ctx* ctx, const xgpu_batch* bh, int nb, BatchDev& bd)
 extern "C" void xgpu_plan_destroy(xgpu_plan* p)
 {
   if (!p) return;
-  if (p->adj_ptr) cudaFree(p->adj_ptr);
-  if (p->adj) cudaFree(p->adj);
-  if (p->rowptr) cudaFree(p->rowptr);
-  if (p->tmp32) cudaFree(p->tmp32);
+  if (p->adj_ptr) cudaFreeAsync(p->adj_ptr, p->stream);
+  if (p->adj) cudaFreeAsync(p->adj, p->stream);
+  if (p->rowptr) cudaFreeAsync(p->rowptr, p->stream);
+  if (p->candoff) cudaFreeAsync(p->candoff, p->stream);
+  if (p->tmp32) cudaFreeAsync(p->tmp32, p->stream);
   delete p;
 }
+
+namespace {
+
+// lanes of a warp are split into G groups of SL slots: group g handles adjacency entry t0+g,
+// slot ls the local column lj = ls, ls+SL, ... (trips iterations) of that entry's table row
+void lane_split(int wmax, int* SL, int* G, int* trips)
+{
+  *SL = wmax <= 32 ? (wmax < 1 ? 1 : wmax) : 32;
+  *G = 32 / *SL;
+  *trips = (wmax + *SL - 1) / *SL;
+}
+
+// the pattern pass: fills the shared scratch (slot 8) with the sorted unique columns of every row
+// at the row's candidate offset, the unique counts in tmp32, the longest row in stats[2]
+int run_pattern(xgpu_ctx* ctx, xgpu_plan* P, int* stats)
+{
+  void* sp;
+  int rc = xgpu_scratch(ctx, 8, sizeof(int32_t) * (size_t)(P->ncand > 0 ? P->ncand : 1), &sp);
+  if (rc) return rc;
+  int HCAP = 64;
+  while (HCAP < 2 * P->maxcand) HCAP <<= 1;
+  int nw = 8;
+  while (nw > 1 && (size_t)nw * (HCAP + 4) * sizeof(int) > 200 * 1024) nw >>= 1;
+  const size_t sm = (size_t)nw * (HCAP + 4) * sizeof(int);
+  if (sm > 220 * 1024) return xgpu_fail(ctx, XGPU_ERR_CAPACITY, "csr: a row has too many candidate columns");
+  XGPU_CUDA(ctx, cudaFuncSetAttribute(k_pattern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+  int SL, G, trips;
+  lane_split(P->wmax, &SL, &G, &trips);
+  unsigned grid = nblk(P->ndof, nw);
+  if (grid > XGPU_NSM * 32) grid = XGPU_NSM * 32;
+  k_pattern<<<grid, nw * 32, sm, ctx->stream>>>(P->ndof, P->adj_ptr, P->adj, P->bd, HCAP, SL, G, trips, P->candoff,
+                                               (int32_t*)sp, P->tmp32, stats);
+  XGPU_LAUNCH_CHECK(ctx);
+  P->epoch = ++ctx->epoch;
+  return XGPU_OK;
+}
+
+}  // namespace
 
 extern "C" int xgpu_csr_plan(xgpu_ctx* ctx, int64_t ndof, const xgpu_batch* batches_host, int nbatches,
                              xgpu_plan** plan_out, int64_t* nnz_host)
@@ -241,12 +387,15 @@ extern "C" int xgpu_csr_plan(xgpu_ctx* ctx, int64_t ndof, const xgpu_batch* batc
   int rc = fill_bd(ctx, batches_host, nbatches, P->bd);
   if (rc) { delete P; return rc; }
   P->ndof = ndof;
+  for (int i = 0; i < nbatches; i++) P->wmax = std::max(P->wmax, batches_host[i].width);
   cudaStream_t st = ctx->stream;
+  P->stream = st;
 #define XG_TRY(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { xgpu_plan_destroy(P); return xgpu_fail(ctx, XGPU_ERR_CUDA, cudaGetErrorString(e_)); } } while (0)
 #define XG_TRYRC(call) do { int r_ = (call); if (r_) { xgpu_plan_destroy(P); return r_; } } while (0)
-  XG_TRY(cudaMalloc(&P->adj_ptr, sizeof(long long) * (ndof + 1)));
-  XG_TRY(cudaMalloc(&P->rowptr, sizeof(long long) * (ndof + 1)));
-  XG_TRY(cudaMalloc(&P->tmp32, sizeof(int32_t) * (ndof + 2)));
+  XG_TRY(cudaMallocAsync(&P->adj_ptr, sizeof(long long) * (ndof + 1), st));
+  XG_TRY(cudaMallocAsync(&P->rowptr, sizeof(long long) * (ndof + 1), st));
+  XG_TRY(cudaMallocAsync(&P->candoff, sizeof(long long) * (ndof + 1), st));
+  XG_TRY(cudaMallocAsync(&P->tmp32, sizeof(int32_t) * (ndof + 2), st));
   XG_TRY(cudaMemsetAsync(P->tmp32, 0, sizeof(int32_t) * (ndof + 2), st));
   for (int i = 0; i < nbatches; i++) {
     const int64_t nent = batches_host[i].nrows * batches_host[i].width;
@@ -258,7 +407,7 @@ extern "C" int xgpu_csr_plan(xgpu_ctx* ctx, int64_t ndof, const xgpu_batch* batc
   XG_TRY(cudaMemcpyAsync(ctx->h_pinned, P->adj_ptr + ndof, sizeof(long long), cudaMemcpyDeviceToHost, st));
   XG_TRY(cudaStreamSynchronize(st));
   P->nadj = ctx->h_pinned[0];
-  XG_TRY(cudaMalloc(&P->adj, sizeof(long long) * (P->nadj > 0 ? P->nadj : 1)));
+  XG_TRY(cudaMallocAsync(&P->adj, sizeof(long long) * (P->nadj > 0 ? P->nadj : 1), st));
   XG_TRY(cudaMemsetAsync(P->tmp32, 0, sizeof(int32_t) * (ndof + 2), st));
   for (int i = 0; i < nbatches; i++) {
     const int64_t nent = batches_host[i].nrows * batches_host[i].width;
@@ -269,32 +418,26 @@ extern "C" int xgpu_csr_plan(xgpu_ctx* ctx, int64_t ndof, const xgpu_batch* batc
   }
   void* sp;
   XG_TRYRC(xgpu_scratch(ctx, 6, 64, &sp));
-  int* d_max = (int*)sp;
-  XG_TRY(cudaMemsetAsync(d_max, 0, sizeof(int), st));
+  int* stats = (int*)sp;  // [0] max candidates of a row, [1] duplicate dofs inside a table row, [2] longest row
+  XG_TRY(cudaMemsetAsync(stats, 0, 4 * sizeof(int), st));
   if (ndof > 0) {
-    k_adj_sort<<<nblk(ndof, 128), 128, 0, st>>>(ndof, P->adj_ptr, P->adj, P->bd, P->tmp32, d_max);
+    k_adj_sort<<<nblk(ndof, 128), 128, 0, st>>>(ndof, P->adj_ptr, P->adj, P->bd, P->tmp32, stats);
     ctx->launches++;
   }
-  XG_TRY(cudaMemcpyAsync(ctx->h_pinned, d_max, sizeof(int), cudaMemcpyDeviceToHost, st));
+  XG_TRYRC(xgpu_exclusive_scan_i32(ctx, P->tmp32, ndof, (int64_t*)P->candoff));
+  XG_TRY(cudaMemcpyAsync(ctx->h_pinned, stats, 2 * sizeof(int), cudaMemcpyDeviceToHost, st));
+  XG_TRY(cudaMemcpyAsync(ctx->h_pinned + 1, P->candoff + ndof, sizeof(long long), cudaMemcpyDeviceToHost, st));
   XG_TRY(cudaStreamSynchronize(st));
-  P->maxcand = *(int*)ctx->h_pinned;
-  int CAP = 32;
-  while (CAP < P->maxcand) CAP <<= 1;
-  if (CAP > 8192) { xgpu_plan_destroy(P); return xgpu_fail(ctx, XGPU_ERR_CAPACITY, "csr: a row has more than 8192 candidate columns"); }
-  // count pass
-  if (ndof > 0) {
-    const size_t sm = sizeof(int) * 4 * CAP;
-    XG_TRY(cudaFuncSetAttribute(k_pattern<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-    unsigned grid = nblk(ndof, 4);
-    if (grid > XGPU_NSM * 16) grid = XGPU_NSM * 16;
-    k_pattern<false><<<grid, 128, sm, st>>>(ndof, P->adj_ptr, P->adj, P->bd, CAP, P->tmp32, nullptr, nullptr);
-    ctx->launches++;
-    XG_TRY(cudaGetLastError());
-  }
+  P->maxcand = ((int*)ctx->h_pinned)[0];
+  P->dups = ((int*)ctx->h_pinned)[1];
+  P->ncand = ctx->h_pinned[1];
+  if (ndof > 0) XG_TRYRC(run_pattern(ctx, P, stats));
   XG_TRYRC(xgpu_exclusive_scan_i32(ctx, P->tmp32, ndof, (int64_t*)P->rowptr));
   XG_TRY(cudaMemcpyAsync(ctx->h_pinned, P->rowptr + ndof, sizeof(long long), cudaMemcpyDeviceToHost, st));
+  XG_TRY(cudaMemcpyAsync(ctx->h_pinned + 1, stats + 2, sizeof(int), cudaMemcpyDeviceToHost, st));
   XG_TRY(cudaStreamSynchronize(st));
   P->nnz = ctx->h_pinned[0];
+  P->maxnr = ((int*)(ctx->h_pinned + 1))[0];
   if (nnz_host) *nnz_host = P->nnz;
   *plan_out = P;
   return XGPU_OK;
@@ -308,13 +451,16 @@ extern "C" int xgpu_csr_pattern(xgpu_ctx* ctx, xgpu_plan* P, int64_t* rowptr, in
   cudaStream_t st = ctx->stream;
   XGPU_CUDA(ctx, cudaMemcpyAsync(rowptr, P->rowptr, sizeof(long long) * (P->ndof + 1), cudaMemcpyDeviceToDevice, st));
   if (P->ndof == 0 || P->nnz == 0) return XGPU_OK;
-  int CAP = 32;
-  while (CAP < P->maxcand) CAP <<= 1;
-  const size_t sm = sizeof(int) * 4 * CAP;
-  XGPU_CUDA(ctx, cudaFuncSetAttribute(k_pattern<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-  unsigned grid = nblk(P->ndof, 4);
-  if (grid > XGPU_NSM * 16) grid = XGPU_NSM * 16;
-  k_pattern<true><<<grid, 128, sm, st>>>(P->ndof, P->adj_ptr, P->adj, P->bd, CAP, nullptr, P->rowptr, colidx);
+  if (P->epoch != ctx->epoch) {  // another plan has used the shared scratch since: redo the pass
+    void* sp;
+    int rc = xgpu_scratch(ctx, 6, 64, &sp);
+    if (rc) return rc;
+    rc = run_pattern(ctx, P, (int*)sp);
+    if (rc) return rc;
+  }
+  unsigned grid = nblk(P->ndof, 8);
+  if (grid > XGPU_NSM * 32) grid = XGPU_NSM * 32;
+  k_compact<<<grid, 256, 0, st>>>(P->ndof, P->candoff, P->rowptr, (const int32_t*)ctx->scratch[8], colidx);
   XGPU_LAUNCH_CHECK(ctx);
   return XGPU_OK;
 }
@@ -328,13 +474,27 @@ extern "C" int xgpu_csr_scatter(xgpu_ctx* ctx, xgpu_plan* P, const xgpu_batch* b
     if (batches_host[i].nrows != bd.rowoff[i + 1] - bd.rowoff[i] || batches_host[i].width != bd.width[i])
       return xgpu_fail(ctx, XGPU_ERR_ARG, "xgpu_csr_scatter: batches do not match the plan");
     bd.table[i] = batches_host[i].table;
-    bd.mats[i] = batches_host[i].mats;
-    if (!bd.mats[i] && batches_host[i].nrows > 0) return xgpu_fail(ctx, XGPU_ERR_ARG, "xgpu_csr_scatter: mats missing");
+    bd.mats[i] = batches_host[i].mats;  // NULL: the batch only contributes sparsity
   }
-  if (P->ndof == 0) return XGPU_OK;
-  unsigned grid = nblk(P->ndof, 8);
-  if (grid > XGPU_NSM * 16) grid = XGPU_NSM * 16;
-  k_scatter<<<grid, 256, 0, ctx->stream>>>(P->ndof, P->adj_ptr, P->adj, bd, (const long long*)rowptr, colidx, vals);
+  if (P->ndof == 0 || P->nnz == 0) return XGPU_OK;
+  const int RCAP = std::max(32, (P->maxnr + 31) & ~31);
+  int nw = 8;
+  while (nw > 1 && (size_t)nw * RCAP * 12 > 200 * 1024) nw >>= 1;
+  const size_t sm = (size_t)nw * RCAP * 12;
+  if (sm > 220 * 1024) return xgpu_fail(ctx, XGPU_ERR_CAPACITY, "csr: a row is too long for the shared-memory gather");
+  int SL, G, trips;
+  lane_split(P->wmax, &SL, &G, &trips);
+  unsigned grid = nblk(P->ndof, nw);
+  if (grid > XGPU_NSM * 32) grid = XGPU_NSM * 32;
+  if (P->dups) {
+    XGPU_CUDA(ctx, cudaFuncSetAttribute(k_scatter<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+    k_scatter<true><<<grid, nw * 32, sm, ctx->stream>>>(P->ndof, P->adj_ptr, P->adj, bd, RCAP, SL, G, trips,
+                                                        (const long long*)rowptr, colidx, vals);
+  } else {
+    XGPU_CUDA(ctx, cudaFuncSetAttribute(k_scatter<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+    k_scatter<false><<<grid, nw * 32, sm, ctx->stream>>>(P->ndof, P->adj_ptr, P->adj, bd, RCAP, SL, G, trips,
+                                                         (const long long*)rowptr, colidx, vals);
+  }
   XGPU_LAUNCH_CHECK(ctx);
   return XGPU_OK;
 }

@@ -152,6 +152,13 @@ extern "C" int xgpu_create(int device, xgpu_ctx** out)
   if (cudaSetDevice(device) != cudaSuccess) return XGPU_ERR_CUDA;
   xgpu_ctx* ctx = new xgpu_ctx();
   ctx->device = device;
+  {  // keep freed blocks of the stream-ordered pool cached (see xgpu_scratch)
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+      unsigned long long thr = ~0ull;
+      cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+    }
+  }
   if (cudaMalloc(&ctx->d_status, 2 * sizeof(int)) != cudaSuccess ||
       cudaMalloc(&ctx->d_status_elem, sizeof(unsigned long long)) != cudaSuccess ||
       cudaMallocHost(&ctx->h_pinned, 16 * sizeof(int64_t)) != cudaSuccess) {
@@ -167,7 +174,8 @@ extern "C" void xgpu_destroy(xgpu_ctx* ctx)
   if (!ctx) return;
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
-  for (int i = 0; i < 8; i++) if (ctx->scratch[i]) cudaFree(ctx->scratch[i]);
+  for (int i = 0; i < XGPU_NSCRATCH; i++) if (ctx->scratch[i]) cudaFreeAsync(ctx->scratch[i], ctx->stream);
+  cudaStreamSynchronize(ctx->stream);
   for (auto& kv : ctx->rules) { if (kv.second.d_pts) cudaFree(kv.second.d_pts); if (kv.second.d_wts) cudaFree(kv.second.d_wts); }
   for (auto& kv : ctx->reftensors) if (kv.second) cudaFree(kv.second);
   if (ctx->d_status) cudaFree(ctx->d_status);
@@ -179,6 +187,10 @@ extern "C" void xgpu_destroy(xgpu_ctx* ctx)
 extern "C" int xgpu_set_stream(xgpu_ctx* ctx, void* s)
 {
   if (!ctx) return XGPU_ERR_ARG;
+  if (ctx->stream != (cudaStream_t)s) {
+    // scratch / plan buffers are ordered on the old stream: drain it before switching
+    XGPU_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  }
   ctx->stream = (cudaStream_t)s;
   return XGPU_OK;
 }

@@ -435,7 +435,7 @@ class BilinearForm:
                 if fel.shape[0]:
                     t_g = torch.cat([self._rows(fel[:, 0].contiguous()), self._rows(fel[:, 1].contiguous())], dim=1).contiguous()
                     tables.append(t_g)
-                    mats.append(torch.zeros((t_g.shape[0], 2 * nd, 2 * nd), dtype=torch.float64, device=dev))
+                    mats.append(None)  # sparsity only
 
         plan = ops.csr_plan(sp.ndof, tables, ctx=ctx)
         rowptr, col = ops.csr_pattern(plan, dev)

@@ -319,8 +319,10 @@ def csr_pattern(plan, device):
 
 
 def csr_scatter(plan, batches, rowptr, col, vals=None):
+    """vals is OVERWRITTEN (every entry of the pattern is written once; explicit zeros kept);
+    a batch (table, None) contributes sparsity only"""
     if vals is None:
-        vals = torch.zeros(plan.nnz, dtype=torch.float64, device=rowptr.device)
+        vals = torch.empty(plan.nnz, dtype=torch.float64, device=rowptr.device)
     arr = _batches(batches)
     plan.ctx.check(plan.ctx.lib.xgpu_csr_scatter(plan.ctx.h, plan.h, arr, len(batches), ptr(rowptr), ptr(col), ptr(vals)))
     return vals
