@@ -51,12 +51,13 @@ namespace {
 
 inline unsigned nblk(int64_t n, int t) { return (unsigned)((n + t - 1) / t); }
 
-__device__ __forceinline__ int find_batch(const BatchDev& bd, long long grow)
-{
-  int b = 0;
-  while (b + 1 < bd.nb && grow >= bd.rowoff[b + 1]) b++;
-  return b;
-}
+// adjacency entry: (batch << 56) | (local table row << 8) | local index — ascending order is
+// (batch, row, local index), the summation order of the scatter
+#define XG_ADJ(bi, r, loc) (((long long)(bi) << 56) | ((long long)(r) << 8) | (long long)(loc))
+#define XG_ADJ_BATCH(e) ((int)((unsigned long long)(e) >> 56))
+#define XG_ADJ_ROW(e) ((int)(unsigned)((unsigned long long)(e) >> 8))  // rows < 2^31 per batch
+#define XG_ADJ_LOC(e) ((int)((e) & 255))
+#define XG_ADJ_ROWKEY(e) ((e) >> 8)  // (batch, row)
 
 __global__ void k_adj_count(const int32_t* __restrict__ table, int64_t nent, int32_t* __restrict__ cnt)
 {
@@ -66,7 +67,7 @@ __global__ void k_adj_count(const int32_t* __restrict__ table, int64_t nent, int
   if (d >= 0) atomicAdd(cnt + d, 1);
 }
 
-__global__ void k_adj_fill(const int32_t* __restrict__ table, int64_t nent, int width, long long rowoff,
+__global__ void k_adj_fill(const int32_t* __restrict__ table, int64_t nent, int width, int bi,
                            const long long* __restrict__ adj_ptr, int32_t* __restrict__ cursor, long long* __restrict__ adj)
 {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -76,7 +77,7 @@ __global__ void k_adj_fill(const int32_t* __restrict__ table, int64_t nent, int 
   const int64_t r = i / width;
   const int loc = (int)(i - r * width);
   const int pos = atomicAdd(cursor + d, 1);
-  adj[adj_ptr[d] + pos] = ((rowoff + r) << 8) | (long long)loc;
+  adj[adj_ptr[d] + pos] = XG_ADJ(bi, r, loc);
 }
 
 // sort every adjacency segment ascending (insertion sort, segments are short), compute the
@@ -97,10 +98,10 @@ __global__ void k_adj_sort(int64_t ndof, const long long* __restrict__ adj_ptr, 
     }
     long long prev = -1;
     for (long long i = a; i < b; i++) {
-      const long long g = adj[i] >> 8;
-      dup |= (g == prev);
-      prev = g;
-      c += bd.width[find_batch(bd, g)];
+      const long long e = adj[i];
+      dup |= (XG_ADJ_ROWKEY(e) == prev);
+      prev = XG_ADJ_ROWKEY(e);
+      c += bd.width[XG_ADJ_BATCH(e)];
     }
     cand[d] = c;
   }
@@ -112,37 +113,59 @@ __global__ void k_adj_sort(int64_t ndof, const long long* __restrict__ adj_ptr, 
   }
 }
 
+// rank sort of nu distinct values in tab (shared): K values per lane, rank = #smaller values
+template <int K>
+__device__ __forceinline__ void rank_sort_store(const int* tab, int nu, int lane, int32_t* __restrict__ out)
+{
+  int x[K], r[K];
+#pragma unroll
+  for (int k = 0; k < K; k++) { const int i = lane + 32 * k; x[k] = (i < nu) ? tab[i] : XG_EMPTY; r[k] = 0; }
+  for (int j = 0; j < nu; j += 4) {
+    const int4 v = *reinterpret_cast<const int4*>(tab + j);  // padded with XG_EMPTY (never smaller)
+#pragma unroll
+    for (int k = 0; k < K; k++) r[k] += (v.x < x[k]) + (v.y < x[k]) + (v.z < x[k]) + (v.w < x[k]);
+  }
+#pragma unroll
+  for (int k = 0; k < K; k++) if (lane + 32 * k < nu) out[r[k]] = x[k];
+}
+
 // ---- one pattern pass: hash-set dedupe + rank sort, one warp per matrix row
-__global__ void __launch_bounds__(256) k_pattern(int64_t ndof, const long long* __restrict__ adj_ptr,
+template <bool DUPS>
+__global__ void __launch_bounds__(256) k_pattern(int ndof, const long long* __restrict__ adj_ptr,
                                                  const long long* __restrict__ adj, BatchDev bd, int HCAP, int SL, int G,
-                                                 int trips, const long long* __restrict__ candoff,
+                                                 const long long* __restrict__ candoff,
                                                  int32_t* __restrict__ tmpcol, int32_t* __restrict__ rowcnt,
                                                  int* __restrict__ stats)
 {
   extern __shared__ int sbuf[];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-  int* tab = sbuf + (size_t)wib * (HCAP + 4);
-  const int64_t warp0 = (int64_t)blockIdx.x * (blockDim.x >> 5) + wib;
-  const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
+  int* tab = sbuf + wib * (HCAP + 4);
+  const int warp0 = blockIdx.x * (blockDim.x >> 5) + wib;
+  const int nwarps = gridDim.x * (blockDim.x >> 5);
   const int g = lane / SL, ls = lane - g * SL;
   int mymax = 0;
-  for (int64_t d = warp0; d < ndof; d += nwarps) {
+  for (int d = warp0; d < ndof; d += nwarps) {
     const long long o = candoff[d];
     const int cand = (int)(candoff[d + 1] - o);
     if (cand == 0) { if (lane == 0) rowcnt[d] = 0; continue; }
-    int H = 64, shift = 26;
-    while (H < 2 * cand) { H <<= 1; shift--; }
+    // table size: power of two >= 1.25 * candidates (duplicates keep the load far lower)
+    int H = 32, shift = 27;
+    while (H < cand + (cand >> 2)) { H <<= 1; shift--; }
     for (int k = lane; k < H; k += 32) tab[k] = XG_EMPTY;
     __syncwarp();
-    const long long a = adj_ptr[d], b = adj_ptr[d + 1];
-    for (long long t0 = a; t0 < b; t0 += G) {
-      const long long t = t0 + g;
-      if (g < G && t < b) {
-        const long long grow = adj[t] >> 8;
-        if (t == a || (adj[t - 1] >> 8) != grow) {  // the same table row twice: insert once
-          const int bi = find_batch(bd, grow);
+    const long long a = adj_ptr[d];
+    const int na = (int)(adj_ptr[d + 1] - a);
+    const long long* __restrict__ adjd = adj + a;
+    for (int t0 = 0; t0 < na; t0 += G) {
+      const int t = t0 + g;
+      if (g < G && t < na) {
+        const long long e = adjd[t];
+        bool fresh = true;
+        if (DUPS) fresh = (t == 0) || (XG_ADJ_ROWKEY(adjd[t - 1]) != XG_ADJ_ROWKEY(e));  // same table row twice
+        if (fresh) {
+          const int bi = XG_ADJ_BATCH(e);
           const int w = bd.width[bi];
-          const int32_t* row = bd.table[bi] + (grow - bd.rowoff[bi]) * w;
+          const int32_t* __restrict__ row = bd.table[bi] + XG_ADJ_ROW(e) * w;  // nrows*width < 2^31 (checked on the host)
           for (int lj = ls; lj < w; lj += SL) {
             const int c = __ldg(row + lj);
             if (c >= 0) {
@@ -172,23 +195,15 @@ __global__ void __launch_bounds__(256) k_pattern(int64_t ndof, const long long* 
     if (lane == 0) rowcnt[d] = nu;
     mymax = max(mymax, nu);
     if (nu <= 128) {
-      // rank sort: all values distinct, rank = number of smaller values (broadcast reads)
       if (lane < 4) tab[nu + lane] = XG_EMPTY;  // pad for the int4 reads (slots exist: HCAP + 4)
       __syncwarp();
-      int x[4], r[4];
-#pragma unroll
-      for (int k = 0; k < 4; k++) { const int i = lane + 32 * k; x[k] = (i < nu) ? tab[i] : XG_EMPTY; r[k] = 0; }
-      for (int j = 0; j < nu; j += 4) {
-        const int4 v = *reinterpret_cast<const int4*>(tab + j);
-#pragma unroll
-        for (int k = 0; k < 4; k++) r[k] += (v.x < x[k]) + (v.y < x[k]) + (v.z < x[k]) + (v.w < x[k]);
-      }
-#pragma unroll
-      for (int k = 0; k < 4; k++) if (lane + 32 * k < nu) tmpcol[o + r[k]] = x[k];
+      if (nu <= 32) rank_sort_store<1>(tab, nu, lane, tmpcol + o);
+      else if (nu <= 64) rank_sort_store<2>(tab, nu, lane, tmpcol + o);
+      else rank_sort_store<4>(tab, nu, lane, tmpcol + o);
     } else {
       int P = 256;
       while (P < nu) P <<= 1;
-      for (int k = nu + lane; k < P; k += 32) tab[k] = XG_EMPTY;  // P <= H <= HCAP (nu <= cand <= H/2)
+      for (int k = nu + lane; k < P; k += 32) tab[k] = XG_EMPTY;  // P <= HCAP (host sizes HCAP >= 2 * maxcand)
       __syncwarp();
       for (int size = 2; size <= P; size <<= 1)
         for (int stride = size >> 1; stride > 0; stride >>= 1) {
@@ -225,42 +240,55 @@ __global__ void __launch_bounds__(256) k_compact(int64_t ndof, const long long* 
   }
 }
 
-// row-wise gather of the element matrices (see header comment)
+// row-wise gather of the element matrices (see header comment).  Shared memory per warp:
+// NACC accumulator arrays of RCAP doubles (one per lane group, so the groups add without
+// ordering constraints; the arrays are summed in a fixed order at the end) + RCAP column ids
+// (RCAP is a power of two, the tail padded with INT_MAX for the branch-free search).
 template <bool DUPS>
-__global__ void __launch_bounds__(256) k_scatter(int64_t ndof, const long long* __restrict__ adj_ptr,
+__global__ void __launch_bounds__(256) k_scatter(int ndof, const long long* __restrict__ adj_ptr,
                                                  const long long* __restrict__ adj, BatchDev bd, int RCAP, int SL, int G,
                                                  int trips, const long long* __restrict__ rowptr,
                                                  const int32_t* __restrict__ colidx, double* __restrict__ vals)
 {
   extern __shared__ double sacc[];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, nwb = blockDim.x >> 5;
-  double* acc = sacc + (size_t)wib * RCAP;
-  int* cols = reinterpret_cast<int*>(sacc + (size_t)nwb * RCAP) + (size_t)wib * RCAP;
-  const int64_t warp0 = (int64_t)blockIdx.x * nwb + wib;
-  const int64_t nwarps = (int64_t)gridDim.x * nwb;
+  const int NACC = DUPS ? 1 : G;
+  double* acc = sacc + wib * NACC * RCAP;
+  int* cols = reinterpret_cast<int*>(sacc + nwb * NACC * RCAP) + wib * RCAP;
+  const int warp0 = blockIdx.x * nwb + wib;
+  const int nwarps = gridDim.x * nwb;
   const int g = lane / SL, ls = lane - g * SL;
-  for (int64_t d = warp0; d < ndof; d += nwarps) {
+  double* myacc = acc + (DUPS ? 0 : (g < G ? g : 0) * RCAP);
+  for (int d = warp0; d < ndof; d += nwarps) {
     const long long r0 = rowptr[d];
     const int nr = (int)(rowptr[d + 1] - r0);
     if (nr == 0) continue;
-    for (int k = lane; k < nr; k += 32) { cols[k] = __ldg(colidx + r0 + k); acc[k] = 0.0; }
+    int P = 32;
+    while (P < nr) P <<= 1;
+    {
+      const int32_t* __restrict__ cr = colidx + r0;
+      for (int k = lane; k < P; k += 32) {
+        cols[k] = (k < nr) ? __ldg(cr + k) : 0x7fffffff;
+        for (int q = 0; q < NACC; q++) acc[q * RCAP + k] = 0.0;
+      }
+    }
     __syncwarp();
-    const long long a = adj_ptr[d], b = adj_ptr[d + 1];
-    for (long long t0 = a; t0 < b; t0 += G) {
-      const long long t = t0 + g;
+    const long long a = adj_ptr[d];
+    const int na = (int)(adj_ptr[d + 1] - a);
+    const long long* __restrict__ adjd = adj + a;
+    for (int t0 = 0; t0 < na; t0 += G) {
+      const int t = t0 + g;
       int w = 0;
-      const int32_t* row = nullptr;
-      const double* mrow = nullptr;
-      if (g < G && t < b) {
-        const long long e = adj[t];
-        const long long grow = e >> 8;
-        const int li = (int)(e & 255);
-        const int bi = find_batch(bd, grow);
-        const long long lr = grow - bd.rowoff[bi];
+      const int32_t* __restrict__ row = nullptr;
+      const double* __restrict__ mrow = nullptr;
+      if (g < G && t < na) {
+        const long long e = adjd[t];
+        const int bi = XG_ADJ_BATCH(e);
         if (bd.mats[bi]) {  // a batch without matrices only contributes sparsity (explicit zeros)
           w = bd.width[bi];
-          row = bd.table[bi] + lr * w;
-          mrow = bd.mats[bi] + ((size_t)lr * w + li) * w;
+          const int ro = XG_ADJ_ROW(e) * w;  // nrows*width < 2^31 (checked on the host)
+          row = bd.table[bi] + ro;
+          mrow = bd.mats[bi] + (size_t)(ro + XG_ADJ_LOC(e)) * w;
         }
       }
       for (int it = 0; it < trips; it++) {
@@ -271,33 +299,38 @@ __global__ void __launch_bounds__(256) k_scatter(int64_t ndof, const long long* 
           const int c = __ldg(row + lj);
           if (c >= 0) {
             m = __ldg(mrow + lj);
-            int lo = 0, hi = nr;
-            while (lo < hi) { const int mid = (lo + hi) >> 1; if (cols[mid] < c) lo = mid + 1; else hi = mid; }
-            pos = (lo < nr && cols[lo] == c) ? lo : -1;
+            int lo = 0;  // branch-free lower bound over the padded power-of-two list
+            for (int step = P >> 1; step > 0; step >>= 1) lo += (cols[lo + step - 1] < c) ? step : 0;
+            pos = (cols[lo] == c) ? lo : -1;
           }
         }
-        // ordered adds: entry by entry (ascending adjacency), so the summation order is fixed
-        for (int gg = 0; gg < G; gg++) {
-          const bool mine = (g == gg) && (pos >= 0);
-          if (DUPS) {
-            // a dof may occur twice in one table row: sum the duplicates in lane order, leader adds
-            const unsigned peers = __match_any_sync(0xffffffffu, mine ? pos : (-1 - lane));
-            unsigned rem = mine ? peers : 0u;
-            double s = 0.0;
-            while (__any_sync(0xffffffffu, rem != 0u)) {
-              const int src = rem ? (__ffs(rem) - 1) : lane;
-              const double v = __shfl_sync(0xffffffffu, m, src);
-              if (rem) { s += v; rem &= rem - 1; }
-            }
-            if (mine && lane == __ffs(peers) - 1) acc[pos] += s;
-          } else {
-            if (mine) acc[pos] += m;
+        if (DUPS) {
+          // a dof may occur twice in one table row, and the groups share one accumulator array:
+          // lanes hitting the same slot are summed in lane order (= entry, then local index) and
+          // the first lane adds
+          const unsigned peers = __match_any_sync(0xffffffffu, pos >= 0 ? pos : (-1 - lane));
+          unsigned rem = (pos >= 0) ? peers : 0u;
+          double s = 0.0;
+          while (__any_sync(0xffffffffu, rem != 0u)) {
+            const int src = rem ? (__ffs(rem) - 1) : lane;
+            const double v = __shfl_sync(0xffffffffu, m, src);
+            if (rem) { s += v; rem &= rem - 1; }
           }
-          __syncwarp();
+          if (pos >= 0 && lane == __ffs(peers) - 1) acc[pos] += s;
+        } else {
+          if (pos >= 0) myacc[pos] += m;  // distinct dofs inside one table row: no conflict in a group
         }
+        __syncwarp();
       }
     }
-    for (int k = lane; k < nr; k += 32) vals[r0 + k] = acc[k];
+    {
+      double* __restrict__ vr = vals + r0;
+      for (int k = lane; k < nr; k += 32) {
+        double s = acc[k];
+        for (int q = 1; q < NACC; q++) s += acc[q * RCAP + k];
+        vr[k] = s;
+      }
+    }
     __syncwarp();
   }
 }
@@ -321,6 +354,7 @@ int fill_bd(xgpu_ctx* ctx, const xgpu_batch* bh, int nb, BatchDev& bd)
   bd.rowoff[0] = 0;
   for (int i = 0; i < nb; i++) {
     if (bh[i].width < 1 || bh[i].width > 255 || bh[i].nrows < 0) return xgpu_fail(ctx, XGPU_ERR_ARG, "csr: bad batch");
+    if (bh[i].nrows * bh[i].width >= (int64_t)0x7fffffff) return xgpu_fail(ctx, XGPU_ERR_CAPACITY, "csr: a batch has 2^31 or more table entries; split it");
     bd.table[i] = bh[i].table; bd.mats[i] = bh[i].mats; bd.width[i] = bh[i].width;
     bd.rowoff[i + 1] = bd.rowoff[i] + bh[i].nrows;
   }
@@ -364,13 +398,19 @@ int run_pattern(xgpu_ctx* ctx, xgpu_plan* P, int* stats)
   while (nw > 1 && (size_t)nw * (HCAP + 4) * sizeof(int) > 200 * 1024) nw >>= 1;
   const size_t sm = (size_t)nw * (HCAP + 4) * sizeof(int);
   if (sm > 220 * 1024) return xgpu_fail(ctx, XGPU_ERR_CAPACITY, "csr: a row has too many candidate columns");
-  XGPU_CUDA(ctx, cudaFuncSetAttribute(k_pattern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
   int SL, G, trips;
   lane_split(P->wmax, &SL, &G, &trips);
   unsigned grid = nblk(P->ndof, nw);
   if (grid > XGPU_NSM * 32) grid = XGPU_NSM * 32;
-  k_pattern<<<grid, nw * 32, sm, ctx->stream>>>(P->ndof, P->adj_ptr, P->adj, P->bd, HCAP, SL, G, trips, P->candoff,
-                                               (int32_t*)sp, P->tmp32, stats);
+  if (P->dups) {
+    XGPU_CUDA(ctx, cudaFuncSetAttribute(k_pattern<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+    k_pattern<true><<<grid, nw * 32, sm, ctx->stream>>>((int)P->ndof, P->adj_ptr, P->adj, P->bd, HCAP, SL, G, P->candoff,
+                                                        (int32_t*)sp, P->tmp32, stats);
+  } else {
+    XGPU_CUDA(ctx, cudaFuncSetAttribute(k_pattern<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+    k_pattern<false><<<grid, nw * 32, sm, ctx->stream>>>((int)P->ndof, P->adj_ptr, P->adj, P->bd, HCAP, SL, G, P->candoff,
+                                                         (int32_t*)sp, P->tmp32, stats);
+  }
   XGPU_LAUNCH_CHECK(ctx);
   P->epoch = ++ctx->epoch;
   return XGPU_OK;
@@ -381,7 +421,8 @@ int run_pattern(xgpu_ctx* ctx, xgpu_plan* P, int* stats)
 extern "C" int xgpu_csr_plan(xgpu_ctx* ctx, int64_t ndof, const xgpu_batch* batches_host, int nbatches,
                              xgpu_plan** plan_out, int64_t* nnz_host)
 {
-  if (!ctx || !plan_out || ndof < 0) return xgpu_fail(ctx, XGPU_ERR_ARG, "xgpu_csr_plan: bad argument");
+  if (!ctx || !plan_out || ndof < 0 || ndof >= (int64_t)0x7fffffff)
+    return xgpu_fail(ctx, XGPU_ERR_ARG, "xgpu_csr_plan: bad argument (0 <= ndof < 2^31: column indices are int32)");
   *plan_out = nullptr;
   xgpu_plan* P = new xgpu_plan();
   int rc = fill_bd(ctx, batches_host, nbatches, P->bd);
@@ -412,7 +453,7 @@ extern "C" int xgpu_csr_plan(xgpu_ctx* ctx, int64_t ndof, const xgpu_batch* batc
   for (int i = 0; i < nbatches; i++) {
     const int64_t nent = batches_host[i].nrows * batches_host[i].width;
     if (nent == 0) continue;
-    k_adj_fill<<<nblk(nent, 256), 256, 0, st>>>(batches_host[i].table, nent, batches_host[i].width, P->bd.rowoff[i],
+    k_adj_fill<<<nblk(nent, 256), 256, 0, st>>>(batches_host[i].table, nent, batches_host[i].width, i,
                                                  P->adj_ptr, P->tmp32, P->adj);
     ctx->launches++;
   }
@@ -477,22 +518,24 @@ extern "C" int xgpu_csr_scatter(xgpu_ctx* ctx, xgpu_plan* P, const xgpu_batch* b
     bd.mats[i] = batches_host[i].mats;  // NULL: the batch only contributes sparsity
   }
   if (P->ndof == 0 || P->nnz == 0) return XGPU_OK;
-  const int RCAP = std::max(32, (P->maxnr + 31) & ~31);
-  int nw = 8;
-  while (nw > 1 && (size_t)nw * RCAP * 12 > 200 * 1024) nw >>= 1;
-  const size_t sm = (size_t)nw * RCAP * 12;
-  if (sm > 220 * 1024) return xgpu_fail(ctx, XGPU_ERR_CAPACITY, "csr: a row is too long for the shared-memory gather");
+  int RCAP = 32;
+  while (RCAP < P->maxnr) RCAP <<= 1;
   int SL, G, trips;
   lane_split(P->wmax, &SL, &G, &trips);
+  const size_t per_warp = (size_t)RCAP * (8 * (P->dups ? 1 : G) + 4);
+  int nw = 8;
+  while (nw > 1 && nw * per_warp > 200 * 1024) nw >>= 1;
+  const size_t sm = nw * per_warp;
+  if (sm > 220 * 1024) return xgpu_fail(ctx, XGPU_ERR_CAPACITY, "csr: a row is too long for the shared-memory gather");
   unsigned grid = nblk(P->ndof, nw);
   if (grid > XGPU_NSM * 32) grid = XGPU_NSM * 32;
   if (P->dups) {
     XGPU_CUDA(ctx, cudaFuncSetAttribute(k_scatter<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-    k_scatter<true><<<grid, nw * 32, sm, ctx->stream>>>(P->ndof, P->adj_ptr, P->adj, bd, RCAP, SL, G, trips,
+    k_scatter<true><<<grid, nw * 32, sm, ctx->stream>>>((int)P->ndof, P->adj_ptr, P->adj, bd, RCAP, SL, G, trips,
                                                         (const long long*)rowptr, colidx, vals);
   } else {
     XGPU_CUDA(ctx, cudaFuncSetAttribute(k_scatter<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-    k_scatter<false><<<grid, nw * 32, sm, ctx->stream>>>(P->ndof, P->adj_ptr, P->adj, bd, RCAP, SL, G, trips,
+    k_scatter<false><<<grid, nw * 32, sm, ctx->stream>>>((int)P->ndof, P->adj_ptr, P->adj, bd, RCAP, SL, G, trips,
                                                          (const long long*)rowptr, colidx, vals);
   }
   XGPU_LAUNCH_CHECK(ctx);
