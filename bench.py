@@ -132,6 +132,10 @@ class ClockSampler:
 # algorithmic bytes per unit of the candidate dominant kernels (DESIGN.md "Kernels")
 def kernel_bytes(phase, r, nd):
     nn = nd * nd
+    if phase == "csr":           # distributed path: plan + pattern + scatter timed as one phase
+        return sum(kernel_bytes(k, r, nd) for k in ("csr_plan", "csr_pattern", "csr_scatter"))
+    if phase == "elmat":
+        return kernel_bytes("elmat_uncut", r, nd) + kernel_bytes("elmat_cut", r, nd)
     if phase == "csr_scatter":   # read every element matrix once + dof rows, write vals, read colidx/rowptr
         return r["units"] * (nn * 8 + nd * 4) + r["nnz"] * (8 + 4) + r["ndof"] * 8
     if phase == "csr_pattern":   # read dof rows (through the adjacency), write colidx + rowptr
@@ -168,11 +172,38 @@ def run_gpu(args):
     # ---- synthetic inputs (not timed).  N>1: every rank owns one unit-cube slab of the chain
     # [0,1]^2 x [0,N] with its own sphere (weak scaling; element ranges are contiguous per rank)
     n = args.n
-    mesh = xf.MakeStructured3DMesh(nx=n, device=dev)
-    V0 = xf.H1(mesh, order=2)
-    phi = sphere_levelset(mesh.points, [(.5, .5, .5)], 0.4)
-    prob = CutAssembly(3, mesh.elements, mesh.points, V0.el_dofs, V0.ndof, 2, ctx=ctx)
-    hb = HostBuffers(mesh.elements, mesh.points, V0.el_dofs, phi)
+    nd = 10
+    if world == 1:
+        mesh = xf.MakeStructured3DMesh(nx=n, device=dev)
+        V0 = xf.H1(mesh, order=2)
+        phi = sphere_levelset(mesh.points, [(.5, .5, .5)], 0.4)
+        prob = CutAssembly(3, mesh.elements, mesh.points, V0.el_dofs, V0.ndof, 2, ctx=ctx)
+        hb = HostBuffers(mesh.elements, mesh.points, V0.el_dofs, phi)
+        step_dev = lambda t: prob.step(phi, timer=t)
+
+        def step_e2e():
+            return step_host(hb, 3, V0.ndof, 2, dev, ctx=ctx)
+    else:
+        # element-partitioned chain of `world` unit cubes, one per rank, halo layer + NCCL interface merge
+        import copy
+        from ngsxfem_b200.distributed import DistributedCutAssembly, GpuBackend, make_slab_partition
+        part, phi = make_slab_partition(n, world, rank, dev, fe_order=2)
+        asm = DistributedCutAssembly(part, GpuBackend(ctx), rank, world)
+        hb = HostBuffers(part.el_vtx, part.vtx_xyz, part.el_dofs, phi)
+        step_dev = lambda t: asm.step(phi, timer=t)
+
+        def step_e2e():
+            p2 = copy.copy(part)
+            p2.el_vtx = hb.el_vtx.to(dev, non_blocking=True)
+            p2.vtx_xyz = hb.vtx_xyz.to(dev, non_blocking=True)
+            p2.el_dofs = hb.el_dofs.to(dev, non_blocking=True)
+            ph = hb.phi.to(dev, non_blocking=True)
+            r = DistributedCutAssembly(p2, asm.be, rank, world).step(ph)
+            d2h = sum(hb.land(f"bits{i}", b) for i, b in enumerate(r["cls"][:3])) + hb.land("cut_ratio", r["cls"][3])
+            rows_g, rp, cols_g, vals = DistributedCutAssembly.owned_rows_global(r)
+            d2h += hb.land("rows", rows_g) + hb.land("rowptr", rp) + hb.land("col", cols_g) + hb.land("vals", vals)
+            torch.cuda.current_stream().synchronize()
+            return r, hb.h2d_bytes(), d2h
     torch.cuda.synchronize()
 
     def barrier():
@@ -202,7 +233,7 @@ def run_gpu(args):
 
     steps, warmup = args.steps, max(3, args.warmup)
     with ClockSampler(local) as cs:
-        ms, res, timers, launches = timed_loop(lambda t: prob.step(phi, timer=t), steps, warmup)
+        ms, res, timers, launches = timed_loop(step_dev, steps, warmup)
     clocks = cs.summary()
     units = res["units"]
     # phase shares (CUDA events on the launching stream, inside the timed steps)
@@ -210,7 +241,10 @@ def run_gpu(args):
     for t in timers:
         for k, v in t.result().items():
             phases[k] = phases.get(k, 0.0) + v / steps
-    dom = max((k for k in phases if kernel_bytes(k, res, prob.nd)), key=lambda k: phases[k])
+    if "npts" not in res:
+        res["npts"] = (0, 0)
+        res["ndof"] = res["ndof_local"]
+    dom = max((k for k in phases if kernel_bytes(k, res, nd)), key=lambda k: phases[k])
     del res["vals"], res["col"], res["rowptr"]
     torch.cuda.empty_cache()
 
@@ -219,7 +253,7 @@ def run_gpu(args):
     info = {}
 
     def e2e_fn(_):
-        r, h2d, d2h = step_host(hb, 3, V0.ndof, 2, dev, ctx=ctx)
+        r, h2d, d2h = step_e2e()
         info.update(h2d=h2d, d2h=d2h)
         return r
     ms_e2e, _, _, _ = timed_loop(e2e_fn, e2e_steps, 1)
@@ -237,7 +271,7 @@ def run_gpu(args):
             pass
         peak = float(peaks.get("hbm_gbs", 6650.0))
         peak_src = "MEASURED_PEAKS.json hbm_gbs (of measured)" if "hbm_gbs" in peaks else "6650 GB/s (of fallback)"
-        kb = kernel_bytes(dom, res, prob.nd)
+        kb = kernel_bytes(dom, res, nd)
         ach = kb / (phases[dom] * 1e-3) / 1e9
         cpu_val, cores, cinfo = cpu_sample(SAMPLE_N, 2, 1)
         sample = f"same workload at n={SAMPLE_N} ({6 * SAMPLE_N ** 3} tets, {cinfo['units_per_step']} matrices per step), 2 timed passes"
@@ -245,7 +279,9 @@ def run_gpu(args):
             "metric": METRIC, "value": tot_units * steps / (ms * 1e-3), "unit": UNIT, "n_gpus": world,
             "steps": steps, "warmup": warmup, "ms_per_step": ms / steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": workload_name(n), "units_per_step_per_gpu": units, "n_neg": res["n_neg"], "n_if": res["n_if"],
+            "config": {"workload": workload_name(n) + ("" if world == 1 else f"; x{world} ranks: chain of {world} unit cubes, "
+                       "spheres centred on the slab interfaces (same per-rank element counts), halo layer + NCCL interface-row merge"),
+                       "units_per_step_per_gpu": units, "n_neg": res["n_neg"], "n_if": res["n_if"],
                        "ndof": res["ndof"], "nnz": res["nnz"], "cut_points": list(res["npts"]),
                        "l2_policy": "inputs+outputs of a step (>5 GB) exceed the 126 MB L2; no flush needed",
                        "phases_ms": {k: round(v, 4) for k, v in phases.items()}},

@@ -1,0 +1,311 @@
+"""Element-partitioned cut assembly over several GPUs (north_star: "elements are
+partitioned by contiguous index ranges across the GPUs of one box, and the per-rank CSR pieces are
+merged with NCCL over NVLink only at the final interface-row reduction").
+
+One process per GPU (`torch.distributed`, backend nccl; gloo on CPU for the host-logic tests).
+Each rank holds a LOCAL mesh = its own contiguous element range followed by one layer of HALO
+elements of its neighbours (connectivity / level set only: halo element matrices are never
+computed here).  Every local dof carries a global key `gid` (any total order that all ranks
+agree on) and an `owner` rank.
+
+Per assembly:
+  1. classify all local elements (own + halo)                      [compute backend]
+  2. `mark`: OR the activity of shared dofs with the neighbours — the reference's
+     `AllReduceNodalData(…, MPI_LOR)` (xfem/cutinfo.cpp:194-199).  With a complete halo layer this is
+     already implied locally (a dof shared with a neighbour is touched by that neighbour's halo
+     elements), so no message is needed.
+  3. number the active local dofs by (owner, gid): every rank sees shared dofs in the same relative
+     order, hence the rows of an interface dof have IDENTICAL column order on both sides
+  4. element matrices of the OWN active elements                    [compute backend]
+  5. local CSR over own batches + the halo batch as sparsity only (mats = NULL), so the owner's
+     pattern of an interface row is already final ("union of cliques" over both sides)
+  6. interface-row reduction: for each neighbour q, the values of the rows {owner == q, touched by
+     my own elements} are packed and sent (P2P send/recv over NVLink), the owner adds them into
+     its rows in a fixed order (lower rank first) — the only data-path communication
+  7. global numbering: offset[owner] + index among the owner's active dofs; ghost columns get their
+     global ids from the owner (one int message per neighbour)
+The result is a row-distributed CSR (rows = owned dofs) with global column ids.
+
+The compute backend is duck-typed (`classify`, `elmats`, `csr`): `GpuBackend` below drives the
+CUDA kernels through the C ABI; the CPU gloo tests inject a checker backend built on the oracle.
+"""
+import torch
+import torch.distributed as dist
+
+
+# ------------------------------------------------------------------ helpers (torch plumbing, CPU or CUDA)
+def _excl_cumsum(x):
+    c = torch.cumsum(x, 0)
+    return c - x
+
+
+def row_positions(rowptr, rows):
+    """flat positions in vals of the listed CSR rows (row after row)"""
+    rows = rows.long()
+    start = rowptr[rows]
+    ln = rowptr[rows + 1] - start
+    tot = int(ln.sum().item()) if rows.numel() else 0
+    if tot == 0:
+        return torch.zeros(0, dtype=torch.int64, device=rowptr.device), ln
+    off = _excl_cumsum(ln)
+    idx = torch.repeat_interleave(start - off, ln) + torch.arange(tot, device=rowptr.device)
+    return idx, ln
+
+
+class LocalPartition:
+    """inputs of one rank (all tensors on the rank's device):
+    el_vtx (ne_loc x D+1 int32, own elements first), ne_own, el_rank (ne_loc int32: owning rank of
+    every local element), vtx_xyz, el_dofs (ne_loc x nd int32, local dof ids), ndof_loc,
+    gid (ndof_loc int64 global key), owner (ndof_loc int32), halo_for {q: int32 list of OWN elements
+    that rank q holds as halo}.
+
+    The constructor renumbers the local dofs ONCE into (owner, gid) order, so that per assembly the
+    compressed numbering of the active dofs is the plain ascending compression of the single-GPU
+    path (Restrict), dofs of one owner form a contiguous range, and the small static interface
+    tables below can be prepared up front."""
+
+    def __init__(self, dim, el_vtx, ne_own, el_rank, vtx_xyz, el_dofs, ndof_loc, gid, owner, halo_for, fe_order, rank):
+        self.dim, self.el_vtx, self.ne_own, self.el_rank, self.vtx_xyz = dim, el_vtx, int(ne_own), el_rank, vtx_xyz
+        self.ndof_loc, self.fe_order, self.rank = int(ndof_loc), fe_order, rank
+        self.neighbors = sorted(halo_for.keys())
+        dev = el_vtx.device
+        assert int(gid.max().item()) < (1 << 52)
+        key = (owner.to(torch.int64) << 52) | gid
+        order = torch.argsort(key)                       # old local dof ids in key order
+        inv = torch.empty_like(order)
+        inv[order] = torch.arange(order.numel(), device=dev)
+        self.el_dofs = inv[el_dofs.long()].to(torch.int32).contiguous()   # key-order dof ids
+        self.gid, self.owner = gid[order].contiguous(), owner[order].contiguous()
+        # contiguous static dof range per owner
+        ow = self.owner.to(torch.int64)
+        self.range_of = {}
+        for q in [rank] + self.neighbors:
+            idx = torch.nonzero(ow == q).reshape(-1)
+            self.range_of[q] = (int(idx[0].item()), int(idx[-1].item()) + 1) if idx.numel() else (0, 0)
+        # static interface tables per neighbour q
+        self.iface = {}
+        for q in self.neighbors:
+            E = halo_for[q].long()                                        # my elements that q holds as halo
+            H = torch.nonzero(el_rank.to(torch.int64) == q).reshape(-1)     # my halo elements owned by q
+            TE, TH = self.el_dofs[E].long(), self.el_dofs[H].long()
+            ent = {"E": E, "H": H}
+            # candidate rows I send to q: dofs owned by q among the dofs of my elements E
+            ent["C_send"], ent["pos_send"] = self._candidates(TE, ow, q)
+            # candidate dofs owned by me that q can see / contribute to
+            D, pos = self._candidates(torch.cat([TE, TH]), ow, rank)
+            ent["D"], ent["posE"], ent["posH"] = D, pos[:TE.shape[0]], pos[TE.shape[0]:]
+            self.iface[q] = ent
+
+    @staticmethod
+    def _candidates(T, ow, q):
+        """sorted unique dofs of table T owned by q, and for every entry of T its position in that list (-1)"""
+        m = ow[T] == q
+        C = torch.unique(T[m])                           # ascending = key order
+        pos = torch.full(T.shape, -1, dtype=torch.int64, device=T.device)
+        pos[m] = torch.searchsorted(C, T[m])
+        return C, pos
+
+
+def _marked(pos_rows, n):
+    """flags over a candidate list: positions hit by the given (active) table rows"""
+    f = torch.zeros(n, dtype=torch.bool, device=pos_rows.device)
+    v = pos_rows.reshape(-1)
+    f[v[v >= 0]] = True
+    return f
+
+
+class DistributedCutAssembly:
+    def __init__(self, part, backend, rank, world, group=None):
+        self.part, self.be, self.rank, self.world, self.group = part, backend, rank, world, group
+
+    # ---- communication primitives (P2P; lower rank sends first to avoid deadlock with blocking gloo)
+    def _exchange(self, q, send_t, recv_t):
+        if self.rank < q:
+            dist.send(send_t, q, group=self.group)
+            dist.recv(recv_t, q, group=self.group)
+        else:
+            dist.recv(recv_t, q, group=self.group)
+            dist.send(send_t, q, group=self.group)
+
+    def step(self, phi, timer=None):
+        p, be, r = self.part, self.be, self.rank
+        dev = p.el_vtx.device
+        mark = timer.mark if timer is not None else (lambda name: None)
+        mark("start")
+        # 1. classification of own + halo elements; own elements come first, lists are ascending
+        l_neg, l_if, cls = be.classify(p.el_vtx, phi)
+        mark("classify")
+        kn = int(torch.searchsorted(l_neg, p.ne_own).item())
+        ki = int(torch.searchsorted(l_if, p.ne_own).item())
+        l_neg_own, l_if_own = l_neg[:kn], l_if[:ki]
+        l_halo = torch.cat([l_neg[kn:], l_if[ki:]]).sort().values
+        # 2./3. active dofs of own + halo elements; dof ids are already in (owner, gid) order
+        dofmap, ndof = be.active_dofs(p, cls, l_neg, l_if)
+        a, b = p.range_of[r]
+        n_lo = int((dofmap[:a] >= 0).sum().item())
+        n_own = int((dofmap[a:b] >= 0).sum().item())
+        t_neg = be.gather_rows(p.el_dofs, l_neg_own, dofmap)
+        t_if = be.gather_rows(p.el_dofs, l_if_own, dofmap)
+        t_halo = be.gather_rows(p.el_dofs, l_halo, dofmap)
+        mark("restrict")
+        # 4. element matrices of the own active elements
+        m_neg, m_if = be.elmats(p, phi, l_neg_own, l_if_own)
+        mark("elmat")
+        # 5. local CSR; the halo batch contributes sparsity only
+        batches = [(t_neg, m_neg), (t_if, m_if), (t_halo, None)]
+        rowptr, col, vals = be.csr(ndof, [bt for bt in batches if bt[0].shape[0] > 0])
+        mark("csr")
+        # 6. interface-row reduction (small static candidate tables, see LocalPartition)
+        el_act = torch.zeros(p.el_vtx.shape[0], dtype=torch.bool, device=dev)
+        el_act[l_neg.long()] = True
+        el_act[l_if.long()] = True
+        recvs, seen = [], {}
+        for q in p.neighbors:
+            it = p.iface[q]
+            actE, actH = el_act[it["E"]], el_act[it["H"]]
+            snd = it["C_send"][_marked(it["pos_send"][actE], it["C_send"].numel())]
+            fH = _marked(it["posH"][actH], it["D"].numel())
+            rcv = it["D"][fH]
+            seen[q] = it["D"][fH | _marked(it["posE"][actE], it["D"].numel())]
+            sidx, _ = row_positions(rowptr, dofmap[snd])
+            ridx, _ = row_positions(rowptr, dofmap[rcv])
+            sbuf = vals[sidx].contiguous()
+            rbuf = torch.empty(ridx.numel(), dtype=vals.dtype, device=dev)
+            self._exchange(q, sbuf, rbuf)
+            recvs.append((q, ridx, rbuf))
+        for q, ridx, rbuf in sorted(recvs, key=lambda t: t[0]):     # fixed order: lower rank first
+            vals[ridx] += rbuf
+        mark("merge")
+        # 7. global numbering: offset[owner] + index among the owner's active dofs (ascending key)
+        counts = torch.zeros(self.world, dtype=torch.int64, device=dev)
+        counts[r] = n_own
+        if self.world > 1:
+            dist.all_reduce(counts, group=self.group)
+        offsets = _excl_cumsum(counts)
+        l2g = torch.full((ndof,), -1, dtype=torch.int64, device=dev)
+        l2g[n_lo:n_lo + n_own] = offsets[r] + torch.arange(n_own, device=dev)
+        for q in p.neighbors:
+            sbuf = l2g[dofmap[seen[q]].long()].contiguous()         # my owned dofs that q sees, key order
+            qa, qb = p.range_of[q]
+            ga = int((dofmap[:qa] >= 0).sum().item())
+            gn = int((dofmap[qa:qb] >= 0).sum().item())             # my ghosts owned by q: a contiguous range
+            rbuf = torch.empty(gn, dtype=torch.int64, device=dev)
+            self._exchange(q, sbuf, rbuf)
+            l2g[ga:ga + gn] = rbuf
+        mark("numbering")
+        return dict(ndof_local=ndof, n_lo=n_lo, n_own=n_own, rowptr=rowptr, col=col, vals=vals, l2g=l2g, dofmap=dofmap,
+                    ndof_global=int(counts.sum().item()), units=int(l_neg_own.numel() + l_if_own.numel()),
+                    n_neg=int(l_neg_own.numel()), n_if=int(l_if_own.numel()), nnz=int(col.numel()), cls=cls)
+
+    @staticmethod
+    def owned_rows_global(res):
+        """(global row ids, rowptr slice, global cols, vals) of the rows this rank owns"""
+        a, b = res["n_lo"], res["n_lo"] + res["n_own"]
+        rp = res["rowptr"]
+        lo, hi = int(rp[a].item()), int(rp[b].item())
+        return res["l2g"][a:b], rp[a:b + 1] - lo, res["l2g"][res["col"][lo:hi].long()], res["vals"][lo:hi]
+
+
+# ------------------------------------------------------------------ CUDA compute backend
+class GpuBackend:
+    """drives libxgpu.so (C ABI) — there is no CPU fallback"""
+
+    def __init__(self, ctx=None):
+        from . import ops
+        self.ops = ops
+        self.ctx = ctx or ops.default_ctx()
+
+    def classify(self, el_vtx, phi):
+        ops, ctx = self.ops, self.ctx
+        dim, ne = el_vtx.shape[1] - 1, el_vtx.shape[0]
+        bn, bp, bi, cr = ops.classify(dim, el_vtx, phi, ctx=ctx)
+        ctx.raise_on_geometry_error()
+        return ops.bitset_to_list(bn, ne, ctx=ctx), ops.bitset_to_list(bi, ne, ctx=ctx), (bn, bp, bi, cr)
+
+    def active_dofs(self, part, cls, l_neg, l_if):
+        ops, ctx = self.ops, self.ctx
+        bn, bp, bi, cr = cls
+        has = ops.bitset_op(ops.BIT_OR, bn, bi, part.el_vtx.shape[0], ctx=ctx)
+        act = ops.dofs_of_elements(part.el_dofs, has, part.ndof_loc, ctx=ctx)
+        return ops.bitset_rank(act, part.ndof_loc, ctx=ctx)
+
+    def gather_rows(self, el_dofs, lst, dofmap):
+        return self.ops.gather_rows(el_dofs, lst.contiguous(), dofmap, ctx=self.ctx)
+
+    def elmats(self, part, phi, l_neg, l_if):
+        from .pipeline import TERMS_IF, TERMS_VOL
+        ops, ctx, dim, p = self.ops, self.ctx, part.dim, part.fe_order
+        els, xyz = part.el_vtx, part.vtx_xyz
+        order = 2 * p
+        l_neg, l_if = l_neg.contiguous(), l_if.contiguous()
+        m_neg = ops.elmat_std(dim, p, l_neg, els, xyz, phi, order, TERMS_VOL, ctx=ctx)
+        off, q, w = ops.cutquad(dim, l_if, els, xyz, phi, ops.NEG, order, ctx=ctx)
+        m_if = ops.elmat_rule(dim, p, l_if, els, xyz, phi, off, q, w, TERMS_VOL, ctx=ctx)
+        off2, q2, w2 = ops.cutquad(dim, l_if, els, xyz, phi, ops.IF, order, ctx=ctx)
+        ops.elmat_rule(dim, p, l_if, els, xyz, phi, off2, q2, w2, TERMS_IF, out=m_if, accumulate=True, ctx=ctx)
+        ctx.raise_on_geometry_error()
+        return m_neg, m_if
+
+    def csr(self, ndof, batches):
+        ops = self.ops
+        tables = [b[0] for b in batches]
+        plan = ops.csr_plan(ndof, tables, ctx=self.ctx)
+        rowptr, col = ops.csr_pattern(plan, tables[0].device)
+        vals = ops.csr_scatter(plan, batches, rowptr, col)
+        return rowptr, col, vals
+
+
+# ------------------------------------------------------------------ slab partition of the structured chain (input producer)
+def make_slab_partition(n, world, rank, device, fe_order=2, radius=0.4):
+    """Chain [0,1]^2 x [0,world] of `world` unit cubes, n^3 x 6 Kuhn tets each; rank r owns cube r
+    (a contiguous element range of the global mesh) plus one halo layer of cells per neighbour.
+    Level set: spheres of `radius` centred at (1/2, 1/2, j), j = 0..world for world > 1 (centres ON
+    the slab interfaces, so the interface rows are active and each rank sees two half spheres = the
+    config-2 element counts), the centred sphere for world == 1."""
+    from . import meshes
+    from .fes import H1
+    from .pipeline import sphere_levelset
+    if fe_order > 2:
+        raise NotImplementedError("distributed numbering keys are built for vertex and edge dofs (order <= 2)")
+    lo, hi = (1 if rank > 0 else 0), (1 if rank < world - 1 else 0)
+    nzl = n + lo + hi
+    mesh = meshes.MakeStructured3DMesh(nx=n, ny=n, nz=nzl, device=device)
+    # physical coordinates: local z in [0,1] covers global cells [rank*n - lo, (rank+1)*n + hi)
+    k0 = rank * n - lo
+    pts = mesh.points.clone()
+    nv1 = n + 1
+    # z = K / n from the integer layer index K: bit-identical on every rank that holds the vertex
+    kk = torch.arange(mesh.nv, device=device, dtype=torch.int64) // (nv1 * nv1)
+    pts[:, 2] = (kk + k0).to(torch.float64) / n
+    # own elements first (cells lo .. lo+n-1), then halo
+    ne_layer = 6 * n * n
+    cell_k = torch.arange(mesh.ne, device=device) // ne_layer
+    own = (cell_k >= lo) & (cell_k < lo + n)
+    perm = torch.cat([torch.nonzero(own).reshape(-1), torch.nonzero(~own).reshape(-1)])
+    el_vtx = mesh.elements[perm].contiguous()
+    el_rank = torch.where(cell_k[perm] < lo, rank - 1, torch.where(cell_k[perm] >= lo + n, rank + 1, rank)).to(torch.int32)
+    lmesh = meshes.Mesh(pts, el_vtx)
+    V = H1(lmesh, order=fe_order)
+    # global keys: vertex gid = i + (n+1)(j + (n+1)K); edge key from its two global vertex ids
+    vloc = torch.arange(lmesh.nv, device=device, dtype=torch.int64)
+    K = vloc // (nv1 * nv1) + k0
+    vg = vloc % (nv1 * nv1) + nv1 * nv1 * K
+    NV = nv1 * nv1 * (n * world + 1)
+    v_owner = torch.where(K <= 0, torch.zeros_like(K), (K + n - 1) // n - 1).clamp(max=world - 1)
+    gid, owner = [vg], [v_owner]
+    if fe_order == 2:
+        ev, _ = lmesh.edges()
+        a, b = vg[ev[:, 0].long()], vg[ev[:, 1].long()]
+        gid.append(NV + torch.minimum(a, b) * NV + torch.maximum(a, b))
+        owner.append(torch.maximum(v_owner[ev[:, 0].long()], v_owner[ev[:, 1].long()]))
+    gid, owner = torch.cat(gid), torch.cat(owner).to(torch.int32)
+    halo_for = {}
+    own_cells_k = cell_k[perm][:6 * n ** 3]
+    if rank > 0:
+        halo_for[rank - 1] = torch.nonzero(own_cells_k == lo).reshape(-1).to(torch.int32)
+    if rank < world - 1:
+        halo_for[rank + 1] = torch.nonzero(own_cells_k == lo + n - 1).reshape(-1).to(torch.int32)
+    centers = [(.5, .5, .5)] if world == 1 else [(.5, .5, float(j)) for j in range(world + 1)]
+    phi = sphere_levelset(pts, centers, radius)
+    part = LocalPartition(3, el_vtx, 6 * n ** 3, el_rank, pts, V.el_dofs, V.ndof, gid, owner, halo_for, fe_order, rank)
+    return part, phi

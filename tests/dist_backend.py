@@ -1,0 +1,52 @@
+"""Checker compute backend for the distributed host logic (CPU, gloo): the same three operations
+as ngsxfem_b200.distributed.GpuBackend, served by the oracle.  Test infrastructure only."""
+import numpy as np
+import torch
+
+from oracle import xoracle as xo
+from oracle.pipeline_ref import TERMS_IF, TERMS_VOL, bits_to_list
+
+
+class OracleBackend:
+    def classify(self, el_vtx, phi):
+        els, ph = el_vtx.numpy(), phi.numpy()
+        dim, ne = els.shape[1] - 1, els.shape[0]
+        bn, bp, bi, cr, err, _ = xo.cutinfo_update(dim, els, ph)
+        assert err == 0
+        return torch.from_numpy(bits_to_list(bn, ne)), torch.from_numpy(bits_to_list(bi, ne)), (bn, bp, bi, cr)
+
+    def active_dofs(self, part, cls, l_neg, l_if):
+        act = torch.zeros(part.ndof_loc, dtype=torch.bool)
+        act[part.el_dofs[torch.cat([l_neg, l_if]).long()].reshape(-1).long()] = True
+        dofmap = torch.full((part.ndof_loc,), -1, dtype=torch.int32)
+        n = int(act.sum())
+        dofmap[act] = torch.arange(n, dtype=torch.int32)
+        return dofmap, n
+
+    def gather_rows(self, el_dofs, lst, dofmap):
+        return dofmap[el_dofs[lst.long()].long()].to(torch.int32)
+
+    def elmats(self, part, phi, l_neg, l_if):
+        els, xyz, ph = part.el_vtx.numpy(), part.vtx_xyz.numpy(), phi.numpy()
+        dim, p = part.dim, part.fe_order
+        order = 2 * p
+        ln, li = l_neg.numpy().astype(np.int32), l_if.numpy().astype(np.int32)
+        m_neg = xo.batch_cut_elmats(dim, p, ln, els, xyz, ph, xo.NEG, order, TERMS_VOL)
+        m_if = xo.batch_cut_elmats(dim, p, li, els, xyz, ph, xo.NEG, order, TERMS_VOL)
+        m_if = m_if + xo.batch_cut_elmats(dim, p, li, els, xyz, ph, xo.IF, order, TERMS_IF)
+        return torch.from_numpy(m_neg), torch.from_numpy(m_if)
+
+    def csr(self, ndof, batches):
+        W = max(t.shape[1] for t, _ in batches)
+        tabs, mats = [], []
+        for t, m in batches:
+            tn = np.full((t.shape[0], W), -1, np.int32)
+            tn[:, :t.shape[1]] = t.numpy()
+            mn = np.zeros((t.shape[0], W, W))
+            if m is not None:
+                mn[:, :t.shape[1], :t.shape[1]] = m.numpy()
+            tabs.append(tn); mats.append(mn)
+        tab, mt = np.concatenate(tabs), np.concatenate(mats)
+        rowptr, col = xo.graph(ndof, tab)
+        vals = xo.scatter(ndof, tab, mt, rowptr, col)
+        return torch.from_numpy(rowptr), torch.from_numpy(col), torch.from_numpy(vals)

@@ -1,0 +1,134 @@
+"""Multi-process host logic of the element-partitioned assembly (world_size 2 and 3, gloo on CPU):
+slab partition with halo layers, (owner, gid) numbering, interface-row exchange, global ids.
+The merged row-distributed matrix must equal the single-process assembly of the whole chain."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+for p in (ROOT, HERE):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+
+def _global_reference(n, world, fe_order):
+    """whole chain on one process through the oracle; returns dict key -> row (dict key -> value)"""
+    import ngsxfem_b200 as xf
+    from ngsxfem_b200.pipeline import sphere_levelset
+    from oracle.pipeline_ref import oracle_step
+    mesh = xf.MakeStructured3DMesh(nx=n, ny=n, nz=n * world)
+    nv1 = n + 1
+    pts = mesh.points.clone()
+    K = torch.arange(mesh.nv, dtype=torch.int64) // (nv1 * nv1)
+    pts[:, 2] = K.to(torch.float64) / n
+    gmesh = xf.Mesh(pts, mesh.elements)
+    V = xf.H1(gmesh, order=fe_order)
+    centers = [(.5, .5, .5)] if world == 1 else [(.5, .5, float(j)) for j in range(world + 1)]
+    phi = sphere_levelset(pts, centers, 0.4).numpy()
+    res, _ = oracle_step(3, gmesh.elements.numpy(), pts.numpy(), V.el_dofs.numpy(), V.ndof, fe_order, phi)
+    # keys of the global dofs (same construction as make_slab_partition)
+    NV = nv1 * nv1 * (n * world + 1)
+    gid = [torch.arange(gmesh.nv, dtype=torch.int64)]
+    if fe_order == 2:
+        ev, _ = gmesh.edges()
+        a, b = ev[:, 0].long(), ev[:, 1].long()
+        gid.append(NV + torch.minimum(a, b) * NV + torch.maximum(a, b))
+    gid = torch.cat(gid).numpy()
+    # compressed id -> key
+    act = np.zeros(V.ndof, dtype=bool)
+    els_act = np.concatenate([np.flatnonzero(np.unpackbits(res["bits"][0], bitorder="little")[:gmesh.ne]),
+                              np.flatnonzero(np.unpackbits(res["bits"][2], bitorder="little")[:gmesh.ne])])
+    act[V.el_dofs.numpy()[els_act].reshape(-1)] = True
+    keys = gid[act]
+    return res, keys
+
+
+def _worker(rank, world, n, fe_order, port, out, gpu=False):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    if gpu:
+        torch.cuda.set_device(rank)
+        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    else:
+        dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from ngsxfem_b200.distributed import DistributedCutAssembly, make_slab_partition
+        if gpu:
+            from ngsxfem_b200.distributed import GpuBackend
+            part, phi = make_slab_partition(n, world, rank, torch.device("cuda", rank), fe_order=fe_order)
+            asm = DistributedCutAssembly(part, GpuBackend(), rank, world)
+        else:
+            from dist_backend import OracleBackend
+            part, phi = make_slab_partition(n, world, rank, "cpu", fe_order=fe_order)
+            asm = DistributedCutAssembly(part, OracleBackend(), rank, world)
+        res = asm.step(phi)
+        rows_g, rp, cols_g, vals = asm.owned_rows_global(res)
+        a, b = part.range_of[rank]
+        own_ids = a + torch.nonzero(res["dofmap"][a:b] >= 0).reshape(-1)   # owned active dofs, key order
+        cpu = lambda t: t.cpu()
+        rows_g, rp, cols_g, vals, own_ids = cpu(rows_g), cpu(rp), cpu(cols_g), cpu(vals), cpu(own_ids)
+        torch.save(dict(rows=rows_g, rowptr=rp, cols=cols_g, vals=vals, keys=part.gid.cpu()[own_ids], units=res["units"],
+                        ndof_global=res["ndof_global"], n_neg=res["n_neg"], n_if=res["n_if"]),
+                   os.path.join(out, f"rank{rank}.pt"))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,n,fe_order", [(2, 4, 2), (3, 3, 2), (2, 5, 1)])
+def test_slab_partition_merge_equals_global(tmp_path, world, n, fe_order):
+    _run_and_check(tmp_path, world, n, fe_order, gpu=False)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("world,n,fe_order", [(2, 6, 2), (2, 5, 1)])
+def test_nccl_slab_partition_merge_equals_global(tmp_path, world, n, fe_order):
+    """the same check with the CUDA kernels and NCCL send/recv (needs >= 2 GPUs: gpurun --gpus 2)"""
+    if torch.cuda.device_count() < world:
+        pytest.skip("needs %d GPUs" % world)
+    _run_and_check(tmp_path, world, n, fe_order, gpu=True)
+
+
+def _run_and_check(tmp_path, world, n, fe_order, gpu):
+    port = 29500 + (os.getpid() % 2000) + world + (7 if gpu else 0)
+    mp.spawn(_worker, args=(world, n, fe_order, port, str(tmp_path), gpu), nprocs=world, join=True)
+    ref, keys = _global_reference(n, world, fe_order)
+    parts = [torch.load(os.path.join(str(tmp_path), f"rank{r}.pt")) for r in range(world)]
+    ndofg = parts[0]["ndof_global"]
+    assert ndofg == ref["ndof"] == len(keys)
+    assert sum(p["units"] for p in parts) == ref["units"]
+    if world > 1:  # weak-scaling construction: every rank sees two half spheres = the same element counts
+        assert len({(p["n_neg"], p["n_if"]) for p in parts}) == 1
+    # distributed global id -> key
+    key_of = np.zeros(ndofg, dtype=np.int64)
+    seen = np.zeros(ndofg, dtype=bool)
+    for p in parts:
+        r = p["rows"].numpy()
+        assert not seen[r].any()
+        seen[r] = True
+        key_of[r] = p["keys"].numpy()
+    assert seen.all()
+    # reference rows keyed by gid
+    ref_id_of_key = {int(k): i for i, k in enumerate(keys)}
+    rp, col, val = ref["rowptr"], ref["col"], ref["vals"]
+    nnz = 0
+    scale = np.abs(val).max()
+    for p in parts:
+        rows, prp, cols, vals = p["rows"].numpy(), p["rowptr"].numpy(), p["cols"].numpy(), p["vals"].numpy()
+        assert (cols >= 0).all()
+        for i, g in enumerate(rows):
+            ri = ref_id_of_key[int(key_of[g])]
+            c_ref = col[rp[ri]:rp[ri + 1]]
+            v_ref = val[rp[ri]:rp[ri + 1]]
+            c_d = np.array([ref_id_of_key[int(key_of[c])] for c in cols[prp[i]:prp[i + 1]]])
+            v_d = vals[prp[i]:prp[i + 1]]
+            o = np.argsort(c_d)
+            assert np.array_equal(c_d[o], c_ref), f"pattern of row {g}"
+            assert np.allclose(v_d[o], v_ref, rtol=1e-12, atol=1e-13 * scale)
+            nnz += len(c_ref)
+    assert nnz == ref["nnz"]
