@@ -273,8 +273,11 @@ def run_gpu(args):
         peak_src = "MEASURED_PEAKS.json hbm_gbs (of measured)" if "hbm_gbs" in peaks else "6650 GB/s (of fallback)"
         kb = kernel_bytes(dom, res, nd)
         ach = kb / (phases[dom] * 1e-3) / 1e9
-        cpu_val, cores, cinfo = cpu_sample(SAMPLE_N, 2, 1)
-        sample = f"same workload at n={SAMPLE_N} ({6 * SAMPLE_N ** 3} tets, {cinfo['units_per_step']} matrices per step), 2 timed passes"
+        cpu_baseline = None
+        if world == 1:  # the CPU arm is timed on rank 0 at N=1 only (other ranks would compete for the host cores)
+            cpu_val, cores, cinfo = cpu_sample(SAMPLE_N, 2, 1)
+            sample = f"same workload at n={SAMPLE_N} ({6 * SAMPLE_N ** 3} tets, {cinfo['units_per_step']} matrices per step), 2 timed passes"
+            cpu_baseline = {"value": cpu_val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample}
         line = {
             "metric": METRIC, "value": tot_units * steps / (ms * 1e-3), "unit": UNIT, "n_gpus": world,
             "steps": steps, "warmup": warmup, "ms_per_step": ms / steps, "higher_is_better": True,
@@ -291,7 +294,7 @@ def run_gpu(args):
             "roofline": {"kernel": dom, "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
                          "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": kb,
                          "ms_per_launch": phases[dom]},
-            "cpu_baseline": {"value": cpu_val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "cpu_baseline": cpu_baseline,
             "clocks": clocks,
         }
         print(json.dumps(line), flush=True)

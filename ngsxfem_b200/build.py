@@ -15,6 +15,11 @@ CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "build")
 LIB = os.path.join(HERE, "libxgpu.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+# Geometry kernels take discrete decisions (which sub-simplices survive a clamped re-evaluation,
+# straightcutrule.cpp:548-556) from floating-point values at the 1e-14 threshold; they are compiled
+# without FMA contraction so that those decisions are taken from the same IEEE operations as the
+# CPU restatement (gcc -ffp-contract=off).  The dense contraction kernels keep FMA.
+NO_FMA = {"cutquad.cu", "cutquad_ext.cu", "classify.cu"}
 FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
          "-Xcompiler", "-fPIC", "-ccbin", "/usr/bin/g++", "--expt-relaxed-constexpr"]
 
@@ -38,7 +43,8 @@ def build(force=False, verbose=False):
 
     def cc(job):
         src, obj = job
-        cmd = [NVCC] + FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", src, "-o", obj]
+        extra = ["-fmad=false"] if os.path.basename(src) in NO_FMA else []
+        cmd = [NVCC] + FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-c", src, "-o", obj]
         r = subprocess.run(cmd, capture_output=True, text=True)
         return src, r.returncode, r.stdout + r.stderr
 
