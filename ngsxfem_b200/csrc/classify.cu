@@ -61,59 +61,53 @@ __global__ void __launch_bounds__(256) k_classify(int64_t ne, const int32_t* __r
   if (valid && cut_ratio && !is_if) cut_ratio[el] = is_neg ? 1.0 : 0.0;
 }
 
+// one thread per element, only the sign-cut ones (bit set in bits_if) do work: in a warp that holds
+// a cut element the geometry runs once with the cut lanes active
 template <int D>
-__global__ void __launch_bounds__(128) k_cut_ratio(int64_t ne, const int32_t* __restrict__ el_vtx,
+__global__ void __launch_bounds__(256) k_cut_ratio(int64_t ne, const int32_t* __restrict__ el_vtx,
                                                    const double* __restrict__ phi, const double* __restrict__ w0, int nw0,
                                                    uint32_t* __restrict__ bits_neg, uint32_t* __restrict__ bits_pos,
                                                    uint32_t* __restrict__ bits_if, double* __restrict__ cut_ratio,
                                                    int* status, unsigned long long* status_elem)
 {
-  const int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const int64_t nwords = (ne + 31) >> 5;
-  if (w >= nwords) return;
-  uint32_t word = bits_if[w];
-  uint32_t clr_if = 0, set_neg = 0, set_pos = 0;
-  while (word) {
-    const int b = __ffs(word) - 1;
-    word &= word - 1;
-    const int64_t el = (w << 5) + b;
-    int v[D + 1];
-    double l[D + 1];
-    load_vtx<D>(el_vtx, el, v);
+  const int64_t el = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (el >= ne) return;
+  const int64_t w = el >> 5;
+  const uint32_t bit = 1u << (el & 31);
+  if (!(bits_if[w] & bit)) return;  // my own bit: only this thread ever changes it
+  int v[D + 1];
+  double l[D + 1];
+  load_vtx<D>(el_vtx, el, v);
 #pragma unroll
-    for (int k = 0; k < D + 1; k++) l[k] = __ldg(phi + v[k]);
-    XgSimplex ref, sub[3];
-    xg_ref_simplex(D, ref);
-    double part[2] = {0.0, 0.0};
-    int err = 0;
-    // POS first, then NEG, as cutinfo.cpp:93
-    for (int a = 0; a < 2 && !err; a++) {
-      const int np = (a == 0) ? XGPU_POS : XGPU_NEG;
-      int ns = xg_decompose(ref, l, np, sub);
-      if (ns < 0) { err = ns; break; }
-      double s = 0.0;
-      for (int i = 0; i < ns; i++) {
-        const double vol = xg_volume(sub[i]);
-        for (int q = 0; q < nw0; q++) s += w0[q] * vol;
-      }
-      part[np] = s;
+  for (int k = 0; k < D + 1; k++) l[k] = __ldg(phi + v[k]);
+  XgSimplex ref, sub[3];
+  xg_ref_simplex(D, ref);
+  double part[2] = {0.0, 0.0};
+  int err = 0;
+  // POS first, then NEG, as cutinfo.cpp:93
+  for (int a = 0; a < 2 && !err; a++) {
+    const int np = (a == 0) ? XGPU_POS : XGPU_NEG;
+    int ns = xg_decompose(ref, l, np, sub);
+    if (ns < 0) { err = ns; break; }
+    double s = 0.0;
+    for (int i = 0; i < ns; i++) {
+      const double vol = xg_volume(sub[i]);
+      for (int q = 0; q < nw0; q++) s += w0[q] * vol;
     }
-    if (err) {
-      xgpu_record_error(status, status_elem, err, el);
-      if (cut_ratio) cut_ratio[el] = nan("");
-      clr_if |= 1u << b;
-      continue;
-    }
-    if (cut_ratio) cut_ratio[el] = part[XGPU_NEG] / (part[XGPU_NEG] + part[XGPU_POS]);
-    // volume based decision of cutinfo.cpp:104-124 (differs from the sign test only on underflow)
-    if (!(part[XGPU_NEG] > 0.0 && part[XGPU_POS] > 0.0)) {
-      clr_if |= 1u << b;
-      if (part[XGPU_NEG] > 0.0) set_neg |= 1u << b; else set_pos |= 1u << b;
-    }
+    part[np] = s;
   }
-  if (clr_if) bits_if[w] &= ~clr_if;
-  if (set_neg) bits_neg[w] |= set_neg;
-  if (set_pos) bits_pos[w] |= set_pos;
+  if (err) {
+    xgpu_record_error(status, status_elem, err, el);
+    if (cut_ratio) cut_ratio[el] = nan("");
+    atomicAnd(bits_if + w, ~bit);
+    return;
+  }
+  if (cut_ratio) cut_ratio[el] = part[XGPU_NEG] / (part[XGPU_NEG] + part[XGPU_POS]);
+  // volume based decision of cutinfo.cpp:104-124 (differs from the sign test only on underflow)
+  if (!(part[XGPU_NEG] > 0.0 && part[XGPU_POS] > 0.0)) {
+    atomicAnd(bits_if + w, ~bit);
+    if (part[XGPU_NEG] > 0.0) atomicOr(bits_neg + w, bit); else atomicOr(bits_pos + w, bit);
+  }
 }
 
 __global__ void k_bitset_op(int op, const uint32_t* __restrict__ a, const uint32_t* __restrict__ b,
@@ -248,15 +242,22 @@ __global__ void k_els_of_facets(int64_t nf, const int32_t* __restrict__ facet_el
   if (e.y >= 0) atomicOr(out + (e.y >> 5), 1u << (e.y & 31));
 }
 
-__global__ void k_dofs_of_els(int64_t ne, int nd, const int32_t* __restrict__ el_dofs, const uint32_t* __restrict__ eb,
-                              uint32_t* __restrict__ out)
+// one thread per element; only marked elements read their dof row.  A plain load tests the bit
+// before the atomic: most dofs are shared by 5-25 elements, so only the first toucher pays for the
+// L2 atomic (a stale read merely repeats an idempotent atomicOr).
+__global__ void __launch_bounds__(256) k_dofs_of_els(int64_t ne, int nd, const int32_t* __restrict__ el_dofs,
+                                                     const uint32_t* __restrict__ eb, uint32_t* out)
 {
-  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= ne * nd) return;
-  const int64_t el = i / nd;
-  if (!tbit(eb, el)) return;
-  const int32_t d = __ldg(el_dofs + i);
-  if (d >= 0) atomicOr(out + (d >> 5), 1u << (d & 31));
+  const int64_t el = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (el >= ne || !tbit(eb, el)) return;
+  const int32_t* __restrict__ row = el_dofs + el * nd;
+  for (int k = 0; k < nd; k++) {
+    const int32_t d = __ldg(row + k);
+    if (d < 0) continue;
+    const uint32_t m = 1u << (d & 31);
+    volatile uint32_t* wp = out + (d >> 5);
+    if (!(*wp & m)) atomicOr(out + (d >> 5), m);
+  }
 }
 
 __global__ void k_gather_rows(int64_t n, const int32_t* __restrict__ list, int width, const int32_t* __restrict__ table,
@@ -283,12 +284,11 @@ extern "C" int xgpu_classify(xgpu_ctx* ctx, int dim, int64_t ne, const int32_t* 
   if (ne == 0) return XGPU_OK;
   const xgpu_rule_host* r0 = xgpu_rule_lookup(ctx, dim, 0);
   if (!r0) return xgpu_fail(ctx, XGPU_ERR_ARG, "xgpu_classify: no order-0 rule");
-  const int64_t nwords = (ne + 31) >> 5;
   cudaStream_t st = ctx->stream;
 #define XG_CLS(DD)                                                                                         \
   k_classify<DD><<<nblk(ne, 256), 256, 0, st>>>(ne, el_vtx, phi, bits_neg, bits_pos, bits_if, cut_ratio);  \
   XGPU_LAUNCH_CHECK(ctx);                                                                                  \
-  k_cut_ratio<DD><<<nblk(nwords, 128), 128, 0, st>>>(ne, el_vtx, phi, r0->d_wts, r0->n, bits_neg, bits_pos, \
+  k_cut_ratio<DD><<<nblk(ne, 256), 256, 0, st>>>(ne, el_vtx, phi, r0->d_wts, r0->n, bits_neg, bits_pos, \
                                                      bits_if, cut_ratio, ctx->d_status, ctx->d_status_elem); \
   XGPU_LAUNCH_CHECK(ctx);
   if (dim == 3) { XG_CLS(3) } else if (dim == 2) { XG_CLS(2) } else { XG_CLS(1) }
@@ -426,7 +426,7 @@ extern "C" int xgpu_dofs_of_elements(xgpu_ctx* ctx, int64_t ne, int nd, const in
   if (!ctx) return XGPU_ERR_ARG;
   XGPU_CUDA(ctx, cudaMemsetAsync(bits_out, 0, sizeof(uint32_t) * ((ndof + 31) >> 5), ctx->stream));
   if (ne == 0) return XGPU_OK;
-  k_dofs_of_els<<<nblk(ne * nd, 256), 256, 0, ctx->stream>>>(ne, nd, el_dofs, el_bits, bits_out);
+  k_dofs_of_els<<<nblk(ne, 256), 256, 0, ctx->stream>>>(ne, nd, el_dofs, el_bits, bits_out);
   XGPU_LAUNCH_CHECK(ctx);
   return XGPU_OK;
 }

@@ -171,6 +171,132 @@ __global__ void __launch_bounds__(128) k_elmat_points(
   }
 }
 
+// ---------------------------------------------------------------- mass + stiffness on point rules
+// Specialisation of k_elmat_points for sums of ID*ID and GRAD.GRAD terms (the volume and interface
+// integrators of CutFEM Poisson-type forms): compile-time order (the basis evaluation unrolls, no
+// operator dispatch in the contraction), the coefficients of all terms are folded per element into
+// one mass and one stiffness weight per point.  Per point and lane: 9 shared loads (128 bit) and
+// 22 FP64 operations on a 2x2 register block.
+template <int D>
+struct StageSinkMS {
+  double* B;         // this point's slab: [val | g0 | .. | g(D-1)], each NDP long
+  int ndp;
+  const double* Fi;
+  __device__ __forceinline__ void operator()(int i, const AD<D>& a)
+  {
+    B[i] = a.v;
+#pragma unroll
+    for (int c = 0; c < D; c++) {
+      double g = 0.0;
+#pragma unroll
+      for (int j = 0; j < D; j++) g += Fi[j * D + c] * a.d[j];
+      B[(1 + c) * ndp + i] = g;
+    }
+  }
+};
+
+template <int D, int P>
+__global__ void __launch_bounds__(128) k_elmat_ms(
+    int64_t n, const int32_t* __restrict__ elems, const int32_t* __restrict__ el_vtx,
+    const double* __restrict__ vtx_xyz, const int64_t* __restrict__ offsets, const double* __restrict__ pts,
+    const double* __restrict__ wts, int np_shared, int CH, TermsDev T, int accumulate,
+    const int32_t* __restrict__ slots, double* __restrict__ mats)
+{
+  constexpr int ND = (D == 1) ? P + 1 : ((D == 2) ? 3 + 3 * (P - 1) + (P - 1) * (P - 2) / 2
+                                                   : 4 + 6 * (P - 1) + 4 * ((P - 1) * (P - 2) / 2) + (P - 1) * (P - 2) * (P - 3) / 6);
+  constexpr int NDP = (ND + 1) & ~1, NBK = NDP / 2, NBLK = NBK * NBK, MAXB = (NBLK + 31) / 32;
+  constexpr int PS = NDP * (1 + D) + 2;  // per point: val, D physical gradients, (mass, stiffness) weights
+  extern __shared__ double smem[];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  double* Bw = smem + (size_t)wib * CH * PS;
+  const int64_t warp0 = (int64_t)blockIdx.x * (blockDim.x >> 5) + wib;
+  const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
+  for (int64_t e = warp0; e < n; e += nwarps) {
+    const int64_t el = elems ? (int64_t)elems[e] : e;
+    int v[D + 1];
+    double vx[D + 1][3], F[D * D], Fi[D * D];
+#pragma unroll
+    for (int k = 0; k < D + 1; k++) {
+      v[k] = __ldg(el_vtx + el * (D + 1) + k);
+#pragma unroll
+      for (int c = 0; c < 3; c++) vx[k][c] = (c < D) ? __ldg(vtx_xyz + (int64_t)v[k] * D + c) : 0.0;
+    }
+    xg_affine_jac<D>(vx, F);
+    const double meas = fabs(xg_inv<D>(F, Fi));
+    const double h = (D == 1) ? meas : ((D == 2) ? sqrt(meas) : cbrt(meas));
+    double cm = 0.0, cs = 0.0;
+    for (int t = 0; t < T.n; t++) {
+      const double c = T.coef[t] * ipow(h, T.hpow[t]) * meas;
+      if (T.op_test[t] == 0) cm += c; else cs += c;
+    }
+    const int64_t q0 = offsets ? offsets[e] : 0;
+    const int npe = offsets ? (int)(offsets[e + 1] - q0) : np_shared;
+    double acc[MAXB][4];
+#pragma unroll
+    for (int b = 0; b < MAXB; b++) { acc[b][0] = acc[b][1] = acc[b][2] = acc[b][3] = 0.0; }
+    for (int c0 = 0; c0 < npe; c0 += CH) {
+      const int cnt = min(CH, npe - c0);
+      __syncwarp();
+      for (int ql = lane; ql < cnt; ql += 32) {
+        double* B = Bw + (size_t)ql * PS;
+        const double* xq = pts + 3 * (q0 + c0 + ql);
+        double xh[3] = {xq[0], xq[1], xq[2]};
+        if (ND < NDP) {
+#pragma unroll
+          for (int k = 0; k < 1 + D; k++) B[k * NDP + ND] = 0.0;
+        }
+        StageSinkMS<D> sink{B, NDP, Fi};
+        xg_h1_shapes<D, P>(v, xh, sink);
+        const double w = wts[q0 + c0 + ql];
+        B[NDP * (1 + D)] = cm * w;
+        B[NDP * (1 + D) + 1] = cs * w;
+      }
+      __syncwarp();
+#pragma unroll
+      for (int b = 0; b < MAXB; b++) {
+        const int blk = lane + 32 * b;
+        if (blk < NBLK) {
+          const int i0 = 2 * (blk / NBK), j0 = 2 * (blk % NBK);
+          for (int q = 0; q < cnt; q++) {
+            const double* B = Bw + (size_t)q * PS;
+            const double2 wq = *reinterpret_cast<const double2*>(B + NDP * (1 + D));
+            double s00 = 0, s01 = 0, s10 = 0, s11 = 0;
+#pragma unroll
+            for (int c = 0; c < D; c++) {
+              const double2 a = *reinterpret_cast<const double2*>(B + (1 + c) * NDP + i0);
+              const double2 bb = *reinterpret_cast<const double2*>(B + (1 + c) * NDP + j0);
+              s00 += a.x * bb.x; s01 += a.x * bb.y; s10 += a.y * bb.x; s11 += a.y * bb.y;
+            }
+            const double2 a = *reinterpret_cast<const double2*>(B + i0);
+            const double2 bb = *reinterpret_cast<const double2*>(B + j0);
+            const double m0 = wq.x * a.x, m1 = wq.x * a.y;
+            acc[b][0] += wq.y * s00 + m0 * bb.x; acc[b][1] += wq.y * s01 + m0 * bb.y;
+            acc[b][2] += wq.y * s10 + m1 * bb.x; acc[b][3] += wq.y * s11 + m1 * bb.y;
+          }
+        }
+      }
+    }
+    double* M = mats + (size_t)(slots ? (int64_t)slots[e] : e) * ND * ND;
+#pragma unroll
+    for (int b = 0; b < MAXB; b++) {
+      const int blk = lane + 32 * b;
+      if (blk < NBLK) {
+        const int i0 = 2 * (blk / NBK), j0 = 2 * (blk % NBK);
+#pragma unroll
+        for (int a = 0; a < 2; a++)
+#pragma unroll
+          for (int c = 0; c < 2; c++) {
+            const int i = i0 + a, j = j0 + c;
+            if (i < ND && j < ND) {
+              if (accumulate) M[i * ND + j] += acc[b][2 * a + c];
+              else M[i * ND + j] = acc[b][2 * a + c];
+            }
+          }
+      }
+    }
+  }
+}
+
 // ---------------------------------------------------------------- affine fast path
 template <int D>
 __global__ void __launch_bounds__(256) k_elmat_affine(
@@ -272,11 +398,39 @@ int make_terms(xgpu_ctx* ctx, const xgpu_term* th, int nt, TermsDev& T, bool* on
   return XGPU_OK;
 }
 
+template <int D, int P>
+int launch_ms(xgpu_ctx* ctx, int64_t n, const int32_t* elems, const int32_t* el_vtx, const double* vtx_xyz,
+              const int64_t* offsets, const double* pts, const double* wts, int np_shared, const TermsDev& T,
+              int accumulate, const int32_t* slots, double* mats)
+{
+  const int nd = xg_h1_ndof(D, P);
+  const int ndp = (nd + 1) & ~1;
+  const int PS = ndp * (1 + D) + 2;
+  int CH = 32;
+  while (CH > 4 && (size_t)4 * CH * PS * sizeof(double) > 56 * 1024) CH >>= 1;
+  const size_t sm = (size_t)4 * CH * PS * sizeof(double);
+  unsigned grid = nblk(n, 4);
+  if (grid > XGPU_NSM * 16) grid = XGPU_NSM * 16;
+  XGPU_CUDA(ctx, cudaFuncSetAttribute(k_elmat_ms<D, P>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+  k_elmat_ms<D, P><<<grid, 128, sm, ctx->stream>>>(n, elems, el_vtx, vtx_xyz, offsets, pts, wts, np_shared, CH, T,
+                                                   accumulate, slots, mats);
+  XGPU_LAUNCH_CHECK(ctx);
+  return XGPU_OK;
+}
+
 template <int D>
 int launch_points(xgpu_ctx* ctx, int64_t n, const int32_t* elems, const int32_t* el_vtx, const double* vtx_xyz,
                   const double* phi, const int64_t* offsets, const double* pts, const double* wts, int np_shared,
-                  int p, const TermsDev& T, int accumulate, const int32_t* slots, double* mats)
+                  int p, const TermsDev& T, int accumulate, const int32_t* slots, double* mats, bool only_ms = false)
 {
+  if (only_ms) {
+    switch (p) {
+      case 1: return launch_ms<D, 1>(ctx, n, elems, el_vtx, vtx_xyz, offsets, pts, wts, np_shared, T, accumulate, slots, mats);
+      case 2: return launch_ms<D, 2>(ctx, n, elems, el_vtx, vtx_xyz, offsets, pts, wts, np_shared, T, accumulate, slots, mats);
+      case 3: return launch_ms<D, 3>(ctx, n, elems, el_vtx, vtx_xyz, offsets, pts, wts, np_shared, T, accumulate, slots, mats);
+      case 4: return launch_ms<D, 4>(ctx, n, elems, el_vtx, vtx_xyz, offsets, pts, wts, np_shared, T, accumulate, slots, mats);
+    }
+  }
   const int nd = xg_h1_ndof(D, p);
   const int ndp = (nd + 1) & ~1;
   const int PS = ndp * (2 + D) + XG_MAXTERMS;
@@ -346,9 +500,9 @@ extern "C" int xgpu_elmat_rule(xgpu_ctx* ctx, int dim, int fe_order, int64_t n, 
   TermsDev T; bool ms;
   int rc = make_terms(ctx, terms_host, nterms, T, &ms);
   if (rc) return rc;
-  if (dim == 3) return launch_points<3>(ctx, n, elems, el_vtx, vtx_xyz, phi, offsets, pts, wts, 0, fe_order, T, accumulate, slots, mats);
-  if (dim == 2) return launch_points<2>(ctx, n, elems, el_vtx, vtx_xyz, phi, offsets, pts, wts, 0, fe_order, T, accumulate, slots, mats);
-  return launch_points<1>(ctx, n, elems, el_vtx, vtx_xyz, phi, offsets, pts, wts, 0, fe_order, T, accumulate, slots, mats);
+  if (dim == 3) return launch_points<3>(ctx, n, elems, el_vtx, vtx_xyz, phi, offsets, pts, wts, 0, fe_order, T, accumulate, slots, mats, ms);
+  if (dim == 2) return launch_points<2>(ctx, n, elems, el_vtx, vtx_xyz, phi, offsets, pts, wts, 0, fe_order, T, accumulate, slots, mats, ms);
+  return launch_points<1>(ctx, n, elems, el_vtx, vtx_xyz, phi, offsets, pts, wts, 0, fe_order, T, accumulate, slots, mats, ms);
 }
 
 extern "C" int xgpu_elmat_std(xgpu_ctx* ctx, int dim, int fe_order, int64_t n, const int32_t* elems,
@@ -386,7 +540,7 @@ extern "C" int xgpu_elmat_std(xgpu_ctx* ctx, int dim, int fe_order, int64_t n, c
   }
   const xgpu_rule_host* r = xgpu_rule_lookup(ctx, dim, order);
   if (!r) return xgpu_fail(ctx, XGPU_ERR_ARG, "xgpu_elmat_std: no rule");
-  if (dim == 3) return launch_points<3>(ctx, n, elems, el_vtx, vtx_xyz, phi, nullptr, r->d_pts, r->d_wts, r->n, fe_order, T, accumulate, slots, mats);
-  if (dim == 2) return launch_points<2>(ctx, n, elems, el_vtx, vtx_xyz, phi, nullptr, r->d_pts, r->d_wts, r->n, fe_order, T, accumulate, slots, mats);
-  return launch_points<1>(ctx, n, elems, el_vtx, vtx_xyz, phi, nullptr, r->d_pts, r->d_wts, r->n, fe_order, T, accumulate, slots, mats);
+  if (dim == 3) return launch_points<3>(ctx, n, elems, el_vtx, vtx_xyz, phi, nullptr, r->d_pts, r->d_wts, r->n, fe_order, T, accumulate, slots, mats, ms);
+  if (dim == 2) return launch_points<2>(ctx, n, elems, el_vtx, vtx_xyz, phi, nullptr, r->d_pts, r->d_wts, r->n, fe_order, T, accumulate, slots, mats, ms);
+  return launch_points<1>(ctx, n, elems, el_vtx, vtx_xyz, phi, nullptr, r->d_pts, r->d_wts, r->n, fe_order, T, accumulate, slots, mats, ms);
 }
