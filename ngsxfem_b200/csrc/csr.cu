@@ -240,48 +240,53 @@ __global__ void __launch_bounds__(256) k_compact(int64_t ndof, const long long* 
   }
 }
 
-// row-wise gather of the element matrices (see header comment).  Shared memory per warp:
-// NACC accumulator arrays of RCAP doubles (one per lane group, so the groups add without
-// ordering constraints; the arrays are summed in a fixed order at the end) + RCAP column ids
-// (RCAP is a power of two, the tail padded with INT_MAX for the branch-free search).
+// row-wise gather of the element matrices (see header comment).  A warp is split into NG lane
+// groups of GS lanes (GS = widest table row, e.g. 3 groups of 10 lanes for P2 tets); every group
+// owns ONE matrix row: its column ids (power-of-two padded with INT_MAX for the branch-free
+// search) and FP64 accumulators live in shared memory, its lanes take the local columns of one
+// adjacency entry per pass.  Entries are walked in ascending (batch, table row, local index)
+// order, so every nonzero is summed in exactly the order of a sequential AddElementMatrix loop.
+// The per-row fixed cost is shared by NG rows and no pass ever waits for another group.
 template <bool DUPS>
 __global__ void __launch_bounds__(256) k_scatter(int ndof, const long long* __restrict__ adj_ptr,
-                                                 const long long* __restrict__ adj, BatchDev bd, int RCAP, int SL, int G,
+                                                 const long long* __restrict__ adj, BatchDev bd, int RCAP, int GS, int NG,
                                                  int trips, const long long* __restrict__ rowptr,
                                                  const int32_t* __restrict__ colidx, double* __restrict__ vals)
 {
   extern __shared__ double sacc[];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, nwb = blockDim.x >> 5;
-  const int NACC = DUPS ? 1 : G;
-  double* acc = sacc + wib * NACC * RCAP;
-  int* cols = reinterpret_cast<int*>(sacc + nwb * NACC * RCAP) + wib * RCAP;
-  const int warp0 = blockIdx.x * nwb + wib;
-  const int nwarps = gridDim.x * nwb;
-  const int g = lane / SL, ls = lane - g * SL;
-  double* myacc = acc + (DUPS ? 0 : (g < G ? g : 0) * RCAP);
-  for (int d = warp0; d < ndof; d += nwarps) {
-    const long long r0 = rowptr[d];
-    const int nr = (int)(rowptr[d + 1] - r0);
-    if (nr == 0) continue;
+  const int g = lane / GS, ls = lane - g * GS;
+  const bool live = g < NG;
+  double* acc = sacc + (wib * NG + (live ? g : 0)) * RCAP;
+  int* cols = reinterpret_cast<int*>(sacc + nwb * NG * RCAP) + (wib * NG + (live ? g : 0)) * RCAP;
+  const int rows_per_sweep = gridDim.x * nwb * NG;
+  for (int d0 = (blockIdx.x * nwb + wib) * NG; d0 < ndof; d0 += rows_per_sweep) {
+    const int d = d0 + g;
+    const bool have = live && d < ndof;
+    long long r0 = 0, a = 0;
+    int nr = 0, na = 0;
+    if (have) {
+      r0 = rowptr[d]; nr = (int)(rowptr[d + 1] - r0);
+      a = adj_ptr[d]; na = (int)(adj_ptr[d + 1] - a);
+      if (nr == 0) na = 0;
+    }
     int P = 32;
     while (P < nr) P <<= 1;
     {
       const int32_t* __restrict__ cr = colidx + r0;
-      for (int k = lane; k < P; k += 32) {
+      for (int k = ls; k < (have ? P : 0); k += GS) {
         cols[k] = (k < nr) ? __ldg(cr + k) : 0x7fffffff;
-        for (int q = 0; q < NACC; q++) acc[q * RCAP + k] = 0.0;
+        acc[k] = 0.0;
       }
     }
     __syncwarp();
-    const long long a = adj_ptr[d];
-    const int na = (int)(adj_ptr[d + 1] - a);
     const long long* __restrict__ adjd = adj + a;
-    for (int t0 = 0; t0 < na; t0 += G) {
-      const int t = t0 + g;
+    const int maxna = __reduce_max_sync(0xffffffffu, na);
+    for (int t = 0; t < maxna; t++) {
       int w = 0;
       const int32_t* __restrict__ row = nullptr;
       const double* __restrict__ mrow = nullptr;
-      if (g < G && t < na) {
+      if (t < na) {
         const long long e = adjd[t];
         const int bi = XG_ADJ_BATCH(e);
         if (bd.mats[bi]) {  // a batch without matrices only contributes sparsity (explicit zeros)
@@ -292,7 +297,7 @@ __global__ void __launch_bounds__(256) k_scatter(int ndof, const long long* __re
         }
       }
       for (int it = 0; it < trips; it++) {
-        const int lj = it * SL + ls;
+        const int lj = it * GS + ls;
         int pos = -1;
         double m = 0.0;
         if (lj < w) {
@@ -305,10 +310,9 @@ __global__ void __launch_bounds__(256) k_scatter(int ndof, const long long* __re
           }
         }
         if (DUPS) {
-          // a dof may occur twice in one table row, and the groups share one accumulator array:
-          // lanes hitting the same slot are summed in lane order (= entry, then local index) and
-          // the first lane adds
-          const unsigned peers = __match_any_sync(0xffffffffu, pos >= 0 ? pos : (-1 - lane));
+          // a dof may occur twice in one table row: lanes of a group hitting the same slot are
+          // summed in lane (= local index) order and the first lane adds
+          const unsigned peers = __match_any_sync(0xffffffffu, pos >= 0 ? (pos | (g << 20)) : (-1 - lane));
           unsigned rem = (pos >= 0) ? peers : 0u;
           double s = 0.0;
           while (__any_sync(0xffffffffu, rem != 0u)) {
@@ -318,18 +322,14 @@ __global__ void __launch_bounds__(256) k_scatter(int ndof, const long long* __re
           }
           if (pos >= 0 && lane == __ffs(peers) - 1) acc[pos] += s;
         } else {
-          if (pos >= 0) myacc[pos] += m;  // distinct dofs inside one table row: no conflict in a group
+          if (pos >= 0) acc[pos] += m;  // distinct dofs inside one table row: no conflict in a group
         }
         __syncwarp();
       }
     }
     {
       double* __restrict__ vr = vals + r0;
-      for (int k = lane; k < nr; k += 32) {
-        double s = acc[k];
-        for (int q = 1; q < NACC; q++) s += acc[q * RCAP + k];
-        vr[k] = s;
-      }
+      for (int k = ls; k < nr; k += GS) vr[k] = acc[k];
     }
     __syncwarp();
   }
@@ -522,12 +522,12 @@ extern "C" int xgpu_csr_scatter(xgpu_ctx* ctx, xgpu_plan* P, const xgpu_batch* b
   while (RCAP < P->maxnr) RCAP <<= 1;
   int SL, G, trips;
   lane_split(P->wmax, &SL, &G, &trips);
-  const size_t per_warp = (size_t)RCAP * (8 * (P->dups ? 1 : G) + 4);
+  const size_t per_warp = (size_t)RCAP * 12 * G;
   int nw = 8;
   while (nw > 1 && nw * per_warp > 200 * 1024) nw >>= 1;
   const size_t sm = nw * per_warp;
   if (sm > 220 * 1024) return xgpu_fail(ctx, XGPU_ERR_CAPACITY, "csr: a row is too long for the shared-memory gather");
-  unsigned grid = nblk(P->ndof, nw);
+  unsigned grid = nblk(P->ndof, nw * G);
   if (grid > XGPU_NSM * 32) grid = XGPU_NSM * 32;
   if (P->dups) {
     XGPU_CUDA(ctx, cudaFuncSetAttribute(k_scatter<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));

@@ -46,6 +46,18 @@ __global__ void __launch_bounds__(256) k_cq_count(int64_t n, const int32_t* __re
   counts[i] = cnt;
 }
 
+// Fill: a block owns 128 consecutive listed elements.  Phase 1, one THREAD per element: the
+// decomposition (<= 4 cut points, <= 3 sub-simplices) and the weight factors go to shared memory
+// (no redundant per-lane geometry).  Phase 2, one WARP per element in turn: lanes stride over the
+// (sub-simplex, rule point) pairs and write the 32 B/point output coalesced.
+struct CqDesc {
+  double p[3][4][3];  // sub-simplex vertices
+  double vol[3];      // |det| of every sub-simplex
+  double iffac;       // interface weight factor (1 for NEG/POS)
+  int ns;             // >0 sub-simplices, 0 = standard rule of an uncut matching element, <0 = error / nothing
+  int D;              // dimension of the sub-simplices
+};
+
 template <int D>
 __global__ void __launch_bounds__(128) k_cq_fill(int64_t n, const int32_t* __restrict__ elems,
                                                  const int32_t* __restrict__ el_vtx, const double* __restrict__ vtx_xyz,
@@ -55,61 +67,89 @@ __global__ void __launch_bounds__(128) k_cq_fill(int64_t n, const int32_t* __res
                                                  const int64_t* __restrict__ offsets, double* __restrict__ pts,
                                                  double* __restrict__ wts, int* status, unsigned long long* status_elem)
 {
-  extern __shared__ double smem[];  // sub rule: np_sub x 4 (xi0, xi1, xi2, w)
+  extern __shared__ double smem[];  // sub rule: np_sub x 4 (xi0, xi1, xi2, w), then 128 descriptors
+  CqDesc* desc = reinterpret_cast<CqDesc*>(smem + 4 * ((np_sub + 1) & ~1));
   for (int t = threadIdx.x; t < np_sub; t += blockDim.x) {
     smem[4 * t + 0] = rs_p[3 * t + 0]; smem[4 * t + 1] = rs_p[3 * t + 1]; smem[4 * t + 2] = rs_p[3 * t + 2];
     smem[4 * t + 3] = rs_w[t];
   }
-  __syncthreads();
-  const int lane = threadIdx.x & 31;
-  const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-  for (int64_t i = warp0; i < n; i += nwarps) {
-    const int64_t el = elems ? (int64_t)elems[i] : i;
-    const int64_t off = offsets[i];
-    const int cnt = (int)(offsets[i + 1] - off);
-    if (cnt == 0) continue;
-    int v[D + 1]; double l[D + 1];
-    load_el<D>(el_vtx, phi, el, v, l);
-    const int dom = xg_check_cut(l, D + 1);
-    if (dom != XGPU_IF) {  // uncut, matching: the standard rule (:669-674)
-      for (int q = lane; q < cnt; q += 32) {
-        pts[3 * (off + q) + 0] = rv_p[3 * q + 0]; pts[3 * (off + q) + 1] = rv_p[3 * q + 1]; pts[3 * (off + q) + 2] = rv_p[3 * q + 2];
-        wts[off + q] = rv_w[q];
-      }
-      continue;
-    }
-    XgSimplex ref, sub[3];
-    xg_ref_simplex(D, ref);
-    const int ns = xg_decompose(ref, l, dt, sub);
-    if (ns < 0) {
-      if (lane == 0) xgpu_record_error(status, status_elem, ns, el);
-      for (int q = lane; q < cnt; q += 32) {
-        pts[3 * (off + q) + 0] = 0.0; pts[3 * (off + q) + 1] = 0.0; pts[3 * (off + q) + 2] = 0.0; wts[off + q] = 0.0;
-      }
-      continue;
-    }
-    double vol[3];
-    for (int s = 0; s < 3; s++) vol[s] = (s < ns) ? xg_volume(sub[s]) : 0.0;
-    double iffac = 1.0;
-    if (dt == XGPU_IF) {  // w <- w * ||F^{-T} n_ref||  (:558-578); affine F from the vertices
-      double vx[D + 1][3], F[D * D], Fi[D * D];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  for (int64_t base = (int64_t)blockIdx.x * 128; base < n; base += (int64_t)gridDim.x * 128) {
+    __syncthreads();
+    {  // phase 1
+      const int64_t i = base + threadIdx.x;
+      CqDesc& Dd = desc[threadIdx.x];
+      Dd.ns = -1;
+      if (i < n && offsets[i + 1] > offsets[i]) {
+        const int64_t el = elems ? (int64_t)elems[i] : i;
+        int v[D + 1]; double l[D + 1];
+        load_el<D>(el_vtx, phi, el, v, l);
+        const int dom = xg_check_cut(l, D + 1);
+        if (dom != XGPU_IF) Dd.ns = 0;  // uncut, matching: the standard rule (:669-674)
+        else {
+          XgSimplex ref, sub[3];
+          xg_ref_simplex(D, ref);
+          const int ns = xg_decompose(ref, l, dt, sub);
+          if (ns < 0) xgpu_record_error(status, status_elem, ns, el);
+          else {
+            double iffac = 1.0;
+            if (dt == XGPU_IF) {  // w <- w * ||F^{-T} n_ref||  (:558-578); affine F from the vertices
+              double vx[D + 1][3], F[D * D], Fi[D * D];
 #pragma unroll
-      for (int k = 0; k < D + 1; k++)
+              for (int k = 0; k < D + 1; k++)
 #pragma unroll
-        for (int c = 0; c < 3; c++) vx[k][c] = (c < D) ? __ldg(vtx_xyz + (int64_t)v[k] * D + c) : 0.0;
-      xg_affine_jac<D>(vx, F);
-      xg_inv<D>(F, Fi);
-      iffac = xg_if_weight_factor<D>(Fi, l);
+                for (int c = 0; c < 3; c++) vx[k][c] = (c < D) ? __ldg(vtx_xyz + (int64_t)v[k] * D + c) : 0.0;
+              xg_affine_jac<D>(vx, F);
+              xg_inv<D>(F, Fi);
+              iffac = xg_if_weight_factor<D>(Fi, l);
+            }
+            for (int s = 0; s < ns; s++) {
+              Dd.vol[s] = xg_volume(sub[s]);
+              for (int a = 0; a < 4; a++) for (int c = 0; c < 3; c++) Dd.p[s][a][c] = sub[s].p[a][c];
+            }
+            Dd.D = sub[0].D;
+            Dd.iffac = iffac;
+          }
+          Dd.ns = ns;
+        }
+      }
     }
-    for (int idx = lane; idx < cnt; idx += 32) {
-      const int s = idx / np_sub, q = idx - s * np_sub;
-      double x[3];
-      const XgSimplex& S = (s == 0) ? sub[0] : ((s == 1) ? sub[1] : sub[2]);
-      xg_map_point(S, &smem[4 * q], x);
-      const double vs = (s == 0) ? vol[0] : ((s == 1) ? vol[1] : vol[2]);
-      pts[3 * (off + idx) + 0] = x[0]; pts[3 * (off + idx) + 1] = x[1]; pts[3 * (off + idx) + 2] = x[2];
-      wts[off + idx] = smem[4 * q + 3] * vs * iffac;
+    __syncthreads();
+    // phase 2
+    for (int k = wib; k < 128; k += 4) {
+      const int64_t i = base + k;
+      if (i >= n) break;
+      const CqDesc& Dd = desc[k];
+      const int64_t off = offsets[i];
+      const int cnt = (int)(offsets[i + 1] - off);
+      if (cnt == 0) continue;
+      if (Dd.ns == 0) {
+        for (int q = lane; q < cnt; q += 32) {
+          pts[3 * (off + q) + 0] = rv_p[3 * q + 0]; pts[3 * (off + q) + 1] = rv_p[3 * q + 1]; pts[3 * (off + q) + 2] = rv_p[3 * q + 2];
+          wts[off + q] = rv_w[q];
+        }
+      } else if (Dd.ns < 0) {
+        for (int q = lane; q < cnt; q += 32) {
+          pts[3 * (off + q) + 0] = 0.0; pts[3 * (off + q) + 1] = 0.0; pts[3 * (off + q) + 2] = 0.0; wts[off + q] = 0.0;
+        }
+      } else {
+        const int sd = Dd.D;
+        for (int idx = lane; idx < cnt; idx += 32) {
+          const int s = idx / np_sub, q = idx - s * np_sub;
+          const double* xi = &smem[4 * q];
+          double ow = 1.0;
+          for (int m = 0; m < sd; m++) ow -= xi[m];
+          double x[3];
+#pragma unroll
+          for (int c = 0; c < 3; c++) {
+            double t = ow * Dd.p[s][0][c];
+            for (int m = 0; m < sd; m++) t += xi[m] * Dd.p[s][m + 1][c];
+            x[c] = t;
+          }
+          pts[3 * (off + idx) + 0] = x[0]; pts[3 * (off + idx) + 1] = x[1]; pts[3 * (off + idx) + 2] = x[2];
+          wts[off + idx] = xi[3] * Dd.vol[s] * Dd.iffac;
+        }
+      }
     }
   }
 }
@@ -233,9 +273,9 @@ extern "C" int xgpu_cutquad_fill(xgpu_ctx* ctx, int dim, int64_t n, const int32_
   const xgpu_rule_host* rv = xgpu_rule_lookup(ctx, dim, order);
   const xgpu_rule_host* rs = (dt == XGPU_IF) ? xgpu_rule_lookup(ctx, dim - 1, order) : rv;
   if (!rv || !rs) return xgpu_fail(ctx, XGPU_ERR_ARG, "xgpu_cutquad_fill: no rule");
-  const size_t sm = sizeof(double) * 4 * rs->n;
-  unsigned grid = nblk(n, 4);  // 4 warps (elements) per block
-  if (grid > XGPU_NSM * 16) grid = XGPU_NSM * 16;
+  const size_t sm = sizeof(double) * 4 * ((rs->n + 1) & ~1) + 128 * sizeof(CqDesc);
+  unsigned grid = nblk(n, 128);  // 128 listed elements per block and pass
+  if (grid > XGPU_NSM * 8) grid = XGPU_NSM * 8;
 #define XG_FILL(DD)                                                                                                  \
   {                                                                                                                  \
     if (sm > 48 * 1024) XGPU_CUDA(ctx, cudaFuncSetAttribute(k_cq_fill<DD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm)); \
