@@ -52,20 +52,27 @@ class CutAssembly:
         self.ctx = ctx or default_ctx(self.dev.index)
         self.nd = ops.h1_ndof(dim, fe_order)
 
-    def step(self, phi, timer=None, keep=False):
-        """one pass of the hot path; returns a dict with the CSR matrix and the unit counts"""
+    def step(self, phi, timer=None, keep=False, hooks=None):
+        """one pass of the hot path; returns a dict with the CSR matrix and the unit counts.
+        hooks: optional {"classified"|"need_dofs"|"pattern"|"values": fn(partial results)} called at those
+        points (the host-buffer path overlaps its H2D / D2H copies with the kernels through them)"""
         t = timer or PhaseTimer(False)
+        hooks = hooks or {}
         ctx, dim, p, ne = self.ctx, self.dim, self.p, self.ne
         els, xyz = self.el_vtx, self.vtx_xyz
         t.mark("start")
         # (a) CutInfo.Update
         bn, bp, bi, cr = ops.classify(dim, els, phi, ctx=ctx)
         t.mark("classify")
+        if "classified" in hooks:
+            hooks["classified"](dict(bits=(bn, bp, bi), cut_ratio=cr))
         has = ops.bitset_op(ops.BIT_OR, bn, bi, ne, ctx=ctx)
         l_neg = ops.bitset_to_list(bn, ne, ctx=ctx)
         l_if = ops.bitset_to_list(bi, ne, ctx=ctx)
         t.mark("lists")
         # Restrict(H1, hasneg): active dofs, compressed numbering, dof rows of the two batches
+        if "need_dofs" in hooks:
+            hooks["need_dofs"](None)
         act = ops.dofs_of_elements(self.el_dofs, has, self.ndof_full, ctx=ctx)
         dofmap, ndof = ops.bitset_rank(act, self.ndof_full, ctx=ctx)
         t_neg = ops.gather_rows(self.el_dofs, l_neg, dofmap, ctx=ctx)
@@ -91,8 +98,12 @@ class CutAssembly:
         t.mark("csr_plan")
         rowptr, col = ops.csr_pattern(plan, self.dev)
         t.mark("csr_pattern")
+        if "pattern" in hooks:
+            hooks["pattern"](dict(rowptr=rowptr, col=col))
         vals = ops.csr_scatter(plan, [(t_neg, m_neg), (t_if, m_if)], rowptr, col)
         t.mark("csr_scatter")
+        if "values" in hooks:
+            hooks["values"](dict(vals=vals))
         out = dict(ndof=ndof, nnz=plan.nnz, n_neg=l_neg.numel(), n_if=l_if.numel(),
                    units=l_neg.numel() + l_if.numel(), rowptr=rowptr, col=col, vals=vals,
                    bits=(bn, bp, bi), cut_ratio=cr, npts=(w.numel(), w2.numel()))
@@ -114,34 +125,86 @@ class HostBuffers:
     def h2d_bytes(self):
         return sum(t.numel() * t.element_size() for t in (self.el_vtx, self.vtx_xyz, self.el_dofs, self.phi))
 
-    def land(self, name, t):
-        """device tensor -> pinned host buffer (grown on demand); returns bytes copied"""
+    def land(self, name, t, streams=None):
+        """device tensor -> pinned host buffer (grown on demand); returns bytes copied.
+        streams: optional list of copy streams — a large tensor is split into one slice per stream so
+        that several DMA engines share the PCIe link"""
         buf = self.out.get(name)
         if buf is None or buf.numel() < t.numel() or buf.dtype != t.dtype:
             buf = torch.empty(int(t.numel() * 1.05) + 16, dtype=t.dtype).pin_memory()
             self.out[name] = buf
-        buf[:t.numel()].copy_(t.reshape(-1), non_blocking=True)
-        return t.numel() * t.element_size()
+        flat = t.reshape(-1)
+        n = flat.numel()
+        if streams and n * t.element_size() > (32 << 20):
+            k = len(streams)
+            step = (n + k - 1) // k
+            for i, st in enumerate(streams):
+                a, b = i * step, min(n, (i + 1) * step)
+                if a < b:
+                    with torch.cuda.stream(st):
+                        buf[a:b].copy_(flat[a:b], non_blocking=True)
+        else:
+            buf[:n].copy_(flat, non_blocking=True)
+        return n * t.element_size()
 
 
-def step_host(hb, dim, ndof_full, fe_order, device, ctx=None):
+def step_host(hb, dim, ndof_full, fe_order, device, ctx=None, overlap=True):
     """the same pass starting from HOST buffers: H2D of every input, assembly, D2H of the CutInfo
-    BitArrays / cut ratios and of the CSR matrix.  returns (result dict, h2d bytes, d2h bytes)"""
-    els = hb.el_vtx.to(device, non_blocking=True)
-    xyz = hb.vtx_xyz.to(device, non_blocking=True)
-    eld = hb.el_dofs.to(device, non_blocking=True)
-    phi = hb.phi.to(device, non_blocking=True)
+    BitArrays / cut ratios and of the CSR matrix.  returns (result dict, h2d bytes, d2h bytes).
+
+    overlap=True: the copies run on two side streams ordered against the kernels by events — the
+    connectivity and level set go first (classification needs only those), the dof table follows while
+    the classification runs, the CutInfo outputs / the sparsity pattern / the values leave as soon
+    as their kernels have finished (PCIe is full duplex; the D2H of 1.7 GB is the long pole)."""
+    main = torch.cuda.current_stream(device)
+    if not overlap:
+        els = hb.el_vtx.to(device, non_blocking=True)
+        xyz = hb.vtx_xyz.to(device, non_blocking=True)
+        eld = hb.el_dofs.to(device, non_blocking=True)
+        phi = hb.phi.to(device, non_blocking=True)
+        prob = CutAssembly(dim, els, xyz, eld, ndof_full, fe_order, ctx=ctx)
+        r = prob.step(phi)
+        d2h = sum(hb.land(f"bits{i}", b) for i, b in enumerate(r["bits"]))
+        for k in ("cut_ratio", "rowptr", "col", "vals"):
+            d2h += hb.land(k, r[k])
+        main.synchronize()
+        return r, hb.h2d_bytes(), d2h
+    if not hasattr(hb, "s_in"):
+        hb.s_in, hb.s_out = torch.cuda.Stream(device), torch.cuda.Stream(device)
+    s_in, s_out = hb.s_in, hb.s_out
+    s_in.wait_stream(main)
+    s_out.wait_stream(main)
+    with torch.cuda.stream(s_in):
+        els = hb.el_vtx.to(device, non_blocking=True)
+        phi = hb.phi.to(device, non_blocking=True)
+        e_first = torch.cuda.Event(); e_first.record(s_in)
+        xyz = hb.vtx_xyz.to(device, non_blocking=True)
+        eld = hb.el_dofs.to(device, non_blocking=True)
+        e_rest = torch.cuda.Event(); e_rest.record(s_in)
+    for t_ in (els, phi, xyz, eld):
+        t_.record_stream(main)
+    main.wait_event(e_first)
+    d2h = [0]
+
+    def send(items):
+        ev = torch.cuda.Event(); ev.record(main)
+        s_out.wait_event(ev)
+        with torch.cuda.stream(s_out):
+            for name, t_ in items:
+                t_.record_stream(s_out)
+                d2h[0] += hb.land(name, t_)  # one D2H stream: two did not add bandwidth (PCIe bound, profiles/r01_notes.md)
+
+    hooks = {
+        "classified": lambda p: send([(f"bits{i}", b) for i, b in enumerate(p["bits"])] + [("cut_ratio", p["cut_ratio"])]),
+        "need_dofs": lambda p: main.wait_event(e_rest),
+        "pattern": lambda p: send([("rowptr", p["rowptr"]), ("col", p["col"])]),
+        "values": lambda p: send([("vals", p["vals"])]),
+    }
     prob = CutAssembly(dim, els, xyz, eld, ndof_full, fe_order, ctx=ctx)
-    r = prob.step(phi)
-    d2h = 0
-    for i, b in enumerate(r["bits"]):
-        d2h += hb.land(f"bits{i}", b)
-    d2h += hb.land("cut_ratio", r["cut_ratio"])
-    d2h += hb.land("rowptr", r["rowptr"])
-    d2h += hb.land("col", r["col"])
-    d2h += hb.land("vals", r["vals"])
-    torch.cuda.current_stream().synchronize()
-    return r, hb.h2d_bytes(), d2h
+    r = prob.step(phi, hooks=hooks)
+    s_out.synchronize()
+    main.synchronize()
+    return r, hb.h2d_bytes(), d2h[0]
 
 
 def sphere_levelset(points, centers, radius, eps=1e-14):
