@@ -25,6 +25,7 @@
 
 #define XG_MAXBATCH 8
 #define XG_EMPTY 0x7fffffff
+#define XG_UB 4  // adjacency entries per prefetch batch
 
 struct BatchDev {
   int nb;
@@ -242,23 +243,27 @@ __global__ void __launch_bounds__(256) k_compact(int64_t ndof, const long long* 
 
 // row-wise gather of the element matrices (see header comment).  A warp is split into NG lane
 // groups of GS lanes (GS = widest table row, e.g. 3 groups of 10 lanes for P2 tets); every group
-// owns ONE matrix row: its column ids (power-of-two padded with INT_MAX for the branch-free
-// search) and FP64 accumulators live in shared memory, its lanes take the local columns of one
-// adjacency entry per pass.  Entries are walked in ascending (batch, table row, local index)
-// order, so every nonzero is summed in exactly the order of a sequential AddElementMatrix loop.
-// The per-row fixed cost is shared by NG rows and no pass ever waits for another group.
+// owns ONE matrix row: FP64 accumulators and a small open-addressing hash  column id -> slot  live
+// in shared memory (1-2 probes per lookup; a binary search over the sorted columns cost 6
+// dependent shared loads per contribution and made the kernel shared-memory bound,
+// profiles/r01_notes.md), its lanes take the local columns of one adjacency entry per pass.
+// Entries are walked in ascending (batch, table row, local index) order, so every nonzero is summed
+// in exactly the order of a sequential AddElementMatrix loop.  The per-row fixed cost is shared by
+// NG rows and no pass ever waits for another group.
 template <bool DUPS>
 __global__ void __launch_bounds__(256) k_scatter(int ndof, const long long* __restrict__ adj_ptr,
-                                                 const long long* __restrict__ adj, BatchDev bd, int RCAP, int GS, int NG,
-                                                 int trips, const long long* __restrict__ rowptr,
+                                                 const long long* __restrict__ adj, BatchDev bd, int RCAP, int HS, int GS,
+                                                 int NG, int trips, const long long* __restrict__ rowptr,
                                                  const int32_t* __restrict__ colidx, double* __restrict__ vals)
 {
   extern __shared__ double sacc[];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, nwb = blockDim.x >> 5;
   const int g = lane / GS, ls = lane - g * GS;
   const bool live = g < NG;
-  double* acc = sacc + (wib * NG + (live ? g : 0)) * RCAP;
-  int* cols = reinterpret_cast<int*>(sacc + nwb * NG * RCAP) + (wib * NG + (live ? g : 0)) * RCAP;
+  const int slot_id = wib * NG + (live ? g : 0);
+  double* acc = sacc + slot_id * RCAP;
+  int* hkey = reinterpret_cast<int*>(sacc + nwb * NG * RCAP) + slot_id * HS;
+  unsigned short* hpos = reinterpret_cast<unsigned short*>(reinterpret_cast<int*>(sacc + nwb * NG * RCAP) + nwb * NG * HS) + slot_id * HS;
   const int rows_per_sweep = gridDim.x * nwb * NG;
   for (int d0 = (blockIdx.x * nwb + wib) * NG; d0 < ndof; d0 += rows_per_sweep) {
     const int d = d0 + g;
@@ -270,61 +275,84 @@ __global__ void __launch_bounds__(256) k_scatter(int ndof, const long long* __re
       a = adj_ptr[d]; na = (int)(adj_ptr[d + 1] - a);
       if (nr == 0) na = 0;
     }
-    int P = 32;
-    while (P < nr) P <<= 1;
+    // hash size for this row: power of two >= 1.5 * nr (<= HS by the host's sizing)
+    int H = 16, shift = 28;
+    while (H < nr + (nr >> 1)) { H <<= 1; shift--; }
+    for (int k = ls; k < (have ? H : 0); k += GS) hkey[k] = XG_EMPTY;
+    __syncwarp();
     {
       const int32_t* __restrict__ cr = colidx + r0;
-      for (int k = ls; k < (have ? P : 0); k += GS) {
-        cols[k] = (k < nr) ? __ldg(cr + k) : 0x7fffffff;
+      for (int k = ls; k < nr; k += GS) {
+        const int c = __ldg(cr + k);
         acc[k] = 0.0;
+        unsigned h = ((unsigned)c * 2654435761u) >> shift;
+        while (atomicCAS(&hkey[h], XG_EMPTY, c) != XG_EMPTY) h = (h + 1) & (H - 1);  // columns of a row are distinct
+        hpos[h] = (unsigned short)k;
       }
     }
     __syncwarp();
     const long long* __restrict__ adjd = adj + a;
     const int maxna = __reduce_max_sync(0xffffffffu, na);
-    for (int t = 0; t < maxna; t++) {
-      int w = 0;
-      const int32_t* __restrict__ row = nullptr;
-      const double* __restrict__ mrow = nullptr;
-      if (t < na) {
-        const long long e = adjd[t];
-        const int bi = XG_ADJ_BATCH(e);
-        if (bd.mats[bi]) {  // a batch without matrices only contributes sparsity (explicit zeros)
-          w = bd.width[bi];
-          const int ro = XG_ADJ_ROW(e) * w;  // nrows*width < 2^31 (checked on the host)
-          row = bd.table[bi] + ro;
-          mrow = bd.mats[bi] + (size_t)(ro + XG_ADJ_LOC(e)) * w;
-        }
-      }
+    // The passes of a row are independent loads followed by ordered shared-memory adds.  To keep
+    // the memory latency off the critical path the entries are taken in batches of XG_UB: the
+    // adjacency entries of the NEXT batch are prefetched by the first lanes of the group, the table
+    // and matrix rows of the whole batch are loaded before the first add.
+    const int UB = GS < XG_UB ? GS : XG_UB;
+    const int src0 = live ? g * GS : lane;
+    long long e_pref = (ls < UB && ls < na) ? adjd[ls] : 0;
+    for (int t0 = 0; t0 < maxna; t0 += UB) {
+      const long long e_cur = e_pref;
+      e_pref = (ls < UB && t0 + UB + ls < na) ? adjd[t0 + UB + ls] : 0;
       for (int it = 0; it < trips; it++) {
         const int lj = it * GS + ls;
-        int pos = -1;
-        double m = 0.0;
-        if (lj < w) {
-          const int c = __ldg(row + lj);
-          if (c >= 0) {
-            m = __ldg(mrow + lj);
-            int lo = 0;  // branch-free lower bound over the padded power-of-two list
-            for (int step = P >> 1; step > 0; step >>= 1) lo += (cols[lo + step - 1] < c) ? step : 0;
-            pos = (cols[lo] == c) ? lo : -1;
+        int cc[XG_UB];
+        double mm[XG_UB];
+#pragma unroll
+        for (int u = 0; u < XG_UB; u++) {
+          const long long e = __shfl_sync(0xffffffffu, e_cur, live ? src0 + (u < UB ? u : 0) : lane);
+          cc[u] = -1; mm[u] = 0.0;
+          if (u < UB && t0 + u < na) {
+            const int bi = XG_ADJ_BATCH(e);
+            if (bd.mats[bi]) {  // a batch without matrices only contributes sparsity (explicit zeros)
+              const int w = bd.width[bi];
+              if (lj < w) {
+                const int ro = XG_ADJ_ROW(e) * w;  // nrows*width < 2^31 (checked on the host)
+                cc[u] = __ldg(bd.table[bi] + ro + lj);
+                mm[u] = __ldg(bd.mats[bi] + (size_t)(ro + XG_ADJ_LOC(e)) * w + lj);
+              }
+            }
           }
         }
-        if (DUPS) {
-          // a dof may occur twice in one table row: lanes of a group hitting the same slot are
-          // summed in lane (= local index) order and the first lane adds
-          const unsigned peers = __match_any_sync(0xffffffffu, pos >= 0 ? (pos | (g << 20)) : (-1 - lane));
-          unsigned rem = (pos >= 0) ? peers : 0u;
-          double s = 0.0;
-          while (__any_sync(0xffffffffu, rem != 0u)) {
-            const int src = rem ? (__ffs(rem) - 1) : lane;
-            const double v = __shfl_sync(0xffffffffu, m, src);
-            if (rem) { s += v; rem &= rem - 1; }
+#pragma unroll
+        for (int u = 0; u < XG_UB; u++) {
+          if (u < UB) {
+            const int c = cc[u];
+            const double m = mm[u];
+            int pos = -1;
+            if (c >= 0) {
+              unsigned h = ((unsigned)c * 2654435761u) >> shift;
+              int key = hkey[h];
+              while (key != c && key != XG_EMPTY) { h = (h + 1) & (H - 1); key = hkey[h]; }
+              pos = (key == c) ? (int)hpos[h] : -1;
+            }
+            if (DUPS) {
+              // a dof may occur twice in one table row: lanes of a group hitting the same slot are
+              // summed in lane (= local index) order and the first lane adds
+              const unsigned peers = __match_any_sync(0xffffffffu, pos >= 0 ? (pos | (g << 20)) : (-1 - lane));
+              unsigned rem = (pos >= 0) ? peers : 0u;
+              double sum = 0.0;
+              while (__any_sync(0xffffffffu, rem != 0u)) {
+                const int src = rem ? (__ffs(rem) - 1) : lane;
+                const double v = __shfl_sync(0xffffffffu, m, src);
+                if (rem) { sum += v; rem &= rem - 1; }
+              }
+              if (pos >= 0 && lane == __ffs(peers) - 1) acc[pos] += sum;
+            } else {
+              if (pos >= 0) acc[pos] += m;  // distinct dofs inside one table row: no conflict in a group
+            }
+            __syncwarp();
           }
-          if (pos >= 0 && lane == __ffs(peers) - 1) acc[pos] += s;
-        } else {
-          if (pos >= 0) acc[pos] += m;  // distinct dofs inside one table row: no conflict in a group
         }
-        __syncwarp();
       }
     }
     {
@@ -518,11 +546,13 @@ extern "C" int xgpu_csr_scatter(xgpu_ctx* ctx, xgpu_plan* P, const xgpu_batch* b
     bd.mats[i] = batches_host[i].mats;  // NULL: the batch only contributes sparsity
   }
   if (P->ndof == 0 || P->nnz == 0) return XGPU_OK;
-  int RCAP = 32;
-  while (RCAP < P->maxnr) RCAP <<= 1;
+  const int RCAP = std::max(32, (P->maxnr + 31) & ~31);
+  int HS = 16;
+  while (HS < P->maxnr + (P->maxnr >> 1)) HS <<= 1;
+  if (HS > 65536) return xgpu_fail(ctx, XGPU_ERR_CAPACITY, "csr: a row is too long for the shared-memory gather");
   int SL, G, trips;
   lane_split(P->wmax, &SL, &G, &trips);
-  const size_t per_warp = (size_t)RCAP * 12 * G;
+  const size_t per_warp = ((size_t)RCAP * 8 + (size_t)HS * 6) * G;
   int nw = 8;
   while (nw > 1 && nw * per_warp > 200 * 1024) nw >>= 1;
   const size_t sm = nw * per_warp;
@@ -531,11 +561,11 @@ extern "C" int xgpu_csr_scatter(xgpu_ctx* ctx, xgpu_plan* P, const xgpu_batch* b
   if (grid > XGPU_NSM * 32) grid = XGPU_NSM * 32;
   if (P->dups) {
     XGPU_CUDA(ctx, cudaFuncSetAttribute(k_scatter<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-    k_scatter<true><<<grid, nw * 32, sm, ctx->stream>>>((int)P->ndof, P->adj_ptr, P->adj, bd, RCAP, SL, G, trips,
+    k_scatter<true><<<grid, nw * 32, sm, ctx->stream>>>((int)P->ndof, P->adj_ptr, P->adj, bd, RCAP, HS, SL, G, trips,
                                                         (const long long*)rowptr, colidx, vals);
   } else {
     XGPU_CUDA(ctx, cudaFuncSetAttribute(k_scatter<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-    k_scatter<false><<<grid, nw * 32, sm, ctx->stream>>>((int)P->ndof, P->adj_ptr, P->adj, bd, RCAP, SL, G, trips,
+    k_scatter<false><<<grid, nw * 32, sm, ctx->stream>>>((int)P->ndof, P->adj_ptr, P->adj, bd, RCAP, HS, SL, G, trips,
                                                          (const long long*)rowptr, colidx, vals);
   }
   XGPU_LAUNCH_CHECK(ctx);
