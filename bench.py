@@ -134,7 +134,7 @@ def kernel_bytes(phase, r, nd):
     nn = nd * nd
     if phase == "csr":           # distributed path: plan + pattern + scatter timed as one phase
         return sum(kernel_bytes(k, r, nd) for k in ("csr_plan", "csr_pattern", "csr_scatter"))
-    if phase == "elmat":
+    if phase == "elmat":         # cut quadrature + uncut + cut element matrices
         return kernel_bytes("elmat_uncut", r, nd) + kernel_bytes("elmat_cut", r, nd)
     if phase == "csr_scatter":   # read every element matrix once + dof rows, write vals, read colidx/rowptr
         return r["units"] * (nn * 8 + nd * 4) + r["nnz"] * (8 + 4) + r["ndof"] * 8

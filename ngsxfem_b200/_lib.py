@@ -130,7 +130,9 @@ class Ctx:
 
     def use_current_stream(self):
         s = torch.cuda.current_stream(self.device).cuda_stream
-        self.check(self.lib.xgpu_set_stream(self.h, VP(s)))
+        if s != getattr(self, "_stream", None):
+            self.check(self.lib.xgpu_set_stream(self.h, VP(s)))
+            self._stream = s
 
     def check(self, rc):
         if rc != 0:

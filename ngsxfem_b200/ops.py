@@ -182,19 +182,32 @@ def gather_rows(table, lst=None, mp=None, ctx=None):
 
 
 # ---------------------------------------------------------------- (b) cut quadrature
-def cutquad(dim, elems, el_vtx, vtx_xyz, phi, dt, order, ctx=None):
-    """returns (offsets int64 [n+1], pts [total,3], wts [total])"""
+def cutquad_count(dim, elems, el_vtx, phi, dt, order, ctx=None):
+    """first half of cutquad: (offsets int64 [n+1], total number of points) — synchronises the context's stream"""
     ctx = ctx or default_ctx()
     n = el_vtx.shape[0] if elems is None else elems.numel()
-    dev = el_vtx.device
-    off = torch.empty(n + 1, dtype=torch.int64, device=dev)
+    off = torch.empty(n + 1, dtype=torch.int64, device=el_vtx.device)
     tot = C.c_int64(0)
     ctx.check(ctx.lib.xgpu_cutquad_count(ctx.h, dim, n, ptr(elems), ptr(_i32(el_vtx)), ptr(_f64(phi)), dt, order,
                                          ptr(off), C.byref(tot)))
-    pts = torch.empty((tot.value, 3), dtype=torch.float64, device=dev)
-    wts = torch.empty(tot.value, dtype=torch.float64, device=dev)
+    return off, tot.value
+
+
+def cutquad_fill(dim, elems, el_vtx, vtx_xyz, phi, dt, order, off, total, ctx=None):
+    """second half of cutquad: (pts [total,3], wts [total]); only enqueues"""
+    ctx = ctx or default_ctx()
+    n = el_vtx.shape[0] if elems is None else elems.numel()
+    pts = torch.empty((total, 3), dtype=torch.float64, device=el_vtx.device)
+    wts = torch.empty(total, dtype=torch.float64, device=el_vtx.device)
     ctx.check(ctx.lib.xgpu_cutquad_fill(ctx.h, dim, n, ptr(elems), ptr(el_vtx), ptr(_f64(vtx_xyz)), ptr(phi), dt, order,
                                         ptr(off), ptr(pts), ptr(wts)))
+    return pts, wts
+
+
+def cutquad(dim, elems, el_vtx, vtx_xyz, phi, dt, order, ctx=None):
+    """returns (offsets int64 [n+1], pts [total,3], wts [total])"""
+    off, total = cutquad_count(dim, elems, el_vtx, phi, dt, order, ctx=ctx)
+    pts, wts = cutquad_fill(dim, elems, el_vtx, vtx_xyz, phi, dt, order, off, total, ctx=ctx)
     return off, pts, wts
 
 

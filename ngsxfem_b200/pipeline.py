@@ -14,7 +14,7 @@ inputs; `step_host()` runs it from pinned HOST buffers with the host<->device co
 import torch
 
 from . import ops
-from ._lib import default_ctx
+from ._lib import Ctx, default_ctx
 
 TERMS_VOL = [(ops.OP_GRAD, ops.OP_GRAD, 1.0, 0), (ops.OP_ID, ops.OP_ID, 1.0, 0)]
 TERMS_IF = [(ops.OP_ID, ops.OP_ID, 1.0, 0)]
@@ -41,6 +41,18 @@ class PhaseTimer:
         return out
 
 
+_SIDE = {}
+
+
+def _side_context(dev):
+    """one (stream, xgpu context) pair per device for the concurrent element-matrix branch"""
+    if dev.index not in _SIDE:
+        st = torch.cuda.Stream(dev)
+        with torch.cuda.stream(st):
+            _SIDE[dev.index] = (st, Ctx(dev.index))
+    return _SIDE[dev.index]
+
+
 class CutAssembly:
     """device-resident mesh / space tables + one assembly pass"""
 
@@ -51,11 +63,17 @@ class CutAssembly:
         self.dev = el_vtx.device
         self.ctx = ctx or default_ctx(self.dev.index)
         self.nd = ops.h1_ndof(dim, fe_order)
+        # second context on a side stream: the element matrices (HBM-write / FP64 bound) run
+        # concurrently with the sparsity graph (shared-memory / issue bound); they only meet in the scatter
+        self.side_stream, self.ctx2 = _side_context(self.dev)
 
-    def step(self, phi, timer=None, keep=False, hooks=None):
+    def step(self, phi, timer=None, keep=False, hooks=None, concurrent=False):
         """one pass of the hot path; returns a dict with the CSR matrix and the unit counts.
         hooks: optional {"classified"|"need_dofs"|"pattern"|"values": fn(partial results)} called at those
-        points (the host-buffer path overlaps its H2D / D2H copies with the kernels through them)"""
+        points (the host-buffer path overlaps its H2D / D2H copies with the kernels through them).
+        concurrent=True runs the element-matrix branch on a side stream next to the graph construction
+        (measured: 12.6 -> 12.2 ms on config 2; off by default so that the per-phase CUDA-event times
+        that bench.py reports are those of the kernels alone)"""
         t = timer or PhaseTimer(False)
         hooks = hooks or {}
         ctx, dim, p, ne = self.ctx, self.dim, self.p, self.ne
@@ -79,20 +97,28 @@ class CutAssembly:
         t_if = ops.gather_rows(self.el_dofs, l_if, dofmap, ctx=ctx)
         t.mark("restrict")
         order = 2 * p  # symboliccutbfi.cpp:100-118 (ID*ID present: min diff order 0)
-        # (c) uncut NEG elements: shared standard rule
-        m_neg = ops.elmat_std(dim, p, l_neg, els, xyz, phi, order, TERMS_VOL, ctx=ctx)
-        t.mark("elmat_uncut")
-        # (b) cut quadrature + (c) cut element matrices: NEG part, then the IF integrator added
-        off, q, w = ops.cutquad(dim, l_if, els, xyz, phi, ops.NEG, order, ctx=ctx)
-        t.mark("cutquad")
-        m_if = ops.elmat_rule(dim, p, l_if, els, xyz, phi, off, q, w, TERMS_VOL, ctx=ctx)
-        t.mark("elmat_cut")
-        off2, q2, w2 = ops.cutquad(dim, l_if, els, xyz, phi, ops.IF, order, ctx=ctx)
-        t.mark("cutquad")
-        ops.elmat_rule(dim, p, l_if, els, xyz, phi, off2, q2, w2, TERMS_IF, out=m_if, accumulate=True, ctx=ctx)
-        t.mark("elmat_cut")
-        ctx.raise_on_geometry_error()
-        # (e) graph + scatter
+        main = torch.cuda.current_stream(self.dev)
+        side, ctx2 = (self.side_stream, self.ctx2) if concurrent else (main, ctx)
+        m_neg = torch.empty((l_neg.numel(), self.nd, self.nd), dtype=torch.float64, device=self.dev)
+        m_if = torch.empty((l_if.numel(), self.nd, self.nd), dtype=torch.float64, device=self.dev)
+        if concurrent:
+            side.wait_stream(main)
+        with torch.cuda.stream(side):
+            # (b) cut quadrature: the two count passes first (each synchronises the SIDE stream only, while it is
+            # still short), then everything else of this branch is enqueued without a host wait
+            off, n1 = ops.cutquad_count(dim, l_if, els, phi, ops.NEG, order, ctx=ctx2)
+            off2, n2 = ops.cutquad_count(dim, l_if, els, phi, ops.IF, order, ctx=ctx2)
+            q, w = ops.cutquad_fill(dim, l_if, els, xyz, phi, ops.NEG, order, off, n1, ctx=ctx2)
+            q2, w2 = ops.cutquad_fill(dim, l_if, els, xyz, phi, ops.IF, order, off2, n2, ctx=ctx2)
+            # (c) element matrices: uncut NEG elements with the shared standard rule; cut elements NEG part,
+            # then the IF integrator accumulated into the same matrices
+            ops.elmat_std(dim, p, l_neg, els, xyz, phi, order, TERMS_VOL, out=m_neg, ctx=ctx2)
+            ops.elmat_rule(dim, p, l_if, els, xyz, phi, off, q, w, TERMS_VOL, out=m_if, ctx=ctx2)
+            ops.elmat_rule(dim, p, l_if, els, xyz, phi, off2, q2, w2, TERMS_IF, out=m_if, accumulate=True, ctx=ctx2)
+            for t_ in (off, off2, q, w, q2, w2):
+                t_.record_stream(side)
+        t.mark("elmat")
+        # (e) graph on the main stream, concurrently
         tables = [t_neg, t_if]
         plan = ops.csr_plan(ndof, tables, ctx=ctx)
         t.mark("csr_plan")
@@ -100,13 +126,17 @@ class CutAssembly:
         t.mark("csr_pattern")
         if "pattern" in hooks:
             hooks["pattern"](dict(rowptr=rowptr, col=col))
+        if concurrent:
+            main.wait_stream(side)
+        ctx2.raise_on_geometry_error()
+        t.mark("elmat_join")
         vals = ops.csr_scatter(plan, [(t_neg, m_neg), (t_if, m_if)], rowptr, col)
         t.mark("csr_scatter")
         if "values" in hooks:
             hooks["values"](dict(vals=vals))
         out = dict(ndof=ndof, nnz=plan.nnz, n_neg=l_neg.numel(), n_if=l_if.numel(),
                    units=l_neg.numel() + l_if.numel(), rowptr=rowptr, col=col, vals=vals,
-                   bits=(bn, bp, bi), cut_ratio=cr, npts=(w.numel(), w2.numel()))
+                   bits=(bn, bp, bi), cut_ratio=cr, npts=(n1, n2))
         if keep:
             out.update(l_neg=l_neg, l_if=l_if, t_neg=t_neg, t_if=t_if, m_neg=m_neg, m_if=m_if)
         return out
