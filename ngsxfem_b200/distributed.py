@@ -27,7 +27,7 @@ Per assembly:
 The result is a row-distributed CSR (rows = owned dofs) with global column ids.
 
 The compute backend is duck-typed (`classify`, `elmats`, `csr`): `GpuBackend` below drives the
-CUDA kernels through the C ABI; the CPU gloo tests inject a checker backend built on the oracle.
+CUDA kernels through the C ABI; the CPU gloo tests inject their own checker backend (tests/dist_backend.py).
 """
 import torch
 import torch.distributed as dist
