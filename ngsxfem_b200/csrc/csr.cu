@@ -136,7 +136,7 @@ __global__ void __launch_bounds__(256) k_pattern(int ndof, const long long* __re
                                                  const long long* __restrict__ adj, BatchDev bd, int HCAP, int SL, int G,
                                                  const long long* __restrict__ candoff,
                                                  int32_t* __restrict__ tmpcol, int32_t* __restrict__ rowcnt,
-                                                 int* __restrict__ stats)
+                                                 int* __restrict__ stats, int small_max)
 {
   extern __shared__ int sbuf[];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
@@ -148,6 +148,7 @@ __global__ void __launch_bounds__(256) k_pattern(int ndof, const long long* __re
   for (int d = warp0; d < ndof; d += nwarps) {
     const long long o = candoff[d];
     const int cand = (int)(candoff[d + 1] - o);
+    if (cand <= small_max) continue;  // rows of k_pattern_small (it also writes the empty rows)
     if (cand == 0) { if (lane == 0) rowcnt[d] = 0; continue; }
     // table size: power of two >= 1.25 * candidates (duplicates keep the load far lower)
     int H = 32, shift = 27;
@@ -225,6 +226,127 @@ __global__ void __launch_bounds__(256) k_pattern(int ndof, const long long* __re
   if (lane == 0 && mymax > 0) atomicMax(stats + 2, mymax);
 }
 
+// ---- short rows (at most XG_SMALL_CAND candidates, e.g. the edge dofs of a P2 tet mesh: 4-6
+// adjacent elements): one THREAD per row.  The warp-per-row pass above spends most of its
+// instructions on per-row fixed costs when a row only has 40-60 candidates; here every thread owns
+// a private 64-slot hash set in shared memory, laid out slot-major (slot s of thread t at
+// [s * blockDim + t]) so that the 32 lanes of a warp always hit 32 different banks, inserts its
+// candidates serially (no atomics, no warp synchronisation), and compacts + insertion-sorts the
+// survivors in place.
+#define XG_SMALL_CAND 63
+#define XG_SMALL_H 64
+#define XG_SMALL_BLOCK 128
+#define XG_SMALL_CH 10  // table entries loaded per batch (even)
+template <bool DUPS>
+__global__ void __launch_bounds__(XG_SMALL_BLOCK) k_pattern_small(int ndof, const long long* __restrict__ adj_ptr,
+                                                                  const long long* __restrict__ adj, BatchDev bd,
+                                                                  const long long* __restrict__ candoff,
+                                                                  int32_t* __restrict__ tmpcol, int32_t* __restrict__ rowcnt,
+                                                                  int* __restrict__ stats)
+{
+  __shared__ int stab[XG_SMALL_H * XG_SMALL_BLOCK];
+  int* tab = stab + threadIdx.x;
+#define TAB(s) tab[(s) * XG_SMALL_BLOCK]
+  int mymax = 0;
+  for (int d = blockIdx.x * XG_SMALL_BLOCK + threadIdx.x; d < ndof; d += gridDim.x * XG_SMALL_BLOCK) {
+    const long long o = candoff[d];
+    const int cand = (int)(candoff[d + 1] - o);
+    if (cand > XG_SMALL_CAND) continue;
+    if (cand == 0) { rowcnt[d] = 0; continue; }
+#pragma unroll
+    for (int k = 0; k < XG_SMALL_H; k++) TAB(k) = XG_EMPTY;
+    const long long a = adj_ptr[d];
+    const int na = (int)(adj_ptr[d + 1] - a);
+    long long prev = -1;
+    long long e_next = adj[a];
+    for (int t = 0; t < na; t++) {
+      const long long e = e_next;
+      if (t + 1 < na) e_next = adj[a + t + 1];
+      if (DUPS) {
+        const bool same = (XG_ADJ_ROWKEY(e) == prev);
+        prev = XG_ADJ_ROWKEY(e);
+        if (same) continue;
+      }
+      const int bi = XG_ADJ_BATCH(e);
+      const int w = bd.width[bi];
+      const int32_t* __restrict__ row = bd.table[bi] + XG_ADJ_ROW(e) * w;
+      for (int j0 = 0; j0 < w; j0 += XG_SMALL_CH) {
+        int cc[XG_SMALL_CH];  // the whole chunk is loaded before the first probe (loads in flight)
+        if ((w & 1) == 0) {   // even width: rows are 8-byte aligned
+#pragma unroll
+          for (int u = 0; u < XG_SMALL_CH; u += 2) {
+            int2 v = make_int2(-1, -1);
+            if (j0 + u < w) v = __ldg(reinterpret_cast<const int2*>(row + j0 + u));
+            cc[u] = v.x; cc[u + 1] = v.y;
+          }
+        } else {
+#pragma unroll
+          for (int u = 0; u < XG_SMALL_CH; u++) cc[u] = (j0 + u < w) ? __ldg(row + j0 + u) : -1;
+        }
+#pragma unroll
+        for (int u = 0; u < XG_SMALL_CH; u++) {
+          const int c = cc[u];
+          if (c >= 0) {
+            unsigned h = ((unsigned)c * 2654435761u) >> 26;
+            while (true) {  // at most 63 keys in 64 slots: an empty slot always ends the probe
+              const int old = TAB(h);
+              if (old == c) break;
+              if (old == XG_EMPTY) { TAB(h) = c; break; }
+              h = (h + 1) & (XG_SMALL_H - 1);
+            }
+          }
+        }
+      }
+    }
+    // compaction of the occupied slots (write index <= read index) ...
+    int nu = 0;
+#pragma unroll
+    for (int k = 0; k < XG_SMALL_H; k++) {
+      const int x = TAB(k);
+      if (x != XG_EMPTY) { TAB(nu) = x; nu++; }
+    }
+    rowcnt[d] = nu;
+    mymax = max(mymax, nu);
+    if (nu <= 32) {
+      // ... then a bitonic network on 32 REGISTERS (fully unrolled, static indices: no memory traffic,
+      // no divergence between the rows of a warp), padded with XG_EMPTY which sorts to the end
+      int r[32];
+#pragma unroll
+      for (int k = 0; k < 32; k++) r[k] = (k < nu) ? TAB(k) : XG_EMPTY;
+#pragma unroll
+      for (int size = 2; size <= 32; size <<= 1)
+#pragma unroll
+        for (int stride = size >> 1; stride > 0; stride >>= 1)
+#pragma unroll
+          for (int i = 0; i < 32; i++) {
+            const int l = i ^ stride;
+            if (l > i) {
+              const int lo = min(r[i], r[l]), hi = max(r[i], r[l]);
+              if ((i & size) == 0) { r[i] = lo; r[l] = hi; } else { r[i] = hi; r[l] = lo; }
+            }
+          }
+#pragma unroll
+      for (int k = 0; k < 32; k++) if (k < nu) tmpcol[o + k] = r[k];
+    } else {
+      for (int i = 1; i < nu; i++) {  // rare: insertion sort in shared memory
+        const int x = TAB(i);
+        int j = i - 1;
+        while (j >= 0) {
+          const int y = TAB(j);
+          if (y <= x) break;
+          TAB(j + 1) = y;
+          j--;
+        }
+        TAB(j + 1) = x;
+      }
+      for (int k = 0; k < nu; k++) tmpcol[o + k] = TAB(k);
+    }
+  }
+#undef TAB
+  mymax = __reduce_max_sync(0xffffffffu, mymax);
+  if ((threadIdx.x & 31) == 0 && mymax > 0) atomicMax(stats + 2, mymax);
+}
+
 // copy the unique columns of every row from the candidate-offset scratch to the final CSR
 __global__ void __launch_bounds__(256) k_compact(int64_t ndof, const long long* __restrict__ candoff,
                                                  const long long* __restrict__ rowptr, const int32_t* __restrict__ tmpcol,
@@ -254,7 +376,7 @@ template <bool DUPS>
 __global__ void __launch_bounds__(256) k_scatter(int ndof, const long long* __restrict__ adj_ptr,
                                                  const long long* __restrict__ adj, BatchDev bd, int RCAP, int HS, int GS,
                                                  int NG, int trips, const long long* __restrict__ rowptr,
-                                                 const int32_t* __restrict__ colidx, double* __restrict__ vals)
+                                                 const int32_t* __restrict__ colidx, double* __restrict__ vals, int small_nr)
 {
   extern __shared__ double sacc[];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, nwb = blockDim.x >> 5;
@@ -273,7 +395,7 @@ __global__ void __launch_bounds__(256) k_scatter(int ndof, const long long* __re
     if (have) {
       r0 = rowptr[d]; nr = (int)(rowptr[d + 1] - r0);
       a = adj_ptr[d]; na = (int)(adj_ptr[d + 1] - a);
-      if (nr == 0) na = 0;
+      if (nr <= small_nr) { nr = 0; na = 0; }  // empty rows, and the short rows of k_scatter_small
     }
     // hash size for this row: power of two >= 1.5 * nr (<= HS by the host's sizing)
     int H = 16, shift = 28;
@@ -363,6 +485,84 @@ __global__ void __launch_bounds__(256) k_scatter(int ndof, const long long* __re
   }
 }
 
+// ---- short rows (at most 32 nonzeros): one THREAD per row.  The row's sorted columns and FP64
+// accumulators sit in the thread's private, bank-conflict-free column of shared memory
+// (slot k of thread t at [k * blockDim + t]); every contribution finds its slot with a branch-free
+// 5-step binary search and is added in (batch, table row, local index) order — the same order as
+// the lane-group kernel above, without any per-row warp bookkeeping.
+#define XG_SMALL_NR 32
+__global__ void __launch_bounds__(XG_SMALL_BLOCK) k_scatter_small(int ndof, const long long* __restrict__ adj_ptr,
+                                                                  const long long* __restrict__ adj, BatchDev bd,
+                                                                  const long long* __restrict__ rowptr,
+                                                                  const int32_t* __restrict__ colidx, double* __restrict__ vals)
+{
+  extern __shared__ double ssm[];
+  double* acc = ssm + threadIdx.x;
+  int* cols = reinterpret_cast<int*>(ssm + XG_SMALL_NR * XG_SMALL_BLOCK) + threadIdx.x;
+#define ACC(k) acc[(k) * XG_SMALL_BLOCK]
+#define COL(k) cols[(k) * XG_SMALL_BLOCK]
+  for (int d = blockIdx.x * XG_SMALL_BLOCK + threadIdx.x; d < ndof; d += gridDim.x * XG_SMALL_BLOCK) {
+    const long long r0 = rowptr[d];
+    const int nr = (int)(rowptr[d + 1] - r0);
+    if (nr == 0 || nr > XG_SMALL_NR) continue;
+#pragma unroll
+    for (int k = 0; k < XG_SMALL_NR; k++) {
+      COL(k) = (k < nr) ? __ldg(colidx + r0 + k) : XG_EMPTY;
+      ACC(k) = 0.0;
+    }
+    const long long a = adj_ptr[d];
+    const int na = (int)(adj_ptr[d + 1] - a);
+    for (int t = 0; t < na; t++) {
+      const long long e = adj[a + t];
+      const int bi = XG_ADJ_BATCH(e);
+      const double* __restrict__ mb = bd.mats[bi];
+      if (!mb) continue;  // sparsity-only batch
+      const int w = bd.width[bi];
+      const int ro = XG_ADJ_ROW(e) * w;
+      const int32_t* __restrict__ trow = bd.table[bi] + ro;
+      const double* __restrict__ mrow = mb + (size_t)(ro + XG_ADJ_LOC(e)) * w;
+      for (int j0 = 0; j0 < w; j0 += XG_SMALL_CH) {
+        int cc[XG_SMALL_CH];
+        double mm[XG_SMALL_CH];  // table and matrix entries of the chunk are in flight together
+        if ((w & 1) == 0) {      // even width: 8-byte aligned table rows, 16-byte aligned matrix rows
+#pragma unroll
+          for (int u = 0; u < XG_SMALL_CH; u += 2) {
+            int2 v = make_int2(-1, -1);
+            double2 m2 = make_double2(0.0, 0.0);
+            if (j0 + u < w) {
+              v = __ldg(reinterpret_cast<const int2*>(trow + j0 + u));
+              m2 = __ldg(reinterpret_cast<const double2*>(mrow + j0 + u));
+            }
+            cc[u] = v.x; cc[u + 1] = v.y; mm[u] = m2.x; mm[u + 1] = m2.y;
+          }
+        } else {
+#pragma unroll
+          for (int u = 0; u < XG_SMALL_CH; u++) {
+            const bool in = j0 + u < w;
+            cc[u] = in ? __ldg(trow + j0 + u) : -1;
+            mm[u] = in ? __ldg(mrow + j0 + u) : 0.0;
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < XG_SMALL_CH; u++) {
+          const int c = cc[u];
+          if (c >= 0) {
+            int pos = (COL(16) <= c) ? 16 : 0;
+            pos += (COL(pos + 8) <= c) ? 8 : 0;
+            pos += (COL(pos + 4) <= c) ? 4 : 0;
+            pos += (COL(pos + 2) <= c) ? 2 : 0;
+            pos += (COL(pos + 1) <= c) ? 1 : 0;
+            ACC(pos) += mm[u];
+          }
+        }
+      }
+    }
+    for (int k = 0; k < nr; k++) vals[r0 + k] = ACC(k);
+  }
+#undef ACC
+#undef COL
+}
+
 __global__ void k_spmv(int64_t nrows, const long long* __restrict__ rowptr, const int32_t* __restrict__ colidx,
                        const double* __restrict__ vals, const double* __restrict__ x, double* __restrict__ y)
 {
@@ -430,16 +630,25 @@ int run_pattern(xgpu_ctx* ctx, xgpu_plan* P, int* stats)
   lane_split(P->wmax, &SL, &G, &trips);
   unsigned grid = nblk(P->ndof, nw);
   if (grid > XGPU_NSM * 32) grid = XGPU_NSM * 32;
-  if (P->dups) {
-    XGPU_CUDA(ctx, cudaFuncSetAttribute(k_pattern<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-    k_pattern<true><<<grid, nw * 32, sm, ctx->stream>>>((int)P->ndof, P->adj_ptr, P->adj, P->bd, HCAP, SL, G, P->candoff,
-                                                        (int32_t*)sp, P->tmp32, stats);
-  } else {
-    XGPU_CUDA(ctx, cudaFuncSetAttribute(k_pattern<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-    k_pattern<false><<<grid, nw * 32, sm, ctx->stream>>>((int)P->ndof, P->adj_ptr, P->adj, P->bd, HCAP, SL, G, P->candoff,
-                                                         (int32_t*)sp, P->tmp32, stats);
+  {  // short rows first: thread per row
+    unsigned gs = nblk(P->ndof, XG_SMALL_BLOCK);
+    if (gs > XGPU_NSM * 64) gs = XGPU_NSM * 64;
+    if (P->dups) k_pattern_small<true><<<gs, XG_SMALL_BLOCK, 0, ctx->stream>>>((int)P->ndof, P->adj_ptr, P->adj, P->bd, P->candoff, (int32_t*)sp, P->tmp32, stats);
+    else k_pattern_small<false><<<gs, XG_SMALL_BLOCK, 0, ctx->stream>>>((int)P->ndof, P->adj_ptr, P->adj, P->bd, P->candoff, (int32_t*)sp, P->tmp32, stats);
+    XGPU_LAUNCH_CHECK(ctx);
   }
-  XGPU_LAUNCH_CHECK(ctx);
+  if (P->maxcand > XG_SMALL_CAND) {
+    if (P->dups) {
+      XGPU_CUDA(ctx, cudaFuncSetAttribute(k_pattern<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+      k_pattern<true><<<grid, nw * 32, sm, ctx->stream>>>((int)P->ndof, P->adj_ptr, P->adj, P->bd, HCAP, SL, G, P->candoff,
+                                                          (int32_t*)sp, P->tmp32, stats, XG_SMALL_CAND);
+    } else {
+      XGPU_CUDA(ctx, cudaFuncSetAttribute(k_pattern<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+      k_pattern<false><<<grid, nw * 32, sm, ctx->stream>>>((int)P->ndof, P->adj_ptr, P->adj, P->bd, HCAP, SL, G, P->candoff,
+                                                           (int32_t*)sp, P->tmp32, stats, XG_SMALL_CAND);
+    }
+    XGPU_LAUNCH_CHECK(ctx);
+  }
   P->epoch = ++ctx->epoch;
   return XGPU_OK;
 }
@@ -559,14 +768,23 @@ extern "C" int xgpu_csr_scatter(xgpu_ctx* ctx, xgpu_plan* P, const xgpu_batch* b
   if (sm > 220 * 1024) return xgpu_fail(ctx, XGPU_ERR_CAPACITY, "csr: a row is too long for the shared-memory gather");
   unsigned grid = nblk(P->ndof, nw * G);
   if (grid > XGPU_NSM * 32) grid = XGPU_NSM * 32;
+  {  // short rows: thread per row
+    unsigned gs = nblk(P->ndof, XG_SMALL_BLOCK);
+    if (gs > XGPU_NSM * 64) gs = XGPU_NSM * 64;
+    const size_t sms = (size_t)XG_SMALL_NR * XG_SMALL_BLOCK * (sizeof(double) + sizeof(int));
+    XGPU_CUDA(ctx, cudaFuncSetAttribute(k_scatter_small, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sms));
+    k_scatter_small<<<gs, XG_SMALL_BLOCK, sms, ctx->stream>>>((int)P->ndof, P->adj_ptr, P->adj, bd, (const long long*)rowptr, colidx, vals);
+    XGPU_LAUNCH_CHECK(ctx);
+  }
+  if (P->maxnr <= XG_SMALL_NR) return XGPU_OK;
   if (P->dups) {
     XGPU_CUDA(ctx, cudaFuncSetAttribute(k_scatter<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
     k_scatter<true><<<grid, nw * 32, sm, ctx->stream>>>((int)P->ndof, P->adj_ptr, P->adj, bd, RCAP, HS, SL, G, trips,
-                                                        (const long long*)rowptr, colidx, vals);
+                                                        (const long long*)rowptr, colidx, vals, XG_SMALL_NR);
   } else {
     XGPU_CUDA(ctx, cudaFuncSetAttribute(k_scatter<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
     k_scatter<false><<<grid, nw * 32, sm, ctx->stream>>>((int)P->ndof, P->adj_ptr, P->adj, bd, RCAP, HS, SL, G, trips,
-                                                         (const long long*)rowptr, colidx, vals);
+                                                         (const long long*)rowptr, colidx, vals, XG_SMALL_NR);
   }
   XGPU_LAUNCH_CHECK(ctx);
   return XGPU_OK;
