@@ -47,6 +47,9 @@ typedef struct xgpu_plan xgpu_plan;
 int xgpu_create(int device, xgpu_ctx** ctx_out);
 void xgpu_destroy(xgpu_ctx* ctx);
 int xgpu_set_stream(xgpu_ctx* ctx, void* cuda_stream);
+/* tuning switches (no reference counterpart).  "elmat_dmma": element-matrix contraction on FP64
+ * tensor-core tiles: -1 never, 0 (default) at FE order >= 3, 1 also at order 2 */
+int xgpu_set_option(xgpu_ctx* ctx, const char* key, int value);
 int xgpu_sync(xgpu_ctx* ctx);
 const char* xgpu_last_error(xgpu_ctx* ctx);
 /* per-element geometry error recorded by kernels since the last xgpu_clear_status; syncs. */

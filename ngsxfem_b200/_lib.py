@@ -35,6 +35,7 @@ _SIGS = {
     "xgpu_create": (C.c_int, [C.c_int, C.POINTER(VP)]),
     "xgpu_destroy": (None, [VP]),
     "xgpu_set_stream": (C.c_int, [VP, VP]),
+    "xgpu_set_option": (C.c_int, [VP, C.c_char_p, C.c_int]),
     "xgpu_sync": (C.c_int, [VP]),
     "xgpu_last_error": (C.c_char_p, [VP]),
     "xgpu_get_status": (C.c_int, [VP, c_intp, c_i64p]),
@@ -133,6 +134,9 @@ class Ctx:
         if s != getattr(self, "_stream", None):
             self.check(self.lib.xgpu_set_stream(self.h, VP(s)))
             self._stream = s
+
+    def set_option(self, key, value):
+        self.check(self.lib.xgpu_set_option(self.h, key.encode(), int(value)))
 
     def check(self, rc):
         if rc != 0:

@@ -30,6 +30,7 @@ struct xgpu_ctx {
   // grow-only scratch arena (slots by index so independent temporaries do not alias)
   void* scratch[XGPU_NSCRATCH] = {};
   size_t scratch_bytes[XGPU_NSCRATCH] = {};
+  int opt_dmma = 0;   // element matrices on FP64 tensor tiles: -1 never, 0 at order >= 3, 1 also at order 2
   int64_t epoch = 0;  // bumped whenever a plan takes over the shared pattern scratch (slot 8)
   int64_t* h_pinned = nullptr;  // 16 x int64 pinned staging for host scalars
   std::map<std::pair<int, int>, xgpu_rule_host> rules;  // (dim, order) -> rule

@@ -195,6 +195,13 @@ extern "C" int xgpu_set_stream(xgpu_ctx* ctx, void* s)
   return XGPU_OK;
 }
 
+extern "C" int xgpu_set_option(xgpu_ctx* ctx, const char* key, int value)
+{
+  if (!ctx || !key) return XGPU_ERR_ARG;
+  if (std::string(key) == "elmat_dmma") { ctx->opt_dmma = value < 0 ? -1 : (value > 0 ? 1 : 0); return XGPU_OK; }
+  return xgpu_fail(ctx, XGPU_ERR_ARG, "xgpu_set_option: unknown key");
+}
+
 extern "C" int xgpu_sync(xgpu_ctx* ctx)
 {
   if (!ctx) return XGPU_ERR_ARG;

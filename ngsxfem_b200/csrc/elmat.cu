@@ -297,6 +297,155 @@ __global__ void __launch_bounds__(128) k_elmat_ms(
   }
 }
 
+// ---------------------------------------------------------------- FP64 tensor-core contraction (order >= 3)
+// M = sum_q  S_q^T diag(w_q) S_q  with S_q the 4 x nd slab [val ; g0 ; g1 ; g2] of one point: a point
+// IS one k-step of the FP64 tensor instruction (sm_100a lowers every mma.sync f64 shape to
+// DMMA.8x8x4, checked with cuobjdump), so the contraction over the quadrature points is a chain of
+// m8n8k4 MMAs on 8x8 tiles of the element matrix:
+//   A fragment (8 x 4, row i, col c) = w_c S_q[c][8 ti + i]   (lane = 4 i + c)
+//   B fragment (4 x 8, row c, col j) =     S_q[c][8 tj + j]   (lane = 4 j + c)
+// — the SAME shared-memory word, weighted for A, plain for B: per point a lane loads NT values and
+// one weight and issues NT(NT+1)/2 DMMAs (the forms on this path have op_test == op_trial, so only
+// the tiles ti <= tj are computed and mirrored in the epilogue; the reference computes both halves,
+// they agree to rounding).  One warp per element; lanes stage one point each (basis + physical
+// gradients), row stride = 8 mod 16 doubles so that the four component rows of a fragment load fall
+// into disjoint bank groups; the finished tiles go through shared memory for coalesced stores.
+__device__ __forceinline__ void xg_dmma884(double& d0, double& d1, double a, double b)
+{
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+               : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
+}
+
+template <int D>
+struct StageSinkT {
+  double* B;         // this point's slab: 4 rows of RS doubles
+  int rs;
+  const double* Fi;
+  __device__ __forceinline__ void operator()(int i, const AD<D>& a)
+  {
+    B[i] = a.v;
+#pragma unroll
+    for (int c = 0; c < D; c++) {
+      double g = 0.0;
+#pragma unroll
+      for (int j = 0; j < D; j++) g += Fi[j * D + c] * a.d[j];
+      B[(1 + c) * rs + i] = g;
+    }
+  }
+};
+
+template <int D, int P>
+struct DmmaGeom {
+  static constexpr int ND = (D == 1) ? P + 1 : ((D == 2) ? 3 + 3 * (P - 1) + (P - 1) * (P - 2) / 2
+                                                         : 4 + 6 * (P - 1) + 4 * ((P - 1) * (P - 2) / 2) + (P - 1) * (P - 2) * (P - 3) / 6);
+  static constexpr int NT = (ND + 7) / 8, NDP = NT * 8;
+  static constexpr int RS = NDP + ((NDP % 16 == 0) ? 8 : 0);  // row stride: 8 mod 16 doubles
+  static constexpr int PS = 4 * RS + 4;                       // 4 component rows + 4 weights (PS = 4 mod 8: 16 B aligned slabs)
+  static constexpr int NPAIR = NT * (NT + 1) / 2;
+};
+
+template <int D, int P>
+__global__ void __launch_bounds__(160) k_elmat_dmma(
+    int64_t n, const int32_t* __restrict__ elems, const int32_t* __restrict__ el_vtx,
+    const double* __restrict__ vtx_xyz, const int64_t* __restrict__ offsets, const double* __restrict__ pts,
+    const double* __restrict__ wts, int np_shared, int CH, TermsDev T, int accumulate,
+    const int32_t* __restrict__ slots, double* __restrict__ mats)
+{
+  using G = DmmaGeom<D, P>;
+  constexpr int ND = G::ND, NT = G::NT, NDP = G::NDP, RS = G::RS, PS = G::PS, NPAIR = G::NPAIR;
+  extern __shared__ double smem[];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const int fr = lane >> 2, fc = lane & 3;  // fragment row / component
+  double* Bw = smem + (size_t)wib * CH * PS;
+  const int64_t warp0 = (int64_t)blockIdx.x * (blockDim.x >> 5) + wib;
+  const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
+  for (int64_t e = warp0; e < n; e += nwarps) {
+    const int64_t el = elems ? (int64_t)elems[e] : e;
+    int v[D + 1];
+    double vx[D + 1][3], F[D * D], Fi[D * D];
+#pragma unroll
+    for (int k = 0; k < D + 1; k++) {
+      v[k] = __ldg(el_vtx + el * (D + 1) + k);
+#pragma unroll
+      for (int c = 0; c < 3; c++) vx[k][c] = (c < D) ? __ldg(vtx_xyz + (int64_t)v[k] * D + c) : 0.0;
+    }
+    xg_affine_jac<D>(vx, F);
+    const double meas = fabs(xg_inv<D>(F, Fi));
+    const double h = (D == 1) ? meas : ((D == 2) ? sqrt(meas) : cbrt(meas));
+    double cm = 0.0, cs = 0.0;
+    for (int t = 0; t < T.n; t++) {
+      const double c = T.coef[t] * ipow(h, T.hpow[t]) * meas;
+      if (T.op_test[t] == 0) cm += c; else cs += c;
+    }
+    const int64_t q0 = offsets ? offsets[e] : 0;
+    const int npe = offsets ? (int)(offsets[e + 1] - q0) : np_shared;
+    double acc[NPAIR][2];
+#pragma unroll
+    for (int b = 0; b < NPAIR; b++) acc[b][0] = acc[b][1] = 0.0;
+    for (int c0 = 0; c0 < npe; c0 += CH) {
+      const int cnt = min(CH, npe - c0);
+      __syncwarp();
+      for (int ql = lane; ql < cnt; ql += 32) {
+        double* B = Bw + (size_t)ql * PS;
+        const double* xq = pts + 3 * (q0 + c0 + ql);
+        double xh[3] = {xq[0], xq[1], xq[2]};
+#pragma unroll
+        for (int k = 0; k < 4; k++)
+#pragma unroll
+          for (int i = ND; i < NDP; i++) B[k * RS + i] = 0.0;
+        if (D < 3) {
+#pragma unroll
+          for (int k = 1 + D; k < 4; k++)
+            for (int i = 0; i < ND; i++) B[k * RS + i] = 0.0;
+        }
+        StageSinkT<D> sink{B, RS, Fi};
+        xg_h1_shapes<D, P>(v, xh, sink);
+        const double w = wts[q0 + c0 + ql];
+        B[4 * RS] = cm * w;
+        B[4 * RS + 1] = B[4 * RS + 2] = B[4 * RS + 3] = cs * w;
+      }
+      __syncwarp();
+      for (int q = 0; q < cnt; q++) {
+        const double* Sq = Bw + (size_t)q * PS;
+        const double wq = Sq[4 * RS + fc];
+        double sv[NT], av[NT];
+#pragma unroll
+        for (int t = 0; t < NT; t++) { sv[t] = Sq[fc * RS + 8 * t + fr]; av[t] = wq * sv[t]; }
+        int idx = 0;
+#pragma unroll
+        for (int ti = 0; ti < NT; ti++)
+#pragma unroll
+          for (int tj = ti; tj < NT; tj++, idx++) xg_dmma884(acc[idx][0], acc[idx][1], av[ti], sv[tj]);
+      }
+    }
+    // epilogue: tiles -> shared (full NDP x NDP matrix, both halves) -> coalesced global stores
+    __syncwarp();
+    double* Ms = Bw;  // NDP * NDP doubles <= CH * PS (checked on the host)
+    {
+      int idx = 0;
+#pragma unroll
+      for (int ti = 0; ti < NT; ti++)
+#pragma unroll
+        for (int tj = ti; tj < NT; tj++, idx++) {
+          const int i = 8 * ti + fr, j = 8 * tj + 2 * fc;
+          Ms[i * NDP + j] = acc[idx][0];
+          Ms[i * NDP + j + 1] = acc[idx][1];
+          if (ti != tj) {
+            Ms[j * NDP + i] = acc[idx][0];
+            Ms[(j + 1) * NDP + i] = acc[idx][1];
+          }
+        }
+    }
+    __syncwarp();
+    double* M = mats + (size_t)(slots ? (int64_t)slots[e] : e) * ND * ND;
+    for (int k = lane; k < ND * ND; k += 32) {
+      const int i = k / ND, j = k - i * ND;
+      const double val = Ms[i * NDP + j];
+      if (accumulate) M[k] += val; else M[k] = val;
+    }
+  }
+}
+
 // ---------------------------------------------------------------- affine fast path
 template <int D>
 __global__ void __launch_bounds__(256) k_elmat_affine(
@@ -418,11 +567,40 @@ int launch_ms(xgpu_ctx* ctx, int64_t n, const int32_t* elems, const int32_t* el_
   return XGPU_OK;
 }
 
+template <int D, int P>
+int launch_dmma(xgpu_ctx* ctx, int64_t n, const int32_t* elems, const int32_t* el_vtx, const double* vtx_xyz,
+                const int64_t* offsets, const double* pts, const double* wts, int np_shared, const TermsDev& T,
+                int accumulate, const int32_t* slots, double* mats)
+{
+  using G = DmmaGeom<D, P>;
+  // points per chunk: 32 (one per lane) when 4-5 warps of slabs fit the 227 KB of an SM
+  int CH = 32, nw = 4;
+  if ((size_t)5 * CH * G::PS * sizeof(double) <= 220 * 1024 && (size_t)4 * CH * G::PS * sizeof(double) > 110 * 1024) nw = 5;
+  while (CH > 8 && (size_t)nw * CH * G::PS * sizeof(double) > 220 * 1024) CH >>= 1;
+  if (CH * G::PS < G::NDP * G::NDP) return xgpu_fail(ctx, XGPU_ERR_CAPACITY, "elmat: staging buffer smaller than the element matrix");
+  const size_t sm = (size_t)nw * CH * G::PS * sizeof(double);
+  unsigned grid = nblk(n, nw);
+  if (grid > XGPU_NSM * 8) grid = XGPU_NSM * 8;
+  XGPU_CUDA(ctx, cudaFuncSetAttribute(k_elmat_dmma<D, P>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+  k_elmat_dmma<D, P><<<grid, nw * 32, sm, ctx->stream>>>(n, elems, el_vtx, vtx_xyz, offsets, pts, wts, np_shared, CH, T,
+                                                         accumulate, slots, mats);
+  XGPU_LAUNCH_CHECK(ctx);
+  return XGPU_OK;
+}
+
 template <int D>
 int launch_points(xgpu_ctx* ctx, int64_t n, const int32_t* elems, const int32_t* el_vtx, const double* vtx_xyz,
                   const double* phi, const int64_t* offsets, const double* pts, const double* wts, int np_shared,
                   int p, const TermsDev& T, int accumulate, const int32_t* slots, double* mats, bool only_ms = false)
 {
+  // FP64 tensor tiles at order >= 3 (dense contraction); ctx->opt_dmma: -1 never, 0 policy, 1 whenever compiled (p >= 2)
+  if constexpr (D >= 2) if (only_ms && ctx->opt_dmma >= 0 && (p >= 3 || (ctx->opt_dmma > 0 && p == 2))) {
+    switch (p) {
+      case 2: return launch_dmma<D, 2>(ctx, n, elems, el_vtx, vtx_xyz, offsets, pts, wts, np_shared, T, accumulate, slots, mats);
+      case 3: return launch_dmma<D, 3>(ctx, n, elems, el_vtx, vtx_xyz, offsets, pts, wts, np_shared, T, accumulate, slots, mats);
+      case 4: return launch_dmma<D, 4>(ctx, n, elems, el_vtx, vtx_xyz, offsets, pts, wts, np_shared, T, accumulate, slots, mats);
+    }
+  }
   if (only_ms) {
     switch (p) {
       case 1: return launch_ms<D, 1>(ctx, n, elems, el_vtx, vtx_xyz, offsets, pts, wts, np_shared, T, accumulate, slots, mats);

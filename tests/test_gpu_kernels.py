@@ -358,3 +358,39 @@ def test_csr_pattern_and_values_match_oracle(dim, n, p):
     x = np.random.default_rng(0).standard_normal(V.ndof)
     y = ops.csr_spmv(rowptr, col, vals, torch.from_numpy(x).to(DEV)).cpu().numpy()
     assert np.allclose(y, A @ x, rtol=1e-11, atol=1e-12 * np.abs(A @ x).max())
+
+
+@pytest.mark.parametrize("dim,n", [(2, 9), (3, 5)])
+@pytest.mark.parametrize("p", [2, 3, 4])
+def test_elmat_tensor_tiles_match_cuda_core_path_and_oracle(dim, n, p):
+    """north_star (c): the FP64 tensor-core (DMMA) contraction against the CUDA-core kernel and the oracle,
+    cut elements (per-element rules: NEG part + IF mass accumulated) and uncut elements (shared rule)"""
+    from ngsxfem_b200._lib import default_ctx
+    ctx = default_ctx()
+    m = make_mesh(dim, n)
+    phi = level_set(m, "sphere", 30 + dim)
+    pts, els = mesh_np(m)
+    md = to_dev(m)
+    gphi = torch.from_numpy(phi).to(DEV)
+    _, _, gi, _ = ops.classify(dim, md.elements, gphi)
+    lst = ops.bitset_to_list(gi, m.ne)
+    lnp = lst.cpu().numpy()
+    off, q, w = ops.cutquad(dim, lst, md.elements, md.points, gphi, NEG, 2 * p)
+    off2, q2, w2 = ops.cutquad(dim, lst, md.elements, md.points, gphi, IF, 2 * p)
+    res = {}
+    try:
+        for mode in (-1, 1):
+            ctx.set_option("elmat_dmma", mode)
+            g = ops.elmat_rule(dim, p, lst, md.elements, md.points, gphi, off, q, w, TERMS_VOL)
+            ops.elmat_rule(dim, p, lst, md.elements, md.points, gphi, off2, q2, w2, [(0, 0, 3.0, -1)], out=g, accumulate=True)
+            u = ops.elmat_std(dim, 3 if p == 2 else p, None, md.elements, md.points, gphi, 2 * p, TERMS_VOL)
+            res[mode] = (g.cpu().numpy(), u.cpu().numpy())
+    finally:
+        ctx.set_option("elmat_dmma", 0)
+    o = xo.batch_cut_elmats(dim, p, lnp, els, pts, phi, NEG, 2 * p, TERMS_VOL) + \
+        xo.batch_cut_elmats(dim, p, lnp, els, pts, phi, IF, 2 * p, [(0, 0, 3.0, -1)])
+    assert rel_err(res[1][0], o) < 1e-12
+    assert rel_err(res[1][0], res[-1][0]) < 1e-12
+    assert rel_err(res[1][1], res[-1][1]) < 1e-12
+    # the tensor path computes the tiles ti <= tj and mirrors the off-diagonal ones
+    assert rel_err(res[1][0], res[1][0].transpose(0, 2, 1)) < 1e-14
