@@ -133,15 +133,17 @@ class ClockSampler:
 def kernel_bytes(phase, r, nd):
     nn = nd * nd
     if phase == "csr":           # distributed path: plan + pattern + scatter timed as one phase
-        return sum(kernel_bytes(k, r, nd) for k in ("csr_plan", "csr_pattern", "csr_scatter"))
+        return sum(kernel_bytes(k, r, nd) for k in ("csr_adjacency", "csr_pattern_pass", "csr_pattern", "csr_scatter"))
     if phase == "elmat":         # cut quadrature + uncut + cut element matrices
         return kernel_bytes("elmat_uncut", r, nd) + kernel_bytes("elmat_cut", r, nd)
     if phase == "csr_scatter":   # read every element matrix once + dof rows, write vals, read colidx/rowptr
         return r["units"] * (nn * 8 + nd * 4) + r["nnz"] * (8 + 4) + r["ndof"] * 8
-    if phase == "csr_pattern":   # read dof rows (through the adjacency), write colidx + rowptr
-        return r["units"] * nd * (4 + 8) + r["nnz"] * 4 + r["ndof"] * 8
-    if phase == "csr_plan":
-        return r["units"] * nd * (4 + 8) * 2 + r["ndof"] * 16
+    if phase == "csr_pattern":   # compaction copy: read + write colidx, rowptr
+        return r["nnz"] * 8 + r["ndof"] * 16
+    if phase == "csr_pattern_pass":  # read dof rows (through the adjacency), write the sorted unique columns + counts
+        return r["units"] * nd * (4 + 8) + r["nnz"] * 4 + r["ndof"] * 12
+    if phase == "csr_adjacency":     # read the dof rows twice (count, fill), write + sort the transposed table
+        return r["units"] * nd * (4 + 4 + 8 + 16) + r["ndof"] * 24
     if phase == "elmat_uncut":   # 16 B vtx ids + 96 B coords in, nd^2 doubles out
         return r["n_neg"] * (16 + 96 + 4 + nn * 8)
     if phase == "elmat_cut":
@@ -273,6 +275,15 @@ def run_gpu(args):
         peak_src = "MEASURED_PEAKS.json hbm_gbs (of measured)" if "hbm_gbs" in peaks else "6650 GB/s (of fallback)"
         kb = kernel_bytes(dom, res, nd)
         ach = kb / (phases[dom] * 1e-3) / 1e9
+        # DRAM bytes of that phase's kernels from the committed `ncu --set full` capture of this workload
+        # (profiles/ncu_traffic.json: dram__bytes_read.sum + dram__bytes_write.sum per launch), n=128 / 1 GPU only
+        traffic = None
+        try:
+            tj = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+            if world == 1 and n == tj.get("n"):
+                traffic = tj["phases"].get(dom)
+        except Exception:
+            pass
         cpu_baseline = None
         if world == 1:  # the CPU arm is timed on rank 0 at N=1 only (other ranks would compete for the host cores)
             cpu_val, cores, cinfo = cpu_sample(SAMPLE_N, 2, 1)
@@ -292,7 +303,7 @@ def run_gpu(args):
                     "steps": e2e_steps, "h2d_bytes_per_step": info["h2d"], "d2h_bytes_per_step": info["d2h"]},
             "gpu_launches": int(launches),
             "roofline": {"kernel": dom, "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                         "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": kb,
+                         "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_launch": kb,
                          "ms_per_launch": phases[dom]},
             "cpu_baseline": cpu_baseline,
             "clocks": clocks,

@@ -50,6 +50,15 @@ int xgpu_set_stream(xgpu_ctx* ctx, void* cuda_stream);
 /* tuning switches (no reference counterpart).  "elmat_dmma": element-matrix contraction on FP64
  * tensor-core tiles: -1 never, 0 (default) at FE order >= 3, 1 also at order 2 */
 int xgpu_set_option(xgpu_ctx* ctx, const char* key, int value);
+/* Isoparametric mesh deformation — the state NGSolve keeps in the mesh (`mesh.SetDeformation(gf)`, set and
+ * unset around every assembly by the `deformation=` argument of dCut / dFacetPatch / Integrate,
+ * python/__init__.py:361-439,749-864; cutint/cutintegral.cpp:126-212): while set, every geometric call
+ * below (xgpu_cutquad_fill for dt=IF, xgpu_elmat_*, xgpu_facetpatch, xgpu_integrate_monomial) uses
+ *   x(xhat) = x_affine(xhat) + sum_j d_j phi_j(xhat),   F = F_affine + sum_j d_j (x) grad phi_j
+ * with d in H1(order)^dim: el_dofs ne x xgpu_h1_ndof(dim, order) (same mesh element numbering as el_vtx),
+ * vals ndof x dim.  The arrays must stay valid until the deformation is unset (order = 0 / NULL).
+ * Multi-level-set and space-time rules do not support a deformation (XGPU_ERR_UNSUPPORTED). */
+int xgpu_set_deformation(xgpu_ctx* ctx, int order, const int32_t* el_dofs, const double* vals);
 int xgpu_sync(xgpu_ctx* ctx);
 const char* xgpu_last_error(xgpu_ctx* ctx);
 /* per-element geometry error recorded by kernels since the last xgpu_clear_status; syncs. */
@@ -182,6 +191,9 @@ int xgpu_csr_pattern(xgpu_ctx* ctx, xgpu_plan* plan, int64_t* rowptr, int32_t* c
 int xgpu_csr_scatter(xgpu_ctx* ctx, xgpu_plan* plan, const xgpu_batch* batches_host, int nbatches,
                      const int64_t* rowptr, const int32_t* colidx, double* vals);
 void xgpu_plan_destroy(xgpu_plan* plan);
+/* device time of the two halves of xgpu_csr_plan (CUDA events on the plan's stream): ms_host[0] =
+ * transposed table (histogram, scan, fill, segment sort), ms_host[1] = pattern pass (bench.py) */
+int xgpu_plan_phase_ms(xgpu_plan* plan, double* ms_host);
 /* y = A x for checks (CSR SpMV, one warp per row) */
 int xgpu_csr_spmv(xgpu_ctx* ctx, int64_t nrows, const int64_t* rowptr, const int32_t* colidx,
                   const double* vals, const double* x, double* y);

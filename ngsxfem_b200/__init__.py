@@ -11,7 +11,7 @@ Importing the package does not need a GPU (tables, meshes and symbol checks work
 """
 from ._lib import XgpuError, LIB_PATH, exported_symbols, load as load_library
 from .meshes import Mesh, MakeStructured1DMesh, MakeStructured2DMesh, MakeStructured3DMesh
-from .fes import H1, Restrict
+from .fes import H1, Restrict, Deformation
 from .cutinfo import (NEG, POS, IF, VOL, BND, HAS, BitArray, GridFunction, InterpolateToP1, CutInfo,
                       MultiLevelsetCutInfo, GetFacetsWithNeighborTypes, GetElementsWithNeighborFacets,
                       GetDofsOfElements, CombinedDomainType)

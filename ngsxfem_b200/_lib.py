@@ -36,6 +36,7 @@ _SIGS = {
     "xgpu_destroy": (None, [VP]),
     "xgpu_set_stream": (C.c_int, [VP, VP]),
     "xgpu_set_option": (C.c_int, [VP, C.c_char_p, C.c_int]),
+    "xgpu_set_deformation": (C.c_int, [VP, C.c_int, VP, VP]),
     "xgpu_sync": (C.c_int, [VP]),
     "xgpu_last_error": (C.c_char_p, [VP]),
     "xgpu_get_status": (C.c_int, [VP, c_intp, c_i64p]),
@@ -78,6 +79,7 @@ _SIGS = {
     "xgpu_csr_pattern": (C.c_int, [VP, VP, VP, VP]),
     "xgpu_csr_scatter": (C.c_int, [VP, VP, C.POINTER(Batch), C.c_int, VP, VP, VP]),
     "xgpu_plan_destroy": (None, [VP]),
+    "xgpu_plan_phase_ms": (C.c_int, [VP, c_f64p]),
     "xgpu_csr_spmv": (C.c_int, [VP, C.c_int64, VP, VP, VP, VP, VP]),
 }
 
@@ -138,6 +140,11 @@ class Ctx:
     def set_option(self, key, value):
         self.check(self.lib.xgpu_set_option(self.h, key.encode(), int(value)))
 
+    def deformation(self, defo):
+        """context manager: `with ctx.deformation(d): ...` = mesh.SetDeformation(d) ... mesh.UnsetDeformation()
+        (python/__init__.py: the `deformation=` argument of dCut / dFacetPatch / Integrate); d=None: no-op"""
+        return _DeformationScope(self, defo)
+
     def check(self, rc):
         if rc != 0:
             msg = self.lib.xgpu_last_error(self.h)
@@ -169,6 +176,23 @@ class Ctx:
                 self.h = None
         except Exception:
             pass
+
+
+class _DeformationScope:
+    def __init__(self, ctx, defo):
+        self.ctx, self.defo = ctx, defo
+
+    def __enter__(self):
+        d = self.defo
+        if d is not None:
+            assert d.el_dofs.is_contiguous() and d.vals.is_contiguous()
+            self.ctx.check(self.ctx.lib.xgpu_set_deformation(self.ctx.h, int(d.order), d.el_dofs.data_ptr(), d.vals.data_ptr()))
+        return self
+
+    def __exit__(self, *a):
+        if self.defo is not None:
+            self.ctx.check(self.ctx.lib.xgpu_set_deformation(self.ctx.h, 0, None, None))
+        return False
 
 
 _CTX = {}

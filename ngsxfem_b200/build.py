@@ -19,7 +19,7 @@ NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 # straightcutrule.cpp:548-556) from floating-point values at the 1e-14 threshold; they are compiled
 # without FMA contraction so that those decisions are taken from the same IEEE operations as the
 # CPU restatement (gcc -ffp-contract=off).  The dense contraction kernels keep FMA.
-NO_FMA = {"cutquad.cu", "cutquad_ext.cu", "classify.cu"}
+NO_FMA = {"cutquad.cu", "cutquad_ext.cu", "classify.cu", "deform.cu"}
 FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
          "-Xcompiler", "-fPIC", "-ccbin", "/usr/bin/g++", "--expt-relaxed-constexpr"]
 

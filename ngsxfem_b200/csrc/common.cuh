@@ -30,6 +30,10 @@ struct xgpu_ctx {
   // grow-only scratch arena (slots by index so independent temporaries do not alias)
   void* scratch[XGPU_NSCRATCH] = {};
   size_t scratch_bytes[XGPU_NSCRATCH] = {};
+  // current mesh deformation (xgpu_set_deformation): order 0 = none
+  int def_order = 0;
+  const int32_t* def_el_dofs = nullptr;  // ne x nd(def_order)
+  const double* def_vals = nullptr;      // ndof x dim
   int opt_dmma = 0;   // element matrices on FP64 tensor tiles: -1 never, 0 at order >= 3, 1 also at order 2
   int64_t epoch = 0;  // bumped whenever a plan takes over the shared pattern scratch (slot 8)
   int64_t* h_pinned = nullptr;  // 16 x int64 pinned staging for host scalars
@@ -89,5 +93,13 @@ __device__ __forceinline__ void xgpu_record_error(int* status, unsigned long lon
 int xgpu_exclusive_scan_i32(xgpu_ctx* ctx, const int32_t* in, int64_t n, int64_t* out);
 // the same with 32-bit output offsets (n+1 entries)
 int xgpu_exclusive_scan_i32_o32(xgpu_ctx* ctx, const int32_t* in, int64_t n, int32_t* out);
+
+// deform.cu: per-point interface weight factor / integrals on the deformed mesh (ctx->def_* set)
+int xgpu_if_weights_def(xgpu_ctx* ctx, int dim, int64_t n, const int32_t* elems, const int32_t* el_vtx,
+                        const double* vtx_xyz, const double* phi, const int64_t* offsets, const double* pts, double* wts);
+int xgpu_integrate_def(xgpu_ctx* ctx, int dim, int64_t n, const int32_t* elems, const int32_t* el_vtx,
+                       const double* vtx_xyz, const int64_t* offsets, const double* pts, const double* wts,
+                       int e0, int e1, int e2, double* elsum);
+int xgpu_sum_f64(xgpu_ctx* ctx, double* buf_a, int64_t n, double* buf_b, double* result_host);
 
 const xgpu_rule_host* xgpu_rule_lookup(xgpu_ctx* ctx, int dim, int order);

@@ -46,6 +46,7 @@ struct xgpu_plan {
   long long* candoff = nullptr;   // ndof+1: offsets of the rows in the candidate scratch
   int32_t* tmp32 = nullptr;       // ndof+2 counters
   cudaStream_t stream = 0;        // the buffers are stream-ordered allocations on this stream
+  cudaEvent_t ev[3] = {};         // start / adjacency built / pattern pass done (xgpu_plan_phase_ms)
 };
 
 namespace {
@@ -599,6 +600,7 @@ extern "C" void xgpu_plan_destroy(xgpu_plan* p)
   if (p->rowptr) cudaFreeAsync(p->rowptr, p->stream);
   if (p->candoff) cudaFreeAsync(p->candoff, p->stream);
   if (p->tmp32) cudaFreeAsync(p->tmp32, p->stream);
+  for (int i = 0; i < 3; i++) if (p->ev[i]) cudaEventDestroy(p->ev[i]);
   delete p;
 }
 
@@ -670,6 +672,8 @@ extern "C" int xgpu_csr_plan(xgpu_ctx* ctx, int64_t ndof, const xgpu_batch* batc
   P->stream = st;
 #define XG_TRY(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { xgpu_plan_destroy(P); return xgpu_fail(ctx, XGPU_ERR_CUDA, cudaGetErrorString(e_)); } } while (0)
 #define XG_TRYRC(call) do { int r_ = (call); if (r_) { xgpu_plan_destroy(P); return r_; } } while (0)
+  for (int i = 0; i < 3; i++) XG_TRY(cudaEventCreate(&P->ev[i]));
+  XG_TRY(cudaEventRecord(P->ev[0], st));
   XG_TRY(cudaMallocAsync(&P->adj_ptr, sizeof(long long) * (ndof + 1), st));
   XG_TRY(cudaMallocAsync(&P->rowptr, sizeof(long long) * (ndof + 1), st));
   XG_TRY(cudaMallocAsync(&P->candoff, sizeof(long long) * (ndof + 1), st));
@@ -703,6 +707,7 @@ extern "C" int xgpu_csr_plan(xgpu_ctx* ctx, int64_t ndof, const xgpu_batch* batc
     ctx->launches++;
   }
   XG_TRYRC(xgpu_exclusive_scan_i32(ctx, P->tmp32, ndof, (int64_t*)P->candoff));
+  XG_TRY(cudaEventRecord(P->ev[1], st));
   XG_TRY(cudaMemcpyAsync(ctx->h_pinned, stats, 2 * sizeof(int), cudaMemcpyDeviceToHost, st));
   XG_TRY(cudaMemcpyAsync(ctx->h_pinned + 1, P->candoff + ndof, sizeof(long long), cudaMemcpyDeviceToHost, st));
   XG_TRY(cudaStreamSynchronize(st));
@@ -711,6 +716,7 @@ extern "C" int xgpu_csr_plan(xgpu_ctx* ctx, int64_t ndof, const xgpu_batch* batc
   P->ncand = ctx->h_pinned[1];
   if (ndof > 0) XG_TRYRC(run_pattern(ctx, P, stats));
   XG_TRYRC(xgpu_exclusive_scan_i32(ctx, P->tmp32, ndof, (int64_t*)P->rowptr));
+  XG_TRY(cudaEventRecord(P->ev[2], st));
   XG_TRY(cudaMemcpyAsync(ctx->h_pinned, P->rowptr + ndof, sizeof(long long), cudaMemcpyDeviceToHost, st));
   XG_TRY(cudaMemcpyAsync(ctx->h_pinned + 1, stats + 2, sizeof(int), cudaMemcpyDeviceToHost, st));
   XG_TRY(cudaStreamSynchronize(st));
@@ -721,6 +727,16 @@ extern "C" int xgpu_csr_plan(xgpu_ctx* ctx, int64_t ndof, const xgpu_batch* batc
   return XGPU_OK;
 #undef XG_TRY
 #undef XG_TRYRC
+}
+
+extern "C" int xgpu_plan_phase_ms(xgpu_plan* P, double* ms_host)
+{
+  if (!P || !ms_host || !P->ev[2]) return XGPU_ERR_ARG;
+  float a = 0.f, b = 0.f;
+  if (cudaEventElapsedTime(&a, P->ev[0], P->ev[1]) != cudaSuccess) return XGPU_ERR_CUDA;
+  if (cudaEventElapsedTime(&b, P->ev[1], P->ev[2]) != cudaSuccess) return XGPU_ERR_CUDA;
+  ms_host[0] = a; ms_host[1] = b;
+  return XGPU_OK;
 }
 
 extern "C" int xgpu_csr_pattern(xgpu_ctx* ctx, xgpu_plan* P, int64_t* rowptr, int32_t* colidx)

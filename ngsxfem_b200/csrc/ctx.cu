@@ -202,6 +202,19 @@ extern "C" int xgpu_set_option(xgpu_ctx* ctx, const char* key, int value)
   return xgpu_fail(ctx, XGPU_ERR_ARG, "xgpu_set_option: unknown key");
 }
 
+extern "C" int xgpu_set_deformation(xgpu_ctx* ctx, int order, const int32_t* el_dofs, const double* vals)
+{
+  if (!ctx) return XGPU_ERR_ARG;
+  if (order <= 0 || !el_dofs || !vals) {
+    if (order > 0) return xgpu_fail(ctx, XGPU_ERR_ARG, "xgpu_set_deformation: el_dofs / vals missing");
+    ctx->def_order = 0; ctx->def_el_dofs = nullptr; ctx->def_vals = nullptr;
+    return XGPU_OK;
+  }
+  if (order > XG_MAX_ORDER) return xgpu_fail(ctx, XGPU_ERR_UNSUPPORTED, "xgpu_set_deformation: orders 1..4");
+  ctx->def_order = order; ctx->def_el_dofs = el_dofs; ctx->def_vals = vals;
+  return XGPU_OK;
+}
+
 extern "C" int xgpu_sync(xgpu_ctx* ctx)
 {
   if (!ctx) return XGPU_ERR_ARG;

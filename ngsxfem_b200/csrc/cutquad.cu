@@ -65,7 +65,8 @@ __global__ void __launch_bounds__(128) k_cq_fill(int64_t n, const int32_t* __res
                                                  const double* __restrict__ rv_p, const double* __restrict__ rv_w, int np_vol,
                                                  const double* __restrict__ rs_p, const double* __restrict__ rs_w, int np_sub,
                                                  const int64_t* __restrict__ offsets, double* __restrict__ pts,
-                                                 double* __restrict__ wts, int* status, unsigned long long* status_elem)
+                                                 double* __restrict__ wts, int* status, unsigned long long* status_elem,
+                                                 int untransformed)
 {
   extern __shared__ double smem[];  // sub rule: np_sub x 4 (xi0, xi1, xi2, w), then 128 descriptors
   CqDesc* desc = reinterpret_cast<CqDesc*>(smem + 4 * ((np_sub + 1) & ~1));
@@ -93,7 +94,8 @@ __global__ void __launch_bounds__(128) k_cq_fill(int64_t n, const int32_t* __res
           if (ns < 0) xgpu_record_error(status, status_elem, ns, el);
           else {
             double iffac = 1.0;
-            if (dt == XGPU_IF) {  // w <- w * ||F^{-T} n_ref||  (:558-578); affine F from the vertices
+            // untransformed (straightcutrule.cpp:814-879): the factor is applied per point afterwards (deformed mesh)
+            if (dt == XGPU_IF && !untransformed) {  // w <- w * ||F^{-T} n_ref||  (:558-578); affine F from the vertices
               double vx[D + 1][3], F[D * D], Fi[D * D];
 #pragma unroll
               for (int k = 0; k < D + 1; k++)
@@ -273,6 +275,8 @@ extern "C" int xgpu_cutquad_fill(xgpu_ctx* ctx, int dim, int64_t n, const int32_
   const xgpu_rule_host* rv = xgpu_rule_lookup(ctx, dim, order);
   const xgpu_rule_host* rs = (dt == XGPU_IF) ? xgpu_rule_lookup(ctx, dim - 1, order) : rv;
   if (!rv || !rs) return xgpu_fail(ctx, XGPU_ERR_ARG, "xgpu_cutquad_fill: no rule");
+  const int deformed_if = (ctx->def_order > 0 && dt == XGPU_IF) ? 1 : 0;
+  if (deformed_if && dim < 2) return xgpu_fail(ctx, XGPU_ERR_UNSUPPORTED, "xgpu_cutquad_fill: deformation needs dim >= 2");
   const size_t sm = sizeof(double) * 4 * ((rs->n + 1) & ~1) + 128 * sizeof(CqDesc);
   unsigned grid = nblk(n, 128);  // 128 listed elements per block and pass
   if (grid > XGPU_NSM * 8) grid = XGPU_NSM * 8;
@@ -281,11 +285,13 @@ extern "C" int xgpu_cutquad_fill(xgpu_ctx* ctx, int dim, int64_t n, const int32_
     if (sm > 48 * 1024) XGPU_CUDA(ctx, cudaFuncSetAttribute(k_cq_fill<DD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm)); \
     k_cq_fill<DD><<<grid, 128, sm, ctx->stream>>>(n, elems, el_vtx, vtx_xyz, phi, dt, rv->d_pts, rv->d_wts, rv->n,   \
                                                   rs->d_pts, rs->d_wts, rs->n, offsets, pts, wts, ctx->d_status,     \
-                                                  ctx->d_status_elem);                                               \
+                                                  ctx->d_status_elem, deformed_if);                                  \
   }
   if (dim == 3) XG_FILL(3) else if (dim == 2) XG_FILL(2) else XG_FILL(1)
 #undef XG_FILL
   XGPU_LAUNCH_CHECK(ctx);
+  // deformed mesh: the interface factor ||F^{-T} n_ref|| depends on the point (straightcutrule.cpp:558-578)
+  if (deformed_if) return xgpu_if_weights_def(ctx, dim, n, elems, el_vtx, vtx_xyz, phi, offsets, pts, wts);
   return XGPU_OK;
 }
 
@@ -302,6 +308,11 @@ extern "C" int xgpu_integrate_monomial(xgpu_ctx* ctx, int dim, int64_t n, const 
   if (rc) return rc;
   double* elsum = (double*)p;
   const int e0 = expo_host[0], e1 = dim > 1 ? expo_host[1] : 0, e2 = dim > 2 ? expo_host[2] : 0;
+  if (ctx->def_order > 0) {
+    rc = xgpu_integrate_def(ctx, dim, n, elems, el_vtx, vtx_xyz, offsets, pts, wts, e0, e1, e2, elsum);
+    if (rc) return rc;
+    return xgpu_sum_f64(ctx, elsum, n, elsum + n, result_host);
+  }
   const unsigned grid = nblk(n * 32, 128);
   if (dim == 3) k_integrate<3><<<grid, 128, 0, ctx->stream>>>(n, elems, el_vtx, vtx_xyz, offsets, pts, wts, e0, e1, e2, elsum);
   else if (dim == 2) k_integrate<2><<<grid, 128, 0, ctx->stream>>>(n, elems, el_vtx, vtx_xyz, offsets, pts, wts, e0, e1, e2, elsum);

@@ -454,6 +454,7 @@ extern "C" int xgpu_cutquad_ml_fill(xgpu_ctx* ctx, int dim, int64_t n, const int
                                     int ntuples, int order, const int64_t* offsets, double* pts, double* wts)
 {
   if (!ctx || dim < 1 || dim > 3 || n < 0) return xgpu_fail(ctx, XGPU_ERR_ARG, "xgpu_cutquad_ml_fill: bad argument");
+  if (ctx->def_order > 0) return xgpu_fail(ctx, XGPU_ERR_UNSUPPORTED, "xgpu_cutquad_ml_fill: no deformation support (unset it)");
   if (n == 0) return XGPU_OK;
   MlTuples tp; RuleSet R;
   int rc = make_tuples(ctx, M, dts_host, ntuples, tp);
@@ -488,6 +489,7 @@ extern "C" int xgpu_cutquad_st_fill(xgpu_ctx* ctx, int dim, int64_t n, const int
                                     int order_time, int order_space, const int64_t* offsets, double* pts, double* tvals,
                                     double* wts)
 {
+  if (ctx && ctx->def_order > 0) return xgpu_fail(ctx, XGPU_ERR_UNSUPPORTED, "xgpu_cutquad_st_fill: no deformation support (unset it)");
   if (!ctx || dim < 1 || dim > 3 || n < 0 || dt < 0 || dt > 2 || time_fe_order < 0 || time_fe_order > XG_ST_MAXORD)
     return xgpu_fail(ctx, XGPU_ERR_ARG, "xgpu_cutquad_st_fill: bad argument (time order <= 8)");
   if (n == 0) return XGPU_OK;

@@ -1,0 +1,141 @@
+// deform.cu — geometry passes that depend on the isoparametric deformation (xgpu_set_deformation):
+//   k_if_weights_def<D>  interface rules on a deformed mesh: w_q <- w_q ||F(xhat_q)^{-T} n_ref||
+//                        (TransformQuadUntrafoToIRInterface, cutint/straightcutrule.cpp:558-578; the
+//                        affine part of the factor is skipped in k_cq_fill, `untransformed`)
+//   k_integrate_def<D>   sum_q w_q |det F(xhat_q)| x(xhat_q)^e  (cutint/cutintegral.cpp:126-212)
+// One warp per listed element: the element's deformation coefficients are gathered into shared
+// memory once, lanes stride over the element's points.  Compiled without FMA contraction like the
+// other geometry kernels (build.py NO_FMA).
+#include "common.cuh"
+#include "cutgeom.cuh"
+#include "deform.cuh"
+
+namespace {
+
+inline unsigned nblk(int64_t n, int t) { return (unsigned)((n + t - 1) / t); }
+
+template <int D>
+__device__ __forceinline__ void load_vertices(const int32_t* __restrict__ el_vtx, const double* __restrict__ vtx_xyz,
+                                              int64_t el, int* v, double (*vx)[3])
+{
+#pragma unroll
+  for (int k = 0; k < D + 1; k++) {
+    v[k] = __ldg(el_vtx + el * (D + 1) + k);
+#pragma unroll
+    for (int c = 0; c < 3; c++) vx[k][c] = (c < D) ? __ldg(vtx_xyz + (int64_t)v[k] * D + c) : 0.0;
+  }
+}
+
+template <int D>
+__global__ void __launch_bounds__(128) k_if_weights_def(int64_t n, const int32_t* __restrict__ elems,
+                                                        const int32_t* __restrict__ el_vtx, const double* __restrict__ vtx_xyz,
+                                                        const double* __restrict__ phi, const int64_t* __restrict__ offsets,
+                                                        const double* __restrict__ pts, double* __restrict__ wts, DefDev df)
+{
+  __shared__ double sdefs[4][XG_DEFS];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  double* defs = sdefs[wib];
+  const int64_t warp0 = (int64_t)blockIdx.x * 4 + wib, nwarps = (int64_t)gridDim.x * 4;
+  for (int64_t i = warp0; i < n; i += nwarps) {
+    const int64_t q0 = offsets[i], q1 = offsets[i + 1];
+    if (q1 == q0) continue;
+    const int64_t el = elems ? (int64_t)elems[i] : i;
+    int v[D + 1];
+    double vx[D + 1][3], l[D + 1], F[D * D];
+    load_vertices<D>(el_vtx, vtx_xyz, el, v, vx);
+#pragma unroll
+    for (int k = 0; k < D + 1; k++) l[k] = __ldg(phi + v[k]);
+    xg_affine_jac<D>(vx, F);
+    __syncwarp();
+    xg_def_gather<D>(df, el, lane, defs);
+    __syncwarp();
+    for (int64_t q = q0 + lane; q < q1; q += 32) {
+      const double xh[3] = {pts[3 * q], pts[3 * q + 1], pts[3 * q + 2]};
+      double Fq[D * D], Fiq[D * D], xd[3] = {0, 0, 0};
+#pragma unroll
+      for (int k = 0; k < D * D; k++) Fq[k] = F[k];
+      xg_def_apply<D>(df.order, v, xh, defs, Fq, xd);
+      xg_inv<D>(Fq, Fiq);
+      wts[q] *= xg_if_weight_factor<D>(Fiq, l);
+    }
+  }
+}
+
+template <int D>
+__global__ void __launch_bounds__(128) k_integrate_def(int64_t n, const int32_t* __restrict__ elems,
+                                                       const int32_t* __restrict__ el_vtx, const double* __restrict__ vtx_xyz,
+                                                       const int64_t* __restrict__ offsets, const double* __restrict__ pts,
+                                                       const double* __restrict__ wts, int e0, int e1, int e2,
+                                                       double* __restrict__ elsum, DefDev df)
+{
+  __shared__ double sdefs[4][XG_DEFS];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  double* defs = sdefs[wib];
+  const int64_t i = (int64_t)blockIdx.x * 4 + wib;
+  if (i >= n) return;
+  const int64_t el = elems ? (int64_t)elems[i] : i;
+  int v[D + 1];
+  double vx[D + 1][3], F[D * D];
+  load_vertices<D>(el_vtx, vtx_xyz, el, v, vx);
+  xg_affine_jac<D>(vx, F);
+  xg_def_gather<D>(df, el, lane, defs);
+  __syncwarp();
+  const int ex[3] = {e0, e1, e2};
+  double s = 0.0;
+  for (int64_t q = offsets[i] + lane; q < offsets[i + 1]; q += 32) {
+    const double xh[3] = {pts[3 * q], pts[3 * q + 1], pts[3 * q + 2]};
+    double lam[D + 1], sl = 1.0, x[3] = {0, 0, 0}, Fq[D * D], Fiq[D * D];
+#pragma unroll
+    for (int k = 0; k < D; k++) { lam[k] = xh[k]; sl -= lam[k]; }
+    lam[D] = sl;
+#pragma unroll
+    for (int c = 0; c < D; c++) {
+      double xc = 0.0;
+#pragma unroll
+      for (int k = 0; k < D + 1; k++) xc += lam[k] * vx[k][c];
+      x[c] = xc;
+    }
+#pragma unroll
+    for (int k = 0; k < D * D; k++) Fq[k] = F[k];
+    xg_def_apply<D>(df.order, v, xh, defs, Fq, x);
+    const double meas = fabs(xg_inv<D>(Fq, Fiq));
+    double f = 1.0;
+#pragma unroll
+    for (int c = 0; c < D; c++)
+      for (int e = 0; e < ex[c]; e++) f *= x[c];
+    s += wts[q] * meas * f;
+  }
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) s += __shfl_down_sync(0xffffffffu, s, d);
+  if (lane == 0) elsum[i] = s;
+}
+
+}  // namespace
+
+int xgpu_if_weights_def(xgpu_ctx* ctx, int dim, int64_t n, const int32_t* elems, const int32_t* el_vtx,
+                        const double* vtx_xyz, const double* phi, const int64_t* offsets, const double* pts, double* wts)
+{
+  if (n == 0) return XGPU_OK;
+  const DefDev df = xg_defdev(ctx, dim);
+  unsigned grid = nblk(n, 4);
+  if (grid > XGPU_NSM * 16) grid = XGPU_NSM * 16;
+  if (dim == 3) k_if_weights_def<3><<<grid, 128, 0, ctx->stream>>>(n, elems, el_vtx, vtx_xyz, phi, offsets, pts, wts, df);
+  else if (dim == 2) k_if_weights_def<2><<<grid, 128, 0, ctx->stream>>>(n, elems, el_vtx, vtx_xyz, phi, offsets, pts, wts, df);
+  else return xgpu_fail(ctx, XGPU_ERR_UNSUPPORTED, "deformation needs dim >= 2");
+  XGPU_LAUNCH_CHECK(ctx);
+  return XGPU_OK;
+}
+
+int xgpu_integrate_def(xgpu_ctx* ctx, int dim, int64_t n, const int32_t* elems, const int32_t* el_vtx,
+                       const double* vtx_xyz, const int64_t* offsets, const double* pts, const double* wts,
+                       int e0, int e1, int e2, double* elsum)
+{
+  if (n == 0) return XGPU_OK;
+  const DefDev df = xg_defdev(ctx, dim);
+  const unsigned grid = nblk(n, 4);
+  if (dim == 3) k_integrate_def<3><<<grid, 128, 0, ctx->stream>>>(n, elems, el_vtx, vtx_xyz, offsets, pts, wts, e0, e1, e2, elsum, df);
+  else if (dim == 2) k_integrate_def<2><<<grid, 128, 0, ctx->stream>>>(n, elems, el_vtx, vtx_xyz, offsets, pts, wts, e0, e1, e2, elsum, df);
+  else return xgpu_fail(ctx, XGPU_ERR_UNSUPPORTED, "deformation needs dim >= 2");
+  XGPU_LAUNCH_CHECK(ctx);
+  return XGPU_OK;
+}

@@ -16,6 +16,7 @@
 //        (nd^2 * 8 B out per element, 16 B + vertex gathers in).
 #include "common.cuh"
 #include "cutgeom.cuh"
+#include "deform.cuh"
 #include <vector>
 
 namespace {
@@ -36,6 +37,16 @@ __device__ __forceinline__ double ipow(double h, int p)
   const int ap = p < 0 ? -p : p;
   for (int i = 0; i < ap; i++) r *= h;
   return p < 0 ? 1.0 / r : r;
+}
+
+// folded weights of the ID*ID (mass) and GRAD.GRAD (stiffness) terms at measure `meas`, mesh size h
+__device__ __forceinline__ void ms_coefs(const TermsDev& T, double h, double meas, double& cm, double& cs)
+{
+  cm = 0.0; cs = 0.0;
+  for (int t = 0; t < T.n; t++) {
+    const double c = T.coef[t] * ipow(h, T.hpow[t]) * meas;
+    if (T.op_test[t] == 0) cm += c; else cs += c;
+  }
 }
 
 // staging sink: values, physical gradients and normal derivative of shape i at one point
@@ -61,18 +72,20 @@ struct StageSink {
   }
 };
 
-template <int D, int MAXB>
+template <int D, int MAXB, bool DEF>
 __global__ void __launch_bounds__(128) k_elmat_points(
     int64_t n, const int32_t* __restrict__ elems, const int32_t* __restrict__ el_vtx,
     const double* __restrict__ vtx_xyz, const double* __restrict__ phi,
     const int64_t* __restrict__ offsets, const double* __restrict__ pts, const double* __restrict__ wts, int np_shared,
-    int p, int nd, int CH, TermsDev T, int accumulate, const int32_t* __restrict__ slots, double* __restrict__ mats)
+    int p, int nd, int CH, TermsDev T, int accumulate, const int32_t* __restrict__ slots, double* __restrict__ mats,
+    DefDev df)
 {
   extern __shared__ double smem[];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const int ndp = (nd + 1) & ~1, nbk = ndp >> 1;
   const int PS = ndp * (2 + D) + XG_MAXTERMS;  // per point: val, D grads, dn, term weights
-  double* Bw = smem + (size_t)wib * CH * PS;
+  double* Bw = smem + (size_t)wib * (CH * PS + (DEF ? XG_DEFS : 0));
+  double* defs = Bw + (size_t)CH * PS;
   const int64_t warp0 = (int64_t)blockIdx.x * (blockDim.x >> 5) + wib;
   const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
   const int nblocks = nbk * nbk;
@@ -89,19 +102,9 @@ __global__ void __launch_bounds__(128) k_elmat_points(
     }
     xg_affine_jac<D>(vx, F);
     const double meas = fabs(xg_inv<D>(F, Fi));
-    const double h = (D == 1) ? meas : ((D == 2) ? sqrt(meas) : cbrt(meas));
-    if (phi) {  // n = F^{-T} grad_ref(lset) normalised (Normalize(grad(lsetp1)))
-      double nn = 0.0;
-#pragma unroll
-      for (int c = 0; c < D; c++) {
-        double s = 0.0;
-#pragma unroll
-        for (int j = 0; j < D; j++) s += Fi[j * D + c] * (l[j] - l[D]);
-        nrm[c] = s; nn += s * s;
-      }
-      nn = sqrt(nn);
-      if (nn > 0.0) { for (int c = 0; c < D; c++) nrm[c] /= nn; }
-    }
+    const double h = xg_mesh_size<D>(meas);
+    if (phi) xg_phys_normal<D>(Fi, l, nrm);  // n = F^{-T} grad_ref(lset) normalised (Normalize(grad(lsetp1)))
+    if (DEF) { __syncwarp(); xg_def_gather<D>(df, el, lane, defs); __syncwarp(); }
     const int64_t q0 = offsets ? offsets[e] : 0;
     const int npe = offsets ? (int)(offsets[e + 1] - q0) : np_shared;
     double acc[MAXB][4];
@@ -115,10 +118,20 @@ __global__ void __launch_bounds__(128) k_elmat_points(
         const double* xq = pts + 3 * (q0 + c0 + lane);
         double xh[3] = {xq[0], xq[1], xq[2]};
         for (int i = nd; i < ndp; i++) for (int k = 0; k < 2 + D; k++) B[k * ndp + i] = 0.0;
-        StageSink<D> sink{B, ndp, Fi, nrm};
+        double Fiq[D * D], nq[3] = {0, 0, 0}, measq = meas, hq = h;
+        if (DEF) {  // Jacobian of the deformed element at this point
+          double Fq[D * D], xd[3] = {0, 0, 0};
+#pragma unroll
+          for (int k = 0; k < D * D; k++) Fq[k] = F[k];
+          xg_def_apply<D>(df.order, v, xh, defs, Fq, xd);
+          measq = fabs(xg_inv<D>(Fq, Fiq));
+          hq = xg_mesh_size<D>(measq);
+          if (phi) xg_phys_normal<D>(Fiq, l, nq);
+        }
+        StageSink<D> sink{B, ndp, DEF ? Fiq : Fi, DEF ? nq : nrm};
         xg_h1_shapes_rt<D>(p, v, xh, sink);
-        const double fac = wts[q0 + c0 + lane] * meas;
-        for (int t = 0; t < T.n; t++) B[(2 + D) * ndp + t] = T.coef[t] * ipow(h, T.hpow[t]) * fac;
+        const double fac = wts[q0 + c0 + lane] * measq;
+        for (int t = 0; t < T.n; t++) B[(2 + D) * ndp + t] = T.coef[t] * ipow(hq, T.hpow[t]) * fac;
       }
       __syncwarp();
 #pragma unroll
@@ -195,12 +208,12 @@ struct StageSinkMS {
   }
 };
 
-template <int D, int P>
+template <int D, int P, bool DEF>
 __global__ void __launch_bounds__(128) k_elmat_ms(
     int64_t n, const int32_t* __restrict__ elems, const int32_t* __restrict__ el_vtx,
     const double* __restrict__ vtx_xyz, const int64_t* __restrict__ offsets, const double* __restrict__ pts,
     const double* __restrict__ wts, int np_shared, int CH, TermsDev T, int accumulate,
-    const int32_t* __restrict__ slots, double* __restrict__ mats)
+    const int32_t* __restrict__ slots, double* __restrict__ mats, DefDev df)
 {
   constexpr int ND = (D == 1) ? P + 1 : ((D == 2) ? 3 + 3 * (P - 1) + (P - 1) * (P - 2) / 2
                                                    : 4 + 6 * (P - 1) + 4 * ((P - 1) * (P - 2) / 2) + (P - 1) * (P - 2) * (P - 3) / 6);
@@ -208,7 +221,8 @@ __global__ void __launch_bounds__(128) k_elmat_ms(
   constexpr int PS = NDP * (1 + D) + 2;  // per point: val, D physical gradients, (mass, stiffness) weights
   extern __shared__ double smem[];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-  double* Bw = smem + (size_t)wib * CH * PS;
+  double* Bw = smem + (size_t)wib * (CH * PS + (DEF ? XG_DEFS : 0));
+  double* defs = Bw + (size_t)CH * PS;
   const int64_t warp0 = (int64_t)blockIdx.x * (blockDim.x >> 5) + wib;
   const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
   for (int64_t e = warp0; e < n; e += nwarps) {
@@ -223,12 +237,9 @@ __global__ void __launch_bounds__(128) k_elmat_ms(
     }
     xg_affine_jac<D>(vx, F);
     const double meas = fabs(xg_inv<D>(F, Fi));
-    const double h = (D == 1) ? meas : ((D == 2) ? sqrt(meas) : cbrt(meas));
-    double cm = 0.0, cs = 0.0;
-    for (int t = 0; t < T.n; t++) {
-      const double c = T.coef[t] * ipow(h, T.hpow[t]) * meas;
-      if (T.op_test[t] == 0) cm += c; else cs += c;
-    }
+    double cm, cs;
+    ms_coefs(T, xg_mesh_size<D>(meas), meas, cm, cs);
+    if (DEF) { __syncwarp(); xg_def_gather<D>(df, el, lane, defs); __syncwarp(); }
     const int64_t q0 = offsets ? offsets[e] : 0;
     const int npe = offsets ? (int)(offsets[e + 1] - q0) : np_shared;
     double acc[MAXB][4];
@@ -245,11 +256,20 @@ __global__ void __launch_bounds__(128) k_elmat_ms(
 #pragma unroll
           for (int k = 0; k < 1 + D; k++) B[k * NDP + ND] = 0.0;
         }
-        StageSinkMS<D> sink{B, NDP, Fi};
+        double Fiq[D * D], cmq = cm, csq = cs;
+        if (DEF) {
+          double Fq[D * D], xd[3] = {0, 0, 0};
+#pragma unroll
+          for (int k = 0; k < D * D; k++) Fq[k] = F[k];
+          xg_def_apply<D>(df.order, v, xh, defs, Fq, xd);
+          const double measq = fabs(xg_inv<D>(Fq, Fiq));
+          ms_coefs(T, xg_mesh_size<D>(measq), measq, cmq, csq);
+        }
+        StageSinkMS<D> sink{B, NDP, DEF ? Fiq : Fi};
         xg_h1_shapes<D, P>(v, xh, sink);
         const double w = wts[q0 + c0 + ql];
-        B[NDP * (1 + D)] = cm * w;
-        B[NDP * (1 + D) + 1] = cs * w;
+        B[NDP * (1 + D)] = cmq * w;
+        B[NDP * (1 + D) + 1] = csq * w;
       }
       __syncwarp();
 #pragma unroll
@@ -344,19 +364,20 @@ struct DmmaGeom {
   static constexpr int NPAIR = NT * (NT + 1) / 2;
 };
 
-template <int D, int P>
+template <int D, int P, bool DEF>
 __global__ void __launch_bounds__(160) k_elmat_dmma(
     int64_t n, const int32_t* __restrict__ elems, const int32_t* __restrict__ el_vtx,
     const double* __restrict__ vtx_xyz, const int64_t* __restrict__ offsets, const double* __restrict__ pts,
     const double* __restrict__ wts, int np_shared, int CH, TermsDev T, int accumulate,
-    const int32_t* __restrict__ slots, double* __restrict__ mats)
+    const int32_t* __restrict__ slots, double* __restrict__ mats, DefDev df)
 {
   using G = DmmaGeom<D, P>;
   constexpr int ND = G::ND, NT = G::NT, NDP = G::NDP, RS = G::RS, PS = G::PS, NPAIR = G::NPAIR;
   extern __shared__ double smem[];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const int fr = lane >> 2, fc = lane & 3;  // fragment row / component
-  double* Bw = smem + (size_t)wib * CH * PS;
+  double* Bw = smem + (size_t)wib * (CH * PS + (DEF ? XG_DEFS : 0));
+  double* defs = Bw + (size_t)CH * PS;
   const int64_t warp0 = (int64_t)blockIdx.x * (blockDim.x >> 5) + wib;
   const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
   for (int64_t e = warp0; e < n; e += nwarps) {
@@ -371,12 +392,9 @@ __global__ void __launch_bounds__(160) k_elmat_dmma(
     }
     xg_affine_jac<D>(vx, F);
     const double meas = fabs(xg_inv<D>(F, Fi));
-    const double h = (D == 1) ? meas : ((D == 2) ? sqrt(meas) : cbrt(meas));
-    double cm = 0.0, cs = 0.0;
-    for (int t = 0; t < T.n; t++) {
-      const double c = T.coef[t] * ipow(h, T.hpow[t]) * meas;
-      if (T.op_test[t] == 0) cm += c; else cs += c;
-    }
+    double cm, cs;
+    ms_coefs(T, xg_mesh_size<D>(meas), meas, cm, cs);
+    if (DEF) { __syncwarp(); xg_def_gather<D>(df, el, lane, defs); __syncwarp(); }
     const int64_t q0 = offsets ? offsets[e] : 0;
     const int npe = offsets ? (int)(offsets[e + 1] - q0) : np_shared;
     double acc[NPAIR][2];
@@ -398,11 +416,20 @@ __global__ void __launch_bounds__(160) k_elmat_dmma(
           for (int k = 1 + D; k < 4; k++)
             for (int i = 0; i < ND; i++) B[k * RS + i] = 0.0;
         }
-        StageSinkT<D> sink{B, RS, Fi};
+        double Fiq[D * D], cmq = cm, csq = cs;
+        if (DEF) {
+          double Fq[D * D], xd[3] = {0, 0, 0};
+#pragma unroll
+          for (int k = 0; k < D * D; k++) Fq[k] = F[k];
+          xg_def_apply<D>(df.order, v, xh, defs, Fq, xd);
+          const double measq = fabs(xg_inv<D>(Fq, Fiq));
+          ms_coefs(T, xg_mesh_size<D>(measq), measq, cmq, csq);
+        }
+        StageSinkT<D> sink{B, RS, DEF ? Fiq : Fi};
         xg_h1_shapes<D, P>(v, xh, sink);
         const double w = wts[q0 + c0 + ql];
-        B[4 * RS] = cm * w;
-        B[4 * RS + 1] = B[4 * RS + 2] = B[4 * RS + 3] = cs * w;
+        B[4 * RS] = cmq * w;
+        B[4 * RS + 1] = B[4 * RS + 2] = B[4 * RS + 3] = csq * w;
       }
       __syncwarp();
       for (int q = 0; q < cnt; q++) {
@@ -557,12 +584,21 @@ int launch_ms(xgpu_ctx* ctx, int64_t n, const int32_t* elems, const int32_t* el_
   const int PS = ndp * (1 + D) + 2;
   int CH = 32;
   while (CH > 4 && (size_t)4 * CH * PS * sizeof(double) > 56 * 1024) CH >>= 1;
-  const size_t sm = (size_t)4 * CH * PS * sizeof(double);
+  const DefDev df = xg_defdev(ctx, D);
+  const size_t sm = (size_t)4 * (CH * PS + (df.order > 0 ? XG_DEFS : 0)) * sizeof(double);
   unsigned grid = nblk(n, 4);
   if (grid > XGPU_NSM * 16) grid = XGPU_NSM * 16;
-  XGPU_CUDA(ctx, cudaFuncSetAttribute(k_elmat_ms<D, P>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-  k_elmat_ms<D, P><<<grid, 128, sm, ctx->stream>>>(n, elems, el_vtx, vtx_xyz, offsets, pts, wts, np_shared, CH, T,
-                                                   accumulate, slots, mats);
+  if (df.order > 0) {
+    if constexpr (D >= 2) {
+      XGPU_CUDA(ctx, cudaFuncSetAttribute(k_elmat_ms<D, P, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+      k_elmat_ms<D, P, true><<<grid, 128, sm, ctx->stream>>>(n, elems, el_vtx, vtx_xyz, offsets, pts, wts, np_shared, CH, T,
+                                                             accumulate, slots, mats, df);
+    } else return xgpu_fail(ctx, XGPU_ERR_UNSUPPORTED, "elmat: deformation needs dim >= 2");
+  } else {
+    XGPU_CUDA(ctx, cudaFuncSetAttribute(k_elmat_ms<D, P, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+    k_elmat_ms<D, P, false><<<grid, 128, sm, ctx->stream>>>(n, elems, el_vtx, vtx_xyz, offsets, pts, wts, np_shared, CH, T,
+                                                            accumulate, slots, mats, df);
+  }
   XGPU_LAUNCH_CHECK(ctx);
   return XGPU_OK;
 }
@@ -574,16 +610,24 @@ int launch_dmma(xgpu_ctx* ctx, int64_t n, const int32_t* elems, const int32_t* e
 {
   using G = DmmaGeom<D, P>;
   // points per chunk: 32 (one per lane) when 4-5 warps of slabs fit the 227 KB of an SM
+  const DefDev df = xg_defdev(ctx, D);
+  const size_t dfs = df.order > 0 ? XG_DEFS : 0;
   int CH = 32, nw = 4;
-  if ((size_t)5 * CH * G::PS * sizeof(double) <= 220 * 1024 && (size_t)4 * CH * G::PS * sizeof(double) > 110 * 1024) nw = 5;
-  while (CH > 8 && (size_t)nw * CH * G::PS * sizeof(double) > 220 * 1024) CH >>= 1;
+  if ((size_t)5 * (CH * G::PS + dfs) * sizeof(double) <= 220 * 1024 && (size_t)4 * CH * G::PS * sizeof(double) > 110 * 1024) nw = 5;
+  while (CH > 8 && (size_t)nw * (CH * G::PS + dfs) * sizeof(double) > 220 * 1024) CH >>= 1;
   if (CH * G::PS < G::NDP * G::NDP) return xgpu_fail(ctx, XGPU_ERR_CAPACITY, "elmat: staging buffer smaller than the element matrix");
-  const size_t sm = (size_t)nw * CH * G::PS * sizeof(double);
+  const size_t sm = (size_t)nw * (CH * G::PS + dfs) * sizeof(double);
   unsigned grid = nblk(n, nw);
   if (grid > XGPU_NSM * 8) grid = XGPU_NSM * 8;
-  XGPU_CUDA(ctx, cudaFuncSetAttribute(k_elmat_dmma<D, P>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-  k_elmat_dmma<D, P><<<grid, nw * 32, sm, ctx->stream>>>(n, elems, el_vtx, vtx_xyz, offsets, pts, wts, np_shared, CH, T,
-                                                         accumulate, slots, mats);
+  if (df.order > 0) {
+    XGPU_CUDA(ctx, cudaFuncSetAttribute(k_elmat_dmma<D, P, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+    k_elmat_dmma<D, P, true><<<grid, nw * 32, sm, ctx->stream>>>(n, elems, el_vtx, vtx_xyz, offsets, pts, wts, np_shared, CH, T,
+                                                                 accumulate, slots, mats, df);
+  } else {
+    XGPU_CUDA(ctx, cudaFuncSetAttribute(k_elmat_dmma<D, P, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+    k_elmat_dmma<D, P, false><<<grid, nw * 32, sm, ctx->stream>>>(n, elems, el_vtx, vtx_xyz, offsets, pts, wts, np_shared, CH, T,
+                                                                  accumulate, slots, mats, df);
+  }
   XGPU_LAUNCH_CHECK(ctx);
   return XGPU_OK;
 }
@@ -614,19 +658,28 @@ int launch_points(xgpu_ctx* ctx, int64_t n, const int32_t* elems, const int32_t*
   const int PS = ndp * (2 + D) + XG_MAXTERMS;
   int CH = 32;
   while (CH > 4 && (size_t)4 * CH * PS * sizeof(double) > 56 * 1024) CH >>= 1;
-  const size_t sm = (size_t)4 * CH * PS * sizeof(double);
+  const DefDev df = xg_defdev(ctx, D);
+  const size_t sm = (size_t)4 * (CH * PS + (df.order > 0 ? XG_DEFS : 0)) * sizeof(double);
   const int nblocks = (ndp / 2) * (ndp / 2);
   unsigned grid = nblk(n, 4);
   if (grid > XGPU_NSM * 8) grid = XGPU_NSM * 8;
+#define XG_LP2(MB, DF)                                                                                              \
+  {                                                                                                                 \
+    XGPU_CUDA(ctx, cudaFuncSetAttribute(k_elmat_points<D, MB, DF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm)); \
+    k_elmat_points<D, MB, DF><<<grid, 128, sm, ctx->stream>>>(n, elems, el_vtx, vtx_xyz, phi, offsets, pts, wts, np_shared, \
+                                                              p, nd, CH, T, accumulate, slots, mats, df);           \
+  }
 #define XG_LP(MB)                                                                                                   \
   {                                                                                                                 \
-    XGPU_CUDA(ctx, cudaFuncSetAttribute(k_elmat_points<D, MB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm)); \
-    k_elmat_points<D, MB><<<grid, 128, sm, ctx->stream>>>(n, elems, el_vtx, vtx_xyz, phi, offsets, pts, wts, np_shared, \
-                                                          p, nd, CH, T, accumulate, slots, mats);                   \
+    if (df.order > 0) {                                                                                             \
+      if constexpr (D >= 2) XG_LP2(MB, true)                                                                        \
+      else return xgpu_fail(ctx, XGPU_ERR_UNSUPPORTED, "elmat: deformation needs dim >= 2");                        \
+    } else XG_LP2(MB, false)                                                                                        \
   }
   if (nblocks <= 32) XG_LP(1) else if (nblocks <= 128) XG_LP(4) else if (nblocks <= 352) XG_LP(11)
   else return xgpu_fail(ctx, XGPU_ERR_UNSUPPORTED, "elmat: element too large");
 #undef XG_LP
+#undef XG_LP2
   XGPU_LAUNCH_CHECK(ctx);
   return XGPU_OK;
 }
@@ -702,8 +755,8 @@ extern "C" int xgpu_elmat_std(xgpu_ctx* ctx, int dim, int fe_order, int64_t n, c
     if (nterms == 0) dtr = dte = 0;
     order = 2 * fe_order - (dtr + dte);
   }
-  // fast path: orientation independent bases (P1, P2) and mass / stiffness terms only
-  if (ms && fe_order <= 2) {
+  // fast path: affine elements (no deformation), orientation independent bases (P1, P2), mass / stiffness terms only
+  if (ms && fe_order <= 2 && ctx->def_order == 0) {
     const double* Tref;
     rc = get_reftensor(ctx, dim, fe_order, order, &Tref);
     if (rc) return rc;

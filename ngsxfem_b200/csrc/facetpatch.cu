@@ -9,6 +9,7 @@
 // lanes own 2x2 blocks of the (2nd)^2 matrix and accumulate c_q J J^T over the staged points.
 #include "common.cuh"
 #include "cutgeom.cuh"
+#include "deform.cuh"
 
 namespace {
 
@@ -61,20 +62,97 @@ __device__ __forceinline__ void map_inv(const double (*vx)[3], const double* Fi,
   for (int i = D; i < 3; i++) xh[i] = 0.0;
 }
 
+// x(xhat) and F(xhat) of a (deformed) element: affine part from the vertices + deformation
+template <int D>
+__device__ __forceinline__ void trafo_eval(const double (*vx)[3], const double* Faff, const int* v, int def_order,
+                                           const double* defs, const double* xh, double* F, double* x)
+{
+  map_fwd<D>(vx, xh, x);
+#pragma unroll
+  for (int k = 0; k < D * D; k++) F[k] = Faff[k];
+  xg_def_apply<D>(def_order, v, xh, defs, F, x);
+}
+
+// MapPatchIntegrationPoint<D> (symboliccutbfi.cpp:1747-1846, non space-time) on deformed elements:
+// (xf, wf) on the `from` element -> xt, wt on the `to` element; affine start value, Newton with the
+// reference's constants (ngsxstd.cpp:66-82: eps 1e-12, 15 iterations, max distance 10), low-order
+// guess kept on failure.
+template <int D>
+__device__ __forceinline__ void map_patch_def(const double (*vxf)[3], const double* Ff, const int* vf, const double* defs_f,
+                                              const double (*vxt)[3], const double* Ft, const int* vt, const double* defs_t,
+                                              int def_order, const double* xf, double wf, double* xt, double* wt)
+{
+  double F[D * D], Fi[D * D], vec[3] = {0, 0, 0};
+  trafo_eval<D>(vxf, Ff, vf, def_order, defs_f, xf, F, vec);
+  const double detf = xg_inv<D>(F, Fi);
+  const double h = sqrt(detf);
+  const double mipw = wf * fabs(detf);
+  double a0[3] = {0, 0, 0}, A[D * D], Ainv[D * D], x00[3] = {0, 0, 0}, x0[3] = {0, 0, 0};
+  const double zero[3] = {0, 0, 0};
+  trafo_eval<D>(vxt, Ft, vt, def_order, defs_t, zero, F, a0);
+#pragma unroll
+  for (int d = 0; d < D; d++) {
+    double e[3] = {0, 0, 0}, ai[3] = {0, 0, 0};
+    e[d] = 1.0;
+    trafo_eval<D>(vxt, Ft, vt, def_order, defs_t, e, F, ai);
+#pragma unroll
+    for (int i = 0; i < D; i++) A[i * D + d] = ai[i] - a0[i];
+  }
+  const double w00 = fabs(xg_inv<D>(A, Ainv));
+#pragma unroll
+  for (int i = 0; i < D; i++) {
+    double t = 0.0;
+#pragma unroll
+    for (int j = 0; j < D; j++) t += Ainv[i * D + j] * (vec[j] - a0[j]);
+    x00[i] = t; x0[i] = t;
+  }
+  int its = 0;
+  double w = 0.0, diffn = 0.0;
+  while (its == 0 || (diffn > 1e-12 * h && its < 15)) {
+    double xm[3] = {0, 0, 0}, diff[3];
+    trafo_eval<D>(vxt, Ft, vt, def_order, defs_t, x0, F, xm);
+    const double det = xg_inv<D>(F, Fi);
+    diffn = 0.0;
+#pragma unroll
+    for (int i = 0; i < D; i++) { diff[i] = vec[i] - xm[i]; diffn += diff[i] * diff[i]; }
+    diffn = sqrt(diffn);
+#pragma unroll
+    for (int i = 0; i < D; i++) {
+      double u = 0.0;
+#pragma unroll
+      for (int j = 0; j < D; j++) u += Fi[i * D + j] * diff[j];
+      x0[i] += u;
+    }
+    its++;
+    w = fabs(det);
+  }
+  double dist = 0.0;
+#pragma unroll
+  for (int i = 0; i < D; i++) dist += (x0[i] - x00[i]) * (x0[i] - x00[i]);
+  dist = sqrt(dist);
+  if (its >= 15 || diffn > 1e-12 * h || dist > 10.0) {
+    xt[0] = x00[0]; xt[1] = x00[1]; xt[2] = x00[2]; *wt = mipw / w00;
+  } else {
+    xt[0] = x0[0]; xt[1] = x0[1]; xt[2] = x0[2]; *wt = mipw / w;
+  }
+}
+
 constexpr int FP_MAXB = 13;
 
-template <int D>
+template <int D, bool DEF>
 __global__ void __launch_bounds__(128) k_facetpatch(
     int64_t n, const int32_t* __restrict__ facets, const int32_t* __restrict__ facet_els,
     const int32_t* __restrict__ el_vtx, const double* __restrict__ vtx_xyz,
     const double* __restrict__ rp, const double* __restrict__ rw, int np,
-    int p, int nd, int CH, double coef, int hpow, double* __restrict__ mats)
+    int p, int nd, int CH, double coef, int hpow, double* __restrict__ mats, DefDev df)
 {
   extern __shared__ double smem[];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const int N = 2 * nd, Np = (N + 1) & ~1, nbk = Np >> 1, nblocks = nbk * nbk;
   const int PS = Np + 1;
-  double* Bw = smem + (size_t)wib * CH * PS;
+  double* Bw = smem + (size_t)wib * (CH * PS + (DEF ? 2 * XG_DEFS : 0));
+  double* defs1 = Bw + (size_t)CH * PS;
+  double* defs2 = defs1 + XG_DEFS;
   const int64_t warp0 = (int64_t)blockIdx.x * (blockDim.x >> 5) + wib;
   const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
   const int npatch = 2 * np;
@@ -90,6 +168,12 @@ __global__ void __launch_bounds__(128) k_facetpatch(
     double vx1[D + 1][3], vx2[D + 1][3], F1[D * D], Fi1[D * D], F2[D * D], Fi2[D * D], meas1, meas2;
     load_geom<D>(el_vtx, vtx_xyz, e1, v1, vx1, F1, Fi1, &meas1);
     load_geom<D>(el_vtx, vtx_xyz, e2, v2, vx2, F2, Fi2, &meas2);
+    if (DEF) {
+      __syncwarp();
+      xg_def_gather<D>(df, e1, lane, defs1);
+      xg_def_gather<D>(df, e2, lane, defs2);
+      __syncwarp();
+    }
     const double h = (D == 1) ? meas1 : ((D == 2) ? sqrt(meas1) : cbrt(meas1));
     double hp = 1.0;
     { const int ap = hpow < 0 ? -hpow : hpow; for (int i = 0; i < ap; i++) hp *= h; if (hpow < 0) hp = 1.0 / hp; }
@@ -104,7 +188,27 @@ __global__ void __launch_bounds__(128) k_facetpatch(
           const int l = c0 + lane;
           double* B = Bw + (size_t)lane * PS;
           double x1[3], x2[3], x[3], w;
-          if (l < np) {
+          double cwq = coef * hp;
+          if (DEF) {
+            double w1, wd;
+            if (l < np) {
+              x1[0] = rp[3 * l]; x1[1] = rp[3 * l + 1]; x1[2] = rp[3 * l + 2];
+              w1 = rw[l];
+              map_patch_def<D>(vx1, F1, v1, defs1, vx2, F2, v2, defs2, df.order, x1, w1, x2, &wd);
+            } else {
+              const int q = l - np;
+              x2[0] = rp[3 * q]; x2[1] = rp[3 * q + 1]; x2[2] = rp[3 * q + 2];
+              map_patch_def<D>(vx2, F2, v2, defs2, vx1, F1, v1, defs1, df.order, x2, rw[q], x1, &w1);
+            }
+            double Fq[D * D], Fiq[D * D];
+            trafo_eval<D>(vx1, F1, v1, df.order, defs1, x1, Fq, x);
+            const double measq = fabs(xg_inv<D>(Fq, Fiq));
+            const double hq = xg_mesh_size<D>(measq);
+            double hpq = 1.0;
+            { const int ap = hpow < 0 ? -hpow : hpow; for (int i = 0; i < ap; i++) hpq *= hq; if (hpow < 0) hpq = 1.0 / hpq; }
+            w = w1 * measq;
+            cwq = coef * hpq;
+          } else if (l < np) {
             x1[0] = rp[3 * l]; x1[1] = rp[3 * l + 1]; x1[2] = rp[3 * l + 2];
             map_fwd<D>(vx1, x1, x);
             map_inv<D>(vx2, Fi2, x, x2);
@@ -120,7 +224,7 @@ __global__ void __launch_bounds__(128) k_facetpatch(
           ValSink s1{B, 1.0}, s2{B + nd, -1.0};
           xg_h1_shapes_rt<D>(p, v1, x1, s1);
           xg_h1_shapes_rt<D>(p, v2, x2, s2);
-          B[Np] = coef * hp * w;
+          B[Np] = cwq * w;
         }
         __syncwarp();
 #pragma unroll
@@ -171,16 +275,19 @@ extern "C" int xgpu_facetpatch(xgpu_ctx* ctx, int dim, int fe_order, int64_t n, 
   const int Np = (2 * nd + 1) & ~1, PS = Np + 1;
   int CH = 32;
   while (CH > 4 && (size_t)4 * CH * PS * sizeof(double) > 56 * 1024) CH >>= 1;
-  const size_t sm = (size_t)4 * CH * PS * sizeof(double);
+  const DefDev df = xg_defdev(ctx, dim);
+  if (df.order > 0 && dim < 2) return xgpu_fail(ctx, XGPU_ERR_UNSUPPORTED, "xgpu_facetpatch: deformation needs dim >= 2");
+  const size_t sm = (size_t)4 * (CH * PS + (df.order > 0 ? 2 * XG_DEFS : 0)) * sizeof(double);
   unsigned grid = nblk(n, 4);
   if (grid > XGPU_NSM * 8) grid = XGPU_NSM * 8;
-#define XG_FP(DD)                                                                                                   \
+#define XG_FP(DD, DF)                                                                                               \
   {                                                                                                                 \
-    XGPU_CUDA(ctx, cudaFuncSetAttribute(k_facetpatch<DD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));   \
-    k_facetpatch<DD><<<grid, 128, sm, ctx->stream>>>(n, facets, facet_els, el_vtx, vtx_xyz, r->d_pts, r->d_wts, r->n, \
-                                                     fe_order, nd, CH, coef, hpow, mats);                           \
+    XGPU_CUDA(ctx, cudaFuncSetAttribute(k_facetpatch<DD, DF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm)); \
+    k_facetpatch<DD, DF><<<grid, 128, sm, ctx->stream>>>(n, facets, facet_els, el_vtx, vtx_xyz, r->d_pts, r->d_wts, r->n, \
+                                                         fe_order, nd, CH, coef, hpow, mats, df);                   \
   }
-  if (dim == 3) XG_FP(3) else if (dim == 2) XG_FP(2) else XG_FP(1)
+  if (df.order > 0) { if (dim == 3) XG_FP(3, true) else XG_FP(2, true) }
+  else if (dim == 3) XG_FP(3, false) else if (dim == 2) XG_FP(2, false) else XG_FP(1, false)
 #undef XG_FP
   XGPU_LAUNCH_CHECK(ctx);
   return XGPU_OK;

@@ -64,6 +64,38 @@ class H1:
         return self.TnT()[1]
 
 
+class Deformation:
+    """isoparametric mesh deformation: a GridFunction of H1(order)^dim (python/lsetcurv.py:281-356 produces it
+    in the reference; here it is an INPUT).  vals: ndof x dim coefficients in the hierarchical basis of `space`."""
+
+    def __init__(self, space, vals=None):
+        self.space, self.order = space, space.order
+        self.el_dofs = space.el_dofs
+        dim = space.mesh.dim
+        if vals is None:
+            vals = torch.zeros((space.ndof, dim), dtype=torch.float64, device=space.mesh.device)
+        self.vals = torch.as_tensor(vals, dtype=torch.float64).to(space.mesh.device).contiguous()
+        assert self.vals.shape == (space.ndof, dim)
+
+    @staticmethod
+    def interpolate_p2(space, fn):
+        """nodal interpolation of a displacement field into an order-2 space: vertex dofs d(v); the order-2
+        edge function is L_2(lam_b-lam_a, lam_a+lam_b) = -2 lam_a lam_b (h1.cuh), so its coefficient is
+        d(a) + d(b) - 2 d(midpoint).  Exact for quadratic fields."""
+        assert space.order == 2
+        mesh = space.mesh
+        p = mesh.points
+        dv = fn(p)
+        edges, _ = mesh.edges()
+        a, b = p[edges[:, 0].long()], p[edges[:, 1].long()]
+        de = fn(a) + fn(b) - 2.0 * fn(0.5 * (a + b))
+        return Deformation(space, torch.cat([dv, de], dim=0))
+
+    def local(self):
+        """per-element coefficients ne x nd x dim (the oracle's layout)"""
+        return self.vals[self.el_dofs.long()]
+
+
 class RestrictedH1:
     """Restrict(fes, active_elements): CompressedFESpace over the dofs of the active elements."""
 

@@ -201,8 +201,6 @@ def dCut(levelset, domain_type, order=None, subdivlvl=None, time_order=-1, level
         raise XgpuError("subdivlvl > 0 selects ngsxfem's legacy subdivision path: not provided")
     if element_boundary or skeleton or element_vb != 0 or vb != 0:
         raise XgpuError("element-boundary / skeleton / BND cut integrals are not on the accelerated path yet")
-    if deformation is not None:
-        raise XgpuError("isoparametric deformation is not on the accelerated path yet")
     if time_order >= 0 or tref is not None:
         raise XgpuError("space-time forms are not assembled on the accelerated path yet (rules: ops.cutquad_st)")
     if kwargs:
@@ -211,18 +209,18 @@ def dCut(levelset, domain_type, order=None, subdivlvl=None, time_order=-1, level
 
 
 class FacetPatchDifferentialSymbol:
-    def __init__(self, definedonelements, order):
-        self.definedonelements, self.order = definedonelements, order
+    def __init__(self, definedonelements, order, deformation=None):
+        self.definedonelements, self.order, self.deformation = definedonelements, order, deformation
 
 
 def dFacetPatch(definedonelements=None, deformation=None, time_order=-1, tref=None, downscale=None,
                 bonus_intorder=0, **kwargs):
     """python/__init__.py:749-778; bonus_intorder is accepted and ignored as in the reference"""
-    if deformation is not None or time_order >= 0 or tref is not None or downscale not in (None, 1, 1.0):
-        raise XgpuError("dFacetPatch: deformation / space-time / downscale are not on the accelerated path yet")
+    if time_order >= 0 or tref is not None or downscale not in (None, 1, 1.0):
+        raise XgpuError("dFacetPatch: space-time / downscale are not on the accelerated path yet")
     if definedonelements is None:
         raise XgpuError("dFacetPatch needs definedonelements (a BitArray over the facets)")
-    return FacetPatchDifferentialSymbol(definedonelements, -1)
+    return FacetPatchDifferentialSymbol(definedonelements, -1, deformation)
 
 
 class Integral:
@@ -308,29 +306,67 @@ class BilinearForm:
             return sp.rows(elem_list)
         return ops.gather_rows(sp.el_dofs, elem_list, None)
 
-    def Assemble(self):
+    def _intorder(self, integ):
+        """symboliccutbfi.cpp:100-118: ord_trial + ord_test - (min diff orders), overridden by the domain's order"""
+        order = integ.dx.order
+        if order < 0:
+            terms = integ.form.terms
+            dtr = min(0 if t[0] == OP_ID else 1 for t in terms)
+            dte = min(0 if t[1] == OP_ID else 1 for t in terms)
+            order = 2 * self.space.order - (dtr + dte)
+        return order
+
+    def _assemble_general(self, vol, active, tables, mats, ctx):
+        """several level sets / multi-level-set domains (cutint/mlsetintegration.cpp:6-186): ONE batch over
+        the active elements; every integrator builds its per-element rules on (definedonelements & active)
+        — uncut relevant elements get the standard rule, irrelevant ones no points — and accumulates."""
         sp = self.space
         mesh = sp.mesh
-        dim, p = mesh.dim, sp.order
-        ctx = default_ctx(mesh.device.index)
-        dev = mesh.device
-        ne = mesh.ne
-        nd = sp.nd
-        active = self._active_elements()
+        dim, p, ne, nd, dev = mesh.dim, sp.order, mesh.ne, sp.nd, mesh.device
+        l_A = active.indices()
+        if not l_A.numel():
+            return
+        slot_A = ops.bitset_rank(active.bits, ne, ctx=ctx)[0]
+        m_A = torch.zeros((l_A.numel(), nd, nd), dtype=torch.float64, device=dev)
+        for integ in vol:
+            dx = integ.dx
+            terms = list(integ.form.terms)
+            if any(t[0] == OP_JUMP for t in terms):
+                raise XgpuError("jump terms belong on dFacetPatch")
+            order = self._intorder(integ)
+            don = dx.definedonelements
+            if don is None:
+                l, slots = l_A, None
+            else:
+                sel = ops.bitset_op(ops.BIT_AND, active.bits, don.bits, ne, ctx=ctx)
+                l = ops.bitset_to_list(sel, ne, ctx=ctx)
+                slots = slot_A[l.long()].contiguous()
+            if not l.numel():
+                continue
+            ls = dx.levelset
+            with ctx.deformation(dx.deformation):
+                if isinstance(ls, (list, tuple)):
+                    if any(t[0] == OP_DN or t[1] == OP_DN for t in terms):
+                        raise XgpuError("normal-derivative terms need a single level set")
+                    phis = torch.stack([_lset_vec(g, mesh) for g in ls]).contiguous()
+                    dts = _normalize_dtlist(dx.domain_type, len(ls))
+                    off, q, w = ops.cutquad_ml(dim, l, mesh.elements, mesh.points, phis, dts, order, ctx=ctx)
+                    phi = phis[0].contiguous()
+                else:
+                    phi = _lset_vec(ls, mesh)
+                    off, q, w = ops.cutquad(dim, l, mesh.elements, mesh.points, phi, int(dx.domain_type), order, ctx=ctx)
+                ctx.raise_on_geometry_error()
+                if w.numel():
+                    ops.elmat_rule(dim, p, l, mesh.elements, mesh.points, phi, off, q, w, terms, out=m_A, accumulate=True,
+                                   slots=slots, ctx=ctx)
+        tables.append(self._rows(l_A)); mats.append(m_A)
 
-        # ---- volume (cut) integrators: group per level set; per element ONE matrix summing all integrators
-        vol = [i for i in self.integrals if isinstance(i.dx, CutDifferentialSymbol)]
-        fac = [i for i in self.integrals if isinstance(i.dx, FacetPatchDifferentialSymbol)]
-        tables, mats = [], []
-        # two batches: U = uncut active elements, C = cut active elements (w.r.t. the level set of the
-        # integrators); every integrator accumulates into its elements' slot, so each element has ONE
-        # matrix as in NGSolve's element loop (CalcElementMatrixAdd over all integrators, then one
-        # AddElementMatrix).  A batch whose first integrator covers it completely is written without
-        # a prior memset (write-only traffic).
+    def _assemble_single_lset(self, vol, active, tables, mats, ctx):
+        sp = self.space
+        mesh = sp.mesh
+        dim, p, ne, nd, dev = mesh.dim, sp.order, mesh.ne, sp.nd, mesh.device
         phi0 = None
         for integ in vol:
-            if isinstance(integ.dx.levelset, (list, tuple)):
-                raise XgpuError("multi-level-set forms: use ops.cutquad_ml + ops.elmat_rule (assembly wrapper pending)")
             phi = _lset_vec(integ.dx.levelset, mesh)
             if phi0 is None:
                 phi0 = phi
@@ -371,8 +407,9 @@ class BilinearForm:
                     full = l.numel() == l_U.numel()
                     if not init_U and not full:
                         m_U.zero_()
-                    ops.elmat_std(dim, p, l, mesh.elements, mesh.points, phi0, order, terms, out=m_U,
-                                  accumulate=init_U or not full, slots=None if full else slot_U[l.long()].contiguous(), ctx=ctx)
+                    with ctx.deformation(dx.deformation):
+                        ops.elmat_std(dim, p, l, mesh.elements, mesh.points, phi0, order, terms, out=m_U,
+                                      accumulate=init_U or not full, slots=None if full else slot_U[l.long()].contiguous(), ctx=ctx)
                     init_U = True
             if l_C.numel():
                 sel = Cc.bits if don is None else ops.bitset_op(ops.BIT_AND, Cc.bits, don.bits, ne, ctx=ctx)
@@ -381,10 +418,11 @@ class BilinearForm:
                     full = l.numel() == l_C.numel()
                     if not init_C and not full:
                         m_C.zero_()
-                    off, q, w = ops.cutquad(dim, l, mesh.elements, mesh.points, phi0, dt, order, ctx=ctx)
-                    ctx.raise_on_geometry_error()
-                    ops.elmat_rule(dim, p, l, mesh.elements, mesh.points, phi0, off, q, w, terms, out=m_C,
-                                   accumulate=init_C or not full, slots=None if full else slot_C[l.long()].contiguous(), ctx=ctx)
+                    with ctx.deformation(dx.deformation):
+                        off, q, w = ops.cutquad(dim, l, mesh.elements, mesh.points, phi0, dt, order, ctx=ctx)
+                        ctx.raise_on_geometry_error()
+                        ops.elmat_rule(dim, p, l, mesh.elements, mesh.points, phi0, off, q, w, terms, out=m_C,
+                                       accumulate=init_C or not full, slots=None if full else slot_C[l.long()].contiguous(), ctx=ctx)
                     init_C = True
         if not init_U:
             m_U.zero_()
@@ -394,6 +432,38 @@ class BilinearForm:
             tables.append(self._rows(l_U)); mats.append(m_U)
         if l_C.numel():
             tables.append(self._rows(l_C)); mats.append(m_C)
+
+
+    def Assemble(self):
+        sp = self.space
+        mesh = sp.mesh
+        dim, p = mesh.dim, sp.order
+        ctx = default_ctx(mesh.device.index)
+        dev = mesh.device
+        ne = mesh.ne
+        nd = sp.nd
+        active = self._active_elements()
+
+        # ---- volume (cut) integrators: group per level set; per element ONE matrix summing all integrators
+        vol = [i for i in self.integrals if isinstance(i.dx, CutDifferentialSymbol)]
+        fac = [i for i in self.integrals if isinstance(i.dx, FacetPatchDifferentialSymbol)]
+        tables, mats = [], []
+        # two batches: U = uncut active elements, C = cut active elements (w.r.t. the level set of the
+        # integrators); every integrator accumulates into its elements' slot, so each element has ONE
+        # matrix as in NGSolve's element loop (CalcElementMatrixAdd over all integrators, then one
+        # AddElementMatrix).  A batch whose first integrator covers it completely is written without
+        # a prior memset (write-only traffic).
+        lsets = []
+        for integ in vol:
+            ls = integ.dx.levelset
+            key = tuple(id(l) for l in ls) if isinstance(ls, (list, tuple)) else id(ls)
+            if key not in lsets:
+                lsets.append(key)
+        general = len(lsets) > 1 or any(isinstance(i.dx.levelset, (list, tuple)) for i in vol)
+        if general:
+            self._assemble_general(vol, active, tables, mats, ctx)
+        else:
+            self._assemble_single_lset(vol, active, tables, mats, ctx)
 
         # ---- facet patch integrators
         _, _, fe = mesh.facets() if (fac or sp.dgjumps or self.facet_restriction is not None) else (None, None, None)
@@ -411,7 +481,8 @@ class BilinearForm:
             l_f = integ.dx.definedonelements.indices()
             key = id(integ.dx.definedonelements)
             for (_, _, c, hp) in terms:
-                mm = ops.facetpatch(dim, p, l_f, fe, mesh.elements, mesh.points, integ.dx.order, c, hp, ctx=ctx)
+                with ctx.deformation(integ.dx.deformation):
+                    mm = ops.facetpatch(dim, p, l_f, fe, mesh.elements, mesh.points, integ.dx.order, c, hp, ctx=ctx)
                 if key in facet_mats:
                     facet_mats[key] = (l_f, facet_mats[key][1] + mm)
                 else:
@@ -482,8 +553,8 @@ z = CoordMonomial((0, 0, 1))
 
 def Integrate(levelset_domain=None, mesh=None, cf=1.0, order=5, time_order=-1, deformation=None, heapsize=1000000):
     """python/__init__.py:361-439 -> cutint/python_cutint.cpp:21-163: sum_q w_q |det F| cf(x_q)."""
-    if deformation is not None or time_order >= 0:
-        raise XgpuError("Integrate: deformation / space-time are not on the accelerated path yet")
+    if time_order >= 0:
+        raise XgpuError("Integrate: space-time is not on the accelerated path yet")
     if isinstance(cf, numbers.Number):
         cf = CoordMonomial((0, 0, 0), cf)
     if not isinstance(cf, CoordMonomial):
@@ -496,11 +567,12 @@ def Integrate(levelset_domain=None, mesh=None, cf=1.0, order=5, time_order=-1, d
     dim = mesh.dim
     ctx = default_ctx(mesh.device.index)
     ls, dt = ld["levelset"], ld["domain_type"]
-    if isinstance(ls, (list, tuple)):
-        phis = torch.stack([_lset_vec(l, mesh) for l in ls]).contiguous()
-        dts = _normalize_dtlist(dt, len(ls))
-        off, p, w = ops.cutquad_ml(dim, None, mesh.elements, mesh.points, phis, dts, order, ctx=ctx)
-    else:
-        off, p, w = ops.cutquad(dim, None, mesh.elements, mesh.points, _lset_vec(ls, mesh), int(dt), order, ctx=ctx)
-    ctx.raise_on_geometry_error()
-    return cf.coef * ops.integrate_monomial(dim, None, mesh.elements, mesh.points, off, p, w, cf.expo[:dim], ctx=ctx)
+    with ctx.deformation(deformation):
+        if isinstance(ls, (list, tuple)):
+            phis = torch.stack([_lset_vec(l, mesh) for l in ls]).contiguous()
+            dts = _normalize_dtlist(dt, len(ls))
+            off, p, w = ops.cutquad_ml(dim, None, mesh.elements, mesh.points, phis, dts, order, ctx=ctx)
+        else:
+            off, p, w = ops.cutquad(dim, None, mesh.elements, mesh.points, _lset_vec(ls, mesh), int(dt), order, ctx=ctx)
+        ctx.raise_on_geometry_error()
+        return cf.coef * ops.integrate_monomial(dim, None, mesh.elements, mesh.points, off, p, w, cf.expo[:dim], ctx=ctx)

@@ -296,6 +296,12 @@ class CsrPlan:
     def __init__(self, ctx, handle, nnz, ndof, nb):
         self.ctx, self.h, self.nnz, self.ndof, self.nb = ctx, handle, nnz, ndof, nb
 
+    def phase_ms(self):
+        """(transposed-table ms, pattern-pass ms) of xgpu_csr_plan, CUDA events on its stream"""
+        ms = (C.c_double * 2)()
+        self.ctx.check(self.ctx.lib.xgpu_plan_phase_ms(self.h, ms))
+        return ms[0], ms[1]
+
     def __del__(self):
         try:
             if self.h:

@@ -26,6 +26,12 @@ class PhaseTimer:
     def __init__(self, enabled=True):
         self.enabled = enabled
         self.marks = []
+        self.split = {}
+
+    def split_phase(self, name, parts):
+        """replace phase `name` by named parts (ms measured inside the library); the remainder stays under `name`"""
+        if self.enabled:
+            self.split[name] = parts
 
     def mark(self, name):
         if self.enabled:
@@ -38,6 +44,11 @@ class PhaseTimer:
         out = {}
         for (n0, e0), (n1, e1) in zip(self.marks[:-1], self.marks[1:]):
             out[n1] = out.get(n1, 0.0) + e0.elapsed_time(e1)
+        for name, parts in self.split.items():
+            if name in out:
+                for k, v in parts.items():
+                    out[k] = out.get(k, 0.0) + v
+                    out[name] -= v
         return out
 
 
@@ -122,6 +133,9 @@ class CutAssembly:
         tables = [t_neg, t_if]
         plan = ops.csr_plan(ndof, tables, ctx=ctx)
         t.mark("csr_plan")
+        if t.enabled:
+            a_ms, p_ms = plan.phase_ms()
+            t.split_phase("csr_plan", {"csr_adjacency": a_ms, "csr_pattern_pass": p_ms})
         rowptr, col = ops.csr_pattern(plan, self.dev)
         t.mark("csr_pattern")
         if "pattern" in hooks:

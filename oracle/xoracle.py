@@ -225,6 +225,17 @@ def cut_elmat(T, fe_order, lsetvals, dt, order, terms):
     return m, n
 
 
+def elmat_from_rule(T, fe_order, lsetvals, pts, wts, terms, out=None):
+    """xo_elmat_from_rule: ADDS sum_q coef h^k (w_q |det F|) op_test op_trial into out (nd x nd)"""
+    nd = h1_ndof(T.dim, fe_order)
+    m = np.zeros((nd, nd)) if out is None else out
+    v = None if lsetvals is None else _f64(lsetvals)
+    pts = _f64(pts); wts = _f64(wts)
+    ta = terms_array(terms)
+    lib().xo_elmat_from_rule(C.byref(T), fe_order, _p(v), _p(pts), _p(wts), len(wts), ta, len(terms), _p(m))
+    return m
+
+
 def facet_patch_elmat(T1, T2, fe_order, order, coef, hpow):
     nd = h1_ndof(T1.dim, fe_order)
     m = np.zeros((2 * nd, 2 * nd))
