@@ -92,7 +92,7 @@ class Deformation:
         return Deformation(space, torch.cat([dv, de], dim=0))
 
     def local(self):
-        """per-element coefficients ne x nd x dim (the oracle's layout)"""
+        """per-element coefficients ne x nd x dim (gathered through el_dofs)"""
         return self.vals[self.el_dofs.long()]
 
 
