@@ -170,6 +170,20 @@ int xgpu_elmat_std(xgpu_ctx* ctx, int dim, int fe_order, int64_t n, const int32_
                    const xgpu_term* terms_host, int nterms, int accumulate, const int32_t* slots,
                    double* mats);
 
+/* element vectors: SymbolicCutLinearFormIntegrator::T_CalcElementVector (xfem/symboliccutlfi.cpp:51-140) for
+ * sums of  f(x) * op_test(v),  f = coef * h^hpow * x^expo[0] y^expo[1] z^expo[2],  op_test 0 = ID, 2 = DN.
+ * vecs: n x nd; rule order of _std: `order`, or 2*fe_order if < 0 (:86-88).  Same accumulate / slots meaning. */
+typedef struct { int op_test; double coef; int hpow; int expo[3]; } xgpu_lterm;
+int xgpu_elvec_rule(xgpu_ctx* ctx, int dim, int fe_order, int64_t n, const int32_t* elems,
+                    const int32_t* el_vtx, const double* vtx_xyz, const double* phi,
+                    const int64_t* offsets, const double* pts, const double* wts,
+                    const xgpu_lterm* terms_host, int nterms, int accumulate, const int32_t* slots,
+                    double* vecs);
+int xgpu_elvec_std(xgpu_ctx* ctx, int dim, int fe_order, int64_t n, const int32_t* elems,
+                   const int32_t* el_vtx, const double* vtx_xyz, const double* phi, int order,
+                   const xgpu_lterm* terms_host, int nterms, int accumulate, const int32_t* slots,
+                   double* vecs);
+
 /* ---------------------------------------------------------------- (d) ghost penalty
  * SymbolicFacetPatchBilinearFormIntegrator::T_CalcFacetMatrix (xfem/symboliccutbfi.cpp:
  * 1982-2377) for coef*h^hpow*(u-u.Other())*(v-v.Other()); order<0 -> 2*fe_order (:2004-2012).
@@ -190,6 +204,12 @@ int xgpu_csr_plan(xgpu_ctx* ctx, int64_t ndof, const xgpu_batch* batches_host, i
 int xgpu_csr_pattern(xgpu_ctx* ctx, xgpu_plan* plan, int64_t* rowptr, int32_t* colidx);
 int xgpu_csr_scatter(xgpu_ctx* ctx, xgpu_plan* plan, const xgpu_batch* batches_host, int nbatches,
                      const int64_t* rowptr, const int32_t* colidx, double* vals);
+/* the transposed table alone (no sparsity pattern): enough for xgpu_vec_scatter */
+int xgpu_adjacency_plan(xgpu_ctx* ctx, int64_t ndof, const xgpu_batch* batches_host, int nbatches,
+                        xgpu_plan** plan_out);
+/* LinearForm assembly (NGSolve AddElementVector): out[d] = sum of the element-vector entries whose dof is d, in
+ * (batch, row, local index) order — deterministic.  A batch's `mats` points to nrows x width doubles here. */
+int xgpu_vec_scatter(xgpu_ctx* ctx, xgpu_plan* plan, const xgpu_batch* batches_host, int nbatches, double* out);
 void xgpu_plan_destroy(xgpu_plan* plan);
 /* device time of the two halves of xgpu_csr_plan (CUDA events on the plan's stream): ms_host[0] =
  * transposed table (histogram, scan, fill, segment sort), ms_host[1] = pattern pass (bench.py) */

@@ -17,7 +17,7 @@ from .cutinfo import (NEG, POS, IF, VOL, BND, HAS, BitArray, GridFunction, Inter
                       GetDofsOfElements, CombinedDomainType)
 from .cutinfo import C_NO as NO, C_NEG as CDOM_NEG, C_POS as CDOM_POS, C_UNCUT as UNCUT, C_IF as CDOM_IF, \
     C_HASNEG as HASNEG, C_HASPOS as HASPOS, C_ANY as ANY
-from .forms import (dCut, dFacetPatch, grad, Normalize, specialcf, BilinearForm, RestrictedBilinearForm,
+from .forms import (dCut, dFacetPatch, grad, Normalize, specialcf, BilinearForm, RestrictedBilinearForm, LinearForm,
                     Integrate, TrialFunction, TestFunction, x, y, z)
 
 __all__ = [n for n in dir() if not n.startswith("_")]

@@ -27,6 +27,10 @@ class Term(C.Structure):
     _fields_ = [("op_trial", C.c_int), ("op_test", C.c_int), ("coef", C.c_double), ("hpow", C.c_int)]
 
 
+class LTerm(C.Structure):
+    _fields_ = [("op_test", C.c_int), ("coef", C.c_double), ("hpow", C.c_int), ("expo", C.c_int * 3)]
+
+
 class Batch(C.Structure):
     _fields_ = [("table", VP), ("mats", VP), ("nrows", C.c_int64), ("width", C.c_int)]
 
@@ -74,10 +78,16 @@ _SIGS = {
                                   C.c_int, C.c_int, VP, VP]),
     "xgpu_elmat_std": (C.c_int, [VP, C.c_int, C.c_int, C.c_int64, VP, VP, VP, VP, C.c_int, C.POINTER(Term),
                                  C.c_int, C.c_int, VP, VP]),
+    "xgpu_elvec_rule": (C.c_int, [VP, C.c_int, C.c_int, C.c_int64, VP, VP, VP, VP, VP, VP, VP, C.POINTER(LTerm),
+                                  C.c_int, C.c_int, VP, VP]),
+    "xgpu_elvec_std": (C.c_int, [VP, C.c_int, C.c_int, C.c_int64, VP, VP, VP, VP, C.c_int, C.POINTER(LTerm),
+                                 C.c_int, C.c_int, VP, VP]),
     "xgpu_facetpatch": (C.c_int, [VP, C.c_int, C.c_int, C.c_int64, VP, VP, VP, VP, C.c_int, C.c_double, C.c_int, VP]),
     "xgpu_csr_plan": (C.c_int, [VP, C.c_int64, C.POINTER(Batch), C.c_int, C.POINTER(VP), c_i64p]),
     "xgpu_csr_pattern": (C.c_int, [VP, VP, VP, VP]),
     "xgpu_csr_scatter": (C.c_int, [VP, VP, C.POINTER(Batch), C.c_int, VP, VP, VP]),
+    "xgpu_adjacency_plan": (C.c_int, [VP, C.c_int64, C.POINTER(Batch), C.c_int, C.POINTER(VP)]),
+    "xgpu_vec_scatter": (C.c_int, [VP, VP, C.POINTER(Batch), C.c_int, VP]),
     "xgpu_plan_destroy": (None, [VP]),
     "xgpu_plan_phase_ms": (C.c_int, [VP, c_f64p]),
     "xgpu_csr_spmv": (C.c_int, [VP, C.c_int64, VP, VP, VP, VP, VP]),

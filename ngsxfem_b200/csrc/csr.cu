@@ -564,6 +564,21 @@ __global__ void __launch_bounds__(XG_SMALL_BLOCK) k_scatter_small(int ndof, cons
 #undef COL
 }
 
+// LinearForm assembly: thread per dof walks its (sorted) adjacency segment
+__global__ void k_vec_scatter(int64_t ndof, const long long* __restrict__ adj_ptr, const long long* __restrict__ adj,
+                              BatchDev bd, double* __restrict__ out)
+{
+  const int64_t d = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (d >= ndof) return;
+  double s = 0.0;
+  for (long long i = adj_ptr[d]; i < adj_ptr[d + 1]; i++) {
+    const long long e = adj[i];
+    const int bi = XG_ADJ_BATCH(e);
+    if (bd.mats[bi]) s += __ldg(bd.mats[bi] + (size_t)XG_ADJ_ROW(e) * bd.width[bi] + XG_ADJ_LOC(e));
+  }
+  out[d] = s;
+}
+
 __global__ void k_spmv(int64_t nrows, const long long* __restrict__ rowptr, const int32_t* __restrict__ colidx,
                        const double* __restrict__ vals, const double* __restrict__ x, double* __restrict__ y)
 {
@@ -657,8 +672,23 @@ int run_pattern(xgpu_ctx* ctx, xgpu_plan* P, int* stats)
 
 }  // namespace
 
+static int build_plan(xgpu_ctx* ctx, int64_t ndof, const xgpu_batch* batches_host, int nbatches,
+                      xgpu_plan** plan_out, int64_t* nnz_host, bool with_pattern);
+
 extern "C" int xgpu_csr_plan(xgpu_ctx* ctx, int64_t ndof, const xgpu_batch* batches_host, int nbatches,
                              xgpu_plan** plan_out, int64_t* nnz_host)
+{
+  return build_plan(ctx, ndof, batches_host, nbatches, plan_out, nnz_host, true);
+}
+
+extern "C" int xgpu_adjacency_plan(xgpu_ctx* ctx, int64_t ndof, const xgpu_batch* batches_host, int nbatches,
+                                   xgpu_plan** plan_out)
+{
+  return build_plan(ctx, ndof, batches_host, nbatches, plan_out, nullptr, false);
+}
+
+static int build_plan(xgpu_ctx* ctx, int64_t ndof, const xgpu_batch* batches_host, int nbatches,
+                      xgpu_plan** plan_out, int64_t* nnz_host, bool with_pattern)
 {
   if (!ctx || !plan_out || ndof < 0 || ndof >= (int64_t)0x7fffffff)
     return xgpu_fail(ctx, XGPU_ERR_ARG, "xgpu_csr_plan: bad argument (0 <= ndof < 2^31: column indices are int32)");
@@ -714,6 +744,11 @@ extern "C" int xgpu_csr_plan(xgpu_ctx* ctx, int64_t ndof, const xgpu_batch* batc
   P->maxcand = ((int*)ctx->h_pinned)[0];
   P->dups = ((int*)ctx->h_pinned)[1];
   P->ncand = ctx->h_pinned[1];
+  if (!with_pattern) {  // transposed table only (vector assembly)
+    XG_TRY(cudaEventRecord(P->ev[2], st));
+    *plan_out = P;
+    return XGPU_OK;
+  }
   if (ndof > 0) XG_TRYRC(run_pattern(ctx, P, stats));
   XG_TRYRC(xgpu_exclusive_scan_i32(ctx, P->tmp32, ndof, (int64_t*)P->rowptr));
   XG_TRY(cudaEventRecord(P->ev[2], st));
@@ -741,7 +776,7 @@ extern "C" int xgpu_plan_phase_ms(xgpu_plan* P, double* ms_host)
 
 extern "C" int xgpu_csr_pattern(xgpu_ctx* ctx, xgpu_plan* P, int64_t* rowptr, int32_t* colidx)
 {
-  if (!ctx || !P) return xgpu_fail(ctx, XGPU_ERR_ARG, "xgpu_csr_pattern: bad argument");
+  if (!ctx || !P || P->epoch < 0) return xgpu_fail(ctx, XGPU_ERR_ARG, "xgpu_csr_pattern: bad argument (adjacency-only plan?)");
   cudaStream_t st = ctx->stream;
   XGPU_CUDA(ctx, cudaMemcpyAsync(rowptr, P->rowptr, sizeof(long long) * (P->ndof + 1), cudaMemcpyDeviceToDevice, st));
   if (P->ndof == 0 || P->nnz == 0) return XGPU_OK;
@@ -762,7 +797,7 @@ extern "C" int xgpu_csr_pattern(xgpu_ctx* ctx, xgpu_plan* P, int64_t* rowptr, in
 extern "C" int xgpu_csr_scatter(xgpu_ctx* ctx, xgpu_plan* P, const xgpu_batch* batches_host, int nbatches,
                                 const int64_t* rowptr, const int32_t* colidx, double* vals)
 {
-  if (!ctx || !P || nbatches != P->bd.nb) return xgpu_fail(ctx, XGPU_ERR_ARG, "xgpu_csr_scatter: bad argument");
+  if (!ctx || !P || nbatches != P->bd.nb || P->epoch < 0) return xgpu_fail(ctx, XGPU_ERR_ARG, "xgpu_csr_scatter: bad argument");
   BatchDev bd = P->bd;
   for (int i = 0; i < nbatches; i++) {
     if (batches_host[i].nrows != bd.rowoff[i + 1] - bd.rowoff[i] || batches_host[i].width != bd.width[i])
@@ -802,6 +837,21 @@ extern "C" int xgpu_csr_scatter(xgpu_ctx* ctx, xgpu_plan* P, const xgpu_batch* b
     k_scatter<false><<<grid, nw * 32, sm, ctx->stream>>>((int)P->ndof, P->adj_ptr, P->adj, bd, RCAP, HS, SL, G, trips,
                                                          (const long long*)rowptr, colidx, vals, XG_SMALL_NR);
   }
+  XGPU_LAUNCH_CHECK(ctx);
+  return XGPU_OK;
+}
+
+extern "C" int xgpu_vec_scatter(xgpu_ctx* ctx, xgpu_plan* P, const xgpu_batch* batches_host, int nbatches, double* out)
+{
+  if (!ctx || !P || nbatches != P->bd.nb) return xgpu_fail(ctx, XGPU_ERR_ARG, "xgpu_vec_scatter: bad argument");
+  BatchDev bd = P->bd;
+  for (int i = 0; i < nbatches; i++) {
+    if (batches_host[i].nrows != bd.rowoff[i + 1] - bd.rowoff[i] || batches_host[i].width != bd.width[i])
+      return xgpu_fail(ctx, XGPU_ERR_ARG, "xgpu_vec_scatter: batches do not match the plan");
+    bd.mats[i] = batches_host[i].mats;
+  }
+  if (P->ndof == 0) return XGPU_OK;
+  k_vec_scatter<<<nblk(P->ndof, 256), 256, 0, ctx->stream>>>(P->ndof, P->adj_ptr, P->adj, bd, out);
   XGPU_LAUNCH_CHECK(ctx);
   return XGPU_OK;
 }

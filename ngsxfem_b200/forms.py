@@ -122,6 +122,49 @@ class Proxy:
             return Form.from_pair(self, o)
         if isinstance(o, Form):
             return o.__rmul__(self)
+        if isinstance(o, CoordMonomial):
+            return LForm.from_proxy(self) * o
+        if isinstance(o, CutDifferentialSymbol):
+            return Integral(LForm.from_proxy(self), o)
+        return NotImplemented
+
+    __rmul__ = __mul__
+
+
+class LForm:
+    """linear form integrand: sum of (op_test, coef, hpow, expo) = coef h^hpow x^expo op_test(v)
+    (menu of xfem/symboliccutlfi.cpp's CoefficientFunction on the accelerated path)"""
+
+    def __init__(self, terms, space):
+        self.terms, self.space = terms, space
+
+    @staticmethod
+    def from_proxy(v):
+        if not v.is_test:
+            raise XgpuError("a linear form needs a test function")
+        if v.op not in (OP_ID, OP_DN) or v.other:
+            raise XgpuError("linear forms: menu is f*v and f*(grad(v)*n)")
+        return LForm([(v.op, v.scal.c, v.scal.hpow, (0, 0, 0))], v.space)
+
+    def __add__(self, o):
+        if isinstance(o, Proxy):
+            o = LForm.from_proxy(o)
+        if isinstance(o, LForm):
+            return LForm(self.terms + o.terms, self.space)
+        return NotImplemented
+
+    def __mul__(self, o):
+        if isinstance(o, numbers.Number):
+            o = Scalar(float(o))
+        if isinstance(o, MeshSize):
+            o = Scalar(1.0, o.power)
+        if isinstance(o, Scalar):
+            return LForm([(a, c * o.c, hp + o.hpow, ex) for a, c, hp, ex in self.terms], self.space)
+        if isinstance(o, CoordMonomial):
+            return LForm([(a, c * o.coef, hp, tuple(e1 + e2 for e1, e2 in zip(ex, o.expo))) for a, c, hp, ex in self.terms],
+                         self.space)
+        if isinstance(o, CutDifferentialSymbol):
+            return Integral(self, o)
         return NotImplemented
 
     __rmul__ = __mul__
@@ -479,6 +522,9 @@ class BilinearForm:
             if not all(t[0] == OP_JUMP and t[1] == OP_JUMP for t in terms):
                 raise XgpuError("dFacetPatch: only c*h^k*(u-u.Other())*(v-v.Other()) is supported")
             l_f = integ.dx.definedonelements.indices()
+            # interior facets only: NGSolve's facet loop hands boundary facets to BND integrators, a facet-patch
+            # integrator never sees them (T_CalcFacetMatrix throws for LocalFacetNr2 == -1, symboliccutbfi.cpp:1992)
+            l_f = l_f[fe[l_f.long(), 1] >= 0].contiguous()
             key = id(integ.dx.definedonelements)
             for (_, _, c, hp) in terms:
                 with ctx.deformation(integ.dx.deformation):
@@ -515,6 +561,67 @@ class BilinearForm:
         return self
 
 
+class LinearForm:
+    """LinearForm(space); f += coef * x**a * y**b * v * dCut(lset, dt, definedonelements=...); f.Assemble() -> f.vec
+    (SymbolicCutLinearFormIntegrator, xfem/symboliccutlfi.cpp:51-140; demos/fictdom.py:132-137).  Element vectors
+    on the GPU, summed per dof in a fixed (element, local index) order."""
+
+    def __init__(self, space, name="lf", **flags):
+        self.space, self.integrals, self.vec = space, [], None
+
+    def __iadd__(self, o):
+        ints = [o] if isinstance(o, Integral) else (o.ints if isinstance(o, SumOfIntegrals) else None)
+        if ints is None or not all(isinstance(i.form, LForm) and isinstance(i.dx, CutDifferentialSymbol) for i in ints):
+            raise XgpuError("LinearForm += expects f * v * dCut(...)")
+        self.integrals.extend(ints)
+        return self
+
+    def Assemble(self):
+        sp = self.space
+        mesh = sp.mesh
+        dim, p, ne, nd, dev = mesh.dim, sp.order, mesh.ne, sp.nd, mesh.device
+        ctx = default_ctx(dev.index)
+        act = getattr(sp, "active_elements", None)
+        active = BitArray(ne, words=act) if act is not None else BitArray(ne, dev).Set()
+        l_A = active.indices()
+        self.vec = torch.zeros(sp.ndof, dtype=torch.float64, device=dev)
+        if not l_A.numel() or not self.integrals:
+            return self
+        slot_A = ops.bitset_rank(active.bits, ne, ctx=ctx)[0]
+        v_A = torch.zeros((l_A.numel(), nd), dtype=torch.float64, device=dev)
+        for integ in self.integrals:
+            dx = integ.dx
+            order = dx.order if dx.order >= 0 else 2 * p  # symboliccutlfi.cpp:86-88
+            don = dx.definedonelements
+            if don is None:
+                l, slots = l_A, None
+            else:
+                l = ops.bitset_to_list(ops.bitset_op(ops.BIT_AND, active.bits, don.bits, ne, ctx=ctx), ne, ctx=ctx)
+                slots = slot_A[l.long()].contiguous()
+            if not l.numel():
+                continue
+            ls = dx.levelset
+            with ctx.deformation(dx.deformation):
+                if isinstance(ls, (list, tuple)):
+                    if any(t[0] == OP_DN for t in integ.form.terms):
+                        raise XgpuError("normal-derivative terms need a single level set")
+                    phis = torch.stack([_lset_vec(g, mesh) for g in ls]).contiguous()
+                    dts = _normalize_dtlist(dx.domain_type, len(ls))
+                    off, q, w = ops.cutquad_ml(dim, l, mesh.elements, mesh.points, phis, dts, order, ctx=ctx)
+                    phi = phis[0].contiguous()
+                else:
+                    phi = _lset_vec(ls, mesh)
+                    off, q, w = ops.cutquad(dim, l, mesh.elements, mesh.points, phi, int(dx.domain_type), order, ctx=ctx)
+                ctx.raise_on_geometry_error()
+                if w.numel():
+                    ops.elvec_rule(dim, p, l, mesh.elements, mesh.points, phi, off, q, w, integ.form.terms, out=v_A,
+                                   accumulate=True, slots=slots, ctx=ctx)
+        table = sp.rows(l_A) if hasattr(sp, "rows") else ops.gather_rows(sp.el_dofs, l_A, None)
+        plan = ops.adjacency_plan(sp.ndof, [table], ctx=ctx)
+        ops.vec_scatter(plan, [(table, v_A)], out=self.vec)
+        return self
+
+
 def _mask_from_list(lst, n):
     import numpy as np
     m = np.zeros(n, dtype=bool)
@@ -538,6 +645,10 @@ class CoordMonomial:
     def __mul__(self, o):
         if isinstance(o, numbers.Number):
             return CoordMonomial(self.expo, self.coef * o)
+        if isinstance(o, (Proxy, LForm)):
+            return o.__mul__(self)
+        if not isinstance(o, CoordMonomial):
+            return NotImplemented
         return CoordMonomial(tuple(a + b for a, b in zip(self.expo, o.expo)), self.coef * o.coef)
 
     __rmul__ = __mul__

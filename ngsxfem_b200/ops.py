@@ -8,7 +8,7 @@ import ctypes as C
 import torch
 
 from . import _lib
-from ._lib import Batch, Term, default_ctx, ptr
+from ._lib import Batch, LTerm, Term, default_ctx, ptr
 
 NEG, POS, IF = 0, 1, 2
 OP_ID, OP_GRAD, OP_DN = 0, 1, 2
@@ -280,6 +280,40 @@ def elmat_std(dim, fe_order, elems, el_vtx, vtx_xyz, phi, order, terms, out=None
     return out
 
 
+def lterms_array(terms):
+    """terms: (op_test, coef, hpow, (e0, e1, e2))"""
+    arr = (LTerm * max(1, len(terms)))()
+    for i, (ot, c, hp, ex) in enumerate(terms):
+        arr[i].op_test = int(ot); arr[i].coef = float(c); arr[i].hpow = int(hp)
+        for k in range(3):
+            arr[i].expo[k] = int(ex[k]) if k < len(ex) else 0
+    return arr
+
+
+def elvec_rule(dim, fe_order, elems, el_vtx, vtx_xyz, phi, off, pts, wts, terms, out=None, accumulate=False, slots=None, ctx=None):
+    """element vectors on per-element rules (xfem/symboliccutlfi.cpp:51-140)"""
+    ctx = ctx or default_ctx()
+    n = el_vtx.shape[0] if elems is None else elems.numel()
+    nd = h1_ndof(dim, fe_order)
+    if out is None:
+        out = torch.empty((n, nd), dtype=torch.float64, device=el_vtx.device)
+    ctx.check(ctx.lib.xgpu_elvec_rule(ctx.h, dim, fe_order, n, ptr(elems), ptr(_i32(el_vtx)), ptr(_f64(vtx_xyz)), ptr(phi),
+                                      ptr(off), ptr(pts), ptr(wts), lterms_array(terms), len(terms), int(accumulate),
+                                      ptr(slots), ptr(out)))
+    return out
+
+
+def elvec_std(dim, fe_order, elems, el_vtx, vtx_xyz, phi, order, terms, out=None, accumulate=False, slots=None, ctx=None):
+    ctx = ctx or default_ctx()
+    n = el_vtx.shape[0] if elems is None else elems.numel()
+    nd = h1_ndof(dim, fe_order)
+    if out is None:
+        out = torch.empty((n, nd), dtype=torch.float64, device=el_vtx.device)
+    ctx.check(ctx.lib.xgpu_elvec_std(ctx.h, dim, fe_order, n, ptr(elems), ptr(_i32(el_vtx)), ptr(_f64(vtx_xyz)), ptr(phi),
+                                     order, lterms_array(terms), len(terms), int(accumulate), ptr(slots), ptr(out)))
+    return out
+
+
 def facetpatch(dim, fe_order, facets, facet_els, el_vtx, vtx_xyz, order, coef, hpow, out=None, ctx=None):
     ctx = ctx or default_ctx()
     n = facet_els.shape[0] if facets is None else facets.numel()
@@ -328,6 +362,24 @@ def csr_plan(ndof, tables, ctx=None):
     nnz = C.c_int64(0)
     ctx.check(ctx.lib.xgpu_csr_plan(ctx.h, ndof, arr, len(tables), C.byref(h), C.byref(nnz)))
     return CsrPlan(ctx, h, nnz.value, ndof, len(tables))
+
+
+def adjacency_plan(ndof, tables, ctx=None):
+    """transposed table only (LinearForm assembly)"""
+    ctx = ctx or default_ctx()
+    arr = _batches([(t, None) for t in tables])
+    h = _lib.VP()
+    ctx.check(ctx.lib.xgpu_adjacency_plan(ctx.h, ndof, arr, len(tables), C.byref(h)))
+    return CsrPlan(ctx, h, 0, ndof, len(tables))
+
+
+def vec_scatter(plan, batches, out=None):
+    """batches: (table, vecs[nrows x width]); out[d] = fixed-order sum of the entries of dof d"""
+    if out is None:
+        out = torch.empty(plan.ndof, dtype=torch.float64, device=batches[0][0].device)
+    arr = _batches(batches)
+    plan.ctx.check(plan.ctx.lib.xgpu_vec_scatter(plan.ctx.h, plan.h, arr, len(batches), ptr(out)))
+    return out
 
 
 def csr_pattern(plan, device):

@@ -240,6 +240,56 @@ int xo_cut_elmat(const xo_trafo* T, int p, const double* lsetvals, int dt, int o
   return np;
 }
 
+/* symboliccutlfi.cpp:51-140 (scalar evaluation branch :141-175): elvec += sum_q B_q^T (f(x_q) w_q |det F|) */
+void xo_elvec_from_rule(const xo_trafo* T, int p, const double* lsetvals,
+                        const double* pts, const double* wts, int np,
+                        const xo_lterm* terms, int nterms, double* elvec)
+{
+  int D = T->dim, nd = xo_h1_ndof(D, p);
+  double sh[64], dsh[64 * 3], dn[64];
+  double lgr[3] = { 0, 0, 0 };
+  if (lsetvals) for (int i = 0; i < D; i++) lgr[i] = lsetvals[i] - lsetvals[D];
+  for (int q = 0; q < np; q++) {
+    double F[9], Fi[9], x[3] = { 0, 0, 0 };
+    xo_trafo_eval(T, &pts[3 * q], F, x);
+    double det = inv_det(D, F, Fi);
+    double meas = fabs(det);
+    double h = pow(meas, 1.0 / D);
+    xo_h1_shapes(D, p, T->vnum, &pts[3 * q], sh, dsh);
+    double n[3] = { 0, 0, 0 }, nn = 0;
+    for (int i = 0; i < D; i++) { for (int j = 0; j < D; j++) n[i] += Fi[j * D + i] * lgr[j]; nn += n[i] * n[i]; }
+    nn = sqrt(nn);
+    if (nn > 0) for (int i = 0; i < D; i++) n[i] /= nn;
+    for (int a = 0; a < nd; a++) {
+      dn[a] = 0;
+      for (int i = 0; i < D; i++) {
+        double s = 0;
+        for (int j = 0; j < D; j++) s += Fi[j * D + i] * dsh[a * D + j];
+        dn[a] += s * n[i];
+      }
+    }
+    double fac = wts[q] * meas;
+    for (int t = 0; t < nterms; t++) {
+      double c = terms[t].coef * fac;
+      if (terms[t].hpow != 0) c *= pow(h, (double)terms[t].hpow);
+      for (int i = 0; i < D; i++) for (int e = 0; e < terms[t].expo[i]; e++) c *= x[i];
+      const double* b = (terms[t].op_test == XO_OP_ID) ? sh : dn;
+      for (int i = 0; i < nd; i++) elvec[i] += c * b[i];
+    }
+  }
+}
+
+int xo_cut_elvec(const xo_trafo* T, int p, const double* lsetvals, int dt, int order,
+                 const xo_lterm* terms, int nterms, double* elvec)
+{
+  static __thread double pts[3 * 4 * XO_MAXPTS_RULE], wts[4 * XO_MAXPTS_RULE];
+  if (order < 0) order = 2 * p; /* symboliccutlfi.cpp:86-88 */
+  int np = xo_straight_cut_rule(T, lsetvals, dt, order, pts, wts, 4 * XO_MAXPTS_RULE, 0);
+  if (np <= 0) return np;
+  xo_elvec_from_rule(T, p, lsetvals, pts, wts, np, terms, nterms, elvec);
+  return np;
+}
+
 /* MapPatchIntegrationPoint<D>: symboliccutbfi.cpp:1747-1846 (non space-time).
  * from (xhat_from, weight w_from) on T_from  ->  xhat_to, weight w_to on T_to.  returns 1 on
  * Newton failure (low order guess taken). */

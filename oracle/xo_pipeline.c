@@ -89,6 +89,33 @@ int xo_batch_cut_elmats(int dim, int fe_order, int64_t n, const int32_t* elems, 
   return err;
 }
 
+/* element vectors for a list of elements (SymbolicCutLFI over dCut(lset, dt, order)): vecs[i] (nd) zeroed then filled */
+int xo_batch_cut_elvecs(int dim, int fe_order, int64_t n, const int32_t* elems, const int32_t* el_vtx,
+                        const double* vtx_xyz, const double* phi, int dt, int order,
+                        const xo_lterm* terms, int nterms, int def_order, const double* def,
+                        double* vecs)
+{
+  int nv = dim + 1, nd = xo_h1_ndof(dim, fe_order);
+  int ndd = def_order > 0 ? xo_h1_ndof(dim, def_order) : 0;
+  int err = 0;
+#pragma omp parallel for schedule(dynamic, 256)
+  for (int64_t i = 0; i < n; i++) {
+    int64_t el = elems ? elems[i] : i;
+    double v[4];
+    xo_trafo T;
+    fill_trafo(&T, dim, el_vtx + el * nv, vtx_xyz, def_order, def ? def + el * (int64_t)ndd * dim : 0);
+    for (int k = 0; k < nv; k++) v[k] = phi[el_vtx[el * nv + k]];
+    double* m = vecs + i * (int64_t)nd;
+    memset(m, 0, sizeof(double) * nd);
+    int c = xo_cut_elvec(&T, fe_order, v, dt, order, terms, nterms, m);
+    if (c < 0) {
+#pragma omp critical
+      err = c;
+    }
+  }
+  return err;
+}
+
 /* facet patch matrices for a list of facets */
 int xo_batch_facet_patch(int dim, int fe_order, int64_t n, const int32_t* facets, const int32_t* facet_els,
                          const int32_t* el_vtx, const double* vtx_xyz, int order, double coef, int hpow,

@@ -139,6 +139,21 @@ void xo_elmat_from_rule(const xo_trafo* T, int fe_order, const double* lsetvals,
 int xo_facet_patch_elmat(const xo_trafo* T1, const xo_trafo* T2, int fe_order, int order,
                          double coef, int hpow, double* elmat);
 
+/* SymbolicCutLinearFormIntegrator::T_CalcElementVector (xfem/symboliccutlfi.cpp:51-140) for the closed menu
+ *   f(x) * op_test(v),  f = coef * h^hpow * x^e0 y^e1 z^e2,  op_test in {ID, DN}:
+ * elvec_i += sum_q (w_q |det F|) f(x_q) op_test(phi_i)(x_q).  Rule order: `order`, or 2*fe_order if < 0
+ * (:86-88; no reduction by the differentiation order).  returns #points used or an error. */
+typedef struct { int op_test; double coef; int hpow; int expo[3]; } xo_lterm;
+void xo_elvec_from_rule(const xo_trafo* T, int fe_order, const double* lsetvals,
+                        const double* pts, const double* wts, int np,
+                        const xo_lterm* terms, int nterms, double* elvec);
+int xo_cut_elvec(const xo_trafo* T, int fe_order, const double* lsetvals, int dt, int order,
+                 const xo_lterm* terms, int nterms, double* elvec);
+int xo_batch_cut_elvecs(int dim, int fe_order, int64_t n, const int32_t* elems, const int32_t* el_vtx,
+                        const double* vtx_xyz, const double* phi, int dt, int order,
+                        const xo_lterm* terms, int nterms, int def_order, const double* def,
+                        double* vecs);
+
 /* ------------------------------------------------------------------ sparse assembly */
 /* Graph = union of cliques of the rows of `table` (nrows x width, -1 = unused), sorted columns
  * (restrictedblf.cpp:142-163 -> NGSolve MatrixGraph).  Call with colidx==NULL to get nnz via rowptr. */

@@ -236,6 +236,35 @@ def elmat_from_rule(T, fe_order, lsetvals, pts, wts, terms, out=None):
     return m
 
 
+class LTerm(C.Structure):
+    _fields_ = [("op_test", C.c_int), ("coef", C.c_double), ("hpow", C.c_int), ("expo", C.c_int * 3)]
+
+
+def lterms_array(terms):
+    """terms: (op_test, coef, hpow, (e0, e1, e2))"""
+    arr = (LTerm * len(terms))()
+    for i, (ot, c, hp, ex) in enumerate(terms):
+        arr[i].op_test = ot; arr[i].coef = c; arr[i].hpow = hp
+        for k in range(3):
+            arr[i].expo[k] = int(ex[k]) if k < len(ex) else 0
+    return arr
+
+
+def batch_cut_elvecs(dim, fe_order, elems, el_vtx, vtx_xyz, phi, dt, order, terms, def_order=0, deform=None):
+    el_vtx = _i32(el_vtx); vtx_xyz = _f64(vtx_xyz); phi = _f64(phi)
+    el = None if elems is None else _i32(elems)
+    n = el_vtx.shape[0] if el is None else len(el)
+    nd = h1_ndof(dim, fe_order)
+    vecs = np.zeros((n, nd))
+    ta = lterms_array(terms)
+    d = None if deform is None else _f64(deform)
+    err = lib().xo_batch_cut_elvecs(dim, fe_order, C.c_int64(n), _p(el, C.c_int32), _p(el_vtx, C.c_int32), _p(vtx_xyz),
+                                    _p(phi), dt, order, ta, len(terms), def_order, _p(d), _p(vecs))
+    if err:
+        raise RuntimeError(f"oracle error {err}")
+    return vecs
+
+
 def facet_patch_elmat(T1, T2, fe_order, order, coef, hpow):
     nd = h1_ndof(T1.dim, fe_order)
     m = np.zeros((2 * nd, 2 * nd))

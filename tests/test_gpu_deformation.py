@@ -117,7 +117,9 @@ def test_uncut_elements_on_a_deformed_mesh_leave_the_affine_fast_path(p):
 @pytest.mark.parametrize("dim,p,n", [(3, 2, 3), (3, 3, 2), (2, 2, 5), (2, 4, 3)])
 def test_facet_patch_on_deformed_elements_matches_oracle(dim, p, n):
     mesh = (xf.MakeStructured3DMesh if dim == 3 else xf.MakeStructured2DMesh)(nx=n, **({} if dim == 3 else {"ny": n}), device=DEV)
-    defo = random_deformation(xf.H1(mesh, order=p), 0.04 / n, 17)
+    # higher-order bubbles are extrapolated into the neighbour element by the patch mapping: keep them small enough
+    # for the Newton iteration of MapPatchIntegrationPoint to converge everywhere (the oracle counts failures)
+    defo = random_deformation(xf.H1(mesh, order=p), (0.04 if p <= 2 else 0.004) / n, 17)
     _, _, fe = mesh.facets()
     inner = torch.nonzero(fe[:, 1] >= 0).reshape(-1).to(torch.int32)
     ctx = ops.default_ctx()
@@ -135,7 +137,7 @@ def test_isoparametric_assembly_with_ghost_penalty_matches_oracle():
     mesh = xf.MakeStructured3DMesh(nx=n, device=DEV)
     lset = sphere(mesh)
     V0 = xf.H1(mesh, order=p, dgjumps=True)
-    defo = random_deformation(xf.H1(mesh, order=p), 0.03 / n, 23)
+    defo = random_deformation(xf.H1(mesh, order=p), 0.004 / n, 23)
     ci = xf.CutInfo(mesh, lset)
     hasneg, hasif = ci.GetElementsOfType(xf.HASNEG), ci.GetElementsOfType(xf.IF)
     gpf = xf.GetFacetsWithNeighborTypes(mesh, a=hasneg, b=hasif, use_and=True)
@@ -157,11 +159,13 @@ def test_isoparametric_assembly_with_ghost_penalty_matches_oracle():
     for k, e in enumerate(l_if):
         m[pos[e]] += m_if[k]
     _, _, fe = mesh.facets()
-    l_f = gpf.indices().cpu().numpy()
+    l_f = gpf.indices()
+    l_f = l_f[fe[l_f.long(), 1] >= 0].contiguous()  # boundary facets carry no patch
+    fel = fe[l_f.long()]
+    l_f = l_f.cpu().numpy()
     mf, nfail = xo.batch_facet_patch(3, p, l_f, fe.cpu().numpy(), els, pts, -1, 0.1, -2, def_order=p, deform=loc)
     assert nfail == 0 and len(l_f) > 0
     t_el = V.rows(hasneg.indices()).cpu().numpy()
-    fel = fe[gpf.indices().long()]
     t_f = torch.cat([V.rows(fel[:, 0].contiguous()), V.rows(fel[:, 1].contiguous())], dim=1).cpu().numpy()
     av = a.mat.to_scipy()
     # dense comparison through scipy (two batches of different width)

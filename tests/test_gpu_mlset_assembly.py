@@ -39,7 +39,7 @@ def _oracle_mats(mesh, elems, phis, dts, p, order, terms):
 
 
 @pytest.mark.parametrize("n,p,dts", [(4, 3, [(NEG, NEG, NEG, NEG)]), (5, 2, [(NEG, NEG, NEG, NEG), (NEG, NEG, NEG, IF)]),
-                                     (4, 1, [(NEG, IF, NEG, NEG)])])
+                                     (4, 1, [(IF, NEG, NEG, NEG)])])
 def test_mlset_domain_assembly_matches_oracle(n, p, dts):
     mesh = xf.MakeStructured3DMesh(nx=n, device=DEV)
     lsets = _lsets(mesh)
