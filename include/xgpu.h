@@ -210,6 +210,11 @@ int xgpu_adjacency_plan(xgpu_ctx* ctx, int64_t ndof, const xgpu_batch* batches_h
 /* LinearForm assembly (NGSolve AddElementVector): out[d] = sum of the element-vector entries whose dof is d, in
  * (batch, row, local index) order — deterministic.  A batch's `mats` points to nrows x width doubles here. */
 int xgpu_vec_scatter(xgpu_ctx* ctx, xgpu_plan* plan, const xgpu_batch* batches_host, int nbatches, double* out);
+/* xgpu_csr_pattern + xgpu_csr_scatter in one pass over the rows (BilinearForm.Assemble builds both every time):
+ * the scatter kernels read each row's columns from the plan's pattern scratch and write rowptr, colidx AND vals
+ * — the separate compaction copy (and its 1.6 GB of DRAM traffic on config 2) disappears.  Same results, bit for bit. */
+int xgpu_csr_assemble(xgpu_ctx* ctx, xgpu_plan* plan, const xgpu_batch* batches_host, int nbatches,
+                      int64_t* rowptr, int32_t* colidx, double* vals);
 void xgpu_plan_destroy(xgpu_plan* plan);
 /* device time of the two halves of xgpu_csr_plan (CUDA events on the plan's stream): ms_host[0] =
  * transposed table (histogram, scan, fill, segment sort), ms_host[1] = pattern pass (bench.py) */

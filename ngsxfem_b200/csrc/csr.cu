@@ -82,9 +82,43 @@ __global__ void k_adj_fill(const int32_t* __restrict__ table, int64_t nent, int 
   adj[adj_ptr[d] + pos] = XG_ADJ(bi, r, loc);
 }
 
-// sort every adjacency segment ascending (insertion sort, segments are short), compute the
-// candidate count of each row = sum of the widths of the adjacent table rows, and note whether
-// any dof occurs twice inside one table row (facet-patch rows [dofs(el1) ; dofs(el2)] do)
+// bitonic network on K registers (compile-time indices: the array never leaves the register file)
+template <int K>
+__device__ __forceinline__ void sort_regs(long long (&r)[K])
+{
+#pragma unroll
+  for (int size = 2; size <= K; size <<= 1)
+#pragma unroll
+    for (int stride = size >> 1; stride > 0; stride >>= 1)
+#pragma unroll
+      for (int i = 0; i < K; i++) {
+        const int j = i ^ stride;
+        if (j > i) {
+          const bool up = ((i & size) == 0);
+          const long long a = r[i], b = r[j];
+          const bool sw = (a > b) == up;
+          r[i] = sw ? b : a;
+          r[j] = sw ? a : b;
+        }
+      }
+}
+
+template <int K>
+__device__ __forceinline__ void sort_segment_regs(long long* __restrict__ seg, int na)
+{
+  long long r[K];
+#pragma unroll
+  for (int k = 0; k < K; k++) r[k] = (k < na) ? seg[k] : 0x7fffffffffffffffLL;  // all loads in flight together
+  sort_regs<K>(r);
+#pragma unroll
+  for (int k = 0; k < K; k++) if (k < na) seg[k] = r[k];
+}
+
+// sort every adjacency segment ascending (the atomic-cursor fill leaves them in arbitrary order): segments of up to
+// 32 entries go through a register sorting network (loads / stores of the whole segment are independent, so they
+// pipeline; the former in-place insertion sort was a chain of dependent global accesses), longer ones fall back to
+// insertion sort.  Also computes the candidate count of each row = sum of the widths of the adjacent table rows, and
+// notes whether any dof occurs twice inside one table row (facet-patch rows [dofs(el1) ; dofs(el2)] do)
 __global__ void k_adj_sort(int64_t ndof, const long long* __restrict__ adj_ptr, long long* __restrict__ adj,
                            BatchDev bd, int32_t* __restrict__ cand, int* __restrict__ stats)
 {
@@ -92,11 +126,18 @@ __global__ void k_adj_sort(int64_t ndof, const long long* __restrict__ adj_ptr, 
   int c = 0, dup = 0;
   if (d < ndof) {
     const long long a = adj_ptr[d], b = adj_ptr[d + 1];
-    for (long long i = a + 1; i < b; i++) {
-      const long long key = adj[i];
-      long long j = i - 1;
-      while (j >= a && adj[j] > key) { adj[j + 1] = adj[j]; j--; }
-      adj[j + 1] = key;
+    const int na = (int)(b - a);
+    if (na <= 1) {
+    } else if (na <= 8) sort_segment_regs<8>(adj + a, na);
+    else if (na <= 16) sort_segment_regs<16>(adj + a, na);
+    else if (na <= 32) sort_segment_regs<32>(adj + a, na);
+    else {
+      for (long long i = a + 1; i < b; i++) {
+        const long long key = adj[i];
+        long long j = i - 1;
+        while (j >= a && adj[j] > key) { adj[j + 1] = adj[j]; j--; }
+        adj[j + 1] = key;
+      }
     }
     long long prev = -1;
     for (long long i = a; i < b; i++) {
@@ -377,7 +418,8 @@ template <bool DUPS>
 __global__ void __launch_bounds__(256) k_scatter(int ndof, const long long* __restrict__ adj_ptr,
                                                  const long long* __restrict__ adj, BatchDev bd, int RCAP, int HS, int GS,
                                                  int NG, int trips, const long long* __restrict__ rowptr,
-                                                 const int32_t* __restrict__ colidx, double* __restrict__ vals, int small_nr)
+                                                 const int32_t* __restrict__ colidx, double* __restrict__ vals, int small_nr,
+                                                 const long long* __restrict__ src_off, int32_t* __restrict__ col_out)
 {
   extern __shared__ double sacc[];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, nwb = blockDim.x >> 5;
@@ -404,9 +446,12 @@ __global__ void __launch_bounds__(256) k_scatter(int ndof, const long long* __re
     for (int k = ls; k < (have ? H : 0); k += GS) hkey[k] = XG_EMPTY;
     __syncwarp();
     {
-      const int32_t* __restrict__ cr = colidx + r0;
+      // fused compaction (xgpu_csr_assemble): the row's columns come from the pattern scratch at its candidate
+      // offset and are copied to their final place here
+      const int32_t* __restrict__ cr = src_off ? colidx + (have ? src_off[d] : 0) : colidx + r0;
       for (int k = ls; k < nr; k += GS) {
         const int c = __ldg(cr + k);
+        if (col_out) col_out[r0 + k] = c;
         acc[k] = 0.0;
         unsigned h = ((unsigned)c * 2654435761u) >> shift;
         while (atomicCAS(&hkey[h], XG_EMPTY, c) != XG_EMPTY) h = (h + 1) & (H - 1);  // columns of a row are distinct
@@ -495,7 +540,9 @@ __global__ void __launch_bounds__(256) k_scatter(int ndof, const long long* __re
 __global__ void __launch_bounds__(XG_SMALL_BLOCK) k_scatter_small(int ndof, const long long* __restrict__ adj_ptr,
                                                                   const long long* __restrict__ adj, BatchDev bd,
                                                                   const long long* __restrict__ rowptr,
-                                                                  const int32_t* __restrict__ colidx, double* __restrict__ vals)
+                                                                  const int32_t* __restrict__ colidx, double* __restrict__ vals,
+                                                                  const long long* __restrict__ src_off,
+                                                                  int32_t* __restrict__ col_out)
 {
   extern __shared__ double ssm[];
   double* acc = ssm + threadIdx.x;
@@ -506,9 +553,10 @@ __global__ void __launch_bounds__(XG_SMALL_BLOCK) k_scatter_small(int ndof, cons
     const long long r0 = rowptr[d];
     const int nr = (int)(rowptr[d + 1] - r0);
     if (nr == 0 || nr > XG_SMALL_NR) continue;
+    const int32_t* __restrict__ cr = src_off ? colidx + src_off[d] : colidx + r0;  // fused compaction, see k_scatter
 #pragma unroll
     for (int k = 0; k < XG_SMALL_NR; k++) {
-      COL(k) = (k < nr) ? __ldg(colidx + r0 + k) : XG_EMPTY;
+      COL(k) = (k < nr) ? __ldg(cr + k) : XG_EMPTY;
       ACC(k) = 0.0;
     }
     const long long a = adj_ptr[d];
@@ -559,6 +607,7 @@ __global__ void __launch_bounds__(XG_SMALL_BLOCK) k_scatter_small(int ndof, cons
       }
     }
     for (int k = 0; k < nr; k++) vals[r0 + k] = ACC(k);
+    if (col_out) for (int k = 0; k < nr; k++) col_out[r0 + k] = COL(k);
   }
 #undef ACC
 #undef COL
@@ -794,8 +843,34 @@ extern "C" int xgpu_csr_pattern(xgpu_ctx* ctx, xgpu_plan* P, int64_t* rowptr, in
   return XGPU_OK;
 }
 
+static int run_scatter(xgpu_ctx* ctx, xgpu_plan* P, const xgpu_batch* batches_host, int nbatches,
+                       const int64_t* rowptr, const int32_t* colidx, double* vals, const long long* src_off, int32_t* col_out);
+
 extern "C" int xgpu_csr_scatter(xgpu_ctx* ctx, xgpu_plan* P, const xgpu_batch* batches_host, int nbatches,
                                 const int64_t* rowptr, const int32_t* colidx, double* vals)
+{
+  return run_scatter(ctx, P, batches_host, nbatches, rowptr, colidx, vals, nullptr, nullptr);
+}
+
+extern "C" int xgpu_csr_assemble(xgpu_ctx* ctx, xgpu_plan* P, const xgpu_batch* batches_host, int nbatches,
+                                 int64_t* rowptr, int32_t* colidx, double* vals)
+{
+  if (!ctx || !P || P->epoch < 0) return xgpu_fail(ctx, XGPU_ERR_ARG, "xgpu_csr_assemble: bad argument");
+  XGPU_CUDA(ctx, cudaMemcpyAsync(rowptr, P->rowptr, sizeof(long long) * (P->ndof + 1), cudaMemcpyDeviceToDevice, ctx->stream));
+  if (P->ndof == 0 || P->nnz == 0) return XGPU_OK;
+  if (P->epoch != ctx->epoch) {  // another plan has used the shared scratch since: redo the pass
+    void* sp;
+    int rc = xgpu_scratch(ctx, 6, 64, &sp);
+    if (rc) return rc;
+    rc = run_pattern(ctx, P, (int*)sp);
+    if (rc) return rc;
+  }
+  return run_scatter(ctx, P, batches_host, nbatches, (const int64_t*)P->rowptr, (const int32_t*)ctx->scratch[8], vals,
+                     P->candoff, colidx);
+}
+
+static int run_scatter(xgpu_ctx* ctx, xgpu_plan* P, const xgpu_batch* batches_host, int nbatches,
+                       const int64_t* rowptr, const int32_t* colidx, double* vals, const long long* src_off, int32_t* col_out)
 {
   if (!ctx || !P || nbatches != P->bd.nb || P->epoch < 0) return xgpu_fail(ctx, XGPU_ERR_ARG, "xgpu_csr_scatter: bad argument");
   BatchDev bd = P->bd;
@@ -824,18 +899,19 @@ extern "C" int xgpu_csr_scatter(xgpu_ctx* ctx, xgpu_plan* P, const xgpu_batch* b
     if (gs > XGPU_NSM * 64) gs = XGPU_NSM * 64;
     const size_t sms = (size_t)XG_SMALL_NR * XG_SMALL_BLOCK * (sizeof(double) + sizeof(int));
     XGPU_CUDA(ctx, cudaFuncSetAttribute(k_scatter_small, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sms));
-    k_scatter_small<<<gs, XG_SMALL_BLOCK, sms, ctx->stream>>>((int)P->ndof, P->adj_ptr, P->adj, bd, (const long long*)rowptr, colidx, vals);
+    k_scatter_small<<<gs, XG_SMALL_BLOCK, sms, ctx->stream>>>((int)P->ndof, P->adj_ptr, P->adj, bd, (const long long*)rowptr, colidx, vals,
+                                                              src_off, col_out);
     XGPU_LAUNCH_CHECK(ctx);
   }
   if (P->maxnr <= XG_SMALL_NR) return XGPU_OK;
   if (P->dups) {
     XGPU_CUDA(ctx, cudaFuncSetAttribute(k_scatter<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
     k_scatter<true><<<grid, nw * 32, sm, ctx->stream>>>((int)P->ndof, P->adj_ptr, P->adj, bd, RCAP, HS, SL, G, trips,
-                                                        (const long long*)rowptr, colidx, vals, XG_SMALL_NR);
+                                                        (const long long*)rowptr, colidx, vals, XG_SMALL_NR, src_off, col_out);
   } else {
     XGPU_CUDA(ctx, cudaFuncSetAttribute(k_scatter<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
     k_scatter<false><<<grid, nw * 32, sm, ctx->stream>>>((int)P->ndof, P->adj_ptr, P->adj, bd, RCAP, HS, SL, G, trips,
-                                                         (const long long*)rowptr, colidx, vals, XG_SMALL_NR);
+                                                         (const long long*)rowptr, colidx, vals, XG_SMALL_NR, src_off, col_out);
   }
   XGPU_LAUNCH_CHECK(ctx);
   return XGPU_OK;

@@ -106,26 +106,42 @@ class LocalPartition:
         return C, pos
 
 
-def _marked(pos_rows, n):
-    """flags over a candidate list: positions hit by the given (active) table rows"""
-    f = torch.zeros(n, dtype=torch.bool, device=pos_rows.device)
-    v = pos_rows.reshape(-1)
-    f[v[v >= 0]] = True
-    return f
+def _marked(pos, act, n):
+    """flags over a candidate list of length n: positions hit by the ACTIVE rows of the position table `pos`
+    (rows x width, -1 = not a candidate).  Mask arithmetic only: no data-dependent sizes, no host synchronisation."""
+    f = torch.zeros(n + 1, dtype=torch.bool, device=pos.device)
+    idx = torch.where(act.reshape(-1, 1) & (pos >= 0), pos, torch.full_like(pos, n))
+    f[idx.reshape(-1)] = True
+    return f[:n]
 
 
 class DistributedCutAssembly:
     def __init__(self, part, backend, rank, world, group=None):
         self.part, self.be, self.rank, self.world, self.group = part, backend, rank, world, group
+        dev = part.el_vtx.device
+        self._ne_own = torch.tensor([part.ne_own], dtype=torch.int64, device=dev)
 
-    # ---- communication primitives (P2P; lower rank sends first to avoid deadlock with blocking gloo)
-    def _exchange(self, q, send_t, recv_t):
-        if self.rank < q:
-            dist.send(send_t, q, group=self.group)
-            dist.recv(recv_t, q, group=self.group)
-        else:
-            dist.recv(recv_t, q, group=self.group)
-            dist.send(send_t, q, group=self.group)
+    # ---- communication primitives
+    def _exchange_all(self, msgs):
+        """msgs: [(q, send_tensor, recv_tensor)].  NCCL: one batched group of isend/irecv (all neighbours in
+        flight together, ordered on the current stream).  gloo (CPU tests): blocking pairs, lower rank sends first."""
+        if not msgs:
+            return
+        if dist.get_backend(self.group) == "nccl":
+            ops = []
+            for q, s_t, r_t in msgs:
+                ops.append(dist.P2POp(dist.isend, s_t, q, self.group))
+                ops.append(dist.P2POp(dist.irecv, r_t, q, self.group))
+            for w in dist.batch_isend_irecv(ops):
+                w.wait()
+            return
+        for q, s_t, r_t in msgs:
+            if self.rank < q:
+                dist.send(s_t, q, group=self.group)
+                dist.recv(r_t, q, group=self.group)
+            else:
+                dist.recv(r_t, q, group=self.group)
+                dist.send(s_t, q, group=self.group)
 
     def step(self, phi, timer=None):
         p, be, r = self.part, self.be, self.rank
@@ -135,18 +151,34 @@ class DistributedCutAssembly:
         # 1. classification of own + halo elements; own elements come first, lists are ascending
         l_neg, l_if, cls = be.classify(p.el_vtx, phi)
         mark("classify")
-        kn = int(torch.searchsorted(l_neg, p.ne_own).item())
-        ki = int(torch.searchsorted(l_if, p.ne_own).item())
-        l_neg_own, l_if_own = l_neg[:kn], l_if[:ki]
-        l_halo = torch.cat([l_neg[kn:], l_if[ki:]]).sort().values
         # 2./3. active dofs of own + halo elements; dof ids are already in (owner, gid) order
         dofmap, ndof = be.active_dofs(p, cls, l_neg, l_if)
+
+        def below(i):  # number of active dofs with local id < i (dofmap is the ascending compression, -1 = inactive)
+            if i <= 0:
+                return torch.zeros((), dtype=torch.int64, device=dev)
+            return (dofmap[:i].max().to(torch.int64) + 1).clamp(min=0)
+
+        ne_own = self._ne_own.to(l_neg.dtype)
+        sizes = [torch.searchsorted(l_neg, ne_own)[0].to(torch.int64), torch.searchsorted(l_if, ne_own)[0].to(torch.int64)]
         a, b = p.range_of[r]
-        n_lo = int((dofmap[:a] >= 0).sum().item())
-        n_own = int((dofmap[a:b] >= 0).sum().item())
+        sizes += [below(a), below(b)]
+        sizes = torch.stack(sizes).tolist()          # the ONE host synchronisation of this phase
+        kn, ki = sizes[0], sizes[1]
+        n_lo, n_own = sizes[2], sizes[3] - sizes[2]
+        l_neg_own, l_if_own = l_neg[:kn], l_if[:ki]
+        l_halo = torch.cat([l_neg[kn:], l_if[ki:]]).sort().values
         t_neg = be.gather_rows(p.el_dofs, l_neg_own, dofmap)
         t_if = be.gather_rows(p.el_dofs, l_if_own, dofmap)
         t_halo = be.gather_rows(p.el_dofs, l_halo, dofmap)
+        # activity of the static interface candidates (masks over the static lists: no compaction, no host sync)
+        m_snd, m_rcv, m_seen = {}, {}, {}
+        for q in p.neighbors:
+            it = p.iface[q]
+            actE, actH = be.element_activity(cls, it["E"]), be.element_activity(cls, it["H"])
+            m_snd[q] = _marked(it["pos_send"], actE, it["C_send"].numel())
+            m_rcv[q] = _marked(it["posH"], actH, it["D"].numel())
+            m_seen[q] = m_rcv[q] | _marked(it["posE"], actE, it["D"].numel())
         mark("restrict")
         # 4. element matrices of the own active elements
         m_neg, m_if = be.elmats(p, phi, l_neg_own, l_if_own)
@@ -155,46 +187,64 @@ class DistributedCutAssembly:
         batches = [(t_neg, m_neg), (t_if, m_if), (t_halo, None)]
         rowptr, col, vals = be.csr(ndof, [bt for bt in batches if bt[0].shape[0] > 0])
         mark("csr")
-        # 6. interface-row reduction (small static candidate tables, see LocalPartition)
-        el_act = torch.zeros(p.el_vtx.shape[0], dtype=torch.bool, device=dev)
-        el_act[l_neg.long()] = True
-        el_act[l_if.long()] = True
-        recvs, seen = [], {}
+        # 6. interface-row reduction: the values of the rows {owner == q, touched by my own elements} are packed and
+        #    sent, the owner adds what it receives in a fixed order (lower rank first)
+        pos = []
         for q in p.neighbors:
             it = p.iface[q]
-            actE, actH = el_act[it["E"]], el_act[it["H"]]
-            snd = it["C_send"][_marked(it["pos_send"][actE], it["C_send"].numel())]
-            fH = _marked(it["posH"][actH], it["D"].numel())
-            rcv = it["D"][fH]
-            seen[q] = it["D"][fH | _marked(it["posE"][actE], it["D"].numel())]
-            sidx, _ = row_positions(rowptr, dofmap[snd])
-            ridx, _ = row_positions(rowptr, dofmap[rcv])
-            sbuf = vals[sidx].contiguous()
-            rbuf = torch.empty(ridx.numel(), dtype=vals.dtype, device=dev)
-            self._exchange(q, sbuf, rbuf)
-            recvs.append((q, ridx, rbuf))
-        for q, ridx, rbuf in sorted(recvs, key=lambda t: t[0]):     # fixed order: lower rank first
-            vals[ridx] += rbuf
-        mark("merge")
-        # 7. global numbering: offset[owner] + index among the owner's active dofs (ascending key)
+            for cand, m in ((it["C_send"], m_snd[q]), (it["D"], m_rcv[q])):
+                rows = dofmap[cand].long()
+                live = m & (rows >= 0)
+                rows = rows.clamp(min=0)
+                start = rowptr[rows]
+                ln = torch.where(live, rowptr[rows + 1] - start, torch.zeros_like(start))
+                pos.append((start, ln))
+        tots = torch.stack([ln.sum() if ln.numel() else torch.zeros((), dtype=torch.int64, device=dev) for _, ln in pos]).tolist() \
+            if pos else []
+        idx = []
+        for (start, ln), tot in zip(pos, tots):
+            if tot == 0:
+                idx.append(torch.zeros(0, dtype=torch.int64, device=dev))
+            else:
+                idx.append(torch.repeat_interleave(start - _excl_cumsum(ln), ln, output_size=tot) + torch.arange(tot, device=dev))
+        # 7. global numbering = offset[owner] + index among the owner's active dofs (ascending key).  The owner-local
+        #    indices of the interface dofs travel in the SAME message round as the interface values: one STATIC-size
+        #    int message per neighbour over all interface candidates (-1 = inactive) — my candidate list D towards q
+        #    and q's ghost range of my dofs are the same dofs in the same key order (LocalPartition); the offsets come
+        #    from one all-reduce of the owned counts, issued first so that it overlaps the packing.
         counts = torch.zeros(self.world, dtype=torch.int64, device=dev)
         counts[r] = n_own
+        red = None
         if self.world > 1:
-            dist.all_reduce(counts, group=self.group)
-        offsets = _excl_cumsum(counts)
-        l2g = torch.full((ndof,), -1, dtype=torch.int64, device=dev)
-        l2g[n_lo:n_lo + n_own] = offsets[r] + torch.arange(n_own, device=dev)
-        for q in p.neighbors:
-            sbuf = l2g[dofmap[seen[q]].long()].contiguous()         # my owned dofs that q sees, key order
+            red = dist.all_reduce(counts, group=self.group, async_op=True)
+        msgs = []
+        for k, q in enumerate(p.neighbors):
+            sidx, ridx = idx[2 * k], idx[2 * k + 1]
+            msgs.append((q, vals[sidx].contiguous(), torch.empty(ridx.numel(), dtype=vals.dtype, device=dev)))
+            loc = dofmap[p.iface[q]["D"]].long()
             qa, qb = p.range_of[q]
-            ga = int((dofmap[:qa] >= 0).sum().item())
-            gn = int((dofmap[qa:qb] >= 0).sum().item())             # my ghosts owned by q: a contiguous range
-            rbuf = torch.empty(gn, dtype=torch.int64, device=dev)
-            self._exchange(q, sbuf, rbuf)
-            l2g[ga:ga + gn] = rbuf
+            msgs.append((q, torch.where(m_seen[q], loc - n_lo, torch.full_like(loc, -1)).contiguous(),
+                         torch.empty(qb - qa, dtype=torch.int64, device=dev)))
+        self._exchange_all(msgs)
+        for k, q in enumerate(p.neighbors):                               # neighbours ascending: lower rank first
+            vals[idx[2 * k + 1]] += msgs[2 * k][2]
+        mark("merge")
+        if red is not None:
+            red.wait()
+        offsets = _excl_cumsum(counts)
+        l2g = torch.full((ndof + 1,), -1, dtype=torch.int64, device=dev)   # slot ndof: sink of the inactive candidates
+        l2g[n_lo:n_lo + n_own] = offsets[r] + torch.arange(n_own, device=dev)
+        for k, q in enumerate(p.neighbors):
+            rbuf = msgs[2 * k + 1][2]
+            qa, qb = p.range_of[q]
+            loc = dofmap[qa:qb].long()                                     # my ghosts owned by q
+            l2g.scatter_(0, torch.where(loc >= 0, loc, torch.full_like(loc, ndof)),
+                         torch.where(rbuf >= 0, rbuf + offsets[q], rbuf))
+        l2g = l2g[:ndof]
+        ndof_global = counts.sum()
         mark("numbering")
         return dict(ndof_local=ndof, n_lo=n_lo, n_own=n_own, rowptr=rowptr, col=col, vals=vals, l2g=l2g, dofmap=dofmap,
-                    ndof_global=int(counts.sum().item()), units=int(l_neg_own.numel() + l_if_own.numel()),
+                    ndof_global=int(ndof_global.item()), units=int(l_neg_own.numel() + l_if_own.numel()),
                     n_neg=int(l_neg_own.numel()), n_if=int(l_if_own.numel()), nnz=int(col.numel()), cls=cls)
 
     @staticmethod
@@ -221,6 +271,13 @@ class GpuBackend:
         bn, bp, bi, cr = ops.classify(dim, el_vtx, phi, ctx=ctx)
         ctx.raise_on_geometry_error()
         return ops.bitset_to_list(bn, ne, ctx=ctx), ops.bitset_to_list(bi, ne, ctx=ctx), (bn, bp, bi, cr)
+
+    def element_activity(self, cls, elems):
+        """bool per listed element: HASNEG bit (NEG | IF) looked up in the BitArray words"""
+        bn, bp, bi, cr = cls
+        e = elems.long()
+        w = (bn | bi)[e >> 5]
+        return ((w >> (e & 31).to(torch.int32)) & 1).bool()
 
     def active_dofs(self, part, cls, l_neg, l_if):
         ops, ctx = self.ops, self.ctx
@@ -250,9 +307,7 @@ class GpuBackend:
         ops = self.ops
         tables = [b[0] for b in batches]
         plan = ops.csr_plan(ndof, tables, ctx=self.ctx)
-        rowptr, col = ops.csr_pattern(plan, tables[0].device)
-        vals = ops.csr_scatter(plan, batches, rowptr, col)
-        return rowptr, col, vals
+        return ops.csr_assemble(plan, batches)
 
 
 # ------------------------------------------------------------------ slab partition of the structured chain (input producer)

@@ -555,8 +555,7 @@ class BilinearForm:
                     mats.append(None)  # sparsity only
 
         plan = ops.csr_plan(sp.ndof, tables, ctx=ctx)
-        rowptr, col = ops.csr_pattern(plan, dev)
-        vals = ops.csr_scatter(plan, list(zip(tables, mats)), rowptr, col)
+        rowptr, col, vals = ops.csr_assemble(plan, list(zip(tables, mats)))
         self.mat = SparseMatrixCSR(sp.ndof, rowptr, col, vals)
         return self
 

@@ -399,6 +399,17 @@ def csr_scatter(plan, batches, rowptr, col, vals=None):
     return vals
 
 
+def csr_assemble(plan, batches):
+    """pattern + values in one pass (xgpu_csr_assemble): returns rowptr, col, vals"""
+    dev = batches[0][0].device
+    rowptr = torch.empty(plan.ndof + 1, dtype=torch.int64, device=dev)
+    col = torch.empty(plan.nnz, dtype=torch.int32, device=dev)
+    vals = torch.empty(plan.nnz, dtype=torch.float64, device=dev)
+    arr = _batches(batches)
+    plan.ctx.check(plan.ctx.lib.xgpu_csr_assemble(plan.ctx.h, plan.h, arr, len(batches), ptr(rowptr), ptr(col), ptr(vals)))
+    return rowptr, col, vals
+
+
 def csr_spmv(rowptr, col, vals, x, ctx=None):
     ctx = ctx or default_ctx()
     y = torch.empty(rowptr.numel() - 1, dtype=torch.float64, device=x.device)

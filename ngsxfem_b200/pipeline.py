@@ -136,16 +136,15 @@ class CutAssembly:
         if t.enabled:
             a_ms, p_ms = plan.phase_ms()
             t.split_phase("csr_plan", {"csr_adjacency": a_ms, "csr_pattern_pass": p_ms})
-        rowptr, col = ops.csr_pattern(plan, self.dev)
-        t.mark("csr_pattern")
-        if "pattern" in hooks:
-            hooks["pattern"](dict(rowptr=rowptr, col=col))
         if concurrent:
             main.wait_stream(side)
         ctx2.raise_on_geometry_error()
         t.mark("elmat_join")
-        vals = ops.csr_scatter(plan, [(t_neg, m_neg), (t_if, m_if)], rowptr, col)
+        # pattern compaction fused into the scatter (xgpu_csr_assemble): rowptr, colidx and vals in one pass
+        rowptr, col, vals = ops.csr_assemble(plan, [(t_neg, m_neg), (t_if, m_if)])
         t.mark("csr_scatter")
+        if "pattern" in hooks:
+            hooks["pattern"](dict(rowptr=rowptr, col=col))
         if "values" in hooks:
             hooks["values"](dict(vals=vals))
         out = dict(ndof=ndof, nnz=plan.nnz, n_neg=l_neg.numel(), n_if=l_if.numel(),

@@ -15,6 +15,11 @@ class OracleBackend:
         assert err == 0
         return torch.from_numpy(bits_to_list(bn, ne)), torch.from_numpy(bits_to_list(bi, ne)), (bn, bp, bi, cr)
 
+    def element_activity(self, cls, elems):
+        bn, bp, bi, cr = cls
+        bits = np.unpackbits(np.asarray(bn, np.uint8) | np.asarray(bi, np.uint8), bitorder="little")
+        return torch.from_numpy(bits[elems.numpy()].astype(bool))
+
     def active_dofs(self, part, cls, l_neg, l_if):
         act = torch.zeros(part.ndof_loc, dtype=torch.bool)
         act[part.el_dofs[torch.cat([l_neg, l_if]).long()].reshape(-1).long()] = True

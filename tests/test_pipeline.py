@@ -46,6 +46,24 @@ def test_sphere_cut_assembly_matches_oracle(n, p, center, radius):
     assert torch.equal(r["vals"], r2["vals"]) and torch.equal(r["col"], r2["col"])
 
 
+def test_fused_assemble_equals_pattern_plus_scatter():
+    """xgpu_csr_assemble (compaction fused into the scatter) against xgpu_csr_pattern + xgpu_csr_scatter: bit identical"""
+    mesh = xf.MakeStructured3DMesh(nx=8, device=DEV)
+    V0 = xf.H1(mesh, order=2)
+    phi = sphere_levelset(mesh.points, [(.5, .5, .5)], 0.4)
+    r = CutAssembly(3, mesh.elements, mesh.points, V0.el_dofs, V0.ndof, 2).step(phi, keep=True)
+    batches = [(r["t_neg"], r["m_neg"]), (r["t_if"], r["m_if"])]
+    plan = ops.csr_plan(r["ndof"], [b[0] for b in batches])
+    rowptr, col = ops.csr_pattern(plan, mesh.device)
+    vals = ops.csr_scatter(plan, batches, rowptr, col)
+    assert torch.equal(rowptr, r["rowptr"]) and torch.equal(col, r["col"]) and torch.equal(vals, r["vals"])
+    # a second plan takes over the shared pattern scratch: the first one must redo its pass transparently
+    plan2 = ops.csr_plan(r["ndof"], [batches[0][0]])
+    rp2, c2, v2 = ops.csr_assemble(plan, batches)
+    assert torch.equal(rp2, rowptr) and torch.equal(c2, col) and torch.equal(v2, vals)
+    del plan2
+
+
 def test_host_buffer_path_matches_device_path():
     mesh = xf.MakeStructured3DMesh(nx=7, device=DEV)
     V0 = xf.H1(mesh, order=2)
