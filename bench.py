@@ -245,6 +245,12 @@ def run_gpu(args):
     for t in timers:
         for k, v in t.result().items():
             phases[k] = phases.get(k, 0.0) + v / steps
+    phases_max = None
+    if world > 1:  # the slowest rank per phase (interior ranks of the chain have two neighbours)
+        keys = sorted(phases)
+        pv = torch.tensor([phases[k] for k in keys], device=dev, dtype=torch.float64)
+        dist.all_reduce(pv, op=dist.ReduceOp.MAX)
+        phases_max = {k: round(float(v), 4) for k, v in zip(keys, pv.tolist())}
     if "npts" not in res:
         res["npts"] = (0, 0)
         res["ndof"] = res["ndof_local"]
@@ -300,7 +306,8 @@ def run_gpu(args):
                        "units_per_step_per_gpu": units, "n_neg": res["n_neg"], "n_if": res["n_if"],
                        "ndof": res["ndof"], "nnz": res["nnz"], "cut_points": list(res["npts"]),
                        "l2_policy": "inputs+outputs of a step (>5 GB) exceed the 126 MB L2; no flush needed",
-                       "phases_ms": {k: round(v, 4) for k, v in phases.items()}},
+                       "phases_ms": {k: round(v, 4) for k, v in phases.items()},
+                       **({"phases_ms_max_over_ranks": phases_max} if phases_max else {})},
             "e2e": {"value": tot_units * e2e_steps / (ms_e2e * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e / e2e_steps,
                     "steps": e2e_steps, "h2d_bytes_per_step": info["h2d"], "d2h_bytes_per_step": info["d2h"]},
             "gpu_launches": int(launches),

@@ -77,17 +77,13 @@ __device__ __forceinline__ void trafo_eval(const double (*vx)[3], const double* 
 // (xf, wf) on the `from` element -> xt, wt on the `to` element; affine start value, Newton with the
 // reference's constants (ngsxstd.cpp:66-82: eps 1e-12, 15 iterations, max distance 10), low-order
 // guess kept on failure.
+// the point independent part of the mapping INTO element t: the affine start value uses the images of the
+// reference vertices (out: pc[0..2] = a0, pc[3..3+D*D) = A^{-1}, pc[12] = |det A|)
 template <int D>
-__device__ __forceinline__ void map_patch_def(const double (*vxf)[3], const double* Ff, const int* vf, const double* defs_f,
-                                              const double (*vxt)[3], const double* Ft, const int* vt, const double* defs_t,
-                                              int def_order, const double* xf, double wf, double* xt, double* wt)
+__device__ __forceinline__ void patch_consts(const double (*vxt)[3], const double* Ft, const int* vt, const double* defs_t,
+                                             int def_order, double* pc)
 {
-  double F[D * D], Fi[D * D], vec[3] = {0, 0, 0};
-  trafo_eval<D>(vxf, Ff, vf, def_order, defs_f, xf, F, vec);
-  const double detf = xg_inv<D>(F, Fi);
-  const double h = sqrt(detf);
-  const double mipw = wf * fabs(detf);
-  double a0[3] = {0, 0, 0}, A[D * D], Ainv[D * D], x00[3] = {0, 0, 0}, x0[3] = {0, 0, 0};
+  double F[D * D], a0[3] = {0, 0, 0}, A[D * D], Ainv[D * D];
   const double zero[3] = {0, 0, 0};
   trafo_eval<D>(vxt, Ft, vt, def_order, defs_t, zero, F, a0);
 #pragma unroll
@@ -99,6 +95,26 @@ __device__ __forceinline__ void map_patch_def(const double (*vxf)[3], const doub
     for (int i = 0; i < D; i++) A[i * D + d] = ai[i] - a0[i];
   }
   const double w00 = fabs(xg_inv<D>(A, Ainv));
+  pc[0] = a0[0]; pc[1] = a0[1]; pc[2] = a0[2];
+#pragma unroll
+  for (int k = 0; k < D * D; k++) pc[3 + k] = Ainv[k];
+  pc[12] = w00;
+}
+
+template <int D>
+__device__ __forceinline__ void map_patch_def(const double (*vxf)[3], const double* Ff, const int* vf, const double* defs_f,
+                                              const double (*vxt)[3], const double* Ft, const int* vt, const double* defs_t,
+                                              int def_order, const double* pc, const double* xf, double wf, double* xt, double* wt)
+{
+  double F[D * D], Fi[D * D], vec[3] = {0, 0, 0};
+  trafo_eval<D>(vxf, Ff, vf, def_order, defs_f, xf, F, vec);
+  const double detf = xg_inv<D>(F, Fi);
+  const double h = sqrt(detf);
+  const double mipw = wf * fabs(detf);
+  double a0[3] = {pc[0], pc[1], pc[2]}, Ainv[D * D], x00[3] = {0, 0, 0}, x0[3] = {0, 0, 0};
+#pragma unroll
+  for (int k = 0; k < D * D; k++) Ainv[k] = pc[3 + k];
+  const double w00 = pc[12];
 #pragma unroll
   for (int i = 0; i < D; i++) {
     double t = 0.0;
@@ -150,9 +166,12 @@ __global__ void __launch_bounds__(128) k_facetpatch(
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const int N = 2 * nd, Np = (N + 1) & ~1, nbk = Np >> 1, nblocks = nbk * nbk;
   const int PS = Np + 1;
-  double* Bw = smem + (size_t)wib * (CH * PS + (DEF ? 2 * XG_DEFS : 0));
+  const int npatch_ = 2 * np;
+  double* Bw = smem + (size_t)wib * (CH * PS + (DEF ? 2 * XG_DEFS + 32 + 7 * npatch_ : 0));
   double* defs1 = Bw + (size_t)CH * PS;
   double* defs2 = defs1 + XG_DEFS;
+  double* pcs = defs2 + XG_DEFS;   // mapping constants: [0..15] into element 2, [16..31] into element 1
+  double* mp = pcs + 32;           // mapped patch points: x1[3], x2[3], weight  (DEF: computed ONCE per facet)
   const int64_t warp0 = (int64_t)blockIdx.x * (blockDim.x >> 5) + wib;
   const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
   const int npatch = 2 * np;
@@ -173,6 +192,32 @@ __global__ void __launch_bounds__(128) k_facetpatch(
       xg_def_gather<D>(df, e1, lane, defs1);
       xg_def_gather<D>(df, e2, lane, defs2);
       __syncwarp();
+      if (lane == 0) patch_consts<D>(vx2, F2, v2, defs2, df.order, pcs);
+      if (lane == 1) patch_consts<D>(vx1, F1, v1, defs1, df.order, pcs + 16);
+      __syncwarp();
+      // Newton mapping of every patch point, all lanes busy, once per facet (not once per accumulator panel)
+      for (int l = lane; l < 2 * np; l += 32) {
+        double x1[3], x2[3], x[3], w1, wd;
+        if (l < np) {
+          x1[0] = rp[3 * l]; x1[1] = rp[3 * l + 1]; x1[2] = rp[3 * l + 2];
+          w1 = rw[l];
+          map_patch_def<D>(vx1, F1, v1, defs1, vx2, F2, v2, defs2, df.order, pcs, x1, w1, x2, &wd);
+        } else {
+          const int q = l - np;
+          x2[0] = rp[3 * q]; x2[1] = rp[3 * q + 1]; x2[2] = rp[3 * q + 2];
+          map_patch_def<D>(vx2, F2, v2, defs2, vx1, F1, v1, defs1, df.order, pcs + 16, x2, rw[q], x1, &w1);
+        }
+        double Fq[D * D], Fiq[D * D];
+        trafo_eval<D>(vx1, F1, v1, df.order, defs1, x1, Fq, x);
+        const double measq = fabs(xg_inv<D>(Fq, Fiq));
+        const double hq = xg_mesh_size<D>(measq);
+        double hpq = 1.0;
+        { const int ap = hpow < 0 ? -hpow : hpow; for (int i = 0; i < ap; i++) hpq *= hq; if (hpow < 0) hpq = 1.0 / hpq; }
+        double* m = mp + 7 * l;
+        m[0] = x1[0]; m[1] = x1[1]; m[2] = x1[2]; m[3] = x2[0]; m[4] = x2[1]; m[5] = x2[2];
+        m[6] = coef * hpq * (w1 * measq);
+      }
+      __syncwarp();
     }
     const double h = (D == 1) ? meas1 : ((D == 2) ? sqrt(meas1) : cbrt(meas1));
     double hp = 1.0;
@@ -190,24 +235,9 @@ __global__ void __launch_bounds__(128) k_facetpatch(
           double x1[3], x2[3], x[3], w;
           double cwq = coef * hp;
           if (DEF) {
-            double w1, wd;
-            if (l < np) {
-              x1[0] = rp[3 * l]; x1[1] = rp[3 * l + 1]; x1[2] = rp[3 * l + 2];
-              w1 = rw[l];
-              map_patch_def<D>(vx1, F1, v1, defs1, vx2, F2, v2, defs2, df.order, x1, w1, x2, &wd);
-            } else {
-              const int q = l - np;
-              x2[0] = rp[3 * q]; x2[1] = rp[3 * q + 1]; x2[2] = rp[3 * q + 2];
-              map_patch_def<D>(vx2, F2, v2, defs2, vx1, F1, v1, defs1, df.order, x2, rw[q], x1, &w1);
-            }
-            double Fq[D * D], Fiq[D * D];
-            trafo_eval<D>(vx1, F1, v1, df.order, defs1, x1, Fq, x);
-            const double measq = fabs(xg_inv<D>(Fq, Fiq));
-            const double hq = xg_mesh_size<D>(measq);
-            double hpq = 1.0;
-            { const int ap = hpow < 0 ? -hpow : hpow; for (int i = 0; i < ap; i++) hpq *= hq; if (hpow < 0) hpq = 1.0 / hpq; }
-            w = w1 * measq;
-            cwq = coef * hpq;
+            const double* m = mp + 7 * l;
+            x1[0] = m[0]; x1[1] = m[1]; x1[2] = m[2]; x2[0] = m[3]; x2[1] = m[4]; x2[2] = m[5];
+            w = m[6]; cwq = 1.0;
           } else if (l < np) {
             x1[0] = rp[3 * l]; x1[1] = rp[3 * l + 1]; x1[2] = rp[3 * l + 2];
             map_fwd<D>(vx1, x1, x);
@@ -273,11 +303,13 @@ extern "C" int xgpu_facetpatch(xgpu_ctx* ctx, int dim, int fe_order, int64_t n, 
   if (!r) return xgpu_fail(ctx, XGPU_ERR_ARG, "xgpu_facetpatch: no rule");
   const int nd = xg_h1_ndof(dim, fe_order);
   const int Np = (2 * nd + 1) & ~1, PS = Np + 1;
-  int CH = 32;
-  while (CH > 4 && (size_t)4 * CH * PS * sizeof(double) > 56 * 1024) CH >>= 1;
   const DefDev df = xg_defdev(ctx, dim);
   if (df.order > 0 && dim < 2) return xgpu_fail(ctx, XGPU_ERR_UNSUPPORTED, "xgpu_facetpatch: deformation needs dim >= 2");
-  const size_t sm = (size_t)4 * (CH * PS + (df.order > 0 ? 2 * XG_DEFS : 0)) * sizeof(double);
+  const size_t extra = df.order > 0 ? (size_t)(2 * XG_DEFS + 32 + 7 * 2 * r->n) : 0;  // doubles per warp
+  int CH = 32;  // staged points per pass: the kernels are register limited to 2 blocks / SM, so up to ~100 KB per block is free
+  while (CH > 4 && (size_t)4 * (CH * PS + extra) * sizeof(double) > 100 * 1024) CH >>= 1;
+  const size_t sm = (size_t)4 * (CH * PS + extra) * sizeof(double);
+  if (sm > 220 * 1024) return xgpu_fail(ctx, XGPU_ERR_CAPACITY, "xgpu_facetpatch: patch rule too large for the shared-memory staging");
   unsigned grid = nblk(n, 4);
   if (grid > XGPU_NSM * 8) grid = XGPU_NSM * 8;
 #define XG_FP(DD, DF)                                                                                               \

@@ -90,10 +90,11 @@ class LocalPartition:
             TE, TH = self.el_dofs[E].long(), self.el_dofs[H].long()
             ent = {"E": E, "H": H}
             # candidate rows I send to q: dofs owned by q among the dofs of my elements E
-            ent["C_send"], ent["pos_send"] = self._candidates(TE, ow, q)
+            ent["C_send"], pos = self._candidates(TE, ow, q)
+            ent["pos_send"] = _compact_pos(pos)
             # candidate dofs owned by me that q can see / contribute to
             D, pos = self._candidates(torch.cat([TE, TH]), ow, rank)
-            ent["D"], ent["posE"], ent["posH"] = D, pos[:TE.shape[0]], pos[TE.shape[0]:]
+            ent["D"], ent["posE"], ent["posH"] = D, _compact_pos(pos[:TE.shape[0]]), _compact_pos(pos[TE.shape[0]:])
             self.iface[q] = ent
 
     @staticmethod
@@ -106,12 +107,18 @@ class LocalPartition:
         return C, pos
 
 
-def _marked(pos, act, n):
-    """flags over a candidate list of length n: positions hit by the ACTIVE rows of the position table `pos`
-    (rows x width, -1 = not a candidate).  Mask arithmetic only: no data-dependent sizes, no host synchronisation."""
-    f = torch.zeros(n + 1, dtype=torch.bool, device=pos.device)
-    idx = torch.where(act.reshape(-1, 1) & (pos >= 0), pos, torch.full_like(pos, n))
-    f[idx.reshape(-1)] = True
+def _compact_pos(pos):
+    """static (row, candidate position) pairs of a position table (rows x width, -1 = not a candidate)"""
+    r, c = torch.nonzero(pos >= 0, as_tuple=True)
+    return r.contiguous(), pos[r, c].contiguous()
+
+
+def _marked(rp, act, n):
+    """flags over a candidate list of length n: positions hit by the ACTIVE rows; rp = _compact_pos(table).
+    Mask arithmetic over the static pair list only: no data-dependent sizes, no host synchronisation."""
+    rows, posv = rp
+    f = torch.zeros(n + 1, dtype=torch.bool, device=posv.device)
+    f[torch.where(act[rows], posv, torch.full_like(posv, n))] = True
     return f[:n]
 
 
@@ -166,11 +173,13 @@ class DistributedCutAssembly:
         sizes = torch.stack(sizes).tolist()          # the ONE host synchronisation of this phase
         kn, ki = sizes[0], sizes[1]
         n_lo, n_own = sizes[2], sizes[3] - sizes[2]
+        mark("restrict_sizes")
         l_neg_own, l_if_own = l_neg[:kn], l_if[:ki]
         l_halo = torch.cat([l_neg[kn:], l_if[ki:]]).sort().values
         t_neg = be.gather_rows(p.el_dofs, l_neg_own, dofmap)
         t_if = be.gather_rows(p.el_dofs, l_if_own, dofmap)
         t_halo = be.gather_rows(p.el_dofs, l_halo, dofmap)
+        mark("restrict_rows")
         # activity of the static interface candidates (masks over the static lists: no compaction, no host sync)
         m_snd, m_rcv, m_seen = {}, {}, {}
         for q in p.neighbors:
@@ -199,6 +208,7 @@ class DistributedCutAssembly:
                 start = rowptr[rows]
                 ln = torch.where(live, rowptr[rows + 1] - start, torch.zeros_like(start))
                 pos.append((start, ln))
+        mark("merge_rows")
         tots = torch.stack([ln.sum() if ln.numel() else torch.zeros((), dtype=torch.int64, device=dev) for _, ln in pos]).tolist() \
             if pos else []
         idx = []
@@ -225,7 +235,9 @@ class DistributedCutAssembly:
             qa, qb = p.range_of[q]
             msgs.append((q, torch.where(m_seen[q], loc - n_lo, torch.full_like(loc, -1)).contiguous(),
                          torch.empty(qb - qa, dtype=torch.int64, device=dev)))
+        mark("merge_pack")
         self._exchange_all(msgs)
+        mark("merge_exchange")
         for k, q in enumerate(p.neighbors):                               # neighbours ascending: lower rank first
             vals[idx[2 * k + 1]] += msgs[2 * k][2]
         mark("merge")
@@ -253,7 +265,10 @@ class DistributedCutAssembly:
         a, b = res["n_lo"], res["n_lo"] + res["n_own"]
         rp = res["rowptr"]
         lo, hi = int(rp[a].item()), int(rp[b].item())
-        return res["l2g"][a:b], rp[a:b + 1] - lo, res["l2g"][res["col"][lo:hi].long()], res["vals"][lo:hi]
+        cols = res["l2g"][res["col"][lo:hi].long()]
+        if res["ndof_global"] < 2 ** 31:   # same index width as the single-GPU CSR
+            cols = cols.to(torch.int32)
+        return res["l2g"][a:b], rp[a:b + 1] - lo, cols, res["vals"][lo:hi]
 
 
 # ------------------------------------------------------------------ CUDA compute backend
