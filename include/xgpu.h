@@ -164,6 +164,16 @@ int xgpu_elmat_rule(xgpu_ctx* ctx, int dim, int fe_order, int64_t n, const int32
                     const int64_t* offsets, const double* pts, const double* wts,
                     const xgpu_term* terms_host, int nterms, int accumulate, const int32_t* slots,
                     double* mats);
+/* two integrators over the same element list in ONE pass — NGSolve's element loop calls CalcElementMatrixAdd of every
+ * integrator on an element before it moves on (e.g. the NEG volume terms and the IF interface term of a CutFEM form
+ * on the cut elements): rule A with terms A, then rule B with terms B, one matrix per element. */
+int xgpu_elmat_rule_pair(xgpu_ctx* ctx, int dim, int fe_order, int64_t n, const int32_t* elems,
+                         const int32_t* el_vtx, const double* vtx_xyz, const double* phi,
+                         const int64_t* offsets_a, const double* pts_a, const double* wts_a,
+                         const xgpu_term* terms_a_host, int nterms_a,
+                         const int64_t* offsets_b, const double* pts_b, const double* wts_b,
+                         const xgpu_term* terms_b_host, int nterms_b,
+                         int accumulate, const int32_t* slots, double* mats);
 /* uncut elements: the shared standard rule of `order` on every listed element */
 int xgpu_elmat_std(xgpu_ctx* ctx, int dim, int fe_order, int64_t n, const int32_t* elems,
                    const int32_t* el_vtx, const double* vtx_xyz, const double* phi, int order,

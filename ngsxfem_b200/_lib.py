@@ -76,6 +76,8 @@ _SIGS = {
     "xgpu_integrate_monomial": (C.c_int, [VP, C.c_int, C.c_int64, VP, VP, VP, VP, VP, VP, c_intp, c_f64p]),
     "xgpu_elmat_rule": (C.c_int, [VP, C.c_int, C.c_int, C.c_int64, VP, VP, VP, VP, VP, VP, VP, C.POINTER(Term),
                                   C.c_int, C.c_int, VP, VP]),
+    "xgpu_elmat_rule_pair": (C.c_int, [VP, C.c_int, C.c_int, C.c_int64, VP, VP, VP, VP, VP, VP, VP, C.POINTER(Term), C.c_int,
+                                       VP, VP, VP, C.POINTER(Term), C.c_int, C.c_int, VP, VP]),
     "xgpu_elmat_std": (C.c_int, [VP, C.c_int, C.c_int, C.c_int64, VP, VP, VP, VP, C.c_int, C.POINTER(Term),
                                  C.c_int, C.c_int, VP, VP]),
     "xgpu_elvec_rule": (C.c_int, [VP, C.c_int, C.c_int, C.c_int64, VP, VP, VP, VP, VP, VP, VP, C.POINTER(LTerm),

@@ -208,23 +208,48 @@ struct StageSinkMS {
   }
 };
 
+// optional second integrator of the same pass (xgpu_elmat_rule_pair): its own per-element rule and term weights
+struct Rule2 {
+  const int64_t* offsets;  // nullptr: absent
+  const double* pts;
+  const double* wts;
+  TermsDev T;
+};
+
+// Work split: the matrices of these forms are symmetric, so only the 2x2 blocks (bi <= bj) are computed — NSYM =
+// NBK(NBK+1)/2 of them (15 for P2 tets) — by the 16 lanes of a half warp; the two half warps take the even / odd
+// staged points of every chunk and are summed (fixed order) at the end, half 0 then stores the upper blocks, half 1
+// the mirrored ones.  Two integrators (NEG volume terms + IF interface term of CutFEM forms) run in one pass.
 template <int D, int P, bool DEF>
 __global__ void __launch_bounds__(128) k_elmat_ms(
     int64_t n, const int32_t* __restrict__ elems, const int32_t* __restrict__ el_vtx,
     const double* __restrict__ vtx_xyz, const int64_t* __restrict__ offsets, const double* __restrict__ pts,
     const double* __restrict__ wts, int np_shared, int CH, TermsDev T, int accumulate,
-    const int32_t* __restrict__ slots, double* __restrict__ mats, DefDev df)
+    const int32_t* __restrict__ slots, double* __restrict__ mats, DefDev df, Rule2 R2)
 {
   constexpr int ND = (D == 1) ? P + 1 : ((D == 2) ? 3 + 3 * (P - 1) + (P - 1) * (P - 2) / 2
                                                    : 4 + 6 * (P - 1) + 4 * ((P - 1) * (P - 2) / 2) + (P - 1) * (P - 2) * (P - 3) / 6);
-  constexpr int NDP = (ND + 1) & ~1, NBK = NDP / 2, NBLK = NBK * NBK, MAXB = (NBLK + 31) / 32;
+  constexpr int NDP = (ND + 1) & ~1, NBK = NDP / 2, NSYM = NBK * (NBK + 1) / 2, MAXS = (NSYM + 15) / 16;
   constexpr int PS = NDP * (1 + D) + 2;  // per point: val, D physical gradients, (mass, stiffness) weights
   extern __shared__ double smem[];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const int half = lane >> 4, hl = lane & 15;
   double* Bw = smem + (size_t)wib * (CH * PS + (DEF ? XG_DEFS : 0));
   double* defs = Bw + (size_t)CH * PS;
+  int bi_[MAXS], bj_[MAXS];  // the blocks of this lane (bi = -1: none)
+#pragma unroll
+  for (int b = 0; b < MAXS; b++) {
+    const int blk = hl + 16 * b;
+    bi_[b] = -1; bj_[b] = 0;
+    if (blk < NSYM) {
+      int r = 0, rem = blk;
+      while (rem >= NBK - r) { rem -= NBK - r; r++; }
+      bi_[b] = r; bj_[b] = r + rem;
+    }
+  }
   const int64_t warp0 = (int64_t)blockIdx.x * (blockDim.x >> 5) + wib;
   const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
+  const int nseg = R2.offsets ? 2 : 1;
   for (int64_t e = warp0; e < n; e += nwarps) {
     const int64_t el = elems ? (int64_t)elems[e] : e;
     int v[D + 1];
@@ -237,81 +262,90 @@ __global__ void __launch_bounds__(128) k_elmat_ms(
     }
     xg_affine_jac<D>(vx, F);
     const double meas = fabs(xg_inv<D>(F, Fi));
-    double cm, cs;
-    ms_coefs(T, xg_mesh_size<D>(meas), meas, cm, cs);
     if (DEF) { __syncwarp(); xg_def_gather<D>(df, el, lane, defs); __syncwarp(); }
-    const int64_t q0 = offsets ? offsets[e] : 0;
-    const int npe = offsets ? (int)(offsets[e + 1] - q0) : np_shared;
-    double acc[MAXB][4];
+    double acc[MAXS][4];
 #pragma unroll
-    for (int b = 0; b < MAXB; b++) { acc[b][0] = acc[b][1] = acc[b][2] = acc[b][3] = 0.0; }
-    for (int c0 = 0; c0 < npe; c0 += CH) {
-      const int cnt = min(CH, npe - c0);
-      __syncwarp();
-      for (int ql = lane; ql < cnt; ql += 32) {
-        double* B = Bw + (size_t)ql * PS;
-        const double* xq = pts + 3 * (q0 + c0 + ql);
-        double xh[3] = {xq[0], xq[1], xq[2]};
-        if (ND < NDP) {
+    for (int b = 0; b < MAXS; b++) { acc[b][0] = acc[b][1] = acc[b][2] = acc[b][3] = 0.0; }
+    for (int seg = 0; seg < nseg; seg++) {
+      const TermsDev* Ts = seg ? &R2.T : &T;
+      const int64_t* off_s = seg ? R2.offsets : offsets;
+      const double* pts_s = seg ? R2.pts : pts;
+      const double* wts_s = seg ? R2.wts : wts;
+      double cm, cs;
+      ms_coefs(*Ts, xg_mesh_size<D>(meas), meas, cm, cs);
+      const int64_t q0 = off_s ? off_s[e] : 0;
+      const int npe = off_s ? (int)(off_s[e + 1] - q0) : np_shared;
+      for (int c0 = 0; c0 < npe; c0 += CH) {
+        const int cnt = min(CH, npe - c0);
+        __syncwarp();
+        for (int ql = lane; ql < cnt; ql += 32) {
+          double* B = Bw + (size_t)ql * PS;
+          const double* xq = pts_s + 3 * (q0 + c0 + ql);
+          double xh[3] = {xq[0], xq[1], xq[2]};
+          if (ND < NDP) {
 #pragma unroll
-          for (int k = 0; k < 1 + D; k++) B[k * NDP + ND] = 0.0;
+            for (int k = 0; k < 1 + D; k++) B[k * NDP + ND] = 0.0;
+          }
+          double Fiq[D * D], cmq = cm, csq = cs;
+          if (DEF) {
+            double Fq[D * D], xd[3] = {0, 0, 0};
+#pragma unroll
+            for (int k = 0; k < D * D; k++) Fq[k] = F[k];
+            xg_def_apply<D>(df.order, v, xh, defs, Fq, xd);
+            const double measq = fabs(xg_inv<D>(Fq, Fiq));
+            ms_coefs(*Ts, xg_mesh_size<D>(measq), measq, cmq, csq);
+          }
+          StageSinkMS<D> sink{B, NDP, DEF ? Fiq : Fi};
+          xg_h1_shapes<D, P>(v, xh, sink);
+          const double w = wts_s[q0 + c0 + ql];
+          B[NDP * (1 + D)] = cmq * w;
+          B[NDP * (1 + D) + 1] = csq * w;
         }
-        double Fiq[D * D], cmq = cm, csq = cs;
-        if (DEF) {
-          double Fq[D * D], xd[3] = {0, 0, 0};
+        __syncwarp();
 #pragma unroll
-          for (int k = 0; k < D * D; k++) Fq[k] = F[k];
-          xg_def_apply<D>(df.order, v, xh, defs, Fq, xd);
-          const double measq = fabs(xg_inv<D>(Fq, Fiq));
-          ms_coefs(T, xg_mesh_size<D>(measq), measq, cmq, csq);
-        }
-        StageSinkMS<D> sink{B, NDP, DEF ? Fiq : Fi};
-        xg_h1_shapes<D, P>(v, xh, sink);
-        const double w = wts[q0 + c0 + ql];
-        B[NDP * (1 + D)] = cmq * w;
-        B[NDP * (1 + D) + 1] = csq * w;
-      }
-      __syncwarp();
+        for (int b = 0; b < MAXS; b++) {
+          if (bi_[b] >= 0) {
+            const int i0 = 2 * bi_[b], j0 = 2 * bj_[b];
+            for (int q = half; q < cnt; q += 2) {
+              const double* B = Bw + (size_t)q * PS;
+              const double2 wq = *reinterpret_cast<const double2*>(B + NDP * (1 + D));
+              double s00 = 0, s01 = 0, s10 = 0, s11 = 0;
 #pragma unroll
-      for (int b = 0; b < MAXB; b++) {
-        const int blk = lane + 32 * b;
-        if (blk < NBLK) {
-          const int i0 = 2 * (blk / NBK), j0 = 2 * (blk % NBK);
-          for (int q = 0; q < cnt; q++) {
-            const double* B = Bw + (size_t)q * PS;
-            const double2 wq = *reinterpret_cast<const double2*>(B + NDP * (1 + D));
-            double s00 = 0, s01 = 0, s10 = 0, s11 = 0;
-#pragma unroll
-            for (int c = 0; c < D; c++) {
-              const double2 a = *reinterpret_cast<const double2*>(B + (1 + c) * NDP + i0);
-              const double2 bb = *reinterpret_cast<const double2*>(B + (1 + c) * NDP + j0);
-              s00 += a.x * bb.x; s01 += a.x * bb.y; s10 += a.y * bb.x; s11 += a.y * bb.y;
+              for (int c = 0; c < D; c++) {
+                const double2 a = *reinterpret_cast<const double2*>(B + (1 + c) * NDP + i0);
+                const double2 bb = *reinterpret_cast<const double2*>(B + (1 + c) * NDP + j0);
+                s00 += a.x * bb.x; s01 += a.x * bb.y; s10 += a.y * bb.x; s11 += a.y * bb.y;
+              }
+              const double2 a = *reinterpret_cast<const double2*>(B + i0);
+              const double2 bb = *reinterpret_cast<const double2*>(B + j0);
+              const double m0 = wq.x * a.x, m1 = wq.x * a.y;
+              acc[b][0] += wq.y * s00 + m0 * bb.x; acc[b][1] += wq.y * s01 + m0 * bb.y;
+              acc[b][2] += wq.y * s10 + m1 * bb.x; acc[b][3] += wq.y * s11 + m1 * bb.y;
             }
-            const double2 a = *reinterpret_cast<const double2*>(B + i0);
-            const double2 bb = *reinterpret_cast<const double2*>(B + j0);
-            const double m0 = wq.x * a.x, m1 = wq.x * a.y;
-            acc[b][0] += wq.y * s00 + m0 * bb.x; acc[b][1] += wq.y * s01 + m0 * bb.y;
-            acc[b][2] += wq.y * s10 + m1 * bb.x; acc[b][3] += wq.y * s11 + m1 * bb.y;
           }
         }
       }
     }
     double* M = mats + (size_t)(slots ? (int64_t)slots[e] : e) * ND * ND;
 #pragma unroll
-    for (int b = 0; b < MAXB; b++) {
-      const int blk = lane + 32 * b;
-      if (blk < NBLK) {
-        const int i0 = 2 * (blk / NBK), j0 = 2 * (blk % NBK);
+    for (int b = 0; b < MAXS; b++) {
 #pragma unroll
-        for (int a = 0; a < 2; a++)
+      for (int k = 0; k < 4; k++) acc[b][k] += __shfl_xor_sync(0xffffffffu, acc[b][k], 16);  // even + odd points
+      if (bi_[b] >= 0) {
+        const int i0 = 2 * bi_[b], j0 = 2 * bj_[b];
+        if (half == 0 || bi_[b] != bj_[b]) {
 #pragma unroll
-          for (int c = 0; c < 2; c++) {
-            const int i = i0 + a, j = j0 + c;
-            if (i < ND && j < ND) {
-              if (accumulate) M[i * ND + j] += acc[b][2 * a + c];
-              else M[i * ND + j] = acc[b][2 * a + c];
+          for (int a = 0; a < 2; a++)
+#pragma unroll
+            for (int c = 0; c < 2; c++) {
+              const int i = i0 + a, j = j0 + c;
+              if (i < ND && j < ND) {
+                const int k = half ? j * ND + i : i * ND + j;  // half 1: the mirrored block
+                if (accumulate) M[k] += acc[b][2 * a + c];
+                else M[k] = acc[b][2 * a + c];
+              }
             }
-          }
+        }
       }
     }
   }
@@ -577,7 +611,7 @@ int make_terms(xgpu_ctx* ctx, const xgpu_term* th, int nt, TermsDev& T, bool* on
 template <int D, int P>
 int launch_ms(xgpu_ctx* ctx, int64_t n, const int32_t* elems, const int32_t* el_vtx, const double* vtx_xyz,
               const int64_t* offsets, const double* pts, const double* wts, int np_shared, const TermsDev& T,
-              int accumulate, const int32_t* slots, double* mats)
+              int accumulate, const int32_t* slots, double* mats, const Rule2* r2 = nullptr)
 {
   const int nd = xg_h1_ndof(D, P);
   const int ndp = (nd + 1) & ~1;
@@ -585,6 +619,8 @@ int launch_ms(xgpu_ctx* ctx, int64_t n, const int32_t* elems, const int32_t* el_
   int CH = 32;
   while (CH > 4 && (size_t)4 * CH * PS * sizeof(double) > 56 * 1024) CH >>= 1;
   const DefDev df = xg_defdev(ctx, D);
+  Rule2 R2;
+  if (r2) R2 = *r2; else { R2.offsets = nullptr; R2.pts = nullptr; R2.wts = nullptr; R2.T.n = 0; }
   const size_t sm = (size_t)4 * (CH * PS + (df.order > 0 ? XG_DEFS : 0)) * sizeof(double);
   unsigned grid = nblk(n, 4);
   if (grid > XGPU_NSM * 16) grid = XGPU_NSM * 16;
@@ -592,12 +628,12 @@ int launch_ms(xgpu_ctx* ctx, int64_t n, const int32_t* elems, const int32_t* el_
     if constexpr (D >= 2) {
       XGPU_CUDA(ctx, cudaFuncSetAttribute(k_elmat_ms<D, P, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
       k_elmat_ms<D, P, true><<<grid, 128, sm, ctx->stream>>>(n, elems, el_vtx, vtx_xyz, offsets, pts, wts, np_shared, CH, T,
-                                                             accumulate, slots, mats, df);
+                                                             accumulate, slots, mats, df, R2);
     } else return xgpu_fail(ctx, XGPU_ERR_UNSUPPORTED, "elmat: deformation needs dim >= 2");
   } else {
     XGPU_CUDA(ctx, cudaFuncSetAttribute(k_elmat_ms<D, P, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
     k_elmat_ms<D, P, false><<<grid, 128, sm, ctx->stream>>>(n, elems, el_vtx, vtx_xyz, offsets, pts, wts, np_shared, CH, T,
-                                                            accumulate, slots, mats, df);
+                                                            accumulate, slots, mats, df, R2);
   }
   XGPU_LAUNCH_CHECK(ctx);
   return XGPU_OK;
@@ -734,6 +770,52 @@ extern "C" int xgpu_elmat_rule(xgpu_ctx* ctx, int dim, int fe_order, int64_t n, 
   if (dim == 3) return launch_points<3>(ctx, n, elems, el_vtx, vtx_xyz, phi, offsets, pts, wts, 0, fe_order, T, accumulate, slots, mats, ms);
   if (dim == 2) return launch_points<2>(ctx, n, elems, el_vtx, vtx_xyz, phi, offsets, pts, wts, 0, fe_order, T, accumulate, slots, mats, ms);
   return launch_points<1>(ctx, n, elems, el_vtx, vtx_xyz, phi, offsets, pts, wts, 0, fe_order, T, accumulate, slots, mats, ms);
+}
+
+namespace {
+template <int D>
+int launch_pair(xgpu_ctx* ctx, int p, int64_t n, const int32_t* elems, const int32_t* el_vtx, const double* vtx_xyz,
+                const int64_t* offsets, const double* pts, const double* wts, const TermsDev& T, const Rule2& R2,
+                int accumulate, const int32_t* slots, double* mats)
+{
+  switch (p) {
+    case 1: return launch_ms<D, 1>(ctx, n, elems, el_vtx, vtx_xyz, offsets, pts, wts, 0, T, accumulate, slots, mats, &R2);
+    case 2: return launch_ms<D, 2>(ctx, n, elems, el_vtx, vtx_xyz, offsets, pts, wts, 0, T, accumulate, slots, mats, &R2);
+    case 3: return launch_ms<D, 3>(ctx, n, elems, el_vtx, vtx_xyz, offsets, pts, wts, 0, T, accumulate, slots, mats, &R2);
+    case 4: return launch_ms<D, 4>(ctx, n, elems, el_vtx, vtx_xyz, offsets, pts, wts, 0, T, accumulate, slots, mats, &R2);
+  }
+  return xgpu_fail(ctx, XGPU_ERR_ARG, "elmat: order");
+}
+}  // namespace
+
+extern "C" int xgpu_elmat_rule_pair(xgpu_ctx* ctx, int dim, int fe_order, int64_t n, const int32_t* elems,
+                                    const int32_t* el_vtx, const double* vtx_xyz, const double* phi,
+                                    const int64_t* offsets_a, const double* pts_a, const double* wts_a,
+                                    const xgpu_term* terms_a_host, int nterms_a,
+                                    const int64_t* offsets_b, const double* pts_b, const double* wts_b,
+                                    const xgpu_term* terms_b_host, int nterms_b,
+                                    int accumulate, const int32_t* slots, double* mats)
+{
+  if (!ctx || dim < 1 || dim > 3 || fe_order < 1 || fe_order > XG_MAX_ORDER || !offsets_a || !offsets_b)
+    return xgpu_fail(ctx, XGPU_ERR_ARG, "xgpu_elmat_rule_pair: bad argument (orders 1..4)");
+  if (n == 0) return XGPU_OK;
+  TermsDev Ta; Rule2 R2; bool msa, msb;
+  int rc = make_terms(ctx, terms_a_host, nterms_a, Ta, &msa);
+  if (rc) return rc;
+  rc = make_terms(ctx, terms_b_host, nterms_b, R2.T, &msb);
+  if (rc) return rc;
+  const bool tensor = dim >= 2 && ctx->opt_dmma >= 0 && (fe_order >= 3 || (ctx->opt_dmma > 0 && fe_order == 2));
+  if (!(msa && msb) || tensor) {  // not the mass/stiffness CUDA-core kernel: two passes, the second accumulating
+    rc = xgpu_elmat_rule(ctx, dim, fe_order, n, elems, el_vtx, vtx_xyz, phi, offsets_a, pts_a, wts_a, terms_a_host, nterms_a,
+                         accumulate, slots, mats);
+    if (rc) return rc;
+    return xgpu_elmat_rule(ctx, dim, fe_order, n, elems, el_vtx, vtx_xyz, phi, offsets_b, pts_b, wts_b, terms_b_host, nterms_b,
+                           1, slots, mats);
+  }
+  R2.offsets = offsets_b; R2.pts = pts_b; R2.wts = wts_b;
+  if (dim == 3) return launch_pair<3>(ctx, fe_order, n, elems, el_vtx, vtx_xyz, offsets_a, pts_a, wts_a, Ta, R2, accumulate, slots, mats);
+  if (dim == 2) return launch_pair<2>(ctx, fe_order, n, elems, el_vtx, vtx_xyz, offsets_a, pts_a, wts_a, Ta, R2, accumulate, slots, mats);
+  return launch_pair<1>(ctx, fe_order, n, elems, el_vtx, vtx_xyz, offsets_a, pts_a, wts_a, Ta, R2, accumulate, slots, mats);
 }
 
 extern "C" int xgpu_elmat_std(xgpu_ctx* ctx, int dim, int fe_order, int64_t n, const int32_t* elems,

@@ -311,10 +311,9 @@ class GpuBackend:
         order = 2 * p
         l_neg, l_if = l_neg.contiguous(), l_if.contiguous()
         m_neg = ops.elmat_std(dim, p, l_neg, els, xyz, phi, order, TERMS_VOL, ctx=ctx)
-        off, q, w = ops.cutquad(dim, l_if, els, xyz, phi, ops.NEG, order, ctx=ctx)
-        m_if = ops.elmat_rule(dim, p, l_if, els, xyz, phi, off, q, w, TERMS_VOL, ctx=ctx)
-        off2, q2, w2 = ops.cutquad(dim, l_if, els, xyz, phi, ops.IF, order, ctx=ctx)
-        ops.elmat_rule(dim, p, l_if, els, xyz, phi, off2, q2, w2, TERMS_IF, out=m_if, accumulate=True, ctx=ctx)
+        ra = ops.cutquad(dim, l_if, els, xyz, phi, ops.NEG, order, ctx=ctx)
+        rb = ops.cutquad(dim, l_if, els, xyz, phi, ops.IF, order, ctx=ctx)
+        m_if = ops.elmat_rule_pair(dim, p, l_if, els, xyz, phi, ra, TERMS_VOL, rb, TERMS_IF, ctx=ctx)
         ctx.raise_on_geometry_error()
         return m_neg, m_if
 

@@ -268,6 +268,21 @@ def elmat_rule(dim, fe_order, elems, el_vtx, vtx_xyz, phi, off, pts, wts, terms,
     return out
 
 
+def elmat_rule_pair(dim, fe_order, elems, el_vtx, vtx_xyz, phi, rule_a, terms_a, rule_b, terms_b, out=None, accumulate=False,
+                    slots=None, ctx=None):
+    """two integrators in one pass: rule_x = (offsets, pts, wts)"""
+    ctx = ctx or default_ctx()
+    n = el_vtx.shape[0] if elems is None else elems.numel()
+    nd = h1_ndof(dim, fe_order)
+    if out is None:
+        out = torch.empty((n, nd, nd), dtype=torch.float64, device=el_vtx.device)
+    ctx.check(ctx.lib.xgpu_elmat_rule_pair(ctx.h, dim, fe_order, n, ptr(elems), ptr(_i32(el_vtx)), ptr(_f64(vtx_xyz)), ptr(phi),
+                                           ptr(rule_a[0]), ptr(rule_a[1]), ptr(rule_a[2]), terms_array(terms_a), len(terms_a),
+                                           ptr(rule_b[0]), ptr(rule_b[1]), ptr(rule_b[2]), terms_array(terms_b), len(terms_b),
+                                           int(accumulate), ptr(slots), ptr(out)))
+    return out
+
+
 def elmat_std(dim, fe_order, elems, el_vtx, vtx_xyz, phi, order, terms, out=None, accumulate=False, slots=None, ctx=None):
     ctx = ctx or default_ctx()
     n = el_vtx.shape[0] if elems is None else elems.numel()

@@ -394,3 +394,35 @@ def test_elmat_tensor_tiles_match_cuda_core_path_and_oracle(dim, n, p):
     assert rel_err(res[1][1], res[-1][1]) < 1e-12
     # the tensor path computes the tiles ti <= tj and mirrors the off-diagonal ones
     assert rel_err(res[1][0], res[1][0].transpose(0, 2, 1)) < 1e-14
+
+
+@pytest.mark.parametrize("dim,n,p", [(3, 5, 2), (3, 4, 1), (2, 9, 2), (3, 3, 3), (3, 3, 4)])
+def test_elmat_rule_pair_equals_two_accumulating_passes(dim, n, p):
+    """xgpu_elmat_rule_pair (NEG volume terms + IF interface term in one pass) against the oracle and against the two
+    separate accumulating calls (same sums, different association: 1e-14)"""
+    m = (meshes.MakeStructured3DMesh(nx=n) if dim == 3 else meshes.MakeStructured2DMesh(nx=n, ny=n)).to(DEV)
+    c = (.47, .52, .5)
+    phi = torch.sqrt(sum((m.points[:, i] - c[i]) ** 2 for i in range(dim))) - 0.34
+    phi = torch.where(phi.abs() < 1e-14, torch.full_like(phi, 1e-14), phi).contiguous()
+    bn, bp, bi, _ = ops.classify(dim, m.elements, phi)
+    l_if = ops.bitset_to_list(bi, m.ne)
+    TV = [(ops.OP_GRAD, ops.OP_GRAD, 1.0, 0), (ops.OP_ID, ops.OP_ID, 0.5, 0)]
+    TI = [(ops.OP_ID, ops.OP_ID, 3.0, -1)]
+    ra = ops.cutquad(dim, l_if, m.elements, m.points, phi, ops.NEG, 2 * p)
+    rb = ops.cutquad(dim, l_if, m.elements, m.points, phi, ops.IF, 2 * p)
+    ctx = ops.default_ctx()
+    for mode in (0, -1):
+        ctx.set_option("elmat_dmma", mode)
+        try:
+            pair = ops.elmat_rule_pair(dim, p, l_if, m.elements, m.points, phi, ra, TV, rb, TI)
+            two = ops.elmat_rule(dim, p, l_if, m.elements, m.points, phi, ra[0], ra[1], ra[2], TV)
+            ops.elmat_rule(dim, p, l_if, m.elements, m.points, phi, rb[0], rb[1], rb[2], TI, out=two, accumulate=True)
+        finally:
+            ctx.set_option("elmat_dmma", 0)
+        assert torch.allclose(pair, two, rtol=1e-13, atol=1e-14 * float(two.abs().max()))
+        assert torch.allclose(pair, pair.transpose(1, 2), rtol=1e-13, atol=1e-14 * float(two.abs().max()))
+    pts, els = m.points.cpu().numpy(), m.elements.cpu().numpy()
+    lo = l_if.cpu().numpy()
+    mo = xo.batch_cut_elmats(dim, p, lo, els, pts, phi.cpu().numpy(), xo.NEG, 2 * p, TV)
+    mo += xo.batch_cut_elmats(dim, p, lo, els, pts, phi.cpu().numpy(), xo.IF, 2 * p, TI)
+    assert np.linalg.norm(pair.cpu().numpy() - mo) <= 1e-12 * np.linalg.norm(mo)
