@@ -229,6 +229,17 @@ void xgpu_plan_destroy(xgpu_plan* plan);
 /* device time of the two halves of xgpu_csr_plan (CUDA events on the plan's stream): ms_host[0] =
  * transposed table (histogram, scan, fill, segment sort), ms_host[1] = pattern pass (bench.py) */
 int xgpu_plan_phase_ms(xgpu_plan* plan, double* ms_host);
+/* ---------------------------------------------------------------- (e') multi-GPU interface rows
+ * Element-partitioned assembly: rows whose dof is shared with a neighbouring rank are summed at the owner.  Both sides
+ * hold identical column orders for such rows, so the message is the packed VALUES of the listed rows (rows[i] < 0: an
+ * inactive candidate, length 0).  The send/recv itself (NCCL over NVLink) is issued by the host layer on `out` / `in`.
+ * offsets: n+1 int64 (device) = exclusive scan of the row lengths; total_host may be NULL (no synchronisation). */
+int xgpu_rows_offsets(xgpu_ctx* ctx, int64_t n, const int64_t* rowptr, const int32_t* rows, int64_t* offsets,
+                      int64_t* total_host);
+int xgpu_rows_pack(xgpu_ctx* ctx, int64_t n, const int64_t* rowptr, const int32_t* rows, const int64_t* offsets,
+                   const double* vals, double* out);
+int xgpu_rows_add(xgpu_ctx* ctx, int64_t n, const int64_t* rowptr, const int32_t* rows, const int64_t* offsets,
+                  const double* in, double* vals);
 /* y = A x for checks (CSR SpMV, one warp per row) */
 int xgpu_csr_spmv(xgpu_ctx* ctx, int64_t nrows, const int64_t* rowptr, const int32_t* colidx,
                   const double* vals, const double* x, double* y);

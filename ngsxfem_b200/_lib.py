@@ -93,6 +93,9 @@ _SIGS = {
     "xgpu_csr_assemble": (C.c_int, [VP, VP, C.POINTER(Batch), C.c_int, VP, VP, VP]),
     "xgpu_plan_destroy": (None, [VP]),
     "xgpu_plan_phase_ms": (C.c_int, [VP, c_f64p]),
+    "xgpu_rows_offsets": (C.c_int, [VP, C.c_int64, VP, VP, VP, c_i64p]),
+    "xgpu_rows_pack": (C.c_int, [VP, C.c_int64, VP, VP, VP, VP, VP]),
+    "xgpu_rows_add": (C.c_int, [VP, C.c_int64, VP, VP, VP, VP, VP]),
     "xgpu_csr_spmv": (C.c_int, [VP, C.c_int64, VP, VP, VP, VP, VP]),
 }
 

@@ -1,0 +1,89 @@
+// merge.cu — interface-row exchange of the element-partitioned assembly (the reference's analogue is
+// NGSolve's ParallelDofs cumulation of a distributed matrix [third party]): the values of a list of CSR rows are
+// packed into one contiguous message buffer, and a received buffer is added into the owner's rows.  Both sides of an
+// interface hold IDENTICAL column orders for these rows (the numbering is (owner, gid) ordered), so only values travel.
+// One warp per listed row; rows[i] < 0 marks an inactive candidate (length 0).  The NCCL send/recv itself is issued
+// by the host layer (torch.distributed) on these buffers.
+#include "common.cuh"
+
+namespace {
+
+inline unsigned nblk(int64_t n, int t) { return (unsigned)((n + t - 1) / t); }
+
+__global__ void k_rows_len(int64_t n, const long long* __restrict__ rowptr, const int32_t* __restrict__ rows,
+                           int32_t* __restrict__ len)
+{
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int r = rows[i];
+  len[i] = (r >= 0) ? (int32_t)(rowptr[r + 1] - rowptr[r]) : 0;
+}
+
+template <bool ADD>
+__global__ void __launch_bounds__(256) k_rows_move(int64_t n, const long long* __restrict__ rowptr,
+                                                   const int32_t* __restrict__ rows, const long long* __restrict__ offsets,
+                                                   double* __restrict__ vals, double* __restrict__ buf)
+{
+  const int lane = threadIdx.x & 31;
+  const int64_t w0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t i = w0; i < n; i += nw) {
+    const int r = rows[i];
+    if (r < 0) continue;
+    const long long a = rowptr[r], o = offsets[i];
+    const int len = (int)(rowptr[r + 1] - a);
+    for (int k = lane; k < len; k += 32) {
+      if (ADD) vals[a + k] += buf[o + k];
+      else buf[o + k] = vals[a + k];
+    }
+  }
+}
+
+}  // namespace
+
+extern "C" int xgpu_rows_offsets(xgpu_ctx* ctx, int64_t n, const int64_t* rowptr, const int32_t* rows, int64_t* offsets,
+                                 int64_t* total_host)
+{
+  if (!ctx || n < 0 || !offsets) return xgpu_fail(ctx, XGPU_ERR_ARG, "xgpu_rows_offsets: bad argument");
+  if (total_host) *total_host = 0;
+  void* p;
+  int rc = xgpu_scratch(ctx, 0, sizeof(int32_t) * (n + 1), &p);
+  if (rc) return rc;
+  if (n > 0) {
+    k_rows_len<<<nblk(n, 256), 256, 0, ctx->stream>>>(n, (const long long*)rowptr, rows, (int32_t*)p);
+    XGPU_LAUNCH_CHECK(ctx);
+  }
+  rc = xgpu_exclusive_scan_i32(ctx, (const int32_t*)p, n, offsets);
+  if (rc) return rc;
+  if (total_host) {
+    XGPU_CUDA(ctx, cudaMemcpyAsync(ctx->h_pinned, offsets + n, sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
+    XGPU_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    *total_host = ctx->h_pinned[0];
+  }
+  return XGPU_OK;
+}
+
+extern "C" int xgpu_rows_pack(xgpu_ctx* ctx, int64_t n, const int64_t* rowptr, const int32_t* rows, const int64_t* offsets,
+                              const double* vals, double* out)
+{
+  if (!ctx || n < 0) return xgpu_fail(ctx, XGPU_ERR_ARG, "xgpu_rows_pack: bad argument");
+  if (n == 0) return XGPU_OK;
+  unsigned grid = nblk(n, 8);
+  if (grid > XGPU_NSM * 16) grid = XGPU_NSM * 16;
+  k_rows_move<false><<<grid, 256, 0, ctx->stream>>>(n, (const long long*)rowptr, rows, (const long long*)offsets,
+                                                    const_cast<double*>(vals), out);
+  XGPU_LAUNCH_CHECK(ctx);
+  return XGPU_OK;
+}
+
+extern "C" int xgpu_rows_add(xgpu_ctx* ctx, int64_t n, const int64_t* rowptr, const int32_t* rows, const int64_t* offsets,
+                             const double* in, double* vals)
+{
+  if (!ctx || n < 0) return xgpu_fail(ctx, XGPU_ERR_ARG, "xgpu_rows_add: bad argument");
+  if (n == 0) return XGPU_OK;
+  unsigned grid = nblk(n, 8);
+  if (grid > XGPU_NSM * 16) grid = XGPU_NSM * 16;
+  k_rows_move<true><<<grid, 256, 0, ctx->stream>>>(n, (const long long*)rowptr, rows, (const long long*)offsets, vals,
+                                                   const_cast<double*>(in));
+  XGPU_LAUNCH_CHECK(ctx);
+  return XGPU_OK;
+}

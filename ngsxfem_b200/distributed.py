@@ -198,25 +198,15 @@ class DistributedCutAssembly:
         mark("csr")
         # 6. interface-row reduction: the values of the rows {owner == q, touched by my own elements} are packed and
         #    sent, the owner adds what it receives in a fixed order (lower rank first)
-        pos = []
+        lists = []
         for q in p.neighbors:
             it = p.iface[q]
             for cand, m in ((it["C_send"], m_snd[q]), (it["D"], m_rcv[q])):
-                rows = dofmap[cand].long()
-                live = m & (rows >= 0)
-                rows = rows.clamp(min=0)
-                start = rowptr[rows]
-                ln = torch.where(live, rowptr[rows + 1] - start, torch.zeros_like(start))
-                pos.append((start, ln))
+                loc = dofmap[cand]
+                rows = torch.where(m, loc, torch.full_like(loc, -1)).contiguous()   # -1: inactive candidate
+                lists.append((rows, be.rows_offsets(rowptr, rows)))
         mark("merge_rows")
-        tots = torch.stack([ln.sum() if ln.numel() else torch.zeros((), dtype=torch.int64, device=dev) for _, ln in pos]).tolist() \
-            if pos else []
-        idx = []
-        for (start, ln), tot in zip(pos, tots):
-            if tot == 0:
-                idx.append(torch.zeros(0, dtype=torch.int64, device=dev))
-            else:
-                idx.append(torch.repeat_interleave(start - _excl_cumsum(ln), ln, output_size=tot) + torch.arange(tot, device=dev))
+        tots = torch.stack([off[-1] for _, off in lists]).tolist() if lists else []   # the one host sync of this phase
         # 7. global numbering = offset[owner] + index among the owner's active dofs (ascending key).  The owner-local
         #    indices of the interface dofs travel in the SAME message round as the interface values: one STATIC-size
         #    int message per neighbour over all interface candidates (-1 = inactive) — my candidate list D towards q
@@ -229,8 +219,9 @@ class DistributedCutAssembly:
             red = dist.all_reduce(counts, group=self.group, async_op=True)
         msgs = []
         for k, q in enumerate(p.neighbors):
-            sidx, ridx = idx[2 * k], idx[2 * k + 1]
-            msgs.append((q, vals[sidx].contiguous(), torch.empty(ridx.numel(), dtype=vals.dtype, device=dev)))
+            (srows, soff), (rrows, roff) = lists[2 * k], lists[2 * k + 1]
+            msgs.append((q, be.rows_pack(rowptr, srows, soff, vals, tots[2 * k]),
+                         torch.empty(tots[2 * k + 1], dtype=vals.dtype, device=dev)))
             loc = dofmap[p.iface[q]["D"]].long()
             qa, qb = p.range_of[q]
             msgs.append((q, torch.where(m_seen[q], loc - n_lo, torch.full_like(loc, -1)).contiguous(),
@@ -239,7 +230,8 @@ class DistributedCutAssembly:
         self._exchange_all(msgs)
         mark("merge_exchange")
         for k, q in enumerate(p.neighbors):                               # neighbours ascending: lower rank first
-            vals[idx[2 * k + 1]] += msgs[2 * k][2]
+            rrows, roff = lists[2 * k + 1]
+            be.rows_add(rowptr, rrows, roff, msgs[2 * k][2], vals)
         mark("merge")
         if red is not None:
             red.wait()
@@ -316,6 +308,15 @@ class GpuBackend:
         m_if = ops.elmat_rule_pair(dim, p, l_if, els, xyz, phi, ra, TERMS_VOL, rb, TERMS_IF, ctx=ctx)
         ctx.raise_on_geometry_error()
         return m_neg, m_if
+
+    def rows_offsets(self, rowptr, rows):
+        return self.ops.rows_offsets(rowptr, rows, ctx=self.ctx)
+
+    def rows_pack(self, rowptr, rows, off, vals, total):
+        return self.ops.rows_pack(rowptr, rows, off, vals, total, ctx=self.ctx)
+
+    def rows_add(self, rowptr, rows, off, buf, vals):
+        return self.ops.rows_add(rowptr, rows, off, buf, vals, ctx=self.ctx)
 
     def csr(self, ndof, batches):
         ops = self.ops

@@ -425,6 +425,27 @@ def csr_assemble(plan, batches):
     return rowptr, col, vals
 
 
+def rows_offsets(rowptr, rows, ctx=None):
+    """offsets (n+1, int64, device) of the packed values of the listed CSR rows (rows < 0: length 0); no host sync"""
+    ctx = ctx or default_ctx()
+    off = torch.empty(rows.numel() + 1, dtype=torch.int64, device=rows.device)
+    ctx.check(ctx.lib.xgpu_rows_offsets(ctx.h, rows.numel(), ptr(rowptr), ptr(_i32(rows)), ptr(off), None))
+    return off
+
+
+def rows_pack(rowptr, rows, off, vals, total, ctx=None):
+    ctx = ctx or default_ctx()
+    out = torch.empty(total, dtype=torch.float64, device=vals.device)
+    ctx.check(ctx.lib.xgpu_rows_pack(ctx.h, rows.numel(), ptr(rowptr), ptr(_i32(rows)), ptr(off), ptr(vals), ptr(out)))
+    return out
+
+
+def rows_add(rowptr, rows, off, buf, vals, ctx=None):
+    ctx = ctx or default_ctx()
+    ctx.check(ctx.lib.xgpu_rows_add(ctx.h, rows.numel(), ptr(rowptr), ptr(_i32(rows)), ptr(off), ptr(buf), ptr(vals)))
+    return vals
+
+
 def csr_spmv(rowptr, col, vals, x, ctx=None):
     ctx = ctx or default_ctx()
     y = torch.empty(rowptr.numel() - 1, dtype=torch.float64, device=x.device)

@@ -41,6 +41,31 @@ class OracleBackend:
         m_if = m_if + xo.batch_cut_elmats(dim, p, li, els, xyz, ph, xo.IF, order, TERMS_IF)
         return torch.from_numpy(m_neg), torch.from_numpy(m_if)
 
+    @staticmethod
+    def _positions(rowptr, rows, off):
+        live = rows >= 0
+        r = rows[live].long()
+        ln = rowptr[r + 1] - rowptr[r]
+        src = torch.repeat_interleave(rowptr[r], ln) + (torch.arange(int(ln.sum())) - torch.repeat_interleave(torch.cumsum(ln, 0) - ln, ln))
+        dst = torch.repeat_interleave(off[:-1][live], ln) + (torch.arange(int(ln.sum())) - torch.repeat_interleave(torch.cumsum(ln, 0) - ln, ln))
+        return src, dst
+
+    def rows_offsets(self, rowptr, rows):
+        r = rows.long().clamp(min=0)
+        ln = torch.where(rows >= 0, rowptr[r + 1] - rowptr[r], torch.zeros_like(rowptr[r]))
+        return torch.cat([torch.zeros(1, dtype=torch.int64), torch.cumsum(ln, 0)])
+
+    def rows_pack(self, rowptr, rows, off, vals, total):
+        out = torch.zeros(total, dtype=vals.dtype)
+        src, dst = self._positions(rowptr, rows, off)
+        out[dst] = vals[src]
+        return out
+
+    def rows_add(self, rowptr, rows, off, buf, vals):
+        src, dst = self._positions(rowptr, rows, off)
+        vals[src] += buf[dst]
+        return vals
+
     def csr(self, ndof, batches):
         W = max(t.shape[1] for t, _ in batches)
         tabs, mats = [], []
