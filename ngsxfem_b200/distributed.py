@@ -19,11 +19,12 @@ Per assembly:
   4. element matrices of the OWN active elements                    [compute backend]
   5. local CSR over own batches + the halo batch as sparsity only (mats = NULL), so the owner's
      pattern of an interface row is already final ("union of cliques" over both sides)
-  6. interface-row reduction: for each neighbour q, the values of the rows {owner == q, touched by
-     my own elements} are packed and sent (P2P send/recv over NVLink), the owner adds them into
-     its rows in a fixed order (lower rank first) — the only data-path communication
-  7. global numbering: offset[owner] + index among the owner's active dofs; ghost columns get their
-     global ids from the owner (one int message per neighbour)
+  6. interface-row reduction: for each neighbour q, the values of the rows {owner == q, touched by my own elements}
+     are packed (xgpu_rows_pack) and sent, the owner adds what it receives (xgpu_rows_add) in a fixed order (lower rank
+     first).  All candidate lists are static; inactive candidates have length 0 (masks, no compaction).
+  7. global numbering: offset[owner] + index among the owner's active dofs; the owner-local indices of the interface
+     dofs travel in the SAME batched NCCL isend/irecv round as the values (static-size int message per neighbour),
+     the offsets come from one all-reduce of the owned counts.  These are the only data-path communications.
 The result is a row-distributed CSR (rows = owned dofs) with global column ids.
 
 The compute backend is duck-typed (`classify`, `elmats`, `csr`): `GpuBackend` below drives the
