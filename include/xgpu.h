@@ -150,6 +150,13 @@ int xgpu_integrate_monomial(xgpu_ctx* ctx, int dim, int64_t n, const int32_t* el
                             const double* vtx_xyz, const int64_t* offsets, const double* pts,
                             const double* wts, const int* expo_host, double* result_host);
 
+/* the same over BOUNDARY elements (dCut(..., vb=BND), tests/pytests/test_bndcut.py): simplices of dimension `dim`
+ * embedded in R^sdim (segments in 2D / 3D, triangles in 3D), measure sqrt(det F^T F); rules from
+ * xgpu_cutquad_count/_fill with the boundary elements' table and dt = NEG / POS. */
+int xgpu_integrate_monomial_bnd(xgpu_ctx* ctx, int dim, int sdim, int64_t n, const int32_t* elems,
+                                const int32_t* el_vtx, const double* vtx_xyz, const int64_t* offsets,
+                                const double* pts, const double* wts, const int* expo_host, double* result_host);
+
 /* ---------------------------------------------------------------- (c) element matrices
  * SymbolicCutBilinearFormIntegrator::T_CalcElementMatrixAdd (xfem/symboliccutbfi.cpp:76-486)
  * for a closed menu of integrands: sum of terms  coef * h^hpow * op_test(v) * op_trial(u),

@@ -198,6 +198,59 @@ __global__ void __launch_bounds__(128) k_integrate(int64_t n, const int32_t* __r
   if (lane == 0) elsum[i] = s;
 }
 
+// the same for simplices of dimension D embedded in R^SD (boundary elements, dCut(..., vb=BND)): the measure is
+// sqrt(det F^T F) of the D x SD Jacobian (segment length in 2D / 3D, triangle: |cross product|)
+template <int D, int SD>
+__global__ void __launch_bounds__(128) k_integrate_emb(int64_t n, const int32_t* __restrict__ elems,
+                                                       const int32_t* __restrict__ el_vtx, const double* __restrict__ vtx_xyz,
+                                                       const int64_t* __restrict__ offsets, const double* __restrict__ pts,
+                                                       const double* __restrict__ wts, int e0, int e1, int e2,
+                                                       double* __restrict__ elsum)
+{
+  const int lane = threadIdx.x & 31;
+  const int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (i >= n) return;
+  const int64_t el = elems ? (int64_t)elems[i] : i;
+  double vx[D + 1][3];
+#pragma unroll
+  for (int k = 0; k < D + 1; k++) {
+    const int v = __ldg(el_vtx + el * (D + 1) + k);
+#pragma unroll
+    for (int c = 0; c < 3; c++) vx[k][c] = (c < SD) ? __ldg(vtx_xyz + (int64_t)v * SD + c) : 0.0;
+  }
+  double meas;
+  {
+    double a[3], b[3];
+#pragma unroll
+    for (int c = 0; c < 3; c++) { a[c] = vx[0][c] - vx[D][c]; b[c] = (D == 2) ? vx[1][c] - vx[D][c] : 0.0; }
+    if (D == 1) meas = sqrt(a[0] * a[0] + a[1] * a[1] + a[2] * a[2]);
+    else {
+      const double c0 = a[1] * b[2] - a[2] * b[1], c1 = a[2] * b[0] - a[0] * b[2], c2 = a[0] * b[1] - a[1] * b[0];
+      meas = sqrt(c0 * c0 + c1 * c1 + c2 * c2);
+    }
+  }
+  const int ex[3] = {e0, e1, e2};
+  double s = 0.0;
+  for (int64_t q = offsets[i] + lane; q < offsets[i + 1]; q += 32) {
+    double lam[D + 1], sl = 1.0;
+#pragma unroll
+    for (int k = 0; k < D; k++) { lam[k] = pts[3 * q + k]; sl -= lam[k]; }
+    lam[D] = sl;
+    double f = 1.0;
+#pragma unroll
+    for (int c = 0; c < SD; c++) {
+      double xc = 0.0;
+#pragma unroll
+      for (int k = 0; k < D + 1; k++) xc += lam[k] * vx[k][c];
+      for (int e = 0; e < ex[c]; e++) f *= xc;
+    }
+    s += wts[q] * meas * f;
+  }
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) s += __shfl_down_sync(0xffffffffu, s, d);
+  if (lane == 0) elsum[i] = s;
+}
+
 // fixed-order sum: each block reduces a contiguous tile with a shared-memory tree
 __global__ void __launch_bounds__(256) k_sum_tiles(const double* __restrict__ in, int64_t n, double* __restrict__ out)
 {
@@ -317,6 +370,29 @@ extern "C" int xgpu_integrate_monomial(xgpu_ctx* ctx, int dim, int64_t n, const 
   if (dim == 3) k_integrate<3><<<grid, 128, 0, ctx->stream>>>(n, elems, el_vtx, vtx_xyz, offsets, pts, wts, e0, e1, e2, elsum);
   else if (dim == 2) k_integrate<2><<<grid, 128, 0, ctx->stream>>>(n, elems, el_vtx, vtx_xyz, offsets, pts, wts, e0, e1, e2, elsum);
   else k_integrate<1><<<grid, 128, 0, ctx->stream>>>(n, elems, el_vtx, vtx_xyz, offsets, pts, wts, e0, e1, e2, elsum);
+  XGPU_LAUNCH_CHECK(ctx);
+  return xgpu_sum_f64(ctx, elsum, n, elsum + n, result_host);
+}
+
+extern "C" int xgpu_integrate_monomial_bnd(xgpu_ctx* ctx, int dim, int sdim, int64_t n, const int32_t* elems,
+                                           const int32_t* el_vtx, const double* vtx_xyz, const int64_t* offsets,
+                                           const double* pts, const double* wts, const int* expo_host, double* result_host)
+{
+  if (!ctx || !result_host || !((dim == 1 && (sdim == 2 || sdim == 3)) || (dim == 2 && sdim == 3)))
+    return xgpu_fail(ctx, XGPU_ERR_ARG, "xgpu_integrate_monomial_bnd: segments in 2D/3D or triangles in 3D");
+  if (ctx->def_order > 0) return xgpu_fail(ctx, XGPU_ERR_UNSUPPORTED, "xgpu_integrate_monomial_bnd: no deformation support");
+  *result_host = 0.0;
+  if (n == 0) return XGPU_OK;
+  void* p;
+  const int64_t nb = (n + 4095) / 4096;
+  int rc = xgpu_scratch(ctx, 1, sizeof(double) * (n + nb + 2), &p);
+  if (rc) return rc;
+  double* elsum = (double*)p;
+  const int e0 = expo_host[0], e1 = expo_host[1], e2 = sdim > 2 ? expo_host[2] : 0;
+  const unsigned grid = nblk(n * 32, 128);
+  if (dim == 1 && sdim == 2) k_integrate_emb<1, 2><<<grid, 128, 0, ctx->stream>>>(n, elems, el_vtx, vtx_xyz, offsets, pts, wts, e0, e1, e2, elsum);
+  else if (dim == 1) k_integrate_emb<1, 3><<<grid, 128, 0, ctx->stream>>>(n, elems, el_vtx, vtx_xyz, offsets, pts, wts, e0, e1, e2, elsum);
+  else k_integrate_emb<2, 3><<<grid, 128, 0, ctx->stream>>>(n, elems, el_vtx, vtx_xyz, offsets, pts, wts, e0, e1, e2, elsum);
   XGPU_LAUNCH_CHECK(ctx);
   return xgpu_sum_f64(ctx, elsum, n, elsum + n, result_host);
 }

@@ -172,6 +172,14 @@ class CutInfo:
         self._ba = {m: BitArray(ne, dev) for m in range(8)}      # VOL BitArrays by combined mask
         self._ba[7].Set()
         self.cut_ratio = torch.zeros(ne, dtype=torch.float64, device=dev)
+        # BND elements (cutinfo.cpp:82-125 loops over VOL and BND): boundary facets as (dim-1)-simplices
+        self._bnd = None
+        if mesh.dim >= 2:
+            bv, _ = mesh.boundary_elements()
+            nb = bv.shape[0]
+            bb = {m: BitArray(nb, dev) for m in range(8)}
+            bb[7].Set()
+            self._bnd = (bv, bb, torch.zeros(nb, dtype=torch.float64, device=dev))
         self._updated = False
         if levelset is not None:
             self.Update(levelset, subdivlvl, time_order, heapsize)
@@ -195,15 +203,29 @@ class CutInfo:
         ops.bitset_op(ops.BIT_OR, b[CDOM_NEG].bits, b[CDOM_IF].bits, m.ne, out=b[HASNEG].bits, ctx=ctx)
         ops.bitset_op(ops.BIT_OR, b[CDOM_POS].bits, b[CDOM_IF].bits, m.ne, out=b[HASPOS].bits, ctx=ctx)
         b[NO].Clear(); b[ANY].Set()
+        if self._bnd is not None and self._bnd[0].shape[0] > 0:
+            bv, bb, br = self._bnd
+            nb = bv.shape[0]
+            ops.classify(m.dim - 1, bv, phi, ctx=ctx, out=(bb[CDOM_NEG].bits, bb[CDOM_POS].bits, bb[CDOM_IF].bits, br))
+            ops.bitset_op(ops.BIT_OR, bb[CDOM_NEG].bits, bb[CDOM_POS].bits, nb, out=bb[UNCUT].bits, ctx=ctx)
+            ops.bitset_op(ops.BIT_OR, bb[CDOM_NEG].bits, bb[CDOM_IF].bits, nb, out=bb[HASNEG].bits, ctx=ctx)
+            ops.bitset_op(ops.BIT_OR, bb[CDOM_POS].bits, bb[CDOM_IF].bits, nb, out=bb[HASPOS].bits, ctx=ctx)
         ctx.raise_on_geometry_error()
         self._updated = True
 
+    def _bnd_or_raise(self):
+        if self._bnd is None:
+            raise XgpuError("BND elements of a 1D mesh are points: not provided")
+        return self._bnd
+
     def GetElementsOfType(self, dt, vb=VOL):
-        if vb != VOL:
-            raise XgpuError("BND elements: pass the boundary mesh to its own CutInfo")
+        if vb == BND:
+            return self._bnd_or_raise()[1][_to_cdt(dt)]
         return self._ba[_to_cdt(dt)]
 
     def GetCutRatios(self, vb=VOL):
+        if vb == BND:
+            return self._bnd_or_raise()[2]
         return self.cut_ratio
 
     def GetElementsWithThresholdContribution(self, domain_type=NEG, threshold=1.0, vb=VOL):

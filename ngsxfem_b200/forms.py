@@ -677,6 +677,15 @@ def Integrate(levelset_domain=None, mesh=None, cf=1.0, order=5, time_order=-1, d
     dim = mesh.dim
     ctx = default_ctx(mesh.device.index)
     ls, dt = ld["levelset"], ld["domain_type"]
+    if ld.get("vb", 0) == 1:  # BND: dCut(lset, dt, vb=BND) of tests/pytests/test_bndcut.py — boundary facets as elements
+        if isinstance(ls, (list, tuple)) or deformation is not None or int(dt) == IF:
+            raise XgpuError("Integrate over BND: single level set, NEG / POS, no deformation")
+        if dim < 2:
+            raise XgpuError("Integrate over BND needs dim >= 2")
+        bv, _ = mesh.boundary_elements()
+        off, p, w = ops.cutquad(dim - 1, None, bv, mesh.points, _lset_vec(ls, mesh), int(dt), order, ctx=ctx)
+        ctx.raise_on_geometry_error()
+        return cf.coef * ops.integrate_monomial_bnd(dim - 1, dim, None, bv, mesh.points, off, p, w, cf.expo[:dim], ctx=ctx)
     with ctx.deformation(deformation):
         if isinstance(ls, (list, tuple)):
             phis = torch.stack([_lset_vec(l, mesh) for l in ls]).contiguous()

@@ -103,6 +103,15 @@ class Mesh:
             self._topo["facets"] = (ents, el_f, fe)
         return self._topo["facets"]
 
+    def boundary_elements(self):
+        """(bnd_vtx (nbe, dim) int32, facet ids): the boundary facets as surface elements (VorB = BND), ascending facet
+        id.  NGSolve's own boundary-element numbering is third party and not needed: the table is an input."""
+        if "bnd" not in self._topo:
+            ents, _, fe = self.facets()
+            ids = torch.nonzero(fe[:, 1] < 0).reshape(-1)
+            self._topo["bnd"] = (ents[ids].contiguous(), ids.to(torch.int32))
+        return self._topo["bnd"]
+
     @property
     def nedge(self):
         return self.edges()[0].shape[0]

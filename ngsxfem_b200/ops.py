@@ -255,6 +255,17 @@ def integrate_monomial(dim, elems, el_vtx, vtx_xyz, off, pts, wts, expo, ctx=Non
     return res.value
 
 
+def integrate_monomial_bnd(dim, sdim, elems, el_vtx, vtx_xyz, off, pts, wts, expo, ctx=None):
+    """boundary elements: simplices of dimension dim embedded in R^sdim"""
+    ctx = ctx or default_ctx()
+    n = el_vtx.shape[0] if elems is None else elems.numel()
+    ex = (C.c_int * 3)(*([int(e) for e in expo] + [0] * (3 - len(expo))))
+    res = C.c_double(0.0)
+    ctx.check(ctx.lib.xgpu_integrate_monomial_bnd(ctx.h, dim, sdim, n, ptr(elems), ptr(_i32(el_vtx)), ptr(_f64(vtx_xyz)),
+                                                  ptr(off), ptr(pts), ptr(wts), ex, C.byref(res)))
+    return res.value
+
+
 # ---------------------------------------------------------------- (c,d) matrices
 def elmat_rule(dim, fe_order, elems, el_vtx, vtx_xyz, phi, off, pts, wts, terms, out=None, accumulate=False, slots=None, ctx=None):
     ctx = ctx or default_ctx()
