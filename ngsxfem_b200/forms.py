@@ -89,17 +89,19 @@ def Normalize(g):
 class Proxy:
     """trial / test function with an operator"""
 
-    def __init__(self, space, is_test, op=OP_ID, scal=None, other=False):
+    def __init__(self, space, is_test, op=OP_ID, scal=None, other=False, nlset=None):
         self.space, self.is_test, self.op, self.other = space, is_test, op, other
         self.scal = scal or Scalar(1.0)
+        self.nlset = nlset   # level set of the normal in grad(u)*n (OP_DN)
 
     def Other(self):
         if self.op != OP_ID:
             raise XgpuError(".Other() is supported on u / v only")
         return Proxy(self.space, self.is_test, OP_ID, self.scal, other=True)
 
-    def _with(self, op=None, scal=None):
-        return Proxy(self.space, self.is_test, self.op if op is None else op, scal or self.scal, self.other)
+    def _with(self, op=None, scal=None, nlset=None):
+        return Proxy(self.space, self.is_test, self.op if op is None else op, scal or self.scal, self.other,
+                     nlset if nlset is not None else self.nlset)
 
     def __neg__(self):
         return self._with(scal=self.scal * -1.0)
@@ -117,7 +119,7 @@ class Proxy:
         if isinstance(o, Normal):
             if self.op != OP_GRAD:
                 raise XgpuError("only grad(u)*n is supported with the level-set normal")
-            return self._with(op=OP_DN)
+            return self._with(op=OP_DN, nlset=o.lset)
         if isinstance(o, Proxy):
             return Form.from_pair(self, o)
         if isinstance(o, Form):
@@ -135,8 +137,8 @@ class LForm:
     """linear form integrand: sum of (op_test, coef, hpow, expo) = coef h^hpow x^expo op_test(v)
     (menu of xfem/symboliccutlfi.cpp's CoefficientFunction on the accelerated path)"""
 
-    def __init__(self, terms, space):
-        self.terms, self.space = terms, space
+    def __init__(self, terms, space, nlset=None):
+        self.terms, self.space, self.nlset = terms, space, nlset
 
     @staticmethod
     def from_proxy(v):
@@ -144,13 +146,13 @@ class LForm:
             raise XgpuError("a linear form needs a test function")
         if v.op not in (OP_ID, OP_DN) or v.other:
             raise XgpuError("linear forms: menu is f*v and f*(grad(v)*n)")
-        return LForm([(v.op, v.scal.c, v.scal.hpow, (0, 0, 0))], v.space)
+        return LForm([(v.op, v.scal.c, v.scal.hpow, (0, 0, 0))], v.space, v.nlset)
 
     def __add__(self, o):
         if isinstance(o, Proxy):
             o = LForm.from_proxy(o)
         if isinstance(o, LForm):
-            return LForm(self.terms + o.terms, self.space)
+            return LForm(self.terms + o.terms, self.space, Form._merge_nlset(self.nlset, o.nlset))
         return NotImplemented
 
     def __mul__(self, o):
@@ -159,10 +161,10 @@ class LForm:
         if isinstance(o, MeshSize):
             o = Scalar(1.0, o.power)
         if isinstance(o, Scalar):
-            return LForm([(a, c * o.c, hp + o.hpow, ex) for a, c, hp, ex in self.terms], self.space)
+            return LForm([(a, c * o.c, hp + o.hpow, ex) for a, c, hp, ex in self.terms], self.space, self.nlset)
         if isinstance(o, CoordMonomial):
             return LForm([(a, c * o.coef, hp, tuple(e1 + e2 for e1, e2 in zip(ex, o.expo))) for a, c, hp, ex in self.terms],
-                         self.space)
+                         self.space, self.nlset)
         if isinstance(o, CutDifferentialSymbol):
             return Integral(self, o)
         return NotImplemented
@@ -191,8 +193,14 @@ def grad(u):
 class Form:
     """sum of monomials (op_trial, op_test, coef, hpow)"""
 
-    def __init__(self, terms, space):
-        self.terms, self.space = terms, space
+    def __init__(self, terms, space, nlset=None):
+        self.terms, self.space, self.nlset = terms, space, nlset
+
+    @staticmethod
+    def _merge_nlset(a, b):
+        if a is None or b is None or a is b:
+            return a if a is not None else b
+        raise XgpuError("one integrand may use the normal of ONE level set only (split it into several integrals)")
 
     @staticmethod
     def from_pair(a, b):
@@ -204,11 +212,11 @@ class Form:
         if (u.op == OP_JUMP) != (v.op == OP_JUMP):
             raise XgpuError("jump terms must pair (u-u.Other()) with (v-v.Other())")
         s = u.scal * v.scal
-        return Form([(u.op, v.op, s.c, s.hpow)], u.space)
+        return Form([(u.op, v.op, s.c, s.hpow)], u.space, Form._merge_nlset(u.nlset, v.nlset))
 
     def __add__(self, o):
         if isinstance(o, Form):
-            return Form(self.terms + o.terms, self.space)
+            return Form(self.terms + o.terms, self.space, Form._merge_nlset(self.nlset, o.nlset))
         return NotImplemented
 
     def __sub__(self, o):
@@ -220,7 +228,7 @@ class Form:
     def __mul__(self, o):
         if isinstance(o, (numbers.Number, Scalar, MeshSize)):
             s = o if isinstance(o, Scalar) else (Scalar(float(o)) if isinstance(o, numbers.Number) else Scalar(1.0, o.power))
-            return Form([(a, b, c * s.c, hp + s.hpow) for a, b, c, hp in self.terms], self.space)
+            return Form([(a, b, c * s.c, hp + s.hpow) for a, b, c, hp in self.terms], self.space, self.nlset)
         if isinstance(o, (CutDifferentialSymbol, FacetPatchDifferentialSymbol)):
             return Integral(self, o)
         return NotImplemented
@@ -388,9 +396,10 @@ class BilinearForm:
                 continue
             ls = dx.levelset
             with ctx.deformation(dx.deformation):
+                has_dn = any(t[0] == OP_DN or t[1] == OP_DN for t in terms)
                 if isinstance(ls, (list, tuple)):
-                    if any(t[0] == OP_DN or t[1] == OP_DN for t in terms):
-                        raise XgpuError("normal-derivative terms need a single level set")
+                    if has_dn and integ.form.nlset is None:
+                        raise XgpuError("normal-derivative terms on a multi-level-set domain: build n from ONE of the level sets")
                     phis = torch.stack([_lset_vec(g, mesh) for g in ls]).contiguous()
                     dts = _normalize_dtlist(dx.domain_type, len(ls))
                     off, q, w = ops.cutquad_ml(dim, l, mesh.elements, mesh.points, phis, dts, order, ctx=ctx)
@@ -398,9 +407,11 @@ class BilinearForm:
                 else:
                     phi = _lset_vec(ls, mesh)
                     off, q, w = ops.cutquad(dim, l, mesh.elements, mesh.points, phi, int(dx.domain_type), order, ctx=ctx)
+                # n = Normalize(grad(lset)) of the level set the integrand names (square.GetOuterNormals style forms)
+                phi_n = _lset_vec(integ.form.nlset, mesh) if (has_dn and integ.form.nlset is not None) else phi
                 ctx.raise_on_geometry_error()
                 if w.numel():
-                    ops.elmat_rule(dim, p, l, mesh.elements, mesh.points, phi, off, q, w, terms, out=m_A, accumulate=True,
+                    ops.elmat_rule(dim, p, l, mesh.elements, mesh.points, phi_n, off, q, w, terms, out=m_A, accumulate=True,
                                    slots=slots, ctx=ctx)
         tables.append(self._rows(l_A)); mats.append(m_A)
 
@@ -502,7 +513,8 @@ class BilinearForm:
             key = tuple(id(l) for l in ls) if isinstance(ls, (list, tuple)) else id(ls)
             if key not in lsets:
                 lsets.append(key)
-        general = len(lsets) > 1 or any(isinstance(i.dx.levelset, (list, tuple)) for i in vol)
+        general = len(lsets) > 1 or any(isinstance(i.dx.levelset, (list, tuple)) for i in vol) \
+            or any(i.form.nlset is not None and i.form.nlset is not i.dx.levelset for i in vol)
         if general:
             self._assemble_general(vol, active, tables, mats, ctx)
         else:
@@ -601,9 +613,10 @@ class LinearForm:
                 continue
             ls = dx.levelset
             with ctx.deformation(dx.deformation):
+                has_dn = any(t[0] == OP_DN for t in integ.form.terms)
                 if isinstance(ls, (list, tuple)):
-                    if any(t[0] == OP_DN for t in integ.form.terms):
-                        raise XgpuError("normal-derivative terms need a single level set")
+                    if has_dn and integ.form.nlset is None:
+                        raise XgpuError("normal-derivative terms on a multi-level-set domain: build n from ONE of the level sets")
                     phis = torch.stack([_lset_vec(g, mesh) for g in ls]).contiguous()
                     dts = _normalize_dtlist(dx.domain_type, len(ls))
                     off, q, w = ops.cutquad_ml(dim, l, mesh.elements, mesh.points, phis, dts, order, ctx=ctx)
@@ -612,6 +625,8 @@ class LinearForm:
                     phi = _lset_vec(ls, mesh)
                     off, q, w = ops.cutquad(dim, l, mesh.elements, mesh.points, phi, int(dx.domain_type), order, ctx=ctx)
                 ctx.raise_on_geometry_error()
+                if has_dn and integ.form.nlset is not None:
+                    phi = _lset_vec(integ.form.nlset, mesh)
                 if w.numel():
                     ops.elvec_rule(dim, p, l, mesh.elements, mesh.points, phi, off, q, w, integ.form.terms, out=v_A,
                                    accumulate=True, slots=slots, ctx=ctx)
