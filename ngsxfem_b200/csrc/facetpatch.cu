@@ -153,6 +153,40 @@ __device__ __forceinline__ void map_patch_def(const double (*vxf)[3], const doub
   }
 }
 
+// all patch points of one facet on deformed elements: (x1, x2, weight) -> mp[7 l ..], once per facet, all lanes busy
+template <int D>
+__device__ __forceinline__ void fp_map_points(int lane, int np, const double* __restrict__ rp, const double* __restrict__ rw,
+                                              const double (*vx1)[3], const double* F1, const int* v1, const double* defs1,
+                                              const double (*vx2)[3], const double* F2, const int* v2, const double* defs2,
+                                              int def_order, double coef, int hpow, double* pcs, double* mp)
+{
+  if (lane == 0) patch_consts<D>(vx2, F2, v2, defs2, def_order, pcs);
+  if (lane == 1) patch_consts<D>(vx1, F1, v1, defs1, def_order, pcs + 16);
+  __syncwarp();
+  for (int l = lane; l < 2 * np; l += 32) {
+    double x1[3], x2[3], x[3], w1, wd;
+    if (l < np) {
+      x1[0] = rp[3 * l]; x1[1] = rp[3 * l + 1]; x1[2] = rp[3 * l + 2];
+      w1 = rw[l];
+      map_patch_def<D>(vx1, F1, v1, defs1, vx2, F2, v2, defs2, def_order, pcs, x1, w1, x2, &wd);
+    } else {
+      const int q = l - np;
+      x2[0] = rp[3 * q]; x2[1] = rp[3 * q + 1]; x2[2] = rp[3 * q + 2];
+      map_patch_def<D>(vx2, F2, v2, defs2, vx1, F1, v1, defs1, def_order, pcs + 16, x2, rw[q], x1, &w1);
+    }
+    double Fq[D * D], Fiq[D * D];
+    trafo_eval<D>(vx1, F1, v1, def_order, defs1, x1, Fq, x);
+    const double measq = fabs(xg_inv<D>(Fq, Fiq));
+    const double hq = xg_mesh_size<D>(measq);
+    double hpq = 1.0;
+    { const int ap = hpow < 0 ? -hpow : hpow; for (int i = 0; i < ap; i++) hpq *= hq; if (hpow < 0) hpq = 1.0 / hpq; }
+    double* m = mp + 7 * l;
+    m[0] = x1[0]; m[1] = x1[1]; m[2] = x1[2]; m[3] = x2[0]; m[4] = x2[1]; m[5] = x2[2];
+    m[6] = coef * hpq * (w1 * measq);
+  }
+  __syncwarp();
+}
+
 constexpr int FP_MAXB = 13;
 
 template <int D, bool DEF>
@@ -192,32 +226,7 @@ __global__ void __launch_bounds__(128) k_facetpatch(
       xg_def_gather<D>(df, e1, lane, defs1);
       xg_def_gather<D>(df, e2, lane, defs2);
       __syncwarp();
-      if (lane == 0) patch_consts<D>(vx2, F2, v2, defs2, df.order, pcs);
-      if (lane == 1) patch_consts<D>(vx1, F1, v1, defs1, df.order, pcs + 16);
-      __syncwarp();
-      // Newton mapping of every patch point, all lanes busy, once per facet (not once per accumulator panel)
-      for (int l = lane; l < 2 * np; l += 32) {
-        double x1[3], x2[3], x[3], w1, wd;
-        if (l < np) {
-          x1[0] = rp[3 * l]; x1[1] = rp[3 * l + 1]; x1[2] = rp[3 * l + 2];
-          w1 = rw[l];
-          map_patch_def<D>(vx1, F1, v1, defs1, vx2, F2, v2, defs2, df.order, pcs, x1, w1, x2, &wd);
-        } else {
-          const int q = l - np;
-          x2[0] = rp[3 * q]; x2[1] = rp[3 * q + 1]; x2[2] = rp[3 * q + 2];
-          map_patch_def<D>(vx2, F2, v2, defs2, vx1, F1, v1, defs1, df.order, pcs + 16, x2, rw[q], x1, &w1);
-        }
-        double Fq[D * D], Fiq[D * D];
-        trafo_eval<D>(vx1, F1, v1, df.order, defs1, x1, Fq, x);
-        const double measq = fabs(xg_inv<D>(Fq, Fiq));
-        const double hq = xg_mesh_size<D>(measq);
-        double hpq = 1.0;
-        { const int ap = hpow < 0 ? -hpow : hpow; for (int i = 0; i < ap; i++) hpq *= hq; if (hpow < 0) hpq = 1.0 / hpq; }
-        double* m = mp + 7 * l;
-        m[0] = x1[0]; m[1] = x1[1]; m[2] = x1[2]; m[3] = x2[0]; m[4] = x2[1]; m[5] = x2[2];
-        m[6] = coef * hpq * (w1 * measq);
-      }
-      __syncwarp();
+      fp_map_points<D>(lane, np, rp, rw, vx1, F1, v1, defs1, vx2, F2, v2, defs2, df.order, coef, hpow, pcs, mp);
     }
     const double h = (D == 1) ? meas1 : ((D == 2) ? sqrt(meas1) : cbrt(meas1));
     double hp = 1.0;
@@ -289,6 +298,166 @@ __global__ void __launch_bounds__(128) k_facetpatch(
   }
 }
 
+// ---------------------------------------------------------------- FP64 tensor-core contraction (order >= 3)
+// M = sum_q c_q J_q J_q^T with J_q = [phi^1(x1_q) ; -phi^2(x2_q)] is a GEMM over the patch points: FOUR points are one
+// k-step of the FP64 tensor instruction (mma.sync m8n8k4: A = c J (8 dofs x 4 points), B = J^T), on the symmetric set of
+// 8x8 tiles (north_star (d): the facet-patch matrices reuse the batched contraction of the element matrices).  The jump
+// vectors are staged ONCE per chunk of points (no accumulator panels: the 70x70 matrix of two P4 tets is 45 tile pairs =
+// 90 accumulator registers), row stride = 4 mod 16 doubles so that the four points of a fragment load hit disjoint banks.
+__device__ __forceinline__ void fp_dmma884(double& d0, double& d1, double a, double b)
+{
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+               : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
+}
+
+template <int D, int P>
+struct FpGeom {
+  static constexpr int ND = (D == 2) ? 3 + 3 * (P - 1) + (P - 1) * (P - 2) / 2
+                                     : 4 + 6 * (P - 1) + 4 * ((P - 1) * (P - 2) / 2) + (P - 1) * (P - 2) * (P - 3) / 6;
+  static constexpr int N = 2 * ND, NT = (N + 7) / 8, NDP = 8 * NT;
+  static constexpr int PS = NDP + ((NDP % 16 == 0) ? 4 : 12);  // = 4 mod 16, slot NDP holds the point's weight
+  static constexpr int NPAIR = NT * (NT + 1) / 2;
+};
+
+template <int D, int P, bool DEF>
+__global__ void __launch_bounds__(128) k_facetpatch_dmma(
+    int64_t n, const int32_t* __restrict__ facets, const int32_t* __restrict__ facet_els,
+    const int32_t* __restrict__ el_vtx, const double* __restrict__ vtx_xyz,
+    const double* __restrict__ rp, const double* __restrict__ rw, int np,
+    int CH, double coef, int hpow, double* __restrict__ mats, DefDev df)
+{
+  using G = FpGeom<D, P>;
+  constexpr int ND = G::ND, N = G::N, NT = G::NT, NDP = G::NDP, PS = G::PS, NPAIR = G::NPAIR;
+  extern __shared__ double smem[];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const int fr = lane >> 2, fc = lane & 3;
+  const int npatch = 2 * np, npad = (npatch + 3) & ~3;
+  double* Bw = smem + (size_t)wib * (CH * PS + (DEF ? 2 * XG_DEFS + 32 + 7 * npatch : 0));
+  double* defs1 = Bw + (size_t)CH * PS;
+  double* defs2 = defs1 + XG_DEFS;
+  double* pcs = defs2 + XG_DEFS;
+  double* mp = pcs + 32;
+  const int64_t warp0 = (int64_t)blockIdx.x * (blockDim.x >> 5) + wib;
+  const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
+  for (int64_t f = warp0; f < n; f += nwarps) {
+    const int64_t fac = facets ? (int64_t)facets[f] : f;
+    const int e1 = __ldg(facet_els + 2 * fac), e2 = __ldg(facet_els + 2 * fac + 1);
+    double* M = mats + (size_t)f * N * N;
+    if (e2 < 0) {
+      for (int k = lane; k < N * N; k += 32) M[k] = 0.0;
+      continue;
+    }
+    int v1[D + 1], v2[D + 1];
+    double vx1[D + 1][3], vx2[D + 1][3], F1[D * D], Fi1[D * D], F2[D * D], Fi2[D * D], meas1, meas2;
+    load_geom<D>(el_vtx, vtx_xyz, e1, v1, vx1, F1, Fi1, &meas1);
+    load_geom<D>(el_vtx, vtx_xyz, e2, v2, vx2, F2, Fi2, &meas2);
+    if (DEF) {
+      __syncwarp();
+      xg_def_gather<D>(df, e1, lane, defs1);
+      xg_def_gather<D>(df, e2, lane, defs2);
+      __syncwarp();
+      fp_map_points<D>(lane, np, rp, rw, vx1, F1, v1, defs1, vx2, F2, v2, defs2, df.order, coef, hpow, pcs, mp);
+    }
+    const double h = xg_mesh_size<D>(meas1);
+    double hp = 1.0;
+    { const int ap = hpow < 0 ? -hpow : hpow; for (int i = 0; i < ap; i++) hp *= h; if (hpow < 0) hp = 1.0 / hp; }
+    double acc[NPAIR][2];
+#pragma unroll
+    for (int b = 0; b < NPAIR; b++) acc[b][0] = acc[b][1] = 0.0;
+    for (int c0 = 0; c0 < npad; c0 += CH) {
+      const int cs = min(CH, npad - c0);  // multiple of 4
+      __syncwarp();
+      if (lane < cs) {
+        const int l = c0 + lane;
+        double* B = Bw + (size_t)lane * PS;
+        if (l >= npatch) {
+          for (int i = 0; i <= NDP; i++) B[i] = 0.0;  // padding point: weight 0
+        } else {
+          double x1[3], x2[3], x[3], w;
+          if (DEF) {
+            const double* m = mp + 7 * l;
+            x1[0] = m[0]; x1[1] = m[1]; x1[2] = m[2]; x2[0] = m[3]; x2[1] = m[4]; x2[2] = m[5];
+            w = m[6];
+          } else if (l < np) {
+            x1[0] = rp[3 * l]; x1[1] = rp[3 * l + 1]; x1[2] = rp[3 * l + 2];
+            map_fwd<D>(vx1, x1, x);
+            map_inv<D>(vx2, Fi2, x, x2);
+            w = coef * hp * (rw[l] * meas1);
+          } else {
+            const int q = l - np;
+            x2[0] = rp[3 * q]; x2[1] = rp[3 * q + 1]; x2[2] = rp[3 * q + 2];
+            map_fwd<D>(vx2, x2, x);
+            map_inv<D>(vx1, Fi1, x, x1);
+            w = coef * hp * (rw[q] * meas2);
+          }
+#pragma unroll
+          for (int i = N; i < NDP; i++) B[i] = 0.0;
+          ValSink s1{B, 1.0}, s2{B + ND, -1.0};
+          xg_h1_shapes<D, P>(v1, x1, s1);
+          xg_h1_shapes<D, P>(v2, x2, s2);
+          B[NDP] = w;
+        }
+      }
+      __syncwarp();
+      for (int q = 0; q < cs; q += 4) {
+        const double* Sq = Bw + (size_t)(q + fc) * PS;
+        const double wq = Sq[NDP];
+        double sv[NT], av[NT];
+#pragma unroll
+        for (int t = 0; t < NT; t++) { sv[t] = Sq[8 * t + fr]; av[t] = wq * sv[t]; }
+        int idx = 0;
+#pragma unroll
+        for (int ti = 0; ti < NT; ti++)
+#pragma unroll
+          for (int tj = ti; tj < NT; tj++, idx++) fp_dmma884(acc[idx][0], acc[idx][1], av[ti], sv[tj]);
+      }
+    }
+    {  // tiles -> global (upper tiles and their mirror images)
+      int idx = 0;
+#pragma unroll
+      for (int ti = 0; ti < NT; ti++)
+#pragma unroll
+        for (int tj = ti; tj < NT; tj++, idx++) {
+          const int i = 8 * ti + fr, j = 8 * tj + 2 * fc;
+          if (i < N) {
+            if (j < N) M[i * N + j] = acc[idx][0];
+            if (j + 1 < N) M[i * N + j + 1] = acc[idx][1];
+            if (ti != tj) {
+              if (j < N) M[j * N + i] = acc[idx][0];
+              if (j + 1 < N) M[(j + 1) * N + i] = acc[idx][1];
+            }
+          }
+        }
+    }
+  }
+}
+
+template <int D, int P>
+int launch_fp_dmma(xgpu_ctx* ctx, int64_t n, const int32_t* facets, const int32_t* facet_els, const int32_t* el_vtx,
+                   const double* vtx_xyz, const xgpu_rule_host* r, double coef, int hpow, double* mats)
+{
+  using G = FpGeom<D, P>;
+  const DefDev df = xg_defdev(ctx, D);
+  const size_t extra = df.order > 0 ? (size_t)(2 * XG_DEFS + 32 + 7 * 2 * r->n) : 0;  // doubles per warp
+  int CH = 32;
+  while (CH > 8 && (size_t)4 * (CH * G::PS + extra) * sizeof(double) > 110 * 1024) CH >>= 1;
+  const size_t sm = (size_t)4 * (CH * G::PS + extra) * sizeof(double);
+  if (sm > 220 * 1024) return xgpu_fail(ctx, XGPU_ERR_CAPACITY, "xgpu_facetpatch: patch rule too large for the shared-memory staging");
+  unsigned grid = nblk(n, 4);
+  if (grid > XGPU_NSM * 8) grid = XGPU_NSM * 8;
+  if (df.order > 0) {
+    XGPU_CUDA(ctx, cudaFuncSetAttribute(k_facetpatch_dmma<D, P, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+    k_facetpatch_dmma<D, P, true><<<grid, 128, sm, ctx->stream>>>(n, facets, facet_els, el_vtx, vtx_xyz, r->d_pts, r->d_wts, r->n,
+                                                                  CH, coef, hpow, mats, df);
+  } else {
+    XGPU_CUDA(ctx, cudaFuncSetAttribute(k_facetpatch_dmma<D, P, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+    k_facetpatch_dmma<D, P, false><<<grid, 128, sm, ctx->stream>>>(n, facets, facet_els, el_vtx, vtx_xyz, r->d_pts, r->d_wts, r->n,
+                                                                   CH, coef, hpow, mats, df);
+  }
+  XGPU_LAUNCH_CHECK(ctx);
+  return XGPU_OK;
+}
+
 }  // namespace
 
 extern "C" int xgpu_facetpatch(xgpu_ctx* ctx, int dim, int fe_order, int64_t n, const int32_t* facets,
@@ -301,6 +470,13 @@ extern "C" int xgpu_facetpatch(xgpu_ctx* ctx, int dim, int fe_order, int64_t n, 
   if (order < 0) order = 2 * fe_order;  // symboliccutbfi.cpp:2004-2012
   const xgpu_rule_host* r = xgpu_rule_lookup(ctx, dim, order);
   if (!r) return xgpu_fail(ctx, XGPU_ERR_ARG, "xgpu_facetpatch: no rule");
+  if (fe_order >= 3 && dim >= 2 && ctx->opt_dmma >= 0) {
+    // dense contraction: FP64 tensor tiles (xgpu_set_option("elmat_dmma", -1) forces the CUDA-core kernel)
+    if (dim == 3 && fe_order == 3) return launch_fp_dmma<3, 3>(ctx, n, facets, facet_els, el_vtx, vtx_xyz, r, coef, hpow, mats);
+    if (dim == 3 && fe_order == 4) return launch_fp_dmma<3, 4>(ctx, n, facets, facet_els, el_vtx, vtx_xyz, r, coef, hpow, mats);
+    if (dim == 2 && fe_order == 3) return launch_fp_dmma<2, 3>(ctx, n, facets, facet_els, el_vtx, vtx_xyz, r, coef, hpow, mats);
+    if (dim == 2 && fe_order == 4) return launch_fp_dmma<2, 4>(ctx, n, facets, facet_els, el_vtx, vtx_xyz, r, coef, hpow, mats);
+  }
   const int nd = xg_h1_ndof(dim, fe_order);
   const int Np = (2 * nd + 1) & ~1, PS = Np + 1;
   const DefDev df = xg_defdev(ctx, dim);

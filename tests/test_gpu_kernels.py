@@ -426,3 +426,31 @@ def test_elmat_rule_pair_equals_two_accumulating_passes(dim, n, p):
     mo = xo.batch_cut_elmats(dim, p, lo, els, pts, phi.cpu().numpy(), xo.NEG, 2 * p, TV)
     mo += xo.batch_cut_elmats(dim, p, lo, els, pts, phi.cpu().numpy(), xo.IF, 2 * p, TI)
     assert np.linalg.norm(pair.cpu().numpy() - mo) <= 1e-12 * np.linalg.norm(mo)
+
+
+@pytest.mark.parametrize("dim,n,p", [(3, 2, 4), (2, 4, 4), (3, 2, 3)])
+def test_facetpatch_tensor_tiles_match_cuda_core_kernel_and_oracle(dim, n, p):
+    """order >= 3: the facet-patch contraction on FP64 tensor tiles (4 patch points per DMMA k-step) against the
+    CUDA-core rank-1 kernel (elmat_dmma = -1) and the oracle"""
+    m = make_mesh(dim, n)
+    pts, els = mesh_np(m)
+    rng = np.random.default_rng(5)
+    pts = pts + 0.1 / n * rng.random(pts.shape)
+    m = meshes.Mesh(torch.from_numpy(pts), m.elements)
+    md = to_dev(m)
+    _, _, fe = md.facets()
+    fe_np = fe.cpu().numpy()
+    sel = np.nonzero(fe_np[:, 1] >= 0)[0].astype(np.int32)[:: 3]
+    ctx = ops.default_ctx()
+    out = {}
+    for mode in (0, -1):
+        ctx.set_option("elmat_dmma", mode)
+        try:
+            out[mode] = ops.facetpatch(dim, p, torch.from_numpy(sel).to(DEV), fe, md.elements, md.points, -1, 0.37, -2).cpu().numpy()
+        finally:
+            ctx.set_option("elmat_dmma", 0)
+    o, nfail = xo.batch_facet_patch(dim, p, sel, fe_np, els, pts, -1, 0.37, -2)
+    assert nfail == 0
+    assert rel_err(out[0], o) < 1e-12 and rel_err(out[-1], o) < 1e-12
+    assert rel_err(out[0], out[-1]) < 1e-13
+    assert np.allclose(out[0], out[0].transpose(0, 2, 1), rtol=1e-13, atol=1e-15 * np.abs(o).max())
