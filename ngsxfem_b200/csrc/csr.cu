@@ -178,7 +178,7 @@ __global__ void __launch_bounds__(256) k_pattern(int ndof, const long long* __re
                                                  const long long* __restrict__ adj, BatchDev bd, int HCAP, int SL, int G,
                                                  const long long* __restrict__ candoff,
                                                  int32_t* __restrict__ tmpcol, int32_t* __restrict__ rowcnt,
-                                                 int* __restrict__ stats, int small_max)
+                                                 int* __restrict__ stats, int small_max, int big_max)
 {
   extern __shared__ int sbuf[];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
@@ -190,7 +190,7 @@ __global__ void __launch_bounds__(256) k_pattern(int ndof, const long long* __re
   for (int d = warp0; d < ndof; d += nwarps) {
     const long long o = candoff[d];
     const int cand = (int)(candoff[d + 1] - o);
-    if (cand <= small_max) continue;  // rows of k_pattern_small (it also writes the empty rows)
+    if (cand <= small_max || cand > big_max) continue;  // rows of k_pattern_small (it also writes the empty rows) / of another size class
     if (cand == 0) { if (lane == 0) rowcnt[d] = 0; continue; }
     // table size: power of two >= 1.25 * candidates (duplicates keep the load far lower)
     int H = 32, shift = 27;
@@ -419,7 +419,7 @@ __global__ void __launch_bounds__(256) k_scatter(int ndof, const long long* __re
                                                  const long long* __restrict__ adj, BatchDev bd, int RCAP, int HS, int GS,
                                                  int NG, int trips, const long long* __restrict__ rowptr,
                                                  const int32_t* __restrict__ colidx, double* __restrict__ vals, int small_nr,
-                                                 const long long* __restrict__ src_off, int32_t* __restrict__ col_out)
+                                                 int big_nr, const long long* __restrict__ src_off, int32_t* __restrict__ col_out)
 {
   extern __shared__ double sacc[];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, nwb = blockDim.x >> 5;
@@ -438,7 +438,7 @@ __global__ void __launch_bounds__(256) k_scatter(int ndof, const long long* __re
     if (have) {
       r0 = rowptr[d]; nr = (int)(rowptr[d + 1] - r0);
       a = adj_ptr[d]; na = (int)(adj_ptr[d + 1] - a);
-      if (nr <= small_nr) { nr = 0; na = 0; }  // empty rows, and the short rows of k_scatter_small
+      if (nr <= small_nr || nr > big_nr) { nr = 0; na = 0; }  // empty rows, the short rows of k_scatter_small, other size classes
     }
     // hash size for this row: power of two >= 1.5 * nr (<= HS by the host's sizing)
     int H = 16, shift = 28;
@@ -686,16 +686,8 @@ int run_pattern(xgpu_ctx* ctx, xgpu_plan* P, int* stats)
   void* sp;
   int rc = xgpu_scratch(ctx, 8, sizeof(int32_t) * (size_t)(P->ncand > 0 ? P->ncand : 1), &sp);
   if (rc) return rc;
-  int HCAP = 64;
-  while (HCAP < 2 * P->maxcand) HCAP <<= 1;
-  int nw = 8;
-  while (nw > 1 && (size_t)nw * (HCAP + 4) * sizeof(int) > 200 * 1024) nw >>= 1;
-  const size_t sm = (size_t)nw * (HCAP + 4) * sizeof(int);
-  if (sm > 220 * 1024) return xgpu_fail(ctx, XGPU_ERR_CAPACITY, "csr: a row has too many candidate columns");
   int SL, G, trips;
   lane_split(P->wmax, &SL, &G, &trips);
-  unsigned grid = nblk(P->ndof, nw);
-  if (grid > XGPU_NSM * 32) grid = XGPU_NSM * 32;
   {  // short rows first: thread per row
     unsigned gs = nblk(P->ndof, XG_SMALL_BLOCK);
     if (gs > XGPU_NSM * 64) gs = XGPU_NSM * 64;
@@ -703,17 +695,33 @@ int run_pattern(xgpu_ctx* ctx, xgpu_plan* P, int* stats)
     else k_pattern_small<false><<<gs, XG_SMALL_BLOCK, 0, ctx->stream>>>((int)P->ndof, P->adj_ptr, P->adj, P->bd, P->candoff, (int32_t*)sp, P->tmp32, stats);
     XGPU_LAUNCH_CHECK(ctx);
   }
-  if (P->maxcand > XG_SMALL_CAND) {
+  // warp-per-row classes by candidate count.  The hash table of a warp is sized for the LONGEST row of its class, and
+  // the shared memory per warp decides the occupancy: with facet-patch batches a few rows have thousands of candidates
+  // (config 3: ~5000) — sizing every warp for them leaves 2 warps per SM.  Rows up to 1023 candidates get their own
+  // launch with 2048-slot tables (8 warps per block, several blocks per SM), only the rest pays for the big tables.
+  const int MID = 1023;
+  int lo = XG_SMALL_CAND;
+  while (P->maxcand > lo) {
+    const int hi = (P->maxcand > MID && lo < MID) ? MID : P->maxcand;
+    int HCAP = 64;
+    while (HCAP < 2 * hi) HCAP <<= 1;
+    int nw = 8;
+    while (nw > 1 && (size_t)nw * (HCAP + 4) * sizeof(int) > 200 * 1024) nw >>= 1;
+    const size_t sm = (size_t)nw * (HCAP + 4) * sizeof(int);
+    if (sm > 220 * 1024) return xgpu_fail(ctx, XGPU_ERR_CAPACITY, "csr: a row has too many candidate columns");
+    unsigned grid = nblk(P->ndof, nw);
+    if (grid > XGPU_NSM * 32) grid = XGPU_NSM * 32;
     if (P->dups) {
       XGPU_CUDA(ctx, cudaFuncSetAttribute(k_pattern<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
       k_pattern<true><<<grid, nw * 32, sm, ctx->stream>>>((int)P->ndof, P->adj_ptr, P->adj, P->bd, HCAP, SL, G, P->candoff,
-                                                          (int32_t*)sp, P->tmp32, stats, XG_SMALL_CAND);
+                                                          (int32_t*)sp, P->tmp32, stats, lo, hi);
     } else {
       XGPU_CUDA(ctx, cudaFuncSetAttribute(k_pattern<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
       k_pattern<false><<<grid, nw * 32, sm, ctx->stream>>>((int)P->ndof, P->adj_ptr, P->adj, P->bd, HCAP, SL, G, P->candoff,
-                                                           (int32_t*)sp, P->tmp32, stats, XG_SMALL_CAND);
+                                                           (int32_t*)sp, P->tmp32, stats, lo, hi);
     }
     XGPU_LAUNCH_CHECK(ctx);
+    lo = hi;
   }
   P->epoch = ++ctx->epoch;
   return XGPU_OK;
@@ -881,19 +889,8 @@ static int run_scatter(xgpu_ctx* ctx, xgpu_plan* P, const xgpu_batch* batches_ho
     bd.mats[i] = batches_host[i].mats;  // NULL: the batch only contributes sparsity
   }
   if (P->ndof == 0 || P->nnz == 0) return XGPU_OK;
-  const int RCAP = std::max(32, (P->maxnr + 31) & ~31);
-  int HS = 16;
-  while (HS < P->maxnr + (P->maxnr >> 1)) HS <<= 1;
-  if (HS > 65536) return xgpu_fail(ctx, XGPU_ERR_CAPACITY, "csr: a row is too long for the shared-memory gather");
   int SL, G, trips;
   lane_split(P->wmax, &SL, &G, &trips);
-  const size_t per_warp = ((size_t)RCAP * 8 + (size_t)HS * 6) * G;
-  int nw = 8;
-  while (nw > 1 && nw * per_warp > 200 * 1024) nw >>= 1;
-  const size_t sm = nw * per_warp;
-  if (sm > 220 * 1024) return xgpu_fail(ctx, XGPU_ERR_CAPACITY, "csr: a row is too long for the shared-memory gather");
-  unsigned grid = nblk(P->ndof, nw * G);
-  if (grid > XGPU_NSM * 32) grid = XGPU_NSM * 32;
   {  // short rows: thread per row
     unsigned gs = nblk(P->ndof, XG_SMALL_BLOCK);
     if (gs > XGPU_NSM * 64) gs = XGPU_NSM * 64;
@@ -903,17 +900,35 @@ static int run_scatter(xgpu_ctx* ctx, xgpu_plan* P, const xgpu_batch* batches_ho
                                                               src_off, col_out);
     XGPU_LAUNCH_CHECK(ctx);
   }
-  if (P->maxnr <= XG_SMALL_NR) return XGPU_OK;
-  if (P->dups) {
-    XGPU_CUDA(ctx, cudaFuncSetAttribute(k_scatter<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-    k_scatter<true><<<grid, nw * 32, sm, ctx->stream>>>((int)P->ndof, P->adj_ptr, P->adj, bd, RCAP, HS, SL, G, trips,
-                                                        (const long long*)rowptr, colidx, vals, XG_SMALL_NR, src_off, col_out);
-  } else {
-    XGPU_CUDA(ctx, cudaFuncSetAttribute(k_scatter<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-    k_scatter<false><<<grid, nw * 32, sm, ctx->stream>>>((int)P->ndof, P->adj_ptr, P->adj, bd, RCAP, HS, SL, G, trips,
-                                                         (const long long*)rowptr, colidx, vals, XG_SMALL_NR, src_off, col_out);
+  // warp-group-per-row classes by row length (the accumulators + slot hash of a group are sized for the longest row of
+  // the class; see run_pattern): rows up to 255 entries, then the rest
+  const int MID = 255;
+  int lo = XG_SMALL_NR;
+  while (P->maxnr > lo) {
+    const int hi = (P->maxnr > MID && lo < MID) ? MID : P->maxnr;
+    const int RCAP = std::max(32, (hi + 31) & ~31);
+    int HS = 16;
+    while (HS < hi + (hi >> 1)) HS <<= 1;
+    if (HS > 65536) return xgpu_fail(ctx, XGPU_ERR_CAPACITY, "csr: a row is too long for the shared-memory gather");
+    const size_t per_warp = ((size_t)RCAP * 8 + (size_t)HS * 6) * G;
+    int nw = 8;
+    while (nw > 1 && nw * per_warp > 200 * 1024) nw >>= 1;
+    const size_t sm = nw * per_warp;
+    if (sm > 220 * 1024) return xgpu_fail(ctx, XGPU_ERR_CAPACITY, "csr: a row is too long for the shared-memory gather");
+    unsigned grid = nblk(P->ndof, nw * G);
+    if (grid > XGPU_NSM * 32) grid = XGPU_NSM * 32;
+    if (P->dups) {
+      XGPU_CUDA(ctx, cudaFuncSetAttribute(k_scatter<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+      k_scatter<true><<<grid, nw * 32, sm, ctx->stream>>>((int)P->ndof, P->adj_ptr, P->adj, bd, RCAP, HS, SL, G, trips,
+                                                          (const long long*)rowptr, colidx, vals, lo, hi, src_off, col_out);
+    } else {
+      XGPU_CUDA(ctx, cudaFuncSetAttribute(k_scatter<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+      k_scatter<false><<<grid, nw * 32, sm, ctx->stream>>>((int)P->ndof, P->adj_ptr, P->adj, bd, RCAP, HS, SL, G, trips,
+                                                           (const long long*)rowptr, colidx, vals, lo, hi, src_off, col_out);
+    }
+    XGPU_LAUNCH_CHECK(ctx);
+    lo = hi;
   }
-  XGPU_LAUNCH_CHECK(ctx);
   return XGPU_OK;
 }
 
