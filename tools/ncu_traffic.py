@@ -30,8 +30,13 @@ def main():
     def val(r, k):
         return float(r[col[k]].replace(",", "")) * UNIT[units[col[k]]]
 
+    # one step = the launches from one k_classify to the next (the capture window may start in the middle of a step)
+    body = rows[2:]
+    starts = [i for i, r in enumerate(body) if "k_classify" in r[ik]]
+    if starts:
+        body = body[starts[0]:(starts[1] if len(starts) > 1 else len(body))]
     phases, kernels = {}, {}
-    for r in rows[2:]:
+    for r in body:
         name = r[ik]
         short = name.split("(")[0].replace("void ", "").replace("<unnamed>::", "")
         b = val(r, "dram__bytes_read.sum") + val(r, "dram__bytes_write.sum")
