@@ -1,0 +1,102 @@
+"""BASELINE.json configs 3, 4 and 5 at (single-GPU) scale, checked through size-independent properties — the oracle
+would need minutes at these sizes (config 2 at full size: tests/test_pipeline.py::test_full_size_invariants).
+
+config 3: order-4 isoparametric stiffness + ghost penalty on a torus, 384 000 tets: constants are in the kernel of both
+          operators on ANY deformed mesh (grad 1 = 0, jump of 1 = 0): |A 1| = 0 up to rounding; A symmetric.
+config 4: multi-level-set domain, order 3, 1.57 M tets: 1^T M 1 = |domain| (order-0 multi-level-set rule), K 1 = 0.
+config 5: space-time cut rules P1 x P2 on 6 367 248 tets (the size BASELINE names): NEG + POS measure = 1 exactly,
+          NEG measure = ball volume up to the P1/P2 interface error."""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+import ngsxfem_b200 as xf
+from ngsxfem_b200 import ops
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+NEG, POS, IF = 0, 1, 2
+
+
+
+
+def test_config3_isoparametric_ghost_penalty_kernel_of_constants():
+    n, k = 40, 4
+    mesh = xf.MakeStructured3DMesh(nx=n, device=DEV)
+    lset = xf.InterpolateToP1(lambda x, y, z: (torch.sqrt((x - .5) ** 2 + (y - .5) ** 2) - 0.28) ** 2 + (z - .5) ** 2 - 0.12 ** 2, mesh)
+    V0 = xf.H1(mesh, order=k, dgjumps=True)
+    g = torch.Generator().manual_seed(7)
+    defo = xf.Deformation(xf.H1(mesh, order=k), ((torch.rand((V0.ndof, 3), generator=g, dtype=torch.float64) - 0.5) * (0.004 / n)).to(DEV))
+    ci = xf.CutInfo(mesh, lset)
+    hasneg, hasif = ci.GetElementsOfType(xf.HASNEG), ci.GetElementsOfType(xf.IF)
+    gpf = xf.GetFacetsWithNeighborTypes(mesh, a=hasneg, b=hasif, use_and=True)
+    V = xf.Restrict(V0, hasneg)
+    u, v = V.TnT()
+    h = xf.specialcf.mesh_size
+    a = xf.RestrictedBilinearForm(V, element_restriction=hasneg, facet_restriction=gpf)
+    a += (xf.grad(u) * xf.grad(v)) * xf.dCut(lset, xf.NEG, definedonelements=hasneg, deformation=defo)
+    a += (0.1 / h ** 2) * (u - u.Other()) * (v - v.Other()) * xf.dFacetPatch(definedonelements=gpf, deformation=defo)
+    a.Assemble()
+    assert hasif.NumSet() > 10000 and gpf.NumSet() > 20000
+    rows = V.rows(hasneg.indices())
+    one = torch.zeros(V.ndof, dtype=torch.float64, device=DEV)
+    one[rows[:, :4].reshape(-1).long()] = 1.0          # u = 1: vertex dofs 1, all higher-order dofs 0
+    y = a.mat * one
+    scale = float(a.mat.vals.abs().max())
+    assert float(y.abs().max()) < 1e-10 * scale
+    x = torch.rand(V.ndof, generator=torch.Generator().manual_seed(1), dtype=torch.float64).to(DEV)
+    z = torch.rand(V.ndof, generator=torch.Generator().manual_seed(2), dtype=torch.float64).to(DEV)
+    s1, s2 = float((z * (a.mat * x)).sum()), float((x * (a.mat * z)).sum())
+    assert abs(s1 - s2) < 1e-11 * abs(s1)              # symmetric operator
+
+
+def test_config4_mlset_order3_volume_and_constants():
+    n = 64
+    mesh = xf.MakeStructured3DMesh(nx=n, device=DEV)
+    x, y, z = (mesh.points[:, i] for i in range(3))
+    fns = [x + 0.31 * y - 0.83, -0.27 * x + y + 0.11 * z - 0.79, 0.13 * x - 0.21 * y + z - 0.81,
+           torch.sqrt((x - .4) ** 2 + (y - .45) ** 2 + (z - .4) ** 2) - 0.37]
+    lsets = [xf.GridFunction(mesh, torch.where(f.abs() < 1e-14, torch.full_like(f, 1e-14), f).contiguous()) for f in fns]
+    dts = (NEG, NEG, NEG, NEG)
+    active = xf.MultiLevelsetCutInfo(mesh, lsets).GetElementsWithContribution(dts)
+    V = xf.Restrict(xf.H1(mesh, order=3), active)
+    u, v = V.TnT()
+
+    def assemble(form):
+        a = xf.RestrictedBilinearForm(V, element_restriction=active)
+        a += form * xf.dCut(lsets, dts, definedonelements=active)
+        return a.Assemble()
+
+    m, kk = assemble(u * v), assemble(xf.grad(u) * xf.grad(v))
+    rows = V.rows(active.indices())
+    one = torch.zeros(V.ndof, dtype=torch.float64, device=DEV)
+    one[rows[:, :4].reshape(-1).long()] = 1.0
+    vol = xf.Integrate({"levelset": lsets, "domain_type": dts}, mesh=mesh, cf=1.0, order=0)
+    tot = float((one * (m.mat * one)).sum())
+    assert active.NumSet() > 300000
+    assert abs(tot - vol) < 1e-11 * vol
+    assert float((kk.mat * one).abs().max()) < 1e-10 * float(kk.mat.vals.abs().max())
+
+
+def test_config5_spacetime_rules_full_size():
+    n, r = 102, 0.3
+    mesh = xf.MakeStructured3DMesh(nx=n, device=DEV)
+    assert mesh.ne == 6367248
+    phis = []
+    for tn in (0.0, 0.5, 1.0):
+        cy = 0.5 + 0.1 * math.sin(2 * math.pi * tn)
+        f = torch.sqrt((mesh.points[:, 0] - .5) ** 2 + (mesh.points[:, 1] - cy) ** 2 + (mesh.points[:, 2] - .5) ** 2) - r
+        phis.append(torch.where(f.abs() < 1e-14, torch.full_like(f, 1e-14), f))
+    phi_st = torch.stack(phis).contiguous()
+    res = {}
+    for dt in (NEG, POS):
+        off, q, tv, w = ops.cutquad_st(3, None, mesh.elements, mesh.points, phi_st, 2, dt, 4, 2)
+        assert ops.default_ctx().status()[0] == 0
+        assert float(tv.min()) >= 0.0 and float(tv.max()) <= 1.0
+        res[dt] = ops.integrate_monomial(3, None, mesh.elements, mesh.points, off, q, w, (0, 0, 0))
+        del off, q, tv, w
+    assert abs(res[NEG] + res[POS] - 1.0) < 1e-11
+    ball = 4.0 / 3.0 * math.pi * r ** 3
+    assert abs(res[NEG] - ball) < 2e-3 * ball
