@@ -326,6 +326,53 @@ class GpuBackend:
         return ops.csr_assemble(plan, batches)
 
 
+class MlsetGpuBackend(GpuBackend):
+    """config 4 of BASELINE.json: a multi-level-set domain (cutint/mlsetintegration.cpp:6-186) assembled element-partitioned.
+    `phi` of DistributedCutAssembly.step is the M x nv_local matrix of nodal level-set values.  Active elements = elements
+    with contribution (xfem/cutinfo.cpp:306-334: positive weight sum of the order -1 multi-level-set rule); every active
+    element gets its rule from xgpu_cutquad_ml_* (uncut relevant elements: the standard rule), forms: grad.grad + u v."""
+
+    def __init__(self, dts, ctx=None):
+        super().__init__(ctx)
+        self.dts = [tuple(int(d) for d in t) for t in dts]
+
+    def classify(self, el_vtx, phis):
+        ops, ctx = self.ops, self.ctx
+        dim, ne = el_vtx.shape[1] - 1, el_vtx.shape[0]
+        off, pts, wts = ops.cutquad_ml(dim, None, el_vtx, self._xyz, phis, self.dts, -1, ctx=ctx)
+        ctx.raise_on_geometry_error()
+        seg = torch.zeros(ne, dtype=torch.float64, device=el_vtx.device)
+        if wts.numel():
+            seg.index_add_(0, torch.repeat_interleave(torch.arange(ne, device=el_vtx.device), off[1:] - off[:-1]), wts)
+        act = seg > 0
+        # pack into BitArray words (bit i = word i >> 5, bit i & 31)
+        pad = (-ne) % 32
+        bits = torch.cat([act, torch.zeros(pad, dtype=torch.bool, device=act.device)]).reshape(-1, 32).to(torch.int64)
+        words = (bits << torch.arange(32, device=act.device, dtype=torch.int64)).sum(1)
+        words = torch.where(words >= 2 ** 31, words - 2 ** 32, words).to(torch.int32).contiguous()
+        zero = torch.zeros_like(words)
+        l_act = torch.nonzero(act).reshape(-1).to(torch.int32)
+        return l_act, l_act[:0], (words, zero, zero.clone(), None)
+
+    def elmats(self, part, phis, l_act, l_none):
+        from .pipeline import TERMS_VOL
+        ops, ctx, dim, p = self.ops, self.ctx, part.dim, part.fe_order
+        els, xyz = part.el_vtx, part.vtx_xyz
+        l_act = l_act.contiguous()
+        nd = ops.h1_ndof(dim, p)
+        m = torch.zeros((l_act.numel(), nd, nd), dtype=torch.float64, device=els.device)
+        if l_act.numel():
+            off, q, w = ops.cutquad_ml(dim, l_act, els, xyz, phis, self.dts, 2 * p, ctx=ctx)
+            ctx.raise_on_geometry_error()
+            if w.numel():
+                ops.elmat_rule(dim, p, l_act, els, xyz, phis[0].contiguous(), off, q, w, TERMS_VOL, out=m, ctx=ctx)
+        return m, torch.zeros((0, nd, nd), dtype=torch.float64, device=els.device)
+
+    def bind(self, part):
+        self._xyz = part.vtx_xyz
+        return self
+
+
 # ------------------------------------------------------------------ slab partition of the structured chain (input producer)
 def make_slab_partition(n, world, rank, device, fe_order=2, radius=0.4):
     """Chain [0,1]^2 x [0,world] of `world` unit cubes, n^3 x 6 Kuhn tets each; rank r owns cube r

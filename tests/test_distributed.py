@@ -132,3 +132,87 @@ def _run_and_check(tmp_path, world, n, fe_order, gpu):
             assert np.allclose(v_d[o], v_ref, rtol=1e-12, atol=1e-13 * scale)
             nnz += len(c_ref)
     assert nnz == ref["nnz"]
+
+
+# ------------------------------------------------------------------ config 4: multi-level-set domain, element-partitioned
+def _mlset_values(pts, world):
+    """cube-chain ∩ 3 planes ∩ sphere around the interface of ranks 0 and 1 (so that interface rows are active)"""
+    x, y, z = pts[:, 0], pts[:, 1], pts[:, 2]
+    fns = [x + 0.31 * y - 0.83, -0.27 * x + y + 0.11 * (z - 0.6) - 0.79, 0.13 * x - 0.21 * y + (z - 0.6) - 0.81,
+           torch.sqrt((x - .4) ** 2 + (y - .45) ** 2 + (z - 1.0) ** 2) - 0.37]
+    return torch.stack([torch.where(f.abs() < 1e-14, torch.full_like(f, 1e-14), f) for f in fns]).contiguous()
+
+
+def _mlset_worker(rank, world, n, port, out):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    try:
+        from ngsxfem_b200.distributed import DistributedCutAssembly, MlsetGpuBackend, make_slab_partition
+        part, _ = make_slab_partition(n, world, rank, dev, fe_order=2)
+        be = MlsetGpuBackend([(0, 0, 0, 0)]).bind(part)
+        asm = DistributedCutAssembly(part, be, rank, world)
+        res = asm.step(_mlset_values(part.vtx_xyz, world))
+        rows_g, rp, cols_g, vals = asm.owned_rows_global(res)
+        a, b = part.range_of[rank]
+        own_ids = a + torch.nonzero(res["dofmap"][a:b] >= 0).reshape(-1)
+        torch.save(dict(rows=rows_g.cpu(), rowptr=rp.cpu(), cols=cols_g.cpu(), vals=vals.cpu(), keys=part.gid.cpu()[own_ids.cpu()],
+                        units=res["units"], ndof_global=res["ndof_global"]), os.path.join(out, f"rank{rank}.pt"))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.gpu
+def test_nccl_mlset_domain_partitioned_equals_single_gpu(tmp_path):
+    """BASELINE config 4 shape: the multi-level-set domain assembled on 2 GPUs (halo layer, NCCL interface rows) equals the
+    single-GPU RestrictedBilinearForm.Assemble of the whole chain, row by row through the global dof keys"""
+    world, n = 2, 5
+    if torch.cuda.device_count() < world:
+        pytest.skip("needs 2 GPUs")
+    import ngsxfem_b200 as xf
+    port = 29500 + (os.getpid() % 2000) + 11
+    mp.spawn(_mlset_worker, args=(world, n, port, str(tmp_path)), nprocs=world, join=True)
+    # single-GPU reference on the whole chain
+    dev = torch.device("cuda", 0)
+    mesh = xf.MakeStructured3DMesh(nx=n, ny=n, nz=n * world, device=dev)
+    nv1 = n + 1
+    pts = mesh.points.clone()
+    K = torch.arange(mesh.nv, device=dev, dtype=torch.int64) // (nv1 * nv1)
+    pts[:, 2] = K.to(torch.float64) / n
+    gmesh = xf.Mesh(pts, mesh.elements)
+    phis = _mlset_values(pts, world)
+    lsets = [xf.GridFunction(gmesh, phis[i]) for i in range(4)]
+    dts = (0, 0, 0, 0)
+    active = xf.MultiLevelsetCutInfo(gmesh, lsets).GetElementsWithContribution(dts)
+    V0 = xf.H1(gmesh, order=2)
+    V = xf.Restrict(V0, active)
+    u, v = V.TnT()
+    a = xf.RestrictedBilinearForm(V, element_restriction=active)
+    a += (xf.grad(u) * xf.grad(v) + u * v) * xf.dCut(lsets, dts, definedonelements=active)
+    a.Assemble()
+    NV = nv1 * nv1 * (n * world + 1)
+    ev, _ = gmesh.edges()
+    ea, eb = ev[:, 0].long(), ev[:, 1].long()
+    gid = torch.cat([torch.arange(gmesh.nv, device=dev, dtype=torch.int64), NV + torch.minimum(ea, eb) * NV + torch.maximum(ea, eb)])
+    keys = gid[V.dofmap >= 0].cpu().numpy()            # compressed id -> key (ascending compression)
+    rp, col, val = (t.cpu().numpy() for t in (a.mat.rowptr, a.mat.col, a.mat.vals))
+    parts = [torch.load(os.path.join(str(tmp_path), f"rank{r}.pt")) for r in range(world)]
+    assert parts[0]["ndof_global"] == V.ndof and sum(p["units"] for p in parts) == active.NumSet()
+    assert all(p["units"] > 0 for p in parts)
+    key_of = np.zeros(V.ndof, dtype=np.int64)
+    for p in parts:
+        key_of[p["rows"].numpy()] = p["keys"].numpy()
+    ref_id = {int(k): i for i, k in enumerate(keys)}
+    scale, nnz = np.abs(val).max(), 0
+    for p in parts:
+        rows, prp, cols, vals = p["rows"].numpy(), p["rowptr"].numpy(), p["cols"].numpy(), p["vals"].numpy()
+        for i, g in enumerate(rows):
+            ri = ref_id[int(key_of[g])]
+            c_d = np.array([ref_id[int(key_of[c])] for c in cols[prp[i]:prp[i + 1]]])
+            o = np.argsort(c_d)
+            assert np.array_equal(c_d[o], col[rp[ri]:rp[ri + 1]])
+            assert np.allclose(vals[prp[i]:prp[i + 1]][o], val[rp[ri]:rp[ri + 1]], rtol=1e-12, atol=1e-13 * scale)
+            nnz += prp[i + 1] - prp[i]
+    assert nnz == len(col)
