@@ -374,6 +374,53 @@ class MlsetGpuBackend(GpuBackend):
 
 
 # ------------------------------------------------------------------ slab partition of the structured chain (input producer)
+def structured_dof_keys(mesh, vg, nv1, NV, p, el_gid, v_owner=None, el_owner=None):
+    """Global keys (any total order all ranks agree on) of the H1(order p) dofs of a sub-mesh of the structured Kuhn
+    chain, in the order fes.H1 numbers them (vertices, (p-1) per edge, (p-1)(p-2)/2 per face, cell bubbles), computed
+    WITHOUT communication from the global vertex ids `vg`: the vertices of an edge / face lie in one cell, so their id
+    differences come from a set of 7 offsets -> key = smallest vertex id * 8 (64) + offset code(s).  Owner of an entity:
+    the largest owner of its vertices; cell dofs belong to the element's rank.  Returns (gid int64, owner int64 or None)."""
+    dev = vg.device
+    offs = torch.tensor(sorted([1, nv1, nv1 + 1, nv1 * nv1, nv1 * nv1 + 1, nv1 * nv1 + nv1, nv1 * nv1 + nv1 + 1]),
+                        dtype=torch.int64, device=dev)
+
+    def code(d):
+        c = torch.searchsorted(offs, d)
+        assert bool((offs[c.clamp(max=6)] == d).all()), "not an edge / face of the structured Kuhn mesh"
+        return c
+
+    gid, owner = [vg], [v_owner]
+    base = NV
+    if p >= 2 and mesh.dim >= 2:
+        ev, _ = mesh.edges()
+        g = torch.sort(vg[ev.long()], dim=1).values
+        ekey = g[:, 0] * 8 + code(g[:, 1] - g[:, 0])
+        k = torch.arange(p - 1, device=dev, dtype=torch.int64)
+        gid.append((base + ekey.reshape(-1, 1) * (p - 1) + k).reshape(-1))
+        if v_owner is not None:
+            owner.append(v_owner[ev.long()].max(dim=1).values.repeat_interleave(p - 1))
+        base += 8 * NV * (p - 1)
+    if p >= 3 and mesh.dim == 3:
+        nfd = (p - 1) * (p - 2) // 2
+        fv, _ = mesh.faces()
+        g = torch.sort(vg[fv.long()], dim=1).values
+        fkey = g[:, 0] * 64 + code(g[:, 1] - g[:, 0]) * 8 + code(g[:, 2] - g[:, 0])
+        k = torch.arange(nfd, device=dev, dtype=torch.int64)
+        gid.append((base + fkey.reshape(-1, 1) * nfd + k).reshape(-1))
+        if v_owner is not None:
+            owner.append(v_owner[fv.long()].max(dim=1).values.repeat_interleave(nfd))
+        base += 64 * NV * nfd
+        ncd = (p - 1) * (p - 2) * (p - 3) // 6
+        if ncd:
+            k = torch.arange(ncd, device=dev, dtype=torch.int64)
+            gid.append((base + el_gid.reshape(-1, 1) * ncd + k).reshape(-1))
+            if v_owner is not None:
+                owner.append(el_owner.repeat_interleave(ncd))
+    gid = torch.cat(gid)
+    assert int(gid.max().item()) < (1 << 52)
+    return gid, (torch.cat(owner) if v_owner is not None else None)
+
+
 def make_slab_partition(n, world, rank, device, fe_order=2, radius=0.4):
     """Chain [0,1]^2 x [0,world] of `world` unit cubes, n^3 x 6 Kuhn tets each; rank r owns cube r
     (a contiguous element range of the global mesh) plus one halo layer of cells per neighbour.
@@ -383,8 +430,8 @@ def make_slab_partition(n, world, rank, device, fe_order=2, radius=0.4):
     from . import meshes
     from .fes import H1
     from .pipeline import sphere_levelset
-    if fe_order > 2:
-        raise NotImplementedError("distributed numbering keys are built for vertex and edge dofs (order <= 2)")
+    if fe_order > 4:
+        raise NotImplementedError("orders 1..4")
     lo, hi = (1 if rank > 0 else 0), (1 if rank < world - 1 else 0)
     nzl = n + lo + hi
     mesh = meshes.MakeStructured3DMesh(nx=n, ny=n, nz=nzl, device=device)
@@ -410,13 +457,10 @@ def make_slab_partition(n, world, rank, device, fe_order=2, radius=0.4):
     vg = vloc % (nv1 * nv1) + nv1 * nv1 * K
     NV = nv1 * nv1 * (n * world + 1)
     v_owner = torch.where(K <= 0, torch.zeros_like(K), (K + n - 1) // n - 1).clamp(max=world - 1)
-    gid, owner = [vg], [v_owner]
-    if fe_order == 2:
-        ev, _ = lmesh.edges()
-        a, b = vg[ev[:, 0].long()], vg[ev[:, 1].long()]
-        gid.append(NV + torch.minimum(a, b) * NV + torch.maximum(a, b))
-        owner.append(torch.maximum(v_owner[ev[:, 0].long()], v_owner[ev[:, 1].long()]))
-    gid, owner = torch.cat(gid), torch.cat(owner).to(torch.int32)
+    e_loc = perm.to(torch.int64)                                   # local element id of the unpermuted local mesh
+    el_gid = e_loc + 6 * n * n * k0                                # global element id (6 * global cell + path)
+    gid, ent_owner = structured_dof_keys(lmesh, vg, nv1, NV, fe_order, el_gid, v_owner, el_rank.to(torch.int64))
+    owner = ent_owner.to(torch.int32)
     halo_for = {}
     own_cells_k = cell_k[perm][:6 * n ** 3]
     if rank > 0:

@@ -33,13 +33,11 @@ def _global_reference(n, world, fe_order):
     phi = sphere_levelset(pts, centers, 0.4).numpy()
     res, _ = oracle_step(3, gmesh.elements.numpy(), pts.numpy(), V.el_dofs.numpy(), V.ndof, fe_order, phi)
     # keys of the global dofs (same construction as make_slab_partition)
+    from ngsxfem_b200.distributed import structured_dof_keys
     NV = nv1 * nv1 * (n * world + 1)
-    gid = [torch.arange(gmesh.nv, dtype=torch.int64)]
-    if fe_order == 2:
-        ev, _ = gmesh.edges()
-        a, b = ev[:, 0].long(), ev[:, 1].long()
-        gid.append(NV + torch.minimum(a, b) * NV + torch.maximum(a, b))
-    gid = torch.cat(gid).numpy()
+    gid, _ = structured_dof_keys(gmesh, torch.arange(gmesh.nv, dtype=torch.int64), nv1, NV, fe_order,
+                                 torch.arange(gmesh.ne, dtype=torch.int64))
+    gid = gid.numpy()
     # compressed id -> key
     act = np.zeros(V.ndof, dtype=bool)
     els_act = np.concatenate([np.flatnonzero(np.unpackbits(res["bits"][0], bitorder="little")[:gmesh.ne]),
@@ -80,7 +78,7 @@ def _worker(rank, world, n, fe_order, port, out, gpu=False):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world,n,fe_order", [(2, 4, 2), (3, 3, 2), (2, 5, 1)])
+@pytest.mark.parametrize("world,n,fe_order", [(2, 4, 2), (3, 3, 2), (2, 5, 1), (2, 3, 3), (2, 2, 4)])
 def test_slab_partition_merge_equals_global(tmp_path, world, n, fe_order):
     _run_and_check(tmp_path, world, n, fe_order, gpu=False)
 
@@ -143,7 +141,7 @@ def _mlset_values(pts, world):
     return torch.stack([torch.where(f.abs() < 1e-14, torch.full_like(f, 1e-14), f) for f in fns]).contiguous()
 
 
-def _mlset_worker(rank, world, n, port, out):
+def _mlset_worker(rank, world, n, fe_order, port, out):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     torch.cuda.set_device(rank)
@@ -151,7 +149,7 @@ def _mlset_worker(rank, world, n, port, out):
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
     try:
         from ngsxfem_b200.distributed import DistributedCutAssembly, MlsetGpuBackend, make_slab_partition
-        part, _ = make_slab_partition(n, world, rank, dev, fe_order=2)
+        part, _ = make_slab_partition(n, world, rank, dev, fe_order=fe_order)
         be = MlsetGpuBackend([(0, 0, 0, 0)]).bind(part)
         asm = DistributedCutAssembly(part, be, rank, world)
         res = asm.step(_mlset_values(part.vtx_xyz, world))
@@ -165,15 +163,16 @@ def _mlset_worker(rank, world, n, port, out):
 
 
 @pytest.mark.gpu
-def test_nccl_mlset_domain_partitioned_equals_single_gpu(tmp_path):
+@pytest.mark.parametrize("n,fe_order", [(5, 2), (4, 3)])
+def test_nccl_mlset_domain_partitioned_equals_single_gpu(tmp_path, n, fe_order):
     """BASELINE config 4 shape: the multi-level-set domain assembled on 2 GPUs (halo layer, NCCL interface rows) equals the
     single-GPU RestrictedBilinearForm.Assemble of the whole chain, row by row through the global dof keys"""
-    world, n = 2, 5
+    world = 2
     if torch.cuda.device_count() < world:
         pytest.skip("needs 2 GPUs")
     import ngsxfem_b200 as xf
-    port = 29500 + (os.getpid() % 2000) + 11
-    mp.spawn(_mlset_worker, args=(world, n, port, str(tmp_path)), nprocs=world, join=True)
+    port = 29500 + (os.getpid() % 2000) + 11 + fe_order
+    mp.spawn(_mlset_worker, args=(world, n, fe_order, port, str(tmp_path)), nprocs=world, join=True)
     # single-GPU reference on the whole chain
     dev = torch.device("cuda", 0)
     mesh = xf.MakeStructured3DMesh(nx=n, ny=n, nz=n * world, device=dev)
@@ -186,16 +185,16 @@ def test_nccl_mlset_domain_partitioned_equals_single_gpu(tmp_path):
     lsets = [xf.GridFunction(gmesh, phis[i]) for i in range(4)]
     dts = (0, 0, 0, 0)
     active = xf.MultiLevelsetCutInfo(gmesh, lsets).GetElementsWithContribution(dts)
-    V0 = xf.H1(gmesh, order=2)
+    V0 = xf.H1(gmesh, order=fe_order)
     V = xf.Restrict(V0, active)
     u, v = V.TnT()
     a = xf.RestrictedBilinearForm(V, element_restriction=active)
     a += (xf.grad(u) * xf.grad(v) + u * v) * xf.dCut(lsets, dts, definedonelements=active)
     a.Assemble()
+    from ngsxfem_b200.distributed import structured_dof_keys
     NV = nv1 * nv1 * (n * world + 1)
-    ev, _ = gmesh.edges()
-    ea, eb = ev[:, 0].long(), ev[:, 1].long()
-    gid = torch.cat([torch.arange(gmesh.nv, device=dev, dtype=torch.int64), NV + torch.minimum(ea, eb) * NV + torch.maximum(ea, eb)])
+    gid, _ = structured_dof_keys(gmesh, torch.arange(gmesh.nv, device=dev, dtype=torch.int64), nv1, NV, fe_order,
+                                 torch.arange(gmesh.ne, device=dev, dtype=torch.int64))
     keys = gid[V.dofmap >= 0].cpu().numpy()            # compressed id -> key (ascending compression)
     rp, col, val = (t.cpu().numpy() for t in (a.mat.rowptr, a.mat.col, a.mat.vals))
     parts = [torch.load(os.path.join(str(tmp_path), f"rank{r}.pt")) for r in range(world)]
