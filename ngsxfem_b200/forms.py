@@ -238,10 +238,10 @@ class Form:
 
 # ------------------------------------------------------------------ differential symbols
 class CutDifferentialSymbol:
-    def __init__(self, levelset, domain_type, order, definedonelements, deformation, time_order=-1, tref=None):
+    def __init__(self, levelset, domain_type, order, definedonelements, deformation, time_order=-1, tref=None, vb=0):
         self.levelset, self.domain_type, self.order = levelset, domain_type, order
         self.definedonelements, self.deformation = definedonelements, deformation
-        self.time_order, self.tref = time_order, tref
+        self.time_order, self.tref, self.vb = time_order, tref, vb
 
 
 def dCut(levelset, domain_type, order=None, subdivlvl=None, time_order=-1, levelset_domain=None,
@@ -250,13 +250,16 @@ def dCut(levelset, domain_type, order=None, subdivlvl=None, time_order=-1, level
     """python/__init__.py:781-864"""
     if subdivlvl not in (None, 0):
         raise XgpuError("subdivlvl > 0 selects ngsxfem's legacy subdivision path: not provided")
-    if element_boundary or skeleton or element_vb != 0 or vb != 0:
-        raise XgpuError("element-boundary / skeleton / BND cut integrals are not on the accelerated path yet")
+    if element_boundary or skeleton or element_vb != 0 or vb not in (0, 1):
+        raise XgpuError("element-boundary / skeleton cut integrals are not on the accelerated path yet")
+    if vb == 1 and (deformation is not None or isinstance(levelset, (list, tuple)) or int(domain_type) == IF):
+        raise XgpuError("dCut(vb=BND): single level set, NEG / POS, no deformation (tests/pytests/test_bndcut.py)")
     if time_order >= 0 or tref is not None:
         raise XgpuError("space-time forms are not assembled on the accelerated path yet (rules: ops.cutquad_st)")
     if kwargs:
         raise XgpuError(f"unsupported dCut arguments: {sorted(kwargs)}")
-    return CutDifferentialSymbol(levelset, domain_type, -1 if order is None else int(order), definedonelements, deformation)
+    return CutDifferentialSymbol(levelset, domain_type, -1 if order is None else int(order), definedonelements, deformation,
+                                 vb=vb)
 
 
 class FacetPatchDifferentialSymbol:
@@ -379,6 +382,7 @@ class BilinearForm:
             return
         slot_A = ops.bitset_rank(active.bits, ne, ctx=ctx)[0]
         m_A = torch.zeros((l_A.numel(), nd, nd), dtype=torch.float64, device=dev)
+        bnd_batches = []
         for integ in vol:
             dx = integ.dx
             terms = list(integ.form.terms)
@@ -386,6 +390,19 @@ class BilinearForm:
                 raise XgpuError("jump terms belong on dFacetPatch")
             order = self._intorder(integ)
             don = dx.definedonelements
+            if dx.vb == 1:
+                # boundary elements (dCut(..., vb=BND)): their cut rules are carried into the adjacent volume element;
+                # one matrix per BOUNDARY element in its own batch (a volume element may own several boundary facets)
+                phi = _lset_vec(dx.levelset, mesh)
+                vol_els, off, q, w = _bnd_rule_in_volume(mesh, phi, int(dx.domain_type), order, ctx, facet_mask=don)
+                keep = torch.nonzero(((active.bits[(vol_els >> 5).long()] >> (vol_els & 31)) & 1).bool()).reshape(-1)
+                if keep.numel() != vol_els.numel():
+                    raise XgpuError("dCut(vb=BND): a boundary element of an inactive volume element (restrict definedonelements)")
+                if w.numel():
+                    phi_n = _lset_vec(integ.form.nlset, mesh) if integ.form.nlset is not None else phi
+                    m_B = ops.elmat_rule(dim, p, vol_els, mesh.elements, mesh.points, phi_n, off, q, w, terms, ctx=ctx)
+                    bnd_batches.append((self._rows(vol_els), m_B))
+                continue
             if don is None:
                 l, slots = l_A, None
             else:
@@ -414,6 +431,8 @@ class BilinearForm:
                     ops.elmat_rule(dim, p, l, mesh.elements, mesh.points, phi_n, off, q, w, terms, out=m_A, accumulate=True,
                                    slots=slots, ctx=ctx)
         tables.append(self._rows(l_A)); mats.append(m_A)
+        for t_B, m_B in bnd_batches:
+            tables.append(t_B); mats.append(m_B)
 
     def _assemble_single_lset(self, vol, active, tables, mats, ctx):
         sp = self.space
@@ -514,6 +533,7 @@ class BilinearForm:
             if key not in lsets:
                 lsets.append(key)
         general = len(lsets) > 1 or any(isinstance(i.dx.levelset, (list, tuple)) for i in vol) \
+            or any(i.dx.vb == 1 for i in vol) \
             or any(i.form.nlset is not None and i.form.nlset is not i.dx.levelset for i in vol)
         if general:
             self._assemble_general(vol, active, tables, mats, ctx)
@@ -572,6 +592,46 @@ class BilinearForm:
         return self
 
 
+def _bnd_rule_in_volume(mesh, phi, dt, order, ctx, facet_mask=None):
+    """dCut(lset, dt, vb=BND): the cut rule of every boundary facet (a (dim-1)-simplex, cutint/straightcutrule.cpp on
+    the BND element) carried into the reference coordinates of the adjacent volume element, so that the volume
+    kernels evaluate the traces: returns (volume element per boundary element, offsets, points, weights) with
+    weights w * |facet| / |det F_vol| (the kernels multiply by the volume measure).  facet_mask: BitArray over the
+    boundary ELEMENTS (definedonelements)."""
+    dim = mesh.dim
+    bv, fids = mesh.boundary_elements()
+    _, _, fe = mesh.facets()
+    vol = fe[fids.long(), 0].contiguous()                                  # adjacent volume element
+    sel = None
+    if facet_mask is not None:
+        sel = facet_mask.indices()
+        bv, vol = bv[sel.long()].contiguous(), vol[sel.long()].contiguous()
+    off, q, w = ops.cutquad(dim - 1, None, bv, mesh.points, phi, dt, order, ctx=ctx)
+    ctx.raise_on_geometry_error()
+    nb = bv.shape[0]
+    b_of_pt = torch.repeat_interleave(torch.arange(nb, device=bv.device), off[1:] - off[:-1])
+    ev = mesh.elements[vol.long()].long()                                   # (nb, dim+1) volume element vertices
+    # local index of every boundary vertex inside its volume element
+    loc = (ev.unsqueeze(1) == bv.long().unsqueeze(2)).to(torch.int64).argmax(dim=2)   # (nb, dim)
+    # barycentric weights of a facet point: reference simplex convention v_k <-> e_k, last vertex <-> origin
+    lam = torch.cat([q[:, :dim - 1], 1.0 - q[:, :dim - 1].sum(dim=1, keepdim=True)], dim=1)          # (npts, dim)
+    E = torch.zeros((dim + 1, 3), dtype=torch.float64, device=bv.device)     # reference coords of the volume vertices
+    E[torch.arange(dim), torch.arange(dim)] = 1.0
+    xh = (lam.unsqueeze(2) * E[loc[b_of_pt]]).sum(dim=1)                     # (npts, 3)
+    # measures
+    P = mesh.points
+    pv = P[bv.long()]                                                        # (nb, dim, dim)
+    if dim == 2:
+        fm = (pv[:, 0] - pv[:, 1]).norm(dim=1)
+    else:
+        fm = torch.linalg.cross(pv[:, 0] - pv[:, 2], pv[:, 1] - pv[:, 2]).norm(dim=1)
+    X = P[ev]                                                                # (nb, dim+1, dim)
+    J = (X[:, :dim] - X[:, dim:dim + 1]).transpose(1, 2)
+    vm = torch.linalg.det(J).abs()
+    w2 = w * (fm / vm)[b_of_pt]
+    return vol, off, xh.contiguous(), w2.contiguous()
+
+
 class LinearForm:
     """LinearForm(space); f += coef * x**a * y**b * v * dCut(lset, dt, definedonelements=...); f.Assemble() -> f.vec
     (SymbolicCutLinearFormIntegrator, xfem/symboliccutlfi.cpp:51-140; demos/fictdom.py:132-137).  Element vectors
@@ -600,10 +660,20 @@ class LinearForm:
             return self
         slot_A = ops.bitset_rank(active.bits, ne, ctx=ctx)[0]
         v_A = torch.zeros((l_A.numel(), nd), dtype=torch.float64, device=dev)
+        rows_of = (lambda l: sp.rows(l)) if hasattr(sp, "rows") else (lambda l: ops.gather_rows(sp.el_dofs, l, None))
+        extra = []
         for integ in self.integrals:
             dx = integ.dx
             order = dx.order if dx.order >= 0 else 2 * p  # symboliccutlfi.cpp:86-88
             don = dx.definedonelements
+            if dx.vb == 1:  # boundary elements: own batch, see BilinearForm._assemble_general
+                phi = _lset_vec(dx.levelset, mesh)
+                vol_els, off, q, w = _bnd_rule_in_volume(mesh, phi, int(dx.domain_type), order, ctx, facet_mask=don)
+                if w.numel():
+                    phi_n = _lset_vec(integ.form.nlset, mesh) if integ.form.nlset is not None else phi
+                    v_B = ops.elvec_rule(dim, p, vol_els, mesh.elements, mesh.points, phi_n, off, q, w, integ.form.terms, ctx=ctx)
+                    extra.append((rows_of(vol_els), v_B))
+                continue
             if don is None:
                 l, slots = l_A, None
             else:
@@ -630,9 +700,10 @@ class LinearForm:
                 if w.numel():
                     ops.elvec_rule(dim, p, l, mesh.elements, mesh.points, phi, off, q, w, integ.form.terms, out=v_A,
                                    accumulate=True, slots=slots, ctx=ctx)
-        table = sp.rows(l_A) if hasattr(sp, "rows") else ops.gather_rows(sp.el_dofs, l_A, None)
-        plan = ops.adjacency_plan(sp.ndof, [table], ctx=ctx)
-        ops.vec_scatter(plan, [(table, v_A)], out=self.vec)
+        table = rows_of(l_A)
+        batches = [(table, v_A)] + extra
+        plan = ops.adjacency_plan(sp.ndof, [b[0] for b in batches], ctx=ctx)
+        ops.vec_scatter(plan, batches, out=self.vec)
         return self
 
 

@@ -57,3 +57,43 @@ def test_integrate_bnd_3d():
     assert abs(val - (1.0 + 4.0 * cut)) < 1e-10
     mx = xf.Integrate({"levelset": lset, "domain_type": xf.NEG, "vb": xf.BND}, mesh=mesh, cf=xf.x, order=1)
     assert abs(mx - 4.0 * cut * cut / 2) < 1e-10
+
+
+@pytest.mark.parametrize("dim,p", [(2, 1), (2, 2), (3, 2)])
+def test_bnd_bilinear_and_linear_forms(dim, p):
+    """tests/pytests/test_bndcut.py:91-150 (BFI / LFI over dCut(lset, NEG, vb=BND)) with basis-independent answers:
+    for g = 1 + 2x - y (in every H1 space): c^T M c = int_{boundary, x < cut} g^2, f^T c = int g * (x y)"""
+    cut = 0.4
+    mesh = xf.MakeStructured3DMesh(nx=3, device=DEV) if dim == 3 else xf.MakeStructured2DMesh(nx=5, ny=4, device=DEV)
+    lset = xf.InterpolateToP1((lambda x, y, z: x - cut) if dim == 3 else (lambda x, y: x - cut), mesh)
+    V = xf.H1(mesh, order=p)
+    u, v = V.TnT()
+    a = xf.BilinearForm(V)
+    a += u * v * xf.dCut(lset, xf.NEG, vb=xf.BND)
+    a.Assemble()
+    f = xf.LinearForm(V)
+    f += (xf.x * xf.y) * v * xf.dCut(lset, xf.NEG, vb=xf.BND, order=2 * p + 2)
+    f.Assemble()
+    pts = mesh.points
+    c = torch.zeros(V.ndof, dtype=torch.float64, device=DEV)
+    c[:mesh.nv] = 1.0 + 2.0 * pts[:, 0] - pts[:, 1]                     # P1 function: higher-order dofs vanish
+    quad = float((c * (a.mat * c)).sum())
+    lin = float((c * f.vec).sum())
+    X = cut
+    if dim == 2:
+        # edges: bottom y=0 (x in [0,X]), top y=1, left x=0 (y in [0,1]); g = 1 + 2x - y
+        ex_quad = ((1 + 2 * X) ** 3 - 1) / 6 + (2 * X) ** 3 / 6 + ((1 - 0) ** 3 - (1 - 1) ** 3) / 3
+        ex_lin = 0.0 + (X ** 2 / 2 * 0 + 2 * X ** 3 / 3) + 0.0            # int_0^X x * 1 * (2x) dx on the top edge
+    else:
+        import scipy.integrate as si
+        g = lambda x, y: 1 + 2 * x - y
+        faces = [(lambda s, t: g(s, 0.0), lambda s, t: s * 0.0, (0, X)), (lambda s, t: g(s, 1.0), lambda s, t: s * 1.0, (0, X)),
+                 (lambda s, t: g(s, t), lambda s, t: s * t, (0, X)), (lambda s, t: g(s, t), lambda s, t: s * t, (0, X))]
+        # y = 0, y = 1 faces (params s = x, t = z); z = 0, z = 1 faces (params s = x, t = y); x = 0 face (params y, z)
+        ex_quad = ex_lin = 0.0
+        for gg, xy, (lo, hi) in faces:
+            ex_quad += si.dblquad(lambda t, s_: gg(s_, t) ** 2, lo, hi, 0, 1)[0]
+            ex_lin += si.dblquad(lambda t, s_: gg(s_, t) * xy(s_, t), lo, hi, 0, 1)[0]
+        ex_quad += si.dblquad(lambda t, s_: g(0.0, s_) ** 2, 0, 1, 0, 1)[0]
+    assert abs(quad - ex_quad) < 1e-10 * abs(ex_quad)
+    assert abs(lin - ex_lin) < 1e-10 * max(1.0, abs(ex_lin))
