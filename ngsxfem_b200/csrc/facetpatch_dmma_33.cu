@@ -1,0 +1,8 @@
+// facetpatch_dmma_33.cu — k_facetpatch_dmma<3, 3, *> instantiations (see facetpatch.cuh)
+#include "facetpatch.cuh"
+
+int xg_fp_dmma_33(xgpu_ctx* ctx, int64_t n, const int32_t* facets, const int32_t* facet_els, const int32_t* el_vtx,
+                  const double* vtx_xyz, const xgpu_rule_host* r, double coef, int hpow, double* mats)
+{
+  return launch_fp_dmma<3, 3>(ctx, n, facets, facet_els, el_vtx, vtx_xyz, r, coef, hpow, mats);
+}
