@@ -280,7 +280,7 @@ __global__ void __launch_bounds__(256) k_pattern(int ndof, const long long* __re
 #define XG_SMALL_BLOCK 128
 #define XG_SMALL_CH 10  // table entries loaded per batch (even)
 template <bool DUPS>
-__global__ void __launch_bounds__(XG_SMALL_BLOCK) k_pattern_small(int ndof, const long long* __restrict__ adj_ptr,
+__global__ void __launch_bounds__(XG_SMALL_BLOCK, 6) k_pattern_small(int ndof, const long long* __restrict__ adj_ptr,
                                                                   const long long* __restrict__ adj, BatchDev bd,
                                                                   const long long* __restrict__ candoff,
                                                                   int32_t* __restrict__ tmpcol, int32_t* __restrict__ rowcnt,

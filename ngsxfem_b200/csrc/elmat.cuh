@@ -224,7 +224,7 @@ struct StageSinkMS {
 // staged points of every chunk and are summed (fixed order) at the end, half 0 then stores the upper blocks, half 1
 // the mirrored ones.  Two integrators (NEG volume terms + IF interface term of CutFEM forms) run in one pass.
 template <int D, int P, bool DEF>
-__global__ void __launch_bounds__(128) k_elmat_ms(
+__global__ void __launch_bounds__(128, (P <= 2 ? 5 : 1)) k_elmat_ms(
     int64_t n, const int32_t* __restrict__ elems, const int32_t* __restrict__ el_vtx,
     const double* __restrict__ vtx_xyz, const int64_t* __restrict__ offsets, const double* __restrict__ pts,
     const double* __restrict__ wts, int np_shared, int CH, TermsDev T, int accumulate,
