@@ -39,6 +39,7 @@ struct xgpu_plan {
   int64_t ndof = 0, nadj = 0, nnz = 0, ncand = 0;
   int maxcand = 0, maxnr = 0, wmax = 0, dups = 0;
   int64_t epoch = -1;             // ctx->epoch at which the pattern scratch (slot 8) was filled
+  bool with_pattern = false;      // false: transposed table only (xgpu_adjacency_plan)
   BatchDev bd;
   long long* adj_ptr = nullptr;   // ndof+1
   long long* adj = nullptr;       // nadj entries: (global table row << 8) | local index
@@ -801,6 +802,7 @@ static int build_plan(xgpu_ctx* ctx, int64_t ndof, const xgpu_batch* batches_hos
   P->maxcand = ((int*)ctx->h_pinned)[0];
   P->dups = ((int*)ctx->h_pinned)[1];
   P->ncand = ctx->h_pinned[1];
+  P->with_pattern = with_pattern;
   if (!with_pattern) {  // transposed table only (vector assembly)
     XG_TRY(cudaEventRecord(P->ev[2], st));
     *plan_out = P;
@@ -833,7 +835,7 @@ extern "C" int xgpu_plan_phase_ms(xgpu_plan* P, double* ms_host)
 
 extern "C" int xgpu_csr_pattern(xgpu_ctx* ctx, xgpu_plan* P, int64_t* rowptr, int32_t* colidx)
 {
-  if (!ctx || !P || P->epoch < 0) return xgpu_fail(ctx, XGPU_ERR_ARG, "xgpu_csr_pattern: bad argument (adjacency-only plan?)");
+  if (!ctx || !P || !P->with_pattern) return xgpu_fail(ctx, XGPU_ERR_ARG, "xgpu_csr_pattern: bad argument (adjacency-only plan?)");
   cudaStream_t st = ctx->stream;
   XGPU_CUDA(ctx, cudaMemcpyAsync(rowptr, P->rowptr, sizeof(long long) * (P->ndof + 1), cudaMemcpyDeviceToDevice, st));
   if (P->ndof == 0 || P->nnz == 0) return XGPU_OK;
@@ -863,7 +865,7 @@ extern "C" int xgpu_csr_scatter(xgpu_ctx* ctx, xgpu_plan* P, const xgpu_batch* b
 extern "C" int xgpu_csr_assemble(xgpu_ctx* ctx, xgpu_plan* P, const xgpu_batch* batches_host, int nbatches,
                                  int64_t* rowptr, int32_t* colidx, double* vals)
 {
-  if (!ctx || !P || P->epoch < 0) return xgpu_fail(ctx, XGPU_ERR_ARG, "xgpu_csr_assemble: bad argument");
+  if (!ctx || !P || !P->with_pattern) return xgpu_fail(ctx, XGPU_ERR_ARG, "xgpu_csr_assemble: bad argument");
   XGPU_CUDA(ctx, cudaMemcpyAsync(rowptr, P->rowptr, sizeof(long long) * (P->ndof + 1), cudaMemcpyDeviceToDevice, ctx->stream));
   if (P->ndof == 0 || P->nnz == 0) return XGPU_OK;
   if (P->epoch != ctx->epoch) {  // another plan has used the shared scratch since: redo the pass
@@ -880,7 +882,7 @@ extern "C" int xgpu_csr_assemble(xgpu_ctx* ctx, xgpu_plan* P, const xgpu_batch* 
 static int run_scatter(xgpu_ctx* ctx, xgpu_plan* P, const xgpu_batch* batches_host, int nbatches,
                        const int64_t* rowptr, const int32_t* colidx, double* vals, const long long* src_off, int32_t* col_out)
 {
-  if (!ctx || !P || nbatches != P->bd.nb || P->epoch < 0) return xgpu_fail(ctx, XGPU_ERR_ARG, "xgpu_csr_scatter: bad argument");
+  if (!ctx || !P || nbatches != P->bd.nb || !P->with_pattern) return xgpu_fail(ctx, XGPU_ERR_ARG, "xgpu_csr_scatter: bad argument");
   BatchDev bd = P->bd;
   for (int i = 0; i < nbatches; i++) {
     if (batches_host[i].nrows != bd.rowoff[i + 1] - bd.rowoff[i] || batches_host[i].width != bd.width[i])

@@ -586,6 +586,10 @@ class BilinearForm:
                     tables.append(t_g)
                     mats.append(None)  # sparsity only
 
+        if not tables:  # nothing active: the empty matrix
+            self.mat = SparseMatrixCSR(sp.ndof, torch.zeros(sp.ndof + 1, dtype=torch.int64, device=dev),
+                                       torch.zeros(0, dtype=torch.int32, device=dev), torch.zeros(0, dtype=torch.float64, device=dev))
+            return self
         plan = ops.csr_plan(sp.ndof, tables, ctx=ctx)
         rowptr, col, vals = ops.csr_assemble(plan, list(zip(tables, mats)))
         self.mat = SparseMatrixCSR(sp.ndof, rowptr, col, vals)
