@@ -195,7 +195,13 @@ class DistributedCutAssembly:
         mark("elmat")
         # 5. local CSR; the halo batch contributes sparsity only
         batches = [(t_neg, m_neg), (t_if, m_if), (t_halo, None)]
-        rowptr, col, vals = be.csr(ndof, [bt for bt in batches if bt[0].shape[0] > 0])
+        batches = [bt for bt in batches if bt[0].shape[0] > 0]
+        if batches:
+            rowptr, col, vals = be.csr(ndof, batches)
+        else:  # nothing active on this rank (not even in the halo): an empty local matrix
+            rowptr = torch.zeros(ndof + 1, dtype=torch.int64, device=dev)
+            col = torch.zeros(0, dtype=torch.int32, device=dev)
+            vals = torch.zeros(0, dtype=torch.float64, device=dev)
         mark("csr")
         # 6. interface-row reduction: the values of the rows {owner == q, touched by my own elements} are packed and
         #    sent, the owner adds what it receives in a fixed order (lower rank first)

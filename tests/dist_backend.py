@@ -51,8 +51,10 @@ class OracleBackend:
         return src, dst
 
     def rows_offsets(self, rowptr, rows):
-        r = rows.long().clamp(min=0)
-        ln = torch.where(rows >= 0, rowptr[r + 1] - rowptr[r], torch.zeros_like(rowptr[r]))
+        ln = torch.zeros(rows.numel(), dtype=torch.int64)
+        live = rows >= 0
+        r = rows[live].long()
+        ln[live] = rowptr[r + 1] - rowptr[r]
         return torch.cat([torch.zeros(1, dtype=torch.int64), torch.cumsum(ln, 0)])
 
     def rows_pack(self, rowptr, rows, off, vals, total):
