@@ -201,6 +201,26 @@ int xgpu_elvec_std(xgpu_ctx* ctx, int dim, int fe_order, int64_t n, const int32_
                    const xgpu_lterm* terms_host, int nterms, int accumulate, const int32_t* slots,
                    double* vecs);
 
+/* space-time element matrices / vectors (BASELINE config 5): T_CalcElementMatrixAdd (xfem/symboliccutbfi.cpp:76-486)
+ * on a SpaceTimeFE (spacetime/SpaceTimeFE.cpp:57-135) with the rule of xgpu_cutquad_st_* (reference point, reference
+ * time, weight).  Basis: shape[j*nd_s + i] = L_j(t) N_i(xhat), time-major (SpaceTimeFE.hpp:185-218), L_j = Lagrange
+ * polynomials on NodalTimeFE's nodes (SpaceTimeFE.cpp:258-282).  Operators: 0 = ID, 1 = GRAD (space gradient,
+ * GRAD.GRAD only), XGPU_OP_DT = derivative w.r.t. the REFERENCE time (dt(u), spacetime/diffopDt.hpp).  fix_tref(u, t0)
+ * terms are the same call with a space rule and tvals = t0.  mats: n x nd x nd, nd = nd_s*(time_fe_order+1),
+ * rows = test; measure = spatial |det F|.  No deformation (XGPU_ERR_UNSUPPORTED). */
+enum { XGPU_OP_DT = 3 };
+int xgpu_elmat_st(xgpu_ctx* ctx, int dim, int fe_order, int time_fe_order, int64_t n, const int32_t* elems,
+                  const int32_t* el_vtx, const double* vtx_xyz, const int64_t* offsets, const double* pts,
+                  const double* tvals, const double* wts, const xgpu_term* terms_host, int nterms,
+                  int accumulate, const int32_t* slots, double* mats);
+/* space-time element vectors (SymbolicCutLinearFormIntegrator with time_order >= 0, xfem/symboliccutlfi.cpp:51-140):
+ * f(x, tref) * op_test(v), f = coef * h^hpow * x^e0 y^e1 z^e2 tref^e3, op_test in {ID, DT}.  vecs: n x nd. */
+typedef struct { int op_test; double coef; int hpow; int expo[4]; } xgpu_stlterm;
+int xgpu_elvec_st(xgpu_ctx* ctx, int dim, int fe_order, int time_fe_order, int64_t n, const int32_t* elems,
+                  const int32_t* el_vtx, const double* vtx_xyz, const int64_t* offsets, const double* pts,
+                  const double* tvals, const double* wts, const xgpu_stlterm* terms_host, int nterms,
+                  int accumulate, const int32_t* slots, double* vecs);
+
 /* ---------------------------------------------------------------- (d) ghost penalty
  * SymbolicFacetPatchBilinearFormIntegrator::T_CalcFacetMatrix (xfem/symboliccutbfi.cpp:
  * 1982-2377) for coef*h^hpow*(u-u.Other())*(v-v.Other()); order<0 -> 2*fe_order (:2004-2012).

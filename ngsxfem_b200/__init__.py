@@ -19,5 +19,7 @@ from .cutinfo import C_NO as NO, C_NEG as CDOM_NEG, C_POS as CDOM_POS, C_UNCUT a
     C_HASNEG as HASNEG, C_HASPOS as HASPOS, C_ANY as ANY
 from .forms import (dCut, dFacetPatch, grad, Normalize, specialcf, BilinearForm, RestrictedBilinearForm, LinearForm,
                     Integrate, TrialFunction, TestFunction, x, y, z)
+from .spacetime import (ScalarTimeFE, SpaceTimeFESpace, SpaceTimeGridFunction, SpaceTimeInterpolateToP1,
+                        ReferenceTimeVariable, tref, dtref, dt, fix_tref, dxtref, dmesh)
 
 __all__ = [n for n in dir() if not n.startswith("_")]

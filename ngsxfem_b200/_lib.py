@@ -31,6 +31,10 @@ class LTerm(C.Structure):
     _fields_ = [("op_test", C.c_int), ("coef", C.c_double), ("hpow", C.c_int), ("expo", C.c_int * 3)]
 
 
+class StLTerm(C.Structure):
+    _fields_ = [("op_test", C.c_int), ("coef", C.c_double), ("hpow", C.c_int), ("expo", C.c_int * 4)]
+
+
 class Batch(C.Structure):
     _fields_ = [("table", VP), ("mats", VP), ("nrows", C.c_int64), ("width", C.c_int)]
 
@@ -85,6 +89,10 @@ _SIGS = {
                                   C.c_int, C.c_int, VP, VP]),
     "xgpu_elvec_std": (C.c_int, [VP, C.c_int, C.c_int, C.c_int64, VP, VP, VP, VP, C.c_int, C.POINTER(LTerm),
                                  C.c_int, C.c_int, VP, VP]),
+    "xgpu_elmat_st": (C.c_int, [VP, C.c_int, C.c_int, C.c_int, C.c_int64, VP, VP, VP, VP, VP, VP, VP, C.POINTER(Term),
+                                C.c_int, C.c_int, VP, VP]),
+    "xgpu_elvec_st": (C.c_int, [VP, C.c_int, C.c_int, C.c_int, C.c_int64, VP, VP, VP, VP, VP, VP, VP, C.POINTER(StLTerm),
+                                C.c_int, C.c_int, VP, VP]),
     "xgpu_facetpatch": (C.c_int, [VP, C.c_int, C.c_int, C.c_int64, VP, VP, VP, VP, C.c_int, C.c_double, C.c_int, VP]),
     "xgpu_csr_plan": (C.c_int, [VP, C.c_int64, C.POINTER(Batch), C.c_int, C.POINTER(VP), c_i64p]),
     "xgpu_csr_pattern": (C.c_int, [VP, VP, VP, VP]),

@@ -181,6 +181,8 @@ def TestFunction(space):
 
 
 def grad(u):
+    if hasattr(u, "_st_grad"):  # proxies of a SpaceTimeFESpace (spacetime.py): the space gradient
+        return u._st_grad()
     if isinstance(u, Proxy):
         if u.op != OP_ID or u.other:
             raise XgpuError("grad of this proxy is not supported")
@@ -254,12 +256,14 @@ def dCut(levelset, domain_type, order=None, subdivlvl=None, time_order=-1, level
         raise XgpuError("element-boundary / skeleton cut integrals are not on the accelerated path yet")
     if vb == 1 and (deformation is not None or isinstance(levelset, (list, tuple)) or int(domain_type) == IF):
         raise XgpuError("dCut(vb=BND): single level set, NEG / POS, no deformation (tests/pytests/test_bndcut.py)")
-    if time_order >= 0 or tref is not None:
-        raise XgpuError("space-time forms are not assembled on the accelerated path yet (rules: ops.cutquad_st)")
     if kwargs:
         raise XgpuError(f"unsupported dCut arguments: {sorted(kwargs)}")
+    if time_order >= 0 or tref is not None:
+        # space-time rules (cutint/xintegration.cpp:41-90): assembled by spacetime.py on a SpaceTimeFESpace
+        if vb != 0 or deformation is not None or isinstance(levelset, (list, tuple)):
+            raise XgpuError("space-time dCut: one level set, volume elements, no deformation")
     return CutDifferentialSymbol(levelset, domain_type, -1 if order is None else int(order), definedonelements, deformation,
-                                 vb=vb)
+                                 time_order=int(time_order), tref=tref, vb=vb)
 
 
 class FacetPatchDifferentialSymbol:
@@ -509,6 +513,11 @@ class BilinearForm:
 
     def Assemble(self):
         sp = self.space
+        if hasattr(sp, "timeFE"):  # SpaceTimeFESpace
+            from . import spacetime
+            return spacetime.assemble_bilinear(self)
+        if any(isinstance(i.dx, CutDifferentialSymbol) and (i.dx.time_order >= 0 or i.dx.tref is not None) for i in self.integrals):
+            raise XgpuError("space-time differential symbols (time_order / tref) need a SpaceTimeFESpace")
         mesh = sp.mesh
         dim, p = mesh.dim, sp.order
         ctx = default_ctx(mesh.device.index)
@@ -646,13 +655,20 @@ class LinearForm:
 
     def __iadd__(self, o):
         ints = [o] if isinstance(o, Integral) else (o.ints if isinstance(o, SumOfIntegrals) else None)
-        if ints is None or not all(isinstance(i.form, LForm) and isinstance(i.dx, CutDifferentialSymbol) for i in ints):
+        st = hasattr(self.space, "timeFE")
+        if ints is None or not all((hasattr(i.form, "fixt") if st else isinstance(i.form, LForm))
+                                   and isinstance(i.dx, CutDifferentialSymbol) for i in ints):
             raise XgpuError("LinearForm += expects f * v * dCut(...)")
         self.integrals.extend(ints)
         return self
 
     def Assemble(self):
         sp = self.space
+        if hasattr(sp, "timeFE"):  # SpaceTimeFESpace
+            from . import spacetime
+            return spacetime.assemble_linear(self)
+        if any(i.dx.time_order >= 0 or i.dx.tref is not None for i in self.integrals):
+            raise XgpuError("space-time differential symbols (time_order / tref) need a SpaceTimeFESpace")
         mesh = sp.mesh
         dim, p, ne, nd, dev = mesh.dim, sp.order, mesh.ne, sp.nd, mesh.device
         ctx = default_ctx(dev.index)

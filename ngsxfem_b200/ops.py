@@ -306,6 +306,44 @@ def elmat_std(dim, fe_order, elems, el_vtx, vtx_xyz, phi, order, terms, out=None
     return out
 
 
+OP_DT = 3  # include/xgpu.h XGPU_OP_DT: derivative w.r.t. the reference time (dt(u))
+
+
+def elmat_st(dim, fe_order, time_fe_order, elems, el_vtx, vtx_xyz, off, pts, tvals, wts, terms, out=None, accumulate=False,
+             slots=None, ctx=None):
+    """space-time element matrices on a space-time rule (cutquad_st): n x nd x nd, nd = nd_s*(time_fe_order+1), time-major"""
+    ctx = ctx or default_ctx()
+    n = el_vtx.shape[0] if elems is None else elems.numel()
+    nd = h1_ndof(dim, fe_order) * (time_fe_order + 1)
+    if out is None:
+        out = torch.empty((n, nd, nd), dtype=torch.float64, device=el_vtx.device)
+        accumulate = False
+    ctx.check(ctx.lib.xgpu_elmat_st(ctx.h, dim, fe_order, time_fe_order, n, ptr(elems), ptr(_i32(el_vtx)), ptr(_f64(vtx_xyz)),
+                                    ptr(off), ptr(pts), ptr(tvals), ptr(wts), terms_array(terms), len(terms), int(accumulate),
+                                    ptr(slots), ptr(out)))
+    return out
+
+
+def elvec_st(dim, fe_order, time_fe_order, elems, el_vtx, vtx_xyz, off, pts, tvals, wts, terms, out=None, accumulate=False,
+             slots=None, ctx=None):
+    """space-time element vectors; terms: (op_test, coef, hpow, (e0, e1, e2, e_tref))"""
+    ctx = ctx or default_ctx()
+    n = el_vtx.shape[0] if elems is None else elems.numel()
+    nd = h1_ndof(dim, fe_order) * (time_fe_order + 1)
+    if out is None:
+        out = torch.empty((n, nd), dtype=torch.float64, device=el_vtx.device)
+        accumulate = False
+    arr = (_lib.StLTerm * max(1, len(terms)))()
+    for i, (ot, c, hp, ex) in enumerate(terms):
+        arr[i].op_test = int(ot); arr[i].coef = float(c); arr[i].hpow = int(hp)
+        for k in range(4):
+            arr[i].expo[k] = int(ex[k]) if k < len(ex) else 0
+    ctx.check(ctx.lib.xgpu_elvec_st(ctx.h, dim, fe_order, time_fe_order, n, ptr(elems), ptr(_i32(el_vtx)), ptr(_f64(vtx_xyz)),
+                                    ptr(off), ptr(pts), ptr(tvals), ptr(wts), arr, len(terms), int(accumulate),
+                                    ptr(slots), ptr(out)))
+    return out
+
+
 def lterms_array(terms):
     """terms: (op_test, coef, hpow, (e0, e1, e2))"""
     arr = (LTerm * max(1, len(terms)))()

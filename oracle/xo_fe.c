@@ -240,6 +240,109 @@ int xo_cut_elmat(const xo_trafo* T, int p, const double* lsetvals, int dt, int o
   return np;
 }
 
+/* ---- space-time FE (spacetime/SpaceTimeFE.cpp:57-135): shape[j*nd_s+i] = L_j(t) N_i(xhat), time-major;
+ *      DiffOpDt = L_j'(t) N_i (reference-time derivative); nodes of NodalTimeFE (SpaceTimeFE.cpp:258-282) ---- */
+void xo_time_dshapes(int order, double t, double* dshape)
+{
+  double nodes[8], sh0[8], sh1[8];
+  /* nodes recovered from the Lagrange property: use the closed list as xo_time_shapes does */
+  if (order == 0) { dshape[0] = 0.0; return; }
+  if (order == 1) { nodes[0] = 0; nodes[1] = 1; }
+  else if (order == 2) { nodes[0] = 0; nodes[1] = 0.5; nodes[2] = 1; }
+  else { nodes[0] = 0; nodes[1] = 0.5 * (1.0 - 1.0 / sqrt(5.0)); nodes[2] = 0.5 * (1.0 + 1.0 / sqrt(5.0)); nodes[3] = 1; }
+  (void)sh0; (void)sh1;
+  for (int i = 0; i <= order; i++) {
+    double ds = 0.0;
+    for (int k = 0; k <= order; k++) if (k != i) {
+      double pr = 1.0 / (nodes[i] - nodes[k]);
+      for (int j = 0; j <= order; j++) if (j != i && j != k) pr *= (t - nodes[j]) / (nodes[i] - nodes[j]);
+      ds += pr;
+    }
+    dshape[i] = ds;
+  }
+}
+
+/* values / physical space gradients / reference-time derivatives of all space-time functions at (xhat, t) */
+static int st_basis(const xo_trafo* T, int p, int kt, const double* xhat, double t, const double* Fi,
+                    double* val, double* g, double* dtv)
+{
+  int D = T->dim, nds = xo_h1_ndof(D, p), nt = kt + 1;
+  double sh[64], dsh[64 * 3], L[8], dL[8];
+  xo_h1_shapes(D, p, T->vnum, xhat, sh, dsh);
+  xo_time_shapes(kt, t, L);
+  xo_time_dshapes(kt, t, dL);
+  for (int j = 0; j < nt; j++)
+    for (int i = 0; i < nds; i++) {
+      int k = j * nds + i;
+      val[k] = L[j] * sh[i];
+      dtv[k] = dL[j] * sh[i];
+      for (int c = 0; c < D; c++) {
+        double s = 0;
+        for (int m = 0; m < D; m++) s += Fi[m * D + c] * dsh[i * D + m];
+        g[k * D + c] = L[j] * s;
+      }
+    }
+  return nds * nt;
+}
+
+/* symboliccutbfi.cpp:133-304 with a SpaceTimeFE and a space-time rule (spacetimecutrule.cpp:104-244):
+ * elmat(test i, trial j) += sum_q coef h^hpow (w_q |det F|) op_test(phi_i) op_trial(phi_j), ops ID / GRAD.GRAD / DT */
+void xo_elmat_st_from_rule(const xo_trafo* T, int p, int kt, const double* pts, const double* tvals,
+                           const double* wts, int np, const xo_term* terms, int nterms, double* elmat)
+{
+  int D = T->dim;
+  static __thread double val[256], g[256 * 3], dtv[256];
+  for (int q = 0; q < np; q++) {
+    double F[9], Fi[9], x[3];
+    xo_trafo_eval(T, &pts[3 * q], F, x);
+    double meas = fabs(inv_det(D, F, Fi));
+    double h = pow(meas, 1.0 / D);
+    int nd = st_basis(T, p, kt, &pts[3 * q], tvals[q], Fi, val, g, dtv);
+    double fac = wts[q] * meas;
+    for (int t = 0; t < nterms; t++) {
+      double c = terms[t].coef * fac;
+      if (terms[t].hpow != 0) c *= pow(h, (double)terms[t].hpow);
+      int ot = terms[t].op_test, ou = terms[t].op_trial;
+      for (int i = 0; i < nd; i++)
+        for (int j = 0; j < nd; j++) {
+          double v;
+          if (ot == XO_OP_GRAD && ou == XO_OP_GRAD) {
+            v = 0;
+            for (int k = 0; k < D; k++) v += g[i * D + k] * g[j * D + k];
+          } else {
+            double a = (ot == XO_OP_ID) ? val[i] : dtv[i];
+            double b = (ou == XO_OP_ID) ? val[j] : dtv[j];
+            v = a * b;
+          }
+          elmat[i * nd + j] += c * v;
+        }
+    }
+  }
+}
+
+/* symboliccutlfi.cpp:51-140 with a SpaceTimeFE: elvec_i += sum_q (w_q |det F|) f(x_q, t_q) op_test(phi_i),
+ * f = coef h^hpow x^e0 y^e1 z^e2 tref^e3 */
+void xo_elvec_st_from_rule(const xo_trafo* T, int p, int kt, const double* pts, const double* tvals,
+                           const double* wts, int np, const xo_stlterm* terms, int nterms, double* elvec)
+{
+  int D = T->dim;
+  static __thread double val[256], g[256 * 3], dtv[256];
+  for (int q = 0; q < np; q++) {
+    double F[9], Fi[9], x[3] = { 0, 0, 0 };
+    xo_trafo_eval(T, &pts[3 * q], F, x);
+    double meas = fabs(inv_det(D, F, Fi));
+    double h = pow(meas, 1.0 / D);
+    int nd = st_basis(T, p, kt, &pts[3 * q], tvals[q], Fi, val, g, dtv);
+    for (int t = 0; t < nterms; t++) {
+      double f = terms[t].coef * wts[q] * meas;
+      if (terms[t].hpow != 0) f *= pow(h, (double)terms[t].hpow);
+      for (int c = 0; c < D; c++) for (int k = 0; k < terms[t].expo[c]; k++) f *= x[c];
+      for (int k = 0; k < terms[t].expo[3]; k++) f *= tvals[q];
+      for (int i = 0; i < nd; i++) elvec[i] += f * (terms[t].op_test == XO_OP_ID ? val[i] : dtv[i]);
+    }
+  }
+}
+
 /* symboliccutlfi.cpp:51-140 (scalar evaluation branch :141-175): elvec += sum_q B_q^T (f(x_q) w_q |det F|) */
 void xo_elvec_from_rule(const xo_trafo* T, int p, const double* lsetvals,
                         const double* pts, const double* wts, int np,

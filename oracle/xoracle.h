@@ -133,6 +133,15 @@ int xo_cut_elmat(const xo_trafo* T, int fe_order, const double* lsetvals, int dt
 void xo_elmat_from_rule(const xo_trafo* T, int fe_order, const double* lsetvals,
                         const double* pts, const double* wts, int np,
                         const xo_term* terms, int nterms, double* elmat);
+/* space-time FE (spacetime/SpaceTimeFE.cpp:57-135, time-major tensor basis) on a space-time rule: ops ID, GRAD.GRAD,
+ * XO_OP_DT (reference-time derivative).  nd = nd_s*(time_fe_order+1); ADDS into elmat / elvec. */
+enum { XO_OP_DT = 3 };
+void xo_time_dshapes(int order, double t, double* dshape);
+void xo_elmat_st_from_rule(const xo_trafo* T, int fe_order, int time_fe_order, const double* pts, const double* tvals,
+                           const double* wts, int np, const xo_term* terms, int nterms, double* elmat);
+typedef struct { int op_test; double coef; int hpow; int expo[4]; } xo_stlterm;
+void xo_elvec_st_from_rule(const xo_trafo* T, int fe_order, int time_fe_order, const double* pts, const double* tvals,
+                           const double* wts, int np, const xo_stlterm* terms, int nterms, double* elvec);
 /* SymbolicFacetPatchBilinearFormIntegrator::T_CalcFacetMatrix (symboliccutbfi.cpp:1982-2377)
  * form: coef * h^hpow * (u-u.Other())*(v-v.Other()); elmat (2nd x 2nd) is ZEROED then filled.
  * returns number of Newton failures. */

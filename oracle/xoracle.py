@@ -346,3 +346,39 @@ def integrate_monomial(dim, el_vtx, vtx_xyz, phi, dt, order, expo):
     if err.value:
         raise RuntimeError(f"oracle error {err.value}")
     return v
+
+
+# ------------------------------------------------------------------ space-time FE on space-time rules
+OP_DT = 3
+
+
+class StLTerm(C.Structure):
+    _fields_ = [("op_test", C.c_int), ("coef", C.c_double), ("hpow", C.c_int), ("expo", C.c_int * 4)]
+
+
+def elmat_st_from_rule(T, fe_order, time_fe_order, pts, tvals, wts, terms, out=None):
+    """xo_elmat_st_from_rule: ADDS into out (nd x nd), nd = nd_s*(time_fe_order+1), time-major"""
+    nd = h1_ndof(T.dim, fe_order) * (time_fe_order + 1)
+    m = np.zeros((nd, nd)) if out is None else out
+    pts = _f64(pts); tv = _f64(tvals); wts = _f64(wts)
+    ta = terms_array(terms)
+    fn = lib().xo_elmat_st_from_rule
+    fn.restype = None
+    fn(C.byref(T), fe_order, time_fe_order, _p(pts), _p(tv), _p(wts), len(wts), ta, len(terms), _p(m))
+    return m
+
+
+def elvec_st_from_rule(T, fe_order, time_fe_order, pts, tvals, wts, terms, out=None):
+    """terms: (op_test, coef, hpow, (e0, e1, e2, e_t)); ADDS into out (nd)"""
+    nd = h1_ndof(T.dim, fe_order) * (time_fe_order + 1)
+    v = np.zeros(nd) if out is None else out
+    pts = _f64(pts); tv = _f64(tvals); wts = _f64(wts)
+    arr = (StLTerm * len(terms))()
+    for i, (ot, c, hp, ex) in enumerate(terms):
+        arr[i].op_test = ot; arr[i].coef = c; arr[i].hpow = hp
+        for k in range(4):
+            arr[i].expo[k] = int(ex[k]) if k < len(ex) else 0
+    fn = lib().xo_elvec_st_from_rule
+    fn.restype = None
+    fn(C.byref(T), fe_order, time_fe_order, _p(pts), _p(tv), _p(wts), len(wts), arr, len(terms), _p(v))
+    return v

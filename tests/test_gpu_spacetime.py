@@ -1,0 +1,240 @@
+"""Space-time element matrices / vectors and their assembly on the GPU (xgpu_elmat_st, xgpu_elvec_st, BilinearForm /
+LinearForm on a SpaceTimeFESpace; BASELINE config 5; SURVEY.md §8 a9 + a10) — against the oracle restatement of
+SpaceTimeFE (1e-12 relative, Frobenius), against the closed-form answers of the reference's own space-time test
+(tests/pytests/test_spacetimecutrule.py:44-69: level set 1-2x-2t on the unit square, NEG 7/8, POS 1/8, IF 1/2) and
+against the weak form of a heat equation whose solution lies in the discrete space (the DG-in-time formulation of
+tests/pytests/test_spacetimecutrule.py:100-104)."""
+import numpy as np
+import pytest
+import torch
+
+import ngsxfem_b200 as xf
+from ngsxfem_b200 import ops
+from oracle import xoracle as xo
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+NEG, POS, IF = 0, 1, 2
+ID, GRAD, DT = 0, 1, 3
+
+
+def moving_lset(mesh, tfe):
+    if mesh.dim == 3:
+        f = lambda x, y, z, t: torch.sqrt((x - .45 - .1 * t) ** 2 + (y - .5) ** 2 + (z - .55) ** 2) - 0.37
+    elif mesh.dim == 2:
+        f = lambda x, y, t: torch.sqrt((x - .5) ** 2 + (y - .45 - .15 * t) ** 2) - 0.31
+    else:
+        f = lambda x, t: x - 0.43 - 0.2 * t
+    return xf.SpaceTimeInterpolateToP1(f, mesh, tfe)
+
+
+def make_mesh(dim, n):
+    if dim == 1:
+        return xf.MakeStructured1DMesh(nx=n, device=DEV)
+    if dim == 2:
+        return xf.MakeStructured2DMesh(nx=n, ny=n, device=DEV)
+    return xf.MakeStructured3DMesh(nx=n, device=DEV)
+
+
+@pytest.mark.parametrize("dim,n,p,kt,dt", [(3, 3, 1, 2, NEG), (3, 3, 2, 1, IF), (3, 2, 2, 2, NEG), (2, 5, 1, 1, POS), (2, 5, 2, 2, NEG),
+                                            (2, 4, 3, 3, IF), (1, 7, 2, 2, NEG), (3, 2, 3, 1, NEG)])
+def test_spacetime_element_matrices_match_oracle(dim, n, p, kt, dt):
+    mesh = make_mesh(dim, n)
+    ls = moving_lset(mesh, xf.ScalarTimeFE(2))
+    terms = [(ID, ID, 1.25, 0), (GRAD, GRAD, 0.5, 1), (DT, ID, -0.75, 0), (ID, DT, 0.3, -1), (DT, DT, 0.1, 0)]
+    off, q, tv, w = ops.cutquad_st(dim, None, mesh.elements, mesh.points, ls.vec, 2, dt, 2 * kt, 2 * p)
+    assert w.numel() > 0
+    m = ops.elmat_st(dim, p, kt, None, mesh.elements, mesh.points, off, q, tv, w, terms)
+    P, E = mesh.points.cpu().numpy(), mesh.elements.cpu().numpy()
+    offn, qn, tvn, wn = off.cpu().numpy(), q.cpu().numpy(), tv.cpu().numpy(), w.cpu().numpy()
+    nd = ops.h1_ndof(dim, p) * (kt + 1)
+    mo = np.zeros((mesh.ne, nd, nd))
+    for el in range(mesh.ne):
+        a, b = offn[el], offn[el + 1]
+        if b > a:
+            T = xo.make_trafo(P[E[el]], E[el])
+            xo.elmat_st_from_rule(T, p, kt, qn[a:b], tvn[a:b], wn[a:b], terms, out=mo[el])
+    assert np.linalg.norm(mo) > 0
+    assert np.linalg.norm(m.cpu().numpy() - mo) <= 1e-12 * np.linalg.norm(mo)
+    # accumulate + slots
+    perm = torch.randperm(mesh.ne, generator=torch.Generator().manual_seed(2)).to(torch.int32).to(DEV)
+    buf = torch.zeros_like(m)
+    for _ in range(2):
+        ops.elmat_st(dim, p, kt, None, mesh.elements, mesh.points, off, q, tv, w, terms, out=buf, accumulate=True, slots=perm)
+    assert torch.allclose(buf[perm.long()], 2 * m, rtol=1e-14, atol=0)
+    # run-to-run bit reproducibility
+    m2 = ops.elmat_st(dim, p, kt, None, mesh.elements, mesh.points, off, q, tv, w, terms)
+    assert torch.equal(m, m2)
+
+
+@pytest.mark.parametrize("dim,n,p,kt,dt", [(3, 3, 1, 2, NEG), (3, 2, 2, 1, IF), (2, 5, 2, 2, NEG), (2, 4, 4, 3, POS), (1, 7, 3, 1, NEG)])
+def test_spacetime_element_vectors_match_oracle(dim, n, p, kt, dt):
+    mesh = make_mesh(dim, n)
+    ls = moving_lset(mesh, xf.ScalarTimeFE(1))
+    ex = lambda e: tuple(v if k < dim or k == 3 else 0 for k, v in enumerate(e))
+    terms = [(ID, 1.5, 0, ex((2, 1, 0, 1))), (DT, -0.5, 1, ex((0, 0, 1, 2))), (ID, 0.25, -1, ex((1, 0, 0, 0)))]
+    off, q, tv, w = ops.cutquad_st(dim, None, mesh.elements, mesh.points, ls.vec, 1, dt, 2 * kt, 2 * p)
+    v = ops.elvec_st(dim, p, kt, None, mesh.elements, mesh.points, off, q, tv, w, terms)
+    P, E = mesh.points.cpu().numpy(), mesh.elements.cpu().numpy()
+    offn, qn, tvn, wn = off.cpu().numpy(), q.cpu().numpy(), tv.cpu().numpy(), w.cpu().numpy()
+    nd = ops.h1_ndof(dim, p) * (kt + 1)
+    vo = np.zeros((mesh.ne, nd))
+    for el in range(mesh.ne):
+        a, b = offn[el], offn[el + 1]
+        if b > a:
+            T = xo.make_trafo(P[E[el]], E[el])
+            xo.elvec_st_from_rule(T, p, kt, qn[a:b], tvn[a:b], wn[a:b], terms, out=vo[el])
+    assert np.linalg.norm(vo) > 0
+    assert np.linalg.norm(v.cpu().numpy() - vo) <= 1e-12 * np.linalg.norm(vo)
+
+
+def test_unsupported_requests_fail_loudly():
+    mesh = make_mesh(2, 3)
+    ls = moving_lset(mesh, xf.ScalarTimeFE(1))
+    off, q, tv, w = ops.cutquad_st(2, None, mesh.elements, mesh.points, ls.vec, 1, NEG, 2, 2)
+    with pytest.raises(xf.XgpuError):   # GRAD paired with ID
+        ops.elmat_st(2, 1, 1, None, mesh.elements, mesh.points, off, q, tv, w, [(GRAD, ID, 1.0, 0)])
+    with pytest.raises(xf.XgpuError):   # DN is not a space-time operator
+        ops.elmat_st(2, 1, 1, None, mesh.elements, mesh.points, off, q, tv, w, [(2, 2, 1.0, 0)])
+    with pytest.raises(xf.XgpuError):   # time order
+        ops.elmat_st(2, 1, 4, None, mesh.elements, mesh.points, off, q, tv, w, [(ID, ID, 1.0, 0)])
+    # a space-time proxy on a merely spatial rule: the reference throws in SpaceTimeFE::CalcShape
+    V = xf.SpaceTimeFESpace(xf.H1(mesh, order=1), xf.ScalarTimeFE(1))
+    u, v = V.TnT()
+    a = xf.BilinearForm(V)
+    a += u * v * xf.dCut(xf.InterpolateToP1(lambda x, y: x - 0.4, mesh), NEG)
+    with pytest.raises(xf.XgpuError, match="mere space IR"):
+        a.Assemble()
+    # and a space-time symbol on a spatial space
+    W = xf.H1(mesh, order=1)
+    uw, vw = W.TnT()
+    b = xf.BilinearForm(W)
+    b += uw * vw * xf.dCut(ls, NEG, time_order=2)
+    with pytest.raises(xf.XgpuError):
+        b.Assemble()
+
+
+def st_coeffs(V, fn):
+    """coefficients of a function that is P1/P2-representable in space and nodal in time: fn(points, t) -> values;
+    hierarchical P2 edge coefficient = f(a) + f(b) - 2 f(mid) (fes.Deformation.interpolate_p2)"""
+    mesh = V.mesh
+    p = mesh.points
+    out = []
+    for t in V.TimeFE_nodes():
+        c = [fn(p, t)]
+        if V.order == 2:
+            edges, _ = mesh.edges()
+            a, b = p[edges[:, 0].long()], p[edges[:, 1].long()]
+            c.append(fn(a, t) + fn(b, t) - 2.0 * fn(0.5 * (a + b), t))
+        out.append(torch.cat(c))
+    return torch.cat(out)
+
+
+@pytest.mark.parametrize("p,kt", [(1, 1), (2, 2)])
+def test_moving_plane_known_answers(p, kt):
+    """tests/pytests/test_spacetimecutrule.py:44-69: lset(t) = 1 - 2x - 2t on the unit square, space-time measures
+    NEG 7/8, POS 1/8, IF 1/2 — here through ASSEMBLED operators applied to polynomial coefficient vectors"""
+    mesh = xf.MakeStructured2DMesh(nx=4, ny=4, device=DEV)
+    tfe_l = xf.ScalarTimeFE(1)
+    ls = xf.SpaceTimeInterpolateToP1(lambda x, y, t: 1 - 2 * x - 2 * t, mesh, tfe_l)
+    V = xf.SpaceTimeFESpace(xf.H1(mesh, order=p), xf.ScalarTimeFE(kt))
+    u, v = V.TnT()
+    one = st_coeffs(V, lambda P, t: torch.ones_like(P[:, 0]))
+    tt = st_coeffs(V, lambda P, t: torch.full_like(P[:, 0], t))
+    xx = st_coeffs(V, lambda P, t: P[:, 0])
+    xt = st_coeffs(V, lambda P, t: P[:, 0] * t)
+    ref = {NEG: 7 / 8, POS: 1 / 8, IF: 0.5}
+    for dom in (NEG, POS, IF):
+        m = xf.BilinearForm(V)
+        m += u * v * xf.dCut(ls, dom, time_order=2 * kt)
+        m.Assemble()
+        assert abs(float(one @ (m.mat * one)) - ref[dom]) < 1e-13
+    # dt(u) v with u = t, v = 1: the NEG measure again; u = 1: zero
+    a = xf.BilinearForm(V)
+    a += xf.dt(u) * v * xf.dCut(ls, NEG, time_order=2 * kt)
+    a.Assemble()
+    assert abs(float(one @ (a.mat * tt)) - 7 / 8) < 1e-13
+    assert abs(float(one @ (a.mat * one))) < 1e-13
+    # grad(u).grad(v) with u = x t, v = x: int_NEG t = 23/48
+    k = xf.BilinearForm(V)
+    k += xf.grad(u) * xf.grad(v) * xf.dCut(ls, NEG, time_order=2 * kt)
+    k.Assemble()
+    assert abs(float(xx @ (k.mat * xt)) - 23 / 48) < 1e-13
+    # linear form: int_NEG x^0 tref v, summed over a partition of unity = int_NEG t = 23/48
+    f = xf.LinearForm(V)
+    f += xf.tref * v * xf.dCut(ls, NEG, time_order=2 * kt)
+    f.Assemble()
+    assert abs(float(one @ f.vec) - 23 / 48) < 1e-13
+    # fixed reference time: the NEG domain at tref = 0.25 is x > 0.25 (area 3/4), at tref = 1 everything
+    for t0, area in ((0.25, 0.75), (1.0, 1.0), (0.0, 0.5)):
+        for lset0 in (ls, xf.InterpolateToP1(lambda x, y: 1 - 2 * x - 2 * t0, mesh)):
+            g = xf.BilinearForm(V)
+            g += xf.fix_tref(u, t0) * xf.fix_tref(v, t0) * xf.dCut(lset0, NEG)
+            g.Assemble()
+            assert abs(float(one @ (g.mat * one)) - area) < 1e-13
+        g = xf.BilinearForm(V)
+        g += u * v * xf.dCut(xf.InterpolateToP1(lambda x, y: 1 - 2 * x - 2 * t0, mesh), NEG, tref=t0)
+        g.Assemble()
+        assert abs(float(one @ (g.mat * one)) - area) < 1e-13
+
+
+def test_heat_equation_weak_form_is_satisfied_by_a_solution_in_the_space():
+    """DG-in-time slab formulation of tests/pytests/test_spacetimecutrule.py:100-104 on [0,1]^2:
+         a = delta_t grad(u).grad(v) dxtref + dt(u) v dxtref + fix_tref(u,0) fix_tref(v,0) dx
+         f = delta_t f v dxtref + u_old fix_tref(v,0) dx
+    u = x y (1 + t_old + delta_t tref) solves u_t - Laplace u = x y and lies in P2 x P1, so (A u - f) vanishes on every
+    test function that vanishes on the boundary of the square."""
+    n, told, dlt = 4, 0.3, 0.1
+    mesh = xf.MakeStructured2DMesh(nx=n, ny=n, device=DEV)
+    Vs = xf.H1(mesh, order=2)
+    V = xf.SpaceTimeFESpace(Vs, xf.ScalarTimeFE(1))
+    u, v = V.TnT()
+    a = xf.BilinearForm(V)
+    a += dlt * xf.grad(u) * xf.grad(v) * xf.dxtref(mesh, time_order=2)
+    a += xf.dt(u) * v * xf.dxtref(mesh, time_order=2)
+    a += xf.fix_tref(u, 0) * xf.fix_tref(v, 0) * xf.dmesh(mesh)
+    a.Assemble()
+    f = xf.LinearForm(V)
+    f += dlt * xf.x * xf.y * v * xf.dxtref(mesh, time_order=2)
+    f += (1 + told) * xf.x * xf.y * xf.fix_tref(v, 0) * xf.dmesh(mesh)
+    f.Assemble()
+    uex = st_coeffs(V, lambda P, t: P[:, 0] * P[:, 1] * (1 + told + dlt * t))
+    r = a.mat * uex - f.vec
+    # interior space dofs: vertices / edges not on the boundary
+    P = mesh.points
+    onb = lambda X: ((X[:, 0] < 1e-12) | (X[:, 0] > 1 - 1e-12) | (X[:, 1] < 1e-12) | (X[:, 1] > 1 - 1e-12))
+    edges, _ = mesh.edges()
+    mid = 0.5 * (P[edges[:, 0].long()] + P[edges[:, 1].long()])
+    interior = torch.cat([~onb(P), ~onb(mid)])
+    interior = torch.cat([interior, interior])
+    assert int(interior.sum()) > 0
+    assert float(r[interior].abs().max()) < 1e-13
+    assert float(r[~interior].abs().max()) > 1e-6   # boundary rows carry the flux: the check is not vacuous
+    # sparsity: time-major blocks share the spatial pattern
+    ms = xf.BilinearForm(Vs)
+    us, vs = Vs.TnT()
+    ms += us * vs * xf.dCut(xf.GridFunction(mesh, -torch.ones(mesh.nv, dtype=torch.float64)), NEG)
+    ms.Assemble()
+    assert a.mat.nze == 4 * ms.mat.nze
+
+
+def test_config5_shape_assembles_and_integrates_to_the_cylinder_volume():
+    """config 5 shape at small size: moving sphere, P1 space x P2 time level set and FE space; 1^T M 1 = space-time
+    volume of the discrete NEG domain = sum of the rule weights x |det F| (basis-independent)"""
+    mesh = xf.MakeStructured3DMesh(nx=8, device=DEV)
+    tfe = xf.ScalarTimeFE(2)
+    ls = xf.SpaceTimeInterpolateToP1(
+        lambda x, y, z, t: torch.sqrt((x - .5) ** 2 + (y - .5 - .1 * np.sin(2 * np.pi * 0.1 * t)) ** 2 + (z - .5) ** 2) - 0.3, mesh, tfe)
+    V = xf.SpaceTimeFESpace(xf.H1(mesh, order=1), tfe)
+    u, v = V.TnT()
+    m = xf.BilinearForm(V)
+    m += (u * v + xf.dt(u) * v) * xf.dCut(ls, NEG, time_order=4)
+    m += 0.01 * xf.grad(u) * xf.grad(v) * xf.dCut(ls, NEG, time_order=4)
+    m.Assemble()
+    one = torch.ones(V.ndof, dtype=torch.float64, device=DEV)
+    off, q, tv, w = ops.cutquad_st(3, None, mesh.elements, mesh.points, ls.vec, 2, NEG, 4, 2)
+    cnt = (off[1:] - off[:-1])
+    vol = float((w * torch.repeat_interleave(torch.full((mesh.ne,), 1.0 / 8 ** 3, dtype=torch.float64, device=DEV), cnt)).sum())
+    got = float(one @ (m.mat * one))
+    assert abs(got - vol) < 1e-13
+    assert abs(vol - 4 / 3 * np.pi * 0.3 ** 3) < 0.02   # polyhedral approximation of the ball, constant in time

@@ -1,0 +1,84 @@
+"""Pins of the oracle's space-time FE restatement (oracle/xo_fe.c: st_basis, xo_elmat_st_from_rule, xo_elvec_st_from_rule)
+— spacetime/SpaceTimeFE.cpp:57-135, :258-282 — against closed forms: the Lagrange property on NodalTimeFE's nodes, the
+time derivative of polynomials, and the reference's own space-time known answers (tests/pytests/
+test_spacetimecutrule.py:14-69: int tref = 1/2, int tref^3 = 1/4, int tref^2 (x^2+y^2) = 2/9 on the unit square;
+level set 1-2x-2t: NEG 7/8, POS 1/8, IF 1/2) computed through element MATRICES and VECTORS."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from oracle import xoracle as xo
+
+NEG, POS, IF = 0, 1, 2
+ID, GRAD, DT = 0, 1, 3
+NODES = {0: [0.0], 1: [0.0, 1.0], 2: [0.0, 0.5, 1.0],
+         3: [0.0, 0.5 * (1 - 1 / np.sqrt(5)), 0.5 * (1 + 1 / np.sqrt(5)), 1.0]}
+
+
+def time_shapes(k, t):
+    sh = np.zeros(k + 1); dsh = np.zeros(k + 1)
+    fn = xo.lib().xo_time_shapes; fn.restype = None
+    fn(k, C.c_double(t), sh.ctypes.data_as(C.POINTER(C.c_double)))
+    fn = xo.lib().xo_time_dshapes; fn.restype = None
+    fn(k, C.c_double(t), dsh.ctypes.data_as(C.POINTER(C.c_double)))
+    return sh, dsh
+
+
+@pytest.mark.parametrize("k", [0, 1, 2, 3])
+def test_time_basis_is_nodal_and_differentiates_polynomials(k):
+    for i, ti in enumerate(NODES[k]):
+        sh, _ = time_shapes(k, ti)
+        assert np.allclose(sh, np.eye(k + 1)[i], atol=1e-15)
+    for t in (0.0, 0.3, 0.77, 1.0):
+        sh, dsh = time_shapes(k, t)
+        assert abs(sh.sum() - 1) < 1e-14 and abs(dsh.sum()) < 1e-13
+        for m in range(1, k + 1):   # d/dt t^m = m t^(m-1), t^m is in the space
+            c = np.array(NODES[k]) ** m
+            assert abs(c @ sh - t ** m) < 1e-14
+            assert abs(c @ dsh - m * t ** (m - 1)) < 1e-13
+
+
+def unit_square():
+    P = np.array([[0, 0], [1, 0], [0, 1], [1, 1]], dtype=float)
+    E = np.array([[0, 1, 3], [0, 3, 2]], dtype=np.int32)
+    return P, E
+
+
+def st_sum(P, E, lset_st, kl, dom, ot, os_, p, kt, terms=None, lterms=None):
+    """sum over the two triangles of 1^T M 1 (terms) or 1^T f (lterms), 1 = constant one (vertex dofs, every time node)"""
+    nds = xo.h1_ndof(2, p)
+    one = np.zeros(nds * (kt + 1))
+    for j in range(kt + 1):
+        one[j * nds: j * nds + 3] = 1.0
+    tot = 0.0
+    for el in range(E.shape[0]):
+        T = xo.make_trafo(P[E[el]], E[el])
+        q, tv, w = xo.spacetime_cut_rule(T, lset_st[:, E[el]], kl, dom, ot, os_)
+        if not len(w):
+            continue
+        if terms is not None:
+            tot += one @ xo.elmat_st_from_rule(T, p, kt, q, tv, w, terms) @ one
+        else:
+            tot += one @ xo.elvec_st_from_rule(T, p, kt, q, tv, w, lterms)
+    return tot
+
+
+@pytest.mark.parametrize("p,kt", [(1, 1), (2, 2), (3, 3)])
+def test_reference_known_answers_through_matrices_and_vectors(p, kt):
+    P, E = unit_square()
+    neg = -np.ones((2, 4))
+    # test_spacetime_integrate_no_cut: (tref, 1/2), (tref^3, 1/4), (x, 1/2), (tref^2 (x^2+y^2), 2/9)
+    assert abs(st_sum(P, E, neg, 1, NEG, 1, 0, p, kt, lterms=[(ID, 1.0, 0, (0, 0, 0, 1))]) - 0.5) < 5e-15
+    assert abs(st_sum(P, E, neg, 1, NEG, 3, 0, p, kt, lterms=[(ID, 1.0, 0, (0, 0, 0, 3))]) - 0.25) < 5e-15
+    assert abs(st_sum(P, E, neg, 1, NEG, 0, 1, p, kt, lterms=[(ID, 1.0, 0, (1, 0, 0, 0))]) - 0.5) < 5e-15
+    got = st_sum(P, E, neg, 1, NEG, 2, 2, p, kt, lterms=[(ID, 1.0, 0, (2, 0, 0, 2)), (ID, 1.0, 0, (0, 2, 0, 2))])
+    assert abs(got - 2 / 9) < 5e-15
+    # test_spacetime_integrateX_via_straight_cutted_quad2Dplus1D: lset = 1 - 2x - 2t
+    ls = np.stack([1 - 2 * P[:, 0] - 2 * t for t in (0.0, 1.0)])
+    ls = np.where(np.abs(ls) < 1e-14, 1e-14, ls)
+    for dom, ref in ((POS, 1 / 8), (NEG, 7 / 8), (IF, 0.5)):
+        assert abs(st_sum(P, E, ls, 1, dom, 2 * kt, 2 * p, p, kt, terms=[(ID, ID, 1.0, 0)]) - ref) < 5e-15
+    # dt(u) v with u = 1: zero row sums; grad.grad annihilates constants
+    assert abs(st_sum(P, E, ls, 1, NEG, 2 * kt, 2 * p, p, kt, terms=[(DT, ID, 1.0, 0)])) < 1e-14
+    assert abs(st_sum(P, E, ls, 1, NEG, 2 * kt, 2 * p, p, kt, terms=[(GRAD, GRAD, 1.0, 0)])) < 1e-14
