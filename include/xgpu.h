@@ -48,7 +48,8 @@ int xgpu_create(int device, xgpu_ctx** ctx_out);
 void xgpu_destroy(xgpu_ctx* ctx);
 int xgpu_set_stream(xgpu_ctx* ctx, void* cuda_stream);
 /* tuning switches (no reference counterpart).  "elmat_dmma": element-matrix contraction on FP64
- * tensor-core tiles: -1 never, 0 (default) at FE order >= 3, 1 also at order 2 */
+ * tensor-core tiles: -1 never, 0 (default) at FE order >= 3, 1 also at order 2.  "elmat_st_tp": space-time element
+ * matrices on the tensor-structured kernel where instantiated (default 1; 0 = always the generic kernel) */
 int xgpu_set_option(xgpu_ctx* ctx, const char* key, int value);
 /* Isoparametric mesh deformation — the state NGSolve keeps in the mesh (`mesh.SetDeformation(gf)`, set and
  * unset around every assembly by the `deformation=` argument of dCut / dFacetPatch / Integrate,
@@ -85,6 +86,12 @@ int xgpu_h1_shapes_host(int dim, int order, const int32_t* vnum_host, const doub
  * of dimension `dim` from nodal P1 level-set values.  cut_ratio may be NULL. */
 int xgpu_classify(xgpu_ctx* ctx, int dim, int64_t ne, const int32_t* el_vtx, const double* phi,
                   uint32_t* bits_neg, uint32_t* bits_pos, uint32_t* bits_if, double* cut_ratio);
+/* CutInformation::Update with a space-time level set (time_order >= 0, cutinfo.cpp:90-124): the part volumes are the
+ * weight sums of the order-0 NEG and POS rules (xgpu_cutquad_st_*; added in rule order), the element is IF iff both are
+ * > 0, NEG iff only the NEG one, POS otherwise; cut_ratio = neg / (neg + pos) (nullable). */
+int xgpu_rule_element_sums(xgpu_ctx* ctx, int64_t n, const int64_t* offsets, const double* wts, double* sums);
+int xgpu_classify_volumes(xgpu_ctx* ctx, int64_t ne, const double* vol_neg, const double* vol_pos,
+                          uint32_t* bits_neg, uint32_t* bits_pos, uint32_t* bits_if, double* cut_ratio);
 /* BitArray algebra used by cutinfo.cpp:127-132 (UNCUT/HASNEG/HASPOS) and by user code.
  * op: 0 OR, 1 AND, 2 ANDNOT (a & ~b), 3 NOT a, 4 COPY a, 5 CLEAR, 6 SET (tail bits stay 0) */
 int xgpu_bitset_op(xgpu_ctx* ctx, int op, const uint32_t* a, const uint32_t* b, uint32_t* out, int64_t nbits);
@@ -149,6 +156,12 @@ int xgpu_cutquad_st_fill(xgpu_ctx* ctx, int dim, int64_t n, const int32_t* elems
 int xgpu_integrate_monomial(xgpu_ctx* ctx, int dim, int64_t n, const int32_t* elems, const int32_t* el_vtx,
                             const double* vtx_xyz, const int64_t* offsets, const double* pts,
                             const double* wts, const int* expo_host, double* result_host);
+
+/* space-time Integrate (cutint/python_cutint.cpp:21-163 with time_order >= 0; tests/pytests/test_spacetimecutrule.py):
+ * sum_q w_q |det F| x^e0 y^e1 z^e2 tref^e3 over a space-time rule batch (xgpu_cutquad_st_*); expo_host has 4 entries. */
+int xgpu_integrate_monomial_st(xgpu_ctx* ctx, int dim, int64_t n, const int32_t* elems, const int32_t* el_vtx,
+                               const double* vtx_xyz, const int64_t* offsets, const double* pts, const double* tvals,
+                               const double* wts, const int* expo_host, double* result_host);
 
 /* the same over BOUNDARY elements (dCut(..., vb=BND), tests/pytests/test_bndcut.py): simplices of dimension `dim`
  * embedded in R^sdim (segments in 2D / 3D, triangles in 3D), measure sqrt(det F^T F); rules from

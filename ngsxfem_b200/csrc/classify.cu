@@ -371,6 +371,57 @@ extern "C" int xgpu_bitset_rank(xgpu_ctx* ctx, const uint32_t* bits, int64_t nbi
   return XGPU_OK;
 }
 
+// ---- classification from part volumes (space-time CutInfo: cutinfo.cpp:90-124 with time_order >= 0) ----
+// sums[i] = sum of the weights of element i's rule, added in rule order (as `for (auto w : wei_arr) part_vol += w`)
+__global__ void __launch_bounds__(256) k_rule_sums(int64_t n, const int64_t* __restrict__ offsets,
+                                                   const double* __restrict__ wts, double* __restrict__ sums)
+{
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double s = 0.0;
+  for (int64_t q = offsets[i]; q < offsets[i + 1]; q++) s += wts[q];
+  sums[i] = s;
+}
+
+// NEG volume > 0 and POS volume > 0 -> IF; only NEG > 0 -> NEG; else POS; ratio = neg / (neg + pos) (cutinfo.cpp:104-124)
+__global__ void __launch_bounds__(256) k_classify_volumes(int64_t ne, const double* __restrict__ vneg,
+                                                          const double* __restrict__ vpos, uint32_t* __restrict__ bneg,
+                                                          uint32_t* __restrict__ bpos, uint32_t* __restrict__ bif,
+                                                          double* __restrict__ ratio)
+{
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const bool in = i < ne;
+  const double a = in ? vneg[i] : 0.0, b = in ? vpos[i] : 0.0;
+  const bool hn = in && a > 0.0, hp = b > 0.0;
+  const unsigned mn = __ballot_sync(0xffffffffu, hn && !hp);
+  const unsigned mi = __ballot_sync(0xffffffffu, hn && hp);
+  const unsigned mp = __ballot_sync(0xffffffffu, in && !hn);
+  if (in && ratio) ratio[i] = a / (a + b);
+  if ((threadIdx.x & 31) == 0 && in) {
+    bneg[i >> 5] = mn; bif[i >> 5] = mi; bpos[i >> 5] = mp;
+  }
+}
+
+extern "C" int xgpu_rule_element_sums(xgpu_ctx* ctx, int64_t n, const int64_t* offsets, const double* wts, double* sums)
+{
+  if (!ctx || !offsets || !sums) return xgpu_fail(ctx, XGPU_ERR_ARG, "xgpu_rule_element_sums: bad argument");
+  if (n == 0) return XGPU_OK;
+  k_rule_sums<<<nblk(n, 256), 256, 0, ctx->stream>>>(n, offsets, wts, sums);
+  XGPU_LAUNCH_CHECK(ctx);
+  return XGPU_OK;
+}
+
+extern "C" int xgpu_classify_volumes(xgpu_ctx* ctx, int64_t ne, const double* vol_neg, const double* vol_pos,
+                                     uint32_t* bits_neg, uint32_t* bits_pos, uint32_t* bits_if, double* cut_ratio)
+{
+  if (!ctx || !vol_neg || !vol_pos || !bits_neg || !bits_pos || !bits_if)
+    return xgpu_fail(ctx, XGPU_ERR_ARG, "xgpu_classify_volumes: bad argument");
+  if (ne == 0) return XGPU_OK;
+  k_classify_volumes<<<nblk(ne, 256), 256, 0, ctx->stream>>>(ne, vol_neg, vol_pos, bits_neg, bits_pos, bits_if, cut_ratio);
+  XGPU_LAUNCH_CHECK(ctx);
+  return XGPU_OK;
+}
+
 extern "C" int xgpu_threshold_elements(xgpu_ctx* ctx, int64_t ne, const double* cut_ratio, int dt, double threshold,
                                        uint32_t* bits_out)
 {

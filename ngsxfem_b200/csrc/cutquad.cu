@@ -161,7 +161,8 @@ __global__ void __launch_bounds__(128) k_integrate(int64_t n, const int32_t* __r
                                                    const int32_t* __restrict__ el_vtx, const double* __restrict__ vtx_xyz,
                                                    const int64_t* __restrict__ offsets, const double* __restrict__ pts,
                                                    const double* __restrict__ wts, int e0, int e1, int e2,
-                                                   double* __restrict__ elsum)
+                                                   double* __restrict__ elsum,
+                                                   const double* __restrict__ tvals = nullptr, int et = 0)
 {
   const int lane = threadIdx.x & 31;
   const int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -191,6 +192,7 @@ __global__ void __launch_bounds__(128) k_integrate(int64_t n, const int32_t* __r
       for (int k = 0; k < D + 1; k++) xc += lam[k] * vx[k][c];
       for (int e = 0; e < ex[c]; e++) f *= xc;
     }
+    if (tvals) { const double t = tvals[q]; for (int e = 0; e < et; e++) f *= t; }  // tref^et (space-time rules)
     s += wts[q] * meas * f;
   }
 #pragma unroll
@@ -370,6 +372,29 @@ extern "C" int xgpu_integrate_monomial(xgpu_ctx* ctx, int dim, int64_t n, const 
   if (dim == 3) k_integrate<3><<<grid, 128, 0, ctx->stream>>>(n, elems, el_vtx, vtx_xyz, offsets, pts, wts, e0, e1, e2, elsum);
   else if (dim == 2) k_integrate<2><<<grid, 128, 0, ctx->stream>>>(n, elems, el_vtx, vtx_xyz, offsets, pts, wts, e0, e1, e2, elsum);
   else k_integrate<1><<<grid, 128, 0, ctx->stream>>>(n, elems, el_vtx, vtx_xyz, offsets, pts, wts, e0, e1, e2, elsum);
+  XGPU_LAUNCH_CHECK(ctx);
+  return xgpu_sum_f64(ctx, elsum, n, elsum + n, result_host);
+}
+
+extern "C" int xgpu_integrate_monomial_st(xgpu_ctx* ctx, int dim, int64_t n, const int32_t* elems, const int32_t* el_vtx,
+                                          const double* vtx_xyz, const int64_t* offsets, const double* pts,
+                                          const double* tvals, const double* wts, const int* expo_host, double* result_host)
+{
+  if (!ctx || dim < 1 || dim > 3 || !result_host || !tvals || !expo_host)
+    return xgpu_fail(ctx, XGPU_ERR_ARG, "xgpu_integrate_monomial_st: bad argument");
+  if (ctx->def_order > 0) return xgpu_fail(ctx, XGPU_ERR_UNSUPPORTED, "space-time integrals do not support a mesh deformation");
+  *result_host = 0.0;
+  if (n == 0) return XGPU_OK;
+  void* p;
+  const int64_t nb = (n + 4095) / 4096;
+  int rc = xgpu_scratch(ctx, 1, sizeof(double) * (n + nb + 2), &p);
+  if (rc) return rc;
+  double* elsum = (double*)p;
+  const int e0 = expo_host[0], e1 = dim > 1 ? expo_host[1] : 0, e2 = dim > 2 ? expo_host[2] : 0, et = expo_host[3];
+  const unsigned grid = nblk(n * 32, 128);
+  if (dim == 3) k_integrate<3><<<grid, 128, 0, ctx->stream>>>(n, elems, el_vtx, vtx_xyz, offsets, pts, wts, e0, e1, e2, elsum, tvals, et);
+  else if (dim == 2) k_integrate<2><<<grid, 128, 0, ctx->stream>>>(n, elems, el_vtx, vtx_xyz, offsets, pts, wts, e0, e1, e2, elsum, tvals, et);
+  else k_integrate<1><<<grid, 128, 0, ctx->stream>>>(n, elems, el_vtx, vtx_xyz, offsets, pts, wts, e0, e1, e2, elsum, tvals, et);
   XGPU_LAUNCH_CHECK(ctx);
   return xgpu_sum_f64(ctx, elsum, n, elsum + n, result_host);
 }

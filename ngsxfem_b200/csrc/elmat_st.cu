@@ -15,16 +15,9 @@
 #include "cutgeom.cuh"
 #include "deform.cuh"
 #include "h1.cuh"
+#include "elmat_st.cuh"
 
 #define XG_ST_MAXT 4  // time orders 0..3
-#define XG_ST_MAXTERMS 8
-
-struct StTermsDev {
-  int n;
-  int op_trial[XG_ST_MAXTERMS], op_test[XG_ST_MAXTERMS], hpow[XG_ST_MAXTERMS];
-  int expo[XG_ST_MAXTERMS][4];  // element vectors only: x^e0 y^e1 z^e2 tref^e3
-  double coef[XG_ST_MAXTERMS];
-};
 
 namespace {
 
@@ -366,6 +359,10 @@ extern "C" int xgpu_elmat_st(xgpu_ctx* ctx, int dim, int fe_order, int time_fe_o
     const bool ok = (ou == 1 && ot == 1) || ((ou == 0 || ou == XGPU_OP_DT) && (ot == 0 || ot == XGPU_OP_DT));
     if (!ok) return xgpu_fail(ctx, XGPU_ERR_UNSUPPORTED, "xgpu_elmat_st: unsupported operator pair (menu: ID/DT x ID/DT, GRAD.GRAD)");
     T.op_trial[t] = ou; T.op_test[t] = ot; T.hpow[t] = terms_host[t].hpow; T.coef[t] = terms_host[t].coef;
+  }
+  if (ctx->opt_st_tp) {  // tensor-structured kernel for the common orders (elmat_st_tp.cu)
+    rc = xg_launch_elmat_st_tp(ctx, dim, fe_order, time_fe_order, n, elems, el_vtx, vtx_xyz, offsets, pts, tvals, wts, T, accumulate, slots, mats);
+    if (rc != 1) return rc;
   }
   if (dim == 3) return launch_elmat_st<3>(ctx, fe_order, time_fe_order, n, elems, el_vtx, vtx_xyz, offsets, pts, tvals, wts, T, accumulate, slots, mats);
   if (dim == 2) return launch_elmat_st<2>(ctx, fe_order, time_fe_order, n, elems, el_vtx, vtx_xyz, offsets, pts, tvals, wts, T, accumulate, slots, mats);

@@ -190,12 +190,12 @@ class CutInfo:
     def Update(self, levelset, subdivlvl=0, time_order=-1, heapsize=1000000):
         if subdivlvl != 0:
             raise XgpuError("subdivlvl != 0 selects ngsxfem's legacy subdivision path: not provided")
-        if time_order > 0:
-            raise XgpuError("CutInfo.Update with time_order > 0 is not provided (time_order=0 suffices, cutinfo.cpp:66-67)")
         m = self.mesh
-        phi = _lset_vec(levelset, m)
         ctx = default_ctx(m.device.index)
         b = self._ba
+        if hasattr(levelset, "timeFE") or time_order >= 0:
+            return self._update_spacetime(levelset, max(time_order, 0), ctx)
+        phi = _lset_vec(levelset, m)
         ops.classify(m.dim, m.elements, phi, ctx=ctx,
                      out=(b[CDOM_NEG].bits, b[CDOM_POS].bits, b[CDOM_IF].bits, self.cut_ratio))
         # cutinfo.cpp:127-132
@@ -211,6 +211,36 @@ class CutInfo:
             ops.bitset_op(ops.BIT_OR, bb[CDOM_NEG].bits, bb[CDOM_IF].bits, nb, out=bb[HASNEG].bits, ctx=ctx)
             ops.bitset_op(ops.BIT_OR, bb[CDOM_POS].bits, bb[CDOM_IF].bits, nb, out=bb[HASPOS].bits, ctx=ctx)
         ctx.raise_on_geometry_error()
+        self._updated = True
+
+    def _update_spacetime(self, levelset, time_order, ctx):
+        """cutinfo.cpp:90-124 with a space-time level set: the part volumes are the weight sums of the order-0
+        space-time NEG / POS rules over the slab (time_order = 0 suffices to detect the cut topology, :66-67); a
+        merely spatial level set is constant in time (cutint/xintegration.cpp:60-70).  BND elements: the reference
+        expects no NEG part there (:101-102), they are marked POS."""
+        m = self.mesh
+        b = self._ba
+        if hasattr(levelset, "timeFE"):
+            phi_st, kt = levelset.vec, levelset.timeFE.order
+        else:
+            phi_st, kt = _lset_vec(levelset, m).reshape(1, -1).contiguous(), 0
+        vols = []
+        for np_ in (POS, NEG):
+            off, _, _, w = ops.cutquad_st(m.dim, None, m.elements, m.points, phi_st, kt, np_, time_order, 0, ctx=ctx)
+            vols.append(ops.rule_element_sums(off, w, ctx=ctx))
+        ctx.raise_on_geometry_error()
+        ops.classify_volumes(vols[1], vols[0], (b[CDOM_NEG].bits, b[CDOM_POS].bits, b[CDOM_IF].bits, self.cut_ratio), ctx=ctx)
+        ops.bitset_op(ops.BIT_OR, b[CDOM_NEG].bits, b[CDOM_POS].bits, m.ne, out=b[UNCUT].bits, ctx=ctx)
+        ops.bitset_op(ops.BIT_OR, b[CDOM_NEG].bits, b[CDOM_IF].bits, m.ne, out=b[HASNEG].bits, ctx=ctx)
+        ops.bitset_op(ops.BIT_OR, b[CDOM_POS].bits, b[CDOM_IF].bits, m.ne, out=b[HASPOS].bits, ctx=ctx)
+        b[NO].Clear(); b[ANY].Set()
+        if self._bnd is not None and self._bnd[0].shape[0] > 0:
+            _, bb, br = self._bnd
+            for k in (CDOM_NEG, CDOM_IF, HASNEG, NO):
+                bb[k].Clear()
+            for k in (CDOM_POS, UNCUT, HASPOS, ANY):
+                bb[k].Set()
+            br.zero_()
         self._updated = True
 
     def _bnd_or_raise(self):

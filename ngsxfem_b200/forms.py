@@ -769,8 +769,12 @@ z = CoordMonomial((0, 0, 1))
 
 def Integrate(levelset_domain=None, mesh=None, cf=1.0, order=5, time_order=-1, deformation=None, heapsize=1000000):
     """python/__init__.py:361-439 -> cutint/python_cutint.cpp:21-163: sum_q w_q |det F| cf(x_q)."""
-    if time_order >= 0:
-        raise XgpuError("Integrate: space-time is not on the accelerated path yet")
+    ld = levelset_domain
+    if "time_order" in ld and ld["time_order"] is not None and ld["time_order"] >= 0:
+        time_order = ld["time_order"]
+    if time_order >= 0 or ld.get("tref", None) is not None or hasattr(cf, "expo") and len(cf.expo) == 4:
+        from . import spacetime
+        return spacetime.integrate(ld, mesh, cf, order, time_order, deformation)
     if isinstance(cf, numbers.Number):
         cf = CoordMonomial((0, 0, 0), cf)
     if not isinstance(cf, CoordMonomial):

@@ -255,6 +255,34 @@ def integrate_monomial(dim, elems, el_vtx, vtx_xyz, off, pts, wts, expo, ctx=Non
     return res.value
 
 
+def rule_element_sums(off, wts, ctx=None):
+    """per-element sums of the rule weights, added in rule order"""
+    ctx = ctx or default_ctx()
+    n = off.numel() - 1
+    out = torch.empty(n, dtype=torch.float64, device=off.device)
+    ctx.check(ctx.lib.xgpu_rule_element_sums(ctx.h, n, ptr(off), ptr(wts), ptr(out)))
+    return out
+
+
+def classify_volumes(vol_neg, vol_pos, out, ctx=None):
+    """out = (bits_neg, bits_pos, bits_if, cut_ratio or None), cutinfo.cpp:104-124"""
+    ctx = ctx or default_ctx()
+    ctx.check(ctx.lib.xgpu_classify_volumes(ctx.h, vol_neg.numel(), ptr(vol_neg), ptr(vol_pos), ptr(out[0]), ptr(out[1]),
+                                            ptr(out[2]), ptr(out[3])))
+    return out
+
+
+def integrate_monomial_st(dim, elems, el_vtx, vtx_xyz, off, pts, tvals, wts, expo, ctx=None):
+    """space-time rule batch: expo = (e0, e1, e2, e_tref)"""
+    ctx = ctx or default_ctx()
+    n = el_vtx.shape[0] if elems is None else elems.numel()
+    ex = (C.c_int * 4)(*[int(e) for e in expo])
+    res = C.c_double(0.0)
+    ctx.check(ctx.lib.xgpu_integrate_monomial_st(ctx.h, dim, n, ptr(elems), ptr(_i32(el_vtx)), ptr(_f64(vtx_xyz)), ptr(off),
+                                                 ptr(pts), ptr(tvals), ptr(wts), ex, C.byref(res)))
+    return res.value
+
+
 def integrate_monomial_bnd(dim, sdim, elems, el_vtx, vtx_xyz, off, pts, wts, expo, ctx=None):
     """boundary elements: simplices of dimension dim embedded in R^sdim"""
     ctx = ctx or default_ctx()

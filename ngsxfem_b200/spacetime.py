@@ -408,3 +408,24 @@ def assemble_linear(lf):
     plan = ops.adjacency_plan(sp.ndof, [table], ctx=ctx)
     ops.vec_scatter(plan, [(table, v_A)], out=lf.vec)
     return lf
+
+
+def integrate(ld, mesh, cf, order, time_order, deformation):
+    """Integrate(levelset_domain, mesh, cf, order, time_order) on space-time rules (python/__init__.py:361-439,
+    cutint/python_cutint.cpp:21-163): cf = constant or coef * x^a y^b z^c tref^d"""
+    if deformation is not None:
+        raise XgpuError("space-time Integrate does not support a mesh deformation")
+    if ld.get("subdivlvl", 0) != 0:
+        raise XgpuError("subdivlvl != 0: legacy path not provided")
+    if isinstance(cf, numbers.Number):
+        cf = STMonomial((0, 0, 0, 0), cf)
+    elif isinstance(cf, CoordMonomial):
+        cf = STMonomial(tuple(cf.expo) + (0,), cf.coef)
+    if not isinstance(cf, STMonomial):
+        raise XgpuError("Integrate: cf must be a constant or a monomial in x, y, z, tref")
+    if "order" in ld and ld["order"] is not None and ld["order"] >= 0:
+        order = ld["order"]
+    ctx = default_ctx(mesh.device.index)
+    dx = CutDifferentialSymbol(ld["levelset"], ld["domain_type"], order, None, None, time_order=time_order, tref=ld.get("tref", None))
+    off, q, tv, w = st_rule(mesh, None, dx, order, None, ctx)
+    return cf.coef * ops.integrate_monomial_st(mesh.dim, None, mesh.elements, mesh.points, off, q, tv, w, cf.expo, ctx=ctx)

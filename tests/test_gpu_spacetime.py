@@ -9,7 +9,7 @@ import pytest
 import torch
 
 import ngsxfem_b200 as xf
-from ngsxfem_b200 import ops
+from ngsxfem_b200 import _lib, ops
 from oracle import xoracle as xo
 
 pytestmark = pytest.mark.gpu
@@ -37,7 +37,8 @@ def make_mesh(dim, n):
 
 
 @pytest.mark.parametrize("dim,n,p,kt,dt", [(3, 3, 1, 2, NEG), (3, 3, 2, 1, IF), (3, 2, 2, 2, NEG), (2, 5, 1, 1, POS), (2, 5, 2, 2, NEG),
-                                            (2, 4, 3, 3, IF), (1, 7, 2, 2, NEG), (3, 2, 3, 1, NEG)])
+                                            (2, 4, 3, 3, IF), (1, 7, 2, 2, NEG), (3, 2, 3, 1, NEG), (3, 3, 1, 1, IF), (2, 5, 1, 2, NEG),
+                                            (2, 5, 2, 1, IF), (3, 2, 1, 0, NEG)])
 def test_spacetime_element_matrices_match_oracle(dim, n, p, kt, dt):
     mesh = make_mesh(dim, n)
     ls = moving_lset(mesh, xf.ScalarTimeFE(2))
@@ -65,6 +66,14 @@ def test_spacetime_element_matrices_match_oracle(dim, n, p, kt, dt):
     # run-to-run bit reproducibility
     m2 = ops.elmat_st(dim, p, kt, None, mesh.elements, mesh.points, off, q, tv, w, terms)
     assert torch.equal(m, m2)
+    # the generic kernel (k_elmat_st) and the tensor-structured one (k_elmat_st_tp, default where instantiated) agree
+    ctx = _lib.default_ctx()
+    ctx.set_option("elmat_st_tp", 0)
+    try:
+        mg = ops.elmat_st(dim, p, kt, None, mesh.elements, mesh.points, off, q, tv, w, terms)
+    finally:
+        ctx.set_option("elmat_st_tp", 1)
+    assert np.linalg.norm(mg.cpu().numpy() - mo) <= 1e-12 * np.linalg.norm(mo)
 
 
 @pytest.mark.parametrize("dim,n,p,kt,dt", [(3, 3, 1, 2, NEG), (3, 2, 2, 1, IF), (2, 5, 2, 2, NEG), (2, 4, 4, 3, POS), (1, 7, 3, 1, NEG)])
@@ -238,3 +247,77 @@ def test_config5_shape_assembles_and_integrates_to_the_cylinder_volume():
     got = float(one @ (m.mat * one))
     assert abs(got - vol) < 1e-13
     assert abs(vol - 4 / 3 * np.pi * 0.3 ** 3) < 0.02   # polyhedral approximation of the ball, constant in time
+
+
+# ---------------------------------------------------------------- Integrate on space-time rules: the reference's own tests
+@pytest.mark.parametrize("cf,ref,so,to", [(lambda: xf.tref, 0.5, 0, 1), (lambda: xf.tref ** 3, 0.25, 0, 3),
+                                          (lambda: xf.x, 0.5, 1, 0), (lambda: xf.tref * xf.tref * xf.x * xf.x, 1 / 9, 2, 2),
+                                          (lambda: xf.tref * xf.tref * xf.y * xf.y, 1 / 9, 2, 2)])
+def test_spacetime_integrate_no_cut(cf, ref, so, to):
+    """tests/pytests/test_spacetimecutrule.py:14-37 (tref^2 (x^2+y^2) = 2/9 split into its two monomials)"""
+    mesh = xf.MakeStructured2DMesh(nx=1, ny=1, device=DEV)
+    ls = xf.SpaceTimeGridFunction(mesh, xf.ScalarTimeFE(1), -torch.ones((2, mesh.nv), dtype=torch.float64))
+    val = xf.Integrate(levelset_domain={"levelset": ls, "domain_type": NEG}, cf=cf(), mesh=mesh, order=so, time_order=to)
+    assert abs(val - ref) < 5e-15
+
+
+@pytest.mark.parametrize("dom,ref", [(POS, 1 / 8), (NEG, 7 / 8), (IF, 0.5)])
+def test_spacetime_integrate_moving_plane(dom, ref):
+    """tests/pytests/test_spacetimecutrule.py:40-69"""
+    mesh = xf.MakeStructured2DMesh(nx=1, ny=1, device=DEV)
+    ls = xf.SpaceTimeInterpolateToP1(lambda x, y, t: 1 - 2 * x - 2 * t, mesh, xf.ScalarTimeFE(1))
+    val = xf.Integrate(levelset_domain={"levelset": ls, "domain_type": dom}, cf=1.0, mesh=mesh, order=0, time_order=0)
+    assert abs(val - ref) < 5e-15
+    # a spatial level set under a space-time rule is constant in time (cutint/xintegration.cpp:60-70)
+    l0 = xf.InterpolateToP1(lambda x, y: x - 0.25, mesh)
+    v0 = xf.Integrate(levelset_domain={"levelset": l0, "domain_type": NEG, "time_order": 2}, cf=xf.tref, mesh=mesh, order=1)
+    assert abs(v0 - 0.25 * 0.5) < 5e-15
+    # fixed reference time (dmesh(tref=...) style domain)
+    v1 = xf.Integrate(levelset_domain={"levelset": l0, "domain_type": POS, "tref": 0.5}, cf=xf.tref * xf.x, mesh=mesh, order=1)
+    assert abs(v1 - 0.5 * (0.5 - 0.25 ** 2 / 2)) < 5e-15
+
+
+# ---------------------------------------------------------------- CutInfo on a time slab
+@pytest.mark.parametrize("dim,n,kt,to", [(2, 6, 1, 0), (2, 5, 2, 2), (3, 3, 2, 0), (1, 9, 1, 1)])
+def test_spacetime_cutinfo_matches_oracle(dim, n, kt, to):
+    """CutInformation::Update (xfem/cutinfo.cpp:90-124) with a space-time level set: part volumes from the order-0
+    space-time rules; bit-exact BitArrays against the oracle's rules, cut ratios to 1e-13"""
+    mesh = make_mesh(dim, n)
+    ls = moving_lset(mesh, xf.ScalarTimeFE(kt))
+    ci = xf.CutInfo(mesh, ls, time_order=to)
+    P, E, L = mesh.points.cpu().numpy(), mesh.elements.cpu().numpy(), ls.vec.cpu().numpy()
+    neg = np.zeros(mesh.ne, bool); pos = np.zeros(mesh.ne, bool); cut = np.zeros(mesh.ne, bool)
+    ratio = np.zeros(mesh.ne)
+    for el in range(mesh.ne):
+        T = xo.make_trafo(P[E[el]], E[el])
+        pv = {}
+        for np_ in (POS, NEG):
+            _, _, w = xo.spacetime_cut_rule(T, L[:, E[el]], kt, np_, to, 0)
+            s = 0.0
+            for x in w:
+                s += x
+            pv[np_] = s
+        ratio[el] = pv[NEG] / (pv[NEG] + pv[POS])
+        if pv[NEG] > 0:
+            (cut if pv[POS] > 0 else neg)[el] = True
+        else:
+            pos[el] = True
+    got = {k: ci.GetElementsOfType(k).to_numpy() for k in (xf.NEG, xf.POS, xf.IF)}
+    assert (got[xf.NEG] == neg).all() and (got[xf.POS] == pos).all() and (got[xf.IF] == cut).all()
+    assert cut.any() and neg.any() and pos.any()
+    assert np.allclose(ci.GetCutRatios().cpu().numpy(), ratio, rtol=1e-13, atol=1e-15)
+    hasneg = ci.GetElementsOfType(xf.HASNEG).to_numpy()
+    assert (hasneg == (neg | cut)).all()
+    # an element that is cut at ANY time of the slab is IF: superset of the spatial IF sets at the time nodes
+    for j in range(kt + 1):
+        cj = xf.CutInfo(mesh, xf.GridFunction(mesh, ls.vec[j]))
+        assert not (cj.GetElementsOfType(xf.IF).to_numpy() & ~cut).any()
+
+
+def test_spacetime_cutinfo_of_a_spatial_level_set_equals_the_spatial_one():
+    mesh = make_mesh(3, 4)
+    l0 = xf.InterpolateToP1(lambda x, y, z: torch.sqrt((x - .5) ** 2 + (y - .5) ** 2 + (z - .5) ** 2) - 0.3, mesh)
+    a, b = xf.CutInfo(mesh, l0), xf.CutInfo(mesh, l0, time_order=0)
+    for k in (xf.NEG, xf.POS, xf.IF, xf.HASNEG, xf.HASPOS, xf.UNCUT):
+        assert (a.GetElementsOfType(k).to_numpy() == b.GetElementsOfType(k).to_numpy()).all()
+    assert torch.allclose(a.GetCutRatios(), b.GetCutRatios(), rtol=1e-13, atol=1e-15)

@@ -38,11 +38,11 @@ ls = xf.SpaceTimeInterpolateToP1(
 print(f"config 5: n={n5} ne={mesh.ne}, P1 x P2 space-time FE (12 dofs / tet), time_order 4", flush=True)
 (off, q, tv, w), t_rule_all = timed("space-time NEG rule on ALL elements (order 2 x 4)",
                                     lambda: ops.cutquad_st(3, None, mesh.elements, mesh.points, ls.vec, 2, NEG, 4, 2))
-cnt = off[1:] - off[:-1]
-vol = float(w.sum()) / n5 ** 3
-active = xf.BitArray.from_numpy((cnt > 0).cpu().numpy(), dev)
+vol = xf.Integrate({"levelset": ls, "domain_type": NEG}, mesh=mesh, cf=1.0, order=2, time_order=4)
+del off, q, tv, w
+ci, t_ci = timed("CutInfo(mesh, lset_st, time_order=0) on the slab", lambda: xf.CutInfo(mesh, ls, time_order=0))
+active = ci.GetElementsOfType(xf.HASNEG)
 nact = active.NumSet()
-del off, q, tv, w, cnt
 V = xf.SpaceTimeFESpace(xf.Restrict(xf.H1(mesh, order=1), active), tfe)
 u, v = V.TnT()
 
