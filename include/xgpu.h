@@ -242,6 +242,15 @@ int xgpu_facetpatch(xgpu_ctx* ctx, int dim, int fe_order, int64_t n, const int32
                     const int32_t* facet_els, const int32_t* el_vtx, const double* vtx_xyz,
                     int order, double coef, int hpow, double* mats);
 
+/* space-time ghost penalty: SymbolicFacetPatchBilinearFormIntegrator with time_order >= 0 (tensor-product rule in time,
+ * xfem/symboliccutbfi.cpp:2095-2160) or a fixed reference time (time_order < 0: tref, :2162-2177) on a SpaceTimeFE.  On an
+ * undeformed mesh the patch map does not depend on time (:2038-2040), so the matrix is (time matrix) kron (spatial patch
+ * matrix of xgpu_facetpatch).  mats: n x (2 nd) x (2 nd), nd = nd_s*(time_fe_order+1), layout [el1 dofs ; el2 dofs], each
+ * time-major. */
+int xgpu_facetpatch_st(xgpu_ctx* ctx, int dim, int fe_order, int time_fe_order, int64_t n, const int32_t* facets,
+                       const int32_t* facet_els, const int32_t* el_vtx, const double* vtx_xyz, int order,
+                       int time_order, double tref, double coef, int hpow, double* mats);
+
 /* ---------------------------------------------------------------- (e) sparse assembly
  * RestrictedBilinearForm::GetGraph (utils/restrictedblf.cpp:142-163) + NGSolve MatrixGraph /
  * SparseMatrix::AddElementMatrix.  A batch is a table of dof rows (nrows x width, -1 = unused)

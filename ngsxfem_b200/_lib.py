@@ -97,6 +97,8 @@ _SIGS = {
     "xgpu_elvec_st": (C.c_int, [VP, C.c_int, C.c_int, C.c_int, C.c_int64, VP, VP, VP, VP, VP, VP, VP, C.POINTER(StLTerm),
                                 C.c_int, C.c_int, VP, VP]),
     "xgpu_facetpatch": (C.c_int, [VP, C.c_int, C.c_int, C.c_int64, VP, VP, VP, VP, C.c_int, C.c_double, C.c_int, VP]),
+    "xgpu_facetpatch_st": (C.c_int, [VP, C.c_int, C.c_int, C.c_int, C.c_int64, VP, VP, VP, VP, C.c_int, C.c_int, C.c_double,
+                                     C.c_double, C.c_int, VP]),
     "xgpu_csr_plan": (C.c_int, [VP, C.c_int64, C.POINTER(Batch), C.c_int, C.POINTER(VP), c_i64p]),
     "xgpu_csr_pattern": (C.c_int, [VP, VP, VP, VP]),
     "xgpu_csr_scatter": (C.c_int, [VP, VP, C.POINTER(Batch), C.c_int, VP, VP, VP]),

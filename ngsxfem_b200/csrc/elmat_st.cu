@@ -276,6 +276,25 @@ __global__ void __launch_bounds__(128) k_elvec_st(
   }
 }
 
+// space-time facet patch = (time matrix) kron (spatial facet-patch matrix): out[(h,j,i),(g,l,k)] = T[j][l] in[(h,i),(g,k)],
+// h, g = element of the patch, time-major dofs per element.  One thread per output entry, coalesced stores.
+struct TimeMat { int nt; double t[XG_ST_MAXT * XG_ST_MAXT]; };
+__global__ void __launch_bounds__(256) k_kron_time(int64_t n, int nds, TimeMat T, const double* __restrict__ in,
+                                                   double* __restrict__ out)
+{
+  const int nt = T.nt, ws = 2 * nds, wo = ws * nt;
+  const int64_t per = (int64_t)wo * wo;
+  const int64_t total = n * per;
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t f = idx / per;
+    const int rc = (int)(idx - f * per);
+    const int r = rc / wo, c = rc - r * wo;
+    const int h = r / (nds * nt), rj = (r - h * nds * nt) / nds, ri = r - h * nds * nt - rj * nds;
+    const int g = c / (nds * nt), cl = (c - g * nds * nt) / nds, ck = c - g * nds * nt - cl * nds;
+    out[idx] = T.t[rj * nt + cl] * __ldg(in + f * ws * ws + (int64_t)(h * nds + ri) * ws + (g * nds + ck));
+  }
+}
+
 int st_chunk(int ndp, int D, size_t* sm)
 {
   const int PS = ndp * (2 + D) + XG_ST_MAXTERMS;
@@ -392,4 +411,54 @@ extern "C" int xgpu_elvec_st(xgpu_ctx* ctx, int dim, int fe_order, int time_fe_o
   if (dim == 3) return launch_elvec_st<3>(ctx, fe_order, time_fe_order, n, elems, el_vtx, vtx_xyz, offsets, pts, tvals, wts, T, accumulate, slots, vecs);
   if (dim == 2) return launch_elvec_st<2>(ctx, fe_order, time_fe_order, n, elems, el_vtx, vtx_xyz, offsets, pts, tvals, wts, T, accumulate, slots, vecs);
   return launch_elvec_st<1>(ctx, fe_order, time_fe_order, n, elems, el_vtx, vtx_xyz, offsets, pts, tvals, wts, T, accumulate, slots, vecs);
+}
+
+// Lagrange values on NodalTimeFE's nodes (host)
+static void st_time_shapes_host(int order, double t, double* L)
+{
+  double nd[XG_ST_MAXT] = {0.0, 1.0, 0.0, 0.0};
+  if (order == 2) { nd[1] = 0.5; nd[2] = 1.0; }
+  if (order == 3) { nd[1] = 0.5 * (1.0 - 1.0 / sqrt(5.0)); nd[2] = 0.5 * (1.0 + 1.0 / sqrt(5.0)); nd[3] = 1.0; }
+  for (int i = 0; i <= order; i++) {
+    double s = 1.0;
+    for (int j = 0; j <= order; j++) if (j != i) s *= (t - nd[j]) / (nd[i] - nd[j]);
+    L[i] = s;
+  }
+}
+
+extern "C" int xgpu_facetpatch_st(xgpu_ctx* ctx, int dim, int fe_order, int time_fe_order, int64_t n, const int32_t* facets,
+                                  const int32_t* facet_els, const int32_t* el_vtx, const double* vtx_xyz, int order,
+                                  int time_order, double tref, double coef, int hpow, double* mats)
+{
+  if (!ctx || dim < 1 || dim > 3 || fe_order < 1 || fe_order > XG_MAX_ORDER || time_fe_order < 0 || time_fe_order >= XG_ST_MAXT)
+    return xgpu_fail(ctx, XGPU_ERR_ARG, "xgpu_facetpatch_st: bad argument (space orders 1..4, time orders 0..3)");
+  if (ctx->def_order > 0) return xgpu_fail(ctx, XGPU_ERR_UNSUPPORTED, "space-time forms do not support a mesh deformation");
+  if (n == 0) return XGPU_OK;
+  const int nds = xg_h1_ndof(dim, fe_order), nt = time_fe_order + 1, ws = 2 * nds;
+  TimeMat T;
+  T.nt = nt;
+  for (int i = 0; i < XG_ST_MAXT * XG_ST_MAXT; i++) T.t[i] = 0.0;
+  double L[XG_ST_MAXT];
+  if (time_order >= 0) {  // tensor-product rule in time (symboliccutbfi.cpp:2095-2160): SelectIntegrationRule(ET_SEGM, time_order)
+    const xgpu_rule_host* rt = xgpu_rule_lookup(ctx, 1, time_order);
+    if (!rt) return xgpu_fail(ctx, XGPU_ERR_ARG, "xgpu_facetpatch_st: no time rule");
+    for (int q = 0; q < rt->n; q++) {
+      st_time_shapes_host(time_fe_order, rt->pts[3 * q], L);
+      for (int j = 0; j < nt; j++) for (int l = 0; l < nt; l++) T.t[j * nt + l] += rt->wts[q] * L[j] * L[l];
+    }
+  } else {                // fixed reference time (:2162-2177)
+    st_time_shapes_host(time_fe_order, tref, L);
+    for (int j = 0; j < nt; j++) for (int l = 0; l < nt; l++) T.t[j * nt + l] = L[j] * L[l];
+  }
+  void* p;
+  int rc = xgpu_scratch(ctx, 9, sizeof(double) * (size_t)n * ws * ws, &p);
+  if (rc) return rc;
+  rc = xgpu_facetpatch(ctx, dim, fe_order, n, facets, facet_els, el_vtx, vtx_xyz, order, coef, hpow, (double*)p);
+  if (rc) return rc;
+  const int64_t total = n * (int64_t)(ws * nt) * (ws * nt);
+  unsigned grid = nblk(total, 256);
+  if (grid > XGPU_NSM * 32) grid = XGPU_NSM * 32;
+  k_kron_time<<<grid, 256, 0, ctx->stream>>>(n, nds, T, (const double*)p, mats);
+  XGPU_LAUNCH_CHECK(ctx);
+  return XGPU_OK;
 }

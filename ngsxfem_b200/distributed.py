@@ -379,6 +379,52 @@ class MlsetGpuBackend(GpuBackend):
         return self
 
 
+class SpaceTimeGpuBackend(GpuBackend):
+    """config 5 of BASELINE.json: one space-time slab (P1/P2 in space x nodal in time) assembled element-partitioned.
+    `phi` of DistributedCutAssembly.step is the (k_l+1) x nv_local matrix of nodal level-set values (time-major).  The
+    partition carries the SPACE-TIME dof table (make_slab_partition(..., time_fe_order=k): dof (j, i) = j * ndof_space + i,
+    global key = space key * (k+1) + j, owner of the space dof).  Classification: CutInfo on the slab (part volumes of the
+    order-0 space-time rules, xfem/cutinfo.cpp:90-124); NEG and IF elements get their space-time rule from
+    xgpu_cutquad_st_* (uncut elements: the tensor-product standard rule), forms: u v + dt(u) v + grad u . grad v."""
+
+    TERMS = [(0, 0, 1.0, 0), (3, 0, 1.0, 0), (1, 1, 1.0, 0)]   # (op_trial, op_test, coef, hpow); 3 = XGPU_OP_DT
+
+    def __init__(self, space_order, time_fe_order, lset_time_order, time_order, ctx=None):
+        super().__init__(ctx)
+        self.p, self.kt, self.kl, self.time_order = int(space_order), int(time_fe_order), int(lset_time_order), int(time_order)
+
+    def bind(self, part):
+        self._xyz = part.vtx_xyz
+        return self
+
+    def classify(self, el_vtx, phi_st):
+        ops, ctx = self.ops, self.ctx
+        dim, ne = el_vtx.shape[1] - 1, el_vtx.shape[0]
+        vols = []
+        for np_ in (ops.POS, ops.NEG):
+            off, _, _, w = ops.cutquad_st(dim, None, el_vtx, self._xyz, phi_st, self.kl, np_, 0, 0, ctx=ctx)
+            vols.append(ops.rule_element_sums(off, w, ctx=ctx))
+        ctx.raise_on_geometry_error()
+        bn, bp, bi = (ops.new_bits(ne, el_vtx.device) for _ in range(3))
+        ops.classify_volumes(vols[1], vols[0], (bn, bp, bi, None), ctx=ctx)
+        return ops.bitset_to_list(bn, ne, ctx=ctx), ops.bitset_to_list(bi, ne, ctx=ctx), (bn, bp, bi, None)
+
+    def elmats(self, part, phi_st, l_neg, l_if):
+        ops, ctx, dim = self.ops, self.ctx, part.dim
+        els, xyz = part.el_vtx, part.vtx_xyz
+        out = []
+        nd = ops.h1_ndof(dim, self.p) * (self.kt + 1)
+        for l in (l_neg.contiguous(), l_if.contiguous()):
+            m = torch.zeros((l.numel(), nd, nd), dtype=torch.float64, device=els.device)
+            if l.numel():
+                off, q, tv, w = ops.cutquad_st(dim, l, els, xyz, phi_st, self.kl, ops.NEG, self.time_order, 2 * self.p, ctx=ctx)
+                if w.numel():
+                    ops.elmat_st(dim, self.p, self.kt, l, els, xyz, off, q, tv, w, self.TERMS, out=m, ctx=ctx)
+            out.append(m)
+        ctx.raise_on_geometry_error()
+        return out[0], out[1]
+
+
 # ------------------------------------------------------------------ slab partition of the structured chain (input producer)
 def structured_dof_keys(mesh, vg, nv1, NV, p, el_gid, v_owner=None, el_owner=None):
     """Global keys (any total order all ranks agree on) of the H1(order p) dofs of a sub-mesh of the structured Kuhn
@@ -427,7 +473,7 @@ def structured_dof_keys(mesh, vg, nv1, NV, p, el_gid, v_owner=None, el_owner=Non
     return gid, (torch.cat(owner) if v_owner is not None else None)
 
 
-def make_slab_partition(n, world, rank, device, fe_order=2, radius=0.4):
+def make_slab_partition(n, world, rank, device, fe_order=2, radius=0.4, time_fe_order=None):
     """Chain [0,1]^2 x [0,world] of `world` unit cubes, n^3 x 6 Kuhn tets each; rank r owns cube r
     (a contiguous element range of the global mesh) plus one halo layer of cells per neighbour.
     Level set: spheres of `radius` centred at (1/2, 1/2, j), j = 0..world for world > 1 (centres ON
@@ -475,5 +521,20 @@ def make_slab_partition(n, world, rank, device, fe_order=2, radius=0.4):
         halo_for[rank + 1] = torch.nonzero(own_cells_k == lo + n - 1).reshape(-1).to(torch.int32)
     centers = [(.5, .5, .5)] if world == 1 else [(.5, .5, float(j)) for j in range(world + 1)]
     phi = sphere_levelset(pts, centers, radius)
+    if time_fe_order is not None:
+        # space-time slab (config 5): time-major dof table, key = space key * nt + time node; the level set is the
+        # sphere chain moving in y, nodal in time on the same time nodes: (nt x nv_local)
+        import math
+        from .spacetime import ScalarTimeFE
+        nt = time_fe_order + 1
+        el_dofs = torch.cat([V.el_dofs + j * V.ndof for j in range(nt)], dim=1).to(torch.int32).contiguous()
+        gid_st = torch.cat([gid * nt + j for j in range(nt)])
+        owner_st = owner.repeat(nt)
+        phis = []
+        for t in ScalarTimeFE(time_fe_order).nodes():
+            cy = 0.5 + 0.1 * math.sin(2 * math.pi * 0.25 * t)
+            phis.append(sphere_levelset(pts, [(c[0], cy, c[2]) for c in centers], radius))
+        part = LocalPartition(3, el_vtx, 6 * n ** 3, el_rank, pts, el_dofs, V.ndof * nt, gid_st, owner_st, halo_for, fe_order, rank)
+        return part, torch.stack(phis).contiguous()
     part = LocalPartition(3, el_vtx, 6 * n ** 3, el_rank, pts, V.el_dofs, V.ndof, gid, owner, halo_for, fe_order, rank)
     return part, phi

@@ -267,18 +267,23 @@ def dCut(levelset, domain_type, order=None, subdivlvl=None, time_order=-1, level
 
 
 class FacetPatchDifferentialSymbol:
-    def __init__(self, definedonelements, order, deformation=None):
+    def __init__(self, definedonelements, order, deformation=None, time_order=-1, tref=None):
         self.definedonelements, self.order, self.deformation = definedonelements, order, deformation
+        self.time_order, self.tref = time_order, tref
 
 
 def dFacetPatch(definedonelements=None, deformation=None, time_order=-1, tref=None, downscale=None,
                 bonus_intorder=0, **kwargs):
     """python/__init__.py:749-778; bonus_intorder is accepted and ignored as in the reference"""
-    if time_order >= 0 or tref is not None or downscale not in (None, 1, 1.0):
-        raise XgpuError("dFacetPatch: space-time / downscale are not on the accelerated path yet")
+    if downscale not in (None, 1, 1.0):
+        raise XgpuError("dFacetPatch: downscale is not on the accelerated path yet")
+    if kwargs:
+        raise XgpuError(f"unsupported dFacetPatch arguments: {sorted(kwargs)}")
     if definedonelements is None:
         raise XgpuError("dFacetPatch needs definedonelements (a BitArray over the facets)")
-    return FacetPatchDifferentialSymbol(definedonelements, -1, deformation)
+    if (time_order >= 0 or tref is not None) and deformation is not None:
+        raise XgpuError("space-time dFacetPatch does not support a mesh deformation")
+    return FacetPatchDifferentialSymbol(definedonelements, -1, deformation, time_order=int(time_order), tref=tref)
 
 
 class Integral:
@@ -516,7 +521,7 @@ class BilinearForm:
         if hasattr(sp, "timeFE"):  # SpaceTimeFESpace
             from . import spacetime
             return spacetime.assemble_bilinear(self)
-        if any(isinstance(i.dx, CutDifferentialSymbol) and (i.dx.time_order >= 0 or i.dx.tref is not None) for i in self.integrals):
+        if any(i.dx.time_order >= 0 or i.dx.tref is not None for i in self.integrals):
             raise XgpuError("space-time differential symbols (time_order / tref) need a SpaceTimeFESpace")
         mesh = sp.mesh
         dim, p = mesh.dim, sp.order

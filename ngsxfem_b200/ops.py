@@ -417,6 +417,18 @@ def facetpatch(dim, fe_order, facets, facet_els, el_vtx, vtx_xyz, order, coef, h
     return out
 
 
+def facetpatch_st(dim, fe_order, time_fe_order, facets, facet_els, el_vtx, vtx_xyz, order, time_order, tref, coef, hpow, ctx=None):
+    """space-time ghost-penalty patch matrices: n x (2 nd) x (2 nd), nd = nd_s*(time_fe_order+1)"""
+    ctx = ctx or default_ctx()
+    n = facet_els.shape[0] if facets is None else facets.numel()
+    nd = h1_ndof(dim, fe_order) * (time_fe_order + 1)
+    out = torch.empty((n, 2 * nd, 2 * nd), dtype=torch.float64, device=el_vtx.device)
+    ctx.check(ctx.lib.xgpu_facetpatch_st(ctx.h, dim, fe_order, time_fe_order, n, ptr(facets), ptr(_i32(facet_els)),
+                                         ptr(_i32(el_vtx)), ptr(_f64(vtx_xyz)), int(order), int(time_order),
+                                         float(0.0 if tref is None else tref), float(coef), int(hpow), ptr(out)))
+    return out
+
+
 # ---------------------------------------------------------------- (e) sparse assembly
 class CsrPlan:
     def __init__(self, ctx, handle, nnz, ndof, nb):

@@ -17,9 +17,11 @@ import torch
 from . import ops
 from ._lib import XgpuError, default_ctx
 from .cutinfo import BitArray, GridFunction, POS, IF
-from .forms import (CoordMonomial, CutDifferentialSymbol, Integral, MeshSize, Scalar, SparseMatrixCSR)
+from .forms import (CoordMonomial, CutDifferentialSymbol, FacetPatchDifferentialSymbol, Integral, MeshSize, Scalar,
+                    SparseMatrixCSR)
 
 OP_ID, OP_GRAD, OP_DT = 0, 1, ops.OP_DT
+OP_JUMP = 9   # u - u.Other() (facet patches only; not a kernel operator code)
 
 
 class ScalarTimeFE:
@@ -144,13 +146,24 @@ def _scal(o):
 
 
 class STProxy:
-    def __init__(self, space, is_test, op=OP_ID, scal=None, fixt=None):
-        self.space, self.is_test, self.op, self.fixt = space, is_test, op, fixt
+    def __init__(self, space, is_test, op=OP_ID, scal=None, fixt=None, other=False):
+        self.space, self.is_test, self.op, self.fixt, self.other = space, is_test, op, fixt, other
         self.scal = scal or Scalar(1.0)
 
     def _with(self, op=None, scal=None, fixt=None):
         return STProxy(self.space, self.is_test, self.op if op is None else op, scal or self.scal,
-                       self.fixt if fixt is None else fixt)
+                       self.fixt if fixt is None else fixt, self.other)
+
+    def Other(self):
+        if self.op != OP_ID:
+            raise XgpuError(".Other() is supported on u / v only")
+        return STProxy(self.space, self.is_test, OP_ID, self.scal, self.fixt, other=True)
+
+    def __sub__(self, o):
+        if isinstance(o, STProxy) and o.other and not self.other and self.op == OP_ID and o.op == OP_ID \
+                and o.is_test == self.is_test and o.fixt == self.fixt:
+            return STProxy(self.space, self.is_test, OP_JUMP, self.scal, self.fixt)
+        raise XgpuError("unsupported difference of proxies (menu: u - u.Other())")
 
     def _st_grad(self):
         if self.op != OP_ID:
@@ -202,6 +215,8 @@ class STForm:
         u, v = (b, a) if a.is_test else (a, b)
         if (u.op == OP_GRAD) != (v.op == OP_GRAD):
             raise XgpuError("grad(u) must be paired with grad(v)")
+        if (u.op == OP_JUMP) != (v.op == OP_JUMP) or u.other or v.other:
+            raise XgpuError("jump terms must pair (u-u.Other()) with (v-v.Other())")
         if u.fixt != v.fixt:
             raise XgpuError("fix_tref: trial and test function must be fixed to the same reference time")
         s = u.scal * v.scal
@@ -224,7 +239,7 @@ class STForm:
         if isinstance(o, (numbers.Number, Scalar, MeshSize)):
             s = _scal(o)
             return STForm([(a, b, c * s.c, hp + s.hpow) for a, b, c, hp in self.terms], self.space, self.fixt)
-        if isinstance(o, CutDifferentialSymbol):
+        if isinstance(o, (CutDifferentialSymbol, FacetPatchDifferentialSymbol)):
             return Integral(self, o)
         return NotImplemented
 
@@ -360,10 +375,36 @@ def assemble_bilinear(blf):
         return blf
     slot_A = ops.bitset_rank(active.bits, mesh.ne, ctx=ctx)[0]
     m_A = torch.zeros((l_A.numel(), nd, nd), dtype=torch.float64, device=dev)
+    facet_batches = []
     for integ in blf.integrals:
-        if not isinstance(integ.form, STForm) or not isinstance(integ.dx, CutDifferentialSymbol):
-            raise XgpuError("space-time BilinearForm += expects a space-time form * dCut / dxtref / dmesh")
+        if not isinstance(integ.form, STForm):
+            raise XgpuError("space-time BilinearForm += expects a space-time form * dCut / dxtref / dmesh / dFacetPatch")
         terms = list(integ.form.terms)
+        if isinstance(integ.dx, FacetPatchDifferentialSymbol):
+            # space-time ghost penalty (xfem/symboliccutbfi.cpp:1982-2377 with time_order / tref): jump . jump only
+            if not all(t[0] == OP_JUMP and t[1] == OP_JUMP for t in terms):
+                raise XgpuError("dFacetPatch: only c*h^k*(u-u.Other())*(v-v.Other()) is supported")
+            t0 = integ.form.fixt if integ.form.fixt is not None else integ.dx.tref
+            if integ.dx.time_order < 0 and t0 is None:
+                raise XgpuError("SpaceTimeFE :: CalcShape called with a mere space IR")
+            if integ.dx.time_order >= 0 and t0 is not None:
+                raise XgpuError("fix_tref / tref and time_order exclude each other")
+            _, _, fe = mesh.facets()
+            l_f = integ.dx.definedonelements.indices()
+            l_f = l_f[fe[l_f.long(), 1] >= 0].contiguous()   # interior facets only (symboliccutbfi.cpp:1992)
+            if not l_f.numel():
+                continue
+            mm = None
+            for (_, _, c, hp) in terms:
+                m1 = ops.facetpatch_st(dim, p, kt, l_f, fe, mesh.elements, mesh.points, integ.dx.order, integ.dx.time_order, t0,
+                                       c, hp, ctx=ctx)
+                mm = m1 if mm is None else mm + m1
+            fel = fe[l_f.long()]
+            t_f = torch.cat([sp.rows(fel[:, 0].contiguous()), sp.rows(fel[:, 1].contiguous())], dim=1).contiguous()
+            facet_batches.append((t_f, mm))
+            continue
+        if not isinstance(integ.dx, CutDifferentialSymbol) or any(t[0] == OP_JUMP for t in terms):
+            raise XgpuError("jump terms belong on dFacetPatch")
         order = integ.dx.order
         if order < 0:  # symboliccutbfi.cpp:100-118 (dt has DIFFORDER 0, spacetime/diffopDt.hpp:19)
             dtr = min(1 if t[0] == OP_GRAD else 0 for t in terms)
@@ -377,8 +418,9 @@ def assemble_bilinear(blf):
             ops.elmat_st(dim, p, kt, l, mesh.elements, mesh.points, off, q, tv, w, terms, out=m_A, accumulate=True,
                          slots=slots, ctx=ctx)
     table = sp.rows(l_A)
-    plan = ops.csr_plan(sp.ndof, [table], ctx=ctx)
-    rowptr, col, vals = ops.csr_assemble(plan, [(table, m_A)])
+    batches = [(table, m_A)] + facet_batches
+    plan = ops.csr_plan(sp.ndof, [b[0] for b in batches], ctx=ctx)
+    rowptr, col, vals = ops.csr_assemble(plan, batches)
     blf.mat = SparseMatrixCSR(sp.ndof, rowptr, col, vals)
     return blf
 

@@ -215,3 +215,87 @@ def test_nccl_mlset_domain_partitioned_equals_single_gpu(tmp_path, n, fe_order):
             assert np.allclose(vals[prp[i]:prp[i + 1]][o], val[rp[ri]:rp[ri + 1]], rtol=1e-12, atol=1e-13 * scale)
             nnz += prp[i + 1] - prp[i]
     assert nnz == len(col)
+
+
+# ------------------------------------------------------------------ config 5: one space-time slab, element-partitioned
+def _st_worker(rank, world, n, p, kt, port, out):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    try:
+        from ngsxfem_b200.distributed import DistributedCutAssembly, SpaceTimeGpuBackend, make_slab_partition
+        part, phi_st = make_slab_partition(n, world, rank, dev, fe_order=p, radius=0.3, time_fe_order=kt)
+        be = SpaceTimeGpuBackend(p, kt, kt, 2 * kt).bind(part)
+        asm = DistributedCutAssembly(part, be, rank, world)
+        res = asm.step(phi_st)
+        rows_g, rp, cols_g, vals = asm.owned_rows_global(res)
+        a, b = part.range_of[rank]
+        own_ids = a + torch.nonzero(res["dofmap"][a:b] >= 0).reshape(-1)
+        torch.save(dict(rows=rows_g.cpu(), rowptr=rp.cpu(), cols=cols_g.cpu(), vals=vals.cpu(), keys=part.gid.cpu()[own_ids.cpu()],
+                        units=res["units"], ndof_global=res["ndof_global"]), os.path.join(out, f"rank{rank}.pt"))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n,p,kt", [(5, 1, 2), (4, 2, 1)])
+def test_nccl_spacetime_slab_partitioned_equals_single_gpu(tmp_path, n, p, kt):
+    """BASELINE config 5 shape: one space-time slab (moving spheres, P1/P2 x nodal time) assembled on 2 GPUs (halo layer,
+    NCCL interface rows) equals the single-GPU BilinearForm(SpaceTimeFESpace).Assemble of the whole chain, row by row
+    through the global space-time dof keys"""
+    import math
+    world = 2
+    if torch.cuda.device_count() < world:
+        pytest.skip("needs 2 GPUs")
+    import ngsxfem_b200 as xf
+    from ngsxfem_b200.pipeline import sphere_levelset
+    port = 29500 + (os.getpid() % 2000) + 23 + p
+    mp.spawn(_st_worker, args=(world, n, p, kt, port, str(tmp_path)), nprocs=world, join=True)
+    dev = torch.device("cuda", 0)
+    mesh = xf.MakeStructured3DMesh(nx=n, ny=n, nz=n * world, device=dev)
+    nv1 = n + 1
+    pts = mesh.points.clone()
+    K = torch.arange(mesh.nv, device=dev, dtype=torch.int64) // (nv1 * nv1)
+    pts[:, 2] = K.to(torch.float64) / n
+    gmesh = xf.Mesh(pts, mesh.elements)
+    tfe = xf.ScalarTimeFE(kt)
+    phis = []
+    for t in tfe.nodes():
+        cy = 0.5 + 0.1 * math.sin(2 * math.pi * 0.25 * t)
+        phis.append(sphere_levelset(pts, [(.5, cy, float(j)) for j in range(world + 1)], 0.3))
+    ls = xf.SpaceTimeGridFunction(gmesh, tfe, torch.stack(phis))
+    hasneg = xf.CutInfo(gmesh, ls, time_order=0).GetElementsOfType(xf.HASNEG)
+    Vs = xf.Restrict(xf.H1(gmesh, order=p), hasneg)
+    V = xf.SpaceTimeFESpace(Vs, tfe)
+    u, v = V.TnT()
+    a = xf.BilinearForm(V)
+    a += (u * v + xf.dt(u) * v + xf.grad(u) * xf.grad(v)) * xf.dCut(ls, xf.NEG, time_order=2 * kt, definedonelements=hasneg)
+    a.Assemble()
+    from ngsxfem_b200.distributed import structured_dof_keys
+    NV = nv1 * nv1 * (n * world + 1)
+    gid, _ = structured_dof_keys(gmesh, torch.arange(gmesh.nv, device=dev, dtype=torch.int64), nv1, NV, p,
+                                 torch.arange(gmesh.ne, device=dev, dtype=torch.int64))
+    nt = kt + 1
+    ks = gid[Vs.dofmap >= 0].cpu().numpy()            # compressed space id -> key
+    keys = np.concatenate([ks * nt + j for j in range(nt)])   # compressed space-time id (time-major) -> key
+    rp, col, val = (t.cpu().numpy() for t in (a.mat.rowptr, a.mat.col, a.mat.vals))
+    parts = [torch.load(os.path.join(str(tmp_path), f"rank{r}.pt")) for r in range(world)]
+    assert parts[0]["ndof_global"] == V.ndof and sum(q["units"] for q in parts) == hasneg.NumSet()
+    assert all(q["units"] > 0 for q in parts)
+    key_of = np.zeros(V.ndof, dtype=np.int64)
+    for q in parts:
+        key_of[q["rows"].numpy()] = q["keys"].numpy()
+    ref_id = {int(k): i for i, k in enumerate(keys)}
+    scale, nnz = np.abs(val).max(), 0
+    for q in parts:
+        rows, prp, cols, vals = q["rows"].numpy(), q["rowptr"].numpy(), q["cols"].numpy(), q["vals"].numpy()
+        for i, g in enumerate(rows):
+            ri = ref_id[int(key_of[g])]
+            c_d = np.array([ref_id[int(key_of[c])] for c in cols[prp[i]:prp[i + 1]]])
+            o = np.argsort(c_d)
+            assert np.array_equal(c_d[o], col[rp[ri]:rp[ri + 1]])
+            assert np.allclose(vals[prp[i]:prp[i + 1]][o], val[rp[ri]:rp[ri + 1]], rtol=1e-12, atol=1e-13 * scale)
+            nnz += prp[i + 1] - prp[i]
+    assert nnz == len(col)
