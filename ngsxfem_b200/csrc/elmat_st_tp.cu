@@ -8,7 +8,7 @@
 // unordered space pair {i,k} and all (k_t+1)^2 time pairs: per point it loads 2 + 2D staged space values and the 2 (k_t+1)^2
 // broadcast time coefficients and updates (k_t+1)^2 accumulators — a third of the shared-memory loads per entry of the
 // generic 2x2-block kernel.  Small elements (P1: 10 pairs in 3D) split the points over 32 / #pairs lane groups; the groups
-// are summed through the shared-memory tile in a fixed order, and the tile is written with coalesced stores.
+// are summed by warp shuffles in a fixed order, and the matrix goes through a shared-memory tile to coalesced stores.
 #include "common.cuh"
 #include "cutgeom.cuh"
 #include "deform.cuh"
@@ -71,7 +71,7 @@ struct TpCfg {
 };
 
 template <int D, int P, int KT>
-__global__ void __launch_bounds__(128) k_elmat_st_tp(
+__global__ void __launch_bounds__(128, (P == 1) ? 5 : 3) k_elmat_st_tp(
     int64_t n, const int32_t* __restrict__ elems, const int32_t* __restrict__ el_vtx, const double* __restrict__ vtx_xyz,
     const int64_t* __restrict__ offsets, const double* __restrict__ pts, const double* __restrict__ tvals,
     const double* __restrict__ wts, StTermsDev T, int accumulate, const int32_t* __restrict__ slots, double* __restrict__ mats)
@@ -167,27 +167,34 @@ __global__ void __launch_bounds__(128) k_elmat_st_tp(
         }
       }
     }
-    // groups -> tile in a fixed order (group 0 writes, the others add), then coalesced stores
+    // point groups -> group 0 by warp shuffles in a fixed order ((g0 + g1) + g2 ...), group 0 fills the tile, coalesced stores
     __syncwarp();
+    if (GROUPS > 1) {
 #pragma unroll
-    for (int gsel = 0; gsel < GROUPS; gsel++) {
+      for (int m = 0; m < NTT; m++) {
+        double a = acc[0][m];
 #pragma unroll
-      for (int r = 0; r < ROUNDS; r++) {
-        if (pv_[r] && grp == gsel) {
-          const int i = pi_[r], k = pk_[r];
-#pragma unroll
-          for (int j = 0; j < NT; j++)
-#pragma unroll
-            for (int l = 0; l < NT; l++) {
-              const double a = acc[r][j * NT + l];
-              const int o1 = (j * NDS + i) * ND + (l * NDS + k), o2 = (j * NDS + k) * ND + (l * NDS + i);
-              if (gsel == 0) { tile[o1] = a; if (i != k) tile[o2] = a; }
-              else { tile[o1] += a; if (i != k) tile[o2] += a; }
-            }
-        }
+        for (int g = 1; g < GROUPS; g++) a += __shfl_down_sync(0xffffffffu, acc[0][m], g * NPAIR);
+        acc[0][m] = a;
       }
-      __syncwarp();
     }
+#pragma unroll
+    for (int r = 0; r < ROUNDS; r++) {
+      if (pv_[r] && grp == 0) {
+        const int i = pi_[r], k = pk_[r];
+        double* t1 = tile + i * ND + k;
+        double* t2 = tile + k * ND + i;
+#pragma unroll
+        for (int j = 0; j < NT; j++)
+#pragma unroll
+          for (int l = 0; l < NT; l++) {
+            const double a = acc[r][j * NT + l];
+            t1[j * NDS * ND + l * NDS] = a;
+            t2[j * NDS * ND + l * NDS] = a;
+          }
+      }
+    }
+    __syncwarp();
     double* M = mats + (size_t)(slots ? (int64_t)slots[e] : e) * ND * ND;
     if (accumulate) {
       for (int idx = lane; idx < ND * ND; idx += 32) M[idx] += tile[idx];
