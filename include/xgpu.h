@@ -89,6 +89,12 @@ int xgpu_classify(xgpu_ctx* ctx, int dim, int64_t ne, const int32_t* el_vtx, con
 /* CutInformation::Update with a space-time level set (time_order >= 0, cutinfo.cpp:90-124): the part volumes are the
  * weight sums of the order-0 NEG and POS rules (xgpu_cutquad_st_*; added in rule order), the element is IF iff both are
  * > 0, NEG iff only the NEG one, POS otherwise; cut_ratio = neg / (neg + pos) (nullable). */
+/* the same decision in ONE pass over the elements (no rule storage): part volumes of the order-0 POS / NEG space-time
+ * rules summed in rule order (bit-identical to xgpu_cutquad_st_* + xgpu_rule_element_sums), ballot classification.
+ * phi_st: (time_fe_order+1) x nv nodal values, time-major. */
+int xgpu_classify_st(xgpu_ctx* ctx, int dim, int64_t ne, const int32_t* el_vtx, const double* phi_st, int64_t nv,
+                     int time_fe_order, int time_order, uint32_t* bits_neg, uint32_t* bits_pos, uint32_t* bits_if,
+                     double* cut_ratio);
 int xgpu_rule_element_sums(xgpu_ctx* ctx, int64_t n, const int64_t* offsets, const double* wts, double* sums);
 int xgpu_classify_volumes(xgpu_ctx* ctx, int64_t ne, const double* vol_neg, const double* vol_pos,
                           uint32_t* bits_neg, uint32_t* bits_pos, uint32_t* bits_if, double* cut_ratio);

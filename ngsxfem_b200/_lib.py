@@ -78,6 +78,7 @@ _SIGS = {
     "xgpu_cutquad_st_fill": (C.c_int, [VP, C.c_int, C.c_int64, VP, VP, VP, VP, C.c_int64, C.c_int, C.c_int, C.c_int,
                                        C.c_int, VP, VP, VP, VP]),
     "xgpu_integrate_monomial": (C.c_int, [VP, C.c_int, C.c_int64, VP, VP, VP, VP, VP, VP, c_intp, c_f64p]),
+    "xgpu_classify_st": (C.c_int, [VP, C.c_int, C.c_int64, VP, VP, C.c_int64, C.c_int, C.c_int, VP, VP, VP, VP]),
     "xgpu_rule_element_sums": (C.c_int, [VP, C.c_int64, VP, VP, VP]),
     "xgpu_classify_volumes": (C.c_int, [VP, C.c_int64, VP, VP, VP, VP, VP, VP]),
     "xgpu_integrate_monomial_st": (C.c_int, [VP, C.c_int, C.c_int64, VP, VP, VP, VP, VP, VP, VP, c_intp, c_f64p]),

@@ -368,6 +368,91 @@ __global__ void __launch_bounds__(128) k_st(int64_t n, const int32_t* __restrict
   if (!FILL) counts[i] = E.n;
 }
 
+// CutInformation::Update on a time slab in ONE pass (xfem/cutinfo.cpp:90-124 with time_order >= 0): the part volumes of
+// the POS and NEG space-time rules are summed in rule order — the same additions, in the same order, as k_st<D,true> of
+// each domain followed by k_rule_sums, without materialising the points — then the element is classified by ballot.
+template <int D>
+__global__ void __launch_bounds__(128) k_st_classify(int64_t n, const int32_t* __restrict__ el_vtx,
+                                                     const double* __restrict__ phi_st, int64_t nv, int tord, RuleSet R,
+                                                     const double* __restrict__ tq_p, const double* __restrict__ tq_w, int ntq,
+                                                     uint32_t* __restrict__ bneg, uint32_t* __restrict__ bpos,
+                                                     uint32_t* __restrict__ bif, double* __restrict__ ratio, int* status,
+                                                     unsigned long long* status_elem)
+{
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const bool in = i < n;
+  double pv[2] = {0.0, 0.0};  // [XGPU_NEG], [XGPU_POS]
+  if (in) {
+    const int nt = tord + 1;
+    int v[D + 1];
+#pragma unroll
+    for (int k = 0; k < D + 1; k++) v[k] = __ldg(el_vtx + i * (D + 1) + k);
+    double nd[XG_ST_MAXORD + 1];
+    time_nodes(tord, nd);
+    double ls[XG_ST_MAXORD + 1][D + 1];
+    for (int j = 0; j < nt; j++)
+#pragma unroll
+      for (int k = 0; k < D + 1; k++) ls[j][k] = __ldg(phi_st + (int64_t)j * nv + v[k]);
+    double cutp[XG_ST_MAXCP];
+    int ncp = 2, err = 0;
+    cutp[0] = 0.0; cutp[1] = 1.0;
+    for (int k = 0; k < D + 1 && !err; k++) {
+      double li[XG_ST_MAXORD + 1];
+      for (int j = 0; j < nt; j++) li[j] = ls[j][k];
+      const int nr = root_finding(li, tord, nd, cutp + ncp, XG_ST_MAXCP - ncp);
+      if (nr < 0) { err = nr; break; }
+      ncp += nr;
+    }
+    if (!err) {
+      for (int a = 1; a < ncp; a++) {
+        const double key = cutp[a];
+        int b = a - 1;
+        while (b >= 0 && cutp[b] > key) { cutp[b + 1] = cutp[b]; b--; }
+        cutp[b + 1] = key;
+      }
+      for (int c = 0; c < ncp - 1 && !err; c++) {
+        const double t0 = cutp[c], t1 = cutp[c + 1];
+        for (int q = 0; q < ntq && !err; q++) {
+          const double t = t0 + tq_p[3 * q] * (t1 - t0);
+          double sh[XG_ST_MAXORD + 1], lt[D + 1];
+          time_shapes(tord, nd, t, sh);
+#pragma unroll
+          for (int k = 0; k < D + 1; k++) {
+            double d = 0.0;
+            for (int j = 0; j < nt; j++) d += ls[j][k] * sh[j];
+            if (fabs(d) < 1e-14) d = (d >= 0) ? 1e-14 : -1e-14;
+            lt[k] = d;
+          }
+          const double wfac = tq_w[q] * (t1 - t0);
+          const int dom = xg_check_cut(lt, D + 1);
+          if (dom == XGPU_IF) {
+            XgSimplex ref, sub[3];
+            xg_ref_simplex(D, ref);
+            for (int np = 0; np < 2 && !err; np++) {
+              const int ns = xg_decompose(ref, lt, np, sub);
+              if (ns < 0) { err = ns; break; }
+              for (int s = 0; s < ns; s++) {
+                const double vol = xg_volume(sub[s]) * wfac;
+                const int npt = R.n[sub[s].D];
+                for (int qq = 0; qq < npt; qq++) pv[np] += R.w[sub[s].D][qq] * vol;
+              }
+            }
+          } else {
+            for (int qq = 0; qq < R.n[D]; qq++) pv[dom] += R.w[D][qq] * wfac;
+          }
+        }
+      }
+    }
+    if (err) { xgpu_record_error(status, status_elem, err, i); pv[0] = pv[1] = 0.0; }
+  }
+  const bool hn = in && pv[XGPU_NEG] > 0.0, hp = pv[XGPU_POS] > 0.0;
+  const unsigned mn = __ballot_sync(0xffffffffu, hn && !hp);
+  const unsigned mi = __ballot_sync(0xffffffffu, hn && hp);
+  const unsigned mp = __ballot_sync(0xffffffffu, in && !hn);
+  if (in && ratio) ratio[i] = pv[XGPU_NEG] / (pv[XGPU_NEG] + pv[XGPU_POS]);
+  if ((threadIdx.x & 31) == 0 && in) { bneg[i >> 5] = mn; bif[i >> 5] = mi; bpos[i >> 5] = mp; }
+}
+
 int make_ruleset(xgpu_ctx* ctx, int dim, int order, RuleSet& R)
 {
   for (int d = 0; d < 4; d++) { R.p[d] = nullptr; R.w[d] = nullptr; R.n[d] = 0; }
@@ -500,4 +585,24 @@ extern "C" int xgpu_cutquad_st_fill(xgpu_ctx* ctx, int dim, int64_t n, const int
   const xgpu_rule_host* tr = xgpu_rule_lookup(ctx, 1, order_time);
   if (!tr) return xgpu_fail(ctx, XGPU_ERR_ARG, "xgpu_cutquad_st_fill: no time rule");
   return launch_st<true>(ctx, dim, n, elems, el_vtx, vtx_xyz, phi_st, nv, time_fe_order, dt, R, tr, offsets, nullptr, pts, tvals, wts);
+}
+
+extern "C" int xgpu_classify_st(xgpu_ctx* ctx, int dim, int64_t ne, const int32_t* el_vtx, const double* phi_st, int64_t nv,
+                                int time_fe_order, int time_order, uint32_t* bits_neg, uint32_t* bits_pos, uint32_t* bits_if,
+                                double* cut_ratio)
+{
+  if (!ctx || dim < 1 || dim > 3 || ne < 0 || time_fe_order < 0 || time_fe_order > XG_ST_MAXORD || !bits_neg || !bits_pos || !bits_if)
+    return xgpu_fail(ctx, XGPU_ERR_ARG, "xgpu_classify_st: bad argument (time order <= 8)");
+  if (ne == 0) return XGPU_OK;
+  RuleSet R;
+  int rc = make_ruleset(ctx, dim, 0, R);  // order 0 (cutinfo.cpp:98)
+  if (rc) return rc;
+  const xgpu_rule_host* tr = xgpu_rule_lookup(ctx, 1, time_order < 0 ? 0 : time_order);
+  if (!tr) return xgpu_fail(ctx, XGPU_ERR_ARG, "xgpu_classify_st: no time rule");
+  const unsigned g = nblk(ne, 128);
+#define XG_STC(DD) k_st_classify<DD><<<g, 128, 0, ctx->stream>>>(ne, el_vtx, phi_st, nv, time_fe_order, R, tr->d_pts, tr->d_wts, tr->n, bits_neg, bits_pos, bits_if, cut_ratio, ctx->d_status, ctx->d_status_elem)
+  if (dim == 3) XG_STC(3); else if (dim == 2) XG_STC(2); else XG_STC(1);
+#undef XG_STC
+  XGPU_LAUNCH_CHECK(ctx);
+  return XGPU_OK;
 }

@@ -224,12 +224,9 @@ class CutInfo:
             phi_st, kt = levelset.vec, levelset.timeFE.order
         else:
             phi_st, kt = _lset_vec(levelset, m).reshape(1, -1).contiguous(), 0
-        vols = []
-        for np_ in (POS, NEG):
-            off, _, _, w = ops.cutquad_st(m.dim, None, m.elements, m.points, phi_st, kt, np_, time_order, 0, ctx=ctx)
-            vols.append(ops.rule_element_sums(off, w, ctx=ctx))
+        ops.classify_st(m.dim, m.elements, phi_st, kt, time_order,
+                        out=(b[CDOM_NEG].bits, b[CDOM_POS].bits, b[CDOM_IF].bits, self.cut_ratio), ctx=ctx)
         ctx.raise_on_geometry_error()
-        ops.classify_volumes(vols[1], vols[0], (b[CDOM_NEG].bits, b[CDOM_POS].bits, b[CDOM_IF].bits, self.cut_ratio), ctx=ctx)
         ops.bitset_op(ops.BIT_OR, b[CDOM_NEG].bits, b[CDOM_POS].bits, m.ne, out=b[UNCUT].bits, ctx=ctx)
         ops.bitset_op(ops.BIT_OR, b[CDOM_NEG].bits, b[CDOM_IF].bits, m.ne, out=b[HASNEG].bits, ctx=ctx)
         ops.bitset_op(ops.BIT_OR, b[CDOM_POS].bits, b[CDOM_IF].bits, m.ne, out=b[HASPOS].bits, ctx=ctx)

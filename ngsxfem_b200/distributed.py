@@ -400,13 +400,8 @@ class SpaceTimeGpuBackend(GpuBackend):
     def classify(self, el_vtx, phi_st):
         ops, ctx = self.ops, self.ctx
         dim, ne = el_vtx.shape[1] - 1, el_vtx.shape[0]
-        vols = []
-        for np_ in (ops.POS, ops.NEG):
-            off, _, _, w = ops.cutquad_st(dim, None, el_vtx, self._xyz, phi_st, self.kl, np_, 0, 0, ctx=ctx)
-            vols.append(ops.rule_element_sums(off, w, ctx=ctx))
+        bn, bp, bi, _ = ops.classify_st(dim, el_vtx, phi_st, self.kl, 0, want_ratio=False, ctx=ctx)
         ctx.raise_on_geometry_error()
-        bn, bp, bi = (ops.new_bits(ne, el_vtx.device) for _ in range(3))
-        ops.classify_volumes(vols[1], vols[0], (bn, bp, bi, None), ctx=ctx)
         return ops.bitset_to_list(bn, ne, ctx=ctx), ops.bitset_to_list(bi, ne, ctx=ctx), (bn, bp, bi, None)
 
     def elmats(self, part, phi_st, l_neg, l_if):

@@ -255,6 +255,18 @@ def integrate_monomial(dim, elems, el_vtx, vtx_xyz, off, pts, wts, expo, ctx=Non
     return res.value
 
 
+def classify_st(dim, el_vtx, phi_st, time_fe_order, time_order, out=None, want_ratio=True, ctx=None):
+    """CutInfo on a time slab in one pass: (bits_neg, bits_pos, bits_if, cut_ratio)"""
+    ctx = ctx or default_ctx()
+    ne, dev = el_vtx.shape[0], el_vtx.device
+    if out is None:
+        out = (new_bits(ne, dev), new_bits(ne, dev), new_bits(ne, dev),
+               torch.empty(ne, dtype=torch.float64, device=dev) if want_ratio else None)
+    ctx.check(ctx.lib.xgpu_classify_st(ctx.h, dim, ne, ptr(_i32(el_vtx)), ptr(_f64(phi_st)), phi_st.shape[1], int(time_fe_order),
+                                       int(time_order), ptr(out[0]), ptr(out[1]), ptr(out[2]), ptr(out[3])))
+    return out
+
+
 def rule_element_sums(off, wts, ctx=None):
     """per-element sums of the rule weights, added in rule order"""
     ctx = ctx or default_ctx()

@@ -389,3 +389,22 @@ def test_spacetime_ghost_penalty_assembled_kernel_and_definiteness():
 def _embed(m, g, x):
     """m.mat x for forms on the same space (same dof numbering)"""
     return m.mat * x
+
+
+@pytest.mark.parametrize("dim,n,kt,to", [(3, 5, 2, 0), (2, 9, 1, 2), (1, 17, 2, 1), (3, 4, 3, 0)])
+def test_one_pass_slab_classification_equals_the_rule_based_one_bit_for_bit(dim, n, kt, to):
+    """xgpu_classify_st (no rule storage) == xgpu_cutquad_st_* + xgpu_rule_element_sums + xgpu_classify_volumes"""
+    mesh = make_mesh(dim, n)
+    ls = moving_lset(mesh, xf.ScalarTimeFE(kt))
+    vols = {}
+    for np_ in (POS, NEG):
+        off, _, _, w = ops.cutquad_st(dim, None, mesh.elements, mesh.points, ls.vec, kt, np_, to, 0)
+        vols[np_] = ops.rule_element_sums(off, w)
+    ref = (ops.new_bits(mesh.ne, DEV), ops.new_bits(mesh.ne, DEV), ops.new_bits(mesh.ne, DEV),
+           torch.empty(mesh.ne, dtype=torch.float64, device=DEV))
+    ops.classify_volumes(vols[NEG], vols[POS], ref)
+    got = ops.classify_st(dim, mesh.elements, ls.vec, kt, to)
+    for a, b in zip(got[:3], ref[:3]):
+        assert torch.equal(a, b)
+    assert torch.equal(got[3], ref[3])
+    assert int(ops.bitset_count(got[2], mesh.ne)) > 0
