@@ -380,7 +380,7 @@ extern "C" int xgpu_integrate_monomial_st(xgpu_ctx* ctx, int dim, int64_t n, con
                                           const double* vtx_xyz, const int64_t* offsets, const double* pts,
                                           const double* tvals, const double* wts, const int* expo_host, double* result_host)
 {
-  if (!ctx || dim < 1 || dim > 3 || !result_host || !tvals || !expo_host)
+  if (!ctx || dim < 1 || dim > 3 || !result_host || !expo_host)  // tvals may be NULL when the batch has no points at all
     return xgpu_fail(ctx, XGPU_ERR_ARG, "xgpu_integrate_monomial_st: bad argument");
   if (ctx->def_order > 0) return xgpu_fail(ctx, XGPU_ERR_UNSUPPORTED, "space-time integrals do not support a mesh deformation");
   *result_host = 0.0;

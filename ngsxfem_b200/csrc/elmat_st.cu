@@ -349,11 +349,11 @@ int launch_elvec_st(xgpu_ctx* ctx, int p, int kt, int64_t n, const int32_t* elem
   return XGPU_OK;
 }
 
-int st_check(xgpu_ctx* ctx, int dim, int fe_order, int time_fe_order, const void* offsets, const void* tvals, const char* who)
+int st_check(xgpu_ctx* ctx, int dim, int fe_order, int time_fe_order, int64_t n, const void* offsets, const void* tvals, const char* who)
 {
   if (!ctx) return XGPU_ERR_ARG;
   if (dim < 1 || dim > 3 || fe_order < 1 || fe_order > XG_MAX_ORDER || time_fe_order < 0 || time_fe_order >= XG_ST_MAXT ||
-      !offsets || !tvals)
+      n < 0 || (n > 0 && (!offsets || !tvals)))  // an empty batch carries no arrays
     return xgpu_fail(ctx, XGPU_ERR_ARG, who);
   if (ctx->def_order > 0)
     return xgpu_fail(ctx, XGPU_ERR_UNSUPPORTED, "space-time forms do not support a mesh deformation");
@@ -367,7 +367,7 @@ extern "C" int xgpu_elmat_st(xgpu_ctx* ctx, int dim, int fe_order, int time_fe_o
                              const double* tvals, const double* wts, const xgpu_term* terms_host, int nterms,
                              int accumulate, const int32_t* slots, double* mats)
 {
-  int rc = st_check(ctx, dim, fe_order, time_fe_order, offsets, tvals, "xgpu_elmat_st: bad argument (space orders 1..4, time orders 0..3)");
+  int rc = st_check(ctx, dim, fe_order, time_fe_order, n, offsets, tvals, "xgpu_elmat_st: bad argument (space orders 1..4, time orders 0..3)");
   if (rc) return rc;
   if (nterms < 0 || nterms > XG_ST_MAXTERMS) return xgpu_fail(ctx, XGPU_ERR_ARG, "xgpu_elmat_st: too many terms (max 8)");
   if (n == 0) return XGPU_OK;
@@ -393,7 +393,7 @@ extern "C" int xgpu_elvec_st(xgpu_ctx* ctx, int dim, int fe_order, int time_fe_o
                              const double* tvals, const double* wts, const xgpu_stlterm* terms_host, int nterms,
                              int accumulate, const int32_t* slots, double* vecs)
 {
-  int rc = st_check(ctx, dim, fe_order, time_fe_order, offsets, tvals, "xgpu_elvec_st: bad argument (space orders 1..4, time orders 0..3)");
+  int rc = st_check(ctx, dim, fe_order, time_fe_order, n, offsets, tvals, "xgpu_elvec_st: bad argument (space orders 1..4, time orders 0..3)");
   if (rc) return rc;
   if (nterms < 0 || nterms > XG_ST_MAXTERMS) return xgpu_fail(ctx, XGPU_ERR_ARG, "xgpu_elvec_st: too many terms (max 8)");
   if (n == 0) return XGPU_OK;

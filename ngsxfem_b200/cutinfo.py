@@ -308,12 +308,12 @@ class MultiLevelsetCutInfo:
         # xfem/cutinfo.cpp:306-334: bit set iff the weights of the (order -1) multi-level-set rule sum to > 0
         off, pts, wts = ops.cutquad_ml(m.dim, None, m.elements, m.points, self._phis(), dts, -1)
         default_ctx(m.device.index).raise_on_geometry_error()
-        seg = torch.zeros(m.ne, dtype=torch.float64, device=wts.device)
-        if wts.numel():
-            idx = torch.repeat_interleave(torch.arange(m.ne, device=wts.device), off[1:] - off[:-1])
-            seg.index_add_(0, idx, wts)
-        mask = (seg > 0).cpu().numpy()
-        ba.bits.copy_(BitArray.from_numpy(mask, m.device).bits)
+        # weight sums in rule order (`for (auto w : wei_arr) sum += w`, :322-325) and the > 0 decision on the device
+        ctx = default_ctx(m.device.index)
+        seg = ops.rule_element_sums(off, wts, ctx=ctx)
+        none = torch.zeros_like(seg)
+        scratch = (ops.new_bits(m.ne, m.device), ops.new_bits(m.ne, m.device))
+        ops.classify_volumes(seg, none, (ba.bits, scratch[0], scratch[1], None), ctx=ctx)   # "NEG" bit = (sum > 0)
 
     def GetElementsWithContribution(self, domain_type, vb=VOL, heapsize=1000000):
         dts = _normalize_dtlist(domain_type, len(self.lsets))

@@ -347,17 +347,11 @@ class MlsetGpuBackend(GpuBackend):
         dim, ne = el_vtx.shape[1] - 1, el_vtx.shape[0]
         off, pts, wts = ops.cutquad_ml(dim, None, el_vtx, self._xyz, phis, self.dts, -1, ctx=ctx)
         ctx.raise_on_geometry_error()
-        seg = torch.zeros(ne, dtype=torch.float64, device=el_vtx.device)
-        if wts.numel():
-            seg.index_add_(0, torch.repeat_interleave(torch.arange(ne, device=el_vtx.device), off[1:] - off[:-1]), wts)
-        act = seg > 0
-        # pack into BitArray words (bit i = word i >> 5, bit i & 31)
-        pad = (-ne) % 32
-        bits = torch.cat([act, torch.zeros(pad, dtype=torch.bool, device=act.device)]).reshape(-1, 32).to(torch.int64)
-        words = (bits << torch.arange(32, device=act.device, dtype=torch.int64)).sum(1)
-        words = torch.where(words >= 2 ** 31, words - 2 ** 32, words).to(torch.int32).contiguous()
-        zero = torch.zeros_like(words)
-        l_act = torch.nonzero(act).reshape(-1).to(torch.int32)
+        seg = ops.rule_element_sums(off, wts, ctx=ctx)           # weight sums in rule order (cutinfo.cpp:322-325)
+        words, zero, zero2 = (ops.new_bits(ne, el_vtx.device) for _ in range(3))
+        ops.classify_volumes(seg, torch.zeros_like(seg), (words, zero, zero2, None), ctx=ctx)   # "NEG" bit = (sum > 0)
+        zero.zero_()                                              # no POS / IF sets in this backend: activity = the one bitset
+        l_act = ops.bitset_to_list(words, ne, ctx=ctx)
         return l_act, l_act[:0], (words, zero, zero.clone(), None)
 
     def elmats(self, part, phis, l_act, l_none):

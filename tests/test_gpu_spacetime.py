@@ -408,3 +408,45 @@ def test_one_pass_slab_classification_equals_the_rule_based_one_bit_for_bit(dim,
         assert torch.equal(a, b)
     assert torch.equal(got[3], ref[3])
     assert int(ops.bitset_count(got[2], mesh.ne)) > 0
+
+
+# ---------------------------------------------------------------- edge cases
+def test_spacetime_edge_cases():
+    mesh = make_mesh(2, 3)                       # 18 triangles: not a multiple of 32
+    tfe = xf.ScalarTimeFE(1)
+    allpos = xf.SpaceTimeGridFunction(mesh, tfe, torch.ones((2, mesh.nv), dtype=torch.float64))
+    allneg = xf.SpaceTimeGridFunction(mesh, tfe, -torch.ones((2, mesh.nv), dtype=torch.float64))
+    for ls, want in ((allpos, xf.POS), (allneg, xf.NEG)):
+        ci = xf.CutInfo(mesh, ls, time_order=0)
+        assert ci.GetElementsOfType(want).NumSet() == mesh.ne
+        assert ci.GetElementsOfType(xf.IF).NumSet() == 0
+        assert ci.GetElementsOfType(xf.UNCUT).NumSet() == mesh.ne
+    assert float(xf.CutInfo(mesh, allneg, time_order=0).GetCutRatios().min()) == 1.0
+    # empty element list: nothing launched, nothing written
+    empty = torch.zeros(0, dtype=torch.int32, device=DEV)
+    off, q, tv, w = ops.cutquad_st(2, empty, mesh.elements, mesh.points, allneg.vec, 1, NEG, 2, 2)
+    assert off.numel() == 1 and w.numel() == 0
+    m = ops.elmat_st(2, 1, 1, empty, mesh.elements, mesh.points, off, q, tv, w, [(ID, ID, 1.0, 0)])
+    assert m.shape == (0, 6, 6)
+    # a NEG integral over an all-POS slab: the pattern of the space, all values zero
+    V = xf.SpaceTimeFESpace(xf.H1(mesh, order=1), tfe)
+    u, v = V.TnT()
+    a = xf.BilinearForm(V)
+    a += u * v * xf.dCut(allpos, NEG, time_order=2)
+    a.Assemble()
+    assert a.mat.nze > 0 and float(a.mat.vals.abs().max()) == 0.0
+    # nothing active at all: the empty matrix
+    none = xf.BitArray(mesh.ne, DEV)
+    Vr = xf.SpaceTimeFESpace(xf.Restrict(xf.H1(mesh, order=1), none), tfe)
+    ur, vr = Vr.TnT()
+    b = xf.BilinearForm(Vr)
+    b += ur * vr * xf.dCut(allneg, NEG, time_order=2, definedonelements=none)
+    b.Assemble()
+    assert Vr.ndof == 0 and b.mat.nze == 0
+    f = xf.LinearForm(Vr)
+    f += xf.tref * vr * xf.dCut(allneg, NEG, time_order=2)
+    f.Assemble()
+    assert f.vec.numel() == 0
+    # integrals of empty domains
+    assert xf.Integrate({"levelset": allpos, "domain_type": NEG}, mesh=mesh, cf=1.0, order=1, time_order=1) == 0.0
+    assert xf.Integrate({"levelset": allpos, "domain_type": IF}, mesh=mesh, cf=xf.tref, order=1, time_order=1) == 0.0
