@@ -82,3 +82,59 @@ class OracleBackend:
         rowptr, col = xo.graph(ndof, tab)
         vals = xo.scatter(ndof, tab, mt, rowptr, col)
         return torch.from_numpy(rowptr), torch.from_numpy(col), torch.from_numpy(vals)
+
+
+class SpaceTimeOracleBackend(OracleBackend):
+    """config 5 (one space-time slab) served by the oracle: slab classification from the part volumes of the order-0
+    space-time rules (xfem/cutinfo.cpp:90-124), space-time element matrices u v + dt(u) v + grad u . grad v on NEG —
+    the CPU counterpart of ngsxfem_b200.distributed.SpaceTimeGpuBackend"""
+    TERMS = [(0, 0, 1.0, 0), (3, 0, 1.0, 0), (1, 1, 1.0, 0)]
+
+    def __init__(self, space_order, time_fe_order, lset_time_order, time_order):
+        self.p, self.kt, self.kl, self.time_order = space_order, time_fe_order, lset_time_order, time_order
+
+    def bind(self, part):
+        self._xyz = part.vtx_xyz
+        return self
+
+    @staticmethod
+    def slab_classes(els, xyz, L, kl):
+        ne = els.shape[0]
+        neg = np.zeros(ne, bool); pos = np.zeros(ne, bool); cut = np.zeros(ne, bool)
+        for el in range(ne):
+            T = xo.make_trafo(xyz[els[el]], els[el])
+            pv = {}
+            for np_ in (xo.POS, xo.NEG):
+                _, _, w = xo.spacetime_cut_rule(T, L[:, els[el]], kl, np_, 0, 0)
+                s = 0.0
+                for x in w:
+                    s += x
+                pv[np_] = s
+            if pv[xo.NEG] > 0:
+                (cut if pv[xo.POS] > 0 else neg)[el] = True
+            else:
+                pos[el] = True
+        return neg, pos, cut
+
+    def classify(self, el_vtx, phi_st):
+        els, L = el_vtx.numpy(), phi_st.numpy()
+        neg, pos, cut = self.slab_classes(els, self._xyz.numpy(), L, self.kl)
+        pk = lambda m: np.packbits(m, bitorder="little")
+        return (torch.from_numpy(np.flatnonzero(neg).astype(np.int32)), torch.from_numpy(np.flatnonzero(cut).astype(np.int32)),
+                (pk(neg), pk(pos), pk(cut), None))
+
+    @staticmethod
+    def slab_elmats(els, xyz, L, lst, p, kt, kl, time_order, terms):
+        nd = xo.h1_ndof(els.shape[1] - 1, p) * (kt + 1)
+        out = np.zeros((len(lst), nd, nd))
+        for i, el in enumerate(lst):
+            T = xo.make_trafo(xyz[els[el]], els[el])
+            q, tv, w = xo.spacetime_cut_rule(T, L[:, els[el]], kl, xo.NEG, time_order, 2 * p)
+            if len(w):
+                xo.elmat_st_from_rule(T, p, kt, q, tv, w, terms, out=out[i])
+        return out
+
+    def elmats(self, part, phi_st, l_neg, l_if):
+        els, xyz, L = part.el_vtx.numpy(), part.vtx_xyz.numpy(), phi_st.numpy()
+        f = lambda l: torch.from_numpy(self.slab_elmats(els, xyz, L, l.numpy(), self.p, self.kt, self.kl, self.time_order, self.TERMS))
+        return f(l_neg), f(l_if)

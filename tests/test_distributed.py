@@ -299,3 +299,84 @@ def test_nccl_spacetime_slab_partitioned_equals_single_gpu(tmp_path, n, p, kt):
             assert np.allclose(vals[prp[i]:prp[i + 1]][o], val[rp[ri]:rp[ri + 1]], rtol=1e-12, atol=1e-13 * scale)
             nnz += prp[i + 1] - prp[i]
     assert nnz == len(col)
+
+
+def _st_gloo_worker(rank, world, n, p, kt, port, out):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from dist_backend import SpaceTimeOracleBackend
+        from ngsxfem_b200.distributed import DistributedCutAssembly, make_slab_partition
+        part, phi_st = make_slab_partition(n, world, rank, "cpu", fe_order=p, radius=0.3, time_fe_order=kt)
+        asm = DistributedCutAssembly(part, SpaceTimeOracleBackend(p, kt, kt, 2 * kt).bind(part), rank, world)
+        res = asm.step(phi_st)
+        rows_g, rp, cols_g, vals = asm.owned_rows_global(res)
+        a, b = part.range_of[rank]
+        own_ids = a + torch.nonzero(res["dofmap"][a:b] >= 0).reshape(-1)
+        torch.save(dict(rows=rows_g, rowptr=rp, cols=cols_g, vals=vals, keys=part.gid[own_ids], units=res["units"],
+                        ndof_global=res["ndof_global"]), os.path.join(out, f"rank{rank}.pt"))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,n,p,kt", [(2, 3, 1, 2), (3, 2, 1, 1), (2, 2, 2, 1)])
+def test_spacetime_slab_partition_merge_equals_global(tmp_path, world, n, p, kt):
+    """config 5 host logic on CPU (gloo): the element-partitioned space-time slab (time-major dof table, keys = space key x
+    (k_t+1) + time node) merged over `world` processes equals the single-process oracle assembly of the whole chain"""
+    import math
+    import ngsxfem_b200 as xf
+    from dist_backend import SpaceTimeOracleBackend as B
+    from ngsxfem_b200.distributed import structured_dof_keys
+    from ngsxfem_b200.pipeline import sphere_levelset
+    from oracle import xoracle as xo
+    port = 29500 + (os.getpid() % 2000) + 31 + world + p
+    mp.spawn(_st_gloo_worker, args=(world, n, p, kt, port, str(tmp_path)), nprocs=world, join=True)
+    # single-process reference of the whole chain
+    mesh = xf.MakeStructured3DMesh(nx=n, ny=n, nz=n * world)
+    nv1 = n + 1
+    pts = mesh.points.clone()
+    K = torch.arange(mesh.nv, dtype=torch.int64) // (nv1 * nv1)
+    pts[:, 2] = K.to(torch.float64) / n
+    gmesh = xf.Mesh(pts, mesh.elements)
+    nodes = xf.ScalarTimeFE(kt).nodes()
+    L = np.stack([sphere_levelset(pts, [(.5, 0.5 + 0.1 * math.sin(2 * math.pi * 0.25 * t), float(j)) for j in range(world + 1)], 0.3).numpy()
+                  for t in nodes])
+    els, xyz = gmesh.elements.numpy(), pts.numpy()
+    neg, pos, cut = B.slab_classes(els, xyz, L, kt)
+    act_el = np.flatnonzero(neg | cut).astype(np.int32)
+    assert cut.any()
+    Vs = xf.H1(gmesh, order=p)
+    eld = Vs.el_dofs.numpy()
+    act = np.zeros(Vs.ndof, bool)
+    act[eld[act_el].reshape(-1)] = True
+    nc = int(act.sum())
+    dofmap = np.full(Vs.ndof, -1, np.int32)
+    dofmap[act] = np.arange(nc, dtype=np.int32)
+    nt = kt + 1
+    rows_s = dofmap[eld[act_el]]
+    table = np.concatenate([rows_s + j * nc for j in range(nt)], axis=1).astype(np.int32)
+    mats = B.slab_elmats(els, xyz, L, act_el, p, kt, kt, 2 * kt, B.TERMS)
+    rp, col = xo.graph(nc * nt, table)
+    val = xo.scatter(nc * nt, table, mats, rp, col)
+    NV = nv1 * nv1 * (n * world + 1)
+    gid, _ = structured_dof_keys(gmesh, torch.arange(gmesh.nv, dtype=torch.int64), nv1, NV, p, torch.arange(gmesh.ne, dtype=torch.int64))
+    ks = gid.numpy()[act]
+    keys = np.concatenate([ks * nt + j for j in range(nt)])
+    parts = [torch.load(os.path.join(str(tmp_path), f"rank{r}.pt")) for r in range(world)]
+    assert parts[0]["ndof_global"] == nc * nt and sum(q["units"] for q in parts) == len(act_el)
+    key_of = np.zeros(nc * nt, dtype=np.int64)
+    for q in parts:
+        key_of[q["rows"].numpy()] = q["keys"].numpy()
+    ref_id = {int(k): i for i, k in enumerate(keys)}
+    scale, nnz = np.abs(val).max(), 0
+    for q in parts:
+        rows, prp, cols, vals = q["rows"].numpy(), q["rowptr"].numpy(), q["cols"].numpy(), q["vals"].numpy()
+        for i, g in enumerate(rows):
+            ri = ref_id[int(key_of[g])]
+            c_d = np.array([ref_id[int(key_of[c])] for c in cols[prp[i]:prp[i + 1]]])
+            o = np.argsort(c_d)
+            assert np.array_equal(c_d[o], col[rp[ri]:rp[ri + 1]])
+            assert np.allclose(vals[prp[i]:prp[i + 1]][o], val[rp[ri]:rp[ri + 1]], rtol=1e-12, atol=1e-13 * scale)
+            nnz += prp[i + 1] - prp[i]
+    assert nnz == len(col)
