@@ -209,14 +209,19 @@ class HostBuffers:
         return n * t.element_size()
 
 
-def step_host(hb, dim, ndof_full, fe_order, device, ctx=None, overlap=True):
+def step_host(hb, dim, ndof_full, fe_order, device, ctx=None, overlap=True, pipelined=False):
     """the same pass starting from HOST buffers: H2D of every input, assembly, D2H of the CutInfo
     BitArrays / cut ratios and of the CSR matrix.  returns (result dict, h2d bytes, d2h bytes).
 
     overlap=True: the copies run on two side streams ordered against the kernels by events — the
     connectivity and level set go first (classification needs only those), the dof table follows while
     the classification runs, the CutInfo outputs / the sparsity pattern / the values leave as soon
-    as their kernels have finished (PCIe is full duplex; the D2H of 1.7 GB is the long pole)."""
+    as their kernels have finished (PCIe is full duplex; the D2H of 1.7 GB is the long pole).
+
+    pipelined=True (needs overlap): the call does not wait for its own D2H — the next step's H2D and kernels run while
+    this step's results are still leaving (software pipelining over steps, two alternating sets of pinned landing
+    buffers).  The caller ends a sequence with `drain_host(hb, device)`; results of step k are valid after the drain or
+    once `hb.done[k % 2]` (a CUDA event) has completed."""
     main = torch.cuda.current_stream(device)
     if not overlap:
         els = hb.el_vtx.to(device, non_blocking=True)
@@ -233,6 +238,14 @@ def step_host(hb, dim, ndof_full, fe_order, device, ctx=None, overlap=True):
     if not hasattr(hb, "s_in"):
         hb.s_in, hb.s_out = torch.cuda.Stream(device), torch.cuda.Stream(device)
     s_in, s_out = hb.s_in, hb.s_out
+    par = ""
+    if pipelined:
+        hb.parity = 1 - getattr(hb, "parity", 1)
+        par = f"#{hb.parity}"
+        if not hasattr(hb, "done"):
+            hb.done = [None, None]
+        if hb.done[hb.parity] is not None:
+            hb.done[hb.parity].synchronize()   # this landing set was filled two steps ago: its consumer has had a full step
     s_in.wait_stream(main)
     s_out.wait_stream(main)
     with torch.cuda.stream(s_in):
@@ -254,7 +267,7 @@ def step_host(hb, dim, ndof_full, fe_order, device, ctx=None, overlap=True):
         with torch.cuda.stream(s_out):
             for name, t_ in items:
                 t_.record_stream(s_out)
-                d2h[0] += hb.land(name, t_)  # one D2H stream: two did not add bandwidth (PCIe bound, profiles/r01_notes.md)
+                d2h[0] += hb.land(name + par, t_)  # one D2H stream: two did not add bandwidth (PCIe bound, profiles/r01_notes.md)
 
     hooks = {
         "classified": lambda p: send([(f"bits{i}", b) for i, b in enumerate(p["bits"])] + [("cut_ratio", p["cut_ratio"])]),
@@ -265,9 +278,21 @@ def step_host(hb, dim, ndof_full, fe_order, device, ctx=None, overlap=True):
     }
     prob = CutAssembly(dim, els, xyz, eld, ndof_full, fe_order, ctx=ctx)
     r = prob.step(phi, hooks=hooks)
+    if pipelined:
+        hb.done[hb.parity] = torch.cuda.Event()
+        hb.done[hb.parity].record(s_out)
+        return r, hb.h2d_bytes(), d2h[0]
     s_out.synchronize()
     main.synchronize()
     return r, hb.h2d_bytes(), d2h[0]
+
+
+def drain_host(hb, device):
+    """end of a pipelined sequence of step_host calls: the launching stream waits for the outstanding copies"""
+    main = torch.cuda.current_stream(device)
+    if hasattr(hb, "s_out"):
+        main.wait_stream(hb.s_out)
+        main.wait_stream(hb.s_in)
 
 
 def sphere_levelset(points, centers, radius, eps=1e-14):

@@ -7,7 +7,7 @@ import torch
 
 import ngsxfem_b200 as xf
 from ngsxfem_b200 import ops
-from ngsxfem_b200.pipeline import CutAssembly, HostBuffers, sphere_levelset, step_host
+from ngsxfem_b200.pipeline import CutAssembly, HostBuffers, drain_host, sphere_levelset, step_host
 from oracle.pipeline_ref import oracle_step
 
 pytestmark = pytest.mark.gpu
@@ -74,6 +74,32 @@ def test_host_buffer_path_matches_device_path():
     assert h2d > 0 and d2h > 0
     assert torch.equal(hb.out["vals"][:r["nnz"]], r["vals"].cpu())
     assert torch.equal(hb.out["col"][:r["nnz"]], r["col"].cpu())
+
+
+def test_pipelined_host_steps_land_the_same_results():
+    """software-pipelined e2e steps (bench.py e2e leg): step k+1 starts while step k's results are still leaving; after the
+    drain both alternating landing sets hold the values of the plain step, bit for bit"""
+    n = 12
+    mesh = xf.MakeStructured3DMesh(nx=n, device=DEV)
+    V0 = xf.H1(mesh, order=2)
+    dev = torch.device(DEV, 0)
+    phis = [sphere_levelset(mesh.points, [(.5, .5, .5)], rr) for rr in (0.4, 0.33, 0.4)]
+    refs = [CutAssembly(3, mesh.elements, mesh.points, V0.el_dofs, V0.ndof, 2).step(ph) for ph in phis]
+    hb = HostBuffers(mesh.elements, mesh.points, V0.el_dofs, phis[0])
+    for k, ph in enumerate(phis):
+        hb.phi = ph.cpu().pin_memory()
+        step_host(hb, 3, V0.ndof, 2, dev, pipelined=True)
+        if k >= 1:   # the landing set of the previous step is complete once its event has fired
+            hb.done[1 - hb.parity].synchronize()
+            r = refs[k - 1]
+            assert torch.equal(hb.out[f"vals#{1 - hb.parity}"][:r["nnz"]], r["vals"].cpu())
+            assert torch.equal(hb.out[f"col#{1 - hb.parity}"][:r["nnz"]], r["col"].cpu())
+    drain_host(hb, dev)
+    torch.cuda.current_stream(dev).synchronize()
+    r = refs[-1]
+    assert torch.equal(hb.out[f"vals#{hb.parity}"][:r["nnz"]], r["vals"].cpu())
+    assert torch.equal(hb.out[f"rowptr#{hb.parity}"][:r["ndof"] + 1], r["rowptr"].cpu())
+    assert torch.equal(hb.out[f"cut_ratio#{hb.parity}"][:mesh.ne], r["cut_ratio"].cpu())
 
 
 def test_full_size_invariants():
