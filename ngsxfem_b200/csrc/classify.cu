@@ -321,7 +321,7 @@ extern "C" int xgpu_bitset_count(xgpu_ctx* ctx, const uint32_t* bits, int64_t nb
   if (g > XGPU_NSM * 8) g = XGPU_NSM * 8;
   k_popc_total<<<g, 256, 0, ctx->stream>>>(bits, nwords, (unsigned long long*)p);
   XGPU_LAUNCH_CHECK(ctx);
-  XGPU_CUDA(ctx, cudaMemcpyAsync(ctx->h_pinned, p, 8, cudaMemcpyDeviceToHost, ctx->stream));
+  XGPU_CUDA(ctx, xgpu_d2h_small(ctx->h_pinned, p, 8, ctx->stream));
   XGPU_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   *count_host = ctx->h_pinned[0];
   return XGPU_OK;
@@ -364,7 +364,7 @@ extern "C" int xgpu_bitset_rank(xgpu_ctx* ctx, const uint32_t* bits, int64_t nbi
   k_bits_rank<<<nblk(nbits, 256), 256, 0, ctx->stream>>>(bits, nbits, woff, map);
   XGPU_LAUNCH_CHECK(ctx);
   if (nactive_host) {
-    XGPU_CUDA(ctx, cudaMemcpyAsync(ctx->h_pinned, woff + nwords, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    XGPU_CUDA(ctx, xgpu_d2h_small(ctx->h_pinned, woff + nwords, 4, ctx->stream));
     XGPU_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     *nactive_host = *(int32_t*)ctx->h_pinned;
   }

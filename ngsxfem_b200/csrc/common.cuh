@@ -83,6 +83,23 @@ inline int xgpu_scratch(xgpu_ctx* ctx, int slot, size_t bytes, void** out)
   return XGPU_OK;
 }
 
+// Host scalars (counts, totals, status words) are read back WITHOUT the copy engine: a one-warp kernel writes them into
+// the context's mapped pinned staging block (cudaHostAlloc(..., Mapped): the host pointer is valid on the device under
+// UVA).  A cudaMemcpyAsync of 8 bytes queues on the device-to-host DMA engine behind any bulk D2H copy running on
+// another stream (the e2e leg ships 1.7 GB of results while the next step is being enqueued) and stalled the host for
+// the whole transfer (profiles/r01_notes.md, v34).
+static __global__ void k_to_host(unsigned char* __restrict__ dst, const unsigned char* __restrict__ src, int nbytes)
+{
+  for (int i = threadIdx.x; i < nbytes; i += blockDim.x) dst[i] = src[i];
+  __threadfence_system();
+}
+
+inline cudaError_t xgpu_d2h_small(void* dst_host_mapped, const void* src_dev, size_t bytes, cudaStream_t st)
+{
+  k_to_host<<<1, 32, 0, st>>>((unsigned char*)dst_host_mapped, (const unsigned char*)src_dev, (int)bytes);
+  return cudaGetLastError();
+}
+
 // record a per-element geometry error: keep the smallest failing element and its code
 __device__ __forceinline__ void xgpu_record_error(int* status, unsigned long long* status_elem, int code, long long elem)
 {

@@ -774,7 +774,7 @@ static int build_plan(xgpu_ctx* ctx, int64_t ndof, const xgpu_batch* batches_hos
     ctx->launches++;
   }
   XG_TRYRC(xgpu_exclusive_scan_i32(ctx, P->tmp32, ndof, (int64_t*)P->adj_ptr));
-  XG_TRY(cudaMemcpyAsync(ctx->h_pinned, P->adj_ptr + ndof, sizeof(long long), cudaMemcpyDeviceToHost, st));
+  XG_TRY(xgpu_d2h_small(ctx->h_pinned, P->adj_ptr + ndof, sizeof(long long), st));
   XG_TRY(cudaStreamSynchronize(st));
   P->nadj = ctx->h_pinned[0];
   XG_TRY(cudaMallocAsync(&P->adj, sizeof(long long) * (P->nadj > 0 ? P->nadj : 1), st));
@@ -796,8 +796,8 @@ static int build_plan(xgpu_ctx* ctx, int64_t ndof, const xgpu_batch* batches_hos
   }
   XG_TRYRC(xgpu_exclusive_scan_i32(ctx, P->tmp32, ndof, (int64_t*)P->candoff));
   XG_TRY(cudaEventRecord(P->ev[1], st));
-  XG_TRY(cudaMemcpyAsync(ctx->h_pinned, stats, 2 * sizeof(int), cudaMemcpyDeviceToHost, st));
-  XG_TRY(cudaMemcpyAsync(ctx->h_pinned + 1, P->candoff + ndof, sizeof(long long), cudaMemcpyDeviceToHost, st));
+  XG_TRY(xgpu_d2h_small(ctx->h_pinned, stats, 2 * sizeof(int), st));
+  XG_TRY(xgpu_d2h_small(ctx->h_pinned + 1, P->candoff + ndof, sizeof(long long), st));
   XG_TRY(cudaStreamSynchronize(st));
   P->maxcand = ((int*)ctx->h_pinned)[0];
   P->dups = ((int*)ctx->h_pinned)[1];
@@ -811,8 +811,8 @@ static int build_plan(xgpu_ctx* ctx, int64_t ndof, const xgpu_batch* batches_hos
   if (ndof > 0) XG_TRYRC(run_pattern(ctx, P, stats));
   XG_TRYRC(xgpu_exclusive_scan_i32(ctx, P->tmp32, ndof, (int64_t*)P->rowptr));
   XG_TRY(cudaEventRecord(P->ev[2], st));
-  XG_TRY(cudaMemcpyAsync(ctx->h_pinned, P->rowptr + ndof, sizeof(long long), cudaMemcpyDeviceToHost, st));
-  XG_TRY(cudaMemcpyAsync(ctx->h_pinned + 1, stats + 2, sizeof(int), cudaMemcpyDeviceToHost, st));
+  XG_TRY(xgpu_d2h_small(ctx->h_pinned, P->rowptr + ndof, sizeof(long long), st));
+  XG_TRY(xgpu_d2h_small(ctx->h_pinned + 1, stats + 2, sizeof(int), st));
   XG_TRY(cudaStreamSynchronize(st));
   P->nnz = ctx->h_pinned[0];
   P->maxnr = ((int*)(ctx->h_pinned + 1))[0];

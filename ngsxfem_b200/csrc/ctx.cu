@@ -161,7 +161,7 @@ extern "C" int xgpu_create(int device, xgpu_ctx** out)
   }
   if (cudaMalloc(&ctx->d_status, 2 * sizeof(int)) != cudaSuccess ||
       cudaMalloc(&ctx->d_status_elem, sizeof(unsigned long long)) != cudaSuccess ||
-      cudaMallocHost(&ctx->h_pinned, 16 * sizeof(int64_t)) != cudaSuccess) {
+      cudaHostAlloc(&ctx->h_pinned, 16 * sizeof(int64_t), cudaHostAllocMapped | cudaHostAllocPortable) != cudaSuccess) {
     delete ctx;
     return XGPU_ERR_CUDA;
   }
@@ -238,8 +238,8 @@ extern "C" int xgpu_clear_status(xgpu_ctx* ctx)
 extern "C" int xgpu_get_status(xgpu_ctx* ctx, int* code_host, int64_t* elem_host)
 {
   if (!ctx) return XGPU_ERR_ARG;
-  XGPU_CUDA(ctx, cudaMemcpyAsync(ctx->h_pinned, ctx->d_status, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
-  XGPU_CUDA(ctx, cudaMemcpyAsync(ctx->h_pinned + 1, ctx->d_status_elem, sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
+  XGPU_CUDA(ctx, xgpu_d2h_small(ctx->h_pinned, ctx->d_status, sizeof(int), ctx->stream));
+  XGPU_CUDA(ctx, xgpu_d2h_small(ctx->h_pinned + 1, ctx->d_status_elem, sizeof(unsigned long long), ctx->stream));
   XGPU_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   int code = *(int*)ctx->h_pinned;
   if (code_host) *code_host = code;

@@ -287,7 +287,7 @@ int xgpu_sum_f64(xgpu_ctx* ctx, double* buf_a, int64_t n, double* buf_b, double*
     double* t = in; in = out; out = t;
     n = nb;
   }
-  XGPU_CUDA(ctx, cudaMemcpyAsync(ctx->h_pinned, in, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  XGPU_CUDA(ctx, xgpu_d2h_small(ctx->h_pinned, in, sizeof(double), ctx->stream));
   XGPU_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   *result_host = *(double*)ctx->h_pinned;
   return XGPU_OK;
@@ -314,7 +314,7 @@ extern "C" int xgpu_cutquad_count(xgpu_ctx* ctx, int dim, int64_t n, const int32
   rc = xgpu_exclusive_scan_i32(ctx, counts, n, offsets);
   if (rc) return rc;
   if (total_host) {
-    XGPU_CUDA(ctx, cudaMemcpyAsync(ctx->h_pinned, offsets + n, sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
+    XGPU_CUDA(ctx, xgpu_d2h_small(ctx->h_pinned, offsets + n, sizeof(int64_t), ctx->stream));
     XGPU_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     *total_host = ctx->h_pinned[0];
   }

@@ -481,7 +481,7 @@ int finish_count(xgpu_ctx* ctx, const int32_t* counts, int64_t n, int64_t* offse
   int rc = xgpu_exclusive_scan_i32(ctx, counts, n, offsets);
   if (rc) return rc;
   if (total_host) {
-    XGPU_CUDA(ctx, cudaMemcpyAsync(ctx->h_pinned, offsets + n, sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
+    XGPU_CUDA(ctx, xgpu_d2h_small(ctx->h_pinned, offsets + n, sizeof(int64_t), ctx->stream));
     XGPU_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     *total_host = ctx->h_pinned[0];
   }

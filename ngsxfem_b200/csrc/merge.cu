@@ -55,7 +55,7 @@ extern "C" int xgpu_rows_offsets(xgpu_ctx* ctx, int64_t n, const int64_t* rowptr
   rc = xgpu_exclusive_scan_i32(ctx, (const int32_t*)p, n, offsets);
   if (rc) return rc;
   if (total_host) {
-    XGPU_CUDA(ctx, cudaMemcpyAsync(ctx->h_pinned, offsets + n, sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
+    XGPU_CUDA(ctx, xgpu_d2h_small(ctx->h_pinned, offsets + n, sizeof(int64_t), ctx->stream));
     XGPU_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     *total_host = ctx->h_pinned[0];
   }

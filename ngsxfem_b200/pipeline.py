@@ -209,7 +209,7 @@ class HostBuffers:
         return n * t.element_size()
 
 
-def step_host(hb, dim, ndof_full, fe_order, device, ctx=None, overlap=True, pipelined=False):
+def step_host(hb, dim, ndof_full, fe_order, device, ctx=None, overlap=True, pipelined=False, trace=None):
     """the same pass starting from HOST buffers: H2D of every input, assembly, D2H of the CutInfo
     BitArrays / cut ratios and of the CSR matrix.  returns (result dict, h2d bytes, d2h bytes).
 
@@ -248,6 +248,11 @@ def step_host(hb, dim, ndof_full, fe_order, device, ctx=None, overlap=True, pipe
             hb.done[hb.parity].synchronize()   # this landing set was filled two steps ago: its consumer has had a full step
     s_in.wait_stream(main)
     s_out.wait_stream(main)
+    def tr(name, stream):
+        if trace is not None:   # timeline of the copies (tools/e2e_timeline.py)
+            ev = torch.cuda.Event(enable_timing=True); ev.record(stream); trace.append((name, ev))
+
+    tr("h2d_begin", s_in)
     with torch.cuda.stream(s_in):
         els = hb.el_vtx.to(device, non_blocking=True)
         phi = hb.phi.to(device, non_blocking=True)
@@ -256,6 +261,7 @@ def step_host(hb, dim, ndof_full, fe_order, device, ctx=None, overlap=True, pipe
         e_rest = torch.cuda.Event(); e_rest.record(s_in)
         xyz = hb.vtx_xyz.to(device, non_blocking=True)       # ... the coordinates only the quadrature / element matrices
         e_xyz = torch.cuda.Event(); e_xyz.record(s_in)
+    tr("h2d_end", s_in)
     for t_ in (els, phi, xyz, eld):
         t_.record_stream(main)
     main.wait_event(e_first)
@@ -264,6 +270,7 @@ def step_host(hb, dim, ndof_full, fe_order, device, ctx=None, overlap=True, pipe
     def send(items):
         ev = torch.cuda.Event(); ev.record(main)
         s_out.wait_event(ev)
+        tr("d2h_begin:" + items[0][0], s_out)
         with torch.cuda.stream(s_out):
             for name, t_ in items:
                 t_.record_stream(s_out)
@@ -278,6 +285,8 @@ def step_host(hb, dim, ndof_full, fe_order, device, ctx=None, overlap=True, pipe
     }
     prob = CutAssembly(dim, els, xyz, eld, ndof_full, fe_order, ctx=ctx)
     r = prob.step(phi, hooks=hooks)
+    tr("d2h_end", s_out)
+    tr("compute_end", main)
     if pipelined:
         hb.done[hb.parity] = torch.cuda.Event()
         hb.done[hb.parity].record(s_out)
