@@ -16,7 +16,7 @@ import torch
 
 from . import ops
 from ._lib import XgpuError, default_ctx
-from .cutinfo import BitArray, GridFunction, POS, IF
+from .cutinfo import BitArray, GridFunction, POS
 from .forms import (CoordMonomial, CutDifferentialSymbol, FacetPatchDifferentialSymbol, Integral, MeshSize, Scalar,
                     SparseMatrixCSR)
 

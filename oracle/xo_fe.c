@@ -244,13 +244,11 @@ int xo_cut_elmat(const xo_trafo* T, int p, const double* lsetvals, int dt, int o
  *      DiffOpDt = L_j'(t) N_i (reference-time derivative); nodes of NodalTimeFE (SpaceTimeFE.cpp:258-282) ---- */
 void xo_time_dshapes(int order, double t, double* dshape)
 {
-  double nodes[8], sh0[8], sh1[8];
-  /* nodes recovered from the Lagrange property: use the closed list as xo_time_shapes does */
+  double nodes[8];
   if (order == 0) { dshape[0] = 0.0; return; }
   if (order == 1) { nodes[0] = 0; nodes[1] = 1; }
   else if (order == 2) { nodes[0] = 0; nodes[1] = 0.5; nodes[2] = 1; }
   else { nodes[0] = 0; nodes[1] = 0.5 * (1.0 - 1.0 / sqrt(5.0)); nodes[2] = 0.5 * (1.0 + 1.0 / sqrt(5.0)); nodes[3] = 1; }
-  (void)sh0; (void)sh1;
   for (int i = 0; i <= order; i++) {
     double ds = 0.0;
     for (int k = 0; k <= order; k++) if (k != i) {
