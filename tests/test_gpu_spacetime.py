@@ -444,3 +444,59 @@ def test_spacetime_edge_cases():
     # integrals of empty domains
     assert xf.Integrate({"levelset": allpos, "domain_type": NEG}, mesh=mesh, cf=1.0, order=1, time_order=1) == 0.0
     assert xf.Integrate({"levelset": allpos, "domain_type": IF}, mesh=mesh, cf=xf.tref, order=1, time_order=1) == 0.0
+
+
+# ---------------------------------------------------------------- solver level: DG-in-time heat equation
+def _heat_run(nx, nsteps, tend):
+    """tests/pytests/test_spacetimecutrule.py:72-140 restated with a polynomial solution (the accelerated path takes
+    monomial coefficients): u = t x(1-x) y(1-y) on the unit square, homogeneous Dirichlet data, slabs of length
+    delta_t, P1 x P1;  a = delta_t grad(u).grad(v) + dt(u) v on the slab + u(0) v(0),  f = delta_t f v + u_old v(0)."""
+    import scipy.sparse.linalg as spla
+    mesh = xf.MakeStructured2DMesh(nx=nx, ny=nx, device=DEV)
+    dlt = tend / nsteps
+    Vs = xf.H1(mesh, order=1)
+    V = xf.SpaceTimeFESpace(Vs, xf.ScalarTimeFE(1))
+    u, v = V.TnT()
+    dxt = xf.dxtref(mesh, time_order=2)
+    a = xf.BilinearForm(V)
+    a += dlt * xf.grad(u) * xf.grad(v) * dxt
+    a += xf.dt(u) * v * dxt
+    a += xf.fix_tref(u, 0) * xf.fix_tref(v, 0) * xf.dmesh(mesh)
+    a.Assemble()
+    ic = xf.BilinearForm(V)
+    ic += xf.fix_tref(u, 0) * xf.fix_tref(v, 0) * xf.dmesh(mesh)
+    ic.Assemble()
+    A, IC = a.mat.to_scipy().tocsr(), ic.mat.to_scipy().tocsr()
+    P = mesh.points.cpu().numpy()
+    inner = ~((P[:, 0] < 1e-12) | (P[:, 0] > 1 - 1e-12) | (P[:, 1] < 1e-12) | (P[:, 1] > 1 - 1e-12))
+    free = np.flatnonzero(np.concatenate([inner, inner]))
+    solve = spla.factorized(A[free][:, free].tocsc())
+    nv = mesh.nv
+    g = [(1.0, (1, 1)), (-1.0, (2, 1)), (-1.0, (1, 2)), (1.0, (2, 2))]       # x(1-x) y(1-y)
+    s = [(1.0, (1, 0)), (-1.0, (2, 0)), (1.0, (0, 1)), (-1.0, (0, 2))]       # x(1-x) + y(1-y)
+    mono = lambda c, e, te=0: c * xf.x ** e[0] * xf.y ** e[1] * (xf.tref ** te if te else 1.0)
+    uold = np.zeros(nv)
+    told = 0.0
+    for _ in range(nsteps):
+        f1 = xf.LinearForm(V)     # delta_t (g + 2 t_old s) v
+        for c, e in g:
+            f1 += mono(dlt * c, e) * v * dxt
+        for c, e in s:
+            f1 += mono(dlt * 2 * told * c, e) * v * dxt
+        for c, e in s:            # delta_t * 2 delta_t tref s v
+            f1 += mono(dlt * 2 * dlt * c, e, 1) * v * dxt
+        f1.Assemble()
+        rhs = f1.vec.cpu().numpy() + IC @ np.concatenate([uold, np.zeros(nv)])
+        sol = np.zeros(2 * nv)
+        sol[free] = solve(rhs[free])
+        uold = sol[nv:]           # nodal in time: the values at tref = 1
+        told += dlt
+    exact = told * P[:, 0] * (1 - P[:, 0]) * P[:, 1] * (1 - P[:, 1])
+    return np.sqrt(np.mean((uold - exact) ** 2)), np.abs(exact).max()
+
+
+def test_spacetime_heat_equation_converges():
+    e8, umax = _heat_run(8, 4, 0.5)
+    e16, _ = _heat_run(16, 4, 0.5)
+    assert e16 < 2e-4 * 1.0 and e16 < 0.02 * umax        # the reference's own bound for its sin solution is 2e-4
+    assert e8 / e16 > 3.0                                 # second order in h (the solution is linear in time: no time error)
