@@ -4,6 +4,7 @@ time derivative of polynomials, and the reference's own space-time known answers
 test_spacetimecutrule.py:14-69: int tref = 1/2, int tref^3 = 1/4, int tref^2 (x^2+y^2) = 2/9 on the unit square;
 level set 1-2x-2t: NEG 7/8, POS 1/8, IF 1/2) computed through element MATRICES and VECTORS."""
 import ctypes as C
+import math
 
 import numpy as np
 import pytest
@@ -82,3 +83,34 @@ def test_reference_known_answers_through_matrices_and_vectors(p, kt):
     # dt(u) v with u = 1: zero row sums; grad.grad annihilates constants
     assert abs(st_sum(P, E, ls, 1, NEG, 2 * kt, 2 * p, p, kt, terms=[(DT, ID, 1.0, 0)])) < 1e-14
     assert abs(st_sum(P, E, ls, 1, NEG, 2 * kt, 2 * p, p, kt, terms=[(GRAD, GRAD, 1.0, 0)])) < 1e-14
+
+
+@pytest.mark.parametrize("dim", [1, 2, 3])
+def test_uncut_p1_element_matrices_are_the_closed_form_tensor_products(dim):
+    """layout and operators of the oracle's space-time basis against closed forms on one uncut affine simplex:
+    mass = M_time (x) M_space, dt-form = D_time (x) M_space, stiffness = M_time (x) K_space with
+    M_space = |T| (1 + delta_ik) / ((D+1)(D+2)),  K_space = |T| grad(lam_i).grad(lam_k),
+    P1 time: M_time = [[1/3, 1/6], [1/6, 1/3]], D_time[j][l] = int L_j L_l' = [[-1/2, 1/2], [-1/2, 1/2]]  (rows = test);
+    P2 time (nodes 0, 1/2, 1): M_time = [[4, 2, -1], [2, 16, 2], [-1, 2, 4]] / 30  (time-major dofs: j * nd_s + i)"""
+    rng = np.random.default_rng(5)
+    V = np.eye(dim + 1, dim) + 0.2 * rng.standard_normal((dim + 1, dim))      # a generic simplex
+    vnum = np.arange(dim + 1, dtype=np.int32)
+    T = xo.make_trafo(V, vnum)
+    E = (V[:dim] - V[dim]).T                                                    # F: columns v_k - v_D (v_D <-> origin)
+    vol = abs(np.linalg.det(E)) / math.factorial(dim)
+    Ms = vol * (np.ones((dim + 1, dim + 1)) + np.eye(dim + 1)) / ((dim + 1) * (dim + 2))
+    G = np.vstack([np.linalg.inv(E), -np.linalg.inv(E).sum(axis=0)])            # rows: physical gradients of lam_k
+    Ks = vol * G @ G.T
+    neg = -np.ones((2, dim + 1))
+    for kt, Mt, Dt in ((1, np.array([[1 / 3, 1 / 6], [1 / 6, 1 / 3]]), np.array([[-.5, .5], [-.5, .5]])),
+                       (2, np.array([[4, 2, -1], [2, 16, 2], [-1, 2, 4]]) / 30.0, None)):
+        q, tv, w = xo.spacetime_cut_rule(T, neg, 1, NEG, 2 * kt, 2)
+        m = xo.elmat_st_from_rule(T, 1, kt, q, tv, w, [(ID, ID, 1.0, 0)])
+        assert np.allclose(m, np.kron(Mt, Ms), rtol=1e-13, atol=1e-16)
+        k = xo.elmat_st_from_rule(T, 1, kt, q, tv, w, [(GRAD, GRAD, 1.0, 0)])
+        assert np.allclose(k, np.kron(Mt, Ks), rtol=1e-12, atol=1e-15)
+        if Dt is not None:
+            d = xo.elmat_st_from_rule(T, 1, kt, q, tv, w, [(DT, ID, 1.0, 0)])   # (op_trial, op_test): dt(u) v
+            assert np.allclose(d, np.kron(Dt, Ms), rtol=1e-13, atol=1e-16)
+            dT = xo.elmat_st_from_rule(T, 1, kt, q, tv, w, [(ID, DT, 1.0, 0)])  # u dt(v): the transpose
+            assert np.allclose(dT, d.T, rtol=1e-13, atol=1e-16)
