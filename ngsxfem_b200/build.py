@@ -41,6 +41,11 @@ def build(force=False, verbose=False):
         if force or not os.path.exists(obj) or os.path.getmtime(obj) < max(os.path.getmtime(src), hdr_t):
             jobs.append((src, obj))
 
+    # longest translation units first (measured seconds on this image), so that the pool's tail is short
+    heavy = {"facetpatch.cu": 136, "elmat_st_d3.cu": 90, "facetpatch_dmma_33.cu": 74, "facetpatch_dmma_34.cu": 72, "elmat_st_d2.cu": 65,
+             "elmat_ms_3.cu": 62, "elmat.cu": 52, "elmat_st_d1.cu": 35, "elmat_dmma_3.cu": 31, "cutquad_ext.cu": 29}
+    jobs.sort(key=lambda j: -heavy.get(os.path.basename(j[0]), 10))
+
     def cc(job):
         src, obj = job
         extra = ["-fmad=false"] if os.path.basename(src) in NO_FMA else []
