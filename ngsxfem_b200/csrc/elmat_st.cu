@@ -11,6 +11,8 @@
 //        functions at one point each in shared memory, then own 2x2 register blocks of the matrix and contract over
 //        the staged points in point order (fixed summation order => bit-reproducible).
 //   k_elvec_st<D>       the same staging, lane per dof sums  f(x_q, t_q) w_q |det F| op(v)  over the points.
+// (both in elmat_st_impl.cuh, instantiated per dimension in elmat_st_d1/2/3.cu; the tensor-structured kernel for the common
+// orders is elmat_st_tp.cu.)  This file: the C ABI, argument checks, dispatch, and the space-time facet-patch expansion.
 #include "common.cuh"
 #include "cutgeom.cuh"
 #include "deform.cuh"
