@@ -114,3 +114,24 @@ def test_uncut_p1_element_matrices_are_the_closed_form_tensor_products(dim):
             assert np.allclose(d, np.kron(Dt, Ms), rtol=1e-13, atol=1e-16)
             dT = xo.elmat_st_from_rule(T, 1, kt, q, tv, w, [(ID, DT, 1.0, 0)])  # u dt(v): the transpose
             assert np.allclose(dT, d.T, rtol=1e-13, atol=1e-16)
+
+
+def test_oracle_reproduces_the_committed_golden_vectors():
+    """tests/golden/spacetime_elmat.json (tools/gen_golden_spacetime.py): rules, element matrices and vectors of three cut
+    space-time elements — freezes the restatement against drift"""
+    import json
+    import os
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, os.path.join(root, "tools"))
+    import gen_golden_spacetime as gg
+    gold = json.load(open(os.path.join(root, "tests", "golden", "spacetime_elmat.json")))
+    assert [tuple(t) for t in gold["terms"]] == gg.TERMS
+    for c in gold["cases"]:
+        q, tv, w, m, v = gg.compute(c)
+        assert len(w) == len(c["wts"]) > 0
+        assert np.allclose(q, np.array(c["pts"]), rtol=0, atol=1e-15)
+        assert np.allclose(tv, np.array(c["tvals"]), rtol=0, atol=1e-15)
+        assert np.allclose(w, np.array(c["wts"]), rtol=1e-14, atol=1e-18)
+        assert np.allclose(m, np.array(c["elmat"]), rtol=1e-14, atol=1e-16)
+        assert np.allclose(v, np.array(c["elvec"]), rtol=1e-14, atol=1e-16)
