@@ -135,3 +135,41 @@ def test_oracle_reproduces_the_committed_golden_vectors():
         assert np.allclose(w, np.array(c["wts"]), rtol=1e-14, atol=1e-18)
         assert np.allclose(m, np.array(c["elmat"]), rtol=1e-14, atol=1e-16)
         assert np.allclose(v, np.array(c["elvec"]), rtol=1e-14, atol=1e-16)
+
+
+@pytest.mark.parametrize("kt", [1, 2])
+def test_moving_plane_in_3d_known_answers(kt):
+    """3D analogue of the reference's moving-plane test: lset = x + t - 1 on the unit cube (6 Kuhn tets): the NEG domain
+    {x < 1 - t} has space-time volume 1/2, POS 1/2, the interface (a unit square for every t) space-time measure 1;
+    first moments int_NEG x = 1/6, int_NEG tref = 1/6 — through the mass matrix / element vectors of a P1 x P_kt space"""
+    import itertools
+    P = np.array(list(itertools.product([0.0, 1.0], repeat=3)))[:, ::-1].copy()      # vertex id = i + 2 j + 4 k
+    vid = lambda c: int(c[0] + 2 * c[1] + 4 * c[2])
+    els = []
+    for perm in itertools.permutations(range(3)):
+        c = [0, 0, 0]
+        path = [vid(c)]
+        for ax in perm:
+            c[ax] = 1
+            path.append(vid(c))
+        els.append(path)
+    E = np.array(els, dtype=np.int32)
+    nodes = NODES[kt]
+    ls = np.stack([P[:, 0] + t - 1 for t in nodes])
+    ls = np.where(np.abs(ls) < 1e-14, 1e-14, ls)
+    one = np.zeros(4 * (kt + 1)); one[:] = 1.0                                    # P1: all shape functions sum to 1
+    res = {}
+    for dom in (NEG, POS, IF):
+        tot = mx = mt = 0.0
+        for el in range(6):
+            T = xo.make_trafo(P[E[el]], E[el])
+            q, tv, w = xo.spacetime_cut_rule(T, ls[:, E[el]], kt, dom, 2 * kt, 2)
+            if not len(w):
+                continue
+            tot += one @ xo.elmat_st_from_rule(T, 1, kt, q, tv, w, [(ID, ID, 1.0, 0)]) @ one
+            mx += one @ xo.elvec_st_from_rule(T, 1, kt, q, tv, w, [(ID, 1.0, 0, (1, 0, 0, 0))])
+            mt += one @ xo.elvec_st_from_rule(T, 1, kt, q, tv, w, [(ID, 1.0, 0, (0, 0, 0, 1))])
+        res[dom] = (tot, mx, mt)
+    assert abs(res[NEG][0] - 0.5) < 1e-13 and abs(res[POS][0] - 0.5) < 1e-13 and abs(res[IF][0] - 1.0) < 1e-13
+    assert abs(res[NEG][1] - 1 / 6) < 1e-13 and abs(res[NEG][2] - 1 / 6) < 1e-13
+    assert abs(res[IF][1] - 0.5) < 1e-13                                             # int_0^1 (1 - t) dt on the interface
