@@ -173,3 +173,17 @@ def test_moving_plane_in_3d_known_answers(kt):
     assert abs(res[NEG][0] - 0.5) < 1e-13 and abs(res[POS][0] - 0.5) < 1e-13 and abs(res[IF][0] - 1.0) < 1e-13
     assert abs(res[NEG][1] - 1 / 6) < 1e-13 and abs(res[NEG][2] - 1 / 6) < 1e-13
     assert abs(res[IF][1] - 0.5) < 1e-13                                             # int_0^1 (1 - t) dt on the interface
+
+
+def test_quadratic_in_time_level_sets_known_answers():
+    """P2-in-time level sets on the unit square (two triangles), space-time rule with time_order 2:
+    (a) lset = x - (1/4 + t^2/2): no vertex changes sign, NEG area(t) = 1/4 + t^2/2, space-time volume 5/12;
+    (b) lset = x - 2 t^2: the vertices with x = 1 change sign at t = 1/sqrt(2) (quadratic root finding,
+        cutint/spacetimecutrule.cpp:20-48), NEG volume = int_0^{1/sqrt 2} 2 t^2 dt + 1 - 1/sqrt 2 = 1 - sqrt(2)/3"""
+    P, E = unit_square()
+    for fn, ref in ((lambda x, t: x - (0.25 + 0.5 * t * t), 5 / 12), (lambda x, t: x - 2 * t * t, 1 - np.sqrt(2) / 3)):
+        ls = np.stack([fn(P[:, 0], t) for t in NODES[2]])
+        ls = np.where(np.abs(ls) < 1e-14, 1e-14, ls)
+        neg = st_sum(P, E, ls, 2, NEG, 2, 2, 1, 2, terms=[(ID, ID, 1.0, 0)])
+        pos = st_sum(P, E, ls, 2, POS, 2, 2, 1, 2, terms=[(ID, ID, 1.0, 0)])
+        assert abs(neg - ref) < 1e-13 and abs(neg + pos - 1.0) < 1e-13
