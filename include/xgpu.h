@@ -48,7 +48,8 @@ int xgpu_create(int device, xgpu_ctx** ctx_out);
 void xgpu_destroy(xgpu_ctx* ctx);
 int xgpu_set_stream(xgpu_ctx* ctx, void* cuda_stream);
 /* tuning switches (no reference counterpart).  "elmat_dmma": element-matrix contraction on FP64
- * tensor-core tiles: -1 never, 0 (default) at FE order >= 3, 1 also at order 2.  "elmat_st_tp": space-time element
+ * tensor-core tiles: -1 never, 0 (default) at FE order >= 3, 1 also at order 2.  "csr_trips": one-pass CSR kernels, 2 = half-width lane groups with two columns per
+ * lane (0 = policy).  "elmat_st_tp": space-time element
  * matrices on the tensor-structured kernel where instantiated (default 1; 0 = always the generic kernel) */
 int xgpu_set_option(xgpu_ctx* ctx, const char* key, int value);
 /* Isoparametric mesh deformation — the state NGSolve keeps in the mesh (`mesh.SetDeformation(gf)`, set and
@@ -206,6 +207,15 @@ int xgpu_elmat_std(xgpu_ctx* ctx, int dim, int fe_order, int64_t n, const int32_
                    const xgpu_term* terms_host, int nterms, int accumulate, const int32_t* slots,
                    double* mats);
 
+/* uncut AFFINE elements, mass / stiffness terms only (ID*ID, GRAD.GRAD): the element matrix is
+ *   sum_m coefs[m] * tref[m]   with  coefs = |det F| * (c_m, c_s G_00, c_s G_01, ...),  G = F^-1 F^-T  (1 + dim(dim+1)/2 entries,
+ * rows padded to 8 doubles) and the reference tensors tref[m] (nd x nd each: M_ref, K_ref^ab) of the rule of `order`.
+ * xgpu_affine_coefs writes the per-element coefficients (64 B instead of nd^2 * 8 B); xgpu_reftensor returns the DEVICE
+ * pointer of the cached tensors.  Consumed by procedural batches of xgpu_csr_assemble_fused. */
+int xgpu_affine_coefs(xgpu_ctx* ctx, int dim, int64_t n, const int32_t* elems, const int32_t* el_vtx,
+                      const double* vtx_xyz, const xgpu_term* terms_host, int nterms, double* coefs /* n x 8 */);
+int xgpu_reftensor(xgpu_ctx* ctx, int dim, int fe_order, int order, const double** tref_dev_out, int* ncoef_host);
+
 /* element vectors: SymbolicCutLinearFormIntegrator::T_CalcElementVector (xfem/symboliccutlfi.cpp:51-140) for
  * sums of  f(x) * op_test(v),  f = coef * h^hpow * x^expo[0] y^expo[1] z^expo[2],  op_test 0 = ID, 2 = DN.
  * vecs: n x nd; rule order of _std: `order`, or 2*fe_order if < 0 (:86-88).  Same accumulate / slots meaning. */
@@ -263,7 +273,13 @@ int xgpu_facetpatch_st(xgpu_ctx* ctx, int dim, int fe_order, int time_fe_order, 
  * with one width x width matrix per row.  The pattern is the union of the row cliques of all
  * batches, columns ascending, explicit zeros kept; values are summed in a fixed order
  * (batch, then row index) so results are bit-reproducible run to run. */
-typedef struct { const int32_t* table; const double* mats; int64_t nrows; int width; } xgpu_batch;
+typedef struct {
+  const int32_t* table;
+  const double* mats;
+  int64_t nrows;
+  int width;
+  const double* coefs; /* xgpu_csr_assemble_fused only: procedural affine batch (xgpu_affine_coefs), mats NULL; else NULL */
+} xgpu_batch;
 int xgpu_csr_plan(xgpu_ctx* ctx, int64_t ndof, const xgpu_batch* batches_host, int nbatches,
                   xgpu_plan** plan_out, int64_t* nnz_host);
 int xgpu_csr_pattern(xgpu_ctx* ctx, xgpu_plan* plan, int64_t* rowptr, int32_t* colidx);
@@ -280,6 +296,20 @@ int xgpu_vec_scatter(xgpu_ctx* ctx, xgpu_plan* plan, const xgpu_batch* batches_h
  * — the separate compaction copy (and its 1.6 GB of DRAM traffic on config 2) disappears.  Same results, bit for bit. */
 int xgpu_csr_assemble(xgpu_ctx* ctx, xgpu_plan* plan, const xgpu_batch* batches_host, int nbatches,
                       int64_t* rowptr, int32_t* colidx, double* vals);
+/* The one-row-pass path.  xgpu_csr_plan_rows = transposed table + a lean COUNT pass (distinct columns per row, keys
+ * only) + scan: the plan knows rowptr and nnz.  xgpu_csr_assemble_fused then finishes every row in ONE visit: its
+ * contributions are deduplicated and summed in (batch, row, local index) order in a shared-memory table sized from the
+ * row's exact length, sorted, and written to their final CSR position (rowptr, colidx, vals; colidx / vals hold nnz
+ * entries).  A batch with `coefs` set is a PROCEDURAL batch of uncut affine elements (SymbolicCutBFI on elements where
+ * the cut rule is the plain rule, xfem/symboliccutbfi.cpp:127-135): row i of its element matrix is
+ * sum_m coefs[e][m] * tref[m][i][:]  with the reference tensors of xgpu_reftensor — bit-identical to xgpu_elmat_std's
+ * affine path, without the matrices ever reaching memory.  XGPU_ERR_UNSUPPORTED from xgpu_csr_plan_rows (duplicate dofs
+ * in a table row, rows wider than 64, rows with too many candidates): use xgpu_csr_plan + xgpu_csr_assemble.  Results
+ * equal the two-pass path bit for bit (rows up to 32 wide; wider rows: same pattern, strict sequential summation order). */
+int xgpu_csr_plan_rows(xgpu_ctx* ctx, int64_t ndof, const xgpu_batch* batches_host, int nbatches,
+                       xgpu_plan** plan_out, int64_t* nnz_host);
+int xgpu_csr_assemble_fused(xgpu_ctx* ctx, xgpu_plan* plan, const xgpu_batch* batches_host, int nbatches,
+                            const double* tref, int ncoef, int64_t* rowptr, int32_t* colidx, double* vals);
 void xgpu_plan_destroy(xgpu_plan* plan);
 /* device time of the two halves of xgpu_csr_plan (CUDA events on the plan's stream): ms_host[0] =
  * transposed table (histogram, scan, fill, segment sort), ms_host[1] = pattern pass (bench.py) */

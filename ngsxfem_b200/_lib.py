@@ -36,7 +36,7 @@ class StLTerm(C.Structure):
 
 
 class Batch(C.Structure):
-    _fields_ = [("table", VP), ("mats", VP), ("nrows", C.c_int64), ("width", C.c_int)]
+    _fields_ = [("table", VP), ("mats", VP), ("nrows", C.c_int64), ("width", C.c_int), ("coefs", VP)]
 
 
 _SIGS = {
@@ -106,6 +106,10 @@ _SIGS = {
     "xgpu_adjacency_plan": (C.c_int, [VP, C.c_int64, C.POINTER(Batch), C.c_int, C.POINTER(VP)]),
     "xgpu_vec_scatter": (C.c_int, [VP, VP, C.POINTER(Batch), C.c_int, VP]),
     "xgpu_csr_assemble": (C.c_int, [VP, VP, C.POINTER(Batch), C.c_int, VP, VP, VP]),
+    "xgpu_csr_plan_rows": (C.c_int, [VP, C.c_int64, C.POINTER(Batch), C.c_int, C.POINTER(VP), c_i64p]),
+    "xgpu_csr_assemble_fused": (C.c_int, [VP, VP, C.POINTER(Batch), C.c_int, VP, C.c_int, VP, VP, VP]),
+    "xgpu_affine_coefs": (C.c_int, [VP, C.c_int, C.c_int64, VP, VP, VP, C.POINTER(Term), C.c_int, VP]),
+    "xgpu_reftensor": (C.c_int, [VP, C.c_int, C.c_int, C.c_int, C.POINTER(VP), c_intp]),
     "xgpu_plan_destroy": (None, [VP]),
     "xgpu_plan_phase_ms": (C.c_int, [VP, c_f64p]),
     "xgpu_rows_offsets": (C.c_int, [VP, C.c_int64, VP, VP, VP, c_i64p]),
@@ -179,7 +183,9 @@ class Ctx:
     def check(self, rc):
         if rc != 0:
             msg = self.lib.xgpu_last_error(self.h)
-            raise XgpuError(f"xgpu error {rc}: {msg.decode() if msg else ''}")
+            err = XgpuError(f"xgpu error {rc}: {msg.decode() if msg else ''}")
+            err.code = rc
+            raise err
 
     def status(self):
         code = C.c_int(0)

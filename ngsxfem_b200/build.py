@@ -6,6 +6,7 @@ nvcc cross-compiles without a GPU; the .so lands next to this file so that it tr
 repository snapshot to the GPU box (it is git-ignored, not gpurun-ignored).
 """
 import os
+import re
 import subprocess
 import sys
 from concurrent.futures import ThreadPoolExecutor
@@ -24,21 +25,32 @@ FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-li
          "-Xcompiler", "-fPIC", "-ccbin", "/usr/bin/g++", "--expt-relaxed-constexpr"]
 
 
-def _deps():
-    hdrs = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h", ".inc"))]
-    hdrs.append(os.path.join(os.path.dirname(HERE), "include", "xgpu.h"))
-    return max(os.path.getmtime(h) for h in hdrs)
+_INC = re.compile(r'^\s*#\s*include\s+"([^"]+)"', re.M)
+
+
+def _deps(src, seen=None):
+    """newest mtime among the files `src` includes (recursively, quoted includes only)"""
+    seen = set() if seen is None else seen
+    t = os.path.getmtime(src)
+    with open(src) as f:
+        text = f.read()
+    for inc in _INC.findall(text):
+        path = os.path.normpath(os.path.join(os.path.dirname(src), inc))
+        if path in seen or not os.path.exists(path):
+            continue
+        seen.add(path)
+        t = max(t, _deps(path, seen))
+    return t
 
 
 def build(force=False, verbose=False):
     os.makedirs(OBJ, exist_ok=True)
     srcs = sorted(f for f in os.listdir(CSRC) if f.endswith(".cu"))
-    hdr_t = _deps()
     jobs = []
     for s in srcs:
         src = os.path.join(CSRC, s)
         obj = os.path.join(OBJ, s[:-3] + ".o")
-        if force or not os.path.exists(obj) or os.path.getmtime(obj) < max(os.path.getmtime(src), hdr_t):
+        if force or not os.path.exists(obj) or os.path.getmtime(obj) < _deps(src):
             jobs.append((src, obj))
 
     # longest translation units first (measured seconds on this image), so that the pool's tail is short

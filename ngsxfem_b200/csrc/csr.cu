@@ -19,48 +19,13 @@
 //             row, local index) order: no atomics, bit-reproducible, every matrix entry is read
 //             once and every value written once (write-only: no memset of vals needed).
 // All kernels are HBM/L2-gather bound; algorithmic bytes are stated in DESIGN.md.
-#include "common.cuh"
+#include "csr.cuh"
 #include <algorithm>
 #include <vector>
-
-#define XG_MAXBATCH 8
-#define XG_EMPTY 0x7fffffff
-#define XG_UB 4  // adjacency entries per prefetch batch
-
-struct BatchDev {
-  int nb;
-  const int32_t* table[XG_MAXBATCH];
-  const double* mats[XG_MAXBATCH];
-  long long rowoff[XG_MAXBATCH + 1];
-  int width[XG_MAXBATCH];
-};
-
-struct xgpu_plan {
-  int64_t ndof = 0, nadj = 0, nnz = 0, ncand = 0;
-  int maxcand = 0, maxnr = 0, wmax = 0, dups = 0;
-  int64_t epoch = -1;             // ctx->epoch at which the pattern scratch (slot 8) was filled
-  bool with_pattern = false;      // false: transposed table only (xgpu_adjacency_plan)
-  BatchDev bd;
-  long long* adj_ptr = nullptr;   // ndof+1
-  long long* adj = nullptr;       // nadj entries: (global table row << 8) | local index
-  long long* rowptr = nullptr;    // ndof+1
-  long long* candoff = nullptr;   // ndof+1: offsets of the rows in the candidate scratch
-  int32_t* tmp32 = nullptr;       // ndof+2 counters
-  cudaStream_t stream = 0;        // the buffers are stream-ordered allocations on this stream
-  cudaEvent_t ev[3] = {};         // start / adjacency built / pattern pass done (xgpu_plan_phase_ms)
-};
 
 namespace {
 
 inline unsigned nblk(int64_t n, int t) { return (unsigned)((n + t - 1) / t); }
-
-// adjacency entry: (batch << 56) | (local table row << 8) | local index — ascending order is
-// (batch, row, local index), the summation order of the scatter
-#define XG_ADJ(bi, r, loc) (((long long)(bi) << 56) | ((long long)(r) << 8) | (long long)(loc))
-#define XG_ADJ_BATCH(e) ((int)((unsigned long long)(e) >> 56))
-#define XG_ADJ_ROW(e) ((int)(unsigned)((unsigned long long)(e) >> 8))  // rows < 2^31 per batch
-#define XG_ADJ_LOC(e) ((int)((e) & 255))
-#define XG_ADJ_ROWKEY(e) ((e) >> 8)  // (batch, row)
 
 __global__ void k_adj_count(const int32_t* __restrict__ table, int64_t nent, int32_t* __restrict__ cnt)
 {
@@ -649,7 +614,7 @@ int fill_bd(xgpu_ctx* ctx, const xgpu_batch* bh, int nb, BatchDev& bd)
   for (int i = 0; i < nb; i++) {
     if (bh[i].width < 1 || bh[i].width > 255 || bh[i].nrows < 0) return xgpu_fail(ctx, XGPU_ERR_ARG, "csr: bad batch");
     if (bh[i].nrows * bh[i].width >= (int64_t)0x7fffffff) return xgpu_fail(ctx, XGPU_ERR_CAPACITY, "csr: a batch has 2^31 or more table entries; split it");
-    bd.table[i] = bh[i].table; bd.mats[i] = bh[i].mats; bd.width[i] = bh[i].width;
+    bd.table[i] = bh[i].table; bd.mats[i] = bh[i].mats; bd.coefs[i] = nullptr; bd.width[i] = bh[i].width;
     bd.rowoff[i + 1] = bd.rowoff[i] + bh[i].nrows;
   }
   return XGPU_OK;
@@ -665,6 +630,7 @@ extern "C" void xgpu_plan_destroy(xgpu_plan* p)
   if (p->rowptr) cudaFreeAsync(p->rowptr, p->stream);
   if (p->candoff) cudaFreeAsync(p->candoff, p->stream);
   if (p->tmp32) cudaFreeAsync(p->tmp32, p->stream);
+  if (p->rowcnt) cudaFreeAsync(p->rowcnt, p->stream);
   for (int i = 0; i < 3; i++) if (p->ev[i]) cudaEventDestroy(p->ev[i]);
   delete p;
 }
@@ -737,6 +703,11 @@ extern "C" int xgpu_csr_plan(xgpu_ctx* ctx, int64_t ndof, const xgpu_batch* batc
                              xgpu_plan** plan_out, int64_t* nnz_host)
 {
   return build_plan(ctx, ndof, batches_host, nbatches, plan_out, nnz_host, true);
+}
+
+int xgpu_build_adjacency(xgpu_ctx* ctx, int64_t ndof, const xgpu_batch* batches_host, int nbatches, xgpu_plan** plan_out)
+{
+  return build_plan(ctx, ndof, batches_host, nbatches, plan_out, nullptr, false);
 }
 
 extern "C" int xgpu_adjacency_plan(xgpu_ctx* ctx, int64_t ndof, const xgpu_batch* batches_host, int nbatches,

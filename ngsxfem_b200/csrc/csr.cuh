@@ -1,0 +1,43 @@
+#pragma once
+// csr.cuh — plan / batch structures shared by csr.cu (transposed table, two-pass pattern + scatter) and
+// csr_fused.cu (one row pass: pattern + values + procedural affine batches)
+#include "common.cuh"
+
+#define XG_MAXBATCH 8
+#define XG_EMPTY 0x7fffffff
+#define XG_UB 4  // adjacency entries per prefetch batch
+
+struct BatchDev {
+  int nb;
+  const int32_t* table[XG_MAXBATCH];
+  const double* mats[XG_MAXBATCH];
+  const double* coefs[XG_MAXBATCH];  // procedural affine batch: nrows x 8 coefficients (mats NULL)
+  long long rowoff[XG_MAXBATCH + 1];
+  int width[XG_MAXBATCH];
+};
+
+struct xgpu_plan {
+  int64_t ndof = 0, nadj = 0, nnz = 0, ncand = 0;
+  int maxcand = 0, maxnr = 0, wmax = 0, dups = 0;
+  int64_t epoch = -1;             // ctx->epoch at which the pattern scratch (slot 8) was filled
+  bool with_pattern = false;      // false: transposed table only (xgpu_adjacency_plan)
+  bool counted = false;           // xgpu_csr_plan_rows: rowptr / nnz / maxnr from the count pass (no pattern scratch)
+  int32_t* rowcnt = nullptr;      // counted plans: distinct columns per row
+  BatchDev bd;
+  long long* adj_ptr = nullptr;   // ndof+1
+  long long* adj = nullptr;       // nadj entries: (global table row << 8) | local index
+  long long* rowptr = nullptr;    // ndof+1
+  long long* candoff = nullptr;   // ndof+1: offsets of the rows in the candidate scratch
+  int32_t* tmp32 = nullptr;       // ndof+2 counters
+  cudaStream_t stream = 0;        // the buffers are stream-ordered allocations on this stream
+  cudaEvent_t ev[3] = {};         // start / adjacency built / pattern pass done (xgpu_plan_phase_ms)
+};
+
+// adjacency entry: (batch << 56) | (local table row << 8) | local index — ascending order is
+// (batch, row, local index), the summation order of the scatter
+#define XG_ADJ(bi, r, loc) (((long long)(bi) << 56) | ((long long)(r) << 8) | (long long)(loc))
+#define XG_ADJ_BATCH(e) ((int)((unsigned long long)(e) >> 56))
+#define XG_ADJ_ROW(e) ((int)(unsigned)((unsigned long long)(e) >> 8))  // rows < 2^31 per batch
+#define XG_ADJ_LOC(e) ((int)((e) & 255))
+#define XG_ADJ_ROWKEY(e) ((e) >> 8)  // (batch, row)
+

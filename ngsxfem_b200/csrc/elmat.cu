@@ -158,6 +158,77 @@ extern "C" int xgpu_elmat_rule_pair(xgpu_ctx* ctx, int dim, int fe_order, int64_
   return launch_pair<1>(ctx, fe_order, n, elems, el_vtx, vtx_xyz, offsets_a, pts_a, wts_a, Ta, R2, accumulate, slots, mats);
 }
 
+namespace {
+// the geometry half of k_elmat_affine: same operations in the same order, so that  sum_m coefs[m] * tref[m]  evaluated
+// elsewhere (csr_fused.cu) reproduces its matrices bit for bit
+template <int D>
+__global__ void __launch_bounds__(256) k_affine_coefs(int64_t n, const int32_t* __restrict__ elems, const int32_t* __restrict__ el_vtx,
+                                                      const double* __restrict__ vtx_xyz, TermsDev T, double* __restrict__ coefs)
+{
+  constexpr int NG = D * (D + 1) / 2;
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n) return;
+  const int64_t el = elems ? (int64_t)elems[e] : e;
+  double vx[D + 1][3], F[D * D], Fi[D * D], coef[8];
+#pragma unroll
+  for (int k = 0; k < D + 1; k++) {
+    const int v = __ldg(el_vtx + el * (D + 1) + k);
+#pragma unroll
+    for (int c = 0; c < 3; c++) vx[k][c] = (c < D) ? __ldg(vtx_xyz + (int64_t)v * D + c) : 0.0;
+  }
+  xg_affine_jac<D>(vx, F);
+  const double meas = fabs(xg_inv<D>(F, Fi));
+  const double h = (D == 1) ? meas : ((D == 2) ? sqrt(meas) : cbrt(meas));
+  double cm = 0.0, cs = 0.0;
+  for (int t = 0; t < T.n; t++) {
+    const double c = T.coef[t] * ipow(h, T.hpow[t]) * meas;
+    if (T.op_test[t] == 0) cm += c; else cs += c;
+  }
+  coef[0] = cm;
+  int m = 1;
+#pragma unroll
+  for (int a = 0; a < D; a++)
+#pragma unroll
+    for (int b = a; b < D; b++) {
+      double gab = 0.0;
+#pragma unroll
+      for (int c = 0; c < D; c++) gab += Fi[a * D + c] * Fi[b * D + c];
+      coef[m++] = cs * gab;
+    }
+#pragma unroll
+  for (int k = 1 + NG; k < 8; k++) coef[k] = 0.0;
+  double2* out = reinterpret_cast<double2*>(coefs + e * 8);
+#pragma unroll
+  for (int k = 0; k < 4; k++) out[k] = make_double2(coef[2 * k], coef[2 * k + 1]);
+}
+}  // namespace
+
+extern "C" int xgpu_affine_coefs(xgpu_ctx* ctx, int dim, int64_t n, const int32_t* elems, const int32_t* el_vtx,
+                                 const double* vtx_xyz, const xgpu_term* terms_host, int nterms, double* coefs)
+{
+  if (!ctx || dim < 1 || dim > 3 || n < 0 || !coefs) return xgpu_fail(ctx, XGPU_ERR_ARG, "xgpu_affine_coefs: bad argument");
+  if (ctx->def_order != 0) return xgpu_fail(ctx, XGPU_ERR_UNSUPPORTED, "xgpu_affine_coefs: the mesh is deformed (elements are not affine)");
+  if (n == 0) return XGPU_OK;
+  TermsDev T; bool ms;
+  int rc = make_terms(ctx, terms_host, nterms, T, &ms);
+  if (rc) return rc;
+  if (!ms) return xgpu_fail(ctx, XGPU_ERR_UNSUPPORTED, "xgpu_affine_coefs: ID*ID and GRAD.GRAD terms only");
+  const unsigned grid = nblk(n, 256);
+  if (dim == 3) k_affine_coefs<3><<<grid, 256, 0, ctx->stream>>>(n, elems, el_vtx, vtx_xyz, T, coefs);
+  else if (dim == 2) k_affine_coefs<2><<<grid, 256, 0, ctx->stream>>>(n, elems, el_vtx, vtx_xyz, T, coefs);
+  else k_affine_coefs<1><<<grid, 256, 0, ctx->stream>>>(n, elems, el_vtx, vtx_xyz, T, coefs);
+  XGPU_LAUNCH_CHECK(ctx);
+  return XGPU_OK;
+}
+
+extern "C" int xgpu_reftensor(xgpu_ctx* ctx, int dim, int fe_order, int order, const double** tref_dev_out, int* ncoef_host)
+{
+  if (!ctx || dim < 1 || dim > 3 || fe_order < 1 || fe_order > 2 || !tref_dev_out)
+    return xgpu_fail(ctx, XGPU_ERR_ARG, "xgpu_reftensor: bad argument (orientation-independent bases: orders 1, 2)");
+  if (ncoef_host) *ncoef_host = 1 + dim * (dim + 1) / 2;
+  return get_reftensor(ctx, dim, fe_order, order, tref_dev_out);
+}
+
 extern "C" int xgpu_elmat_std(xgpu_ctx* ctx, int dim, int fe_order, int64_t n, const int32_t* elems,
                               const int32_t* el_vtx, const double* vtx_xyz, const double* phi, int order,
                               const xgpu_term* terms_host, int nterms, int accumulate, const int32_t* slots, double* mats)

@@ -12,6 +12,7 @@ from ._lib import Batch, LTerm, Term, default_ctx, ptr
 
 NEG, POS, IF = 0, 1, 2
 OP_ID, OP_GRAD, OP_DN = 0, 1, 2
+XGPU_ERR_UNSUPPORTED, XGPU_ERR_CAPACITY = -3, -14
 BIT_OR, BIT_AND, BIT_ANDNOT, BIT_NOT, BIT_COPY, BIT_CLEAR, BIT_SET = range(7)
 
 
@@ -461,11 +462,40 @@ class CsrPlan:
             pass
 
 
+class AffineCoefs:
+    """a PROCEDURAL batch: per-element coefficients (n x 8) of uncut affine elements; the matrices
+    sum_m coefs[e][m] * tref[m] are generated inside xgpu_csr_assemble_fused and never reach memory"""
+
+    def __init__(self, coefs, tref_ptr, ncoef):
+        self.coefs, self.tref_ptr, self.ncoef = coefs, tref_ptr, ncoef
+
+
+def affine_coefs(dim, fe_order, elems, el_vtx, vtx_xyz, order, terms, ctx=None):
+    """xgpu_affine_coefs + xgpu_reftensor: the procedural form of elmat_std's affine fast path"""
+    ctx = ctx or default_ctx()
+    n = el_vtx.shape[0] if elems is None else elems.numel()
+    coefs = torch.empty((n, 8), dtype=torch.float64, device=el_vtx.device)
+    ta = terms_array(terms)
+    if order < 0:  # symboliccutbfi.cpp:100-118
+        order = 2 * fe_order - min(0 if t[0] == OP_ID else 1 for t in terms) - min(0 if t[1] == OP_ID else 1 for t in terms)
+    tref = _lib.VP()
+    nc = C.c_int(0)
+    ctx.check(ctx.lib.xgpu_reftensor(ctx.h, dim, fe_order, order, C.byref(tref), C.byref(nc)))
+    ctx.check(ctx.lib.xgpu_affine_coefs(ctx.h, dim, n, ptr(_i32(elems)) if elems is not None else None, ptr(_i32(el_vtx)),
+                                        ptr(_f64(vtx_xyz)), ta, len(terms), ptr(coefs)))
+    return AffineCoefs(coefs, tref.value, nc.value)
+
+
 def _batches(batches):
     arr = (Batch * len(batches))()
     for i, (table, mats) in enumerate(batches):
         arr[i].table = ptr(_i32(table))
-        arr[i].mats = ptr(mats) if mats is not None else None
+        if isinstance(mats, AffineCoefs):
+            arr[i].mats = None
+            arr[i].coefs = ptr(mats.coefs)
+        else:
+            arr[i].mats = ptr(mats) if mats is not None else None
+            arr[i].coefs = None
         arr[i].nrows = table.shape[0]
         arr[i].width = table.shape[1]
     return arr
@@ -523,6 +553,32 @@ def csr_assemble(plan, batches):
     vals = torch.empty(plan.nnz, dtype=torch.float64, device=dev)
     arr = _batches(batches)
     plan.ctx.check(plan.ctx.lib.xgpu_csr_assemble(plan.ctx.h, plan.h, arr, len(batches), ptr(rowptr), ptr(col), ptr(vals)))
+    return rowptr, col, vals
+
+
+def csr_plan_rows(ndof, tables, ctx=None):
+    """transposed table + count pass (xgpu_csr_plan_rows): the plan of the one-row-pass assembly; raises XgpuError with
+    code XGPU_ERR_UNSUPPORTED for shapes the one-pass kernels do not take (duplicate dofs in a table row, rows wider than 64)"""
+    ctx = ctx or default_ctx()
+    arr = _batches([(t, None) for t in tables])
+    h = _lib.VP()
+    nnz = C.c_int64(0)
+    ctx.check(ctx.lib.xgpu_csr_plan_rows(ctx.h, ndof, arr, len(tables), C.byref(h), C.byref(nnz)))
+    return CsrPlan(ctx, h, nnz.value, ndof, len(tables))
+
+
+def csr_assemble_fused(plan, batches):
+    """ONE visit per row (xgpu_csr_assemble_fused): pattern + values, `AffineCoefs` in place of the matrices = procedural
+    batch.  plan: csr_plan_rows.  returns rowptr, col, vals"""
+    ctx = plan.ctx
+    dev = batches[0][0].device
+    arr = _batches(batches)
+    proc = [m for _, m in batches if isinstance(m, AffineCoefs)]
+    tref, nc = (proc[0].tref_ptr, proc[0].ncoef) if proc else (None, 0)
+    rowptr = torch.empty(plan.ndof + 1, dtype=torch.int64, device=dev)
+    col = torch.empty(plan.nnz, dtype=torch.int32, device=dev)
+    vals = torch.empty(plan.nnz, dtype=torch.float64, device=dev)
+    ctx.check(ctx.lib.xgpu_csr_assemble_fused(ctx.h, plan.h, arr, len(batches), tref, nc, ptr(rowptr), ptr(col), ptr(vals)))
     return rowptr, col, vals
 
 

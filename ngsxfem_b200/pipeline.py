@@ -78,17 +78,23 @@ class CutAssembly:
         # concurrently with the sparsity graph (shared-memory / issue bound); they only meet in the scatter
         self.side_stream, self.ctx2 = _side_context(self.dev)
 
-    def step(self, phi, timer=None, keep=False, hooks=None, concurrent=False):
+    def step(self, phi, timer=None, keep=False, hooks=None, concurrent=False, mode="twopass"):
         """one pass of the hot path; returns a dict with the CSR matrix and the unit counts.
-        hooks: optional {"classified"|"need_dofs"|"pattern"|"values": fn(partial results)} called at those
+        mode="twopass" (default): every element matrix is written to memory, then `xgpu_csr_plan` (pattern pass) +
+        `xgpu_csr_assemble` (gather).  mode="fused": the uncut affine elements are a PROCEDURAL batch (7 coefficients per
+        element, `xgpu_affine_coefs`), a lean count pass gives the row offsets (`xgpu_csr_plan_rows`) and every row is
+        finished in ONE visit (`xgpu_csr_assemble_fused`).  Both give the same bits; on config 2 the two-pass path is
+        the faster one today (9.8 vs 10.4 ms, profiles/r02_notes.md), so it stays the default.
+        hooks: optional {"classified"|"need_dofs"|"need_xyz"|"pattern"|"values": fn(partial results)} called at those
         points (the host-buffer path overlaps its H2D / D2H copies with the kernels through them).
-        concurrent=True runs the element-matrix branch on a side stream next to the graph construction
-        (measured: 12.6 -> 12.2 ms on config 2; off by default so that the per-phase CUDA-event times
-        that bench.py reports are those of the kernels alone)"""
+        concurrent=True runs the cut-element branch (cut quadrature + cut element matrices: FP64 / latency bound, low
+        occupancy) on a side stream next to Restrict + the transposed table (memory / atomics bound); they meet in the
+        row pass.  Off when per-phase CUDA-event times are wanted."""
         t = timer or PhaseTimer(False)
         hooks = hooks or {}
         ctx, dim, p, ne = self.ctx, self.dim, self.p, self.ne
         els, xyz = self.el_vtx, self.vtx_xyz
+        fused = mode == "fused"
         t.mark("start")
         # (a) CutInfo.Update
         bn, bp, bi, cr = ops.classify(dim, els, phi, ctx=ctx)
@@ -99,75 +105,109 @@ class CutAssembly:
         l_neg = ops.bitset_to_list(bn, ne, ctx=ctx)
         l_if = ops.bitset_to_list(bi, ne, ctx=ctx)
         t.mark("lists")
-        # Restrict(H1, hasneg): active dofs, compressed numbering, dof rows of the two batches
-        if "need_dofs" in hooks:
-            hooks["need_dofs"](None)
-        act = ops.dofs_of_elements(self.el_dofs, has, self.ndof_full, ctx=ctx)
-        dofmap, ndof = ops.bitset_rank(act, self.ndof_full, ctx=ctx)
-        t_neg = ops.gather_rows(self.el_dofs, l_neg, dofmap, ctx=ctx)
-        t_if = ops.gather_rows(self.el_dofs, l_if, dofmap, ctx=ctx)
-        t.mark("restrict")
-        tables = [t_neg, t_if]
-        # host-buffer path: the sparsity graph needs only the dof rows, so it is built BEFORE the element matrices and
-        # its pattern leaves for the host while they are computed and summed (separate compaction: +0.7 ms of kernels,
-        # but 0.58 GB of D2H start ~5 ms earlier on an otherwise idle link)
-        early_graph = "pattern" in hooks
-        plan = rowptr = col = None
-
-        def graph():
-            pl = ops.csr_plan(ndof, tables, ctx=ctx)
-            t.mark("csr_plan")
-            if t.enabled:
-                a_ms, p_ms = pl.phase_ms()
-                t.split_phase("csr_plan", {"csr_adjacency": a_ms, "csr_pattern_pass": p_ms})
-            return pl
-
-        if early_graph:
-            plan = graph()
-            rowptr, col = ops.csr_pattern(plan, self.dev)
-            t.mark("csr_pattern")
-            hooks["pattern"](dict(rowptr=rowptr, col=col))
-        if "need_xyz" in hooks:
-            hooks["need_xyz"](None)
         order = 2 * p  # symboliccutbfi.cpp:100-118 (ID*ID present: min diff order 0)
         main = torch.cuda.current_stream(self.dev)
         side, ctx2 = (self.side_stream, self.ctx2) if concurrent else (main, ctx)
-        m_neg = torch.empty((l_neg.numel(), self.nd, self.nd), dtype=torch.float64, device=self.dev)
         m_if = torch.empty((l_if.numel(), self.nd, self.nd), dtype=torch.float64, device=self.dev)
-        if concurrent:
-            side.wait_stream(main)
-        with torch.cuda.stream(side):
-            # (b) cut quadrature: the two count passes first (each synchronises the SIDE stream only, while it is
-            # still short), then everything else of this branch is enqueued without a host wait
-            off, n1 = ops.cutquad_count(dim, l_if, els, phi, ops.NEG, order, ctx=ctx2)
-            off2, n2 = ops.cutquad_count(dim, l_if, els, phi, ops.IF, order, ctx=ctx2)
-            q, w = ops.cutquad_fill(dim, l_if, els, xyz, phi, ops.NEG, order, off, n1, ctx=ctx2)
-            q2, w2 = ops.cutquad_fill(dim, l_if, els, xyz, phi, ops.IF, order, off2, n2, ctx=ctx2)
-            # (c) element matrices: uncut NEG elements with the shared standard rule; cut elements: the NEG volume
-            # terms and the IF interface term in one pass (one matrix per element, as in NGSolve's element loop)
-            ops.elmat_std(dim, p, l_neg, els, xyz, phi, order, TERMS_VOL, out=m_neg, ctx=ctx2)
-            ops.elmat_rule_pair(dim, p, l_if, els, xyz, phi, (off, q, w), TERMS_VOL, (off2, q2, w2), TERMS_IF, out=m_if, ctx=ctx2)
-            for t_ in (off, off2, q, w, q2, w2):
-                t_.record_stream(side)
-        t.mark("elmat")
-        # (e) graph on the main stream (concurrently with the element-matrix branch if requested)
-        if not early_graph:
-            plan = graph()
-        if concurrent:
-            main.wait_stream(side)
-        ctx2.raise_on_geometry_error()
-        t.mark("elmat_join")
-        if early_graph:
-            vals = ops.csr_scatter(plan, [(t_neg, m_neg), (t_if, m_if)], rowptr, col)
+
+        def cut_branch():
+            # (b) cut quadrature: the two count passes first (each synchronises its stream only), then everything else of
+            # this branch is enqueued without a host wait.  (c) cut elements: the NEG volume terms and the IF interface
+            # term in one pass (one matrix per element, as in NGSolve's element loop)
+            if "need_xyz" in hooks:
+                hooks["need_xyz"](None)
+            if concurrent:
+                side.wait_stream(main)
+            with torch.cuda.stream(side):
+                off, n1 = ops.cutquad_count(dim, l_if, els, phi, ops.NEG, order, ctx=ctx2)
+                off2, n2 = ops.cutquad_count(dim, l_if, els, phi, ops.IF, order, ctx=ctx2)
+                q, w = ops.cutquad_fill(dim, l_if, els, xyz, phi, ops.NEG, order, off, n1, ctx=ctx2)
+                q2, w2 = ops.cutquad_fill(dim, l_if, els, xyz, phi, ops.IF, order, off2, n2, ctx=ctx2)
+                t.mark("cutquad")
+                ops.elmat_rule_pair(dim, p, l_if, els, xyz, phi, (off, q, w), TERMS_VOL, (off2, q2, w2), TERMS_IF, out=m_if, ctx=ctx2)
+                for t_ in (off, off2, q, w, q2, w2, m_if):
+                    t_.record_stream(side)
+            t.mark("elmat_cut")
+            return n1, n2
+
+        def restrict():
+            # Restrict(H1, hasneg): active dofs, compressed numbering, dof rows of the two batches
+            if "need_dofs" in hooks:
+                hooks["need_dofs"](None)
+            act = ops.dofs_of_elements(self.el_dofs, has, self.ndof_full, ctx=ctx)
+            dofmap, ndof = ops.bitset_rank(act, self.ndof_full, ctx=ctx)
+            t_neg = ops.gather_rows(self.el_dofs, l_neg, dofmap, ctx=ctx)
+            t_if = ops.gather_rows(self.el_dofs, l_if, dofmap, ctx=ctx)
+            t.mark("restrict")
+            return ndof, t_neg, t_if
+
+        if fused and p <= 2:
+            if concurrent:
+                npts = cut_branch()
+                ndof, t_neg, t_if = restrict()
+            else:
+                ndof, t_neg, t_if = restrict()
+                npts = cut_branch()
+            # (e) transposed table, the 7 coefficients of every uncut element, then the row pass
+            plan = ops.csr_plan_rows(ndof, [t_neg, t_if], ctx=ctx)
+            t.mark("csr_plan_rows")
+            if t.enabled:
+                a_ms, p_ms = plan.phase_ms()
+                t.split_phase("csr_plan_rows", {"csr_adjacency": a_ms, "csr_count_pass": p_ms})
+            m_neg = ops.affine_coefs(dim, p, l_neg, els, xyz, order, TERMS_VOL, ctx=ctx)
+            t.mark("affine_coefs")
+            if concurrent:
+                main.wait_stream(side)
+            ctx2.raise_on_geometry_error()
+            t.mark("join")
+            rowptr, col, vals = ops.csr_assemble_fused(plan, [(t_neg, m_neg), (t_if, m_if)])
+            t.mark("csr_rows_fused")
+            if "pattern" in hooks:
+                hooks["pattern"](dict(rowptr=rowptr, col=col))
         else:
-            # pattern compaction fused into the scatter (xgpu_csr_assemble): rowptr, colidx and vals in one pass
-            rowptr, col, vals = ops.csr_assemble(plan, [(t_neg, m_neg), (t_if, m_if)])
-        t.mark("csr_scatter")
+            ndof, t_neg, t_if = restrict()
+            tables = [t_neg, t_if]
+            # host-buffer path: the sparsity graph needs only the dof rows, so it can be built BEFORE the element matrices and
+            # its pattern leaves for the host while they are computed and summed
+            early_graph = "pattern" in hooks
+            plan = rowptr = col = None
+
+            def graph():
+                pl = ops.csr_plan(ndof, tables, ctx=ctx)
+                t.mark("csr_plan")
+                if t.enabled:
+                    a_ms, p_ms = pl.phase_ms()
+                    t.split_phase("csr_plan", {"csr_adjacency": a_ms, "csr_pattern_pass": p_ms})
+                return pl
+
+            if early_graph:
+                plan = graph()
+                rowptr, col = ops.csr_pattern(plan, self.dev)
+                t.mark("csr_pattern")
+                hooks["pattern"](dict(rowptr=rowptr, col=col))
+            npts = cut_branch()
+            m_neg = torch.empty((l_neg.numel(), self.nd, self.nd), dtype=torch.float64, device=self.dev)
+            with torch.cuda.stream(side):
+                ops.elmat_std(dim, p, l_neg, els, xyz, phi, order, TERMS_VOL, out=m_neg, ctx=ctx2)
+                m_neg.record_stream(side)
+            t.mark("elmat")
+            if not early_graph:
+                plan = graph()
+            if concurrent:
+                main.wait_stream(side)
+            ctx2.raise_on_geometry_error()
+            t.mark("elmat_join")
+            if early_graph:
+                vals = ops.csr_scatter(plan, [(t_neg, m_neg), (t_if, m_if)], rowptr, col)
+            else:
+                # pattern compaction fused into the scatter (xgpu_csr_assemble): rowptr, colidx and vals in one pass
+                rowptr, col, vals = ops.csr_assemble(plan, [(t_neg, m_neg), (t_if, m_if)])
+            t.mark("csr_scatter")
         if "values" in hooks:
             hooks["values"](dict(vals=vals))
         out = dict(ndof=ndof, nnz=plan.nnz, n_neg=l_neg.numel(), n_if=l_if.numel(),
                    units=l_neg.numel() + l_if.numel(), rowptr=rowptr, col=col, vals=vals,
-                   bits=(bn, bp, bi), cut_ratio=cr, npts=(n1, n2))
+                   bits=(bn, bp, bi), cut_ratio=cr, npts=npts)
         if keep:
             out.update(l_neg=l_neg, l_if=l_if, t_neg=t_neg, t_if=t_if, m_neg=m_neg, m_if=m_if)
         return out

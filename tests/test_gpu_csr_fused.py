@@ -1,0 +1,130 @@
+"""xgpu_csr_assemble_fused (one pass over the rows: pattern + values + row offsets by decoupled look-back, procedural affine
+batches) against the two-pass path (xgpu_csr_plan + xgpu_csr_assemble) and a dense numpy reference, through the C ABI.
+Bit-exact pattern; values bit-identical to the two-pass path (same summation order)."""
+import numpy as np
+import pytest
+import torch
+
+import ngsxfem_b200 as xf
+from ngsxfem_b200 import ops
+from ngsxfem_b200._lib import XgpuError
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def random_tables(rng, ndof, shapes, holes=0.0):
+    """table rows with distinct dofs per row (like element dof rows), optional -1 entries"""
+    out = []
+    for nrows, w in shapes:
+        t = np.empty((nrows, w), dtype=np.int32)
+        for r in range(nrows):
+            # clustered like a mesh: dofs near a random centre
+            c = rng.integers(0, ndof)
+            pool = np.unique(np.clip(c + rng.integers(-3 * w, 3 * w + 1, size=6 * w), 0, ndof - 1))
+            while len(pool) < w:
+                pool = np.unique(np.concatenate([pool, rng.integers(0, ndof, size=w)]))
+            t[r] = rng.permutation(pool)[:w]
+        if holes > 0:
+            t[rng.random(t.shape) < holes] = -1
+        out.append(t)
+    return out
+
+
+def dense_reference(ndof, tables, mats):
+    A = np.zeros((ndof, ndof))
+    P = np.zeros((ndof, ndof), dtype=bool)
+    for t, m in zip(tables, mats):
+        for r in range(t.shape[0]):
+            idx = t[r]
+            ok = idx >= 0
+            P[np.ix_(idx[ok], idx[ok])] = True
+            if m is not None:
+                A[np.ix_(idx[ok], idx[ok])] += m[r][np.ix_(ok, ok)]
+    return A, P
+
+
+@pytest.mark.parametrize("ndof,shapes,holes", [
+    (300, [(400, 10)], 0.0),
+    (500, [(300, 4), (100, 4)], 0.0),
+    (200, [(150, 10), (60, 10), (20, 10)], 0.1),
+    (1000, [(700, 20)], 0.0),
+    (400, [(200, 35)], 0.05),      # two trips (rows wider than a warp)
+    (64, [(40, 3)], 0.0),
+    (50, [(30, 1)], 0.0),
+    (700, [(500, 12), (100, 6)], 0.0),  # mixed widths
+])
+def test_fused_rows_match_two_pass_and_dense(ndof, shapes, holes):
+    rng = np.random.default_rng(hash((ndof, len(shapes))) % 2 ** 31)
+    tabs = random_tables(rng, ndof, shapes, holes)
+    mats = [rng.standard_normal((t.shape[0], t.shape[1], t.shape[1])) for t in tabs]
+    if len(tabs) >= 3:
+        mats[2] = None  # sparsity-only batch
+    gt = [torch.from_numpy(t).to(DEV) for t in tabs]
+    gm = [None if m is None else torch.from_numpy(m).to(DEV) for m in mats]
+    batches = list(zip(gt, gm))
+    plan2 = ops.csr_plan(ndof, gt)
+    rp2, c2, v2 = ops.csr_assemble(plan2, batches)
+    plan = ops.csr_plan_rows(ndof, gt)
+    assert plan.nnz == plan2.nnz
+    rp, c, v = ops.csr_assemble_fused(plan, batches)
+    assert torch.equal(rp, rp2) and torch.equal(c, c2)
+    if max(w for _, w in shapes) <= 32:
+        assert torch.equal(v, v2)   # same summation order
+    else:  # rows wider than a warp: the two-pass kernel sums trip-major inside a batch of entries, the one-pass kernel in strict entry order
+        assert torch.allclose(v, v2, rtol=1e-13, atol=1e-13)
+    A, P = dense_reference(ndof, tabs, mats)
+    rpn, cn, vn = rp.cpu().numpy(), c.cpu().numpy(), v.cpu().numpy()
+    assert rpn[-1] == P.sum() == len(cn)
+    for d in range(ndof):
+        cols = cn[rpn[d]:rpn[d + 1]]
+        assert np.array_equal(cols, np.flatnonzero(P[d]))
+        assert np.allclose(vn[rpn[d]:rpn[d + 1]], A[d, cols], rtol=1e-13, atol=1e-13)
+    # the same call again: bit reproducible (the summation order is fixed)
+    rp3, c3, v3 = ops.csr_assemble_fused(plan, batches)
+    assert torch.equal(rp3, rp) and torch.equal(c3, c) and torch.equal(v3, v)
+
+
+def test_unsupported_shapes_are_declined_not_emulated():
+    # a dof twice in one table row (facet-patch rows): the one-pass kernels decline, the two-pass path takes it
+    t = torch.tensor([[0, 1, 2, 1], [2, 3, 4, 5]], dtype=torch.int32, device=DEV)
+    with pytest.raises(XgpuError) as ei:
+        ops.csr_plan_rows(6, [t])
+    assert ei.value.code == ops.XGPU_ERR_UNSUPPORTED
+    # a plan without row counts is rejected by the one-pass assembly
+    t2 = torch.tensor([[0, 1, 2, 3]], dtype=torch.int32, device=DEV)
+    with pytest.raises(XgpuError):
+        ops.csr_assemble_fused(ops.adjacency_plan(6, [t2]), [(t2, torch.ones(1, 4, 4, dtype=torch.float64, device=DEV))])
+
+
+def test_empty_rows_and_empty_matrix():
+    t = torch.tensor([[5, 7, 9]], dtype=torch.int32, device=DEV)
+    m = torch.arange(9, dtype=torch.float64, device=DEV).reshape(1, 3, 3)
+    plan = ops.csr_plan_rows(12, [t])
+    rp, c, v = ops.csr_assemble_fused(plan, [(t, m)])
+    assert rp.tolist() == [0] * 6 + [3, 3, 6, 6, 9, 9, 9]
+    assert c.tolist() == [5, 7, 9] * 3 and v.tolist() == list(range(9))
+    t0 = torch.empty((0, 3), dtype=torch.int32, device=DEV)
+    plan0 = ops.csr_plan_rows(4, [t0])
+    rp0, c0, v0 = ops.csr_assemble_fused(plan0, [(t0, torch.empty((0, 3, 3), dtype=torch.float64, device=DEV))])
+    assert rp0.tolist() == [0] * 5 and c0.numel() == 0
+
+
+@pytest.mark.parametrize("dim,p", [(3, 2), (3, 1), (2, 2), (2, 1), (1, 2)])
+def test_procedural_affine_batch_equals_matrices_in_memory(dim, p):
+    """a batch given by xgpu_affine_coefs (64 B per element) assembles to the same bits as the same elements'
+    matrices from xgpu_elmat_std's affine path"""
+    n = {1: 40, 2: 12, 3: 5}[dim]
+    mesh = {1: lambda: xf.MakeStructured1DMesh(nx=n, device=DEV),
+            2: lambda: xf.MakeStructured2DMesh(nx=n, ny=n, device=DEV),
+            3: lambda: xf.MakeStructured3DMesh(nx=n, device=DEV)}[dim]()
+    V = xf.H1(mesh, order=p)
+    terms = [(ops.OP_GRAD, ops.OP_GRAD, 0.7, 0), (ops.OP_ID, ops.OP_ID, 1.3, -1)]
+    elems = torch.arange(0, mesh.ne, 2, dtype=torch.int32, device=DEV)
+    table = ops.gather_rows(V.el_dofs, elems, None)
+    mats = ops.elmat_std(dim, p, elems, mesh.elements, mesh.points, None, 2 * p, terms)
+    plan = ops.csr_plan_rows(V.ndof, [table])
+    rp, c, v = ops.csr_assemble_fused(plan, [(table, mats)])
+    proc = ops.affine_coefs(dim, p, elems, mesh.elements, mesh.points, 2 * p, terms)
+    rp2, c2, v2 = ops.csr_assemble_fused(plan, [(table, proc)])
+    assert torch.equal(rp, rp2) and torch.equal(c, c2) and torch.equal(v, v2)
