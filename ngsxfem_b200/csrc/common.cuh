@@ -35,6 +35,8 @@ struct xgpu_ctx {
   const int32_t* def_el_dofs = nullptr;  // ne x nd(def_order)
   const double* def_vals = nullptr;      // ndof x dim
   int opt_dmma = 0;   // element matrices on FP64 tensor tiles: -1 never, 0 at order >= 3, 1 also at order 2
+  int opt_csr_small = 1;  // one-pass CSR: thread-per-row kernels (register sorting network) for rows with few adjacent table rows
+  int opt_csr_warp = 1;   // one-pass CSR: warp-per-row kernels (sorting network over the warp) for rows with <= 256 candidates
   int opt_csr_trips = 0;  // one-pass CSR: columns per lane (0 policy = 1 for rows up to 32 wide; 2: half-width lane groups)
   int opt_st_tp = 1;  // space-time element matrices: tensor-structured kernel where instantiated (0: always the generic one)
   int64_t epoch = 0;  // bumped whenever a plan takes over the shared pattern scratch (slot 8)

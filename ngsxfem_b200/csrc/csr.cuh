@@ -21,6 +21,8 @@ struct xgpu_plan {
   int maxcand = 0, maxnr = 0, wmax = 0, dups = 0;
   int64_t epoch = -1;             // ctx->epoch at which the pattern scratch (slot 8) was filled
   bool with_pattern = false;      // false: transposed table only (xgpu_adjacency_plan)
+  int small_na = 0;               // counted plans: rows with 1..small_na adjacent table rows went through the thread-per-row kernels
+  int warp_cand = 0;              // counted plans: the other rows with at most warp_cand candidates went through the warp-per-row kernels
   bool counted = false;           // xgpu_csr_plan_rows: rowptr / nnz / maxnr from the count pass (no pattern scratch)
   int32_t* rowcnt = nullptr;      // counted plans: distinct columns per row
   BatchDev bd;
@@ -41,3 +43,14 @@ struct xgpu_plan {
 #define XG_ADJ_LOC(e) ((int)((e) & 255))
 #define XG_ADJ_ROWKEY(e) ((e) >> 8)  // (batch, row)
 
+
+// csr_rows_small.cu: thread-per-row kernels for rows with at most xg_rows_small_na(width) adjacent table rows
+int xg_rows_small_na(int width, int64_t ndof);
+int xg_rows_small_supports(int width, int ncoef);
+int xg_rows_small_run(xgpu_ctx* ctx, xgpu_plan* P, const BatchDev& bd, const double* tref, int ncoef, bool count,
+                      int32_t* rowcnt, int* stats, int32_t* colidx, double* vals);
+
+// csr_rows_warp.cu: warp-per-row kernels (sorting network over the warp) for rows with at most 256 candidates
+int xg_rows_warp_ok(int width, int64_t ndof);
+int xg_rows_warp_run(xgpu_ctx* ctx, xgpu_plan* P, const BatchDev& bd, const double* tref, int ncoef, bool count, int small_na,
+                     unsigned int* ticket, int32_t* rowcnt, int* stats, int32_t* colidx, double* vals);

@@ -31,9 +31,12 @@ namespace {
 
 #define XF_WARPS 4
 #define XF_GOLD 2654435761u
+#define XF_CHUNK 16
 
 struct FusedPar {
   int ndof, NG, GS, HG, nn;
+  int skip_na;  // rows with 1..skip_na adjacent table rows (full pass: and at most 32 nonzeros) belong to csr_rows_small.cu
+  int skip_cand;  // the other rows with at most skip_cand candidates belong to csr_rows_warp.cu (-1: none)
   unsigned ntiles;
   const long long* adj_ptr;
   const long long* adj;
@@ -137,12 +140,18 @@ __global__ void __launch_bounds__(XF_WARPS * 32) k_rows_fused(const FusedPar P)
   const unsigned gmask = (GS >= 32) ? 0xffffffffu : ((1u << GS) - 1u);
   const unsigned FULL = 0xffffffffu;
 
+  // tiles (NG consecutive rows) are handed out in chunks of XF_CHUNK by an atomic ticket: one ticket per tile made the
+  // single counter the bottleneck (1.6 M same-address atomics ~ 1.4 ms, profiles/r02_notes.md)
+  unsigned tk = 0, tk_end = 0;
   for (;;) {
-    unsigned tk = 0;
-    if (lane == 0) tk = atomicAdd(P.ticket, 1u);
-    tk = __shfl_sync(FULL, tk, 0);
-    if (tk >= P.ntiles) break;
+    if (tk == tk_end) {
+      if (lane == 0) tk = atomicAdd(P.ticket, (unsigned)XF_CHUNK);
+      tk = __shfl_sync(FULL, tk, 0);
+      if (tk >= P.ntiles) break;
+      tk_end = min(tk + (unsigned)XF_CHUNK, P.ntiles);
+    }
     const long long d = (long long)tk * NG + g;
+    tk++;
     const bool have = live && d < P.ndof;
     long long a = 0, rowbase = 0;
     int na = 0, nr = 0;
@@ -151,10 +160,12 @@ __global__ void __launch_bounds__(XF_WARPS * 32) k_rows_fused(const FusedPar P)
       na = (int)(__ldg(P.adj_ptr + d + 1) - a);
       rowbase = __ldg(P.rowptr + d);
       nr = (int)(__ldg(P.rowptr + d + 1) - rowbase);
+      if ((na >= 1 && na <= P.skip_na && nr <= 32) || __ldg(P.cand + d) <= P.skip_cand) { na = 0; nr = 0; }  // a row of the other kernels
     }
+    if (!__any_sync(FULL, nr > 0)) continue;
     int H = 32, shift = 27;
     while (H < nr + (nr >> 1) + 1) { H <<= 1; shift--; }  // load factor <= 2/3 with the exact row length of the count pass
-    if (!have) H = 0;
+    if (!have || nr == 0) H = 0;
     const unsigned hmask = (unsigned)(H - 1);
     for (int k = ls << 2; k < H; k += GS << 2) sts_i4(keyA + (k << 2), XG_EMPTY);
     for (int k = ls << 1; k < H; k += GS << 1) sts_zero16(accA + (k << 3));
@@ -262,7 +273,7 @@ __global__ void __launch_bounds__(XF_WARPS * 32) k_rows_fused(const FusedPar P)
     __syncwarp();
 
     // ---- rank sort of the distinct columns, values follow their column to the final CSR position (nu == nr)
-    const bool wr = have && nu > 0;
+    const bool wr = have && nu > 0;  // skipped rows: na = 0 -> nu = 0
     const int numax = __reduce_max_sync(FULL, wr ? nu : 0);
     if (wr) {
       int32_t* __restrict__ col = P.colidx + rowbase;
@@ -294,12 +305,18 @@ __global__ void __launch_bounds__(XF_WARPS * 32) k_rows_count(const FusedPar P)
   const unsigned keyA = smem_u32(smk) + (((wib * NG + gi) * HG) << 2);
   const unsigned FULL = 0xffffffffu;
   int longest = 0;
+  // tiles (NG consecutive rows) are handed out in chunks of XF_CHUNK by an atomic ticket: one ticket per tile made the
+  // single counter the bottleneck (1.6 M same-address atomics ~ 1.4 ms, profiles/r02_notes.md)
+  unsigned tk = 0, tk_end = 0;
   for (;;) {
-    unsigned tk = 0;
-    if (lane == 0) tk = atomicAdd(P.ticket, 1u);
-    tk = __shfl_sync(FULL, tk, 0);
-    if (tk >= P.ntiles) break;
+    if (tk == tk_end) {
+      if (lane == 0) tk = atomicAdd(P.ticket, (unsigned)XF_CHUNK);
+      tk = __shfl_sync(FULL, tk, 0);
+      if (tk >= P.ntiles) break;
+      tk_end = min(tk + (unsigned)XF_CHUNK, P.ntiles);
+    }
     const long long d = (long long)tk * NG + g;
+    tk++;
     const bool have = live && d < P.ndof;
     long long a = 0;
     int na = 0, cand = 0;
@@ -308,9 +325,12 @@ __global__ void __launch_bounds__(XF_WARPS * 32) k_rows_count(const FusedPar P)
       na = (int)(__ldg(P.adj_ptr + d + 1) - a);
       cand = __ldg(P.cand + d);
     }
+    const bool mine = have && !(na >= 1 && na <= P.skip_na) && cand > P.skip_cand;  // else: a row of the other kernels
+    if (!mine) { na = 0; cand = 0; }
+    if (!__any_sync(FULL, mine)) continue;
     int H = 32, shift = 27;
     while (H <= cand) { H <<= 1; shift--; }
-    if (!have) H = 0;
+    if (!mine) H = 0;
     const unsigned hmask = (unsigned)(H - 1);
     for (int k = ls << 2; k < H; k += GS << 2) sts_i4(keyA + (k << 2), XG_EMPTY);
     __syncwarp();
@@ -333,7 +353,7 @@ __global__ void __launch_bounds__(XF_WARPS * 32) k_rows_count(const FusedPar P)
     }                                                                                      \
   }
     XF_ISSUE_C(e_nx);
-    int mine = 0;
+    int nins = 0;
     for (int t = 0; t < maxna; t++) {
       int c_cur[TRIPS];
 #pragma unroll
@@ -343,19 +363,19 @@ __global__ void __launch_bounds__(XF_WARPS * 32) k_rows_count(const FusedPar P)
       XF_ISSUE_C(e_nx);
 #pragma unroll
       for (int tr = 0; tr < TRIPS; tr++)
-        if (c_cur[tr] >= 0) probe(keyA, hmask, shift, c_cur[tr], mine);
+        if (c_cur[tr] >= 0) probe(keyA, hmask, shift, c_cur[tr], nins);
     }
 #undef XF_ISSUE_C
     // group totals: inclusive scan over the warp, difference at the group boundaries
-    int incl = mine;
+    int incl = nins;
 #pragma unroll
     for (int s = 1; s < 32; s <<= 1) {
       const int y = __shfl_up_sync(FULL, incl, s);
       if (lane >= s) incl += y;
     }
     const int hi = __shfl_sync(FULL, incl, min(31, gi * GS + GS - 1));
-    const int lo = __shfl_sync(FULL, incl - mine, gi * GS);
-    if (have && ls == 0) { P.rowcnt[d] = hi - lo; longest = max(longest, hi - lo); }
+    const int lo = __shfl_sync(FULL, incl - nins, gi * GS);
+    if (mine && ls == 0) { P.rowcnt[d] = hi - lo; longest = max(longest, hi - lo); }
     __syncwarp();  // the next sweep re-initialises the tables
   }
   longest = __reduce_max_sync(FULL, longest);
@@ -379,6 +399,11 @@ static int fused_shape(xgpu_ctx* ctx, xgpu_plan* P, FusedPar& F, int* trips)
   if (ntiles >= (int64_t)0x7fffffff) return xgpu_fail(ctx, XGPU_ERR_CAPACITY, "one-pass CSR: too many rows");
   F.ntiles = (unsigned)ntiles;
   F.adj_ptr = P->adj_ptr; F.adj = P->adj; F.cand = P->tmp32; F.bd = P->bd;
+  // thread-per-row kernels for the short rows (ctx option "csr_small", default on): all table rows of one width
+  bool same_w = true;
+  for (int i = 0; i < P->bd.nb; i++) same_w = same_w && P->bd.width[i] == P->wmax;
+  F.skip_na = (ctx->opt_csr_small && same_w) ? xg_rows_small_na(P->wmax, P->ndof) : 0;
+  F.skip_cand = (ctx->opt_csr_warp && same_w && xg_rows_warp_ok(P->wmax, P->ndof)) ? 256 : -1;
   return XGPU_OK;
 }
 
@@ -400,7 +425,7 @@ extern "C" int xgpu_csr_plan_rows(xgpu_ctx* ctx, int64_t ndof, const xgpu_batch*
   int HG = 32;
   while (HG <= P->maxcand) HG <<= 1;
   const size_t smem = sizeof(int) * (size_t)XF_WARPS * F.NG * HG;
-  if (!rc && smem > 200 * 1024) rc = xgpu_fail(ctx, XGPU_ERR_UNSUPPORTED, "one-pass CSR: a row has too many candidate columns");
+  if (!rc && P->maxcand > F.skip_cand && smem > 200 * 1024) rc = xgpu_fail(ctx, XGPU_ERR_UNSUPPORTED, "one-pass CSR: a row has too many candidate columns");
   if (rc) { xgpu_plan_destroy(P); *plan_out = nullptr; return rc; }
   if (ndof == 0) { P->nnz = 0; P->counted = true; if (nnz_host) *nnz_host = 0; return XGPU_OK; }
   F.HG = HG;
@@ -413,18 +438,30 @@ extern "C" int xgpu_csr_plan_rows(xgpu_ctx* ctx, int64_t ndof, const xgpu_batch*
   F.stats = (int*)sp + 2;
   XF_TRY(cudaMallocAsync(&P->rowcnt, sizeof(int32_t) * (size_t)(ndof + 2), st));
   F.rowcnt = P->rowcnt;
-  int per_sm = (int)std::min<size_t>(12, (220 * 1024) / (smem + 1024));
-  unsigned grid = nblk(F.ntiles, XF_WARPS);
-  if (grid > (unsigned)(XGPU_NSM * per_sm)) grid = XGPU_NSM * per_sm;
-  if (trips == 1) {
-    XF_TRY(cudaFuncSetAttribute(k_rows_count<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_rows_count<1><<<grid, XF_WARPS * 32, smem, st>>>(F);
-  } else {
-    XF_TRY(cudaFuncSetAttribute(k_rows_count<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_rows_count<2><<<grid, XF_WARPS * 32, smem, st>>>(F);
+  if (P->maxcand > F.skip_cand) {  // rows left for the lane-group hash kernel
+    int per_sm = (int)std::min<size_t>(12, (220 * 1024) / (smem + 1024));
+    unsigned grid = nblk(F.ntiles, XF_WARPS);
+    if (grid > (unsigned)(XGPU_NSM * per_sm)) grid = XGPU_NSM * per_sm;
+    if (trips == 1) {
+      XF_TRY(cudaFuncSetAttribute(k_rows_count<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      k_rows_count<1><<<grid, XF_WARPS * 32, smem, st>>>(F);
+    } else {
+      XF_TRY(cudaFuncSetAttribute(k_rows_count<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      k_rows_count<2><<<grid, XF_WARPS * 32, smem, st>>>(F);
+    }
+    ctx->launches++;
+    XF_TRY(cudaGetLastError());
   }
-  ctx->launches++;
-  XF_TRY(cudaGetLastError());
+  P->warp_cand = F.skip_cand;
+  if (F.skip_cand >= 0) {
+    rc = xg_rows_warp_run(ctx, P, P->bd, nullptr, 0, true, F.skip_na, (unsigned int*)sp + 1, P->rowcnt, F.stats, nullptr, nullptr);
+    if (rc) { xgpu_plan_destroy(P); *plan_out = nullptr; return rc; }
+  }
+  P->small_na = F.skip_na;
+  if (F.skip_na > 0) {
+    rc = xg_rows_small_run(ctx, P, P->bd, nullptr, 0, true, P->rowcnt, F.stats, nullptr, nullptr);
+    if (rc) { xgpu_plan_destroy(P); *plan_out = nullptr; return rc; }
+  }
   rc = xgpu_exclusive_scan_i32(ctx, P->rowcnt, ndof, (int64_t*)P->rowptr);
   if (rc) { xgpu_plan_destroy(P); *plan_out = nullptr; return rc; }
   XF_TRY(cudaEventRecord(P->ev[2], st));
@@ -467,6 +504,22 @@ extern "C" int xgpu_csr_assemble_fused(xgpu_ctx* ctx, xgpu_plan* P, const xgpu_b
   cudaStream_t st = ctx->stream;
   XGPU_CUDA(ctx, cudaMemcpyAsync(rowptr, P->rowptr, sizeof(long long) * (P->ndof + 1), cudaMemcpyDeviceToDevice, st));
   if (P->ndof == 0 || P->nnz == 0) return XGPU_OK;
+  const bool fast_ok = xg_rows_small_supports(P->wmax, nproc ? ncoef : 0) != 0;
+  F.skip_na = (P->small_na > 0 && fast_ok) ? P->small_na : 0;
+  F.skip_cand = (P->warp_cand >= 0 && fast_ok) ? P->warp_cand : -1;
+  void* sp;
+  rc = xgpu_scratch(ctx, 9, 64, &sp);
+  if (rc) return rc;
+  XGPU_CUDA(ctx, cudaMemsetAsync(sp, 0, 64, st));
+  if (F.skip_na > 0) {
+    rc = xg_rows_small_run(ctx, P, F.bd, tref, nproc ? ncoef : 0, false, nullptr, nullptr, colidx, vals);
+    if (rc) return rc;
+  }
+  if (F.skip_cand >= 0) {
+    rc = xg_rows_warp_run(ctx, P, F.bd, tref, nproc ? ncoef : 0, false, F.skip_na, (unsigned int*)sp + 1, nullptr, nullptr, colidx, vals);
+    if (rc) return rc;
+  }
+  if (P->maxcand <= F.skip_cand) return XGPU_OK;  // no row left for the lane-group hash kernel
   int HG = 32;
   while (HG < P->maxnr + (P->maxnr >> 1) + 1) HG <<= 1;
   F.HG = HG;
@@ -476,10 +529,6 @@ extern "C" int xgpu_csr_assemble_fused(xgpu_ctx* ctx, xgpu_plan* P, const xgpu_b
   const size_t ntref = ((size_t)NC * F.nn + 1) & ~(size_t)1;
   const size_t smem = sizeof(double) * (ntref + (size_t)XF_WARPS * F.NG * HG) + sizeof(int) * (size_t)XF_WARPS * F.NG * (HG + 4);
   if (smem > 200 * 1024) return xgpu_fail(ctx, XGPU_ERR_UNSUPPORTED, "xgpu_csr_assemble_fused: a row is too long for the one-pass kernel");
-  void* sp;
-  rc = xgpu_scratch(ctx, 9, 64, &sp);
-  if (rc) return rc;
-  XGPU_CUDA(ctx, cudaMemsetAsync(sp, 0, 64, st));
   F.ticket = (unsigned int*)sp;
   F.stats = nullptr;
   F.rowcnt = nullptr;

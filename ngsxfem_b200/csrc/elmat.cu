@@ -206,7 +206,7 @@ __global__ void __launch_bounds__(256) k_affine_coefs(int64_t n, const int32_t* 
 extern "C" int xgpu_affine_coefs(xgpu_ctx* ctx, int dim, int64_t n, const int32_t* elems, const int32_t* el_vtx,
                                  const double* vtx_xyz, const xgpu_term* terms_host, int nterms, double* coefs)
 {
-  if (!ctx || dim < 1 || dim > 3 || n < 0 || !coefs) return xgpu_fail(ctx, XGPU_ERR_ARG, "xgpu_affine_coefs: bad argument");
+  if (!ctx || dim < 1 || dim > 3 || n < 0 || (n > 0 && !coefs)) return xgpu_fail(ctx, XGPU_ERR_ARG, "xgpu_affine_coefs: bad argument");
   if (ctx->def_order != 0) return xgpu_fail(ctx, XGPU_ERR_UNSUPPORTED, "xgpu_affine_coefs: the mesh is deformed (elements are not affine)");
   if (n == 0) return XGPU_OK;
   TermsDev T; bool ms;

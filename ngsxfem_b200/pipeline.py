@@ -78,13 +78,13 @@ class CutAssembly:
         # concurrently with the sparsity graph (shared-memory / issue bound); they only meet in the scatter
         self.side_stream, self.ctx2 = _side_context(self.dev)
 
-    def step(self, phi, timer=None, keep=False, hooks=None, concurrent=False, mode="twopass"):
+    def step(self, phi, timer=None, keep=False, hooks=None, concurrent=False, mode="fused"):
         """one pass of the hot path; returns a dict with the CSR matrix and the unit counts.
-        mode="twopass" (default): every element matrix is written to memory, then `xgpu_csr_plan` (pattern pass) +
-        `xgpu_csr_assemble` (gather).  mode="fused": the uncut affine elements are a PROCEDURAL batch (7 coefficients per
-        element, `xgpu_affine_coefs`), a lean count pass gives the row offsets (`xgpu_csr_plan_rows`) and every row is
-        finished in ONE visit (`xgpu_csr_assemble_fused`).  Both give the same bits; on config 2 the two-pass path is
-        the faster one today (9.8 vs 10.4 ms, profiles/r02_notes.md), so it stays the default.
+        mode="fused" (default): the uncut affine elements are a PROCEDURAL batch (7 coefficients per element,
+        `xgpu_affine_coefs`, no 800 B matrices in HBM), a count pass gives the row offsets (`xgpu_csr_plan_rows`) and every
+        row is finished in ONE visit (`xgpu_csr_assemble_fused`: sorting networks in registers / over the warp, no hash
+        tables).  mode="twopass": the round-1 path — every element matrix written to memory, `xgpu_csr_plan` (pattern
+        pass) + `xgpu_csr_assemble` (gather); kept as the cross-check.  Both give the same bits.
         hooks: optional {"classified"|"need_dofs"|"need_xyz"|"pattern"|"values": fn(partial results)} called at those
         points (the host-buffer path overlaps its H2D / D2H copies with the kernels through them).
         concurrent=True runs the cut-element branch (cut quadrature + cut element matrices: FP64 / latency bound, low
