@@ -310,6 +310,18 @@ int xgpu_csr_assemble(xgpu_ctx* ctx, xgpu_plan* plan, const xgpu_batch* batches_
  * equal the two-pass path bit for bit (rows up to 32 wide; wider rows: same pattern, strict sequential summation order). */
 int xgpu_csr_plan_rows(xgpu_ctx* ctx, int64_t ndof, const xgpu_batch* batches_host, int nbatches,
                        xgpu_plan** plan_out, int64_t* nnz_host);
+/* the count pass alone, on an existing transposed table (xgpu_adjacency_plan, xgpu_restrict_plan) */
+int xgpu_csr_count_rows(xgpu_ctx* ctx, xgpu_plan* plan, int64_t* nnz_host);
+/* Restrict + dof rows + transposed table in one sequence (RestrictedFESpace utils/restrictedfespace.cpp:23-73 followed by
+ * the table of RestrictedBilinearForm::GetGraph, utils/restrictedblf.cpp:142-163): the active dofs are the dofs of the
+ * listed elements (nlists element lists, lists_host[i] = DEVICE pointer to counts_host[i] element numbers, NULL = 0..count-1);
+ * dofmap[d] (ndof_full entries) = compressed number of dof d or -1, *ndof_host = number of active dofs,
+ * tables_host[i] (DEVICE pointers, counts_host[i] x nd int32) = the compressed dof rows of list i = batch i of the plan.
+ * Equivalent to xgpu_dofs_of_elements + xgpu_bitset_rank + xgpu_gather_rows + xgpu_adjacency_plan with one atomic pass
+ * and one table pass less. */
+int xgpu_restrict_plan(xgpu_ctx* ctx, int nd, const int32_t* el_dofs, int nlists, const int32_t* const* lists_host,
+                       const int64_t* counts_host, int64_t ndof_full, int32_t* dofmap, int64_t* ndof_host,
+                       int32_t* const* tables_host, xgpu_plan** plan_out);
 int xgpu_csr_assemble_fused(xgpu_ctx* ctx, xgpu_plan* plan, const xgpu_batch* batches_host, int nbatches,
                             const double* tref, int ncoef, int64_t* rowptr, int32_t* colidx, double* vals);
 void xgpu_plan_destroy(xgpu_plan* plan);

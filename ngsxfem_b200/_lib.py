@@ -107,6 +107,9 @@ _SIGS = {
     "xgpu_vec_scatter": (C.c_int, [VP, VP, C.POINTER(Batch), C.c_int, VP]),
     "xgpu_csr_assemble": (C.c_int, [VP, VP, C.POINTER(Batch), C.c_int, VP, VP, VP]),
     "xgpu_csr_plan_rows": (C.c_int, [VP, C.c_int64, C.POINTER(Batch), C.c_int, C.POINTER(VP), c_i64p]),
+    "xgpu_csr_count_rows": (C.c_int, [VP, VP, c_i64p]),
+    "xgpu_restrict_plan": (C.c_int, [VP, C.c_int, VP, C.c_int, C.POINTER(VP), c_i64p, C.c_int64, VP, c_i64p, C.POINTER(VP),
+                                    C.POINTER(VP)]),
     "xgpu_csr_assemble_fused": (C.c_int, [VP, VP, C.POINTER(Batch), C.c_int, VP, C.c_int, VP, VP, VP]),
     "xgpu_affine_coefs": (C.c_int, [VP, C.c_int, C.c_int64, VP, VP, VP, C.POINTER(Term), C.c_int, VP]),
     "xgpu_reftensor": (C.c_int, [VP, C.c_int, C.c_int, C.c_int, C.POINTER(VP), c_intp]),

@@ -31,8 +31,12 @@ template <int D>
 __global__ void __launch_bounds__(256) k_classify(int64_t ne, const int32_t* __restrict__ el_vtx,
                                                   const double* __restrict__ phi,
                                                   uint32_t* __restrict__ bits_neg, uint32_t* __restrict__ bits_pos,
-                                                  uint32_t* __restrict__ bits_if, double* __restrict__ cut_ratio)
+                                                  uint32_t* __restrict__ bits_if, double* __restrict__ cut_ratio,
+                                                  int32_t* __restrict__ cutlist, unsigned int* __restrict__ cutcount)
 {
+  __shared__ unsigned int s_cnt, s_base;
+  if (threadIdx.x == 0) s_cnt = 0u;
+  __syncthreads();
   const int64_t el = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const bool valid = el < ne;
   bool haspos = false, hasneg = false;
@@ -59,22 +63,31 @@ __global__ void __launch_bounds__(256) k_classify(int64_t ne, const int32_t* __r
   }
   // uncut: part volumes are (ref vol, 0) resp. (0, ref vol) -> ratio 1 resp. 0 (cutinfo.cpp:104)
   if (valid && cut_ratio && !is_if) cut_ratio[el] = is_neg ? 1.0 : 0.0;
+  // the sign-cut elements (~2 %) are appended to a list (one global atomic per block; the order does not matter): the
+  // geometry of k_cut_ratio then runs with full warps instead of one or two lanes per warp of the element sweep
+  unsigned int mypos = 0u;
+  if (is_if) mypos = atomicAdd(&s_cnt, 1u);
+  __syncthreads();
+  if (threadIdx.x == 0 && s_cnt > 0u) s_base = atomicAdd(cutcount, s_cnt);
+  __syncthreads();
+  if (is_if) cutlist[s_base + mypos] = (int32_t)el;
 }
 
 // one thread per element, only the sign-cut ones (bit set in bits_if) do work: in a warp that holds
 // a cut element the geometry runs once with the cut lanes active
 template <int D>
-__global__ void __launch_bounds__(256) k_cut_ratio(int64_t ne, const int32_t* __restrict__ el_vtx,
+__global__ void __launch_bounds__(256) k_cut_ratio(const int32_t* __restrict__ cutlist, const unsigned int* __restrict__ cutcount,
+                                                   const int32_t* __restrict__ el_vtx,
                                                    const double* __restrict__ phi, const double* __restrict__ w0, int nw0,
                                                    uint32_t* __restrict__ bits_neg, uint32_t* __restrict__ bits_pos,
                                                    uint32_t* __restrict__ bits_if, double* __restrict__ cut_ratio,
                                                    int* status, unsigned long long* status_elem)
 {
-  const int64_t el = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (el >= ne) return;
+  const unsigned int ncut = *cutcount;
+  for (unsigned int i = blockIdx.x * blockDim.x + threadIdx.x; i < ncut; i += gridDim.x * blockDim.x) {
+  const int64_t el = cutlist[i];
   const int64_t w = el >> 5;
   const uint32_t bit = 1u << (el & 31);
-  if (!(bits_if[w] & bit)) return;  // my own bit: only this thread ever changes it
   int v[D + 1];
   double l[D + 1];
   load_vtx<D>(el_vtx, el, v);
@@ -100,13 +113,14 @@ __global__ void __launch_bounds__(256) k_cut_ratio(int64_t ne, const int32_t* __
     xgpu_record_error(status, status_elem, err, el);
     if (cut_ratio) cut_ratio[el] = nan("");
     atomicAnd(bits_if + w, ~bit);
-    return;
+    continue;
   }
   if (cut_ratio) cut_ratio[el] = part[XGPU_NEG] / (part[XGPU_NEG] + part[XGPU_POS]);
   // volume based decision of cutinfo.cpp:104-124 (differs from the sign test only on underflow)
   if (!(part[XGPU_NEG] > 0.0 && part[XGPU_POS] > 0.0)) {
     atomicAnd(bits_if + w, ~bit);
     if (part[XGPU_NEG] > 0.0) atomicOr(bits_neg + w, bit); else atomicOr(bits_pos + w, bit);
+  }
   }
 }
 
@@ -285,11 +299,18 @@ extern "C" int xgpu_classify(xgpu_ctx* ctx, int dim, int64_t ne, const int32_t* 
   const xgpu_rule_host* r0 = xgpu_rule_lookup(ctx, dim, 0);
   if (!r0) return xgpu_fail(ctx, XGPU_ERR_ARG, "xgpu_classify: no order-0 rule");
   cudaStream_t st = ctx->stream;
+  if (ne >= (int64_t)0x7fffffff) return xgpu_fail(ctx, XGPU_ERR_CAPACITY, "xgpu_classify: 2^31 or more elements");
+  void* sp;
+  int rc = xgpu_scratch(ctx, 11, sizeof(int32_t) * (size_t)(ne + 4), &sp);
+  if (rc) return rc;
+  unsigned int* cutcount = (unsigned int*)sp;
+  int32_t* cutlist = (int32_t*)sp + 4;
+  XGPU_CUDA(ctx, cudaMemsetAsync(cutcount, 0, sizeof(unsigned int), st));
 #define XG_CLS(DD)                                                                                         \
-  k_classify<DD><<<nblk(ne, 256), 256, 0, st>>>(ne, el_vtx, phi, bits_neg, bits_pos, bits_if, cut_ratio);  \
+  k_classify<DD><<<nblk(ne, 256), 256, 0, st>>>(ne, el_vtx, phi, bits_neg, bits_pos, bits_if, cut_ratio, cutlist, cutcount);  \
   XGPU_LAUNCH_CHECK(ctx);                                                                                  \
-  k_cut_ratio<DD><<<nblk(ne, 256), 256, 0, st>>>(ne, el_vtx, phi, r0->d_wts, r0->n, bits_neg, bits_pos, \
-                                                     bits_if, cut_ratio, ctx->d_status, ctx->d_status_elem); \
+  k_cut_ratio<DD><<<XGPU_NSM * 4, 256, 0, st>>>(cutlist, cutcount, el_vtx, phi, r0->d_wts, r0->n, bits_neg, bits_pos, \
+                                                bits_if, cut_ratio, ctx->d_status, ctx->d_status_elem); \
   XGPU_LAUNCH_CHECK(ctx);
   if (dim == 3) { XG_CLS(3) } else if (dim == 2) { XG_CLS(2) } else { XG_CLS(1) }
 #undef XG_CLS

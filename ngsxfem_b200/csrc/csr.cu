@@ -716,6 +716,35 @@ extern "C" int xgpu_adjacency_plan(xgpu_ctx* ctx, int64_t ndof, const xgpu_batch
   return build_plan(ctx, ndof, batches_host, nbatches, plan_out, nullptr, false);
 }
 
+// second half of the transposed table: sort every segment, candidate counts (tmp32), statistics (max candidates,
+// duplicate dofs inside a table row), optionally the candidate offsets of the two-pass pattern scratch.  Synchronises.
+int xg_plan_finish(xgpu_ctx* ctx, xgpu_plan* P, bool want_candoff)
+{
+  cudaStream_t st = ctx->stream;
+  const int64_t ndof = P->ndof;
+  void* sp;
+  int rc = xgpu_scratch(ctx, 6, 64, &sp);
+  if (rc) return rc;
+  int* stats = (int*)sp;  // [0] max candidates of a row, [1] duplicate dofs inside a table row, [2] longest row
+  XGPU_CUDA(ctx, cudaMemsetAsync(stats, 0, 4 * sizeof(int), st));
+  if (ndof > 0) {
+    k_adj_sort<<<nblk(ndof, 128), 128, 0, st>>>(ndof, P->adj_ptr, P->adj, P->bd, P->tmp32, stats);
+    XGPU_LAUNCH_CHECK(ctx);
+  }
+  if (want_candoff) {
+    rc = xgpu_exclusive_scan_i32(ctx, P->tmp32, ndof, (int64_t*)P->candoff);
+    if (rc) return rc;
+  }
+  XGPU_CUDA(ctx, cudaEventRecord(P->ev[1], st));
+  XGPU_CUDA(ctx, xgpu_d2h_small(ctx->h_pinned, stats, 2 * sizeof(int), st));
+  if (want_candoff) XGPU_CUDA(ctx, xgpu_d2h_small(ctx->h_pinned + 1, P->candoff + ndof, sizeof(long long), st));
+  XGPU_CUDA(ctx, cudaStreamSynchronize(st));
+  P->maxcand = ((int*)ctx->h_pinned)[0];
+  P->dups = ((int*)ctx->h_pinned)[1];
+  P->ncand = want_candoff ? ctx->h_pinned[1] : -1;
+  return XGPU_OK;
+}
+
 static int build_plan(xgpu_ctx* ctx, int64_t ndof, const xgpu_batch* batches_host, int nbatches,
                       xgpu_plan** plan_out, int64_t* nnz_host, bool with_pattern)
 {
@@ -757,22 +786,10 @@ static int build_plan(xgpu_ctx* ctx, int64_t ndof, const xgpu_batch* batches_hos
                                                  P->adj_ptr, P->tmp32, P->adj);
     ctx->launches++;
   }
+  XG_TRYRC(xg_plan_finish(ctx, P, true));
   void* sp;
   XG_TRYRC(xgpu_scratch(ctx, 6, 64, &sp));
-  int* stats = (int*)sp;  // [0] max candidates of a row, [1] duplicate dofs inside a table row, [2] longest row
-  XG_TRY(cudaMemsetAsync(stats, 0, 4 * sizeof(int), st));
-  if (ndof > 0) {
-    k_adj_sort<<<nblk(ndof, 128), 128, 0, st>>>(ndof, P->adj_ptr, P->adj, P->bd, P->tmp32, stats);
-    ctx->launches++;
-  }
-  XG_TRYRC(xgpu_exclusive_scan_i32(ctx, P->tmp32, ndof, (int64_t*)P->candoff));
-  XG_TRY(cudaEventRecord(P->ev[1], st));
-  XG_TRY(xgpu_d2h_small(ctx->h_pinned, stats, 2 * sizeof(int), st));
-  XG_TRY(xgpu_d2h_small(ctx->h_pinned + 1, P->candoff + ndof, sizeof(long long), st));
-  XG_TRY(cudaStreamSynchronize(st));
-  P->maxcand = ((int*)ctx->h_pinned)[0];
-  P->dups = ((int*)ctx->h_pinned)[1];
-  P->ncand = ctx->h_pinned[1];
+  int* stats = (int*)sp;
   P->with_pattern = with_pattern;
   if (!with_pattern) {  // transposed table only (vector assembly)
     XG_TRY(cudaEventRecord(P->ev[2], st));

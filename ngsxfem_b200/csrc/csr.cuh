@@ -54,3 +54,6 @@ int xg_rows_small_run(xgpu_ctx* ctx, xgpu_plan* P, const BatchDev& bd, const dou
 int xg_rows_warp_ok(int width, int64_t ndof);
 int xg_rows_warp_run(xgpu_ctx* ctx, xgpu_plan* P, const BatchDev& bd, const double* tref, int ncoef, bool count, int small_na,
                      unsigned int* ticket, int32_t* rowcnt, int* stats, int32_t* colidx, double* vals);
+
+// csr.cu: sort the segments of a filled transposed table + statistics (synchronises)
+int xg_plan_finish(xgpu_ctx* ctx, xgpu_plan* P, bool want_candoff);

@@ -407,17 +407,32 @@ static int fused_shape(xgpu_ctx* ctx, xgpu_plan* P, FusedPar& F, int* trips)
   return XGPU_OK;
 }
 
-// xgpu_csr_plan_rows: transposed table + count pass + scan.  The plan then holds rowptr / nnz / the longest row; its
-// pattern scratch is not filled (xgpu_csr_pattern / xgpu_csr_assemble run their own pattern pass on demand).
-int xgpu_build_adjacency(xgpu_ctx* ctx, int64_t ndof, const xgpu_batch* batches_host, int nbatches, xgpu_plan** plan_out);
+// xgpu_csr_count_rows: count pass + scan on a transposed table.  The plan then holds rowptr / nnz / the longest row; its
+// pattern scratch is not filled (xgpu_csr_pattern / xgpu_csr_assemble need a plan of xgpu_csr_plan).
+static int count_rows(xgpu_ctx* ctx, xgpu_plan* P, int64_t* nnz_host);
+
+extern "C" int xgpu_csr_count_rows(xgpu_ctx* ctx, xgpu_plan* P, int64_t* nnz_host)
+{
+  if (!ctx || !P) return xgpu_fail(ctx, XGPU_ERR_ARG, "xgpu_csr_count_rows: bad argument");
+  if (P->counted) { if (nnz_host) *nnz_host = P->nnz; return XGPU_OK; }
+  return count_rows(ctx, P, nnz_host);
+}
 
 extern "C" int xgpu_csr_plan_rows(xgpu_ctx* ctx, int64_t ndof, const xgpu_batch* batches_host, int nbatches,
                                   xgpu_plan** plan_out, int64_t* nnz_host)
 {
   if (!plan_out) return xgpu_fail(ctx, XGPU_ERR_ARG, "xgpu_csr_plan_rows: bad argument");
-  int rc = xgpu_build_adjacency(ctx, ndof, batches_host, nbatches, plan_out);
+  int rc = xgpu_adjacency_plan(ctx, ndof, batches_host, nbatches, plan_out);
   if (rc) return rc;
-  xgpu_plan* P = *plan_out;
+  rc = count_rows(ctx, *plan_out, nnz_host);
+  if (rc) { xgpu_plan_destroy(*plan_out); *plan_out = nullptr; }
+  return rc;
+}
+
+static int count_rows(xgpu_ctx* ctx, xgpu_plan* P, int64_t* nnz_host)
+{
+  const int64_t ndof = P->ndof;
+  int rc;
   cudaStream_t st = ctx->stream;
   FusedPar F;
   int trips;
@@ -426,13 +441,13 @@ extern "C" int xgpu_csr_plan_rows(xgpu_ctx* ctx, int64_t ndof, const xgpu_batch*
   while (HG <= P->maxcand) HG <<= 1;
   const size_t smem = sizeof(int) * (size_t)XF_WARPS * F.NG * HG;
   if (!rc && P->maxcand > F.skip_cand && smem > 200 * 1024) rc = xgpu_fail(ctx, XGPU_ERR_UNSUPPORTED, "one-pass CSR: a row has too many candidate columns");
-  if (rc) { xgpu_plan_destroy(P); *plan_out = nullptr; return rc; }
+  if (rc) return rc;
   if (ndof == 0) { P->nnz = 0; P->counted = true; if (nnz_host) *nnz_host = 0; return XGPU_OK; }
   F.HG = HG;
   void* sp;
   rc = xgpu_scratch(ctx, 9, 64, &sp);
-  if (rc) { xgpu_plan_destroy(P); *plan_out = nullptr; return rc; }
-#define XF_TRY(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { xgpu_plan_destroy(P); *plan_out = nullptr; return xgpu_fail(ctx, XGPU_ERR_CUDA, cudaGetErrorString(e_)); } } while (0)
+  if (rc) return rc;
+#define XF_TRY(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return xgpu_fail(ctx, XGPU_ERR_CUDA, cudaGetErrorString(e_)); } while (0)
   XF_TRY(cudaMemsetAsync(sp, 0, 64, st));
   F.ticket = (unsigned int*)sp;
   F.stats = (int*)sp + 2;
@@ -455,15 +470,15 @@ extern "C" int xgpu_csr_plan_rows(xgpu_ctx* ctx, int64_t ndof, const xgpu_batch*
   P->warp_cand = F.skip_cand;
   if (F.skip_cand >= 0) {
     rc = xg_rows_warp_run(ctx, P, P->bd, nullptr, 0, true, F.skip_na, (unsigned int*)sp + 1, P->rowcnt, F.stats, nullptr, nullptr);
-    if (rc) { xgpu_plan_destroy(P); *plan_out = nullptr; return rc; }
+    if (rc) return rc;
   }
   P->small_na = F.skip_na;
   if (F.skip_na > 0) {
     rc = xg_rows_small_run(ctx, P, P->bd, nullptr, 0, true, P->rowcnt, F.stats, nullptr, nullptr);
-    if (rc) { xgpu_plan_destroy(P); *plan_out = nullptr; return rc; }
+    if (rc) return rc;
   }
   rc = xgpu_exclusive_scan_i32(ctx, P->rowcnt, ndof, (int64_t*)P->rowptr);
-  if (rc) { xgpu_plan_destroy(P); *plan_out = nullptr; return rc; }
+  if (rc) return rc;
   XF_TRY(cudaEventRecord(P->ev[2], st));
   XF_TRY(xgpu_d2h_small(ctx->h_pinned, P->rowptr + ndof, sizeof(long long), st));
   XF_TRY(xgpu_d2h_small(ctx->h_pinned + 1, F.stats, sizeof(int), st));

@@ -567,6 +567,33 @@ def csr_plan_rows(ndof, tables, ctx=None):
     return CsrPlan(ctx, h, nnz.value, ndof, len(tables))
 
 
+def csr_count_rows(plan):
+    """count pass on an existing transposed table (xgpu_csr_count_rows); sets plan.nnz"""
+    nnz = C.c_int64(0)
+    plan.ctx.check(plan.ctx.lib.xgpu_csr_count_rows(plan.ctx.h, plan.h, C.byref(nnz)))
+    plan.nnz = nnz.value
+    return plan
+
+
+def restrict_plan(el_dofs, lists, ndof_full, ctx=None):
+    """Restrict + compressed dof rows + transposed table (xgpu_restrict_plan).  lists: element lists (int32 tensors).
+    returns (dofmap, ndof, tables, plan); plan is an adjacency plan of the tables (csr_count_rows / vec_scatter)"""
+    ctx = ctx or default_ctx()
+    dev = el_dofs.device
+    nd = el_dofs.shape[1]
+    n = len(lists)
+    tables = [torch.empty((l.numel(), nd), dtype=torch.int32, device=dev) for l in lists]
+    dofmap = torch.empty(max(1, ndof_full), dtype=torch.int32, device=dev)
+    lp = (_lib.VP * n)(*[ptr(_i32(l)) if l.numel() else None for l in lists])
+    tp = (_lib.VP * n)(*[ptr(t) if t.numel() else None for t in tables])
+    cnts = (C.c_int64 * n)(*[l.numel() for l in lists])
+    ndof = C.c_int64(0)
+    h = _lib.VP()
+    ctx.check(ctx.lib.xgpu_restrict_plan(ctx.h, nd, ptr(_i32(el_dofs)), n, lp, cnts, ndof_full, ptr(dofmap), C.byref(ndof), tp,
+                                         C.byref(h)))
+    return dofmap[:ndof_full], ndof.value, tables, CsrPlan(ctx, h, 0, ndof.value, n)
+
+
 def csr_assemble_fused(plan, batches):
     """ONE visit per row (xgpu_csr_assemble_fused): pattern + values, `AffineCoefs` in place of the matrices = procedural
     batch.  plan: csr_plan_rows.  returns rowptr, col, vals"""

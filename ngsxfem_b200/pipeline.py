@@ -142,18 +142,23 @@ class CutAssembly:
             return ndof, t_neg, t_if
 
         if fused and p <= 2:
+            def restrict_and_table():
+                # Restrict(H1, hasneg) + the dof rows of the two batches + their transposed table: one sequence
+                if "need_dofs" in hooks:
+                    hooks["need_dofs"](None)
+                _, nd_, tabs, pl = ops.restrict_plan(self.el_dofs, [l_neg, l_if], self.ndof_full, ctx=ctx)
+                t.mark("restrict_plan")
+                return nd_, tabs[0], tabs[1], pl
+
             if concurrent:
                 npts = cut_branch()
-                ndof, t_neg, t_if = restrict()
+                ndof, t_neg, t_if, plan = restrict_and_table()
             else:
-                ndof, t_neg, t_if = restrict()
+                ndof, t_neg, t_if, plan = restrict_and_table()
                 npts = cut_branch()
-            # (e) transposed table, the 7 coefficients of every uncut element, then the row pass
-            plan = ops.csr_plan_rows(ndof, [t_neg, t_if], ctx=ctx)
-            t.mark("csr_plan_rows")
-            if t.enabled:
-                a_ms, p_ms = plan.phase_ms()
-                t.split_phase("csr_plan_rows", {"csr_adjacency": a_ms, "csr_count_pass": p_ms})
+            # (e) row lengths, the 7 coefficients of every uncut element, then the row pass
+            ops.csr_count_rows(plan)
+            t.mark("csr_count_pass")
             m_neg = ops.affine_coefs(dim, p, l_neg, els, xyz, order, TERMS_VOL, ctx=ctx)
             t.mark("affine_coefs")
             if concurrent:

@@ -128,3 +128,38 @@ def test_procedural_affine_batch_equals_matrices_in_memory(dim, p):
     proc = ops.affine_coefs(dim, p, elems, mesh.elements, mesh.points, 2 * p, terms)
     rp2, c2, v2 = ops.csr_assemble_fused(plan, [(table, proc)])
     assert torch.equal(rp, rp2) and torch.equal(c, c2) and torch.equal(v, v2)
+
+
+@pytest.mark.parametrize("n,p", [(6, 2), (5, 1), (4, 3)])
+def test_restrict_plan_equals_the_separate_calls(n, p):
+    """xgpu_restrict_plan (one atomic pass + one table pass) against xgpu_dofs_of_elements + xgpu_bitset_rank +
+    xgpu_gather_rows + xgpu_csr_plan_rows: same compressed numbering, same dof rows, same CSR"""
+    mesh = xf.MakeStructured3DMesh(nx=n, device=DEV)
+    V = xf.H1(mesh, order=p)
+    rng = np.random.default_rng(n * 10 + p)
+    sel = torch.from_numpy(rng.random(mesh.ne) < 0.4).to(DEV)
+    l_all = torch.nonzero(sel).flatten().int()
+    l_a, l_b = l_all[::2].contiguous(), l_all[1::2].contiguous()
+    bits = ops.new_bits(mesh.ne, DEV)
+    words = torch.zeros(ops.nwords(mesh.ne) * 32, dtype=torch.int64, device=DEV)
+    words[l_all.long()] = 1
+    w = (words.view(-1, 32) << torch.arange(32, device=DEV)).sum(1)
+    bits.copy_(torch.where(w >= 2 ** 31, w - 2 ** 32, w).int())
+    act = ops.dofs_of_elements(V.el_dofs, bits, V.ndof)
+    dofmap, ndof = ops.bitset_rank(act, V.ndof)
+    t_a, t_b = ops.gather_rows(V.el_dofs, l_a, dofmap), ops.gather_rows(V.el_dofs, l_b, dofmap)
+    dofmap2, ndof2, (u_a, u_b), plan = ops.restrict_plan(V.el_dofs, [l_a, l_b], V.ndof)
+    assert ndof2 == ndof and torch.equal(dofmap2, dofmap)
+    assert torch.equal(u_a, t_a) and torch.equal(u_b, t_b)
+    nd = V.el_dofs.shape[1]
+    m_a = torch.from_numpy(rng.standard_normal((l_a.numel(), nd, nd))).to(DEV)
+    m_b = torch.from_numpy(rng.standard_normal((l_b.numel(), nd, nd))).to(DEV)
+    ref = ops.csr_assemble_fused(ops.csr_plan_rows(ndof, [t_a, t_b]), [(t_a, m_a), (t_b, m_b)])
+    ops.csr_count_rows(plan)
+    got = ops.csr_assemble_fused(plan, [(u_a, m_a), (u_b, m_b)])
+    for x, y in zip(ref, got):
+        assert torch.equal(x, y)
+    # an empty list is a batch without rows
+    e = torch.empty(0, dtype=torch.int32, device=DEV)
+    _, nd3, (v_a, v_e), plan3 = ops.restrict_plan(V.el_dofs, [l_a, e], V.ndof)
+    assert v_e.shape == (0, nd) and nd3 <= ndof
