@@ -48,7 +48,8 @@ int xgpu_create(int device, xgpu_ctx** ctx_out);
 void xgpu_destroy(xgpu_ctx* ctx);
 int xgpu_set_stream(xgpu_ctx* ctx, void* cuda_stream);
 /* tuning switches (no reference counterpart).  "elmat_dmma": element-matrix contraction on FP64
- * tensor-core tiles: -1 never, 0 (default) at FE order >= 3, 1 also at order 2.  "csr_small": one-pass CSR, rows with few adjacent table rows on the thread-per-row
+ * tensor-core tiles: -1 never, 0 (default) at FE order >= 3, 1 also at order 2.  "short_blocks": cut quadrature / cut element matrices with one tile per block
+ * instead of a persistent grid (for a low-priority side stream; default 0).  "csr_small": one-pass CSR, rows with few adjacent table rows on the thread-per-row
  * kernels (default 1).  "csr_warp": one-pass CSR, the other rows with at most 256 candidates on the warp-per-row kernels (default 1).
  * "csr_trips": one-pass CSR lane-group kernels, 2 = half-width lane groups with two columns per
  * lane (0 = policy).  "elmat_st_tp": space-time element

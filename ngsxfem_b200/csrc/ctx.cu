@@ -200,6 +200,7 @@ extern "C" int xgpu_set_option(xgpu_ctx* ctx, const char* key, int value)
   if (!ctx || !key) return XGPU_ERR_ARG;
   if (std::string(key) == "elmat_dmma") { ctx->opt_dmma = value < 0 ? -1 : (value > 0 ? 1 : 0); return XGPU_OK; }
   if (std::string(key) == "csr_small") { ctx->opt_csr_small = value != 0; return XGPU_OK; }
+  if (std::string(key) == "short_blocks") { ctx->opt_short_blocks = value != 0; return XGPU_OK; }
   if (std::string(key) == "csr_warp") { ctx->opt_csr_warp = value != 0; return XGPU_OK; }
   if (std::string(key) == "csr_trips") { ctx->opt_csr_trips = value == 2 ? 2 : 0; return XGPU_OK; }
   if (std::string(key) == "elmat_st_tp") { ctx->opt_st_tp = value != 0; return XGPU_OK; }

@@ -334,7 +334,7 @@ extern "C" int xgpu_cutquad_fill(xgpu_ctx* ctx, int dim, int64_t n, const int32_
   if (deformed_if && dim < 2) return xgpu_fail(ctx, XGPU_ERR_UNSUPPORTED, "xgpu_cutquad_fill: deformation needs dim >= 2");
   const size_t sm = sizeof(double) * 4 * ((rs->n + 1) & ~1) + 128 * sizeof(CqDesc);
   unsigned grid = nblk(n, 128);  // 128 listed elements per block and pass
-  if (grid > XGPU_NSM * 8) grid = XGPU_NSM * 8;
+  if (grid > XGPU_NSM * 8 && !ctx->opt_short_blocks) grid = XGPU_NSM * 8;
 #define XG_FILL(DD)                                                                                                  \
   {                                                                                                                  \
     if (sm > 48 * 1024) XGPU_CUDA(ctx, cudaFuncSetAttribute(k_cq_fill<DD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm)); \

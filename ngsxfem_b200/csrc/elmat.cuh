@@ -626,7 +626,7 @@ int launch_ms(xgpu_ctx* ctx, int64_t n, const int32_t* elems, const int32_t* el_
   if (r2) R2 = *r2; else { R2.offsets = nullptr; R2.pts = nullptr; R2.wts = nullptr; R2.T.n = 0; }
   const size_t sm = (size_t)4 * (CH * PS + (df.order > 0 ? XG_DEFS : 0)) * sizeof(double);
   unsigned grid = nblk(n, 4);
-  if (grid > XGPU_NSM * 16) grid = XGPU_NSM * 16;
+  if (grid > XGPU_NSM * 16 && !ctx->opt_short_blocks) grid = XGPU_NSM * 16;
   if (df.order > 0) {
     if constexpr (D >= 2) {
       XGPU_CUDA(ctx, cudaFuncSetAttribute(k_elmat_ms<D, P, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));

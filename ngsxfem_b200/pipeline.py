@@ -56,11 +56,16 @@ _SIDE = {}
 
 
 def _side_context(dev):
-    """one (stream, xgpu context) pair per device for the concurrent element-matrix branch"""
+    """per device: a LOW-priority (stream, xgpu context) pair for the concurrent cut-element branch (its kernels use
+    short-lived blocks, so they fill whatever the main stream leaves free) and a HIGH-priority pair for the main chain"""
     if dev.index not in _SIDE:
-        st = torch.cuda.Stream(dev)
-        with torch.cuda.stream(st):
-            _SIDE[dev.index] = (st, Ctx(dev.index))
+        lo, hi = torch.cuda.Stream(dev, priority=0), torch.cuda.Stream(dev, priority=-1)
+        with torch.cuda.stream(lo):
+            c_lo = Ctx(dev.index)
+            c_lo.set_option("short_blocks", 1)
+        with torch.cuda.stream(hi):
+            c_hi = Ctx(dev.index)
+        _SIDE[dev.index] = (lo, c_lo, hi, c_hi)
     return _SIDE[dev.index]
 
 
@@ -76,7 +81,7 @@ class CutAssembly:
         self.nd = ops.h1_ndof(dim, fe_order)
         # second context on a side stream: the element matrices (HBM-write / FP64 bound) run
         # concurrently with the sparsity graph (shared-memory / issue bound); they only meet in the scatter
-        self.side_stream, self.ctx2 = _side_context(self.dev)
+        self.side_stream, self.ctx2, self.main_hp, self.ctx_hp = _side_context(self.dev)
 
     def step(self, phi, timer=None, keep=False, hooks=None, concurrent=False, mode="fused"):
         """one pass of the hot path; returns a dict with the CSR matrix and the unit counts.
@@ -90,9 +95,24 @@ class CutAssembly:
         concurrent=True runs the cut-element branch (cut quadrature + cut element matrices: FP64 / latency bound, low
         occupancy) on a side stream next to Restrict + the transposed table (memory / atomics bound); they meet in the
         row pass.  Off when per-phase CUDA-event times are wanted."""
+        if concurrent and torch.cuda.current_stream(self.dev) != self.main_hp:
+            # the main chain on a high-priority stream, the cut-element branch on a low-priority one
+            caller = torch.cuda.current_stream(self.dev)
+            self.main_hp.wait_stream(caller)
+            with torch.cuda.stream(self.main_hp):
+                out = self._step(phi, timer, keep, hooks, True, mode, self.ctx_hp)
+            caller.wait_stream(self.main_hp)
+            for v_ in out.values():
+                for t_ in (v_ if isinstance(v_, tuple) else (v_,)):
+                    if torch.is_tensor(t_):
+                        t_.record_stream(caller)
+            return out
+        return self._step(phi, timer, keep, hooks, concurrent, mode, self.ctx)
+
+    def _step(self, phi, timer, keep, hooks, concurrent, mode, ctx):
         t = timer or PhaseTimer(False)
         hooks = hooks or {}
-        ctx, dim, p, ne = self.ctx, self.dim, self.p, self.ne
+        dim, p, ne = self.dim, self.p, self.ne
         els, xyz = self.el_vtx, self.vtx_xyz
         fused = mode == "fused"
         t.mark("start")
@@ -119,12 +139,19 @@ class CutAssembly:
             if concurrent:
                 side.wait_stream(main)
             with torch.cuda.stream(side):
+                if concurrent and t.enabled:
+                    t.side = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+                    t.side[0].record(side)
                 off, n1 = ops.cutquad_count(dim, l_if, els, phi, ops.NEG, order, ctx=ctx2)
                 off2, n2 = ops.cutquad_count(dim, l_if, els, phi, ops.IF, order, ctx=ctx2)
                 q, w = ops.cutquad_fill(dim, l_if, els, xyz, phi, ops.NEG, order, off, n1, ctx=ctx2)
                 q2, w2 = ops.cutquad_fill(dim, l_if, els, xyz, phi, ops.IF, order, off2, n2, ctx=ctx2)
                 t.mark("cutquad")
+                if concurrent and t.enabled:
+                    t.side[1].record(side)
                 ops.elmat_rule_pair(dim, p, l_if, els, xyz, phi, (off, q, w), TERMS_VOL, (off2, q2, w2), TERMS_IF, out=m_if, ctx=ctx2)
+                if concurrent and t.enabled:
+                    t.side[2].record(side)
                 for t_ in (off, off2, q, w, q2, w2, m_if):
                     t_.record_stream(side)
             t.mark("elmat_cut")
