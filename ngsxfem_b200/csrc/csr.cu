@@ -114,11 +114,13 @@ __global__ void k_adj_sort(int64_t ndof, const long long* __restrict__ adj_ptr, 
     }
     cand[d] = c;
   }
+  const int nbig = __popc(__ballot_sync(0xffffffffu, c > 64));  // rows of the warp-per-row kernels (csr_rows_warp.cu)
   for (int s = 16; s > 0; s >>= 1) c = max(c, __shfl_down_sync(0xffffffffu, c, s));
   dup = __any_sync(0xffffffffu, dup);
   if ((threadIdx.x & 31) == 0) {
     if (c > 0) atomicMax(stats, c);
     if (dup) atomicOr(stats + 1, 1);
+    if (nbig) atomicAdd(stats + 3, nbig);
   }
 }
 
@@ -631,6 +633,9 @@ extern "C" void xgpu_plan_destroy(xgpu_plan* p)
   if (p->candoff) cudaFreeAsync(p->candoff, p->stream);
   if (p->tmp32) cudaFreeAsync(p->tmp32, p->stream);
   if (p->rowcnt) cudaFreeAsync(p->rowcnt, p->stream);
+  if (p->pat_small) cudaFreeAsync(p->pat_small, p->stream);
+  if (p->pat_big) cudaFreeAsync(p->pat_big, p->stream);
+  if (p->bigslot) cudaFreeAsync(p->bigslot, p->stream);
   for (int i = 0; i < 3; i++) if (p->ev[i]) cudaEventDestroy(p->ev[i]);
   delete p;
 }
@@ -736,12 +741,13 @@ int xg_plan_finish(xgpu_ctx* ctx, xgpu_plan* P, bool want_candoff)
     if (rc) return rc;
   }
   XGPU_CUDA(ctx, cudaEventRecord(P->ev[1], st));
-  XGPU_CUDA(ctx, xgpu_d2h_small(ctx->h_pinned, stats, 2 * sizeof(int), st));
-  if (want_candoff) XGPU_CUDA(ctx, xgpu_d2h_small(ctx->h_pinned + 1, P->candoff + ndof, sizeof(long long), st));
+  XGPU_CUDA(ctx, xgpu_d2h_small(ctx->h_pinned, stats, 4 * sizeof(int), st));
+  if (want_candoff) XGPU_CUDA(ctx, xgpu_d2h_small(ctx->h_pinned + 2, P->candoff + ndof, sizeof(long long), st));
   XGPU_CUDA(ctx, cudaStreamSynchronize(st));
   P->maxcand = ((int*)ctx->h_pinned)[0];
   P->dups = ((int*)ctx->h_pinned)[1];
-  P->ncand = want_candoff ? ctx->h_pinned[1] : -1;
+  P->nbig = ((int*)ctx->h_pinned)[3];
+  P->ncand = want_candoff ? ctx->h_pinned[2] : -1;
   return XGPU_OK;
 }
 

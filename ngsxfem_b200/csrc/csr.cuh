@@ -25,6 +25,13 @@ struct xgpu_plan {
   int warp_cand = 0;              // counted plans: the other rows with at most warp_cand candidates went through the warp-per-row kernels
   bool counted = false;           // xgpu_csr_plan_rows: rowptr / nnz / maxnr from the count pass (no pattern scratch)
   int32_t* rowcnt = nullptr;      // counted plans: distinct columns per row
+  // stored pattern of counted plans (csr_rows_small.cu / csr_rows_warp.cu): the values pass needs no sort
+  unsigned char* pat_small = nullptr;  // 192 B records of the thread-per-row kernel, interleaved per 32 rows
+  unsigned char* pat_big = nullptr;    // 1280 B records of the warp-per-row kernel
+  int32_t* bigslot = nullptr;          // ndof: record number of a warp-per-row row
+  int64_t nbig_cap = 0;                // records allocated in pat_big
+  int nbig = 0;                        // rows with more than 64 candidates (k_adj_sort)
+  int small_overflow = 0;              // a thread-per-row row has more than 32 nonzeros: the lane-group kernel assembles those
   BatchDev bd;
   long long* adj_ptr = nullptr;   // ndof+1
   long long* adj = nullptr;       // nadj entries: (global table row << 8) | local index
@@ -44,16 +51,19 @@ struct xgpu_plan {
 #define XG_ADJ_ROWKEY(e) ((e) >> 8)  // (batch, row)
 
 
-// csr_rows_small.cu: thread-per-row kernels for rows with at most xg_rows_small_na(width) adjacent table rows
+// csr_rows_small.cu: thread-per-row kernels (pattern pass / values pass) for rows with at most xg_rows_small_na(width)
+// adjacent table rows
 int xg_rows_small_na(int width, int64_t ndof);
 int xg_rows_small_supports(int width, int ncoef);
-int xg_rows_small_run(xgpu_ctx* ctx, xgpu_plan* P, const BatchDev& bd, const double* tref, int ncoef, bool count,
+size_t xg_rows_small_record_bytes(int64_t ndof);
+int xg_rows_small_run(xgpu_ctx* ctx, xgpu_plan* P, const BatchDev& bd, const double* tref, int ncoef, bool pattern,
                       int32_t* rowcnt, int* stats, int32_t* colidx, double* vals);
 
-// csr_rows_warp.cu: warp-per-row kernels (sorting network over the warp) for rows with at most 256 candidates
+// csr_rows_warp.cu: warp-per-row kernels (sorting network over the warp) for the other rows with fewer than 256 candidates
 int xg_rows_warp_ok(int width, int64_t ndof);
-int xg_rows_warp_run(xgpu_ctx* ctx, xgpu_plan* P, const BatchDev& bd, const double* tref, int ncoef, bool count, int small_na,
-                     unsigned int* ticket, int32_t* rowcnt, int* stats, int32_t* colidx, double* vals);
+size_t xg_rows_warp_record_bytes(int64_t nrows);
+int xg_rows_warp_run(xgpu_ctx* ctx, xgpu_plan* P, const BatchDev& bd, const double* tref, int ncoef, bool pattern, int small_na,
+                     unsigned int* ticket, unsigned int* slotcount, int32_t* rowcnt, int* stats, int32_t* colidx, double* vals);
 
 // csr.cu: sort the segments of a filled transposed table + statistics (synchronises)
 int xg_plan_finish(xgpu_ctx* ctx, xgpu_plan* P, bool want_candoff);

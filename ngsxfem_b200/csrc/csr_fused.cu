@@ -160,7 +160,8 @@ __global__ void __launch_bounds__(XF_WARPS * 32) k_rows_fused(const FusedPar P)
       na = (int)(__ldg(P.adj_ptr + d + 1) - a);
       rowbase = __ldg(P.rowptr + d);
       nr = (int)(__ldg(P.rowptr + d + 1) - rowbase);
-      if ((na >= 1 && na <= P.skip_na && nr <= 32) || __ldg(P.cand + d) <= P.skip_cand) { na = 0; nr = 0; }  // a row of the other kernels
+      const bool srow = na >= 1 && na <= P.skip_na;
+      if (srow ? (nr <= 32) : (__ldg(P.cand + d) <= P.skip_cand)) { na = 0; nr = 0; }  // a row of the other kernels
     }
     if (!__any_sync(FULL, nr > 0)) continue;
     int H = 32, shift = 27;
@@ -403,7 +404,7 @@ static int fused_shape(xgpu_ctx* ctx, xgpu_plan* P, FusedPar& F, int* trips)
   bool same_w = true;
   for (int i = 0; i < P->bd.nb; i++) same_w = same_w && P->bd.width[i] == P->wmax;
   F.skip_na = (ctx->opt_csr_small && same_w) ? xg_rows_small_na(P->wmax, P->ndof) : 0;
-  F.skip_cand = (ctx->opt_csr_warp && same_w && xg_rows_warp_ok(P->wmax, P->ndof)) ? 256 : -1;
+  F.skip_cand = (ctx->opt_csr_warp && same_w && xg_rows_warp_ok(P->wmax, P->ndof)) ? 255 : -1;
   return XGPU_OK;
 }
 
@@ -453,6 +454,13 @@ static int count_rows(xgpu_ctx* ctx, xgpu_plan* P, int64_t* nnz_host)
   F.stats = (int*)sp + 2;
   XF_TRY(cudaMallocAsync(&P->rowcnt, sizeof(int32_t) * (size_t)(ndof + 2), st));
   F.rowcnt = P->rowcnt;
+  unsigned int* slotcount = (unsigned int*)sp + 4;
+  if (F.skip_na > 0) XF_TRY(cudaMallocAsync(&P->pat_small, xg_rows_small_record_bytes(ndof), st));
+  if (F.skip_cand >= 0) {
+    P->nbig_cap = F.skip_na > 0 ? P->nbig : ndof;  // without the thread-per-row kernels every row may come here
+    XF_TRY(cudaMallocAsync(&P->bigslot, sizeof(int32_t) * (size_t)ndof, st));
+    XF_TRY(cudaMallocAsync(&P->pat_big, std::max<size_t>(16, xg_rows_warp_record_bytes(P->nbig_cap)), st));
+  }
   if (P->maxcand > F.skip_cand) {  // rows left for the lane-group hash kernel
     int per_sm = (int)std::min<size_t>(12, (220 * 1024) / (smem + 1024));
     unsigned grid = nblk(F.ntiles, XF_WARPS);
@@ -469,7 +477,7 @@ static int count_rows(xgpu_ctx* ctx, xgpu_plan* P, int64_t* nnz_host)
   }
   P->warp_cand = F.skip_cand;
   if (F.skip_cand >= 0) {
-    rc = xg_rows_warp_run(ctx, P, P->bd, nullptr, 0, true, F.skip_na, (unsigned int*)sp + 1, P->rowcnt, F.stats, nullptr, nullptr);
+    rc = xg_rows_warp_run(ctx, P, P->bd, nullptr, 0, true, F.skip_na, (unsigned int*)sp + 1, slotcount, P->rowcnt, F.stats, nullptr, nullptr);
     if (rc) return rc;
   }
   P->small_na = F.skip_na;
@@ -481,11 +489,12 @@ static int count_rows(xgpu_ctx* ctx, xgpu_plan* P, int64_t* nnz_host)
   if (rc) return rc;
   XF_TRY(cudaEventRecord(P->ev[2], st));
   XF_TRY(xgpu_d2h_small(ctx->h_pinned, P->rowptr + ndof, sizeof(long long), st));
-  XF_TRY(xgpu_d2h_small(ctx->h_pinned + 1, F.stats, sizeof(int), st));
+  XF_TRY(xgpu_d2h_small(ctx->h_pinned + 1, F.stats, 2 * sizeof(int), st));
   XF_TRY(cudaStreamSynchronize(st));
 #undef XF_TRY
   P->nnz = ctx->h_pinned[0];
   P->maxnr = ((int*)(ctx->h_pinned + 1))[0];
+  P->small_overflow = ((int*)(ctx->h_pinned + 1))[1];
   P->counted = true;
   if (nnz_host) *nnz_host = P->nnz;
   return XGPU_OK;
@@ -531,10 +540,10 @@ extern "C" int xgpu_csr_assemble_fused(xgpu_ctx* ctx, xgpu_plan* P, const xgpu_b
     if (rc) return rc;
   }
   if (F.skip_cand >= 0) {
-    rc = xg_rows_warp_run(ctx, P, F.bd, tref, nproc ? ncoef : 0, false, F.skip_na, (unsigned int*)sp + 1, nullptr, nullptr, colidx, vals);
+    rc = xg_rows_warp_run(ctx, P, F.bd, tref, nproc ? ncoef : 0, false, F.skip_na, (unsigned int*)sp + 1, nullptr, nullptr, nullptr, colidx, vals);
     if (rc) return rc;
   }
-  if (P->maxcand <= F.skip_cand) return XGPU_OK;  // no row left for the lane-group hash kernel
+  if (P->maxcand <= F.skip_cand && !(F.skip_na > 0 && P->small_overflow)) return XGPU_OK;  // no row left for the lane-group hash kernel
   int HG = 32;
   while (HG < P->maxnr + (P->maxnr >> 1) + 1) HG <<= 1;
   F.HG = HG;
@@ -566,3 +575,4 @@ extern "C" int xgpu_csr_assemble_fused(xgpu_ctx* ctx, xgpu_plan* P, const xgpu_b
   XGPU_LAUNCH_CHECK(ctx);
   return XGPU_OK;
 }
+

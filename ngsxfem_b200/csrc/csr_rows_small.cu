@@ -1,24 +1,28 @@
 // csr_rows_small.cu — matrix rows with few adjacent elements (e.g. the edge dofs of a P2 tet mesh: 4-6 tets, 40-60
-// candidate columns, 19-27 distinct), ONE THREAD PER ROW, no hash table:
-//   * the thread packs its candidates (column << 6 | candidate index) into 64 REGISTERS and sorts them with a fully
-//     unrolled bitonic network (static register indices, 2 instructions per compare-exchange, all 32 lanes busy on 32
-//     different rows) — duplicates become runs, the columns come out ascending, equal columns stay in candidate
-//     (= batch, table row, local index) order, the summation order of a sequential AddElementMatrix loop;
-//   * count pass: the number of runs is the row length (xgpu_csr_plan_rows);
-//   * full pass: a walk over the sorted registers gives every candidate its position in the row (a byte per candidate in
-//     shared memory), then the adjacent elements are visited in order with STATIC local column indices: the matrix row
-//     (or, for a procedural affine batch, the element's coefficients) arrives with vector loads, procedural values read
-//     the reference tensors at bank-conflict-free addresses (all lanes share j, the row index i differs: padded rows),
-//     and the values are added into the warp's staging buffer, which leaves with coalesced stores.
-// The lane-group kernels of csr_fused.cu spend ~200 instructions per 30 contributions on per-step bookkeeping
+// candidate columns, 19-27 distinct), ONE THREAD PER ROW, no hash table.
+//
+// PATTERN pass (xgpu_csr_count_rows): the thread packs its candidates (column << 6 | candidate index) into 64 REGISTERS
+// and sorts them with a fully unrolled bitonic network (static register indices, 2 instructions per compare-exchange,
+// all 32 lanes busy on 32 different rows).  Duplicates become runs: the run heads are the row's columns (ascending),
+// their number is the row length, and every candidate's run index is its POSITION in the row.  Columns (<= 32 x 4 B) and
+// positions (64 x 1 B) are stored as a 192 B record per row — interleaved over the 32 rows of a warp so that every store
+// / load of the records is a fully coalesced 512 B access.
+// VALUES pass (xgpu_csr_assemble_fused): no table rows, no sort — the thread reads its record, visits its adjacent
+// elements in order with STATIC local column indices (matrix row / procedural coefficients with vector loads, the
+// reference tensors at bank-conflict-free addresses: all lanes share j, the row index differs -> padded rows) and adds
+// value j at position pos[t*W + j] of its own [slot][lane] column of shared memory (bank = lane).  Entries are visited in
+// (batch, table row) order = the summation order of a sequential AddElementMatrix loop.  Columns and values leave
+// row by row with contiguous stores.  The same plan can be assembled again with other values (values pass only).
+// The lane-group hash kernels of csr_fused.cu spend ~200 instructions per 30 contributions on per-step bookkeeping
 // (profiles/r02_notes.md); here the bookkeeping is per 32 rows.
 #include "csr.cuh"
 
 namespace {
 
 #define XS_BLOCK 128
-#define XS_STAGE 1056  // doubles of warp-private shared memory: 32 slots x 33 (padded lane stride: also the transposed reads are conflict free)
-#define XS_LS 33
+#define XS_LS 33          // padded lane stride of the warp-private [slot][lane] arrays (transposed reads conflict free too)
+#define XS_STAGE 1056     // doubles of warp-private shared memory: 32 slots x 33
+#define XS_CHUNKS 12      // 16-byte chunks of a row record: 64 position bytes + 32 columns = 192 B
 
 struct SmallPar {
   int ndof;
@@ -26,9 +30,10 @@ struct SmallPar {
   const long long* adj;
   BatchDev bd;
   const double* tref;       // procedural batches: ncoef x W x W
-  const long long* rowptr;  // full pass
-  int32_t* rowcnt;          // count pass
-  int* stats;               // count pass: [0] longest row
+  const long long* rowptr;  // values pass
+  int32_t* rowcnt;          // pattern pass
+  int* stats;               // pattern pass: [0] longest row, [1] a row of this kernel has more than 32 nonzeros
+  uint4* records;           // row records, chunk c of row d at [((d >> 5) * XS_CHUNKS + c) * 32 + (d & 31)]
   int32_t* colidx;
   double* vals;
 };
@@ -50,25 +55,13 @@ __device__ __forceinline__ void bitonic_regs(unsigned (&r)[N])
       }
 }
 
-// W: width of every table row; NC: coefficients of the procedural batches (0: none); COUNT: count pass.
-// Only the sorting network is unrolled (static register indices); every other phase is a loop over shared memory, so the
-// program stays ~2000 instructions: the first version (everything unrolled, 5800 instructions, each executed once per
-// warp) stalled on instruction fetch (profiles/r02_notes.md).
-template <int W, int NC, bool COUNT>
-__global__ void __launch_bounds__(XS_BLOCK, 4) k_rows_small(const SmallPar P)
+// ---- pattern pass.  W: width of every table row
+template <int W>
+__global__ void __launch_bounds__(XS_BLOCK, 4) k_rows_small_pattern(const SmallPar P)
 {
-  constexpr int NA = 64 / W;          // adjacent table rows a thread can take
-  constexpr int WP = W + 1;           // padded row stride of the reference tensors in shared memory
-  constexpr int NTREF = (!COUNT && NC > 0) ? ((NC * W * WP + 1) & ~1) : 0;
+  constexpr int NA = 64 / W;  // adjacent table rows a thread can take
   extern __shared__ double sms[];
   const int tid = threadIdx.x, lane = tid & 31, wib = tid >> 5;
-  if (!COUNT && NC > 0) {
-    for (int k = tid; k < NC * W * W; k += XS_BLOCK) {
-      const int m = k / (W * W), ij = k - m * W * W, i = ij / W, j = ij - i * W;
-      sms[(m * W + i) * WP + j] = __ldg(P.tref + k);
-    }
-    __syncthreads();
-  }
   const long long d = (long long)blockIdx.x * XS_BLOCK + tid;
   long long a = 0;
   int na = 0;
@@ -76,21 +69,12 @@ __global__ void __launch_bounds__(XS_BLOCK, 4) k_rows_small(const SmallPar P)
     a = __ldg(P.adj_ptr + d);
     na = (int)(__ldg(P.adj_ptr + d + 1) - a);
   }
-  long long rowbase = 0;
-  int nr = 0;
-  bool small = na >= 1 && na <= NA;
-  if (!COUNT && small) {
-    rowbase = __ldg(P.rowptr + d);
-    nr = (int)(__ldg(P.rowptr + d + 1) - rowbase);
-    small = nr <= 32;  // longer rows go to the lane-group kernel (same test there)
-  }
+  const bool small = na >= 1 && na <= NA;
   const unsigned FULL = 0xffffffffu;
-  if (!__any_sync(FULL, small)) return;  // the whole warp leaves together: warp-level primitives below
+  if (!__any_sync(FULL, small)) return;  // the whole warp leaves together
   if (!small) na = 0;
-
   // ---- candidates -> registers (unrolled: static register indices)
   unsigned K[64];
-  unsigned long long okmask = 0ull;  // candidate (t, j) holds a dof (>= 0)
 #pragma unroll
   for (int t = 0; t < NA; t++) {
     int c[W];
@@ -114,124 +98,174 @@ __global__ void __launch_bounds__(XS_BLOCK, 4) k_rows_small(const SmallPar P)
     for (int j = 0; j < W; j++) {
       const int idx = t * W + j;
       K[idx] = c[j] >= 0 ? (((unsigned)c[j] << 6) | (unsigned)idx) : 0xffffffffu;
-      if (c[j] >= 0) okmask |= 1ull << idx;
     }
   }
 #pragma unroll
   for (int idx = NA * W; idx < 64; idx++) K[idx] = 0xffffffffu;
   bitonic_regs<64>(K);
 
-  if (COUNT) {
-    int nu = 0;
+  // ---- runs -> columns [slot][lane] and position bytes [lane][candidate] (row stride 17 words: conflict free both ways)
+  // (64 column slots: a row of this kernel may have up to 64 distinct columns; only the first 32 are stored)
+  unsigned* Cs = reinterpret_cast<unsigned*>(sms) + (size_t)wib * (64 * XS_LS + 32 * 17) + lane;
+  unsigned* Pw = reinterpret_cast<unsigned*>(sms) + (size_t)wib * (64 * XS_LS + 32 * 17) + 64 * XS_LS + lane * 17;
+  unsigned char* Pb = reinterpret_cast<unsigned char*>(Pw);  // the same bytes: no __restrict__ on either
 #pragma unroll
-    for (int p = 0; p < 64; p++) {
-      const bool fresh = K[p] != 0xffffffffu && (p == 0 || (K[p] >> 6) != (K[p - 1] >> 6));
-      nu += fresh ? 1 : 0;
-    }
-    if (small) P.rowcnt[d] = nu;
-    const int longest = __reduce_max_sync(FULL, small ? nu : 0);
-    if (lane == 0 && longest > 0) atomicMax(P.stats, longest);
-    return;
-  }
-
-  // ---- full pass.  Warp-private shared memory, always indexed [slot][lane] (bank = lane: conflict free whatever the
-  // slot): 64 x 32 words = the sorted keys, compacted IN PLACE to the row's columns by the rank loop, then (the same
-  // 8 KB) 32 x 32 doubles = the row's values.  Block: position bytes [candidate][thread].
-  unsigned* __restrict__ Ks = reinterpret_cast<unsigned*>(sms + NTREF + (size_t)wib * XS_STAGE) + lane;
-  double* __restrict__ Vs = sms + NTREF + (size_t)wib * XS_STAGE + lane;
-  unsigned char* __restrict__ pos_s = reinterpret_cast<unsigned char*>(sms + NTREF + (size_t)(XS_BLOCK / 32) * XS_STAGE) + tid;
+  for (int i = 0; i < 16; i++) Pw[i] = 0xffffffffu;  // 255: the candidate holds no dof
+  int q = -1;
+  unsigned prevcol = 0xffffffffu;
 #pragma unroll
-  for (int p = 0; p < 64; p++) Ks[p * XS_LS] = K[p];
-  {
-    // position of every candidate in its row = index of its run; the run heads are the row's columns (q <= p: the
-    // in-place store never overtakes the reads of this lane's column)
-    int q = -1;
-    unsigned prevcol = 0xffffffffu;
-#pragma unroll 4
-    for (int p = 0; p < 64; p++) {
-      const unsigned key = Ks[p * XS_LS];
-      if (key != 0xffffffffu) {
-        const unsigned col = key >> 6;
-        if (col != prevcol) { q++; Ks[q * XS_LS] = col; prevcol = col; }
-        pos_s[(key & 63u) * XS_BLOCK] = (unsigned char)q;
+  for (int p = 0; p < 64; p++) {
+    const unsigned key = K[p];
+    if (key != 0xffffffffu) {
+      const unsigned col = key >> 6;
+      if (col != prevcol) {
+        q++;
+        prevcol = col;
+        Cs[q * XS_LS] = col;
       }
+      Pb[key & 63u] = (unsigned char)q;
+    }
+  }
+  const int nu = q + 1;
+  if (small) P.rowcnt[d] = nu;
+  const int longest = __reduce_max_sync(FULL, small ? nu : 0);
+  if (lane == 0 && longest > 0) {
+    atomicMax(P.stats, longest);
+    if (longest > 32) atomicOr(P.stats + 1, 1);  // such rows are assembled by the lane-group kernel
+  }
+  // ---- record out: chunk c of the warp's 32 rows is one contiguous 512 B store
+  uint4* __restrict__ rec = P.records + (size_t)(d >> 5) * (XS_CHUNKS * 32) + lane;
+#pragma unroll
+  for (int c = 0; c < 4; c++) rec[c * 32] = make_uint4(Pw[4 * c], Pw[4 * c + 1], Pw[4 * c + 2], Pw[4 * c + 3]);
+#pragma unroll
+  for (int c = 0; c < 8; c++)
+    rec[(4 + c) * 32] = make_uint4(Cs[(4 * c) * XS_LS], Cs[(4 * c + 1) * XS_LS], Cs[(4 * c + 2) * XS_LS], Cs[(4 * c + 3) * XS_LS]);
+}
+
+// ---- values pass.  NC: coefficients of the procedural batches (0: none)
+template <int W, int NC>
+__global__ void __launch_bounds__(XS_BLOCK, 4) k_rows_small_values(const SmallPar P)
+{
+  constexpr int NA = 64 / W;
+  constexpr int WP = W + 1;  // padded row stride of the reference tensors in shared memory
+  constexpr int NTREF = (NC > 0) ? ((NC * W * WP + 1) & ~1) : 0;
+  extern __shared__ double sms[];
+  const int tid = threadIdx.x, lane = tid & 31, wib = tid >> 5;
+  if (NC > 0) {
+    for (int k = tid; k < NC * W * W; k += XS_BLOCK) {
+      const int m = k / (W * W), ij = k - m * W * W, i = ij / W, j = ij - i * W;
+      sms[(m * W + i) * WP + j] = __ldg(P.tref + k);
+    }
+    __syncthreads();
+  }
+  const long long d = (long long)blockIdx.x * XS_BLOCK + tid;
+  long long a = 0, rowbase = 0;
+  int na = 0, nr = 0;
+  if (d < P.ndof) {
+    a = __ldg(P.adj_ptr + d);
+    na = (int)(__ldg(P.adj_ptr + d + 1) - a);
+  }
+  bool small = na >= 1 && na <= NA;
+  if (small) {
+    rowbase = __ldg(P.rowptr + d);
+    nr = (int)(__ldg(P.rowptr + d + 1) - rowbase);
+    small = nr <= 32;  // longer rows: the lane-group kernel (same test there)
+  }
+  const unsigned FULL = 0xffffffffu;
+  if (!__any_sync(FULL, small)) return;
+  if (!small) { na = 0; nr = 0; }
+  // warp-private shared memory [slot][lane] (bank = lane whatever the slot): first the row's columns, then (the same
+  // 8 KB) the row's FP64 values
+  unsigned* __restrict__ Cs = reinterpret_cast<unsigned*>(sms + NTREF + (size_t)wib * XS_STAGE) + lane;
+  double* __restrict__ Vs = sms + NTREF + (size_t)wib * XS_STAGE + lane;
+  const uint4* __restrict__ rec = P.records + (size_t)(d >> 5) * (XS_CHUNKS * 32) + lane;
+  unsigned pw[16];
+#pragma unroll
+  for (int c = 0; c < 4; c++) {
+    const uint4 x = small ? __ldg(rec + c * 32) : make_uint4(~0u, ~0u, ~0u, ~0u);
+    pw[4 * c] = x.x; pw[4 * c + 1] = x.y; pw[4 * c + 2] = x.z; pw[4 * c + 3] = x.w;
+  }
+#pragma unroll
+  for (int c = 0; c < 8; c++) {
+    if (4 * c < nr) {  // chunks beyond the row hold nothing
+      const uint4 x = __ldg(rec + (4 + c) * 32);
+      Cs[(4 * c) * XS_LS] = x.x; Cs[(4 * c + 1) * XS_LS] = x.y; Cs[(4 * c + 2) * XS_LS] = x.z; Cs[(4 * c + 3) * XS_LS] = x.w;
     }
   }
   __syncwarp();
-  // columns out: one row per iteration, lanes over its entries (contiguous stores)
-  const int mynr = small ? nr : 0;
-  {
-    const unsigned* __restrict__ Kw = reinterpret_cast<const unsigned*>(sms + NTREF + (size_t)wib * XS_STAGE);
+  {  // columns out: one row per iteration, lanes over its entries (contiguous stores)
+    const unsigned* __restrict__ Cw = reinterpret_cast<const unsigned*>(sms + NTREF + (size_t)wib * XS_STAGE);
     for (int L = 0; L < 32; L++) {
-      const int nL = __shfl_sync(FULL, mynr, L);
+      const int nL = __shfl_sync(FULL, nr, L);
       const long long bL = __shfl_sync(FULL, rowbase, L);
-      if (lane < nL) P.colidx[bL + lane] = (int)Kw[lane * XS_LS + L];
+      if (lane < nL) P.colidx[bL + lane] = (int)Cw[lane * XS_LS + L];
     }
   }
   __syncwarp();
 #pragma unroll 8
   for (int q = 0; q < 32; q++) Vs[q * XS_LS] = 0.0;  // own column only: no synchronisation needed before the adds
-#pragma unroll 1
-  for (int t = 0; t < na; t++) {
-    const long long e = __ldg(P.adj + a + t);
-    const int bi = XG_ADJ_BATCH(e);
-    const size_t row = (size_t)XG_ADJ_ROW(e);
-    const int loc = XG_ADJ_LOC(e);
-    double v[W];
-    bool have = true;
-    const double* __restrict__ cfp = (NC > 0) ? P.bd.coefs[bi] : nullptr;
-    if (NC > 0 && cfp) {
-      double cf[8];
-      const double2* __restrict__ c2 = reinterpret_cast<const double2*>(cfp + row * 8);
 #pragma unroll
-      for (int m = 0; m < (NC + 1) / 2; m++) {
-        const double2 x = __ldg(c2 + m);
-        cf[2 * m] = x.x; cf[2 * m + 1] = x.y;
-      }
-      const double* __restrict__ tr = sms + loc * WP;
+  for (int t = 0; t < NA; t++) {
+    if (t < na) {
+      const long long e = __ldg(P.adj + a + t);
+      const int bi = XG_ADJ_BATCH(e);
+      const size_t row = (size_t)XG_ADJ_ROW(e);
+      const int loc = XG_ADJ_LOC(e);
+      double v[W];
+      bool have = true;
+      const double* __restrict__ cfp = (NC > 0) ? P.bd.coefs[bi] : nullptr;
+      if (NC > 0 && cfp) {
+        double cf[8];
+        const double2* __restrict__ c2 = reinterpret_cast<const double2*>(cfp + row * 8);
 #pragma unroll
-      for (int j = 0; j < W; j++) {
-        double r = 0.0;
+        for (int m = 0; m < (NC + 1) / 2; m++) {
+          const double2 x = __ldg(c2 + m);
+          cf[2 * m] = x.x; cf[2 * m + 1] = x.y;
+        }
+        const double* __restrict__ tr = sms + loc * WP;
 #pragma unroll
-        for (int m = 0; m < NC; m++) r += cf[m] * tr[m * W * WP + j];
-        v[j] = r;
-      }
-    } else {
-      const double* __restrict__ mb = P.bd.mats[bi];
-      have = mb != nullptr;  // a batch without matrices only contributes sparsity (explicit zeros)
-      if (have) {
-        const double* __restrict__ mrow = mb + (row * W + loc) * W;
-        if ((W & 1) == 0) {
+        for (int j = 0; j < W; j++) {
+          double r = 0.0;
 #pragma unroll
-          for (int j = 0; j < W; j += 2) {
-            const double2 x = __ldg(reinterpret_cast<const double2*>(mrow + j));
-            v[j] = x.x; v[j + 1] = x.y;
+          for (int m = 0; m < NC; m++) r += cf[m] * tr[m * W * WP + j];
+          v[j] = r;
+        }
+      } else {
+        const double* __restrict__ mb = P.bd.mats[bi];
+        have = mb != nullptr;  // a batch without matrices only contributes sparsity (explicit zeros)
+        if (have) {
+          const double* __restrict__ mrow = mb + (row * W + loc) * W;
+          if ((W & 1) == 0) {
+#pragma unroll
+            for (int j = 0; j < W; j += 2) {
+              const double2 x = __ldg(reinterpret_cast<const double2*>(mrow + j));
+              v[j] = x.x; v[j + 1] = x.y;
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < W; j++) v[j] = __ldg(mrow + j);
           }
-        } else {
-#pragma unroll
-          for (int j = 0; j < W; j++) v[j] = __ldg(mrow + j);
         }
       }
-    }
-    if (have) {
-      // the columns of one table row are distinct: the W read-modify-writes are independent — all loads first
-      const unsigned ok = (unsigned)(okmask >> (t * W)) & ((1u << W) - 1u);
-      int pp[W];
-      double cur[W];
+      if (have) {
+        // the columns of one table row are distinct: the W read-modify-writes are independent — all loads first
+        int pp[W];
+        double cur[W];
 #pragma unroll
-      for (int j = 0; j < W; j++) pp[j] = pos_s[(t * W + j) * XS_BLOCK];
+        for (int j = 0; j < W; j++) pp[j] = (int)((pw[(t * W + j) >> 2] >> (8 * ((t * W + j) & 3))) & 255u);
 #pragma unroll
-      for (int j = 0; j < W; j++) cur[j] = ((ok >> j) & 1u) ? Vs[pp[j] * XS_LS] : 0.0;
+        for (int j = 0; j < W; j++) cur[j] = (pp[j] != 255) ? Vs[pp[j] * XS_LS] : 0.0;
 #pragma unroll
-      for (int j = 0; j < W; j++)
-        if ((ok >> j) & 1u) Vs[pp[j] * XS_LS] = cur[j] + v[j];
+        for (int j = 0; j < W; j++)
+          if (pp[j] != 255) Vs[pp[j] * XS_LS] = cur[j] + v[j];
+      }
     }
   }
   __syncwarp();
   {
     const double* __restrict__ Vw = sms + NTREF + (size_t)wib * XS_STAGE;
     for (int L = 0; L < 32; L++) {
-      const int nL = __shfl_sync(FULL, mynr, L);
+      const int nL = __shfl_sync(FULL, nr, L);
       const long long bL = __shfl_sync(FULL, rowbase, L);
       if (lane < nL) P.vals[bL + lane] = Vw[lane * XS_LS + L];
     }
@@ -241,19 +275,20 @@ __global__ void __launch_bounds__(XS_BLOCK, 4) k_rows_small(const SmallPar P)
 inline unsigned nblk(int64_t n, int t) { return (unsigned)((n + t - 1) / t); }
 
 template <int W>
-int launch_small(xgpu_ctx* ctx, const SmallPar& S, int NC, bool count)
+int launch_small(xgpu_ctx* ctx, const SmallPar& S, int NC, bool pattern)
 {
   const unsigned grid = nblk(S.ndof, XS_BLOCK);
   cudaStream_t st = ctx->stream;
-  if (count) {
-    k_rows_small<W, 0, true><<<grid, XS_BLOCK, 0, st>>>(S);
+  if (pattern) {
+    const size_t smem = sizeof(unsigned) * (size_t)(XS_BLOCK / 32) * (64 * XS_LS + 32 * 17);
+    k_rows_small_pattern<W><<<grid, XS_BLOCK, smem, st>>>(S);
   } else {
     const size_t ntref = ((size_t)NC * W * (W + 1) + 1) & ~(size_t)1;
-    const size_t smem = sizeof(double) * (ntref + (size_t)(XS_BLOCK / 32) * XS_STAGE) + (size_t)64 * XS_BLOCK;
+    const size_t smem = sizeof(double) * (ntref + (size_t)(XS_BLOCK / 32) * XS_STAGE);
 #define XS_LAUNCH(NCV)                                                                                                   \
   {                                                                                                                      \
-    XGPU_CUDA(ctx, cudaFuncSetAttribute(k_rows_small<W, NCV, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-    k_rows_small<W, NCV, false><<<grid, XS_BLOCK, smem, st>>>(S);                                                        \
+    XGPU_CUDA(ctx, cudaFuncSetAttribute(k_rows_small_values<W, NCV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    k_rows_small_values<W, NCV><<<grid, XS_BLOCK, smem, st>>>(S);                                                        \
   }
     bool done = false;
     if (NC == 0) { XS_LAUNCH(0) done = true; }
@@ -284,18 +319,20 @@ int xg_rows_small_na(int width, int64_t ndof)
   }
 }
 
-int xg_rows_small_run(xgpu_ctx* ctx, xgpu_plan* P, const BatchDev& bd, const double* tref, int ncoef, bool count,
+size_t xg_rows_small_record_bytes(int64_t ndof) { return (size_t)((ndof + 31) / 32) * XS_CHUNKS * 32 * sizeof(uint4); }
+
+int xg_rows_small_run(xgpu_ctx* ctx, xgpu_plan* P, const BatchDev& bd, const double* tref, int ncoef, bool pattern,
                       int32_t* rowcnt, int* stats, int32_t* colidx, double* vals)
 {
   SmallPar S;
   S.ndof = (int)P->ndof;
   S.adj_ptr = P->adj_ptr; S.adj = P->adj; S.bd = bd; S.tref = tref;
-  S.rowptr = P->rowptr; S.rowcnt = rowcnt; S.stats = stats; S.colidx = colidx; S.vals = vals;
+  S.rowptr = P->rowptr; S.rowcnt = rowcnt; S.stats = stats; S.records = (uint4*)P->pat_small; S.colidx = colidx; S.vals = vals;
   switch (P->wmax) {
-    case 4: return launch_small<4>(ctx, S, ncoef, count);
-    case 6: return launch_small<6>(ctx, S, ncoef, count);
-    case 10: return launch_small<10>(ctx, S, ncoef, count);
-    case 12: return launch_small<12>(ctx, S, ncoef, count);
+    case 4: return launch_small<4>(ctx, S, ncoef, pattern);
+    case 6: return launch_small<6>(ctx, S, ncoef, pattern);
+    case 10: return launch_small<10>(ctx, S, ncoef, pattern);
+    case 12: return launch_small<12>(ctx, S, ncoef, pattern);
   }
   return xgpu_fail(ctx, XGPU_ERR_UNSUPPORTED, "csr small rows: width");
 }

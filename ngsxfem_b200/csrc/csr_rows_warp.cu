@@ -13,11 +13,14 @@
 // The lane-group hash kernel of csr_fused.cu needs ~2200 instructions per such row (24 sequential steps with 10 of 32
 // lanes, rank sort); it remains the fallback for rows with more than 256 candidates.
 #include "csr.cuh"
+#include <algorithm>
 
 namespace {
 
 #define XW_WARPS 4
 #define XW_KPL 8  // keys per lane: 256 candidates per row
+
+#define XW_RECB 1280  // bytes of a row record: 256 position bytes + 256 columns
 
 struct WarpPar {
   int ndof, small_na;
@@ -25,10 +28,16 @@ struct WarpPar {
   const long long* adj;
   BatchDev bd;
   const double* tref;       // procedural batches: ncoef x W x W
-  const long long* rowptr;  // full pass
-  int32_t* rowcnt;          // count pass
-  int* stats;               // count pass: [0] longest row
+  const long long* rowptr;  // values pass
+  int32_t* rowcnt;          // pattern pass
+  int* stats;               // pattern pass: [0] longest row
   unsigned int* ticket;
+  unsigned int* slotcount;  // pattern pass: records handed out so far
+  unsigned int slotcap;
+  int32_t* bigslot;         // record number of a row (pattern pass: out, values pass: in)
+  unsigned char* records;
+  int accstride;            // values pass: doubles per row accumulator (>= longest row of this kernel)
+  int namax;                // values pass: adjacent table rows staged per row (>= maxcand / W, even)
   int32_t* colidx;
   double* vals;
 };
@@ -77,20 +86,16 @@ __device__ __forceinline__ void sort256(unsigned (&K)[XW_KPL], int lane)
   }
 }
 
-template <int W, int NC, bool COUNT>
-__global__ void __launch_bounds__(XW_WARPS * 32) k_rows_warp(const WarpPar P)
+// ---- pattern pass: sort, runs -> row length, columns and the position of every candidate, stored as the row's record
+template <int W>
+__global__ void __launch_bounds__(XW_WARPS * 32) k_rows_warp_pattern(const WarpPar P)
 {
-  constexpr int NA_SMALL_W = 64 / W;
-  extern __shared__ double smw[];
-  const int lane = threadIdx.x & 31;
+  __shared__ unsigned int pos_sm[XW_WARPS][64];   // 256 position bytes per warp
+  __shared__ int cols_sm[XW_WARPS][32 * XW_KPL];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const unsigned FULL = 0xffffffffu;
-  if (!COUNT && NC > 0) {
-    for (int k = threadIdx.x; k < NC * W * W; k += blockDim.x) smw[k] = __ldg(P.tref + k);
-    __syncthreads();
-  }
-  (void)NA_SMALL_W;
-  constexpr int NTREF = (!COUNT && NC > 0) ? NC * W * W : 0;
-  double* __restrict__ vals_s = smw + NTREF + (threadIdx.x >> 5) * (32 * XW_KPL);  // this warp's candidate values
+  unsigned char* pos_b = reinterpret_cast<unsigned char*>(pos_sm[wib]);  // aliases pos_sm: no __restrict__
+  int* __restrict__ cols_s = cols_sm[wib];
   int longest = 0;
   for (;;) {
     // 32 consecutive rows per ticket; every lane looks at one of them, the warp then works through the eligible ones
@@ -99,20 +104,15 @@ __global__ void __launch_bounds__(XW_WARPS * 32) k_rows_warp(const WarpPar P)
     base = __shfl_sync(FULL, base, 0);
     if (base >= (unsigned)P.ndof) break;
     const long long dl = (long long)base + lane;
-    long long al = 0, rbl = 0;
-    int nal = 0, nrl = 0;
+    long long al = 0;
+    int nal = 0;
     if (dl < P.ndof) {
       al = __ldg(P.adj_ptr + dl);
       nal = (int)(__ldg(P.adj_ptr + dl + 1) - al);
-      if (!COUNT) {
-        rbl = __ldg(P.rowptr + dl);
-        nrl = (int)(__ldg(P.rowptr + dl + 1) - rbl);
-      }
     }
-    bool small = nal >= 1 && nal <= P.small_na;  // rows of the thread-per-row kernel
-    if (!COUNT) small = small && nrl <= 32;
-    const bool mine = dl < P.ndof && !small && nal * W <= 32 * XW_KPL;
-    if (COUNT && mine && nal == 0) P.rowcnt[dl] = 0;
+    const bool small = nal >= 1 && nal <= P.small_na;  // rows of the thread-per-row kernel
+    const bool mine = dl < P.ndof && !small && nal * W < 32 * XW_KPL;  // < 256 candidates: position 255 stays free as the "no dof" mark
+    if (mine && nal == 0) P.rowcnt[dl] = 0;
     unsigned todo = __ballot_sync(FULL, mine && nal > 0);
     while (todo) {
       const int src = __ffs(todo) - 1;
@@ -120,12 +120,8 @@ __global__ void __launch_bounds__(XW_WARPS * 32) k_rows_warp(const WarpPar P)
       const long long d = (long long)base + src;
       const long long a = __shfl_sync(FULL, al, src);
       const int na = __shfl_sync(FULL, nal, src);
-      const long long rowbase = __shfl_sync(FULL, rbl, src);
       const int cand = na * W;
-      // ---- candidates: index k * 32 + lane (neighbouring lanes read neighbouring table entries and share the adjacency
-      // entry / the element's coefficients: few distinct cache lines per load).  Full pass: the candidate's value is
-      // fetched / generated here, in candidate order, and parked in shared memory — after the sort every lane would
-      // touch 32 different elements per load and the L1 pipe sets the time (profiles/r02_notes.md)
+      // candidates: index k * 32 + lane (neighbouring lanes read neighbouring table entries)
       unsigned K[XW_KPL];
 #pragma unroll
       for (int k = 0; k < XW_KPL; k++) {
@@ -134,47 +130,20 @@ __global__ void __launch_bounds__(XW_WARPS * 32) k_rows_warp(const WarpPar P)
         if (idx < cand) {
           const int t = idx / W, j = idx - t * W;
           const long long e = __ldg(P.adj + a + t);
-          const int bi = XG_ADJ_BATCH(e);
-          const size_t row = (size_t)XG_ADJ_ROW(e);
-          const int c = __ldg(P.bd.table[bi] + row * W + j);
+          const int c = __ldg(P.bd.table[XG_ADJ_BATCH(e)] + (size_t)XG_ADJ_ROW(e) * W + j);
           if (c >= 0) K[k] = ((unsigned)c << 8) | (unsigned)idx;
-          if (!COUNT) {
-            const int loc = XG_ADJ_LOC(e);
-            double val = 0.0;
-            const double* __restrict__ cfp = (NC > 0) ? P.bd.coefs[bi] : nullptr;
-            if (NC > 0 && cfp) {
-              const double2* __restrict__ c2 = reinterpret_cast<const double2*>(cfp + row * 8);
-              double cf[8];
-#pragma unroll
-              for (int m = 0; m < (NC + 1) / 2; m++) {
-                const double2 x = __ldg(c2 + m);
-                cf[2 * m] = x.x; cf[2 * m + 1] = x.y;
-              }
-              const double* __restrict__ tr = smw + loc * W + j;
-#pragma unroll
-              for (int m = 0; m < NC; m++) val += cf[m] * tr[m * W * W];
-            } else {
-              const double* __restrict__ mb = P.bd.mats[bi];
-              if (mb) val = __ldg(mb + (row * W + loc) * W + j);  // else: sparsity only (explicit zero)
-            }
-            vals_s[idx] = val;
-          }
         }
       }
-      if (!COUNT) __syncwarp();
+      pos_sm[wib][lane] = 0xffffffffu; pos_sm[wib][lane + 32] = 0xffffffffu;  // 255: the candidate holds no dof
       sort256(K, lane);
-      // ---- runs: heads (first of an equal-column run) and ends
+      // runs: heads (first key of an equal-column run)
       const unsigned prevlast = __shfl_up_sync(FULL, K[XW_KPL - 1], 1);
-      const unsigned nextfirst = __shfl_down_sync(FULL, K[0], 1);
-      unsigned fresh = 0u, last = 0u, valid = 0u;
+      unsigned fresh = 0u;
 #pragma unroll
       for (int k = 0; k < XW_KPL; k++) {
         if (K[k] != 0xffffffffu) {
-          valid |= 1u << k;
           const unsigned pk = (k == 0) ? ((lane == 0) ? 0xffffffffu : prevlast) : K[k - 1];
-          const unsigned nk = (k == XW_KPL - 1) ? ((lane == 31) ? 0xffffffffu : nextfirst) : K[k + 1];
           if ((pk >> 8) != (K[k] >> 8) || (k == 0 && lane == 0)) fresh |= 1u << k;
-          if ((nk >> 8) != (K[k] >> 8) || (k == XW_KPL - 1 && lane == 31)) last |= 1u << k;
         }
       }
       const int nf = __popc(fresh);
@@ -185,85 +154,163 @@ __global__ void __launch_bounds__(XW_WARPS * 32) k_rows_warp(const WarpPar P)
         if (lane >= s) incl += y;
       }
       const int nr = __shfl_sync(FULL, incl, 31);
-      if (COUNT) {
-        if (lane == 0) P.rowcnt[d] = nr;
-        longest = max(longest, nr);
-        continue;
+      unsigned slot = 0;
+      if (lane == 0) {
+        slot = atomicAdd(P.slotcount, 1u);
+        P.rowcnt[d] = nr;
+        P.bigslot[d] = (int)slot;
       }
-      // ---- full pass: columns at the run heads
-      int slot = incl - nf - 1;  // slot of the run the lane's first key continues (head in an earlier lane)
+      slot = __shfl_sync(FULL, slot, 0);
+      longest = max(longest, nr);
+      __syncwarp();
       {
-        int q = slot;
-#pragma unroll
-        for (int k = 0; k < XW_KPL; k++)
-          if ((fresh >> k) & 1u) { q++; P.colidx[rowbase + q] = (int)(K[k] >> 8); }
-      }
-      // values of the lane's (sorted) candidates
-      double v[XW_KPL];
-#pragma unroll
-      for (int k = 0; k < XW_KPL; k++) v[k] = ((valid >> k) & 1u) ? vals_s[K[k] & 255u] : 0.0;
-      // carry over the lane boundaries: a lane whose 8 keys all continue the previous lane's run passes the
-      // running sum on (sequential adds), every other lane's carry-out is the sum of its own last run
-      const bool cont_in = (valid & 1u) && !(fresh & 1u);
-      const bool through = valid == 0xffu && fresh == 0u;
-      double cout = 0.0;
-      {
-        double r = 0.0;
+        int q = incl - nf - 1;  // run the lane's first key continues (head in an earlier lane)
 #pragma unroll
         for (int k = 0; k < XW_KPL; k++) {
-          if ((fresh >> k) & 1u) r = 0.0;
-          if ((valid >> k) & 1u) r += v[k];
-        }
-        cout = r;
-      }
-      double cin = 0.0;
-      const int iters = (na >> 3) + 1;  // a run has at most na keys: it covers at most na/8 whole lanes
-      for (int it = 0; it < iters; it++) {
-        cin = __shfl_up_sync(FULL, cout, 1);
-        if (lane == 0) cin = 0.0;
-        if (through) {
-          double r = cin;
-#pragma unroll
-          for (int k = 0; k < XW_KPL; k++) r += v[k];
-          cout = r;
+          if (K[k] != 0xffffffffu) {
+            if ((fresh >> k) & 1u) { q++; cols_s[q] = (int)(K[k] >> 8); }
+            pos_b[K[k] & 255u] = (unsigned char)q;
+          }
         }
       }
-      {
-        double r = cont_in ? cin : 0.0;
-        int q = slot;
-#pragma unroll
-        for (int k = 0; k < XW_KPL; k++) {
-          if ((fresh >> k) & 1u) { r = 0.0; q++; }
-          if ((valid >> k) & 1u) r += v[k];
-          if ((last >> k) & 1u) P.vals[rowbase + q] = r;
-        }
+      __syncwarp();
+      if (slot < P.slotcap) {
+        unsigned char* __restrict__ rec = P.records + (size_t)slot * XW_RECB;
+        reinterpret_cast<uint2*>(rec)[lane] = make_uint2(pos_sm[wib][2 * lane], pos_sm[wib][2 * lane + 1]);
+        int* __restrict__ rc = reinterpret_cast<int*>(rec + 256);
+        for (int i = lane; i < nr; i += 32) rc[i] = cols_s[i];
       }
-      __syncwarp();  // the next row overwrites vals_s
+      __syncwarp();
     }
   }
-  if (COUNT) {
-    longest = __reduce_max_sync(FULL, longest);
-    if (lane == 0 && longest > 0) atomicMax(P.stats, longest);
+  longest = __reduce_max_sync(FULL, longest);
+  if (lane == 0 && longest > 0) atomicMax(P.stats, longest);
+}
+
+// ---- values pass: one row per warp at a time, small footprint (high occupancy hides the dependent global loads).
+// Phase 1: the values of the row's candidates, fetched / generated in candidate order (neighbouring lanes share the
+// adjacency entry and the element's coefficients: few distinct cache lines per load), and the row's position bytes go to
+// shared memory.  Phase 2: the adjacent elements one after the other, lane j adds value (t, j) at its position — the
+// summation order of a sequential AddElementMatrix loop.  Phase 3: columns (from the record) and values out.
+template <int W, int NC>
+__global__ void __launch_bounds__(XW_WARPS * 32) k_rows_warp_values(const WarpPar P)
+{
+  constexpr int NCAND = 32 * XW_KPL;
+  constexpr int NTREF = (NC > 0) ? NC * W * W : 0;
+  extern __shared__ double smw[];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const unsigned FULL = 0xffffffffu;
+  if (NC > 0) {
+    for (int k = threadIdx.x; k < NC * W * W; k += blockDim.x) smw[k] = __ldg(P.tref + k);
+    __syncthreads();
+  }
+  const int AS = P.accstride;
+  double* vals_w = smw + NTREF + (size_t)wib * (NCAND + AS + NCAND / 8);
+  double* acc_w = vals_w + NCAND;
+  unsigned char* pos_w = reinterpret_cast<unsigned char*>(acc_w + AS);
+  for (;;) {
+    unsigned base = 0;
+    if (lane == 0) base = atomicAdd(P.ticket, 32u);
+    base = __shfl_sync(FULL, base, 0);
+    if (base >= (unsigned)P.ndof) break;
+    const long long dl = (long long)base + lane;
+    long long al = 0, rbl = 0;
+    int nal = 0, nrl = 0, sll = -1;
+    if (dl < P.ndof) {
+      al = __ldg(P.adj_ptr + dl);
+      nal = (int)(__ldg(P.adj_ptr + dl + 1) - al);
+      rbl = __ldg(P.rowptr + dl);
+      nrl = (int)(__ldg(P.rowptr + dl + 1) - rbl);
+    }
+    const bool small = nal >= 1 && nal <= P.small_na;
+    const bool mine = dl < P.ndof && !small && nal * W < NCAND && nal > 0;
+    if (mine) sll = __ldg(P.bigslot + dl);
+    unsigned todo = __ballot_sync(FULL, mine);
+    while (todo) {
+      const int src = __ffs(todo) - 1;
+      todo &= todo - 1;
+      const long long a = __shfl_sync(FULL, al, src), rowbase = __shfl_sync(FULL, rbl, src);
+      const int na = __shfl_sync(FULL, nal, src), nr = __shfl_sync(FULL, nrl, src);
+      const unsigned char* __restrict__ rec = P.records + (size_t)__shfl_sync(FULL, sll, src) * XW_RECB;
+      const int cand = na * W;
+      // ---- phase 1
+      reinterpret_cast<uint2*>(pos_w)[lane] = __ldg(reinterpret_cast<const uint2*>(rec) + lane);
+      for (int i = lane; i < nr; i += 32) acc_w[i] = 0.0;
+#pragma unroll 2
+      for (int k = 0; k < XW_KPL; k++) {
+        const int idx = k * 32 + lane;
+        if (idx < cand) {
+          const int t = idx / W, j = idx - t * W;
+          const long long e = __ldg(P.adj + a + t);
+          const int bi = XG_ADJ_BATCH(e);
+          const size_t row = (size_t)XG_ADJ_ROW(e);
+          const int loc = XG_ADJ_LOC(e);
+          double val = 0.0;
+          const double* __restrict__ cfp = (NC > 0) ? P.bd.coefs[bi] : nullptr;
+          if (NC > 0 && cfp) {
+            const double2* __restrict__ c2 = reinterpret_cast<const double2*>(cfp + row * 8);
+            double cf[8];
+#pragma unroll
+            for (int m = 0; m < (NC + 1) / 2; m++) {
+              const double2 x = __ldg(c2 + m);
+              cf[2 * m] = x.x; cf[2 * m + 1] = x.y;
+            }
+            const double* __restrict__ tr = smw + loc * W + j;
+#pragma unroll
+            for (int m = 0; m < NC; m++) val += cf[m] * tr[m * W * W];
+          } else {
+            const double* __restrict__ mb = P.bd.mats[bi];
+            if (mb) val = __ldg(mb + (row * W + loc) * W + j);  // else: sparsity only (explicit zero)
+          }
+          vals_w[idx] = val;
+        }
+      }
+      __syncwarp();
+      // ---- phase 2: lane j adds value (t, j)
+      if (lane < W) {
+        for (int t = 0; t < na; t++) {
+          const int idx = t * W + lane;
+          const int p = pos_w[idx];
+          if (p != 255) acc_w[p] += vals_w[idx];   // the lanes' positions are distinct; the next t follows in program order
+        }
+      }
+      __syncwarp();
+      // ---- phase 3
+      {
+        const int* __restrict__ rc = reinterpret_cast<const int*>(rec + 256);
+        for (int i = lane; i < nr; i += 32) {
+          P.colidx[rowbase + i] = __ldg(rc + i);
+          P.vals[rowbase + i] = acc_w[i];
+        }
+      }
+      __syncwarp();
+    }
   }
 }
 
 inline unsigned nblk(int64_t n, int t) { return (unsigned)((n + t - 1) / t); }
 
 template <int W>
-int launch_warp(xgpu_ctx* ctx, const WarpPar& S, int NC, bool count)
+int launch_warp(xgpu_ctx* ctx, const WarpPar& S, int NC, bool pattern)
 {
   cudaStream_t st = ctx->stream;
   unsigned grid = nblk(((int64_t)S.ndof + 31) / 32, XW_WARPS);
   if (grid > XGPU_NSM * 12) grid = XGPU_NSM * 12;
-  if (count) {
-    k_rows_warp<W, 0, true><<<grid, XW_WARPS * 32, 0, st>>>(S);
+  if (pattern) {
+    k_rows_warp_pattern<W><<<grid, XW_WARPS * 32, 0, st>>>(S);
   } else {
-    const size_t smem = sizeof(double) * ((size_t)NC * W * W + (size_t)XW_WARPS * 32 * XW_KPL);
+    const size_t smem = sizeof(double) * ((size_t)NC * W * W + (size_t)XW_WARPS * (32 * XW_KPL + S.accstride + 32 * XW_KPL / 8));
+#define XW_LAUNCH(NCV)                                                                                                  \
+  {                                                                                                                     \
+    XGPU_CUDA(ctx, cudaFuncSetAttribute(k_rows_warp_values<W, NCV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    k_rows_warp_values<W, NCV><<<grid, XW_WARPS * 32, smem, st>>>(S);                                                   \
+  }
     bool done = false;
-    if (NC == 0) { k_rows_warp<W, 0, false><<<grid, XW_WARPS * 32, smem, st>>>(S); done = true; }
-    if constexpr (W == 4 || W == 10) { if (NC == 7) { k_rows_warp<W, 7, false><<<grid, XW_WARPS * 32, smem, st>>>(S); done = true; } }
-    if constexpr (W == 6) { if (NC == 4) { k_rows_warp<W, 4, false><<<grid, XW_WARPS * 32, smem, st>>>(S); done = true; } }
+    if (NC == 0) { XW_LAUNCH(0) done = true; }
+    if constexpr (W == 4 || W == 10) { if (NC == 7) { XW_LAUNCH(7) done = true; } }
+    if constexpr (W == 6) { if (NC == 4) { XW_LAUNCH(4) done = true; } }
     if (!done) return xgpu_fail(ctx, XGPU_ERR_UNSUPPORTED, "csr warp rows: coefficient count");
+#undef XW_LAUNCH
   }
   XGPU_LAUNCH_CHECK(ctx);
   return XGPU_OK;
@@ -271,25 +318,31 @@ int launch_warp(xgpu_ctx* ctx, const WarpPar& S, int NC, bool count)
 
 }  // namespace
 
-// the warp-per-row kernels take rows with at most 256 candidates when (column << 8 | candidate) fits 32 bits
+// the warp-per-row kernels take rows with fewer than 256 candidates when (column << 8 | candidate) fits 32 bits
 int xg_rows_warp_ok(int width, int64_t ndof)
 {
   if (ndof >= ((int64_t)1 << 24)) return 0;
   return width == 4 || width == 6 || width == 10 || width == 12;
 }
 
-int xg_rows_warp_run(xgpu_ctx* ctx, xgpu_plan* P, const BatchDev& bd, const double* tref, int ncoef, bool count, int small_na,
-                     unsigned int* ticket, int32_t* rowcnt, int* stats, int32_t* colidx, double* vals)
+size_t xg_rows_warp_record_bytes(int64_t nrows) { return (size_t)nrows * XW_RECB; }
+
+int xg_rows_warp_run(xgpu_ctx* ctx, xgpu_plan* P, const BatchDev& bd, const double* tref, int ncoef, bool pattern, int small_na,
+                     unsigned int* ticket, unsigned int* slotcount, int32_t* rowcnt, int* stats, int32_t* colidx, double* vals)
 {
   WarpPar S;
   S.ndof = (int)P->ndof; S.small_na = small_na;
   S.adj_ptr = P->adj_ptr; S.adj = P->adj; S.bd = bd; S.tref = tref;
   S.rowptr = P->rowptr; S.rowcnt = rowcnt; S.stats = stats; S.ticket = ticket; S.colidx = colidx; S.vals = vals;
+  S.slotcount = slotcount; S.slotcap = (unsigned)P->nbig_cap; S.bigslot = P->bigslot; S.records = P->pat_big;
+  S.accstride = (std::max(P->maxnr, 8) + 7) & ~7;
+  if (S.accstride > 256) S.accstride = 256;
+  S.namax = (std::min(P->maxcand, 255) / std::max(1, P->wmax) + 2) & ~1;
   switch (P->wmax) {
-    case 4: return launch_warp<4>(ctx, S, ncoef, count);
-    case 6: return launch_warp<6>(ctx, S, ncoef, count);
-    case 10: return launch_warp<10>(ctx, S, ncoef, count);
-    case 12: return launch_warp<12>(ctx, S, ncoef, count);
+    case 4: return launch_warp<4>(ctx, S, ncoef, pattern);
+    case 6: return launch_warp<6>(ctx, S, ncoef, pattern);
+    case 10: return launch_warp<10>(ctx, S, ncoef, pattern);
+    case 12: return launch_warp<12>(ctx, S, ncoef, pattern);
   }
   return xgpu_fail(ctx, XGPU_ERR_UNSUPPORTED, "csr warp rows: width");
 }
