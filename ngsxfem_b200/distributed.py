@@ -270,9 +270,69 @@ class DistributedCutAssembly:
         return res["l2g"][a:b], rp[a:b + 1] - lo, cols, res["vals"][lo:hi]
 
 
+# ------------------------------------------------------------------ consistency of the merged matrix (bench.py, tests)
+def _key_weight(g, a):
+    """deterministic weight in [0.5, 1.5) of a global dof key"""
+    return 0.5 + ((g * a) % 1048573).to(torch.float64) / 1048573.0
+
+
+def _block_checksums(rowptr, col, vals, keys_of_local):
+    """linear functionals of a CSR block whose rows / columns carry global keys: sum of the entries and two
+    position-dependent weighted sums  sum_ij A_ij w(key_i) w'(key_j)"""
+    n = rowptr.numel() - 1
+    ln = rowptr[1:] - rowptr[:-1]
+    rows = torch.repeat_interleave(torch.arange(n, device=vals.device), ln)
+    kr, kc = keys_of_local[rows], keys_of_local[col.long()]
+    v = vals
+    return torch.stack([v.sum(), (v * _key_weight(kr, 7919) * _key_weight(kc, 104729)).sum(),
+                        (v * _key_weight(kr, 611953) * _key_weight(kc, 15485863)).sum(), v.abs().sum()])
+
+
+def merge_check(asm, res, phi, group=None, rtol=1e-10):
+    """Does the row-distributed matrix (after the NCCL interface-row merge) hold exactly the contributions of all ranks?
+    Every rank assembles ITS OWN elements alone (single-GPU path, no halo, no merge); since every element belongs to one
+    rank, the sum over the ranks of any linear functional of those local matrices equals the functional of the global
+    matrix.  Three functionals with position-dependent weights over the GLOBAL dof keys (sum of the entries, two weighted
+    sums) are all-reduced and compared with the same functionals of the owned rows of the merged result.  Returns a dict
+    (ok, relative differences, totals) — bench.py prints it as "check" and fails on a mismatch."""
+    from .pipeline import CutAssembly
+    p = asm.part
+    dev = p.el_vtx.device
+    # merged result: owned rows, columns in local compressed numbering; keys of the local compressed dofs
+    keys = p.gid[res["dofmap"] >= 0]
+    a, b = res["n_lo"], res["n_lo"] + res["n_own"]
+    rp = res["rowptr"]
+    lo, hi = int(rp[a].item()), int(rp[b].item())
+    rows_local = rp[a:b + 1] - lo
+    ln = rows_local[1:] - rows_local[:-1]
+    rr = torch.repeat_interleave(torch.arange(a, b, device=dev), ln)
+    v, c = res["vals"][lo:hi], res["col"][lo:hi].long()
+    got = torch.stack([v.sum(), (v * _key_weight(keys[rr], 7919) * _key_weight(keys[c], 104729)).sum(),
+                       (v * _key_weight(keys[rr], 611953) * _key_weight(keys[c], 15485863)).sum(),
+                       torch.tensor(float(hi - lo), dtype=torch.float64, device=dev)])
+    # reference: own elements only, no halo, no merge
+    ne = p.ne_own
+    loc = CutAssembly(p.dim, p.el_vtx[:ne].contiguous(), p.vtx_xyz, p.el_dofs[:ne].contiguous(), p.ndof_loc, p.fe_order,
+                      ctx=asm.be.ctx).step(phi)
+    k2 = p.gid[loc["dofmap"] >= 0]
+    ref = _block_checksums(loc["rowptr"], loc["col"], loc["vals"], k2)
+    tot = torch.cat([got, ref])
+    if dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(tot, group=group)
+    g, r = tot[:4].tolist(), tot[4:].tolist()
+    scale = max(r[3], 1e-300)
+    rel = [abs(g[i] - r[i]) / scale for i in range(3)]
+    return {"ok": bool(max(rel) < rtol), "rel_diff": rel, "sum_entries": g[0], "sum_entries_ref": r[0], "nnz_owned_total": int(g[3]),
+            "sum_abs_ref": r[3], "tolerance": rtol,
+            "what": "sum over ranks of three linear functionals (weights from the global dof keys) of the owned rows of the merged "
+                    "matrix vs the same functionals of every rank's own elements assembled alone (no halo, no merge)"}
+
+
 # ------------------------------------------------------------------ CUDA compute backend
 class GpuBackend:
     """drives libxgpu.so (C ABI) — there is no CPU fallback"""
+
+    fused = True   # one-row-pass CSR (xgpu_csr_plan_rows + xgpu_csr_assemble_fused) where the shapes allow it
 
     def __init__(self, ctx=None):
         from . import ops
@@ -309,7 +369,10 @@ class GpuBackend:
         els, xyz = part.el_vtx, part.vtx_xyz
         order = 2 * p
         l_neg, l_if = l_neg.contiguous(), l_if.contiguous()
-        m_neg = ops.elmat_std(dim, p, l_neg, els, xyz, phi, order, TERMS_VOL, ctx=ctx)
+        if p <= 2 and self.fused:   # procedural batch: 7 coefficients per uncut element instead of its matrix
+            m_neg = ops.affine_coefs(dim, p, l_neg, els, xyz, order, TERMS_VOL, ctx=ctx)
+        else:
+            m_neg = ops.elmat_std(dim, p, l_neg, els, xyz, phi, order, TERMS_VOL, ctx=ctx)
         ra = ops.cutquad(dim, l_if, els, xyz, phi, ops.NEG, order, ctx=ctx)
         rb = ops.cutquad(dim, l_if, els, xyz, phi, ops.IF, order, ctx=ctx)
         m_if = ops.elmat_rule_pair(dim, p, l_if, els, xyz, phi, ra, TERMS_VOL, rb, TERMS_IF, ctx=ctx)
@@ -328,6 +391,14 @@ class GpuBackend:
     def csr(self, ndof, batches):
         ops = self.ops
         tables = [b[0] for b in batches]
+        if self.fused:
+            from ._lib import XgpuError
+            try:
+                plan = ops.csr_plan_rows(ndof, tables, ctx=self.ctx)
+                return ops.csr_assemble_fused(plan, batches)
+            except XgpuError as e:
+                if getattr(e, "code", 0) != ops.XGPU_ERR_UNSUPPORTED or any(isinstance(b[1], ops.AffineCoefs) for b in batches):
+                    raise
         plan = ops.csr_plan(ndof, tables, ctx=self.ctx)
         return ops.csr_assemble(plan, batches)
 
@@ -462,22 +533,57 @@ def structured_dof_keys(mesh, vg, nv1, NV, p, el_gid, v_owner=None, el_owner=Non
     return gid, (torch.cat(owner) if v_owner is not None else None)
 
 
-def make_slab_partition(n, world, rank, device, fe_order=2, radius=0.4, time_fe_order=None):
-    """Chain [0,1]^2 x [0,world] of `world` unit cubes, n^3 x 6 Kuhn tets each; rank r owns cube r
+def balanced_layers(n, world, radius=0.4, alpha=0.12):
+    """layer bounds (world + 1 ascending layer indices 0..n) of the strong split of the unit cube with the centred sphere:
+    contiguous z-slabs of (nearly) equal WORK, work of a layer = alpha * (all its elements: classification) + its elements
+    inside the sphere (assembly), from the analytic cross-section — SURVEY.md §8(e): the cut elements cluster in few
+    slabs, so the element ranges are weighted, not equal."""
+    import math
+    w = []
+    for k in range(n):
+        z = (k + 0.5) / n - 0.5
+        rr = radius * radius - z * z
+        w.append(alpha + (math.pi * rr if rr > 0 else 0.0))
+    tot = sum(w)
+    bounds, acc, nxt = [0], 0.0, 1
+    for k in range(n):
+        acc += w[k]
+        while nxt < world and acc >= tot * nxt / world and len(bounds) < world:
+            bounds.append(max(k + 1, bounds[-1] + 1))
+            nxt += 1
+    while len(bounds) < world:
+        bounds.append(bounds[-1] + 1)
+    bounds.append(n)
+    for i in range(world, 0, -1):   # every rank keeps at least one layer
+        bounds[i - 1] = min(bounds[i - 1], bounds[i] - 1)
+    return bounds
+
+
+def make_slab_partition(n, world, rank, device, fe_order=2, radius=0.4, time_fe_order=None, scaling="weak", bounds=None):
+    """scaling="weak": chain [0,1]^2 x [0,world] of `world` unit cubes, n^3 x 6 Kuhn tets each; rank r owns cube r
     (a contiguous element range of the global mesh) plus one halo layer of cells per neighbour.
     Level set: spheres of `radius` centred at (1/2, 1/2, j), j = 0..world for world > 1 (centres ON
     the slab interfaces, so the interface rows are active and each rank sees two half spheres = the
-    config-2 element counts), the centred sphere for world == 1."""
+    config-2 element counts), the centred sphere for world == 1.
+    scaling="strong": THE unit cube (n^3 x 6 tets, centred sphere = BASELINE config 2) cut into `world` z-slabs of whole
+    cell layers, `bounds` (default: balanced_layers) = the world + 1 layer indices; rank r owns layers bounds[r]..bounds[r+1]."""
     from . import meshes
     from .fes import H1
     from .pipeline import sphere_levelset
     if fe_order > 4:
         raise NotImplementedError("orders 1..4")
     lo, hi = (1 if rank > 0 else 0), (1 if rank < world - 1 else 0)
-    nzl = n + lo + hi
+    strong = scaling == "strong" and world > 1
+    if strong:
+        bounds = list(bounds) if bounds is not None else balanced_layers(n, world, radius)
+        assert len(bounds) == world + 1 and bounds[0] == 0 and bounds[-1] == n and all(b1 > b0 for b0, b1 in zip(bounds, bounds[1:]))
+        nzo, kbase, ntot = bounds[rank + 1] - bounds[rank], bounds[rank], n      # own layers, first own layer, layers of the global mesh
+    else:
+        nzo, kbase, ntot = n, rank * n, n * world
+    nzl = nzo + lo + hi
     mesh = meshes.MakeStructured3DMesh(nx=n, ny=n, nz=nzl, device=device)
-    # physical coordinates: local z in [0,1] covers global cells [rank*n - lo, (rank+1)*n + hi)
-    k0 = rank * n - lo
+    # physical coordinates: local layers cover the global cell layers [kbase - lo, kbase + nzo + hi)
+    k0 = kbase - lo
     pts = mesh.points.clone()
     nv1 = n + 1
     # z = K / n from the integer layer index K: bit-identical on every rank that holds the vertex
@@ -486,29 +592,34 @@ def make_slab_partition(n, world, rank, device, fe_order=2, radius=0.4, time_fe_
     # own elements first (cells lo .. lo+n-1), then halo
     ne_layer = 6 * n * n
     cell_k = torch.arange(mesh.ne, device=device) // ne_layer
-    own = (cell_k >= lo) & (cell_k < lo + n)
+    own = (cell_k >= lo) & (cell_k < lo + nzo)
     perm = torch.cat([torch.nonzero(own).reshape(-1), torch.nonzero(~own).reshape(-1)])
     el_vtx = mesh.elements[perm].contiguous()
-    el_rank = torch.where(cell_k[perm] < lo, rank - 1, torch.where(cell_k[perm] >= lo + n, rank + 1, rank)).to(torch.int32)
+    el_rank = torch.where(cell_k[perm] < lo, rank - 1, torch.where(cell_k[perm] >= lo + nzo, rank + 1, rank)).to(torch.int32)
     lmesh = meshes.Mesh(pts, el_vtx)
     V = H1(lmesh, order=fe_order)
     # global keys: vertex gid = i + (n+1)(j + (n+1)K); edge key from its two global vertex ids
     vloc = torch.arange(lmesh.nv, device=device, dtype=torch.int64)
     K = vloc // (nv1 * nv1) + k0
     vg = vloc % (nv1 * nv1) + nv1 * nv1 * K
-    NV = nv1 * nv1 * (n * world + 1)
-    v_owner = torch.where(K <= 0, torch.zeros_like(K), (K + n - 1) // n - 1).clamp(max=world - 1)
+    NV = nv1 * nv1 * (ntot + 1)
+    if strong:   # a vertex layer K belongs to the rank whose slab it closes from above: bounds[r] < K <= bounds[r+1] (K = 0: rank 0)
+        bt = torch.tensor(bounds[1:], device=device, dtype=torch.int64)
+        v_owner = torch.searchsorted(bt, K.clamp(min=0)).clamp(max=world - 1)
+    else:
+        v_owner = torch.where(K <= 0, torch.zeros_like(K), (K + n - 1) // n - 1).clamp(max=world - 1)
     e_loc = perm.to(torch.int64)                                   # local element id of the unpermuted local mesh
     el_gid = e_loc + 6 * n * n * k0                                # global element id (6 * global cell + path)
     gid, ent_owner = structured_dof_keys(lmesh, vg, nv1, NV, fe_order, el_gid, v_owner, el_rank.to(torch.int64))
     owner = ent_owner.to(torch.int32)
     halo_for = {}
-    own_cells_k = cell_k[perm][:6 * n ** 3]
+    ne_own = 6 * n * n * nzo
+    own_cells_k = cell_k[perm][:ne_own]
     if rank > 0:
         halo_for[rank - 1] = torch.nonzero(own_cells_k == lo).reshape(-1).to(torch.int32)
     if rank < world - 1:
-        halo_for[rank + 1] = torch.nonzero(own_cells_k == lo + n - 1).reshape(-1).to(torch.int32)
-    centers = [(.5, .5, .5)] if world == 1 else [(.5, .5, float(j)) for j in range(world + 1)]
+        halo_for[rank + 1] = torch.nonzero(own_cells_k == lo + nzo - 1).reshape(-1).to(torch.int32)
+    centers = [(.5, .5, .5)] if (world == 1 or strong) else [(.5, .5, float(j)) for j in range(world + 1)]
     phi = sphere_levelset(pts, centers, radius)
     if time_fe_order is not None:
         # space-time slab (config 5): time-major dof table, key = space key * nt + time node; the level set is the
@@ -523,7 +634,7 @@ def make_slab_partition(n, world, rank, device, fe_order=2, radius=0.4, time_fe_
         for t in ScalarTimeFE(time_fe_order).nodes():
             cy = 0.5 + 0.1 * math.sin(2 * math.pi * 0.25 * t)
             phis.append(sphere_levelset(pts, [(c[0], cy, c[2]) for c in centers], radius))
-        part = LocalPartition(3, el_vtx, 6 * n ** 3, el_rank, pts, el_dofs, V.ndof * nt, gid_st, owner_st, halo_for, fe_order, rank)
+        part = LocalPartition(3, el_vtx, ne_own, el_rank, pts, el_dofs, V.ndof * nt, gid_st, owner_st, halo_for, fe_order, rank)
         return part, torch.stack(phis).contiguous()
-    part = LocalPartition(3, el_vtx, 6 * n ** 3, el_rank, pts, V.el_dofs, V.ndof, gid, owner, halo_for, fe_order, rank)
+    part = LocalPartition(3, el_vtx, ne_own, el_rank, pts, V.el_dofs, V.ndof, gid, owner, halo_for, fe_order, rank)
     return part, phi

@@ -163,6 +163,7 @@ class CutAssembly:
                 hooks["need_dofs"](None)
             act = ops.dofs_of_elements(self.el_dofs, has, self.ndof_full, ctx=ctx)
             dofmap, ndof = ops.bitset_rank(act, self.ndof_full, ctx=ctx)
+            self._dofmap = dofmap
             t_neg = ops.gather_rows(self.el_dofs, l_neg, dofmap, ctx=ctx)
             t_if = ops.gather_rows(self.el_dofs, l_if, dofmap, ctx=ctx)
             t.mark("restrict")
@@ -173,7 +174,8 @@ class CutAssembly:
                 # Restrict(H1, hasneg) + the dof rows of the two batches + their transposed table: one sequence
                 if "need_dofs" in hooks:
                     hooks["need_dofs"](None)
-                _, nd_, tabs, pl = ops.restrict_plan(self.el_dofs, [l_neg, l_if], self.ndof_full, ctx=ctx)
+                dm, nd_, tabs, pl = ops.restrict_plan(self.el_dofs, [l_neg, l_if], self.ndof_full, ctx=ctx)
+                self._dofmap = dm
                 t.mark("restrict_plan")
                 return nd_, tabs[0], tabs[1], pl
 
@@ -239,7 +241,7 @@ class CutAssembly:
             hooks["values"](dict(vals=vals))
         out = dict(ndof=ndof, nnz=plan.nnz, n_neg=l_neg.numel(), n_if=l_if.numel(),
                    units=l_neg.numel() + l_if.numel(), rowptr=rowptr, col=col, vals=vals,
-                   bits=(bn, bp, bi), cut_ratio=cr, npts=npts)
+                   bits=(bn, bp, bi), cut_ratio=cr, npts=npts, dofmap=self._dofmap)
         if keep:
             out.update(l_neg=l_neg, l_if=l_if, t_neg=t_neg, t_if=t_if, m_neg=m_neg, m_if=m_if)
         return out

@@ -7,6 +7,9 @@
 #include "xoracle.h"
 #include <stdlib.h>
 #include <string.h>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
 
 static int cmp_i32(const void* a, const void* b)
 {
@@ -29,16 +32,36 @@ static void sort_i32(int32_t* a, int64_t n)
 int64_t xo_graph(int64_t ndof, int64_t nrows, int width, const int32_t* table,
                  int64_t* rowptr, int32_t* colidx)
 {
-  /* transposed table: dof -> table rows */
+  /* transposed table: dof -> table rows (ascending).  Histogram with atomic increments, then every thread fills the
+   * segments of its own dof range from a scan over the table (segments stay in ascending row order: the result does not
+   * depend on the thread count) */
   int64_t* cnt = (int64_t*)calloc(ndof + 1, sizeof(int64_t));
+#pragma omp parallel for schedule(static)
   for (int64_t r = 0; r < nrows; r++)
-    for (int k = 0; k < width; k++) { int32_t d = table[r * width + k]; if (d >= 0) cnt[d + 1]++; }
+    for (int k = 0; k < width; k++) {
+      int32_t d = table[r * width + k];
+      if (d >= 0) {
+#pragma omp atomic
+        cnt[d + 1]++;
+      }
+    }
   for (int64_t d = 0; d < ndof; d++) cnt[d + 1] += cnt[d];
   int64_t* pos = (int64_t*)malloc(sizeof(int64_t) * (ndof + 1));
   memcpy(pos, cnt, sizeof(int64_t) * (ndof + 1));
   int64_t* adj = (int64_t*)malloc(sizeof(int64_t) * (cnt[ndof] > 0 ? cnt[ndof] : 1));
-  for (int64_t r = 0; r < nrows; r++)
-    for (int k = 0; k < width; k++) { int32_t d = table[r * width + k]; if (d >= 0) adj[pos[d]++] = r; }
+#pragma omp parallel
+  {
+    int nt = 1, me = 0;
+#ifdef _OPENMP
+    nt = omp_get_num_threads(); me = omp_get_thread_num();
+#endif
+    const int64_t d0 = ndof * me / nt, d1 = ndof * (me + 1) / nt;
+    for (int64_t r = 0; r < nrows; r++)
+      for (int k = 0; k < width; k++) {
+        const int32_t d = table[r * width + k];
+        if (d >= d0 && d < d1) adj[pos[d]++] = r;
+      }
+  }
   /* rows are independent: pass 0 counts the unique columns of every row, pass 1 writes them
    * (the result does not depend on the thread count) */
   rowptr[0] = 0;
@@ -112,4 +135,23 @@ void xo_scatter_threads(int64_t ndof, int64_t nrows, int width, const int32_t* t
       }
     }
   }
+}
+
+/* threads the OpenMP loops of this library use (reported by bench.py next to the CPU numbers) */
+int xo_num_threads(void)
+{
+#ifdef _OPENMP
+  return omp_get_max_threads();
+#else
+  return 1;
+#endif
+}
+
+void xo_set_num_threads(int n)
+{
+#ifdef _OPENMP
+  if (n > 0) omp_set_num_threads(n);
+#else
+  (void)n;
+#endif
 }

@@ -272,6 +272,15 @@ def facet_patch_elmat(T1, T2, fe_order, order, coef, hpow):
     return m, nfail
 
 
+def num_threads():
+    """threads the OpenMP loops of libxoracle.so use"""
+    return int(lib().xo_num_threads())
+
+
+def set_num_threads(n):
+    lib().xo_set_num_threads(int(n))
+
+
 def graph(ndof, table):
     t = _i32(table)
     nrows, width = t.shape
