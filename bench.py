@@ -279,6 +279,7 @@ def run_gpu(args):
         check = merge_check(asm, res, phi)
     # ---- phase shares: instrumented steps (CUDA events around every phase, one stream), right after the timed loop
     nphase = 3
+    step_dev(PhaseTimer(True))   # untimed: the one-stream schedule allocates its own pool blocks on first use
     timers = [PhaseTimer(True) for _ in range(nphase)]
     for t in timers:
         res = step_dev(t)

@@ -52,7 +52,9 @@ int xgpu_set_stream(xgpu_ctx* ctx, void* cuda_stream);
  * instead of a persistent grid (for a low-priority side stream; default 0).  "csr_small": one-pass CSR, rows with few adjacent table rows on the thread-per-row
  * kernels (default 1).  "csr_warp": one-pass CSR, the other rows with at most 256 candidates on the warp-per-row kernels (default 1).
  * "csr_trips": one-pass CSR lane-group kernels, 2 = half-width lane groups with two columns per
- * lane (0 = policy).  "elmat_st_tp": space-time element
+ * lane (0 = policy).  "csr_closed_form": one-pass CSR, rows of procedural affine P2-tet batches from the closed-form barycentric
+ * expressions instead of the reference tensors (default 1; equal up to rounding).  "csr_fork": one-pass CSR, the warp-per-row kernel runs on an internal second stream next to the
+ * thread-per-row kernel (default 1; they take disjoint rows).  "elmat_st_tp": space-time element
  * matrices on the tensor-structured kernel where instantiated (default 1; 0 = always the generic kernel) */
 int xgpu_set_option(xgpu_ctx* ctx, const char* key, int value);
 /* Isoparametric mesh deformation — the state NGSolve keeps in the mesh (`mesh.SetDeformation(gf)`, set and

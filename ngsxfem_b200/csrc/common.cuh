@@ -40,6 +40,10 @@ struct xgpu_ctx {
                              // low-priority side stream then yields the SMs to the main stream block by block)
   int opt_csr_warp = 1;   // one-pass CSR: warp-per-row kernels (sorting network over the warp) for rows with <= 256 candidates
   int opt_csr_trips = 0;  // one-pass CSR: columns per lane (0 policy = 1 for rows up to 32 wide; 2: half-width lane groups)
+  int opt_csr_closed_form = 1;  // one-pass CSR: rows of affine P2 tets (mass + stiffness) in closed form instead of the reference tensors
+  int opt_csr_fork = 1;   // one-pass CSR: the warp-per-row kernel runs on an internal second stream next to the thread-per-row one
+  cudaStream_t aux_stream = nullptr;  // created on first use (same priority as `stream` at that time)
+  cudaEvent_t aux_fork = nullptr, aux_join = nullptr;
   int opt_st_tp = 1;  // space-time element matrices: tensor-structured kernel where instantiated (0: always the generic one)
   int64_t epoch = 0;  // bumped whenever a plan takes over the shared pattern scratch (slot 8)
   int64_t* h_pinned = nullptr;  // 16 x int64 pinned staging for host scalars
@@ -105,11 +109,39 @@ inline cudaError_t xgpu_d2h_small(void* dst_host_mapped, const void* src_dev, si
   return cudaGetLastError();
 }
 
-// record a per-element geometry error: keep the smallest failing element and its code
+// fork / join of the context's internal second stream: work launched between xgpu_aux_begin and xgpu_aux_end runs on
+// ctx->aux_stream, ordered after everything enqueued on ctx->stream so far; xgpu_aux_end makes ctx->stream wait for it.
+// Usage: cudaStream_t main = ctx->stream; xgpu_aux_begin(ctx); <launches use ctx->stream (= aux)>; xgpu_aux_end(ctx, main);
+inline cudaError_t xgpu_aux_begin(xgpu_ctx* ctx)
+{
+  cudaError_t e;
+  if (!ctx->aux_stream) {
+    int prio = 0;
+    if ((e = cudaStreamGetPriority(ctx->stream, &prio)) != cudaSuccess) return e;
+    if ((e = cudaStreamCreateWithPriority(&ctx->aux_stream, cudaStreamNonBlocking, prio)) != cudaSuccess) return e;
+    if ((e = cudaEventCreateWithFlags(&ctx->aux_fork, cudaEventDisableTiming)) != cudaSuccess) return e;
+    if ((e = cudaEventCreateWithFlags(&ctx->aux_join, cudaEventDisableTiming)) != cudaSuccess) return e;
+  }
+  if ((e = cudaEventRecord(ctx->aux_fork, ctx->stream)) != cudaSuccess) return e;
+  if ((e = cudaStreamWaitEvent(ctx->aux_stream, ctx->aux_fork, 0)) != cudaSuccess) return e;
+  ctx->stream = ctx->aux_stream;
+  return cudaSuccess;
+}
+inline cudaError_t xgpu_aux_end(xgpu_ctx* ctx, cudaStream_t main)
+{
+  ctx->stream = main;
+  cudaError_t e;
+  if ((e = cudaEventRecord(ctx->aux_join, ctx->aux_stream)) != cudaSuccess) return e;
+  return cudaStreamWaitEvent(main, ctx->aux_join, 0);
+}
+
+// record a per-element geometry error: keep the smallest failing element TOGETHER with its code — one 64-bit word
+// (element << 8 | -code) and ONE atomicMin, so concurrent failures cannot pair an element with another element's code.
+// `status` only flags that something failed (xgpu_get_status decodes the word).
 __device__ __forceinline__ void xgpu_record_error(int* status, unsigned long long* status_elem, int code, long long elem)
 {
-  unsigned long long old = atomicMin(status_elem, (unsigned long long)elem);
-  if ((unsigned long long)elem <= old) atomicExch(status, code);
+  atomicMin(status_elem, ((unsigned long long)elem << 8) | (unsigned long long)((-code) & 0xff));
+  *(volatile int*)status = code;   // any failing code: non-zero flag
 }
 
 // ---- device-wide exclusive scan (int32 counts -> int64 offsets), out has n+1 entries ----

@@ -27,7 +27,7 @@ struct xgpu_plan {
   int32_t* rowcnt = nullptr;      // counted plans: distinct columns per row
   // stored pattern of counted plans (csr_rows_small.cu / csr_rows_warp.cu): the values pass needs no sort
   unsigned char* pat_small = nullptr;  // 192 B records of the thread-per-row kernel, interleaved per 32 rows
-  unsigned char* pat_big = nullptr;    // 1280 B records of the warp-per-row kernel
+  unsigned char* pat_big = nullptr;    // 1536 B records of the warp-per-row kernel
   int32_t* bigslot = nullptr;          // ndof: record number of a warp-per-row row
   int64_t nbig_cap = 0;                // records allocated in pat_big
   int nbig = 0;                        // rows with more than 64 candidates (k_adj_sort)
@@ -64,6 +64,9 @@ int xg_rows_warp_ok(int width, int64_t ndof);
 size_t xg_rows_warp_record_bytes(int64_t nrows);
 int xg_rows_warp_run(xgpu_ctx* ctx, xgpu_plan* P, const BatchDev& bd, const double* tref, int ncoef, bool pattern, int small_na,
                      unsigned int* ticket, unsigned int* slotcount, int32_t* rowcnt, int* stats, int32_t* colidx, double* vals);
+
+// elmat.cu: is `tref` the library's own cached reference tensor of H1 order p on the dim-simplex (any integration order)?
+bool xg_reftensor_is(xgpu_ctx* ctx, const double* tref, int dim, int p);
 
 // csr.cu: sort the segments of a filled transposed table + statistics (synchronises)
 int xg_plan_finish(xgpu_ctx* ctx, xgpu_plan* P, bool want_candoff);

@@ -476,8 +476,13 @@ static int count_rows(xgpu_ctx* ctx, xgpu_plan* P, int64_t* nnz_host)
     XF_TRY(cudaGetLastError());
   }
   P->warp_cand = F.skip_cand;
+  // the two kernels take disjoint rows and are bound by different units (warp per row: latency / shuffles, thread per row:
+  // issue): with both present the warp-per-row one runs on the context's internal second stream
+  const bool fork = ctx->opt_csr_fork && F.skip_cand >= 0 && F.skip_na > 0;
   if (F.skip_cand >= 0) {
+    if (fork) XF_TRY(xgpu_aux_begin(ctx));
     rc = xg_rows_warp_run(ctx, P, P->bd, nullptr, 0, true, F.skip_na, (unsigned int*)sp + 1, slotcount, P->rowcnt, F.stats, nullptr, nullptr);
+    if (fork) { cudaError_t e_ = xgpu_aux_end(ctx, st); if (!rc && e_ != cudaSuccess) rc = xgpu_fail(ctx, XGPU_ERR_CUDA, cudaGetErrorString(e_)); }
     if (rc) return rc;
   }
   P->small_na = F.skip_na;
@@ -535,12 +540,15 @@ extern "C" int xgpu_csr_assemble_fused(xgpu_ctx* ctx, xgpu_plan* P, const xgpu_b
   rc = xgpu_scratch(ctx, 9, 64, &sp);
   if (rc) return rc;
   XGPU_CUDA(ctx, cudaMemsetAsync(sp, 0, 64, st));
-  if (F.skip_na > 0) {
-    rc = xg_rows_small_run(ctx, P, F.bd, tref, nproc ? ncoef : 0, false, nullptr, nullptr, colidx, vals);
+  const bool fork = ctx->opt_csr_fork && F.skip_cand >= 0 && F.skip_na > 0;
+  if (F.skip_cand >= 0) {
+    if (fork) XGPU_CUDA(ctx, xgpu_aux_begin(ctx));
+    rc = xg_rows_warp_run(ctx, P, F.bd, tref, nproc ? ncoef : 0, false, F.skip_na, (unsigned int*)sp + 1, nullptr, nullptr, nullptr, colidx, vals);
+    if (fork) { cudaError_t e_ = xgpu_aux_end(ctx, st); if (!rc && e_ != cudaSuccess) rc = xgpu_fail(ctx, XGPU_ERR_CUDA, cudaGetErrorString(e_)); }
     if (rc) return rc;
   }
-  if (F.skip_cand >= 0) {
-    rc = xg_rows_warp_run(ctx, P, F.bd, tref, nproc ? ncoef : 0, false, F.skip_na, (unsigned int*)sp + 1, nullptr, nullptr, nullptr, colidx, vals);
+  if (F.skip_na > 0) {
+    rc = xg_rows_small_run(ctx, P, F.bd, tref, nproc ? ncoef : 0, false, nullptr, nullptr, colidx, vals);
     if (rc) return rc;
   }
   if (P->maxcand <= F.skip_cand && !(F.skip_na > 0 && P->small_overflow)) return XGPU_OK;  // no row left for the lane-group hash kernel

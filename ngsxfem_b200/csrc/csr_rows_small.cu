@@ -16,6 +16,7 @@
 // The lane-group hash kernels of csr_fused.cu spend ~200 instructions per 30 contributions on per-step bookkeeping
 // (profiles/r02_notes.md); here the bookkeeping is per 32 rows.
 #include "csr.cuh"
+#include "h1.cuh"
 
 namespace {
 
@@ -53,6 +54,58 @@ __device__ __forceinline__ void bitonic_regs(unsigned (&r)[N])
           if ((i & size) == 0) { r[i] = lo; r[l] = hi; } else { r[i] = hi; r[l] = lo; }
         }
       }
+}
+
+// ---- row `loc` of the mass + stiffness matrix of an affine P2 tetrahedron in CLOSED FORM (h1.cuh basis: vertex hats
+// lam_v, edge functions -2 lam_a lam_b; reference tet lam = (x, y, z, 1-x-y-z), edges XG_TET_EDGE_A/B).
+// cf[0] = c_m |det F|, cf[1..6] = c_s |det F| G_ab (a <= b) as xgpu_affine_coefs writes them.  With the barycentric Gram
+// matrix  Gam_ij = grad lam_i . (c_s |det| G) grad lam_j  and  w(x,y) = 1 + delta_xy:
+//   vertex a , vertex c   :  cm w(a,c)/120 + Gam_ac/6
+//   vertex a , edge (c,d) : -cm (w(a,c)+w(a,d)-1)/360 - (Gam_ac+Gam_ad)/12
+//   edge (a,b), vertex c  : -cm (w(a,c)+w(b,c)-1)/360 - (Gam_ac+Gam_bc)/12
+//   edge (a,b), edge (c,d):  cm w(a,c)w(a,d)w(b,c)w(b,d)/1260 + (Gam_bd w(a,c) + Gam_bc w(a,d) + Gam_ad w(b,c) + Gam_ac w(b,d))/30
+// (integrals of barycentric monomials: alpha! / (|alpha|+3)! on the reference tet).  Equal to sum_m cf[m] tref[m][loc][:]
+// up to rounding (tools check: 3e-16); no table loads — the thread-per-row kernel is bound by shared-memory wavefronts
+// when every lane reads its own row of the 7 reference tensors (profiles/r02_notes.md).
+__device__ __forceinline__ void p2tet_row(const double (&cf)[8], int loc, double (&v)[10])
+{
+  const double cm = cf[0];
+  const double g03 = -(cf[1] + cf[2] + cf[3]), g13 = -(cf[2] + cf[4] + cf[5]), g23 = -(cf[3] + cf[5] + cf[6]);
+  const double g33 = -(g03 + g13 + g23);
+  const double R[4][4] = {{cf[1], cf[2], cf[3], g03}, {cf[2], cf[4], cf[5], g13}, {cf[3], cf[5], cf[6], g23}, {g03, g13, g23, g33}};
+  const int e = loc - 4;
+  const int a = (loc < 4) ? loc : (e < 3 ? 3 : (e < 5 ? 0 : 1));
+  const int b = (e < 3) ? e : (e == 3 ? 1 : 2);   // edge rows only
+  double ra[4], wa[4];
+#pragma unroll
+  for (int c = 0; c < 4; c++) {
+    ra[c] = (a == 0) ? R[0][c] : ((a == 1) ? R[1][c] : ((a == 2) ? R[2][c] : R[3][c]));
+    wa[c] = (a == c) ? 2.0 : 1.0;
+  }
+  if (loc < 4) {
+#pragma unroll
+    for (int c = 0; c < 4; c++) v[c] = cm * (wa[c] * (1.0 / 120.0)) + ra[c] * (1.0 / 6.0);
+#pragma unroll
+    for (int f = 0; f < 6; f++) {
+      const int c = XG_TET_EDGE_A(f), d = XG_TET_EDGE_B(f);
+      v[4 + f] = -(cm * ((wa[c] + wa[d] - 1.0) * (1.0 / 360.0)) + (ra[c] + ra[d]) * (1.0 / 12.0));
+    }
+    return;
+  }
+  double rb[4], wb[4];
+#pragma unroll
+  for (int c = 0; c < 4; c++) {
+    rb[c] = (b == 0) ? R[0][c] : ((b == 1) ? R[1][c] : R[2][c]);
+    wb[c] = (b == c) ? 2.0 : 1.0;
+  }
+#pragma unroll
+  for (int c = 0; c < 4; c++) v[c] = -(cm * ((wa[c] + wb[c] - 1.0) * (1.0 / 360.0)) + (ra[c] + rb[c]) * (1.0 / 12.0));
+#pragma unroll
+  for (int f = 0; f < 6; f++) {
+    const int c = XG_TET_EDGE_A(f), d = XG_TET_EDGE_B(f);
+    const double k = rb[d] * wa[c] + rb[c] * wa[d] + ra[d] * wb[c] + ra[c] * wb[d];
+    v[4 + f] = cm * ((wa[c] * wa[d]) * (wb[c] * wb[d]) * (1.0 / 1260.0)) + k * (1.0 / 30.0);
+  }
 }
 
 // ---- pattern pass.  W: width of every table row
@@ -142,16 +195,16 @@ __global__ void __launch_bounds__(XS_BLOCK, 4) k_rows_small_pattern(const SmallP
     rec[(4 + c) * 32] = make_uint4(Cs[(4 * c) * XS_LS], Cs[(4 * c + 1) * XS_LS], Cs[(4 * c + 2) * XS_LS], Cs[(4 * c + 3) * XS_LS]);
 }
 
-// ---- values pass.  NC: coefficients of the procedural batches (0: none)
-template <int W, int NC>
+// ---- values pass.  NC: coefficients of the procedural batches (0: none); CF: their rows in closed form (P2 tets)
+template <int W, int NC, bool CF>
 __global__ void __launch_bounds__(XS_BLOCK, 4) k_rows_small_values(const SmallPar P)
 {
   constexpr int NA = 64 / W;
   constexpr int WP = W + 1;  // padded row stride of the reference tensors in shared memory
-  constexpr int NTREF = (NC > 0) ? ((NC * W * WP + 1) & ~1) : 0;
+  constexpr int NTREF = (NC > 0 && !CF) ? ((NC * W * WP + 1) & ~1) : 0;
   extern __shared__ double sms[];
   const int tid = threadIdx.x, lane = tid & 31, wib = tid >> 5;
-  if (NC > 0) {
+  if (NC > 0 && !CF) {
     for (int k = tid; k < NC * W * W; k += XS_BLOCK) {
       const int m = k / (W * W), ij = k - m * W * W, i = ij / W, j = ij - i * W;
       sms[(m * W + i) * WP + j] = __ldg(P.tref + k);
@@ -222,13 +275,17 @@ __global__ void __launch_bounds__(XS_BLOCK, 4) k_rows_small_values(const SmallPa
           const double2 x = __ldg(c2 + m);
           cf[2 * m] = x.x; cf[2 * m + 1] = x.y;
         }
-        const double* __restrict__ tr = sms + loc * WP;
+        if constexpr (CF && W == 10 && NC == 7) {
+          p2tet_row(cf, loc, v);
+        } else {
+          const double* __restrict__ tr = sms + loc * WP;
 #pragma unroll
-        for (int j = 0; j < W; j++) {
-          double r = 0.0;
+          for (int j = 0; j < W; j++) {
+            double r = 0.0;
 #pragma unroll
-          for (int m = 0; m < NC; m++) r += cf[m] * tr[m * W * WP + j];
-          v[j] = r;
+            for (int m = 0; m < NC; m++) r += cf[m] * tr[m * W * WP + j];
+            v[j] = r;
+          }
         }
       } else {
         const double* __restrict__ mb = P.bd.mats[bi];
@@ -275,7 +332,7 @@ __global__ void __launch_bounds__(XS_BLOCK, 4) k_rows_small_values(const SmallPa
 inline unsigned nblk(int64_t n, int t) { return (unsigned)((n + t - 1) / t); }
 
 template <int W>
-int launch_small(xgpu_ctx* ctx, const SmallPar& S, int NC, bool pattern)
+int launch_small(xgpu_ctx* ctx, const SmallPar& S, int NC, bool pattern, bool closed_form)
 {
   const unsigned grid = nblk(S.ndof, XS_BLOCK);
   cudaStream_t st = ctx->stream;
@@ -283,17 +340,19 @@ int launch_small(xgpu_ctx* ctx, const SmallPar& S, int NC, bool pattern)
     const size_t smem = sizeof(unsigned) * (size_t)(XS_BLOCK / 32) * (64 * XS_LS + 32 * 17);
     k_rows_small_pattern<W><<<grid, XS_BLOCK, smem, st>>>(S);
   } else {
-    const size_t ntref = ((size_t)NC * W * (W + 1) + 1) & ~(size_t)1;
+    const bool cf = closed_form && W == 10 && NC == 7;
+    const size_t ntref = cf ? 0 : (((size_t)NC * W * (W + 1) + 1) & ~(size_t)1);
     const size_t smem = sizeof(double) * (ntref + (size_t)(XS_BLOCK / 32) * XS_STAGE);
-#define XS_LAUNCH(NCV)                                                                                                   \
+#define XS_LAUNCH(NCV, CFV)                                                                                              \
   {                                                                                                                      \
-    XGPU_CUDA(ctx, cudaFuncSetAttribute(k_rows_small_values<W, NCV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-    k_rows_small_values<W, NCV><<<grid, XS_BLOCK, smem, st>>>(S);                                                        \
+    XGPU_CUDA(ctx, cudaFuncSetAttribute(k_rows_small_values<W, NCV, CFV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    k_rows_small_values<W, NCV, CFV><<<grid, XS_BLOCK, smem, st>>>(S);                                                   \
   }
     bool done = false;
-    if (NC == 0) { XS_LAUNCH(0) done = true; }
-    if constexpr (W == 4 || W == 10) { if (NC == 7) { XS_LAUNCH(7) done = true; } }   // P1 / P2 tets
-    if constexpr (W == 6) { if (NC == 4) { XS_LAUNCH(4) done = true; } }              // P2 triangles
+    if (NC == 0) { XS_LAUNCH(0, false) done = true; }
+    if constexpr (W == 10) { if (NC == 7 && cf) { XS_LAUNCH(7, true) done = true; } }   // P2 tets, closed-form rows
+    if constexpr (W == 4 || W == 10) { if (NC == 7 && !done) { XS_LAUNCH(7, false) done = true; } }   // P1 / P2 tets
+    if constexpr (W == 6) { if (NC == 4) { XS_LAUNCH(4, false) done = true; } }              // P2 triangles
     if (!done) return xgpu_fail(ctx, XGPU_ERR_UNSUPPORTED, "csr small rows: coefficient count");
 #undef XS_LAUNCH
   }
@@ -324,15 +383,17 @@ size_t xg_rows_small_record_bytes(int64_t ndof) { return (size_t)((ndof + 31) / 
 int xg_rows_small_run(xgpu_ctx* ctx, xgpu_plan* P, const BatchDev& bd, const double* tref, int ncoef, bool pattern,
                       int32_t* rowcnt, int* stats, int32_t* colidx, double* vals)
 {
+  // closed-form rows only when the reference tensors are the library's own P2-tet tensors (the formula is THAT basis)
+  const bool cfm = !pattern && ctx->opt_csr_closed_form && tref && xg_reftensor_is(ctx, tref, 3, 2);
   SmallPar S;
   S.ndof = (int)P->ndof;
   S.adj_ptr = P->adj_ptr; S.adj = P->adj; S.bd = bd; S.tref = tref;
   S.rowptr = P->rowptr; S.rowcnt = rowcnt; S.stats = stats; S.records = (uint4*)P->pat_small; S.colidx = colidx; S.vals = vals;
   switch (P->wmax) {
-    case 4: return launch_small<4>(ctx, S, ncoef, pattern);
-    case 6: return launch_small<6>(ctx, S, ncoef, pattern);
-    case 10: return launch_small<10>(ctx, S, ncoef, pattern);
-    case 12: return launch_small<12>(ctx, S, ncoef, pattern);
+    case 4: return launch_small<4>(ctx, S, ncoef, pattern, cfm);
+    case 6: return launch_small<6>(ctx, S, ncoef, pattern, cfm);
+    case 10: return launch_small<10>(ctx, S, ncoef, pattern, cfm);
+    case 12: return launch_small<12>(ctx, S, ncoef, pattern, cfm);
   }
   return xgpu_fail(ctx, XGPU_ERR_UNSUPPORTED, "csr small rows: width");
 }

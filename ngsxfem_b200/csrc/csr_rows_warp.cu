@@ -6,10 +6,12 @@
 //   * duplicates are runs of the sorted sequence: run heads = the row's columns (ascending), number of heads = row
 //     length (count pass); inside a run the candidates are in (batch, table row, local index) order, the summation
 //     order of a sequential AddElementMatrix loop;
-//   * full pass: every lane fetches / generates the values of its 8 candidates (procedural affine batches: the element's
-//     coefficients x the reference tensors in shared memory), walks them in order and stores a run's sum at its end.
-//     Runs that continue over a lane boundary get the running sum of the previous lane as carry — resolved
-//     by a short shuffle iteration, so the result has the bits of the sequential order (= the two-pass path).
+//   * the pattern pass stores, per row, the candidate indices in SORTED order (256 bytes), the start of every run (one byte
+//     per column) and the columns: the row's record;
+//   * values pass: every lane fetches / generates the values of its 8 candidates in candidate order (procedural affine
+//     batches: the element's coefficients x the reference tensors in shared memory) into shared memory; then ONE LANE PER
+//     COLUMN sums its run front to back from a register (the loads do not depend on the sum: no load-add-store chain
+//     through shared memory) — the result has the bits of the sequential order (= the two-pass path).
 // The lane-group hash kernel of csr_fused.cu needs ~2200 instructions per such row (24 sequential steps with 10 of 32
 // lanes, rank sort); it remains the fallback for rows with more than 256 candidates.
 #include "csr.cuh"
@@ -20,7 +22,7 @@ namespace {
 #define XW_WARPS 4
 #define XW_KPL 8  // keys per lane: 256 candidates per row
 
-#define XW_RECB 1280  // bytes of a row record: 256 position bytes + 256 columns
+#define XW_RECB 1536  // bytes of a row record: 256 sorted candidate indices + 256 run starts + 256 columns
 
 struct WarpPar {
   int ndof, small_na;
@@ -90,11 +92,11 @@ __device__ __forceinline__ void sort256(unsigned (&K)[XW_KPL], int lane)
 template <int W>
 __global__ void __launch_bounds__(XW_WARPS * 32) k_rows_warp_pattern(const WarpPar P)
 {
-  __shared__ unsigned int pos_sm[XW_WARPS][64];   // 256 position bytes per warp
+  __shared__ unsigned int rs_sm[XW_WARPS][64];    // 256 run-start bytes per warp
   __shared__ int cols_sm[XW_WARPS][32 * XW_KPL];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const unsigned FULL = 0xffffffffu;
-  unsigned char* pos_b = reinterpret_cast<unsigned char*>(pos_sm[wib]);  // aliases pos_sm: no __restrict__
+  unsigned char* rs_b = reinterpret_cast<unsigned char*>(rs_sm[wib]);  // aliases rs_sm: no __restrict__
   int* __restrict__ cols_s = cols_sm[wib];
   int longest = 0;
   for (;;) {
@@ -111,7 +113,7 @@ __global__ void __launch_bounds__(XW_WARPS * 32) k_rows_warp_pattern(const WarpP
       nal = (int)(__ldg(P.adj_ptr + dl + 1) - al);
     }
     const bool small = nal >= 1 && nal <= P.small_na;  // rows of the thread-per-row kernel
-    const bool mine = dl < P.ndof && !small && nal * W < 32 * XW_KPL;  // < 256 candidates: position 255 stays free as the "no dof" mark
+    const bool mine = dl < P.ndof && !small && nal * W < 32 * XW_KPL;  // < 256 candidates: run starts and indices fit a byte
     if (mine && nal == 0) P.rowcnt[dl] = 0;
     unsigned todo = __ballot_sync(FULL, mine && nal > 0);
     while (todo) {
@@ -134,14 +136,15 @@ __global__ void __launch_bounds__(XW_WARPS * 32) k_rows_warp_pattern(const WarpP
           if (c >= 0) K[k] = ((unsigned)c << 8) | (unsigned)idx;
         }
       }
-      pos_sm[wib][lane] = 0xffffffffu; pos_sm[wib][lane + 32] = 0xffffffffu;  // 255: the candidate holds no dof
       sort256(K, lane);
       // runs: heads (first key of an equal-column run)
       const unsigned prevlast = __shfl_up_sync(FULL, K[XW_KPL - 1], 1);
       unsigned fresh = 0u;
+      int nval = 0;
 #pragma unroll
       for (int k = 0; k < XW_KPL; k++) {
         if (K[k] != 0xffffffffu) {
+          nval++;
           const unsigned pk = (k == 0) ? ((lane == 0) ? 0xffffffffu : prevlast) : K[k - 1];
           if ((pk >> 8) != (K[k] >> 8) || (k == 0 && lane == 0)) fresh |= 1u << k;
         }
@@ -154,6 +157,7 @@ __global__ void __launch_bounds__(XW_WARPS * 32) k_rows_warp_pattern(const WarpP
         if (lane >= s) incl += y;
       }
       const int nr = __shfl_sync(FULL, incl, 31);
+      const int nvalid = __reduce_add_sync(FULL, nval);   // the valid keys are the first nvalid of the sorted sequence
       unsigned slot = 0;
       if (lane == 0) {
         slot = atomicAdd(P.slotcount, 1u);
@@ -164,20 +168,22 @@ __global__ void __launch_bounds__(XW_WARPS * 32) k_rows_warp_pattern(const WarpP
       longest = max(longest, nr);
       __syncwarp();
       {
-        int q = incl - nf - 1;  // run the lane's first key continues (head in an earlier lane)
+        int q = incl - nf;  // index of the lane's first head
 #pragma unroll
         for (int k = 0; k < XW_KPL; k++) {
-          if (K[k] != 0xffffffffu) {
-            if ((fresh >> k) & 1u) { q++; cols_s[q] = (int)(K[k] >> 8); }
-            pos_b[K[k] & 255u] = (unsigned char)q;
-          }
+          if ((fresh >> k) & 1u) { cols_s[q] = (int)(K[k] >> 8); rs_b[q] = (unsigned char)(lane * XW_KPL + k); q++; }
         }
+        if (lane == 31) rs_b[nr] = (unsigned char)nvalid;   // nr <= nvalid <= 255
       }
       __syncwarp();
       if (slot < P.slotcap) {
         unsigned char* __restrict__ rec = P.records + (size_t)slot * XW_RECB;
-        reinterpret_cast<uint2*>(rec)[lane] = make_uint2(pos_sm[wib][2 * lane], pos_sm[wib][2 * lane + 1]);
-        int* __restrict__ rc = reinterpret_cast<int*>(rec + 256);
+        // sorted candidate indices: 8 bytes per lane, straight from the registers
+        reinterpret_cast<uint2*>(rec)[lane] =
+            make_uint2((K[0] & 255u) | ((K[1] & 255u) << 8) | ((K[2] & 255u) << 16) | ((K[3] & 255u) << 24),
+                       (K[4] & 255u) | ((K[5] & 255u) << 8) | ((K[6] & 255u) << 16) | ((K[7] & 255u) << 24));
+        reinterpret_cast<uint2*>(rec + 256)[lane] = make_uint2(rs_sm[wib][2 * lane], rs_sm[wib][2 * lane + 1]);
+        int* __restrict__ rc = reinterpret_cast<int*>(rec + 512);
         for (int i = lane; i < nr; i += 32) rc[i] = cols_s[i];
       }
       __syncwarp();
@@ -189,9 +195,10 @@ __global__ void __launch_bounds__(XW_WARPS * 32) k_rows_warp_pattern(const WarpP
 
 // ---- values pass: one row per warp at a time, small footprint (high occupancy hides the dependent global loads).
 // Phase 1: the values of the row's candidates, fetched / generated in candidate order (neighbouring lanes share the
-// adjacency entry and the element's coefficients: few distinct cache lines per load), and the row's position bytes go to
-// shared memory.  Phase 2: the adjacent elements one after the other, lane j adds value (t, j) at its position — the
-// summation order of a sequential AddElementMatrix loop.  Phase 3: columns (from the record) and values out.
+// adjacency entry and the element's coefficients: few distinct cache lines per load) into shared memory; the sorted
+// candidate indices and the run starts of the row's record go there too.  Phase 2: lane q sums run q (the contributions to
+// column q, in candidate order = the summation order of a sequential AddElementMatrix loop) in a register and stores
+// column + value.
 template <int W, int NC>
 __global__ void __launch_bounds__(XW_WARPS * 32) k_rows_warp_values(const WarpPar P)
 {
@@ -204,10 +211,9 @@ __global__ void __launch_bounds__(XW_WARPS * 32) k_rows_warp_values(const WarpPa
     for (int k = threadIdx.x; k < NC * W * W; k += blockDim.x) smw[k] = __ldg(P.tref + k);
     __syncthreads();
   }
-  const int AS = P.accstride;
-  double* vals_w = smw + NTREF + (size_t)wib * (NCAND + AS + NCAND / 8);
-  double* acc_w = vals_w + NCAND;
-  unsigned char* pos_w = reinterpret_cast<unsigned char*>(acc_w + AS);
+  double* vals_w = smw + NTREF + (size_t)wib * (NCAND + NCAND / 4);
+  unsigned char* sidx_w = reinterpret_cast<unsigned char*>(vals_w + NCAND);   // 256 sorted candidate indices
+  unsigned char* rs_w = sidx_w + NCAND;                                       // 256 run starts
   for (;;) {
     unsigned base = 0;
     if (lane == 0) base = atomicAdd(P.ticket, 32u);
@@ -232,55 +238,64 @@ __global__ void __launch_bounds__(XW_WARPS * 32) k_rows_warp_values(const WarpPa
       const long long a = __shfl_sync(FULL, al, src), rowbase = __shfl_sync(FULL, rbl, src);
       const int na = __shfl_sync(FULL, nal, src), nr = __shfl_sync(FULL, nrl, src);
       const unsigned char* __restrict__ rec = P.records + (size_t)__shfl_sync(FULL, sll, src) * XW_RECB;
-      const int cand = na * W;
-      // ---- phase 1
-      reinterpret_cast<uint2*>(pos_w)[lane] = __ldg(reinterpret_cast<const uint2*>(rec) + lane);
-      for (int i = lane; i < nr; i += 32) acc_w[i] = 0.0;
-#pragma unroll 2
-      for (int k = 0; k < XW_KPL; k++) {
-        const int idx = k * 32 + lane;
-        if (idx < cand) {
-          const int t = idx / W, j = idx - t * W;
-          const long long e = __ldg(P.adj + a + t);
-          const int bi = XG_ADJ_BATCH(e);
-          const size_t row = (size_t)XG_ADJ_ROW(e);
-          const int loc = XG_ADJ_LOC(e);
-          double val = 0.0;
-          const double* __restrict__ cfp = (NC > 0) ? P.bd.coefs[bi] : nullptr;
-          if (NC > 0 && cfp) {
-            const double2* __restrict__ c2 = reinterpret_cast<const double2*>(cfp + row * 8);
-            double cf[8];
+      // ---- phase 1: lane t takes adjacent element t — ONE coalesced load of the row's adjacency entries, then every lane's
+      // coefficient / matrix-row loads are independent of each other (two memory latencies per row, not two per candidate)
+      reinterpret_cast<uint2*>(sidx_w)[lane] = __ldg(reinterpret_cast<const uint2*>(rec) + lane);
+      reinterpret_cast<uint2*>(rs_w)[lane] = __ldg(reinterpret_cast<const uint2*>(rec + 256) + lane);
+      for (int t = lane; t < na; t += 32) {
+        const long long e = __ldg(P.adj + a + t);
+        const int bi = XG_ADJ_BATCH(e);
+        const size_t row = (size_t)XG_ADJ_ROW(e);
+        const int loc = XG_ADJ_LOC(e);
+        double* __restrict__ vout = vals_w + t * W;
+        const double* __restrict__ cfp = (NC > 0) ? P.bd.coefs[bi] : nullptr;
+        if (NC > 0 && cfp) {
+          const double2* __restrict__ c2 = reinterpret_cast<const double2*>(cfp + row * 8);
+          double cf[8];
 #pragma unroll
-            for (int m = 0; m < (NC + 1) / 2; m++) {
-              const double2 x = __ldg(c2 + m);
-              cf[2 * m] = x.x; cf[2 * m + 1] = x.y;
-            }
-            const double* __restrict__ tr = smw + loc * W + j;
-#pragma unroll
-            for (int m = 0; m < NC; m++) val += cf[m] * tr[m * W * W];
-          } else {
-            const double* __restrict__ mb = P.bd.mats[bi];
-            if (mb) val = __ldg(mb + (row * W + loc) * W + j);  // else: sparsity only (explicit zero)
+          for (int m = 0; m < (NC + 1) / 2; m++) {
+            const double2 x = __ldg(c2 + m);
+            cf[2 * m] = x.x; cf[2 * m + 1] = x.y;
           }
-          vals_w[idx] = val;
+          const double* __restrict__ tr = smw + loc * W;
+#pragma unroll
+          for (int j = 0; j < W; j++) {
+            double val = 0.0;
+#pragma unroll
+            for (int m = 0; m < NC; m++) val += cf[m] * tr[m * W * W + j];
+            vout[j] = val;
+          }
+        } else {
+          const double* __restrict__ mb = P.bd.mats[bi];
+          if (mb) {
+            const double* __restrict__ mrow = mb + (row * W + loc) * W;
+            if ((W & 1) == 0) {
+              double2 x[W / 2];
+#pragma unroll
+              for (int j = 0; j < W / 2; j++) x[j] = __ldg(reinterpret_cast<const double2*>(mrow) + j);
+#pragma unroll
+              for (int j = 0; j < W / 2; j++) { vout[2 * j] = x[j].x; vout[2 * j + 1] = x[j].y; }
+            } else {
+#pragma unroll
+              for (int j = 0; j < W; j++) vout[j] = __ldg(mrow + j);
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < W; j++) vout[j] = 0.0;  // sparsity only (explicit zeros)
+          }
         }
       }
       __syncwarp();
-      // ---- phase 2: lane j adds value (t, j)
-      if (lane < W) {
-        for (int t = 0; t < na; t++) {
-          const int idx = t * W + lane;
-          const int p = pos_w[idx];
-          if (p != 255) acc_w[p] += vals_w[idx];   // the lanes' positions are distinct; the next t follows in program order
-        }
-      }
-      __syncwarp();
-      // ---- phase 3
+      // ---- phase 2: lane q sums run q
       {
-        const int* __restrict__ rc = reinterpret_cast<const int*>(rec + 256);
-        for (int i = lane; i < nr; i += 32) {
-          P.colidx[rowbase + i] = __ldg(rc + i);
-          P.vals[rowbase + i] = acc_w[i];
+        const int* __restrict__ rc = reinterpret_cast<const int*>(rec + 512);
+        for (int q = lane; q < nr; q += 32) {
+          const int c = __ldg(rc + q);
+          const int g0 = rs_w[q], g1 = rs_w[q + 1];
+          double sum = 0.0;
+          for (int g = g0; g < g1; g++) sum += vals_w[sidx_w[g]];
+          P.colidx[rowbase + q] = c;
+          P.vals[rowbase + q] = sum;
         }
       }
       __syncwarp();
@@ -299,7 +314,7 @@ int launch_warp(xgpu_ctx* ctx, const WarpPar& S, int NC, bool pattern)
   if (pattern) {
     k_rows_warp_pattern<W><<<grid, XW_WARPS * 32, 0, st>>>(S);
   } else {
-    const size_t smem = sizeof(double) * ((size_t)NC * W * W + (size_t)XW_WARPS * (32 * XW_KPL + S.accstride + 32 * XW_KPL / 8));
+    const size_t smem = sizeof(double) * ((size_t)NC * W * W + (size_t)XW_WARPS * (32 * XW_KPL + 32 * XW_KPL / 4));
 #define XW_LAUNCH(NCV)                                                                                                  \
   {                                                                                                                     \
     XGPU_CUDA(ctx, cudaFuncSetAttribute(k_rows_warp_values<W, NCV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \

@@ -178,6 +178,9 @@ extern "C" void xgpu_destroy(xgpu_ctx* ctx)
   cudaStreamSynchronize(ctx->stream);
   for (auto& kv : ctx->rules) { if (kv.second.d_pts) cudaFree(kv.second.d_pts); if (kv.second.d_wts) cudaFree(kv.second.d_wts); }
   for (auto& kv : ctx->reftensors) if (kv.second) cudaFree(kv.second);
+  if (ctx->aux_stream) { cudaStreamSynchronize(ctx->aux_stream); cudaStreamDestroy(ctx->aux_stream); }
+  if (ctx->aux_fork) cudaEventDestroy(ctx->aux_fork);
+  if (ctx->aux_join) cudaEventDestroy(ctx->aux_join);
   if (ctx->d_status) cudaFree(ctx->d_status);
   if (ctx->d_status_elem) cudaFree(ctx->d_status_elem);
   if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
@@ -202,6 +205,8 @@ extern "C" int xgpu_set_option(xgpu_ctx* ctx, const char* key, int value)
   if (std::string(key) == "csr_small") { ctx->opt_csr_small = value != 0; return XGPU_OK; }
   if (std::string(key) == "short_blocks") { ctx->opt_short_blocks = value != 0; return XGPU_OK; }
   if (std::string(key) == "csr_warp") { ctx->opt_csr_warp = value != 0; return XGPU_OK; }
+  if (std::string(key) == "csr_closed_form") { ctx->opt_csr_closed_form = value != 0; return XGPU_OK; }
+  if (std::string(key) == "csr_fork") { ctx->opt_csr_fork = value != 0; return XGPU_OK; }
   if (std::string(key) == "csr_trips") { ctx->opt_csr_trips = value == 2 ? 2 : 0; return XGPU_OK; }
   if (std::string(key) == "elmat_st_tp") { ctx->opt_st_tp = value != 0; return XGPU_OK; }
   return xgpu_fail(ctx, XGPU_ERR_ARG, "xgpu_set_option: unknown key");
@@ -246,8 +251,10 @@ extern "C" int xgpu_get_status(xgpu_ctx* ctx, int* code_host, int64_t* elem_host
   XGPU_CUDA(ctx, xgpu_d2h_small(ctx->h_pinned + 1, ctx->d_status_elem, sizeof(unsigned long long), ctx->stream));
   XGPU_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   int code = *(int*)ctx->h_pinned;
+  const unsigned long long word = ctx->h_pinned[1];   // (element << 8 | -code) of the smallest failing element
+  if (code && word != ~0ull) code = -(int)(word & 0xff);
   if (code_host) *code_host = code;
-  if (elem_host) *elem_host = code ? ctx->h_pinned[1] : -1;
+  if (elem_host) *elem_host = (code && word != ~0ull) ? (int64_t)(word >> 8) : -1;
   return XGPU_OK;
 }
 

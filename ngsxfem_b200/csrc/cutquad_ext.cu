@@ -212,7 +212,29 @@ __device__ __forceinline__ void time_nodes(int order, double* nd)
   if (order == 1) { nd[0] = 0.0; nd[1] = 1.0; return; }
   if (order == 2) { nd[0] = 0.0; nd[1] = 0.5; nd[2] = 1.0; return; }
   if (order == 3) { nd[0] = 0.0; nd[1] = 0.5 * (1.0 - 1.0 / sqrt(5.0)); nd[2] = 0.5 * (1.0 + 1.0 / sqrt(5.0)); nd[3] = 1.0; return; }
-  for (int i = 0; i <= order; i++) nd[i] = 0.5 * (1.0 - cos(3.14159265358979323846 * i / order));
+  if (order == 4) {  // SpaceTimeFE.cpp:271-272 (Gauss-Lobatto)
+    nd[0] = 0.0; nd[1] = 0.5 * (1.0 - sqrt(3.0 / 7.0)); nd[2] = 0.5; nd[3] = 0.5 * (1.0 + sqrt(3.0 / 7.0)); nd[4] = 1.0; return;
+  }
+  if (order == 5) {  // SpaceTimeFE.cpp:273-278
+    const double a = sqrt(1.0 / 3.0 + 2.0 * sqrt(7.0) / 21.0), b = sqrt(1.0 / 3.0 - 2.0 * sqrt(7.0) / 21.0);
+    nd[0] = 0.0; nd[1] = 0.5 * (1.0 - a); nd[2] = 0.5 * (1.0 - b); nd[3] = 0.5 * (1.0 + b); nd[4] = 0.5 * (1.0 + a); nd[5] = 1.0; return;
+  }
+  // order >= 6: Gauss-Lobatto-Legendre points, Newton on x P_N - P_{N-1} from the Chebyshev-Lobatto start
+  // (CalcLobattoPointsRec, SpaceTimeFE.cpp:229-256); rare orders, every thread recomputes them
+  const int N = order;
+  for (int j = 0; j <= N; j++) {
+    double x = cos(3.14159265358979323846 * (double)j / N);
+    for (int it = 0; it < 100; it++) {
+      double pm = 1.0, p = x;
+      for (int k = 1; k < N; k++) { const double pn = ((2.0 * k + 1.0) * (x * p) - (double)k * pm) / ((double)k + 1.0); pm = p; p = pn; }
+      const double xn = x - (x * p - pm) / (N * p);
+      const bool done = fabs(xn - x) <= 1e-20;
+      x = xn;
+      if (done) break;
+    }
+    nd[j] = 0.5 * (1.0 - x);
+  }
+  nd[0] = 0.0; nd[N] = 1.0;
 }
 
 __device__ __forceinline__ void time_shapes(int order, const double* nd, double t, double* sh)

@@ -101,6 +101,13 @@ int get_reftensor(xgpu_ctx* ctx, int dim, int p, int order, const double** out)
 
 }  // namespace
 
+bool xg_reftensor_is(xgpu_ctx* ctx, const double* tref, int dim, int p)
+{
+  for (const auto& kv : ctx->reftensors)
+    if (kv.second == (const void*)tref && kv.first / 10000 == dim && (kv.first / 100) % 100 == p) return true;
+  return false;
+}
+
 extern "C" int xgpu_elmat_rule(xgpu_ctx* ctx, int dim, int fe_order, int64_t n, const int32_t* elems,
                                const int32_t* el_vtx, const double* vtx_xyz, const double* phi,
                                const int64_t* offsets, const double* pts, const double* wts,

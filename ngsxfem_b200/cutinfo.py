@@ -257,6 +257,9 @@ class CutInfo:
 
     def GetElementsWithThresholdContribution(self, domain_type=NEG, threshold=1.0, vb=VOL):
         """xfem/cutinfo.cpp:263-284"""
+        if vb == BND:   # cut_ratio_of_element[vb], ne = GetNE(vb)
+            cr = self._bnd_or_raise()[2]
+            return BitArray(int(cr.numel()), words=ops.threshold_elements(cr, int(domain_type), threshold))
         return BitArray(self.mesh.ne, words=ops.threshold_elements(self.cut_ratio, int(domain_type), threshold))
 
 

@@ -109,6 +109,8 @@ class Proxy:
     def __sub__(self, o):
         if isinstance(o, Proxy) and o.other and not self.other and self.op == OP_ID and o.op == OP_ID \
                 and o.is_test == self.is_test:
+            if (self.scal.c, self.scal.hpow) != (o.scal.c, o.scal.hpow):   # 2*u - u.Other() is not a scaled jump
+                raise XgpuError("unsupported difference of proxies: both sides of u - u.Other() must carry the same factor")
             return Proxy(self.space, self.is_test, OP_JUMP, self.scal)
         raise XgpuError("unsupported difference of proxies (menu: u - u.Other())")
 

@@ -11,6 +11,8 @@
 inputs; `step_host()` runs it from pinned HOST buffers with the host<->device copies inside
 (the e2e leg of bench.py).  Used by bench.py, __graft_entry__.smoke() and the parity tests.
 """
+import os
+
 import torch
 
 from . import ops
@@ -59,10 +61,11 @@ def _side_context(dev):
     """per device: a LOW-priority (stream, xgpu context) pair for the concurrent cut-element branch (its kernels use
     short-lived blocks, so they fill whatever the main stream leaves free) and a HIGH-priority pair for the main chain"""
     if dev.index not in _SIDE:
-        lo, hi = torch.cuda.Stream(dev, priority=0), torch.cuda.Stream(dev, priority=-1)
+        swap = os.environ.get("XGPU_SIDE_PRIO", "low") == "high"   # experiment switch (tools/perf_overlap.py)
+        lo, hi = torch.cuda.Stream(dev, priority=-1 if swap else 0), torch.cuda.Stream(dev, priority=0 if swap else -1)
         with torch.cuda.stream(lo):
             c_lo = Ctx(dev.index)
-            c_lo.set_option("short_blocks", 1)
+            c_lo.set_option("short_blocks", 0 if swap else 1)
         with torch.cuda.stream(hi):
             c_hi = Ctx(dev.index)
         _SIDE[dev.index] = (lo, c_lo, hi, c_hi)

@@ -162,6 +162,8 @@ class STProxy:
     def __sub__(self, o):
         if isinstance(o, STProxy) and o.other and not self.other and self.op == OP_ID and o.op == OP_ID \
                 and o.is_test == self.is_test and o.fixt == self.fixt:
+            if (self.scal.c, self.scal.hpow) != (o.scal.c, o.scal.hpow):
+                raise XgpuError("unsupported difference of proxies: both sides of u - u.Other() must carry the same factor")
             return STProxy(self.space, self.is_test, OP_JUMP, self.scal, self.fixt)
         raise XgpuError("unsupported difference of proxies (menu: u - u.Other())")
 

@@ -393,7 +393,29 @@ static void time_nodes(int order, double* nodes)
   if (order == 3) { /* Gauss-Lobatto on [0,1] */
     nodes[0] = 0; nodes[1] = 0.5 * (1.0 - 1.0 / sqrt(5.0)); nodes[2] = 0.5 * (1.0 + 1.0 / sqrt(5.0)); nodes[3] = 1; return;
   }
-  for (int i = 0; i <= order; i++) nodes[i] = 0.5 * (1.0 - cos(M_PI * i / order));
+  if (order == 4) { /* SpaceTimeFE.cpp:271-272 */
+    nodes[0] = 0; nodes[1] = 0.5 * (1.0 - sqrt(3.0 / 7.0)); nodes[2] = 0.5; nodes[3] = 0.5 * (1.0 + sqrt(3.0 / 7.0)); nodes[4] = 1; return;
+  }
+  if (order == 5) { /* SpaceTimeFE.cpp:273-278 */
+    const double a = sqrt(1.0 / 3.0 + 2.0 * sqrt(7.0) / 21.0), b = sqrt(1.0 / 3.0 - 2.0 * sqrt(7.0) / 21.0);
+    nodes[0] = 0; nodes[1] = 0.5 * (1.0 - a); nodes[2] = 0.5 * (1.0 - b); nodes[3] = 0.5 * (1.0 + b); nodes[4] = 0.5 * (1.0 + a); nodes[5] = 1; return;
+  }
+  /* order >= 6: Gauss-Lobatto-Legendre points by Newton's method on (x P_N - P_{N-1}), started from the Chebyshev-Lobatto
+   * points (CalcLobattoPointsRec, SpaceTimeFE.cpp:229-256); every node iterates on its own */
+  const int N = order;
+  for (int j = 0; j <= N; j++) {
+    double x = cos(M_PI * (double)j / N);
+    for (int it = 0; it < 100; it++) {
+      double pm = 1.0, p = x;                       /* P_0, P_1 */
+      for (int k = 1; k < N; k++) { const double pn = ((2.0 * k + 1.0) * (x * p) - (double)k * pm) / ((double)k + 1.0); pm = p; p = pn; }
+      const double xn = x - (x * p - pm) / (N * p);
+      const int done = fabs(xn - x) <= 1e-20;
+      x = xn;
+      if (done) break;
+    }
+    nodes[j] = 0.5 * (1.0 - x);
+  }
+  nodes[0] = 0.0; nodes[N] = 1.0;
 }
 void xo_time_shapes(int order, double t, double* shape)
 {

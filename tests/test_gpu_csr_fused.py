@@ -126,8 +126,17 @@ def test_procedural_affine_batch_equals_matrices_in_memory(dim, p):
     plan = ops.csr_plan_rows(V.ndof, [table])
     rp, c, v = ops.csr_assemble_fused(plan, [(table, mats)])
     proc = ops.affine_coefs(dim, p, elems, mesh.elements, mesh.points, 2 * p, terms)
-    rp2, c2, v2 = ops.csr_assemble_fused(plan, [(table, proc)])
+    ctx = ops.default_ctx()
+    ctx.set_option("csr_closed_form", 0)   # rows from the reference tensors: the FMA chain of xgpu_elmat_std's affine path
+    try:
+        rp2, c2, v2 = ops.csr_assemble_fused(plan, [(table, proc)])
+    finally:
+        ctx.set_option("csr_closed_form", 1)
     assert torch.equal(rp, rp2) and torch.equal(c, c2) and torch.equal(v, v2)
+    # default: P2-tet rows of the thread-per-row kernel in closed form (barycentric Gram matrix) — equal up to rounding
+    rp3, c3, v3 = ops.csr_assemble_fused(plan, [(table, proc)])
+    assert torch.equal(rp, rp3) and torch.equal(c, c3)
+    assert (v3 - v).abs().max().item() <= 1e-14 * v.abs().max().item()
 
 
 @pytest.mark.parametrize("n,p", [(6, 2), (5, 1), (4, 3)])

@@ -139,8 +139,31 @@ def oracle_st(pts, els, phi_st, tord, dt, ot, os_):
 
 
 def time_nodes(order):
+    if order >= 4:   # Gauss-Lobatto-Legendre points (spacetime/SpaceTimeFE.cpp:258-282): 0, 1 and the roots of P_k'
+        c = np.zeros(order + 1); c[order] = 1
+        r = np.sort(np.polynomial.legendre.legroots(np.polynomial.legendre.legder(c)))
+        return [0.0] + list(0.5 * (1 + r)) + [1.0]
     return {0: [0.0], 1: [0.0, 1.0], 2: [0.0, 0.5, 1.0],
             3: [0.0, 0.5 * (1 - 1 / sqrt(5)), 0.5 * (1 + 1 / sqrt(5)), 1.0]}[order]
+
+
+@pytest.mark.parametrize("k", [4, 5, 6, 8])
+def test_spacetime_high_order_time_nodes_kat(k):
+    # level set x - t^k through its values on the reference's time nodes: NEG = int_0^1 t^k dt = 1/(k+1); a kernel that
+    # interpolated on other nodes (e.g. Chebyshev points) would integrate a different function
+    m = meshes.MakeStructured1DMesh(3)
+    pts, els = mesh_np(m)
+    phi_st = np.stack([pts[:, 0] - t ** k for t in time_nodes(k)])
+    md = m.to(DEV)
+    g = torch.from_numpy(phi_st).to(DEV).contiguous()
+    for dt, ref in ((NEG, 1 / (k + 1)), (POS, k / (k + 1))):
+        off, p, tv, w = ops.cutquad_st(1, None, md.elements, md.points, g, k, dt, k, 1)
+        assert ops.default_ctx().status()[0] == 0
+        val = ops.integrate_monomial(1, None, md.elements, md.points, off, p, w, (0,))
+        assert abs(val - ref) < 1e-12
+        oo, po, tvo, wo = oracle_st(pts, els, phi_st, k, dt, k, 1)
+        assert np.array_equal(off.cpu().numpy(), oo)
+        assert np.allclose(w.cpu().numpy(), wo, rtol=1e-12, atol=1e-14)
 
 
 @pytest.mark.parametrize("dim,n", [(1, 9), (2, 7), (3, 4)])

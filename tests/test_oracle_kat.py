@@ -313,3 +313,26 @@ def test_spacetime_moving_circle_area():
         errs.append(abs(val - pi * r0 * r0))
     eoc = [np.log(errs[i - 1] / errs[i]) / np.log(2) for i in range(1, len(errs))]
     assert errs[-1] < 2e-3 and np.mean(eoc) > 1.5
+
+
+# NodalTimeFE nodes of order >= 4 are Gauss-Lobatto-Legendre points (spacetime/SpaceTimeFE.cpp:258-282, :229-256), not
+# Chebyshev points.  Level set x - t^k given by its values on THOSE nodes is exactly x - t^k, so NEG = int t^k = 1/(k+1);
+# with other nodes the interpolant (and the measure) would differ.
+def lobatto_nodes(k):
+    if k == 4:
+        return [0.0, 0.5 * (1 - np.sqrt(3 / 7)), 0.5, 0.5 * (1 + np.sqrt(3 / 7)), 1.0]
+    # interior nodes: roots of P_k' mapped to [0, 1]
+    c = np.zeros(k + 1); c[k] = 1
+    r = np.sort(np.polynomial.legendre.legroots(np.polynomial.legendre.legder(c)))
+    return [0.0] + list(0.5 * (1 + r)) + [1.0]
+
+
+@pytest.mark.parametrize("k", [4, 5, 6, 8])
+def test_spacetime_high_order_time_nodes(k):
+    m = meshes.MakeStructured1DMesh(3)
+    pts, _ = mesh_np(m)
+    nodes = lobatto_nodes(k)
+    lsn = [interpolate_to_p1(lambda x: x - t ** k, pts) for t in nodes]
+    neg = st_integrate(m, lsn, k, NEG, k, 1)
+    pos = st_integrate(m, lsn, k, POS, k, 1)
+    assert abs(neg - 1 / (k + 1)) < 1e-12 and abs(pos - k / (k + 1)) < 1e-12

@@ -66,6 +66,13 @@ def test_unsupported_requests_raise():
     with pytest.raises(xf.XgpuError):
         (u - u.Other()) * v                              # jump meets jump
     with pytest.raises(xf.XgpuError):
+        u - 2 * u.Other()                                # not a scaled jump: both sides must carry the same factor
+    with pytest.raises(xf.XgpuError):
+        (2 * u) - u.Other()
+    u0, _ = xf.H1(mesh, order=1).TnT()                   # the same rule on a plain space
+    with pytest.raises(xf.XgpuError):
+        u0 - 2 * u0.Other()
+    with pytest.raises(xf.XgpuError):
         u * v + xf.fix_tref(u, 0) * xf.fix_tref(v, 0)   # one fixed time per integrand
     with pytest.raises(xf.XgpuError):
         xf.ScalarTimeFE(4)
