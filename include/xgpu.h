@@ -342,6 +342,22 @@ int xgpu_rows_pack(xgpu_ctx* ctx, int64_t n, const int64_t* rowptr, const int32_
                    const double* vals, double* out);
 int xgpu_rows_add(xgpu_ctx* ctx, int64_t n, const int64_t* rowptr, const int32_t* rows, const int64_t* offsets,
                   const double* in, double* vals);
+/* The interface bookkeeping of a step over the STATIC candidate tables of a partition (ngsxfem_b200/distributed.py), without
+ * host round trips.  xgpu_iface_marks: flags[pair_gpos[i]] = 1 for every static (element, flag position) pair whose element
+ * is active (bit of has_bits = HASNEG BitArray words); flags (nflags bytes) is cleared first — the reference's
+ * AllReduceNodalData(..., MPI_LOR) over shared dofs (xfem/cutinfo.cpp:194-199) restricted to the candidates.
+ * xgpu_iface_rows: rows[i] = flags[i] ? dofmap[cand[i]] : -1 (the row lists xgpu_rows_* take).  xgpu_iface_index: the
+ * owner-local index message idx[i] = flags[i] ? dofmap[cand[i]] - n_lo : -1.  xgpu_l2g_own / xgpu_l2g_ghosts: global dof
+ * numbers = (sum of counts[k], k < owner) + owner-local index; counts = the all-reduced owned counts (device). */
+int xgpu_iface_marks(xgpu_ctx* ctx, const uint32_t* has_bits, int64_t npairs, const int32_t* pair_elem,
+                     const int32_t* pair_gpos, int64_t nflags, uint8_t* flags);
+int xgpu_iface_rows(xgpu_ctx* ctx, int64_t n, const int32_t* cand, const uint8_t* flags, const int32_t* dofmap,
+                    int32_t* rows);
+int xgpu_iface_index(xgpu_ctx* ctx, int64_t n, const int32_t* cand, const uint8_t* flags, const int32_t* dofmap,
+                     int64_t n_lo, int64_t* idx);
+int xgpu_l2g_own(xgpu_ctx* ctx, int64_t ndof, int64_t n_lo, int64_t n_own, const int64_t* counts, int rank, int64_t* l2g);
+int xgpu_l2g_ghosts(xgpu_ctx* ctx, int64_t n, const int32_t* dofmap_range, const int64_t* rbuf, const int64_t* counts,
+                    int q, int64_t* l2g);
 /* y = A x for checks (CSR SpMV, one warp per row) */
 int xgpu_csr_spmv(xgpu_ctx* ctx, int64_t nrows, const int64_t* rowptr, const int32_t* colidx,
                   const double* vals, const double* x, double* y);

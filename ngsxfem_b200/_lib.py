@@ -115,6 +115,11 @@ _SIGS = {
     "xgpu_reftensor": (C.c_int, [VP, C.c_int, C.c_int, C.c_int, C.POINTER(VP), c_intp]),
     "xgpu_plan_destroy": (None, [VP]),
     "xgpu_plan_phase_ms": (C.c_int, [VP, c_f64p]),
+    "xgpu_iface_marks": (C.c_int, [VP, VP, C.c_int64, VP, VP, C.c_int64, VP]),
+    "xgpu_iface_rows": (C.c_int, [VP, C.c_int64, VP, VP, VP, VP]),
+    "xgpu_iface_index": (C.c_int, [VP, C.c_int64, VP, VP, VP, C.c_int64, VP]),
+    "xgpu_l2g_own": (C.c_int, [VP, C.c_int64, C.c_int64, C.c_int64, VP, C.c_int, VP]),
+    "xgpu_l2g_ghosts": (C.c_int, [VP, C.c_int64, VP, VP, VP, C.c_int, VP]),
     "xgpu_rows_offsets": (C.c_int, [VP, C.c_int64, VP, VP, VP, c_i64p]),
     "xgpu_rows_pack": (C.c_int, [VP, C.c_int64, VP, VP, VP, VP, VP]),
     "xgpu_rows_add": (C.c_int, [VP, C.c_int64, VP, VP, VP, VP, VP]),

@@ -38,7 +38,107 @@ __global__ void __launch_bounds__(256) k_rows_move(int64_t n, const long long* _
   }
 }
 
+// ---- static interface tables: activity flags, row lists, index messages, global numbering (no host round trips)
+__global__ void k_iface_marks(int64_t npairs, const unsigned int* __restrict__ has, const int32_t* __restrict__ pair_elem,
+                              const int32_t* __restrict__ pair_gpos, unsigned char* __restrict__ flags)
+{
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= npairs) return;
+  const int e = pair_elem[i];
+  if ((has[e >> 5] >> (e & 31)) & 1u) flags[pair_gpos[i]] = 1;   // plain byte stores of the same value: no atomics needed
+}
+
+__global__ void k_iface_rows(int64_t n, const int32_t* __restrict__ cand, const unsigned char* __restrict__ flags,
+                             const int32_t* __restrict__ dofmap, int32_t* __restrict__ rows)
+{
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  rows[i] = flags[i] ? dofmap[cand[i]] : -1;
+}
+
+__global__ void k_iface_index(int64_t n, const int32_t* __restrict__ cand, const unsigned char* __restrict__ flags,
+                              const int32_t* __restrict__ dofmap, long long n_lo, long long* __restrict__ idx)
+{
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  idx[i] = flags[i] ? (long long)dofmap[cand[i]] - n_lo : -1;
+}
+
+__global__ void k_l2g_own(int64_t ndof, long long n_lo, long long n_own, const long long* __restrict__ counts, int rank,
+                          long long* __restrict__ l2g)
+{
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= ndof) return;
+  long long off = 0;
+  for (int k = 0; k < rank; k++) off += counts[k];
+  l2g[i] = (i >= n_lo && i < n_lo + n_own) ? off + (i - n_lo) : -1;
+}
+
+__global__ void k_l2g_ghosts(int64_t n, const int32_t* __restrict__ dofmap_range, const long long* __restrict__ rbuf,
+                             const long long* __restrict__ counts, int q, long long* __restrict__ l2g)
+{
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int loc = dofmap_range[i];
+  if (loc < 0) return;
+  long long off = 0;
+  for (int k = 0; k < q; k++) off += counts[k];
+  const long long r = rbuf[i];
+  l2g[loc] = r >= 0 ? r + off : r;
+}
+
 }  // namespace
+
+extern "C" int xgpu_iface_marks(xgpu_ctx* ctx, const uint32_t* has_bits, int64_t npairs, const int32_t* pair_elem,
+                                const int32_t* pair_gpos, int64_t nflags, uint8_t* flags)
+{
+  if (!ctx || npairs < 0 || nflags < 0 || (nflags > 0 && !flags)) return xgpu_fail(ctx, XGPU_ERR_ARG, "xgpu_iface_marks: bad argument");
+  if (nflags == 0) return XGPU_OK;
+  XGPU_CUDA(ctx, cudaMemsetAsync(flags, 0, (size_t)nflags, ctx->stream));
+  if (npairs == 0) return XGPU_OK;
+  k_iface_marks<<<nblk(npairs, 256), 256, 0, ctx->stream>>>(npairs, has_bits, pair_elem, pair_gpos, flags);
+  XGPU_LAUNCH_CHECK(ctx);
+  return XGPU_OK;
+}
+
+extern "C" int xgpu_iface_rows(xgpu_ctx* ctx, int64_t n, const int32_t* cand, const uint8_t* flags, const int32_t* dofmap,
+                               int32_t* rows)
+{
+  if (!ctx || n < 0) return xgpu_fail(ctx, XGPU_ERR_ARG, "xgpu_iface_rows: bad argument");
+  if (n == 0) return XGPU_OK;
+  k_iface_rows<<<nblk(n, 256), 256, 0, ctx->stream>>>(n, cand, flags, dofmap, rows);
+  XGPU_LAUNCH_CHECK(ctx);
+  return XGPU_OK;
+}
+
+extern "C" int xgpu_iface_index(xgpu_ctx* ctx, int64_t n, const int32_t* cand, const uint8_t* flags, const int32_t* dofmap,
+                                int64_t n_lo, int64_t* idx)
+{
+  if (!ctx || n < 0) return xgpu_fail(ctx, XGPU_ERR_ARG, "xgpu_iface_index: bad argument");
+  if (n == 0) return XGPU_OK;
+  k_iface_index<<<nblk(n, 256), 256, 0, ctx->stream>>>(n, cand, flags, dofmap, (long long)n_lo, (long long*)idx);
+  XGPU_LAUNCH_CHECK(ctx);
+  return XGPU_OK;
+}
+
+extern "C" int xgpu_l2g_own(xgpu_ctx* ctx, int64_t ndof, int64_t n_lo, int64_t n_own, const int64_t* counts, int rank, int64_t* l2g)
+{
+  if (!ctx || ndof < 0 || rank < 0 || !counts) return xgpu_fail(ctx, XGPU_ERR_ARG, "xgpu_l2g_own: bad argument");
+  if (ndof == 0) return XGPU_OK;
+  k_l2g_own<<<nblk(ndof, 256), 256, 0, ctx->stream>>>(ndof, n_lo, n_own, (const long long*)counts, rank, (long long*)l2g);
+  XGPU_LAUNCH_CHECK(ctx);
+  return XGPU_OK;
+}
+
+extern "C" int xgpu_l2g_ghosts(xgpu_ctx* ctx, int64_t n, const int32_t* dofmap_range, const int64_t* rbuf, const int64_t* counts,
+                               int q, int64_t* l2g)
+{
+  if (!ctx || n < 0 || q < 0 || !counts) return xgpu_fail(ctx, XGPU_ERR_ARG, "xgpu_l2g_ghosts: bad argument");
+  if (n == 0) return XGPU_OK;
+  k_l2g_ghosts<<<nblk(n, 256), 256, 0, ctx->stream>>>(n, dofmap_range, (const long long*)rbuf, (const long long*)counts, q, (long long*)l2g);
+  XGPU_LAUNCH_CHECK(ctx);
+  return XGPU_OK;
+}
 
 extern "C" int xgpu_rows_offsets(xgpu_ctx* ctx, int64_t n, const int64_t* rowptr, const int32_t* rows, int64_t* offsets,
                                  int64_t* total_host)

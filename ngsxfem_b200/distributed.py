@@ -98,6 +98,57 @@ class LocalPartition:
             ent["D"], ent["posE"], ent["posH"] = D, _compact_pos(pos[:TE.shape[0]]), _compact_pos(pos[TE.shape[0]:])
             self.iface[q] = ent
 
+    def kernel_tables(self):
+        """static inputs of the interface kernels (xgpu_iface_marks / _rows / _index; built once, on first use):
+        all candidate lists of all neighbours concatenated — rows part [C_send_q, D_q]_q, then the `seen` part [D_q]_q —
+        the (element, flag position) pairs that mark them, and the static message capacities: cap_recv[q] = sum of the FULL
+        row lengths (every element active) of my candidate rows D_q = an upper bound of what q can send me."""
+        if getattr(self, "_kt", None) is not None:
+            return self._kt
+        dev = self.el_vtx.device
+        i32 = lambda t: t.to(torch.int32).contiguous()
+        cand_rows, pe, pg, views = [], [], [], {}
+        base = 0
+        for q in self.neighbors:
+            it = self.iface[q]
+            nC, nD = it["C_send"].numel(), it["D"].numel()
+            r, pos = it["pos_send"]
+            pe.append(it["E"][r]); pg.append(pos + base)
+            r, pos = it["posH"]
+            pe.append(it["H"][r]); pg.append(pos + base + nC)
+            views[q] = (base, nC, nD)
+            cand_rows += [it["C_send"], it["D"]]
+            base += nC + nD
+        nrows = base
+        seen_base = {}
+        for q in self.neighbors:
+            it = self.iface[q]
+            nD = it["D"].numel()
+            seen_base[q] = base
+            for key, els in (("posH", it["H"]), ("posE", it["E"])):
+                r, pos = it[key]
+                pe.append(els[r]); pg.append(pos + base)
+            base += nD
+        z = torch.zeros(0, dtype=torch.int64, device=dev)
+        cand_seen = [self.iface[q]["D"] for q in self.neighbors]
+        cap_recv = {}
+        for q in self.neighbors:
+            it = self.iface[q]
+            T = torch.cat([self.el_dofs[it["E"]], self.el_dofs[it["H"]]]).long()
+            nd = T.shape[1]
+            inc = torch.zeros(self.ndof_loc, dtype=torch.bool, device=dev)
+            inc[it["D"]] = True
+            rows = T.unsqueeze(2).expand(-1, nd, nd)
+            cols = T.unsqueeze(1).expand(-1, nd, nd)
+            m = (rows >= 0) & (cols >= 0)
+            m &= inc[rows.clamp(min=0)]
+            cap_recv[q] = int(torch.unique(rows[m] * self.ndof_loc + cols[m]).numel())
+        self._kt = dict(cand_rows=i32(torch.cat(cand_rows)) if cand_rows else i32(z), nrows=nrows,
+                        cand_seen=i32(torch.cat(cand_seen)) if cand_seen else i32(z), nflags=base,
+                        pair_elem=i32(torch.cat(pe)) if pe else i32(z), pair_gpos=i32(torch.cat(pg)) if pg else i32(z),
+                        views=views, seen_base=seen_base, cap_recv=cap_recv)
+        return self._kt
+
     @staticmethod
     def _candidates(T, ow, q):
         """sorted unique dofs of table T owned by q, and for every entry of T its position in that list (-1)"""
@@ -121,6 +172,23 @@ def _marked(rp, act, n):
     f = torch.zeros(n + 1, dtype=torch.bool, device=posv.device)
     f[torch.where(act[rows], posv, torch.full_like(posv, n))] = True
     return f[:n]
+
+
+class _StepResult(dict):
+    """result dict of a step; entries given as callables are evaluated on first access (a device read-back that the
+    step itself does not wait for)"""
+
+    def __init__(self, d, **lazy):
+        super().__init__(d)
+        self._lazy = lazy
+
+    def __getitem__(self, k):
+        if k not in self.keys() and k in self._lazy:
+            self[k] = self._lazy.pop(k)()
+        return super().__getitem__(k)
+
+    def __contains__(self, k):
+        return super().__contains__(k) or k in self._lazy
 
 
 class DistributedCutAssembly:
@@ -151,7 +219,118 @@ class DistributedCutAssembly:
                 dist.recv(r_t, q, group=self.group)
                 dist.send(s_t, q, group=self.group)
 
+    def _handshake(self):
+        """once: message capacities (what every neighbour may send me at most) travel to the senders, and the candidate
+        lists are validated — my list D towards q and q's ghost range of my dofs must be the same dofs in the same order
+        (true for complete one-layer halos; a general partition that breaks it fails here instead of hanging in NCCL)"""
+        p, dev = self.part, self.part.el_vtx.device
+        kt = p.kernel_tables()
+        msgs = []
+        for q in p.neighbors:
+            qa, qb = p.range_of[q]
+            mine = torch.tensor([kt["cap_recv"][q], p.iface[q]["D"].numel(), qb - qa,
+                                 int(p.gid[p.iface[q]["D"]].sum().item()) % (1 << 40), int(p.gid[qa:qb].sum().item()) % (1 << 40)],
+                                dtype=torch.int64, device=dev)
+            msgs.append((q, mine, torch.empty_like(mine)))
+        self._exchange_all(msgs)
+        self.cap_send = {}
+        for q, mine, theirs in msgs:
+            t, m = theirs.tolist(), mine.tolist()
+            if t[1] != m[2] or t[2] != m[1] or t[3] != m[4] or t[4] != m[3]:
+                raise RuntimeError(f"rank {self.rank}: the interface candidate lists towards rank {q} do not match its ghost range "
+                                   "(the partition needs a complete one-layer halo)")
+            self.cap_send[q] = t[0]
+
     def step(self, phi, timer=None):
+        if getattr(self.be, "kernel_path", False) and (self.world == 1 or dist.get_backend(self.group) == "nccl"):
+            return self._step_kernels(phi, timer)
+        return self._step_generic(phi, timer)
+
+    def _step_kernels(self, phi, timer=None):
+        """the step on the CUDA backend: the single-GPU kernel sequence (Restrict + transposed table in one sequence, cut
+        elements on a side stream, procedural affine batch, one-row-pass CSR) over own + halo batches, the interface
+        bookkeeping in merge.cu kernels over the static candidate tables, messages of STATIC capacity (no host round trip
+        for their sizes), numbering by kernels.  Same protocol and same results as _step_generic."""
+        p, be, r = self.part, self.be, self.rank
+        ops, ctx = be.ops, be.ctx
+        dev = p.el_vtx.device
+        mark = timer.mark if timer is not None else (lambda name: None)
+        kt = p.kernel_tables()
+        if self.world > 1 and not hasattr(self, "cap_send"):
+            self._handshake()
+        mark("start")
+        ne = p.el_vtx.shape[0]
+        l_neg, l_if, cls = be.classify(p.el_vtx, phi)
+        bn, bp, bi, cr = cls
+        has = ops.bitset_op(ops.BIT_OR, bn, bi, ne, ctx=ctx)
+        l_has = ops.bitset_to_list(has, ne, ctx=ctx, count=l_neg.numel() + l_if.numel())
+        ne_own = self._ne_own.to(l_neg.dtype)
+        kn, ki = torch.stack([torch.searchsorted(l_neg, ne_own)[0], torch.searchsorted(l_if, ne_own)[0]]).tolist()
+        l_neg_own, l_if_own, l_halo = l_neg[:kn], l_if[:ki], l_has[kn + ki:]
+        mark("classify")
+        a, b = p.range_of[r]
+        if not hasattr(self, "_pin"):
+            self._pin = torch.zeros(2, dtype=torch.int64).pin_memory()
+
+        def owned_range(dofmap):
+            # active dofs below the two ends of my owner range: two small reductions + an async copy into pinned memory,
+            # enqueued right after Restrict — the count pass's own host synchronisation (nnz) completes it, so the
+            # distributed logic adds no host round trip of its own here
+            def below(i):
+                if i <= 0:
+                    return torch.zeros((), dtype=torch.int64, device=dev)
+                return (dofmap[:i].max().to(torch.int64) + 1).clamp(min=0)
+            self._pin.copy_(torch.stack([below(a), below(b)]), non_blocking=True)
+
+        res = be.local_assembly(p, phi, l_neg_own, l_if_own, l_halo, mark, after_restrict=owned_range if self.world > 1 else None)
+        dofmap, ndof, rowptr, col, vals = res
+        if self.world > 1 and ndof > 0:
+            n_lo, n_hi = self._pin.tolist()
+        else:
+            n_lo, n_hi = 0, ndof
+        n_own = n_hi - n_lo
+        # interface bookkeeping: flags of all candidates, row lists, index messages — three launches for all neighbours
+        counts = torch.zeros(self.world, dtype=torch.int64, device=dev)
+        counts[r] = n_own
+        red = None
+        if self.world > 1:
+            red = dist.all_reduce(counts, group=self.group, async_op=True)
+        msgs, lists = [], []
+        if p.neighbors:
+            flags = ops.iface_marks(has, kt["pair_elem"], kt["pair_gpos"], kt["nflags"], ctx=ctx)
+            rows_all = ops.iface_rows(kt["cand_rows"], flags, dofmap, ctx=ctx)
+            idx_all = ops.iface_index(kt["cand_seen"], flags[kt["nrows"]:], dofmap, n_lo, ctx=ctx)
+            mark("merge_rows")
+            ib = 0
+            for q in p.neighbors:
+                base, nC, nD = kt["views"][q]
+                srows, rrows = rows_all[base:base + nC], rows_all[base + nC:base + nC + nD]
+                soff, roff = ops.rows_offsets(rowptr, srows, ctx=ctx), ops.rows_offsets(rowptr, rrows, ctx=ctx)
+                lists.append((rrows, roff))
+                msgs.append((q, ops.rows_pack(rowptr, srows, soff, vals, self.cap_send[q], ctx=ctx),
+                             torch.empty(kt["cap_recv"][q], dtype=vals.dtype, device=dev)))
+                qa, qb = p.range_of[q]
+                msgs.append((q, idx_all[ib:ib + nD], torch.empty(qb - qa, dtype=torch.int64, device=dev)))
+                ib += nD
+            mark("merge_pack")
+            self._exchange_all(msgs)
+            mark("merge_exchange")
+            for k, q in enumerate(p.neighbors):                           # neighbours ascending: lower rank first
+                rrows, roff = lists[k]
+                ops.rows_add(rowptr, rrows, roff, msgs[2 * k][2], vals, ctx=ctx)
+            mark("merge")
+        if red is not None:
+            red.wait()
+        l2g = ops.l2g_own(ndof, n_lo, n_own, counts, r, ctx=ctx)
+        for k, q in enumerate(p.neighbors):
+            qa, qb = p.range_of[q]
+            ops.l2g_ghosts(l2g, dofmap[qa:qb], msgs[2 * k + 1][2], counts, q, ctx=ctx)
+        mark("numbering")
+        return _StepResult(dict(ndof_local=ndof, n_lo=n_lo, n_own=n_own, rowptr=rowptr, col=col, vals=vals, l2g=l2g, dofmap=dofmap,
+                                units=kn + ki, n_neg=kn, n_if=ki, nnz=int(col.numel()), cls=cls),
+                           ndof_global=lambda: int(counts.sum().item()))
+
+    def _step_generic(self, phi, timer=None):
         p, be, r = self.part, self.be, self.rank
         dev = p.el_vtx.device
         mark = timer.mark if timer is not None else (lambda name: None)
@@ -333,11 +512,62 @@ class GpuBackend:
     """drives libxgpu.so (C ABI) — there is no CPU fallback"""
 
     fused = True   # one-row-pass CSR (xgpu_csr_plan_rows + xgpu_csr_assemble_fused) where the shapes allow it
+    kernel_path = True   # DistributedCutAssembly._step_kernels (subclasses with other element kernels: generic step)
 
     def __init__(self, ctx=None):
         from . import ops
         self.ops = ops
         self.ctx = ctx or ops.default_ctx()
+
+    def local_assembly(self, part, phi, l_neg, l_if, l_halo, mark=lambda name: None, after_restrict=None):
+        """the single-GPU sequence of pipeline.CutAssembly._step over the rank's own batches + the halo batch (sparsity
+        only): Restrict + dof rows + transposed table in one sequence (xgpu_restrict_plan), the cut-element branch (cut
+        quadrature + cut element matrices) on the side stream, count pass, 7 coefficients per uncut element, one row pass.
+        returns dofmap, ndof, rowptr, col, vals"""
+        from .pipeline import TERMS_IF, TERMS_VOL, _side_context
+        ops, ctx, dim, p = self.ops, self.ctx, part.dim, part.fe_order
+        els, xyz, dev = part.el_vtx, part.vtx_xyz, part.el_vtx.device
+        order = 2 * p
+        nd = ops.h1_ndof(dim, p)
+        l_neg, l_if, l_halo = l_neg.contiguous(), l_if.contiguous(), l_halo.contiguous()
+        if p > 2 or not self.fused:
+            raise NotImplementedError("kernel path: orders 1, 2")
+        side, ctx2, _, _ = _side_context(dev)
+        main = torch.cuda.current_stream(dev)
+        m_if = torch.empty((l_if.numel(), nd, nd), dtype=torch.float64, device=dev)
+        side.wait_stream(main)
+        with torch.cuda.stream(side):
+            if l_if.numel():
+                off, n1 = ops.cutquad_count(dim, l_if, els, phi, ops.NEG, order, ctx=ctx2)
+                off2, n2 = ops.cutquad_count(dim, l_if, els, phi, ops.IF, order, ctx=ctx2)
+                q, w = ops.cutquad_fill(dim, l_if, els, xyz, phi, ops.NEG, order, off, n1, ctx=ctx2)
+                q2, w2 = ops.cutquad_fill(dim, l_if, els, xyz, phi, ops.IF, order, off2, n2, ctx=ctx2)
+                ops.elmat_rule_pair(dim, p, l_if, els, xyz, phi, (off, q, w), TERMS_VOL, (off2, q2, w2), TERMS_IF, out=m_if, ctx=ctx2)
+                for t_ in (off, off2, q, w, q2, w2):
+                    t_.record_stream(side)
+            m_if.record_stream(side)
+        mark("cut_branch_enqueued")
+        lists = [l_neg, l_if, l_halo]
+        keep = [i for i, l in enumerate(lists) if l.numel() > 0]
+        if not keep:   # nothing active on this rank (not even in the halo): an empty local matrix
+            main.wait_stream(side)
+            dofmap = torch.full((part.ndof_loc,), -1, dtype=torch.int32, device=dev)
+            return (dofmap, 0, torch.zeros(1, dtype=torch.int64, device=dev), torch.zeros(0, dtype=torch.int32, device=dev),
+                    torch.zeros(0, dtype=torch.float64, device=dev))
+        dofmap, ndof, tabs, plan = ops.restrict_plan(part.el_dofs, [lists[i] for i in keep], part.ndof_loc, ctx=ctx)
+        if after_restrict is not None:
+            after_restrict(dofmap)   # enqueued before the count pass (whose host synchronisation completes it)
+        mark("restrict_plan")
+        ops.csr_count_rows(plan)
+        mark("csr_count_pass")
+        m_neg = ops.affine_coefs(dim, p, l_neg, els, xyz, order, TERMS_VOL, ctx=ctx)
+        main.wait_stream(side)
+        ctx2.raise_on_geometry_error()
+        mark("elmat")
+        mats = [m_neg, m_if, None]
+        rowptr, col, vals = ops.csr_assemble_fused(plan, [(tabs[k], mats[i]) for k, i in enumerate(keep)])
+        mark("csr_rows_fused")
+        return dofmap, ndof, rowptr, col, vals
 
     def classify(self, el_vtx, phi):
         ops, ctx = self.ops, self.ctx
@@ -409,6 +639,8 @@ class MlsetGpuBackend(GpuBackend):
     with contribution (xfem/cutinfo.cpp:306-334: positive weight sum of the order -1 multi-level-set rule); every active
     element gets its rule from xgpu_cutquad_ml_* (uncut relevant elements: the standard rule), forms: grad.grad + u v."""
 
+    kernel_path = False
+
     def __init__(self, dts, ctx=None):
         super().__init__(ctx)
         self.dts = [tuple(int(d) for d in t) for t in dts]
@@ -453,6 +685,7 @@ class SpaceTimeGpuBackend(GpuBackend):
     xgpu_cutquad_st_* (uncut elements: the tensor-product standard rule), forms: u v + dt(u) v + grad u . grad v."""
 
     TERMS = [(0, 0, 1.0, 0), (3, 0, 1.0, 0), (1, 1, 1.0, 0)]   # (op_trial, op_test, coef, hpow); 3 = XGPU_OP_DT
+    kernel_path = False
 
     def __init__(self, space_order, time_fe_order, lset_time_order, time_order, ctx=None):
         super().__init__(ctx)

@@ -618,6 +618,7 @@ def rows_offsets(rowptr, rows, ctx=None):
 
 
 def rows_pack(rowptr, rows, off, vals, total, ctx=None):
+    """total: size of the message buffer (the exact packed size, or a static capacity >= it: the tail stays unwritten)"""
     ctx = ctx or default_ctx()
     out = torch.empty(total, dtype=torch.float64, device=vals.device)
     ctx.check(ctx.lib.xgpu_rows_pack(ctx.h, rows.numel(), ptr(rowptr), ptr(_i32(rows)), ptr(off), ptr(vals), ptr(out)))
@@ -628,6 +629,43 @@ def rows_add(rowptr, rows, off, buf, vals, ctx=None):
     ctx = ctx or default_ctx()
     ctx.check(ctx.lib.xgpu_rows_add(ctx.h, rows.numel(), ptr(rowptr), ptr(_i32(rows)), ptr(off), ptr(buf), ptr(vals)))
     return vals
+
+
+def iface_marks(has_bits, pair_elem, pair_gpos, nflags, ctx=None):
+    """activity flags (uint8, nflags) of static interface candidates: flags[pair_gpos[i]] = 1 if element pair_elem[i] is active"""
+    ctx = ctx or default_ctx()
+    flags = torch.empty(max(1, nflags), dtype=torch.uint8, device=has_bits.device)
+    ctx.check(ctx.lib.xgpu_iface_marks(ctx.h, ptr(has_bits), pair_elem.numel(), ptr(pair_elem), ptr(pair_gpos), nflags, ptr(flags)))
+    return flags[:nflags]
+
+
+def iface_rows(cand, flags, dofmap, ctx=None):
+    """rows[i] = flags[i] ? dofmap[cand[i]] : -1"""
+    ctx = ctx or default_ctx()
+    rows = torch.empty(cand.numel(), dtype=torch.int32, device=cand.device)
+    ctx.check(ctx.lib.xgpu_iface_rows(ctx.h, cand.numel(), ptr(cand), ptr(flags), ptr(dofmap), ptr(rows)))
+    return rows
+
+
+def iface_index(cand, flags, dofmap, n_lo, ctx=None):
+    """idx[i] = flags[i] ? dofmap[cand[i]] - n_lo : -1 (int64: the owner-local index message)"""
+    ctx = ctx or default_ctx()
+    idx = torch.empty(cand.numel(), dtype=torch.int64, device=cand.device)
+    ctx.check(ctx.lib.xgpu_iface_index(ctx.h, cand.numel(), ptr(cand), ptr(flags), ptr(dofmap), int(n_lo), ptr(idx)))
+    return idx
+
+
+def l2g_own(ndof, n_lo, n_own, counts, rank, ctx=None):
+    ctx = ctx or default_ctx()
+    l2g = torch.empty(ndof, dtype=torch.int64, device=counts.device)
+    ctx.check(ctx.lib.xgpu_l2g_own(ctx.h, ndof, int(n_lo), int(n_own), ptr(counts), int(rank), ptr(l2g)))
+    return l2g
+
+
+def l2g_ghosts(l2g, dofmap_range, rbuf, counts, q, ctx=None):
+    ctx = ctx or default_ctx()
+    ctx.check(ctx.lib.xgpu_l2g_ghosts(ctx.h, dofmap_range.numel(), ptr(dofmap_range), ptr(rbuf), ptr(counts), int(q), ptr(l2g)))
+    return l2g
 
 
 def csr_spmv(rowptr, col, vals, x, ctx=None):

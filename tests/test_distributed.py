@@ -17,11 +17,13 @@ for p in (ROOT, HERE):
         sys.path.insert(0, p)
 
 
-def _global_reference(n, world, fe_order):
-    """whole chain on one process through the oracle; returns dict key -> row (dict key -> value)"""
+def _global_reference(n, world, fe_order, scaling="weak"):
+    """whole chain (weak) / THE cube (strong) on one process through the oracle; returns dict key -> row (dict key -> value)"""
     import ngsxfem_b200 as xf
     from ngsxfem_b200.pipeline import sphere_levelset
     from oracle.pipeline_ref import oracle_step
+    if scaling == "strong":
+        world = 1   # the global problem of a strong split is the single cube
     mesh = xf.MakeStructured3DMesh(nx=n, ny=n, nz=n * world)
     nv1 = n + 1
     pts = mesh.points.clone()
@@ -47,7 +49,7 @@ def _global_reference(n, world, fe_order):
     return res, keys
 
 
-def _worker(rank, world, n, fe_order, port, out, gpu=False):
+def _worker(rank, world, n, fe_order, port, out, gpu=False, scaling="weak"):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     if gpu:
@@ -59,11 +61,11 @@ def _worker(rank, world, n, fe_order, port, out, gpu=False):
         from ngsxfem_b200.distributed import DistributedCutAssembly, make_slab_partition
         if gpu:
             from ngsxfem_b200.distributed import GpuBackend
-            part, phi = make_slab_partition(n, world, rank, torch.device("cuda", rank), fe_order=fe_order)
+            part, phi = make_slab_partition(n, world, rank, torch.device("cuda", rank), fe_order=fe_order, scaling=scaling)
             asm = DistributedCutAssembly(part, GpuBackend(), rank, world)
         else:
             from dist_backend import OracleBackend
-            part, phi = make_slab_partition(n, world, rank, "cpu", fe_order=fe_order)
+            part, phi = make_slab_partition(n, world, rank, "cpu", fe_order=fe_order, scaling=scaling)
             asm = DistributedCutAssembly(part, OracleBackend(), rank, world)
         res = asm.step(phi)
         rows_g, rp, cols_g, vals = asm.owned_rows_global(res)
@@ -83,24 +85,31 @@ def test_slab_partition_merge_equals_global(tmp_path, world, n, fe_order):
     _run_and_check(tmp_path, world, n, fe_order, gpu=False)
 
 
+@pytest.mark.parametrize("world,n,fe_order", [(2, 6, 2), (3, 7, 2), (4, 8, 1)])
+def test_strong_split_of_one_cube_equals_global(tmp_path, world, n, fe_order):
+    """scaling="strong": THE unit cube (BASELINE config 2 shape) cut into `world` z-slabs of work-balanced layer counts"""
+    _run_and_check(tmp_path, world, n, fe_order, gpu=False, scaling="strong")
+
+
 @pytest.mark.gpu
-@pytest.mark.parametrize("world,n,fe_order", [(2, 6, 2), (2, 5, 1)])
-def test_nccl_slab_partition_merge_equals_global(tmp_path, world, n, fe_order):
-    """the same check with the CUDA kernels and NCCL send/recv (needs >= 2 GPUs: gpurun --gpus 2)"""
+@pytest.mark.parametrize("world,n,fe_order,scaling", [(2, 6, 2, "weak"), (2, 5, 1, "weak"), (2, 8, 2, "strong")])
+def test_nccl_slab_partition_merge_equals_global(tmp_path, world, n, fe_order, scaling):
+    """the same check with the CUDA kernels (interface bookkeeping in merge.cu, static-capacity messages) and NCCL
+    send/recv (needs >= 2 GPUs: gpurun --gpus 2)"""
     if torch.cuda.device_count() < world:
         pytest.skip("needs %d GPUs" % world)
-    _run_and_check(tmp_path, world, n, fe_order, gpu=True)
+    _run_and_check(tmp_path, world, n, fe_order, gpu=True, scaling=scaling)
 
 
-def _run_and_check(tmp_path, world, n, fe_order, gpu):
+def _run_and_check(tmp_path, world, n, fe_order, gpu, scaling="weak"):
     port = 29500 + (os.getpid() % 2000) + world + (7 if gpu else 0)
-    mp.spawn(_worker, args=(world, n, fe_order, port, str(tmp_path), gpu), nprocs=world, join=True)
-    ref, keys = _global_reference(n, world, fe_order)
+    mp.spawn(_worker, args=(world, n, fe_order, port, str(tmp_path), gpu, scaling), nprocs=world, join=True)
+    ref, keys = _global_reference(n, world, fe_order, scaling)
     parts = [torch.load(os.path.join(str(tmp_path), f"rank{r}.pt")) for r in range(world)]
     ndofg = parts[0]["ndof_global"]
     assert ndofg == ref["ndof"] == len(keys)
     assert sum(p["units"] for p in parts) == ref["units"]
-    if world > 1:  # weak-scaling construction: every rank sees two half spheres = the same element counts
+    if world > 1 and scaling == "weak":  # weak-scaling construction: every rank sees two half spheres = the same element counts
         assert len({(p["n_neg"], p["n_if"]) for p in parts}) == 1
     # distributed global id -> key
     key_of = np.zeros(ndofg, dtype=np.int64)
