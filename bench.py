@@ -160,8 +160,6 @@ def kernel_bytes(phase, r, nd, ne=None, ndof_full=None):
         return n_neg * (16 + 96 + 64)
     if phase == "csr":           # distributed path (two-pass backend): plan + pattern + scatter timed as one phase
         return units * (nn * 8 + 2 * nd * 4) + nnz * 12 + units * nd * (4 + 8 + 1) + nnz * 4
-    if phase == "elmat":         # distributed path: cut quadrature + uncut + cut element matrices
-        return n_neg * (16 + 96 + 4 + nn * 8) + n_if * (16 + 96 + 32 + 4 + 2 * nn * 8) + npts * 32
     return None
 
 
@@ -221,22 +219,47 @@ def run_gpu(args):
         hb = HostBuffers(part.el_vtx, part.vtx_xyz, part.el_dofs, phi)
         ne_loc, ndof_full = part.el_vtx.shape[0], part.ndof_loc
         step_dev = lambda t: asm.step(phi, timer=t)
-        e2e_finish = None
         asm_e2e = DistributedCutAssembly(part, asm.be, rank, world)
 
+        s_in, s_out = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+        hb.done = [None, None]
+
         def step_e2e():
+            # software-pipelined like the single-GPU leg: the inputs of step k+1 arrive (copy stream s_in) and its kernels
+            # run while the results of step k leave (copy stream s_out, two alternating sets of pinned landing buffers)
+            hb.parity = 1 - getattr(hb, "parity", 1)
+            par = f"#{hb.parity}"
+            if hb.done[hb.parity] is not None:
+                hb.done[hb.parity].synchronize()   # this landing set was filled two steps ago
+            main = torch.cuda.current_stream(dev)
             p2 = copy.copy(part)
-            p2.el_vtx = hb.el_vtx.to(dev, non_blocking=True)
-            p2.vtx_xyz = hb.vtx_xyz.to(dev, non_blocking=True)
-            p2.el_dofs = hb.el_dofs.to(dev, non_blocking=True)
-            ph = hb.phi.to(dev, non_blocking=True)
+            with torch.cuda.stream(s_in):
+                p2.el_vtx = hb.el_vtx.to(dev, non_blocking=True)
+                ph = hb.phi.to(dev, non_blocking=True)
+                p2.el_dofs = hb.el_dofs.to(dev, non_blocking=True)
+                p2.vtx_xyz = hb.vtx_xyz.to(dev, non_blocking=True)
+            main.wait_stream(s_in)
+            for t_ in (p2.el_vtx, ph, p2.el_dofs, p2.vtx_xyz):
+                t_.record_stream(main)
             asm_e2e.part = p2
             r = asm_e2e.step(ph)
-            d2h = sum(hb.land(f"bits{i}", b) for i, b in enumerate(r["cls"][:3])) + hb.land("cut_ratio", r["cls"][3])
             rows_g, rp, cols_g, vals = DistributedCutAssembly.owned_rows_global(r)
-            d2h += hb.land("rows", rows_g) + hb.land("rowptr", rp) + hb.land("col", cols_g) + hb.land("vals", vals)
-            torch.cuda.current_stream().synchronize()
+            s_out.wait_stream(main)
+            with torch.cuda.stream(s_out):
+                outs = [(f"bits{i}", b) for i, b in enumerate(r["cls"][:3])] + [("cut_ratio", r["cls"][3]), ("rows", rows_g),
+                                                                                 ("rowptr", rp), ("col", cols_g), ("vals", vals)]
+                d2h = 0
+                for name, t_ in outs:
+                    t_.record_stream(s_out)
+                    d2h += hb.land(name + par, t_)
+                hb.done[hb.parity] = torch.cuda.Event()
+                hb.done[hb.parity].record(s_out)
             return r, hb.h2d_bytes(), d2h
+
+        def e2e_finish():
+            main = torch.cuda.current_stream(dev)
+            main.wait_stream(s_out)
+            main.wait_stream(s_in)
     torch.cuda.synchronize()
 
     def barrier():
@@ -385,7 +408,7 @@ def run_gpu(args):
             "e2e": {"value": tot_units * e2e_steps / (ms_e2e * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e / e2e_steps,
                     "steps": e2e_steps, "h2d_bytes_per_step": info["h2d"], "d2h_bytes_per_step": info["d2h"],
                     "pipelining": ("steps software-pipelined: H2D + kernels of step k+1 overlap the D2H of step k (two sets of pinned "
-                                   "landing buffers)") if world == 1 else "none"},
+                                   "landing buffers)")},
             "gpu_launches": int(launches),
             "roofline": {"kernel": dom, "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
                          "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_launch": kb,

@@ -342,6 +342,19 @@ int xgpu_rows_pack(xgpu_ctx* ctx, int64_t n, const int64_t* rowptr, const int32_
                    const double* vals, double* out);
 int xgpu_rows_add(xgpu_ctx* ctx, int64_t n, const int64_t* rowptr, const int32_t* rows, const int64_t* offsets,
                   const double* in, double* vals);
+/* ---------------------------------------------------------------- (f4) cut integrals over facets / element boundaries
+ * SymbolicCutFacetBilinearFormIntegrator::T_CalcFacetMatrix (xfem/symboliccutbfi.cpp:886-1290, dCut(..., skeleton=True)) and
+ * SymbolicCutBilinearFormIntegrator::T_CalcElementMatrixEBAdd (:488-883, dCut(..., element_boundary=True)) on affine simplices.
+ * The rule of every listed facet comes from xgpu_cutquad_* applied to the FACET-vertex table (dimension dim-1: points in the
+ * facet's reference coordinates, reference weights; offsets n+1).  facet_vtx: n x dim global vertex numbers in the order the
+ * rule was built for; facet_els: n x 2 (nsides = 1: column 1 unused).  Integrand menu: sum of
+ * coef * h^hpow * Op_test(v|side) * Op_trial(u|side), kind 0 = value, 1 = nF . grad with nF the outward unit normal of the
+ * FIRST element, side 0 = that element, 1 = .Other(); h = mesh size of the first element.  mats: n x (nsides nd)^2 row-major,
+ * rows = test, dofs of side 0 first — written, not accumulated. */
+typedef struct { int trial_kind, trial_side, test_kind, test_side; double coef; int hpow; } xgpu_fterm;
+int xgpu_facet_elmat(xgpu_ctx* ctx, int dim, int fe_order, int64_t n, const int32_t* facet_vtx, const int32_t* facet_els,
+                     const int32_t* el_vtx, const double* vtx_xyz, const int64_t* offsets, const double* pts,
+                     const double* wts, const xgpu_fterm* terms_host, int nterms, int nsides, double* mats);
 /* The interface bookkeeping of a step over the STATIC candidate tables of a partition (ngsxfem_b200/distributed.py), without
  * host round trips.  xgpu_iface_marks: flags[pair_gpos[i]] = 1 for every static (element, flag position) pair whose element
  * is active (bit of has_bits = HASNEG BitArray words); flags (nflags bytes) is cleared first — the reference's

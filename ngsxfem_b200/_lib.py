@@ -35,6 +35,11 @@ class StLTerm(C.Structure):
     _fields_ = [("op_test", C.c_int), ("coef", C.c_double), ("hpow", C.c_int), ("expo", C.c_int * 4)]
 
 
+class FTerm(C.Structure):
+    _fields_ = [("trial_kind", C.c_int), ("trial_side", C.c_int), ("test_kind", C.c_int), ("test_side", C.c_int),
+                ("coef", C.c_double), ("hpow", C.c_int)]
+
+
 class Batch(C.Structure):
     _fields_ = [("table", VP), ("mats", VP), ("nrows", C.c_int64), ("width", C.c_int), ("coefs", VP)]
 
@@ -115,6 +120,7 @@ _SIGS = {
     "xgpu_reftensor": (C.c_int, [VP, C.c_int, C.c_int, C.c_int, C.POINTER(VP), c_intp]),
     "xgpu_plan_destroy": (None, [VP]),
     "xgpu_plan_phase_ms": (C.c_int, [VP, c_f64p]),
+    "xgpu_facet_elmat": (C.c_int, [VP, C.c_int, C.c_int, C.c_int64, VP, VP, VP, VP, VP, VP, VP, C.POINTER(FTerm), C.c_int, C.c_int, VP]),
     "xgpu_iface_marks": (C.c_int, [VP, VP, C.c_int64, VP, VP, C.c_int64, VP]),
     "xgpu_iface_rows": (C.c_int, [VP, C.c_int64, VP, VP, VP, VP]),
     "xgpu_iface_index": (C.c_int, [VP, C.c_int64, VP, VP, VP, C.c_int64, VP]),

@@ -44,6 +44,11 @@ class MeshSize:
 class specialcf:
     mesh_size = MeshSize()
 
+    @staticmethod
+    def normal(dim=None):
+        """the facet normal nF of skeleton / element-boundary integrals (outward unit normal of the first element)"""
+        return FacetNormal()
+
 
 class Scalar:
     """c * h^k"""
@@ -106,7 +111,14 @@ class Proxy:
     def __neg__(self):
         return self._with(scal=self.scal * -1.0)
 
+    def __add__(self, o):
+        if isinstance(o, (Proxy, FacetExpr)) and not isinstance(o, Form):
+            return FacetExpr.of(self) + o
+        return NotImplemented
+
     def __sub__(self, o):
+        if isinstance(o, FacetExpr) or (isinstance(o, Proxy) and OP_FDN in (self.op, o.op)):
+            return FacetExpr.of(self) - o
         if isinstance(o, Proxy) and o.other and not self.other and self.op == OP_ID and o.op == OP_ID \
                 and o.is_test == self.is_test:
             if (self.scal.c, self.scal.hpow) != (o.scal.c, o.scal.hpow):   # 2*u - u.Other() is not a scaled jump
@@ -119,9 +131,17 @@ class Proxy:
             s = o if isinstance(o, Scalar) else (Scalar(float(o)) if isinstance(o, numbers.Number) else Scalar(1.0, o.power))
             return self._with(scal=self.scal * s)
         if isinstance(o, Normal):
-            if self.op != OP_GRAD:
+            if self.op != OP_GRAD or self.other:
                 raise XgpuError("only grad(u)*n is supported with the level-set normal")
             return self._with(op=OP_DN, nlset=o.lset)
+        if isinstance(o, FacetNormal):
+            if self.op != OP_GRAD:
+                raise XgpuError("only grad(u)*nF is supported with the facet normal")
+            return self._with(op=OP_FDN)
+        if isinstance(o, FacetExpr):
+            return o * self
+        if isinstance(o, Proxy) and (self.other or o.other or OP_FDN in (self.op, o.op)):
+            return FacetExpr.of(self) * o
         if isinstance(o, Proxy):
             return Form.from_pair(self, o)
         if isinstance(o, Form):
@@ -133,6 +153,135 @@ class Proxy:
         return NotImplemented
 
     __rmul__ = __mul__
+
+
+# ------------------------------------------------------------------ facet integrands (dCut(..., skeleton / element_boundary))
+OP_FDN = 4   # nF . grad(u): derivative along the facet normal of the first element (specialcf.normal / dn(u, 1))
+
+
+class FacetNormal:
+    """specialcf.normal(dim) inside skeleton / element-boundary integrals: outward unit normal of the first element"""
+
+
+class FacetExpr:
+    """linear combination of traces of ONE trial or test function on a facet: [(kind, side, c, hpow)], kind 0 = value,
+    1 = nF . grad, side 0 = this element, 1 = .Other() — e.g. the DG jump u - u.Other() and the mean flux
+    0.5 (grad(u) + grad(u.Other())) * nF of demos/fictdom_dg.py:108-125, the derivative jump dn(u,1) - dn(u.Other(),1)"""
+
+    def __init__(self, space, is_test, items):
+        self.space, self.is_test, self.items = space, is_test, items
+
+    @staticmethod
+    def of(x):
+        if isinstance(x, FacetExpr):
+            return x
+        if isinstance(x, Proxy):
+            s, side = x.scal, (1 if x.other else 0)
+            if x.op == OP_ID:
+                return FacetExpr(x.space, x.is_test, [(0, side, s.c, s.hpow)])
+            if x.op == OP_FDN:
+                return FacetExpr(x.space, x.is_test, [(1, side, s.c, s.hpow)])
+            if x.op == OP_GRAD:   # a gradient waiting for the facet normal: (grad(u) + grad(u.Other())) * nF
+                return FacetExpr(x.space, x.is_test, [(-1, side, s.c, s.hpow)])
+            if x.op == OP_JUMP:
+                return FacetExpr(x.space, x.is_test, [(0, 0, s.c, s.hpow), (0, 1, -s.c, s.hpow)])
+        raise XgpuError("facet integrands: menu is u, u.Other(), grad(u)*nF, grad(u.Other())*nF and their linear combinations")
+
+    def __add__(self, o):
+        o = FacetExpr.of(o)
+        if o.is_test != self.is_test:
+            raise XgpuError("cannot add a trial and a test function")
+        return FacetExpr(self.space, self.is_test, self.items + o.items)
+
+    __radd__ = __add__
+
+    def __neg__(self):
+        return self * -1.0
+
+    def __sub__(self, o):
+        return self + (-FacetExpr.of(o))
+
+    def __rsub__(self, o):
+        return FacetExpr.of(o) + (-self)
+
+    def __mul__(self, o):
+        if isinstance(o, (numbers.Number, Scalar, MeshSize)):
+            s = o if isinstance(o, Scalar) else (Scalar(float(o)) if isinstance(o, numbers.Number) else Scalar(1.0, o.power))
+            return FacetExpr(self.space, self.is_test, [(k, sd, c * s.c, hp + s.hpow) for k, sd, c, hp in self.items])
+        if isinstance(o, FacetNormal):
+            if any(k != -1 for k, _, _, _ in self.items):
+                raise XgpuError("only gradients can be multiplied with the facet normal")
+            return FacetExpr(self.space, self.is_test, [(1, sd, c, hp) for _, sd, c, hp in self.items])
+        if isinstance(o, (Proxy, FacetExpr)):
+            o = FacetExpr.of(o)
+            if any(k == -1 for k, _, _, _ in self.items + o.items):
+                raise XgpuError("facet integrands: a gradient must be multiplied with the facet normal nF")
+            if o.is_test == self.is_test:
+                raise XgpuError("a bilinear form needs one trial and one test function per term")
+            u, v = (o, self) if self.is_test else (self, o)
+            return FacetForm([(tk, ts, ek, es, c1 * c2, h1 + h2) for tk, ts, c1, h1 in u.items for ek, es, c2, h2 in v.items], u.space)
+        return NotImplemented
+
+    __rmul__ = __mul__
+
+    def __truediv__(self, o):
+        if isinstance(o, MeshSize):
+            return self * Scalar(1.0, -o.power)
+        return self * (1.0 / float(o))
+
+
+class FacetForm:
+    """bilinear facet integrand: [(trial kind, trial side, test kind, test side, coef, hpow)] (xgpu_fterm)"""
+
+    def __init__(self, terms, space):
+        self.terms, self.space, self.nlset = terms, space, None
+
+    @staticmethod
+    def of(f):
+        if isinstance(f, FacetForm):
+            return f
+        if isinstance(f, Form):   # u*v and (u-u.Other())*(v-v.Other()) written with plain proxies
+            out = []
+            for a, b, c, hp in f.terms:
+                if a == OP_ID and b == OP_ID:
+                    out.append((0, 0, 0, 0, c, hp))
+                elif a == OP_JUMP and b == OP_JUMP:
+                    out += [(0, 0, 0, 0, c, hp), (0, 1, 0, 0, -c, hp), (0, 0, 0, 1, -c, hp), (0, 1, 0, 1, c, hp)]
+                else:
+                    raise XgpuError("facet integrands: grad(u)*grad(v) / level-set normals are not traces on a facet (menu: values, nF . grad)")
+            return FacetForm(out, f.space)
+        raise XgpuError("not a facet integrand")
+
+    def __add__(self, o):
+        return FacetForm(self.terms + FacetForm.of(o).terms, self.space)
+
+    __radd__ = __add__
+
+    def __neg__(self):
+        return self * -1.0
+
+    def __sub__(self, o):
+        return self + (-FacetForm.of(o))
+
+    def __mul__(self, o):
+        if isinstance(o, (numbers.Number, Scalar, MeshSize)):
+            s = o if isinstance(o, Scalar) else (Scalar(float(o)) if isinstance(o, numbers.Number) else Scalar(1.0, o.power))
+            return FacetForm([(a, b, c_, d, c * s.c, hp + s.hpow) for a, b, c_, d, c, hp in self.terms], self.space)
+        if isinstance(o, CutDifferentialSymbol):
+            if not (o.skeleton or o.element_boundary):
+                raise XgpuError("facet integrands need dCut(..., skeleton=True) or dCut(..., element_boundary=True)")
+            return Integral(self, o)
+        return NotImplemented
+
+    __rmul__ = __mul__
+
+
+def dn(u, order=1, comp=-1, hdiv=False):
+    """xfem/ghostpenalty.cpp (DiffOpDuDnk): normal derivative across a facet.  Accelerated path: the first derivative,
+    dn(u, 1) = grad(u) * nF; higher orders raise."""
+    if order != 1 or comp != -1 or hdiv:
+        raise XgpuError("dn: only the first normal derivative of a scalar H1 function is on the accelerated path")
+    return grad(u) * FacetNormal()
 
 
 class LForm:
@@ -186,9 +335,9 @@ def grad(u):
     if hasattr(u, "_st_grad"):  # proxies of a SpaceTimeFESpace (spacetime.py): the space gradient
         return u._st_grad()
     if isinstance(u, Proxy):
-        if u.op != OP_ID or u.other:
+        if u.op != OP_ID:
             raise XgpuError("grad of this proxy is not supported")
-        return u._with(op=OP_GRAD)
+        return u._with(op=OP_GRAD)   # grad(u.Other()) only makes sense times the facet normal (checked where it is used)
     if isinstance(u, GridFunction):
         return GradLset(u)
     raise XgpuError("grad: unsupported argument")
@@ -211,6 +360,8 @@ class Form:
         if a.is_test == b.is_test:
             raise XgpuError("a bilinear form needs one trial and one test function per term")
         u, v = (b, a) if a.is_test else (a, b)
+        if (u.other or v.other) and not (u.op == OP_ID and v.op == OP_ID):
+            raise XgpuError(".Other() appears in jumps (u - u.Other()) and facet traces only")
         if (u.op == OP_GRAD) != (v.op == OP_GRAD):
             raise XgpuError("grad(u) must be paired with grad(v) (dot product) or the normal n")
         if (u.op == OP_JUMP) != (v.op == OP_JUMP):
@@ -219,6 +370,8 @@ class Form:
         return Form([(u.op, v.op, s.c, s.hpow)], u.space, Form._merge_nlset(u.nlset, v.nlset))
 
     def __add__(self, o):
+        if isinstance(o, FacetForm):
+            return FacetForm.of(self) + o
         if isinstance(o, Form):
             return Form(self.terms + o.terms, self.space, Form._merge_nlset(self.nlset, o.nlset))
         return NotImplemented
@@ -233,6 +386,8 @@ class Form:
         if isinstance(o, (numbers.Number, Scalar, MeshSize)):
             s = o if isinstance(o, Scalar) else (Scalar(float(o)) if isinstance(o, numbers.Number) else Scalar(1.0, o.power))
             return Form([(a, b, c * s.c, hp + s.hpow) for a, b, c, hp in self.terms], self.space, self.nlset)
+        if isinstance(o, CutDifferentialSymbol) and (o.skeleton or o.element_boundary):
+            return Integral(FacetForm.of(self), o)
         if isinstance(o, (CutDifferentialSymbol, FacetPatchDifferentialSymbol)):
             return Integral(self, o)
         return NotImplemented
@@ -242,10 +397,12 @@ class Form:
 
 # ------------------------------------------------------------------ differential symbols
 class CutDifferentialSymbol:
-    def __init__(self, levelset, domain_type, order, definedonelements, deformation, time_order=-1, tref=None, vb=0):
+    def __init__(self, levelset, domain_type, order, definedonelements, deformation, time_order=-1, tref=None, vb=0,
+                 skeleton=False, element_boundary=False):
         self.levelset, self.domain_type, self.order = levelset, domain_type, order
         self.definedonelements, self.deformation = definedonelements, deformation
         self.time_order, self.tref, self.vb = time_order, tref, vb
+        self.skeleton, self.element_boundary = bool(skeleton), bool(element_boundary)
 
 
 def dCut(levelset, domain_type, order=None, subdivlvl=None, time_order=-1, levelset_domain=None,
@@ -254,8 +411,18 @@ def dCut(levelset, domain_type, order=None, subdivlvl=None, time_order=-1, level
     """python/__init__.py:781-864"""
     if subdivlvl not in (None, 0):
         raise XgpuError("subdivlvl > 0 selects ngsxfem's legacy subdivision path: not provided")
-    if element_boundary or skeleton or element_vb != 0 or vb not in (0, 1):
-        raise XgpuError("element-boundary / skeleton cut integrals are not on the accelerated path yet")
+    if element_vb != 0 or vb not in (0, 1):
+        raise XgpuError("element_vb / vb: not on the accelerated path")
+    if element_boundary or skeleton:
+        # cut integrals over interior facets / element boundaries (xfem/symboliccutbfi.cpp:886-1290, :488-883)
+        if element_boundary and skeleton:
+            raise XgpuError("dCut: skeleton and element_boundary exclude each other (python/__init__.py:826-830)")
+        if vb != 0 or deformation is not None or isinstance(levelset, (list, tuple)) or int(domain_type) == IF \
+                or time_order >= 0 or tref is not None:
+            raise XgpuError("dCut(skeleton / element_boundary): one level set, NEG / POS, affine mesh, no time slab "
+                            "(the codim-2 IF case and deformed facets are not on the accelerated path)")
+        if definedonelements is None:
+            raise XgpuError("dCut(skeleton / element_boundary) needs definedonelements (facets / elements)")
     if vb == 1 and (deformation is not None or isinstance(levelset, (list, tuple)) or int(domain_type) == IF):
         raise XgpuError("dCut(vb=BND): single level set, NEG / POS, no deformation (tests/pytests/test_bndcut.py)")
     if kwargs:
@@ -265,7 +432,7 @@ def dCut(levelset, domain_type, order=None, subdivlvl=None, time_order=-1, level
         if vb != 0 or deformation is not None or isinstance(levelset, (list, tuple)):
             raise XgpuError("space-time dCut: one level set, volume elements, no deformation")
     return CutDifferentialSymbol(levelset, domain_type, -1 if order is None else int(order), definedonelements, deformation,
-                                 time_order=int(time_order), tref=tref, vb=vb)
+                                 time_order=int(time_order), tref=tref, vb=vb, skeleton=skeleton, element_boundary=element_boundary)
 
 
 class FacetPatchDifferentialSymbol:
@@ -355,6 +522,55 @@ class BilinearForm:
         else:
             raise XgpuError("BilinearForm += expects form * dCut(...) or form * dFacetPatch(...)")
         return self
+
+    def _assemble_facet_integrals(self, skel, tables, mats, ctx):
+        """dCut(lset, NEG|POS, skeleton=True, definedonelements=facets): one (2 nd) x (2 nd) matrix per interior facet over
+        the dofs of both neighbours (T_CalcFacetMatrix, xfem/symboliccutbfi.cpp:886-1290); element_boundary=True: one nd x nd
+        matrix per element, summed over its facets (T_CalcElementMatrixEBAdd, :488-883).  The cut rule of a facet is
+        xgpu_cutquad on the facet-vertex table, order 2 * fe order (:978, :1029) unless given.  returns the BitArray of the
+        facets that carry a skeleton integral (their couplings are in the graph already)."""
+        sp, mesh = self.space, self.space.mesh
+        dim, p, dev = mesh.dim, sp.order, mesh.device
+        if dim < 2:
+            raise XgpuError("facet integrals: 2D / 3D meshes")
+        ents, el_f, fe = mesh.facets()
+        covered = None
+        for integ in skel:
+            dx = integ.dx
+            form = FacetForm.of(integ.form)
+            phi = _lset_vec(dx.levelset, mesh)
+            order = 2 * p if dx.order < 0 else dx.order
+            if dx.skeleton:
+                l_f = dx.definedonelements.indices()
+                l_f = l_f[fe[l_f.long(), 1] >= 0].contiguous()   # interior facets only (LocalFacetNr2 == -1 throws, :913)
+                if l_f.numel() == 0:
+                    continue
+                fv = ents[l_f.long()].to(torch.int32).contiguous()
+                fel = fe[l_f.long()].contiguous()
+                off, q, w = ops.cutquad(dim - 1, None, fv, mesh.points, phi, int(dx.domain_type), order, ctx=ctx)
+                ctx.raise_on_geometry_error()
+                mm = ops.facet_elmat(dim, p, fv, fel, mesh.elements, mesh.points, (off, q, w), form.terms, 2, ctx=ctx)
+                t_f = torch.cat([self._rows(fel[:, 0].contiguous()), self._rows(fel[:, 1].contiguous())], dim=1).contiguous()
+                tables.append(t_f); mats.append(mm)
+                fb = BitArray(mesh.nfacet, mesh.device)
+                fb.bits.copy_(BitArray.from_numpy(_mask_from_list(l_f, mesh.nfacet), mesh.device).bits)
+                covered = fb if covered is None else (covered | fb)
+            else:
+                if any(t[1] != 0 or t[3] != 0 for t in form.terms):
+                    raise XgpuError("element-boundary integrals see the element's own functions only (no .Other())")
+                l_e = dx.definedonelements.indices()
+                if l_e.numel() == 0:
+                    continue
+                nl = dim + 1
+                fids = el_f[l_e.long()].reshape(-1).long()                       # (n * (dim+1)) facet ids, element-major
+                fv = ents[fids].to(torch.int32).contiguous()
+                fel = torch.stack([l_e.repeat_interleave(nl), torch.full((l_e.numel() * nl,), -1, dtype=torch.int32, device=dev)], dim=1).contiguous()
+                off, q, w = ops.cutquad(dim - 1, None, fv, mesh.points, phi, int(dx.domain_type), order, ctx=ctx)
+                ctx.raise_on_geometry_error()
+                mm = ops.facet_elmat(dim, p, fv, fel, mesh.elements, mesh.points, (off, q, w), form.terms, 1, ctx=ctx)
+                nd = sp.nd
+                tables.append(self._rows(l_e.contiguous())); mats.append(mm.reshape(l_e.numel(), nl, nd, nd).sum(dim=1).contiguous())
+        return covered
 
     # ---- helpers
     def _active_elements(self):
@@ -534,7 +750,8 @@ class BilinearForm:
         active = self._active_elements()
 
         # ---- volume (cut) integrators: group per level set; per element ONE matrix summing all integrators
-        vol = [i for i in self.integrals if isinstance(i.dx, CutDifferentialSymbol)]
+        vol = [i for i in self.integrals if isinstance(i.dx, CutDifferentialSymbol) and not (i.dx.skeleton or i.dx.element_boundary)]
+        skel = [i for i in self.integrals if isinstance(i.dx, CutDifferentialSymbol) and (i.dx.skeleton or i.dx.element_boundary)]
         fac = [i for i in self.integrals if isinstance(i.dx, FacetPatchDifferentialSymbol)]
         tables, mats = [], []
         # two batches: U = uncut active elements, C = cut active elements (w.r.t. the level set of the
@@ -557,7 +774,8 @@ class BilinearForm:
             self._assemble_single_lset(vol, active, tables, mats, ctx)
 
         # ---- facet patch integrators
-        _, _, fe = mesh.facets() if (fac or sp.dgjumps or self.facet_restriction is not None) else (None, None, None)
+        _, _, fe = mesh.facets() if (fac or skel or sp.dgjumps or self.facet_restriction is not None) else (None, None, None)
+        skel_cover = self._assemble_facet_integrals(skel, tables, mats, ctx) if skel else None
         graph_facets = None
         if self.facet_restriction is not None:
             graph_facets = self.facet_restriction
@@ -581,7 +799,7 @@ class BilinearForm:
                     facet_mats[key] = (l_f, facet_mats[key][1] + mm)
                 else:
                     facet_mats[key] = (l_f, mm)
-        covered = None
+        covered = skel_cover
         for key, (l_f, mm) in facet_mats.items():
             fel = fe[l_f.long()]
             t_f = torch.cat([self._rows(fel[:, 0].contiguous()), self._rows(fel[:, 1].contiguous())], dim=1).contiguous()

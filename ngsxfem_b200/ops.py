@@ -631,6 +631,24 @@ def rows_add(rowptr, rows, off, buf, vals, ctx=None):
     return vals
 
 
+def facet_elmat(dim, fe_order, facet_vtx, facet_els, el_vtx, vtx_xyz, rule, terms, nsides, ctx=None):
+    """xgpu_facet_elmat: matrices of cut integrals over facets (rule = (offsets, pts, wts) of xgpu_cutquad on the facet-vertex
+    table); terms = [(trial kind, trial side, test kind, test side, coef, hpow)]; returns n x (nsides nd)^2"""
+    ctx = ctx or default_ctx()
+    n = facet_vtx.shape[0]
+    nd = h1_ndof(dim, fe_order)
+    N = nsides * nd
+    mats = torch.empty((n, N, N), dtype=torch.float64, device=facet_vtx.device)
+    ta = (_lib.FTerm * max(1, len(terms)))()
+    for i, t in enumerate(terms):
+        ta[i].trial_kind, ta[i].trial_side, ta[i].test_kind, ta[i].test_side = int(t[0]), int(t[1]), int(t[2]), int(t[3])
+        ta[i].coef, ta[i].hpow = float(t[4]), int(t[5])
+    off, q, w = rule
+    ctx.check(ctx.lib.xgpu_facet_elmat(ctx.h, dim, fe_order, n, ptr(_i32(facet_vtx)), ptr(_i32(facet_els)), ptr(_i32(el_vtx)),
+                                       ptr(_f64(vtx_xyz)), ptr(off), ptr(_f64(q)), ptr(_f64(w)), ta, len(terms), nsides, ptr(mats)))
+    return mats
+
+
 def iface_marks(has_bits, pair_elem, pair_gpos, nflags, ctx=None):
     """activity flags (uint8, nflags) of static interface candidates: flags[pair_gpos[i]] = 1 if element pair_elem[i] is active"""
     ctx = ctx or default_ctx()

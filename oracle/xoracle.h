@@ -133,6 +133,11 @@ int xo_cut_elmat(const xo_trafo* T, int fe_order, const double* lsetvals, int dt
 void xo_elmat_from_rule(const xo_trafo* T, int fe_order, const double* lsetvals,
                         const double* pts, const double* wts, int np,
                         const xo_term* terms, int nterms, double* elmat);
+/* cut integrals over interior facets / element boundaries (xo_facet.c; symboliccutbfi.cpp:886-1290, :488-883).
+ * kind: 0 = value, 1 = nF . grad (nF = outward unit normal of the first element); side: 0 = this element, 1 = .Other() */
+typedef struct { int trial_kind, trial_side, test_kind, test_side; double coef; int hpow; } xo_fterm;
+int xo_cut_facet_elmat(const xo_trafo* T1, const xo_trafo* T2, int fe_order, const int* facet_vnum, const double* lset_facet,
+                       int dt, int order, const xo_fterm* terms, int nterms, double* mat);
 /* space-time FE (spacetime/SpaceTimeFE.cpp:57-135, time-major tensor basis) on a space-time rule: ops ID, GRAD.GRAD,
  * XO_OP_DT (reference-time derivative).  nd = nd_s*(time_fe_order+1); ADDS into elmat / elvec. */
 enum { XO_OP_DT = 3 };

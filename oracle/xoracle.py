@@ -207,6 +207,15 @@ def h1_shapes(dim, order, vnum, xhat):
     return sh, dsh
 
 
+def trafo_eval(T, xhat):
+    """(F dim x dim, x) of the element transformation at xhat"""
+    F = np.zeros(9); x = np.zeros(3)
+    xh = np.zeros(3); xh[:len(xhat)] = xhat
+    lib().xo_trafo_eval(C.byref(T), _p(xh), _p(F), _p(x))
+    d = T.dim
+    return F[:d * d].reshape(d, d).copy(), x[:d].copy()
+
+
 def terms_array(terms):
     arr = (Term * len(terms))()
     for i, (ou, ot, c, hp) in enumerate(terms):
@@ -234,6 +243,31 @@ def elmat_from_rule(T, fe_order, lsetvals, pts, wts, terms, out=None):
     ta = terms_array(terms)
     lib().xo_elmat_from_rule(C.byref(T), fe_order, _p(v), _p(pts), _p(wts), len(wts), ta, len(terms), _p(m))
     return m
+
+
+class FTerm(C.Structure):
+    _fields_ = [("trial_kind", C.c_int), ("trial_side", C.c_int), ("test_kind", C.c_int), ("test_side", C.c_int),
+                ("coef", C.c_double), ("hpow", C.c_int)]
+
+
+def cut_facet_elmat(T1, T2, fe_order, facet_vnum, lset_facet, dt, order, terms):
+    """xo_cut_facet_elmat (symboliccutbfi.cpp:886-1290 / :488-883): terms = [(trial_kind, trial_side, test_kind, test_side,
+    coef, hpow)], kind 0 = value / 1 = nF.grad, side 0 = this element / 1 = .Other(); T2 None = one-sided (element boundary).
+    returns (matrix (ns*nd)^2 rows = test, number of points)"""
+    nd = h1_ndof(T1.dim, fe_order)
+    N = nd * (2 if T2 is not None else 1)
+    m = np.zeros((N, N))
+    ta = (FTerm * max(1, len(terms)))()
+    for i, t in enumerate(terms):
+        ta[i].trial_kind, ta[i].trial_side, ta[i].test_kind, ta[i].test_side = int(t[0]), int(t[1]), int(t[2]), int(t[3])
+        ta[i].coef, ta[i].hpow = float(t[4]), int(t[5])
+    fv = np.ascontiguousarray(facet_vnum, dtype=np.int32)
+    ls = _f64(lset_facet)
+    n = lib().xo_cut_facet_elmat(C.byref(T1), C.byref(T2) if T2 is not None else None, fe_order,
+                                 fv.ctypes.data_as(C.POINTER(C.c_int)), _p(ls), dt, order, ta, len(terms), _p(m))
+    if n < 0:
+        raise RuntimeError(f"oracle error {n}")
+    return m, n
 
 
 class LTerm(C.Structure):
