@@ -140,8 +140,9 @@ class Proxy:
             return self._with(op=OP_FDN)
         if isinstance(o, FacetExpr):
             return o * self
-        if isinstance(o, Proxy) and (self.other or o.other or OP_FDN in (self.op, o.op)):
-            return FacetExpr.of(self) * o
+        if isinstance(o, Proxy) and (self.other or o.other or OP_FDN in (self.op, o.op)
+                                     or (OP_JUMP in (self.op, o.op) and self.op != o.op and OP_GRAD not in (self.op, o.op))):
+            return FacetExpr.of(self) * o   # traces on a facet: (u - u.Other()) * v, grad(u)*nF * (v - v.Other()), ...
         if isinstance(o, Proxy):
             return Form.from_pair(self, o)
         if isinstance(o, Form):
