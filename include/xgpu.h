@@ -57,6 +57,15 @@ int xgpu_set_stream(xgpu_ctx* ctx, void* cuda_stream);
  * thread-per-row kernel (default 1; they take disjoint rows).  "elmat_st_tp": space-time element
  * matrices on the tensor-structured kernel where instantiated (default 1; 0 = always the generic kernel) */
 int xgpu_set_option(xgpu_ctx* ctx, const char* key, int value);
+/* counters of a context (the reference has RegionTimer / static Timer objects, xfem/symboliccutbfi.cpp:88,495):
+ * kernels launched, instrumented entry points called (each is an NVTX range "xgpu_<name>"), plans created, bytes of the
+ * grow-only scratch arena, and the sticky geometry status (code + first failing element, as xgpu_get_status).  Synchronises. */
+typedef struct {
+  int64_t kernel_launches, api_calls, plans_created, scratch_bytes;
+  int status_code;
+  int64_t status_element;
+} xgpu_stats;
+int xgpu_get_stats(xgpu_ctx* ctx, xgpu_stats* out);
 /* Isoparametric mesh deformation — the state NGSolve keeps in the mesh (`mesh.SetDeformation(gf)`, set and
  * unset around every assembly by the `deformation=` argument of dCut / dFacetPatch / Integrate,
  * python/__init__.py:361-439,749-864; cutint/cutintegral.cpp:126-212): while set, every geometric call
@@ -189,6 +198,7 @@ int xgpu_integrate_monomial_bnd(xgpu_ctx* ctx, int dim, int sdim, int64_t n, con
  * n = grad(lset_p1)/|grad(lset_p1)|; h = |det F|^(1/dim).  mats: n x nd x nd, row-major,
  * rows = test, cols = trial.  accumulate!=0 ADDS into mats (CalcElementMatrixAdd).  slots (nullable):
  * matrix i is written to mats[slots[i]] instead of mats[i] (several integrators, one batch). */
+enum { XGPU_OP_ID = 0, XGPU_OP_GRAD = 1, XGPU_OP_DN = 2 };
 typedef struct { int op_trial, op_test; double coef; int hpow; } xgpu_term;
 /* per-element rules (cut elements): offsets/pts/wts from xgpu_cutquad_* */
 int xgpu_elmat_rule(xgpu_ctx* ctx, int dim, int fe_order, int64_t n, const int32_t* elems,

@@ -40,6 +40,11 @@ class FTerm(C.Structure):
                 ("coef", C.c_double), ("hpow", C.c_int)]
 
 
+class Stats(C.Structure):
+    _fields_ = [("kernel_launches", C.c_int64), ("api_calls", C.c_int64), ("plans_created", C.c_int64), ("scratch_bytes", C.c_int64),
+                ("status_code", C.c_int), ("status_element", C.c_int64)]
+
+
 class Batch(C.Structure):
     _fields_ = [("table", VP), ("mats", VP), ("nrows", C.c_int64), ("width", C.c_int), ("coefs", VP)]
 
@@ -55,6 +60,7 @@ _SIGS = {
     "xgpu_get_status": (C.c_int, [VP, c_intp, c_i64p]),
     "xgpu_clear_status": (C.c_int, [VP]),
     "xgpu_launch_count": (C.c_int64, [VP]),
+    "xgpu_get_stats": (C.c_int, [VP, C.POINTER(Stats)]),
     "xgpu_version": (C.c_char_p, []),
     "xgpu_rule_size": (C.c_int, [VP, C.c_int, C.c_int]),
     "xgpu_get_rule": (C.c_int, [VP, C.c_int, C.c_int, c_f64p, c_f64p]),
@@ -185,6 +191,12 @@ class Ctx:
         if s != getattr(self, "_stream", None):
             self.check(self.lib.xgpu_set_stream(self.h, VP(s)))
             self._stream = s
+
+    def stats(self):
+        """xgpu_get_stats as a dict"""
+        st = Stats()
+        self.check(self.lib.xgpu_get_stats(self.h, C.byref(st)))
+        return {k: getattr(st, k) for k, _ in Stats._fields_}
 
     def set_option(self, key, value):
         self.check(self.lib.xgpu_set_option(self.h, key.encode(), int(value)))

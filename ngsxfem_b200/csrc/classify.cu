@@ -294,6 +294,7 @@ inline unsigned nblk(int64_t n, int t) { return (unsigned)((n + t - 1) / t); }
 extern "C" int xgpu_classify(xgpu_ctx* ctx, int dim, int64_t ne, const int32_t* el_vtx, const double* phi,
                              uint32_t* bits_neg, uint32_t* bits_pos, uint32_t* bits_if, double* cut_ratio)
 {
+  XGPU_NVTX(ctx, "xgpu_classify");
   if (!ctx || dim < 1 || dim > 3 || ne < 0) return xgpu_fail(ctx, XGPU_ERR_ARG, "xgpu_classify: bad argument");
   if (ne == 0) return XGPU_OK;
   const xgpu_rule_host* r0 = xgpu_rule_lookup(ctx, dim, 0);
@@ -362,6 +363,7 @@ static int word_offsets(xgpu_ctx* ctx, const uint32_t* bits, int64_t nwords, int
 
 extern "C" int xgpu_bitset_to_list(xgpu_ctx* ctx, const uint32_t* bits, int64_t nbits, int32_t* list)
 {
+  XGPU_NVTX(ctx, "xgpu_bitset_to_list");
   if (!ctx) return XGPU_ERR_ARG;
   const int64_t nwords = (nbits + 31) >> 5;
   if (nwords == 0) return XGPU_OK;

@@ -19,11 +19,23 @@ struct xgpu_rule_host {
   double* d_wts = nullptr;
 };
 
+#include <nvtx3/nvToolsExt.h>
+
+struct xgpu_ctx;
+// NVTX range around an entry point (visible in Nsight Systems / ncu --nvtx) + the context's call counter (xgpu_get_stats)
+struct XgpuRange {
+  XgpuRange(xgpu_ctx* ctx, const char* name);
+  ~XgpuRange() { nvtxRangePop(); }
+};
+#define XGPU_NVTX(ctx, name) XgpuRange xgpu_nvtx_range_(ctx, name)
+
 struct xgpu_ctx {
   int device = 0;
   cudaStream_t stream = 0;
   std::string err;
   int64_t launches = 0;
+  int64_t api_calls = 0;      // entry points wrapped in XGPU_NVTX
+  int64_t plans_created = 0;
   // device status: [0] = code, [1] = pad ; elem as unsigned long long min
   int* d_status = nullptr;               // 2 ints
   unsigned long long* d_status_elem = nullptr;
@@ -50,6 +62,12 @@ struct xgpu_ctx {
   std::map<std::pair<int, int>, xgpu_rule_host> rules;  // (dim, order) -> rule
   std::map<int, void*> reftensors;                     // cached reference tensors (device)
 };
+
+inline XgpuRange::XgpuRange(xgpu_ctx* ctx, const char* name)
+{
+  if (ctx) ctx->api_calls++;
+  nvtxRangePushA(name);
+}
 
 inline int xgpu_fail(xgpu_ctx* ctx, int code, const char* msg)
 {

@@ -707,6 +707,7 @@ static int build_plan(xgpu_ctx* ctx, int64_t ndof, const xgpu_batch* batches_hos
 extern "C" int xgpu_csr_plan(xgpu_ctx* ctx, int64_t ndof, const xgpu_batch* batches_host, int nbatches,
                              xgpu_plan** plan_out, int64_t* nnz_host)
 {
+  XGPU_NVTX(ctx, "xgpu_csr_plan");
   return build_plan(ctx, ndof, batches_host, nbatches, plan_out, nnz_host, true);
 }
 
@@ -758,6 +759,7 @@ static int build_plan(xgpu_ctx* ctx, int64_t ndof, const xgpu_batch* batches_hos
     return xgpu_fail(ctx, XGPU_ERR_ARG, "xgpu_csr_plan: bad argument (0 <= ndof < 2^31: column indices are int32)");
   *plan_out = nullptr;
   xgpu_plan* P = new xgpu_plan();
+  ctx->plans_created++;
   int rc = fill_bd(ctx, batches_host, nbatches, P->bd);
   if (rc) { delete P; return rc; }
   P->ndof = ndof;
@@ -859,6 +861,7 @@ extern "C" int xgpu_csr_scatter(xgpu_ctx* ctx, xgpu_plan* P, const xgpu_batch* b
 extern "C" int xgpu_csr_assemble(xgpu_ctx* ctx, xgpu_plan* P, const xgpu_batch* batches_host, int nbatches,
                                  int64_t* rowptr, int32_t* colidx, double* vals)
 {
+  XGPU_NVTX(ctx, "xgpu_csr_assemble");
   if (!ctx || !P || !P->with_pattern) return xgpu_fail(ctx, XGPU_ERR_ARG, "xgpu_csr_assemble: bad argument");
   XGPU_CUDA(ctx, cudaMemcpyAsync(rowptr, P->rowptr, sizeof(long long) * (P->ndof + 1), cudaMemcpyDeviceToDevice, ctx->stream));
   if (P->ndof == 0 || P->nnz == 0) return XGPU_OK;

@@ -414,6 +414,7 @@ static int count_rows(xgpu_ctx* ctx, xgpu_plan* P, int64_t* nnz_host);
 
 extern "C" int xgpu_csr_count_rows(xgpu_ctx* ctx, xgpu_plan* P, int64_t* nnz_host)
 {
+  XGPU_NVTX(ctx, "xgpu_csr_count_rows");
   if (!ctx || !P) return xgpu_fail(ctx, XGPU_ERR_ARG, "xgpu_csr_count_rows: bad argument");
   if (P->counted) { if (nnz_host) *nnz_host = P->nnz; return XGPU_OK; }
   return count_rows(ctx, P, nnz_host);
@@ -422,6 +423,7 @@ extern "C" int xgpu_csr_count_rows(xgpu_ctx* ctx, xgpu_plan* P, int64_t* nnz_hos
 extern "C" int xgpu_csr_plan_rows(xgpu_ctx* ctx, int64_t ndof, const xgpu_batch* batches_host, int nbatches,
                                   xgpu_plan** plan_out, int64_t* nnz_host)
 {
+  XGPU_NVTX(ctx, "xgpu_csr_plan_rows");
   if (!plan_out) return xgpu_fail(ctx, XGPU_ERR_ARG, "xgpu_csr_plan_rows: bad argument");
   int rc = xgpu_adjacency_plan(ctx, ndof, batches_host, nbatches, plan_out);
   if (rc) return rc;
@@ -508,6 +510,7 @@ static int count_rows(xgpu_ctx* ctx, xgpu_plan* P, int64_t* nnz_host)
 extern "C" int xgpu_csr_assemble_fused(xgpu_ctx* ctx, xgpu_plan* P, const xgpu_batch* batches_host, int nbatches,
                                        const double* tref, int ncoef, int64_t* rowptr, int32_t* colidx, double* vals)
 {
+  XGPU_NVTX(ctx, "xgpu_csr_assemble_fused");
   if (!ctx || !P || !batches_host || nbatches != P->bd.nb || !rowptr)
     return xgpu_fail(ctx, XGPU_ERR_ARG, "xgpu_csr_assemble_fused: bad argument");
   if (!P->counted) return xgpu_fail(ctx, XGPU_ERR_ARG, "xgpu_csr_assemble_fused: the plan has no row counts (build it with xgpu_csr_plan_rows)");

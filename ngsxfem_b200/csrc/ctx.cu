@@ -258,6 +258,24 @@ extern "C" int xgpu_get_status(xgpu_ctx* ctx, int* code_host, int64_t* elem_host
   return XGPU_OK;
 }
 
+extern "C" int xgpu_get_stats(xgpu_ctx* ctx, xgpu_stats* out)
+{
+  if (!ctx || !out) return XGPU_ERR_ARG;
+  int code = 0;
+  int64_t elem = -1;
+  int rc = xgpu_get_status(ctx, &code, &elem);
+  if (rc) return rc;
+  out->kernel_launches = ctx->launches;
+  out->api_calls = ctx->api_calls;
+  out->plans_created = ctx->plans_created;
+  size_t sb = 0;
+  for (int i = 0; i < XGPU_NSCRATCH; i++) sb += ctx->scratch_bytes[i];
+  out->scratch_bytes = (int64_t)sb;
+  out->status_code = code;
+  out->status_element = elem;
+  return XGPU_OK;
+}
+
 extern "C" int xgpu_rule_size(xgpu_ctx* ctx, int dim, int order)
 {
   if (!ctx) return XGPU_ERR_ARG;

@@ -194,6 +194,7 @@ extern "C" int xgpu_facet_elmat(xgpu_ctx* ctx, int dim, int fe_order, int64_t n,
                                 const int32_t* el_vtx, const double* vtx_xyz, const int64_t* offsets, const double* pts,
                                 const double* wts, const xgpu_fterm* terms_host, int nterms, int nsides, double* mats)
 {
+  XGPU_NVTX(ctx, "xgpu_facet_elmat");
   if (!ctx || dim < 2 || dim > 3 || fe_order < 1 || fe_order > 4 || n < 0 || (nsides != 1 && nsides != 2) || nterms < 0 ||
       nterms > XF_MAXT || (nterms > 0 && !terms_host) || (n > 0 && (!facet_vtx || !facet_els || !offsets || !mats)))
     return xgpu_fail(ctx, XGPU_ERR_ARG, "xgpu_facet_elmat: bad argument (dim 2, 3; orders 1..4; at most 16 terms)");

@@ -296,6 +296,7 @@ int xgpu_sum_f64(xgpu_ctx* ctx, double* buf_a, int64_t n, double* buf_b, double*
 extern "C" int xgpu_cutquad_count(xgpu_ctx* ctx, int dim, int64_t n, const int32_t* elems, const int32_t* el_vtx,
                                   const double* phi, int dt, int order, int64_t* offsets, int64_t* total_host)
 {
+  XGPU_NVTX(ctx, "xgpu_cutquad_count");
   if (!ctx || dim < 1 || dim > 3 || dt < 0 || dt > 2) return xgpu_fail(ctx, XGPU_ERR_ARG, "xgpu_cutquad_count: bad argument");
   if (total_host) *total_host = 0;
   const xgpu_rule_host* rv = xgpu_rule_lookup(ctx, dim, order);
@@ -325,6 +326,7 @@ extern "C" int xgpu_cutquad_fill(xgpu_ctx* ctx, int dim, int64_t n, const int32_
                                  const double* vtx_xyz, const double* phi, int dt, int order,
                                  const int64_t* offsets, double* pts, double* wts)
 {
+  XGPU_NVTX(ctx, "xgpu_cutquad_fill");
   if (!ctx || dim < 1 || dim > 3 || dt < 0 || dt > 2) return xgpu_fail(ctx, XGPU_ERR_ARG, "xgpu_cutquad_fill: bad argument");
   if (n == 0) return XGPU_OK;
   const xgpu_rule_host* rv = xgpu_rule_lookup(ctx, dim, order);

@@ -560,6 +560,7 @@ extern "C" int xgpu_cutquad_ml_fill(xgpu_ctx* ctx, int dim, int64_t n, const int
                                     const double* vtx_xyz, const double* phis, int64_t nv, int M, const int* dts_host,
                                     int ntuples, int order, const int64_t* offsets, double* pts, double* wts)
 {
+  XGPU_NVTX(ctx, "xgpu_cutquad_ml_fill");
   if (!ctx || dim < 1 || dim > 3 || n < 0) return xgpu_fail(ctx, XGPU_ERR_ARG, "xgpu_cutquad_ml_fill: bad argument");
   if (ctx->def_order > 0) return xgpu_fail(ctx, XGPU_ERR_UNSUPPORTED, "xgpu_cutquad_ml_fill: no deformation support (unset it)");
   if (n == 0) return XGPU_OK;
@@ -596,6 +597,7 @@ extern "C" int xgpu_cutquad_st_fill(xgpu_ctx* ctx, int dim, int64_t n, const int
                                     int order_time, int order_space, const int64_t* offsets, double* pts, double* tvals,
                                     double* wts)
 {
+  XGPU_NVTX(ctx, "xgpu_cutquad_st_fill");
   if (ctx && ctx->def_order > 0) return xgpu_fail(ctx, XGPU_ERR_UNSUPPORTED, "xgpu_cutquad_st_fill: no deformation support (unset it)");
   if (!ctx || dim < 1 || dim > 3 || n < 0 || dt < 0 || dt > 2 || time_fe_order < 0 || time_fe_order > XG_ST_MAXORD)
     return xgpu_fail(ctx, XGPU_ERR_ARG, "xgpu_cutquad_st_fill: bad argument (time order <= 8)");
@@ -613,6 +615,7 @@ extern "C" int xgpu_classify_st(xgpu_ctx* ctx, int dim, int64_t ne, const int32_
                                 int time_fe_order, int time_order, uint32_t* bits_neg, uint32_t* bits_pos, uint32_t* bits_if,
                                 double* cut_ratio)
 {
+  XGPU_NVTX(ctx, "xgpu_classify_st");
   if (!ctx || dim < 1 || dim > 3 || ne < 0 || time_fe_order < 0 || time_fe_order > XG_ST_MAXORD || !bits_neg || !bits_pos || !bits_if)
     return xgpu_fail(ctx, XGPU_ERR_ARG, "xgpu_classify_st: bad argument (time order <= 8)");
   if (ne == 0) return XGPU_OK;

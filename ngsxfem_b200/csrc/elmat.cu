@@ -113,6 +113,7 @@ extern "C" int xgpu_elmat_rule(xgpu_ctx* ctx, int dim, int fe_order, int64_t n, 
                                const int64_t* offsets, const double* pts, const double* wts,
                                const xgpu_term* terms_host, int nterms, int accumulate, const int32_t* slots, double* mats)
 {
+  XGPU_NVTX(ctx, "xgpu_elmat_rule");
   if (!ctx || dim < 1 || dim > 3 || fe_order < 1 || fe_order > XG_MAX_ORDER || !offsets)
     return xgpu_fail(ctx, XGPU_ERR_ARG, "xgpu_elmat_rule: bad argument (orders 1..4)");
   if (n == 0) return XGPU_OK;
@@ -143,6 +144,7 @@ extern "C" int xgpu_elmat_rule_pair(xgpu_ctx* ctx, int dim, int fe_order, int64_
                                     const xgpu_term* terms_b_host, int nterms_b,
                                     int accumulate, const int32_t* slots, double* mats)
 {
+  XGPU_NVTX(ctx, "xgpu_elmat_rule_pair");
   if (!ctx || dim < 1 || dim > 3 || fe_order < 1 || fe_order > XG_MAX_ORDER || !offsets_a || !offsets_b)
     return xgpu_fail(ctx, XGPU_ERR_ARG, "xgpu_elmat_rule_pair: bad argument (orders 1..4)");
   if (n == 0) return XGPU_OK;
@@ -213,6 +215,7 @@ __global__ void __launch_bounds__(256) k_affine_coefs(int64_t n, const int32_t* 
 extern "C" int xgpu_affine_coefs(xgpu_ctx* ctx, int dim, int64_t n, const int32_t* elems, const int32_t* el_vtx,
                                  const double* vtx_xyz, const xgpu_term* terms_host, int nterms, double* coefs)
 {
+  XGPU_NVTX(ctx, "xgpu_affine_coefs");
   if (!ctx || dim < 1 || dim > 3 || n < 0 || (n > 0 && !coefs)) return xgpu_fail(ctx, XGPU_ERR_ARG, "xgpu_affine_coefs: bad argument");
   if (ctx->def_order != 0) return xgpu_fail(ctx, XGPU_ERR_UNSUPPORTED, "xgpu_affine_coefs: the mesh is deformed (elements are not affine)");
   if (n == 0) return XGPU_OK;
@@ -240,6 +243,7 @@ extern "C" int xgpu_elmat_std(xgpu_ctx* ctx, int dim, int fe_order, int64_t n, c
                               const int32_t* el_vtx, const double* vtx_xyz, const double* phi, int order,
                               const xgpu_term* terms_host, int nterms, int accumulate, const int32_t* slots, double* mats)
 {
+  XGPU_NVTX(ctx, "xgpu_elmat_std");
   if (!ctx || dim < 1 || dim > 3 || fe_order < 1 || fe_order > XG_MAX_ORDER)
     return xgpu_fail(ctx, XGPU_ERR_ARG, "xgpu_elmat_std: bad argument (orders 1..4)");
   if (n == 0) return XGPU_OK;

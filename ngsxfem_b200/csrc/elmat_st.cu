@@ -73,6 +73,7 @@ extern "C" int xgpu_elmat_st(xgpu_ctx* ctx, int dim, int fe_order, int time_fe_o
                              const double* tvals, const double* wts, const xgpu_term* terms_host, int nterms,
                              int accumulate, const int32_t* slots, double* mats)
 {
+  XGPU_NVTX(ctx, "xgpu_elmat_st");
   int rc = st_check(ctx, dim, fe_order, time_fe_order, n, offsets, tvals, "xgpu_elmat_st: bad argument (space orders 1..4, time orders 0..3)");
   if (rc) return rc;
   if (nterms < 0 || nterms > XG_ST_MAXTERMS) return xgpu_fail(ctx, XGPU_ERR_ARG, "xgpu_elmat_st: too many terms (max 8)");

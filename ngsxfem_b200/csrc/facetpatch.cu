@@ -13,6 +13,7 @@ extern "C" int xgpu_facetpatch(xgpu_ctx* ctx, int dim, int fe_order, int64_t n, 
                                const int32_t* facet_els, const int32_t* el_vtx, const double* vtx_xyz,
                                int order, double coef, int hpow, double* mats)
 {
+  XGPU_NVTX(ctx, "xgpu_facetpatch");
   if (!ctx || dim < 1 || dim > 3 || fe_order < 1 || fe_order > XG_MAX_ORDER)
     return xgpu_fail(ctx, XGPU_ERR_ARG, "xgpu_facetpatch: bad argument (orders 1..4)");
   if (n == 0) return XGPU_OK;

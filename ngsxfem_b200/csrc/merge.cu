@@ -92,6 +92,7 @@ __global__ void k_l2g_ghosts(int64_t n, const int32_t* __restrict__ dofmap_range
 extern "C" int xgpu_iface_marks(xgpu_ctx* ctx, const uint32_t* has_bits, int64_t npairs, const int32_t* pair_elem,
                                 const int32_t* pair_gpos, int64_t nflags, uint8_t* flags)
 {
+  XGPU_NVTX(ctx, "xgpu_iface_marks");
   if (!ctx || npairs < 0 || nflags < 0 || (nflags > 0 && !flags)) return xgpu_fail(ctx, XGPU_ERR_ARG, "xgpu_iface_marks: bad argument");
   if (nflags == 0) return XGPU_OK;
   XGPU_CUDA(ctx, cudaMemsetAsync(flags, 0, (size_t)nflags, ctx->stream));
@@ -165,6 +166,7 @@ extern "C" int xgpu_rows_offsets(xgpu_ctx* ctx, int64_t n, const int64_t* rowptr
 extern "C" int xgpu_rows_pack(xgpu_ctx* ctx, int64_t n, const int64_t* rowptr, const int32_t* rows, const int64_t* offsets,
                               const double* vals, double* out)
 {
+  XGPU_NVTX(ctx, "xgpu_rows_pack");
   if (!ctx || n < 0) return xgpu_fail(ctx, XGPU_ERR_ARG, "xgpu_rows_pack: bad argument");
   if (n == 0) return XGPU_OK;
   unsigned grid = nblk(n, 8);
@@ -178,6 +180,7 @@ extern "C" int xgpu_rows_pack(xgpu_ctx* ctx, int64_t n, const int64_t* rowptr, c
 extern "C" int xgpu_rows_add(xgpu_ctx* ctx, int64_t n, const int64_t* rowptr, const int32_t* rows, const int64_t* offsets,
                              const double* in, double* vals)
 {
+  XGPU_NVTX(ctx, "xgpu_rows_add");
   if (!ctx || n < 0) return xgpu_fail(ctx, XGPU_ERR_ARG, "xgpu_rows_add: bad argument");
   if (n == 0) return XGPU_OK;
   unsigned grid = nblk(n, 8);

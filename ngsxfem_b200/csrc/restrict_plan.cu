@@ -101,6 +101,7 @@ extern "C" int xgpu_restrict_plan(xgpu_ctx* ctx, int nd, const int32_t* el_dofs,
                                   const int64_t* counts_host, int64_t ndof_full, int32_t* dofmap, int64_t* ndof_host,
                                   int32_t* const* tables_host, xgpu_plan** plan_out)
 {
+  XGPU_NVTX(ctx, "xgpu_restrict_plan");
   if (!ctx || nd < 1 || nd > 255 || !el_dofs || nlists < 1 || nlists > XG_MAXBATCH || !counts_host || ndof_full < 0 ||
       ndof_full >= (int64_t)0x7fffffff || !dofmap || !ndof_host || !tables_host || !plan_out)
     return xgpu_fail(ctx, XGPU_ERR_ARG, "xgpu_restrict_plan: bad argument");
@@ -148,6 +149,7 @@ extern "C" int xgpu_restrict_plan(xgpu_ctx* ctx, int nd, const int32_t* el_dofs,
   *ndof_host = ndof;
   // 3.-5. the transposed table of the compressed dof rows
   xgpu_plan* P = new xgpu_plan();
+  ctx->plans_created++;
   P->ndof = ndof;
   P->wmax = nd;
   P->stream = st;

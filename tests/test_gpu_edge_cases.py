@@ -85,3 +85,17 @@ def test_empty_lists_on_every_batched_entry_point():
     f = xf.LinearForm(V)
     f += 1.0 * v * xf.dCut(xf.GridFunction(mesh, phi), xf.NEG, definedonelements=none)
     assert f.Assemble().vec.numel() == 0
+
+
+def test_context_stats_count_calls_launches_and_carry_the_status():
+    """xgpu_get_stats: NVTX-wrapped entry points and kernel launches are counted, the sticky geometry status comes along"""
+    import ngsxfem_b200 as xf
+    from ngsxfem_b200 import ops
+    ctx = ops.default_ctx()
+    s0 = ctx.stats()
+    mesh = xf.MakeStructured2DMesh(nx=4, ny=4, device="cuda:0")
+    phi = (mesh.points[:, 0] - 0.3).contiguous()
+    ops.classify(2, mesh.elements, phi, ctx=ctx)
+    s1 = ctx.stats()
+    assert s1["api_calls"] > s0["api_calls"] and s1["kernel_launches"] > s0["kernel_launches"]
+    assert s1["status_code"] == 0 and s1["status_element"] == -1 and s1["scratch_bytes"] >= 0
