@@ -154,8 +154,8 @@ def kernel_bytes(phase, r, nd, ne=None, ndof_full=None):
         return int((ne or 0) * 56.4)
     if phase == "cutquad":
         return n_if * 2 * 48 + npts * 32
-    if phase == "elmat_cut":
-        return n_if * (16 + 96 + 32 + 40 + nn * 8) + npts * 32
+    if phase == "elmat_cut":     # connectivity, level set, coordinates in, one matrix out (+ the stored rules when they are read)
+        return n_if * (16 + 96 + 32 + 40 + nn * 8) + (npts * 32 if r.get("rules_stored") else 0)
     if phase == "affine_coefs":
         return n_neg * (16 + 96 + 64)
     if phase == "csr":           # distributed path (two-pass backend): plan + pattern + scatter timed as one phase
@@ -194,6 +194,7 @@ def run_gpu(args):
     n = args.n
     nd = 10
     check = None
+    conc = False
     if world == 1:
         mesh = xf.MakeStructured3DMesh(nx=n, device=dev)
         V0 = xf.H1(mesh, order=2)
@@ -202,7 +203,10 @@ def run_gpu(args):
         hb = HostBuffers(mesh.elements, mesh.points, V0.el_dofs, phi)
         ne_loc, ndof_full = mesh.ne, V0.ndof
         # timed: the production configuration (cut-element branch on a side stream); instrumented: one stream, per phase
-        step_dev = lambda t: prob.step(phi, timer=t, concurrent=(t is None))
+        # production step: ONE stream.  The cut-element branch on a low-priority side stream (XGPU_CONCURRENT=1) gave 5.44-7.76 ms
+        # run to run against a steady 5.52 ms (profiles/r02_notes.md): its kernel fills the register file, so nothing co-resides
+        conc = os.environ.get("XGPU_CONCURRENT", "0") == "1"
+        step_dev = lambda t: prob.step(phi, timer=t, concurrent=(t is None) and conc)
 
         def step_e2e():
             # steps are software-pipelined: the H2D + kernels of step k+1 overlap the D2H of step k (alternating landing
@@ -320,6 +324,8 @@ def run_gpu(args):
     if "npts" not in res:
         res["npts"] = (0, 0)
         res["ndof"] = res["ndof_local"]
+    elif res["npts"][0] is None:   # cut rules made on the fly: the point counts are reporting only, taken here (untimed)
+        res["npts"] = prob.cut_point_counts(phi)
     kb_of = lambda k: kernel_bytes(k, res, nd, ne=ne_loc, ndof_full=ndof_full)
     dom = max((k for k in phases if kb_of(k)), key=lambda k: phases[k])
     for k in ("vals", "col", "rowptr"):
@@ -378,7 +384,7 @@ def run_gpu(args):
             pk64, src64 = fp64_peak()
             fl = sum(res["npts"]) * 950.0
             a64 = fl / (phases["elmat_cut"] * 1e-3) / 1e12
-            roof_fp64 = {"kernel": "elmat_cut (k_elmat_ms)", "bound": "fp64", "achieved": a64, "peak": pk64, "unit": "TFLOP/s",
+            roof_fp64 = {"kernel": "elmat_cut (k_elmat_cut: cut rule + contraction, one lane per point)", "bound": "fp64", "achieved": a64, "peak": pk64, "unit": "TFLOP/s",
                          "frac": a64 / pk64, "peak_source": src64, "flops_per_launch": fl, "ms_per_launch": phases["elmat_cut"]}
         cpu_baseline = None
         if world == 1 and not args.no_cpu:  # the CPU arm is timed on rank 0 at N=1 only (other ranks would compete for the host cores)
@@ -401,7 +407,7 @@ def run_gpu(args):
                        "units_per_step_per_gpu": units, "n_neg": res["n_neg"], "n_if": res["n_if"],
                        "ndof": res["ndof"], "nnz": res["nnz"], "cut_points": list(res["npts"]),
                        "l2_policy": "inputs+outputs of a step (>5 GB) exceed the 126 MB L2; no flush needed",
-                       "timed_region": "production step (cut-element branch on a low-priority side stream)" if world == 1 else "distributed step",
+                       "timed_region": ("production step, one stream" if not conc else "production step (cut-element branch on a low-priority side stream)") if world == 1 else "distributed step",
                        "phases_ms": {k: round(v, 4) for k, v in phases.items()},
                        "phases_note": "instrumented steps on one stream after the timed loop; they sum to slightly more than ms_per_step",
                        **({"phases_ms_max_over_ranks": phases_max} if phases_max else {})},

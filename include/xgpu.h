@@ -54,7 +54,8 @@ int xgpu_set_stream(xgpu_ctx* ctx, void* cuda_stream);
  * "csr_trips": one-pass CSR lane-group kernels, 2 = half-width lane groups with two columns per
  * lane (0 = policy).  "csr_closed_form": one-pass CSR, rows of procedural affine P2-tet batches from the closed-form barycentric
  * expressions instead of the reference tensors (default 1; equal up to rounding).  "csr_fork": one-pass CSR, the warp-per-row kernel runs on an internal second stream next to the
- * thread-per-row kernel (default 1; they take disjoint rows).  "elmat_st_tp": space-time element
+ * thread-per-row kernel (default 1; they take disjoint rows).  "elmat_lp": cut-element matrices at order <= 2 on the lane-per-point kernel
+ * (default 1; 0 = the staged half-warp kernel).  "elmat_st_tp": space-time element
  * matrices on the tensor-structured kernel where instantiated (default 1; 0 = always the generic kernel) */
 int xgpu_set_option(xgpu_ctx* ctx, const char* key, int value);
 /* counters of a context (the reference has RegionTimer / static Timer objects, xfem/symboliccutbfi.cpp:88,495):
@@ -216,6 +217,19 @@ int xgpu_elmat_rule_pair(xgpu_ctx* ctx, int dim, int fe_order, int64_t n, const 
                          const int64_t* offsets_b, const double* pts_b, const double* wts_b,
                          const xgpu_term* terms_b_host, int nterms_b,
                          int accumulate, const int32_t* slots, double* mats);
+/* cut rules made ON THE FLY — what T_CalcElementMatrixAdd does: it calls CreateCutIntegrationRule for the element at hand
+ * and contracts at once, no rule is ever stored (xfem/symboliccutbfi.cpp:105-121; cutint/straightcutrule.cpp:131-196,
+ * 503-677).  Up to two integrators over the same element list in one pass (dt_b < 0: one): domain type, quadrature order
+ * and terms each; a listed element that is not cut gets the standard rule if its type equals dt_x and nothing otherwise,
+ * exactly as xgpu_cutquad_* would hand it on.  Same matrices as xgpu_cutquad_count/_fill + xgpu_elmat_rule_pair (to
+ * rounding), without the 32 B per quadrature point written and read back.  fe_order 1..2, ID*ID and GRAD.GRAD terms,
+ * affine mesh; anything else returns XGPU_ERR_UNSUPPORTED (the caller takes the two-step path).  Geometry errors are
+ * recorded in the sticky status (xgpu_get_status) like those of xgpu_cutquad_fill. */
+int xgpu_elmat_cut_pair(xgpu_ctx* ctx, int dim, int fe_order, int64_t n, const int32_t* elems,
+                        const int32_t* el_vtx, const double* vtx_xyz, const double* phi,
+                        int dt_a, int order_a, const xgpu_term* terms_a_host, int nterms_a,
+                        int dt_b, int order_b, const xgpu_term* terms_b_host, int nterms_b,
+                        int accumulate, const int32_t* slots, double* mats);
 /* uncut elements: the shared standard rule of `order` on every listed element */
 int xgpu_elmat_std(xgpu_ctx* ctx, int dim, int fe_order, int64_t n, const int32_t* elems,
                    const int32_t* el_vtx, const double* vtx_xyz, const double* phi, int order,

@@ -98,6 +98,8 @@ _SIGS = {
                                   C.c_int, C.c_int, VP, VP]),
     "xgpu_elmat_rule_pair": (C.c_int, [VP, C.c_int, C.c_int, C.c_int64, VP, VP, VP, VP, VP, VP, VP, C.POINTER(Term), C.c_int,
                                        VP, VP, VP, C.POINTER(Term), C.c_int, C.c_int, VP, VP]),
+    "xgpu_elmat_cut_pair": (C.c_int, [VP, C.c_int, C.c_int, C.c_int64, VP, VP, VP, VP, C.c_int, C.c_int, C.POINTER(Term), C.c_int,
+                                      C.c_int, C.c_int, C.POINTER(Term), C.c_int, C.c_int, VP, VP]),
     "xgpu_elmat_std": (C.c_int, [VP, C.c_int, C.c_int, C.c_int64, VP, VP, VP, VP, C.c_int, C.POINTER(Term),
                                  C.c_int, C.c_int, VP, VP]),
     "xgpu_elvec_rule": (C.c_int, [VP, C.c_int, C.c_int, C.c_int64, VP, VP, VP, VP, VP, VP, VP, C.POINTER(LTerm),

@@ -48,6 +48,8 @@ struct xgpu_ctx {
   const double* def_vals = nullptr;      // ndof x dim
   int opt_dmma = 0;   // element matrices on FP64 tensor tiles: -1 never, 0 at order >= 3, 1 also at order 2
   int opt_csr_small = 1;  // one-pass CSR: thread-per-row kernels (register sorting network) for rows with few adjacent table rows
+  int opt_elmat_lp = 1;  // cut-element matrices at order <= 2: lane-per-point kernel (elmat_lp.cu); 0 = staged half-warp kernel
+  int opt_cut_bpsm = 2;  // k_elmat_cut: resident blocks per SM (1 leaves half of the register file to concurrent kernels)
   int opt_short_blocks = 0;  // cut quadrature / cut element matrices: one tile per block instead of a persistent grid (a
                              // low-priority side stream then yields the SMs to the main stream block by block)
   int opt_csr_warp = 1;   // one-pass CSR: warp-per-row kernels (sorting network over the warp) for rows with <= 256 candidates

@@ -203,6 +203,8 @@ extern "C" int xgpu_set_option(xgpu_ctx* ctx, const char* key, int value)
   if (!ctx || !key) return XGPU_ERR_ARG;
   if (std::string(key) == "elmat_dmma") { ctx->opt_dmma = value < 0 ? -1 : (value > 0 ? 1 : 0); return XGPU_OK; }
   if (std::string(key) == "csr_small") { ctx->opt_csr_small = value != 0; return XGPU_OK; }
+  if (std::string(key) == "elmat_lp") { ctx->opt_elmat_lp = value != 0; return XGPU_OK; }
+  if (std::string(key) == "cut_blocks_per_sm") { ctx->opt_cut_bpsm = value <= 1 ? 1 : 2; return XGPU_OK; }
   if (std::string(key) == "short_blocks") { ctx->opt_short_blocks = value != 0; return XGPU_OK; }
   if (std::string(key) == "csr_warp") { ctx->opt_csr_warp = value != 0; return XGPU_OK; }
   if (std::string(key) == "csr_closed_form") { ctx->opt_csr_closed_form = value != 0; return XGPU_OK; }

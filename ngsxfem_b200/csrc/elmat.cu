@@ -8,11 +8,16 @@ int xg_launch_ms_3(xgpu_ctx* ctx, int p, int64_t n, const int32_t* elems, const 
 int xg_launch_dmma_2(xgpu_ctx* ctx, int p, int64_t n, const int32_t* elems, const int32_t* el_vtx, const double* vtx_xyz, const int64_t* offsets, const double* pts, const double* wts, int np_shared, const TermsDev& T, int accumulate, const int32_t* slots, double* mats);
 int xg_launch_dmma_3(xgpu_ctx* ctx, int p, int64_t n, const int32_t* elems, const int32_t* el_vtx, const double* vtx_xyz, const int64_t* offsets, const double* pts, const double* wts, int np_shared, const TermsDev& T, int accumulate, const int32_t* slots, double* mats);
 
+int xg_launch_lp(xgpu_ctx* ctx, int dim, int p, int64_t n, const int32_t* elems, const int32_t* el_vtx, const double* vtx_xyz, const int64_t* offsets, const double* pts, const double* wts, const TermsDev& T, int accumulate, const int32_t* slots, double* mats, const Rule2* r2);
+
 namespace {
 
 template <int D>
 int xg_launch_ms(xgpu_ctx* ctx, int p, int64_t n, const int32_t* elems, const int32_t* el_vtx, const double* vtx_xyz, const int64_t* offsets, const double* pts, const double* wts, int np_shared, const TermsDev& T, int accumulate, const int32_t* slots, double* mats, const Rule2* r2 = nullptr)
 {
+  // order <= 2 with per-element rules (cut elements): one lane per quadrature point, matrix in registers (elmat_lp.cu);
+  // ctx->opt_elmat_lp = 0 keeps the staged half-warp kernel
+  if (p <= 2 && offsets && ctx->opt_elmat_lp) return xg_launch_lp(ctx, D, p, n, elems, el_vtx, vtx_xyz, offsets, pts, wts, T, accumulate, slots, mats, r2);
   if (D == 1) return xg_launch_ms_1(ctx, p, n, elems, el_vtx, vtx_xyz, offsets, pts, wts, np_shared, T, accumulate, slots, mats, r2);
   if (D == 2) return xg_launch_ms_2(ctx, p, n, elems, el_vtx, vtx_xyz, offsets, pts, wts, np_shared, T, accumulate, slots, mats, r2);
   return xg_launch_ms_3(ctx, p, n, elems, el_vtx, vtx_xyz, offsets, pts, wts, np_shared, T, accumulate, slots, mats, r2);

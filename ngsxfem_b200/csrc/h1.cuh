@@ -87,7 +87,13 @@ XG_HD void xg_face_shapes(const AD<D>* lam, int a, int b, int c, const int* vnum
     for (int j = 0; j <= N - i; j++) sink(n++, bub * (Pa[i] * Qa[j]));
 }
 
-// all shapes of order P on the D-simplex at xhat; returns ndof
+// all shapes of order P from prepared barycentric coordinates lam[0..D] (value + derivatives w.r.t. ANY coordinates:
+// reference ones, or physical ones when lam[i].d = F^{-T} grad_ref lam_i — the shapes are polynomials in lam, so the
+// chain rule carried by AD yields the physical gradients without a per-function F^{-T} product); returns ndof
+template <int D, int P, class Sink>
+XG_HD int xg_h1_shapes_lam(const int* vnum, const AD<D>* lam, Sink& sink);
+
+// all shapes of order P on the D-simplex at xhat (reference gradients); returns ndof
 template <int D, int P, class Sink>
 XG_HD int xg_h1_shapes(const int* vnum, const double* xhat, Sink& sink)
 {
@@ -100,6 +106,12 @@ XG_HD int xg_h1_shapes(const int* vnum, const double* xhat, Sink& sink)
   lam[D] = ad_const<D>(s);
 #pragma unroll
   for (int i = 0; i < D; i++) lam[D].d[i] = -1.0;
+  return xg_h1_shapes_lam<D, P>(vnum, lam, sink);
+}
+
+template <int D, int P, class Sink>
+XG_HD int xg_h1_shapes_lam(const int* vnum, const AD<D>* lam, Sink& sink)
+{
   int n = 0;
 #pragma unroll
   for (int i = 0; i < D + 1; i++) sink(n++, lam[i]);
@@ -114,7 +126,7 @@ XG_HD int xg_h1_shapes(const int* vnum, const double* xhat, Sink& sink)
   for (int e = 0; e < NED; e++) {
     const int ea = (D == 2) ? XG_TRIG_EDGE_A(e) : XG_TET_EDGE_A(e);
     const int eb = (D == 2) ? XG_TRIG_EDGE_B(e) : XG_TET_EDGE_B(e);
-    bool sw = vnum[ea] > vnum[eb];
+    const bool sw = (P > 2) && vnum[ea] > vnum[eb];   // P == 2: 0.5 ((le-ls)^2 - (le+ls)^2) is swap-invariant bit for bit
     AD<D> la = lam[0], lb = lam[0];
 #pragma unroll
     for (int i = 0; i < D + 1; i++) { if (i == ea) la = lam[i]; if (i == eb) lb = lam[i]; }

@@ -30,6 +30,8 @@ The result is a row-distributed CSR (rows = owned dofs) with global column ids.
 The compute backend is duck-typed (`classify`, `elmats`, `csr`): `GpuBackend` below drives the
 CUDA kernels through the C ABI; the CPU gloo tests inject their own checker backend (tests/dist_backend.py).
 """
+import os
+
 import torch
 import torch.distributed as dist
 
@@ -532,19 +534,17 @@ class GpuBackend:
         l_neg, l_if, l_halo = l_neg.contiguous(), l_if.contiguous(), l_halo.contiguous()
         if p > 2 or not self.fused:
             raise NotImplementedError("kernel path: orders 1, 2")
-        side, ctx2, _, _ = _side_context(dev)
         main = torch.cuda.current_stream(dev)
+        if os.environ.get("XGPU_CONCURRENT", "0") == "1":   # the cut-element branch on a low-priority side stream: not steadier,
+            side, ctx2, _, _ = _side_context(dev)               # not faster than one stream (profiles/r02_notes.md)
+        else:
+            side, ctx2 = main, ctx
         m_if = torch.empty((l_if.numel(), nd, nd), dtype=torch.float64, device=dev)
         side.wait_stream(main)
         with torch.cuda.stream(side):
             if l_if.numel():
-                off, n1 = ops.cutquad_count(dim, l_if, els, phi, ops.NEG, order, ctx=ctx2)
-                off2, n2 = ops.cutquad_count(dim, l_if, els, phi, ops.IF, order, ctx=ctx2)
-                q, w = ops.cutquad_fill(dim, l_if, els, xyz, phi, ops.NEG, order, off, n1, ctx=ctx2)
-                q2, w2 = ops.cutquad_fill(dim, l_if, els, xyz, phi, ops.IF, order, off2, n2, ctx=ctx2)
-                ops.elmat_rule_pair(dim, p, l_if, els, xyz, phi, (off, q, w), TERMS_VOL, (off2, q2, w2), TERMS_IF, out=m_if, ctx=ctx2)
-                for t_ in (off, off2, q, w, q2, w2):
-                    t_.record_stream(side)
+                # cut rules made inside the element-matrix kernel (no count pass / host wait, no stored rules)
+                ops.elmat_cut_pair(dim, p, l_if, els, xyz, phi, ops.NEG, order, TERMS_VOL, ops.IF, order, TERMS_IF, out=m_if, ctx=ctx2)
             m_if.record_stream(side)
         mark("cut_branch_enqueued")
         lists = [l_neg, l_if, l_halo]

@@ -335,6 +335,24 @@ def elmat_rule_pair(dim, fe_order, elems, el_vtx, vtx_xyz, phi, rule_a, terms_a,
     return out
 
 
+def elmat_cut_pair(dim, fe_order, elems, el_vtx, vtx_xyz, phi, dt_a, order_a, terms_a, dt_b=None, order_b=0, terms_b=(),
+                   out=None, accumulate=False, slots=None, ctx=None):
+    """cut-element matrices with the cut rules made on the fly (xgpu_elmat_cut_pair): integrator A = (dt_a, order_a, terms_a),
+    optional integrator B; orders 1..2, mass / stiffness terms, affine mesh — raises XgpuError (unsupported) otherwise"""
+    ctx = ctx or default_ctx()
+    n = el_vtx.shape[0] if elems is None else elems.numel()
+    nd = h1_ndof(dim, fe_order)
+    if out is None:
+        out = torch.empty((n, nd, nd), dtype=torch.float64, device=el_vtx.device)
+        accumulate = False
+    tb = list(terms_b)
+    ctx.check(ctx.lib.xgpu_elmat_cut_pair(ctx.h, dim, fe_order, n, ptr(elems), ptr(_i32(el_vtx)), ptr(_f64(vtx_xyz)), ptr(phi),
+                                          int(dt_a), int(order_a), terms_array(terms_a), len(terms_a),
+                                          -1 if dt_b is None else int(dt_b), int(order_b), terms_array(tb) if tb else None, len(tb),
+                                          int(accumulate), ptr(slots), ptr(out)))
+    return out
+
+
 def elmat_std(dim, fe_order, elems, el_vtx, vtx_xyz, phi, order, terms, out=None, accumulate=False, slots=None, ctx=None):
     ctx = ctx or default_ctx()
     n = el_vtx.shape[0] if elems is None else elems.numel()

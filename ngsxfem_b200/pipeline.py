@@ -65,7 +65,8 @@ def _side_context(dev):
         lo, hi = torch.cuda.Stream(dev, priority=-1 if swap else 0), torch.cuda.Stream(dev, priority=0 if swap else -1)
         with torch.cuda.stream(lo):
             c_lo = Ctx(dev.index)
-            c_lo.set_option("short_blocks", 0 if swap else 1)
+            c_lo.set_option("short_blocks", int(os.environ.get("XGPU_SIDE_SHORT", "0" if swap else "1")))
+            c_lo.set_option("cut_blocks_per_sm", int(os.environ.get("XGPU_CUT_BPSM", "2")))
         with torch.cuda.stream(hi):
             c_hi = Ctx(dev.index)
         _SIDE[dev.index] = (lo, c_lo, hi, c_hi)
@@ -86,7 +87,7 @@ class CutAssembly:
         # concurrently with the sparsity graph (shared-memory / issue bound); they only meet in the scatter
         self.side_stream, self.ctx2, self.main_hp, self.ctx_hp = _side_context(self.dev)
 
-    def step(self, phi, timer=None, keep=False, hooks=None, concurrent=False, mode="fused"):
+    def step(self, phi, timer=None, keep=False, hooks=None, concurrent=False, mode="fused", cut_rules="fly"):
         """one pass of the hot path; returns a dict with the CSR matrix and the unit counts.
         mode="fused" (default): the uncut affine elements are a PROCEDURAL batch (7 coefficients per element,
         `xgpu_affine_coefs`, no 800 B matrices in HBM), a count pass gives the row offsets (`xgpu_csr_plan_rows`) and every
@@ -97,22 +98,34 @@ class CutAssembly:
         points (the host-buffer path overlaps its H2D / D2H copies with the kernels through them).
         concurrent=True runs the cut-element branch (cut quadrature + cut element matrices: FP64 / latency bound, low
         occupancy) on a side stream next to Restrict + the transposed table (memory / atomics bound); they meet in the
-        row pass.  Off when per-phase CUDA-event times are wanted."""
+        row pass.  Off when per-phase CUDA-event times are wanted.
+        cut_rules="fly" (default, order <= 2): the cut rules are made inside the element-matrix kernel
+        (`xgpu_elmat_cut_pair`); "stored": `xgpu_cutquad_count/_fill` write them out, `xgpu_elmat_rule_pair` reads them
+        (the result's "npts" is (None, None) on the "fly" path: `cut_point_counts` gives the numbers)."""
         if concurrent and torch.cuda.current_stream(self.dev) != self.main_hp:
             # the main chain on a high-priority stream, the cut-element branch on a low-priority one
             caller = torch.cuda.current_stream(self.dev)
             self.main_hp.wait_stream(caller)
             with torch.cuda.stream(self.main_hp):
-                out = self._step(phi, timer, keep, hooks, True, mode, self.ctx_hp)
+                out = self._step(phi, timer, keep, hooks, True, mode, self.ctx_hp, cut_rules)
             caller.wait_stream(self.main_hp)
             for v_ in out.values():
                 for t_ in (v_ if isinstance(v_, tuple) else (v_,)):
                     if torch.is_tensor(t_):
                         t_.record_stream(caller)
             return out
-        return self._step(phi, timer, keep, hooks, concurrent, mode, self.ctx)
+        return self._step(phi, timer, keep, hooks, concurrent, mode, self.ctx, cut_rules)
 
-    def _step(self, phi, timer, keep, hooks, concurrent, mode, ctx):
+    def cut_point_counts(self, phi, l_if=None):
+        """(#NEG points, #IF points) of the cut rules on the cut elements — reporting only (the "fly" path never counts)"""
+        if l_if is None:
+            _, _, bi, _ = ops.classify(self.dim, self.el_vtx, phi, ctx=self.ctx)
+            l_if = ops.bitset_to_list(bi, self.ne, ctx=self.ctx)
+        _, n1 = ops.cutquad_count(self.dim, l_if, self.el_vtx, phi, ops.NEG, 2 * self.p, ctx=self.ctx)
+        _, n2 = ops.cutquad_count(self.dim, l_if, self.el_vtx, phi, ops.IF, 2 * self.p, ctx=self.ctx)
+        return n1, n2
+
+    def _step(self, phi, timer, keep, hooks, concurrent, mode, ctx, cut_rules="fly"):
         t = timer or PhaseTimer(False)
         hooks = hooks or {}
         dim, p, ne = self.dim, self.p, self.ne
@@ -145,18 +158,28 @@ class CutAssembly:
                 if concurrent and t.enabled:
                     t.side = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
                     t.side[0].record(side)
-                off, n1 = ops.cutquad_count(dim, l_if, els, phi, ops.NEG, order, ctx=ctx2)
-                off2, n2 = ops.cutquad_count(dim, l_if, els, phi, ops.IF, order, ctx=ctx2)
-                q, w = ops.cutquad_fill(dim, l_if, els, xyz, phi, ops.NEG, order, off, n1, ctx=ctx2)
-                q2, w2 = ops.cutquad_fill(dim, l_if, els, xyz, phi, ops.IF, order, off2, n2, ctx=ctx2)
-                t.mark("cutquad")
-                if concurrent and t.enabled:
-                    t.side[1].record(side)
-                ops.elmat_rule_pair(dim, p, l_if, els, xyz, phi, (off, q, w), TERMS_VOL, (off2, q2, w2), TERMS_IF, out=m_if, ctx=ctx2)
+                if cut_rules == "fly" and p <= 2:
+                    # the reference's own structure: the cut rule of an element is made inside the element-matrix call and
+                    # never stored (xgpu_elmat_cut_pair) — no count pass (host wait), no 32 B per point through HBM
+                    if concurrent and t.enabled:
+                        t.side[1].record(side)
+                    ops.elmat_cut_pair(dim, p, l_if, els, xyz, phi, ops.NEG, order, TERMS_VOL, ops.IF, order, TERMS_IF,
+                                       out=m_if, ctx=ctx2)
+                    n1 = n2 = None
+                    m_if.record_stream(side)
+                else:
+                    off, n1 = ops.cutquad_count(dim, l_if, els, phi, ops.NEG, order, ctx=ctx2)
+                    off2, n2 = ops.cutquad_count(dim, l_if, els, phi, ops.IF, order, ctx=ctx2)
+                    q, w = ops.cutquad_fill(dim, l_if, els, xyz, phi, ops.NEG, order, off, n1, ctx=ctx2)
+                    q2, w2 = ops.cutquad_fill(dim, l_if, els, xyz, phi, ops.IF, order, off2, n2, ctx=ctx2)
+                    t.mark("cutquad")
+                    if concurrent and t.enabled:
+                        t.side[1].record(side)
+                    ops.elmat_rule_pair(dim, p, l_if, els, xyz, phi, (off, q, w), TERMS_VOL, (off2, q2, w2), TERMS_IF, out=m_if, ctx=ctx2)
+                    for t_ in (off, off2, q, w, q2, w2, m_if):
+                        t_.record_stream(side)
                 if concurrent and t.enabled:
                     t.side[2].record(side)
-                for t_ in (off, off2, q, w, q2, w2, m_if):
-                    t_.record_stream(side)
             t.mark("elmat_cut")
             return n1, n2
 

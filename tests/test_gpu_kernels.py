@@ -454,3 +454,102 @@ def test_facetpatch_tensor_tiles_match_cuda_core_kernel_and_oracle(dim, n, p):
     assert rel_err(out[0], o) < 1e-12 and rel_err(out[-1], o) < 1e-12
     assert rel_err(out[0], out[-1]) < 1e-13
     assert np.allclose(out[0], out[0].transpose(0, 2, 1), rtol=1e-13, atol=1e-15 * np.abs(o).max())
+
+
+@pytest.mark.parametrize("dim,n,p", [(3, 6, 2), (3, 5, 1), (2, 11, 2), (2, 9, 1), (1, 9, 2)])
+def test_elmat_lane_per_point_kernel_equals_staged_kernel_and_oracle(dim, n, p):
+    """k_elmat_lp (order <= 2, one lane per quadrature point, matrix in registers, elmat_lp.cu) against the staged half-warp
+    kernel k_elmat_ms (option "elmat_lp" = 0) and the oracle: single rule, rule pair, accumulate, symmetric, reproducible"""
+    if dim == 3:
+        m = meshes.MakeStructured3DMesh(nx=n).to(DEV)
+    elif dim == 2:
+        m = meshes.MakeStructured2DMesh(nx=n, ny=n).to(DEV)
+    else:
+        m = make_mesh(1, n); m = to_dev(m)
+    c = (.47, .52, .5)
+    phi = torch.sqrt(sum((m.points[:, i] - c[i]) ** 2 for i in range(dim))) - 0.34
+    phi = torch.where(phi.abs() < 1e-14, torch.full_like(phi, 1e-14), phi).contiguous()
+    ne = m.elements.shape[0]
+    bn, bp, bi, _ = ops.classify(dim, m.elements, phi)
+    l_if = ops.bitset_to_list(bi, ne)
+    assert l_if.numel() > 0
+    TV = [(ops.OP_GRAD, ops.OP_GRAD, 1.0, 0), (ops.OP_ID, ops.OP_ID, 0.5, 0)]
+    TI = [(ops.OP_ID, ops.OP_ID, 3.0, -1)]
+    ra = ops.cutquad(dim, l_if, m.elements, m.points, phi, ops.NEG, 2 * p)
+    rb = ops.cutquad(dim, l_if, m.elements, m.points, phi, ops.IF, 2 * p)
+    ctx = ops.default_ctx()
+    res = {}
+    for mode in (1, 0):
+        ctx.set_option("elmat_lp", mode)
+        try:
+            pair = ops.elmat_rule_pair(dim, p, l_if, m.elements, m.points, phi, ra, TV, rb, TI)
+            pair2 = ops.elmat_rule_pair(dim, p, l_if, m.elements, m.points, phi, ra, TV, rb, TI)
+            one = ops.elmat_rule(dim, p, l_if, m.elements, m.points, phi, ra[0], ra[1], ra[2], TV)
+            acc = one.clone()
+            ops.elmat_rule(dim, p, l_if, m.elements, m.points, phi, rb[0], rb[1], rb[2], TI, out=acc, accumulate=True)
+        finally:
+            ctx.set_option("elmat_lp", 1)
+        assert torch.equal(pair, pair2)
+        res[mode] = (pair, one, acc)
+    scale = float(res[0][0].abs().max())
+    for a, b in zip(res[1], res[0]):
+        assert torch.allclose(a, b, rtol=1e-12, atol=1e-14 * scale)
+    assert torch.allclose(res[1][0], res[1][2], rtol=1e-12, atol=1e-14 * scale)
+    assert torch.equal(res[1][0], res[1][0].transpose(1, 2))
+    pts, els = m.points.cpu().numpy(), m.elements.cpu().numpy()
+    lo = l_if.cpu().numpy()
+    mo = xo.batch_cut_elmats(dim, p, lo, els, pts, phi.cpu().numpy(), xo.NEG, 2 * p, TV)
+    mo += xo.batch_cut_elmats(dim, p, lo, els, pts, phi.cpu().numpy(), xo.IF, 2 * p, TI)
+    assert np.linalg.norm(res[1][0].cpu().numpy() - mo) <= 1e-12 * np.linalg.norm(mo)
+
+
+@pytest.mark.parametrize("dim,n,p", [(3, 6, 2), (3, 5, 1), (2, 11, 2), (2, 9, 1), (1, 9, 2), (1, 7, 1)])
+def test_elmat_cut_pair_rules_on_the_fly_equal_stored_rules_and_oracle(dim, n, p):
+    """xgpu_elmat_cut_pair (the cut rule of an element is made inside the element-matrix kernel, as T_CalcElementMatrixAdd does,
+    symboliccutbfi.cpp:105-121) against xgpu_cutquad_* + xgpu_elmat_rule_pair and against the oracle — on a list that also
+    holds UNCUT elements (HASNEG: standard rule for the NEG integrator, nothing for the IF one)"""
+    if dim == 3:
+        m = meshes.MakeStructured3DMesh(nx=n).to(DEV)
+    elif dim == 2:
+        m = meshes.MakeStructured2DMesh(nx=n, ny=n).to(DEV)
+    else:
+        m = to_dev(make_mesh(1, n))
+    c = (.47, .52, .5)
+    phi = torch.sqrt(sum((m.points[:, i] - c[i]) ** 2 for i in range(dim))) - 0.34
+    phi = torch.where(phi.abs() < 1e-14, torch.full_like(phi, 1e-14), phi).contiguous()
+    ne = m.elements.shape[0]
+    bn, bp, bi, _ = ops.classify(dim, m.elements, phi)
+    lst = ops.bitset_to_list(ops.bitset_op(ops.BIT_OR, bn, bi, ne), ne)
+    l_if = ops.bitset_to_list(bi, ne)
+    assert lst.numel() > l_if.numel() > 0
+    TV = [(ops.OP_GRAD, ops.OP_GRAD, 1.0, 0), (ops.OP_ID, ops.OP_ID, 0.5, 0)]
+    TI = [(ops.OP_ID, ops.OP_ID, 3.0, -1)]
+    order = 2 * p
+    ra = ops.cutquad(dim, lst, m.elements, m.points, phi, ops.NEG, order)
+    rb = ops.cutquad(dim, lst, m.elements, m.points, phi, ops.IF, order)
+    stored = ops.elmat_rule_pair(dim, p, lst, m.elements, m.points, phi, ra, TV, rb, TI)
+    fly = ops.elmat_cut_pair(dim, p, lst, m.elements, m.points, phi, ops.NEG, order, TV, ops.IF, order, TI)
+    fly2 = ops.elmat_cut_pair(dim, p, lst, m.elements, m.points, phi, ops.NEG, order, TV, ops.IF, order, TI)
+    assert torch.equal(fly, fly2)
+    scale = float(stored.abs().max())
+    assert torch.allclose(fly, stored, rtol=1e-12, atol=1e-14 * scale)
+    assert torch.equal(fly, fly.transpose(1, 2))
+    # one integrator, then the second one accumulated = the pair
+    one = ops.elmat_cut_pair(dim, p, lst, m.elements, m.points, phi, ops.NEG, order, TV)
+    ops.elmat_cut_pair(dim, p, lst, m.elements, m.points, phi, ops.IF, order, TI, out=one, accumulate=True)
+    assert torch.allclose(one, fly, rtol=1e-12, atol=1e-14 * scale)
+    # POS side of the cut elements
+    rp = ops.cutquad(dim, l_if, m.elements, m.points, phi, ops.POS, order)
+    sp = ops.elmat_rule(dim, p, l_if, m.elements, m.points, phi, rp[0], rp[1], rp[2], TV)
+    fp = ops.elmat_cut_pair(dim, p, l_if, m.elements, m.points, phi, ops.POS, order, TV)
+    assert torch.allclose(fp, sp, rtol=1e-12, atol=1e-14 * scale)
+    pts, els = m.points.cpu().numpy(), m.elements.cpu().numpy()
+    lo = lst.cpu().numpy()
+    mo = xo.batch_cut_elmats(dim, p, lo, els, pts, phi.cpu().numpy(), xo.NEG, order, TV)
+    mo += xo.batch_cut_elmats(dim, p, lo, els, pts, phi.cpu().numpy(), xo.IF, order, TI)
+    assert np.linalg.norm(fly.cpu().numpy() - mo) <= 1e-12 * np.linalg.norm(mo)
+    # outside the menu: the caller is told to take the two-step path
+    with pytest.raises(Exception):
+        ops.elmat_cut_pair(dim, 3, lst, m.elements, m.points, phi, ops.NEG, 6, TV)
+    with pytest.raises(Exception):
+        ops.elmat_cut_pair(dim, p, l_if, m.elements, m.points, phi, ops.IF, order, TERMS_NITSCHE)

@@ -92,6 +92,19 @@ def test_one_row_pass_equals_the_two_pass_path_bit_for_bit(n, p, radius, concurr
     assert torch.equal(a1["vals"], a2["vals"]) and torch.equal(a1["col"], a2["col"])
 
 
+def test_cut_rules_on_the_fly_equal_stored_rules_in_the_step():
+    """step(cut_rules="fly") (xgpu_elmat_cut_pair) against step(cut_rules="stored") (xgpu_cutquad_* + xgpu_elmat_rule_pair)"""
+    mesh = xf.MakeStructured3DMesh(nx=9, device=DEV)
+    V0 = xf.H1(mesh, order=2)
+    phi = sphere_levelset(mesh.points, [(.5, .48, .52)], 0.37)
+    prob = CutAssembly(3, mesh.elements, mesh.points, V0.el_dofs, V0.ndof, 2)
+    a = prob.step(phi)
+    b = prob.step(phi, cut_rules="stored")
+    assert a["npts"] == (None, None) and b["npts"] == prob.cut_point_counts(phi)
+    assert torch.equal(a["rowptr"], b["rowptr"]) and torch.equal(a["col"], b["col"])
+    assert (a["vals"] - b["vals"]).abs().max().item() <= 1e-13 * b["vals"].abs().max().item()
+
+
 def test_host_buffer_path_matches_device_path():
     mesh = xf.MakeStructured3DMesh(nx=7, device=DEV)
     V0 = xf.H1(mesh, order=2)
