@@ -320,6 +320,10 @@ int xgpu_adjacency_plan(xgpu_ctx* ctx, int64_t ndof, const xgpu_batch* batches_h
 /* LinearForm assembly (NGSolve AddElementVector): out[d] = sum of the element-vector entries whose dof is d, in
  * (batch, row, local index) order — deterministic.  A batch's `mats` points to nrows x width doubles here. */
 int xgpu_vec_scatter(xgpu_ctx* ctx, xgpu_plan* plan, const xgpu_batch* batches_host, int nbatches, double* out);
+/* the same with the MEAN over the contributing entries instead of the sum (dofs without entries: 0): out[d * stride + comp].
+ * NGSolve's GridFunction.Set and ProjectShift average element-local projections this way (lsetcurving/projshift.cpp:165-197) */
+int xgpu_vec_scatter_mean(xgpu_ctx* ctx, xgpu_plan* plan, const xgpu_batch* batches_host, int nbatches, double* out,
+                          int stride, int comp);
 /* xgpu_csr_pattern + xgpu_csr_scatter in one pass over the rows (BilinearForm.Assemble builds both every time):
  * the scatter kernels read each row's columns from the plan's pattern scratch and write rowptr, colidx AND vals
  * — the separate compaction copy (and its 1.6 GB of DRAM traffic on config 2) disappears.  Same results, bit for bit. */
@@ -398,6 +402,37 @@ int xgpu_l2g_ghosts(xgpu_ctx* ctx, int64_t n, const int32_t* dofmap_range, const
 /* y = A x for checks (CSR SpMV, one warp per row) */
 int xgpu_csr_spmv(xgpu_ctx* ctx, int64_t nrows, const int64_t* rowptr, const int32_t* colidx,
                   const double* vals, const double* x, double* y);
+
+/* ---------------------------------------------------------------- isoparametric deformation producer (row f3)
+ * LevelSetMeshAdaptation.CalcDeformation (python/lsetcurv.py:281-356): lset_ho.Set(levelset); qn.Set(grad lset_ho);
+ * InterpolateToP1; ProjectShift (lsetcurving/projshift.cpp:9-201).  H1 functions are coefficient vectors of the hierarchical
+ * basis (el_dofs: ne x xgpu_h1_ndof(dim, fe_order), all entries >= 0), affine mesh (the deformation is what is being made). */
+/* ElementInRelevantBand for every element (lsetcurving/calcpointshift.cpp:120-141) -> BitArray words */
+int xgpu_band_elements(xgpu_ctx* ctx, int dim, int64_t ne, const int32_t* el_vtx, const double* lset_p1,
+                       double lower, double upper, uint32_t* bits_out);
+/* physical coordinates of the points of SelectIntegrationRule(order_rule) on the listed elements: out n x np x dim
+ * (np = xgpu_rule_size) — where a user level-set function is sampled for GridFunction.Set */
+int xgpu_rule_points_phys(xgpu_ctx* ctx, int dim, int order_rule, int64_t n, const int32_t* elems, const int32_t* el_vtx,
+                          const double* vtx_xyz, double* out);
+/* physical gradient of the H1(fe_order) function `vals` at those points: out n x np x dim (lset_ho.Deriv()) */
+int xgpu_h1_grad_points(xgpu_ctx* ctx, int dim, int fe_order, int order_rule, int64_t n, const int32_t* elems,
+                        const int32_t* el_vtx, const double* vtx_xyz, const int32_t* el_dofs, const double* vals, double* out);
+/* element-local L2 projection of point values (fvals n x np x ncomp at the points of order_rule >= 2 fe_order) onto
+ * H1(fe_order): elres ncomp x n x nd, component-major — one batch per component for xgpu_vec_scatter_mean.  This is the
+ * element half of GridFunction.Set and of ProjectShift (projshift.cpp:92-110; zero_vertex != 0 zeroes the vertex rows, :108) */
+int xgpu_l2_project(xgpu_ctx* ctx, int dim, int fe_order, int order_rule, int64_t n, const int32_t* elems,
+                    const int32_t* el_vtx, int ncomp, const double* fvals, int zero_vertex, double* elres);
+/* ShiftIntegrator::CalcElementVector, pointwise part (lsetcurving/shiftintegrators.cpp:69-121, SearchCorrespondingPoint
+ * calcpointshift.cpp:145-206): for every point of the rule of order 2 fe_order on the listed elements the physical shift
+ * F (xhat* - xhat), xhat* on the line xhat + s F^{-1} qn with lset_ho(xhat*) = (1-alpha) lset_p1(xhat) + alpha lset_ho(xhat),
+ * |xhat* - xhat| clamped to `threshold` (< 0: none).  qn_mode 0: grad lset_p1 (qn == nullptr in the reference; exact gradient
+ * instead of its 1e-7 central difference), 1: grad lset_ho at the point (an L2(order)^dim qn set from lset_ho.Deriv()),
+ * 2: `qn` = coefficients ndof x dim of an H1(fe_order)^dim field.  blending (nullable): alpha at the points, n x np.
+ * shift_out n x np x dim; *nfail_host (nullable, synchronises) = searches that did not converge in 20 steps (shift 0). */
+int xgpu_shift_points(xgpu_ctx* ctx, int dim, int fe_order, int64_t n, const int32_t* elems, const int32_t* el_vtx,
+                      const double* vtx_xyz, const int32_t* el_dofs, const double* lset_ho, const double* lset_p1,
+                      int qn_mode, const double* qn, const double* blending, double threshold, double* shift_out,
+                      int64_t* nfail_host);
 
 #ifdef __cplusplus
 }

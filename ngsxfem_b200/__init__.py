@@ -21,5 +21,6 @@ from .forms import (dCut, dFacetPatch, grad, Normalize, specialcf, BilinearForm,
                     Integrate, TrialFunction, TestFunction, x, y, z, dn)
 from .spacetime import (ScalarTimeFE, SpaceTimeFESpace, SpaceTimeGridFunction, SpaceTimeInterpolateToP1,
                         ReferenceTimeVariable, tref, dtref, dt, fix_tref, dxtref, dmesh)
+from .lsetcurv import LevelSetMeshAdaptation, ProjectShift
 
 __all__ = [n for n in dir() if not n.startswith("_")]

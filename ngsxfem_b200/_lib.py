@@ -118,6 +118,12 @@ _SIGS = {
     "xgpu_csr_scatter": (C.c_int, [VP, VP, C.POINTER(Batch), C.c_int, VP, VP, VP]),
     "xgpu_adjacency_plan": (C.c_int, [VP, C.c_int64, C.POINTER(Batch), C.c_int, C.POINTER(VP)]),
     "xgpu_vec_scatter": (C.c_int, [VP, VP, C.POINTER(Batch), C.c_int, VP]),
+    "xgpu_vec_scatter_mean": (C.c_int, [VP, VP, C.POINTER(Batch), C.c_int, VP, C.c_int, C.c_int]),
+    "xgpu_band_elements": (C.c_int, [VP, C.c_int, C.c_int64, VP, VP, C.c_double, C.c_double, VP]),
+    "xgpu_rule_points_phys": (C.c_int, [VP, C.c_int, C.c_int, C.c_int64, VP, VP, VP, VP]),
+    "xgpu_h1_grad_points": (C.c_int, [VP, C.c_int, C.c_int, C.c_int, C.c_int64, VP, VP, VP, VP, VP, VP]),
+    "xgpu_l2_project": (C.c_int, [VP, C.c_int, C.c_int, C.c_int, C.c_int64, VP, VP, C.c_int, VP, C.c_int, VP]),
+    "xgpu_shift_points": (C.c_int, [VP, C.c_int, C.c_int, C.c_int64, VP, VP, VP, VP, VP, VP, C.c_int, VP, VP, C.c_double, VP, c_i64p]),
     "xgpu_csr_assemble": (C.c_int, [VP, VP, C.POINTER(Batch), C.c_int, VP, VP, VP]),
     "xgpu_csr_plan_rows": (C.c_int, [VP, C.c_int64, C.POINTER(Batch), C.c_int, C.POINTER(VP), c_i64p]),
     "xgpu_csr_count_rows": (C.c_int, [VP, VP, c_i64p]),

@@ -596,6 +596,23 @@ __global__ void k_vec_scatter(int64_t ndof, const long long* __restrict__ adj_pt
   out[d] = s;
 }
 
+// the mean instead of the sum (GridFunction.Set / ProjectShift average the element-local projections over the elements
+// sharing a dof, lsetcurving/projshift.cpp:165-197); out has `stride` doubles per dof, component `comp` is written
+__global__ void k_vec_scatter_mean(int64_t ndof, const long long* __restrict__ adj_ptr, const long long* __restrict__ adj,
+                                   BatchDev bd, double* __restrict__ out, int stride, int comp)
+{
+  const int64_t d = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (d >= ndof) return;
+  double s = 0.0;
+  int cnt = 0;
+  for (long long i = adj_ptr[d]; i < adj_ptr[d + 1]; i++) {
+    const long long e = adj[i];
+    const int bi = XG_ADJ_BATCH(e);
+    if (bd.mats[bi]) { s += __ldg(bd.mats[bi] + (size_t)XG_ADJ_ROW(e) * bd.width[bi] + XG_ADJ_LOC(e)); cnt++; }
+  }
+  out[d * stride + comp] = cnt > 0 ? s * (1.0 / (double)cnt) : 0.0;
+}
+
 __global__ void k_spmv(int64_t nrows, const long long* __restrict__ rowptr, const int32_t* __restrict__ colidx,
                        const double* __restrict__ vals, const double* __restrict__ x, double* __restrict__ y)
 {
@@ -942,6 +959,23 @@ extern "C" int xgpu_vec_scatter(xgpu_ctx* ctx, xgpu_plan* P, const xgpu_batch* b
   }
   if (P->ndof == 0) return XGPU_OK;
   k_vec_scatter<<<nblk(P->ndof, 256), 256, 0, ctx->stream>>>(P->ndof, P->adj_ptr, P->adj, bd, out);
+  XGPU_LAUNCH_CHECK(ctx);
+  return XGPU_OK;
+}
+
+extern "C" int xgpu_vec_scatter_mean(xgpu_ctx* ctx, xgpu_plan* P, const xgpu_batch* batches_host, int nbatches, double* out,
+                                     int stride, int comp)
+{
+  if (!ctx || !P || nbatches != P->bd.nb || stride < 1 || comp < 0 || comp >= stride)
+    return xgpu_fail(ctx, XGPU_ERR_ARG, "xgpu_vec_scatter_mean: bad argument");
+  BatchDev bd = P->bd;
+  for (int i = 0; i < nbatches; i++) {
+    if (batches_host[i].nrows != bd.rowoff[i + 1] - bd.rowoff[i] || batches_host[i].width != bd.width[i])
+      return xgpu_fail(ctx, XGPU_ERR_ARG, "xgpu_vec_scatter_mean: batches do not match the plan");
+    bd.mats[i] = batches_host[i].mats;
+  }
+  if (P->ndof == 0) return XGPU_OK;
+  k_vec_scatter_mean<<<nblk(P->ndof, 256), 256, 0, ctx->stream>>>(P->ndof, P->adj_ptr, P->adj, bd, out, stride, comp);
   XGPU_LAUNCH_CHECK(ctx);
   return XGPU_OK;
 }

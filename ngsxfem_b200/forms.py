@@ -640,7 +640,7 @@ class BilinearForm:
             if not l.numel():
                 continue
             ls = dx.levelset
-            with ctx.deformation(dx.deformation):
+            with ctx.deformation(_eff_def(dx.deformation, mesh)):
                 has_dn = any(t[0] == OP_DN or t[1] == OP_DN for t in terms)
                 if isinstance(ls, (list, tuple)):
                     if has_dn and integ.form.nlset is None:
@@ -708,7 +708,7 @@ class BilinearForm:
                     full = l.numel() == l_U.numel()
                     if not init_U and not full:
                         m_U.zero_()
-                    with ctx.deformation(dx.deformation):
+                    with ctx.deformation(_eff_def(dx.deformation, mesh)):
                         ops.elmat_std(dim, p, l, mesh.elements, mesh.points, phi0, order, terms, out=m_U,
                                       accumulate=init_U or not full, slots=None if full else slot_U[l.long()].contiguous(), ctx=ctx)
                     init_U = True
@@ -719,7 +719,7 @@ class BilinearForm:
                     full = l.numel() == l_C.numel()
                     if not init_C and not full:
                         m_C.zero_()
-                    with ctx.deformation(dx.deformation):
+                    with ctx.deformation(_eff_def(dx.deformation, mesh)):
                         off, q, w = ops.cutquad(dim, l, mesh.elements, mesh.points, phi0, dt, order, ctx=ctx)
                         ctx.raise_on_geometry_error()
                         ops.elmat_rule(dim, p, l, mesh.elements, mesh.points, phi0, off, q, w, terms, out=m_C,
@@ -794,7 +794,7 @@ class BilinearForm:
             l_f = l_f[fe[l_f.long(), 1] >= 0].contiguous()
             key = id(integ.dx.definedonelements)
             for (_, _, c, hp) in terms:
-                with ctx.deformation(integ.dx.deformation):
+                with ctx.deformation(_eff_def(integ.dx.deformation, mesh)):
                     mm = ops.facetpatch(dim, p, l_f, fe, mesh.elements, mesh.points, integ.dx.order, c, hp, ctx=ctx)
                 if key in facet_mats:
                     facet_mats[key] = (l_f, facet_mats[key][1] + mm)
@@ -928,7 +928,7 @@ class LinearForm:
             if not l.numel():
                 continue
             ls = dx.levelset
-            with ctx.deformation(dx.deformation):
+            with ctx.deformation(_eff_def(dx.deformation, mesh)):
                 has_dn = any(t[0] == OP_DN for t in integ.form.terms)
                 if isinstance(ls, (list, tuple)):
                     if has_dn and integ.form.nlset is None:
@@ -993,6 +993,11 @@ y = CoordMonomial((0, 1, 0))
 z = CoordMonomial((0, 0, 1))
 
 
+def _eff_def(deformation, mesh):
+    """the `deformation=` argument, else the one set on the mesh (mesh.SetDeformation, python/lsetcurv.py:358-363)"""
+    return deformation if deformation is not None else getattr(mesh, "deformation", None)
+
+
 def Integrate(levelset_domain=None, mesh=None, cf=1.0, order=5, time_order=-1, deformation=None, heapsize=1000000):
     """python/__init__.py:361-439 -> cutint/python_cutint.cpp:21-163: sum_q w_q |det F| cf(x_q)."""
     ld = levelset_domain
@@ -1022,7 +1027,7 @@ def Integrate(levelset_domain=None, mesh=None, cf=1.0, order=5, time_order=-1, d
         off, p, w = ops.cutquad(dim - 1, None, bv, mesh.points, _lset_vec(ls, mesh), int(dt), order, ctx=ctx)
         ctx.raise_on_geometry_error()
         return cf.coef * ops.integrate_monomial_bnd(dim - 1, dim, None, bv, mesh.points, off, p, w, cf.expo[:dim], ctx=ctx)
-    with ctx.deformation(deformation):
+    with ctx.deformation(_eff_def(deformation, mesh)):
         if isinstance(ls, (list, tuple)):
             phis = torch.stack([_lset_vec(l, mesh) for l in ls]).contiguous()
             dts = _normalize_dtlist(dt, len(ls))

@@ -25,6 +25,15 @@ class Mesh:
         self.dim = self.points.shape[1]
         assert self.elements.shape[1] == self.dim + 1
         self._topo = {}
+        self.deformation = None
+
+    def SetDeformation(self, deformation):
+        """mesh.SetDeformation(gf) (python/lsetcurv.py:358-363): every cut integral / form assembled while it is set uses the
+        isoparametric map (forms without their own `deformation=` argument pick it up)"""
+        self.deformation = deformation
+
+    def UnsetDeformation(self):
+        self.deformation = None
 
     # ---- sizes (NGSolve names) ----
     @property

@@ -546,6 +546,72 @@ def vec_scatter(plan, batches, out=None):
     return out
 
 
+def vec_scatter_mean(plan, batches, out, comp=0):
+    """like vec_scatter with the MEAN over the contributing entries; out: ndof x stride, component `comp` is written"""
+    arr = _batches(batches)
+    stride = 1 if out.dim() == 1 else out.shape[1]
+    plan.ctx.check(plan.ctx.lib.xgpu_vec_scatter_mean(plan.ctx.h, plan.h, arr, len(batches), ptr(out), stride, comp))
+    return out
+
+
+# ---------------------------------------------------------------- isoparametric deformation producer (csrc/lsetcurv.cu)
+def band_elements(dim, el_vtx, lset_p1, lower=0.0, upper=0.0, ctx=None):
+    """ElementInRelevantBand for every element -> BitArray words (lsetcurving/calcpointshift.cpp:120-141)"""
+    ctx = ctx or default_ctx()
+    ne = el_vtx.shape[0]
+    bits = new_bits(ne, el_vtx.device)
+    ctx.check(ctx.lib.xgpu_band_elements(ctx.h, dim, ne, ptr(_i32(el_vtx)), ptr(_f64(lset_p1)), float(lower), float(upper), ptr(bits)))
+    return bits
+
+
+def rule_points_phys(dim, order_rule, elems, el_vtx, vtx_xyz, ctx=None):
+    """physical coordinates of the rule points on the listed elements: n x np x dim"""
+    ctx = ctx or default_ctx()
+    n = el_vtx.shape[0] if elems is None else elems.numel()
+    np_ = ctx.lib.xgpu_rule_size(ctx.h, dim, order_rule)
+    out = torch.empty((n, np_, dim), dtype=torch.float64, device=el_vtx.device)
+    ctx.check(ctx.lib.xgpu_rule_points_phys(ctx.h, dim, order_rule, n, ptr(elems), ptr(_i32(el_vtx)), ptr(_f64(vtx_xyz)), ptr(out)))
+    return out
+
+
+def h1_grad_points(dim, fe_order, order_rule, elems, el_vtx, vtx_xyz, el_dofs, vals, ctx=None):
+    """physical gradient of an H1(fe_order) function at the rule points: n x np x dim"""
+    ctx = ctx or default_ctx()
+    n = el_vtx.shape[0] if elems is None else elems.numel()
+    np_ = ctx.lib.xgpu_rule_size(ctx.h, dim, order_rule)
+    out = torch.empty((n, np_, dim), dtype=torch.float64, device=el_vtx.device)
+    ctx.check(ctx.lib.xgpu_h1_grad_points(ctx.h, dim, fe_order, order_rule, n, ptr(elems), ptr(_i32(el_vtx)), ptr(_f64(vtx_xyz)),
+                                          ptr(_i32(el_dofs)), ptr(_f64(vals)), ptr(out)))
+    return out
+
+
+def l2_project(dim, fe_order, order_rule, elems, el_vtx, fvals, zero_vertex=False, ctx=None):
+    """element-local L2 projection of point values (n x np x ncomp, or n x np) onto H1(fe_order): ncomp x n x nd"""
+    ctx = ctx or default_ctx()
+    n = el_vtx.shape[0] if elems is None else elems.numel()
+    fv = _f64(fvals)
+    ncomp = 1 if fv.dim() == 2 else fv.shape[2]
+    nd = h1_ndof(dim, fe_order)
+    out = torch.empty((ncomp, n, nd), dtype=torch.float64, device=el_vtx.device)
+    ctx.check(ctx.lib.xgpu_l2_project(ctx.h, dim, fe_order, order_rule, n, ptr(elems), ptr(_i32(el_vtx)), ncomp, ptr(fv),
+                                      int(bool(zero_vertex)), ptr(out)))
+    return out
+
+
+def shift_points(dim, fe_order, elems, el_vtx, vtx_xyz, el_dofs, lset_ho, lset_p1, qn_mode=0, qn=None, blending=None,
+                 threshold=-1.0, ctx=None):
+    """pointwise shift of ShiftIntegrator (xgpu_shift_points): (n x np x dim, #searches that did not converge)"""
+    ctx = ctx or default_ctx()
+    n = el_vtx.shape[0] if elems is None else elems.numel()
+    np_ = ctx.lib.xgpu_rule_size(ctx.h, dim, 2 * fe_order)
+    out = torch.empty((n, np_, dim), dtype=torch.float64, device=el_vtx.device)
+    nf = C.c_int64(0)
+    ctx.check(ctx.lib.xgpu_shift_points(ctx.h, dim, fe_order, n, ptr(elems), ptr(_i32(el_vtx)), ptr(_f64(vtx_xyz)), ptr(_i32(el_dofs)),
+                                        ptr(_f64(lset_ho)), ptr(_f64(lset_p1)), int(qn_mode), ptr(_f64(qn)) if qn is not None else None,
+                                        ptr(_f64(blending)) if blending is not None else None, float(threshold), ptr(out), C.byref(nf)))
+    return out, int(nf.value)
+
+
 def csr_pattern(plan, device):
     rowptr = torch.empty(plan.ndof + 1, dtype=torch.int64, device=device)
     col = torch.empty(plan.nnz, dtype=torch.int32, device=device)

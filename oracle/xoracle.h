@@ -184,3 +184,18 @@ void xo_scatter_threads(int64_t ndof, int64_t nrows, int width, const int32_t* t
 }
 #endif
 #endif
+
+/* ------------------------------------------------------------------ isoparametric deformation producer (xo_shift.c)
+ * lsetcurving/projshift.cpp:9-201, shiftintegrators.cpp:39-124, calcpointshift.cpp:81-206; python/lsetcurv.py:281-356 */
+int xo_element_in_band(const double* vals, int n, double lower, double upper);
+int xo_rule_points_phys(int dim, int order_rule, int64_t ne, const int32_t* el_vtx, const double* vtx_xyz, double* out);
+void xo_set_from_points(int dim, int fe_order, int order_rule, int64_t ne, const int32_t* el_vtx, const int32_t* el_dofs,
+                        int64_t ndof, int ncomp, const double* fvals, double* out);
+void xo_set_gradient(int dim, int fe_order, int64_t ne, const int32_t* el_vtx, const double* vtx_xyz, const int32_t* el_dofs,
+                     int64_t ndof, const double* lset_ho, double* qn_out);
+int64_t xo_project_shift(int dim, int fe_order, int64_t ne, const int32_t* el_vtx, const double* vtx_xyz,
+                         const int32_t* el_dofs, int64_t ndof, const double* lset_ho, const double* lset_p1, int qn_mode,
+                         const double* qn, const uint8_t* ba, const double* blending, double lower, double upper,
+                         double threshold, double* deform);
+double xo_integrate_one_deformed(int dim, int64_t ne, const int32_t* el_vtx, const double* vtx_xyz, const double* phi, int dt,
+                                 int order, int def_order, const int32_t* el_dofs_def, const double* def_vals, int* err);

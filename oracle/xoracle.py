@@ -425,3 +425,68 @@ def elvec_st_from_rule(T, fe_order, time_fe_order, pts, tvals, wts, terms, out=N
     fn.restype = None
     fn(C.byref(T), fe_order, time_fe_order, _p(pts), _p(tv), _p(wts), len(wts), arr, len(terms), _p(v))
     return v
+
+
+# ------------------------------------------------------------------ isoparametric deformation producer (xo_shift.c)
+def rule_points_phys(dim, order_rule, el_vtx, vtx_xyz):
+    el_vtx = _i32(el_vtx); vtx_xyz = _f64(vtx_xyz)
+    ne = el_vtx.shape[0]
+    np_ = lib().xo_rule_size(dim, order_rule)
+    out = np.zeros((ne, np_, dim))
+    lib().xo_rule_points_phys(dim, order_rule, C.c_int64(ne), _p(el_vtx, C.c_int32), _p(vtx_xyz), _p(out))
+    return out
+
+
+def set_from_points(dim, fe_order, order_rule, el_vtx, el_dofs, ndof, fvals):
+    """GridFunction.Set restated: element-wise L2 projection of the point values (ne x np [x ncomp]) + mean per dof"""
+    el_vtx = _i32(el_vtx); el_dofs = _i32(el_dofs); fv = _f64(fvals)
+    ne = el_vtx.shape[0]
+    ncomp = 1 if fv.ndim == 2 else fv.shape[2]
+    out = np.zeros((ndof, ncomp))
+    lib().xo_set_from_points(dim, fe_order, order_rule, C.c_int64(ne), _p(el_vtx, C.c_int32), _p(el_dofs, C.c_int32),
+                             C.c_int64(ndof), ncomp, _p(fv), _p(out))
+    return out[:, 0] if fv.ndim == 2 else out
+
+
+def set_gradient(dim, fe_order, el_vtx, vtx_xyz, el_dofs, ndof, lset_ho):
+    el_vtx = _i32(el_vtx); el_dofs = _i32(el_dofs); vtx_xyz = _f64(vtx_xyz); lh = _f64(lset_ho)
+    out = np.zeros((ndof, dim))
+    lib().xo_set_gradient(dim, fe_order, C.c_int64(el_vtx.shape[0]), _p(el_vtx, C.c_int32), _p(vtx_xyz), _p(el_dofs, C.c_int32),
+                          C.c_int64(ndof), _p(lh), _p(out))
+    return out
+
+
+def project_shift(dim, fe_order, el_vtx, vtx_xyz, el_dofs, ndof, lset_ho, lset_p1, qn_mode=0, qn=None, ba=None, blending=None,
+                  lower=0.0, upper=0.0, threshold=-1.0):
+    """ProjectShift (lsetcurving/projshift.cpp:9-201): returns (deform ndof x dim, #searches that did not converge)"""
+    el_vtx = _i32(el_vtx); el_dofs = _i32(el_dofs); vtx_xyz = _f64(vtx_xyz)
+    lh = _f64(lset_ho); l1 = _f64(lset_p1)
+    q = None if qn is None else _f64(qn)
+    b = None if ba is None else np.ascontiguousarray(ba, dtype=np.uint8)
+    bl = None if blending is None else _f64(blending)
+    out = np.zeros((ndof, dim))
+    L = lib()
+    L.xo_project_shift.restype = C.c_int64
+    nf = L.xo_project_shift(dim, fe_order, C.c_int64(el_vtx.shape[0]), _p(el_vtx, C.c_int32), _p(vtx_xyz), _p(el_dofs, C.c_int32),
+                            C.c_int64(ndof), _p(lh), _p(l1), qn_mode, _p(q), _p(b, C.c_uint8), _p(bl), C.c_double(lower),
+                            C.c_double(upper), C.c_double(threshold), _p(out))
+    return out, int(nf)
+
+
+def integrate_one_deformed(dim, el_vtx, vtx_xyz, phi, dt, order, def_order=0, el_dofs_def=None, def_vals=None):
+    el_vtx = _i32(el_vtx); vtx_xyz = _f64(vtx_xyz); phi = _f64(phi)
+    ed = None if el_dofs_def is None else _i32(el_dofs_def)
+    dv = None if def_vals is None else _f64(def_vals)
+    err = C.c_int(0)
+    L = lib()
+    L.xo_integrate_one_deformed.restype = C.c_double
+    v = L.xo_integrate_one_deformed(dim, C.c_int64(el_vtx.shape[0]), _p(el_vtx, C.c_int32), _p(vtx_xyz), _p(phi), dt, order,
+                                    def_order, _p(ed, C.c_int32), _p(dv), C.byref(err))
+    if err.value:
+        raise RuntimeError(f"oracle error {err.value}")
+    return v
+
+
+def element_in_band(vals, lower, upper):
+    v = _f64(vals)
+    return bool(lib().xo_element_in_band(_p(v), len(v), C.c_double(lower), C.c_double(upper)))

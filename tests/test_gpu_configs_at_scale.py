@@ -25,10 +25,18 @@ NEG, POS, IF = 0, 1, 2
 def test_config3_isoparametric_ghost_penalty_kernel_of_constants():
     n, k = 40, 4
     mesh = xf.MakeStructured3DMesh(nx=n, device=DEV)
-    lset = xf.InterpolateToP1(lambda x, y, z: (torch.sqrt((x - .5) ** 2 + (y - .5) ** 2) - 0.28) ** 2 + (z - .5) ** 2 - 0.12 ** 2, mesh)
+    # the deformation is PRODUCED (LevelSetMeshAdaptation, row f3), as BASELINE.json's config 3 names it
+    torus = lambda x, y, z: (torch.sqrt((x - .5) ** 2 + (y - .5) ** 2) - 0.28) ** 2 + (z - .5) ** 2 - 0.12 ** 2   # noqa: E731
+    ad = xf.LevelSetMeshAdaptation(mesh, order=k, threshold=0.1, discontinuous_qn=True)
+    defo = ad.CalcDeformation(torus)
+    lset = ad.lset_p1
+    assert ad.nfail == 0 and float(defo.vals.abs().max()) > 0
+    exact = 2 * math.pi ** 2 * 0.28 * 0.12 ** 2
+    vol = xf.Integrate(levelset_domain={"levelset": lset, "domain_type": xf.NEG}, cf=1.0, mesh=mesh, order=k, deformation=defo)
+    vol0 = xf.Integrate(levelset_domain={"levelset": lset, "domain_type": xf.NEG}, cf=1.0, mesh=mesh, order=k)
+    print("config 3: torus volume error curved", vol - exact, "uncurved", vol0 - exact)
+    assert abs(vol - exact) < 1e-5 and abs(vol0 - exact) > 1e-4
     V0 = xf.H1(mesh, order=k, dgjumps=True)
-    g = torch.Generator().manual_seed(7)
-    defo = xf.Deformation(xf.H1(mesh, order=k), ((torch.rand((V0.ndof, 3), generator=g, dtype=torch.float64) - 0.5) * (0.004 / n)).to(DEV))
     ci = xf.CutInfo(mesh, lset)
     hasneg, hasif = ci.GetElementsOfType(xf.HASNEG), ci.GetElementsOfType(xf.IF)
     gpf = xf.GetFacetsWithNeighborTypes(mesh, a=hasneg, b=hasif, use_and=True)
