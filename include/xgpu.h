@@ -434,6 +434,20 @@ int xgpu_shift_points(xgpu_ctx* ctx, int dim, int fe_order, int64_t n, const int
                       int qn_mode, const double* qn, const double* blending, double threshold, double* shift_out,
                       int64_t* nfail_host);
 
+/* ---------------------------------------------------------------- general coefficient functions
+ * NGSolve evaluates a CoefficientFunction tree at every quadrature point (xfem/symboliccutbfi.cpp:174-193,
+ * xfem/symboliccutlfi.cpp:96-118).  Here a coefficient is TABULATED at the points of the per-element rules and folded into
+ * the rule weights (B^T diag(w D) B and sum_q w f phi_i only see the product), so every kernel above takes it unchanged:
+ * xgpu_rule_phys gives the physical coordinates (and measures |det F(xhat_q)|) of the points — deformation-aware —, the
+ * caller evaluates its function there, multiplies the weights, and calls xgpu_elmat_rule / xgpu_elvec_rule / the integrals.
+ * xgpu_h1_eval_rule evaluates a GridFunction of H1(fe_order) at the same points (el_dofs entries < 0: coefficient 0). */
+int xgpu_rule_phys(xgpu_ctx* ctx, int dim, int64_t n, const int32_t* elems, const int32_t* el_vtx, const double* vtx_xyz,
+                   const int64_t* offsets, const double* pts, double* xyz_out, double* meas_out);
+int xgpu_h1_eval_rule(xgpu_ctx* ctx, int dim, int fe_order, int64_t n, const int32_t* elems, const int32_t* el_vtx,
+                      const int32_t* el_dofs, const double* vals, const int64_t* offsets, const double* pts, double* out);
+/* fixed-order (tile tree) sum of n doubles: bit-reproducible; synchronises (Integrate with a tabulated coefficient) */
+int xgpu_reduce_sum(xgpu_ctx* ctx, int64_t n, const double* vals, double* result_host);
+
 #ifdef __cplusplus
 }
 #endif

@@ -18,7 +18,7 @@ from .cutinfo import (NEG, POS, IF, VOL, BND, HAS, BitArray, GridFunction, Inter
 from .cutinfo import C_NO as NO, C_NEG as CDOM_NEG, C_POS as CDOM_POS, C_UNCUT as UNCUT, C_IF as CDOM_IF, \
     C_HASNEG as HASNEG, C_HASPOS as HASPOS, C_ANY as ANY
 from .forms import (dCut, dFacetPatch, grad, Normalize, specialcf, BilinearForm, RestrictedBilinearForm, LinearForm,
-                    Integrate, TrialFunction, TestFunction, x, y, z, dn)
+                    Integrate, TrialFunction, TestFunction, x, y, z, dn, CoefficientFunction)
 from .spacetime import (ScalarTimeFE, SpaceTimeFESpace, SpaceTimeGridFunction, SpaceTimeInterpolateToP1,
                         ReferenceTimeVariable, tref, dtref, dt, fix_tref, dxtref, dmesh)
 from .lsetcurv import LevelSetMeshAdaptation, ProjectShift

@@ -119,6 +119,9 @@ _SIGS = {
     "xgpu_adjacency_plan": (C.c_int, [VP, C.c_int64, C.POINTER(Batch), C.c_int, C.POINTER(VP)]),
     "xgpu_vec_scatter": (C.c_int, [VP, VP, C.POINTER(Batch), C.c_int, VP]),
     "xgpu_vec_scatter_mean": (C.c_int, [VP, VP, C.POINTER(Batch), C.c_int, VP, C.c_int, C.c_int]),
+    "xgpu_rule_phys": (C.c_int, [VP, C.c_int, C.c_int64, VP, VP, VP, VP, VP, VP, VP]),
+    "xgpu_h1_eval_rule": (C.c_int, [VP, C.c_int, C.c_int, C.c_int64, VP, VP, VP, VP, VP, VP, VP]),
+    "xgpu_reduce_sum": (C.c_int, [VP, C.c_int64, VP, c_f64p]),
     "xgpu_band_elements": (C.c_int, [VP, C.c_int, C.c_int64, VP, VP, C.c_double, C.c_double, VP]),
     "xgpu_rule_points_phys": (C.c_int, [VP, C.c_int, C.c_int, C.c_int64, VP, VP, VP, VP]),
     "xgpu_h1_grad_points": (C.c_int, [VP, C.c_int, C.c_int, C.c_int, C.c_int64, VP, VP, VP, VP, VP, VP]),

@@ -293,6 +293,20 @@ int xgpu_sum_f64(xgpu_ctx* ctx, double* buf_a, int64_t n, double* buf_b, double*
   return XGPU_OK;
 }
 
+extern "C" int xgpu_reduce_sum(xgpu_ctx* ctx, int64_t n, const double* vals, double* result_host)
+{
+  if (!ctx || n < 0 || !result_host || (n > 0 && !vals)) return xgpu_fail(ctx, XGPU_ERR_ARG, "xgpu_reduce_sum: bad argument");
+  *result_host = 0.0;
+  if (n == 0) return XGPU_OK;
+  void* p;
+  const int64_t nb = (n + 4095) / 4096;
+  int rc = xgpu_scratch(ctx, 1, sizeof(double) * (n + nb + 2), &p);
+  if (rc) return rc;
+  double* buf = (double*)p;
+  XGPU_CUDA(ctx, cudaMemcpyAsync(buf, vals, sizeof(double) * n, cudaMemcpyDeviceToDevice, ctx->stream));
+  return xgpu_sum_f64(ctx, buf, n, buf + n, result_host);
+}
+
 extern "C" int xgpu_cutquad_count(xgpu_ctx* ctx, int dim, int64_t n, const int32_t* elems, const int32_t* el_vtx,
                                   const double* phi, int dt, int order, int64_t* offsets, int64_t* total_host)
 {

@@ -242,6 +242,8 @@ class FacetForm:
         if isinstance(f, FacetForm):
             return f
         if isinstance(f, Form):   # u*v and (u-u.Other())*(v-v.Other()) written with plain proxies
+            if f.cf is not None:
+                raise XgpuError("coefficient functions on facet integrands are not on the accelerated path")
             out = []
             for a, b, c, hp in f.terms:
                 if a == OP_ID and b == OP_ID:
@@ -285,12 +287,74 @@ def dn(u, order=1, comp=-1, hdiv=False):
     return grad(u) * FacetNormal()
 
 
+class CoefficientFunction:
+    """a coefficient evaluated at every quadrature point — NGSolve's CoefficientFunction on the accelerated path
+    (xfem/symboliccutbfi.cpp:174-193, xfem/symboliccutlfi.cpp:96-118): fn(x, y[, z], *gf_values) -> tensor, evaluated with
+    torch on the device at the PHYSICAL points of the cut rules (deformed mesh included, xgpu_rule_phys) and folded into
+    the rule weights, so that one coefficient multiplies a whole integrand:  cf * (grad(u)*grad(v) + u*v) * dx,  cf * v * dx.
+    gfs: H1 GridFunctions as (space, coefficient vector) pairs; their values at the points follow the coordinates."""
+
+    def __init__(self, fn, gfs=()):
+        if isinstance(fn, numbers.Number):
+            c = float(fn)
+            fn = lambda *a: torch.full_like(a[0], c)   # noqa: E731
+        self.factors = [(fn, tuple(gfs))]   # a product of functions, each with its own GridFunction arguments
+        self.scale = 1.0
+
+    def _copy(self, factors=None, scale=None):
+        r = CoefficientFunction.__new__(CoefficientFunction)
+        r.factors = list(self.factors if factors is None else factors)
+        r.scale = self.scale if scale is None else scale
+        return r
+
+    def __mul__(self, o):
+        if isinstance(o, numbers.Number):
+            return self._copy(scale=self.scale * float(o))
+        if isinstance(o, CoefficientFunction):
+            return self._copy(self.factors + o.factors, self.scale * o.scale)
+        if isinstance(o, Proxy):
+            if not o.is_test:
+                raise XgpuError("a coefficient multiplies a whole integrand: cf * (u*v), cf * v")
+            o = LForm.from_proxy(o)
+        if isinstance(o, (Form, LForm)):
+            return o._with_cf(self)
+        if isinstance(o, (FacetForm, FacetExpr)):
+            raise XgpuError("coefficient functions on facet integrands are not on the accelerated path (constants and h-powers are)")
+        return NotImplemented
+
+    __rmul__ = __mul__
+
+    def __neg__(self):
+        return self * -1.0
+
+    def evaluate(self, dim, fe_mesh, elems, off, pts, ctx):
+        """values at the points of the per-element rules (off, pts) on the listed elements"""
+        xyz = ops.rule_phys(dim, elems, fe_mesh.elements, fe_mesh.points, off, pts, ctx=ctx)
+        coords = [xyz[:, c] for c in range(dim)]
+        out = torch.full((xyz.shape[0],), self.scale, dtype=torch.float64, device=xyz.device)
+        for fn, gfs in self.factors:
+            args = list(coords)
+            for space, vec in gfs:
+                args.append(ops.h1_eval_rule(dim, space.order, elems, fe_mesh.elements, space.el_dofs, vec, off, pts, ctx=ctx))
+            out = out * torch.as_tensor(fn(*args), dtype=torch.float64, device=xyz.device)
+        return out.contiguous()
+
+
+def _merge_cf(a, b):
+    if a is b:
+        return a
+    raise XgpuError("integrands with different coefficient functions: add them as separate integrals (a += cf1*...*dx; a += cf2*...*dx)")
+
+
 class LForm:
     """linear form integrand: sum of (op_test, coef, hpow, expo) = coef h^hpow x^expo op_test(v)
     (menu of xfem/symboliccutlfi.cpp's CoefficientFunction on the accelerated path)"""
 
-    def __init__(self, terms, space, nlset=None):
-        self.terms, self.space, self.nlset = terms, space, nlset
+    def __init__(self, terms, space, nlset=None, cf=None):
+        self.terms, self.space, self.nlset, self.cf = terms, space, nlset, cf
+
+    def _with_cf(self, cf):
+        return LForm(self.terms, self.space, self.nlset, cf if self.cf is None else self.cf * cf)
 
     @staticmethod
     def from_proxy(v):
@@ -304,7 +368,7 @@ class LForm:
         if isinstance(o, Proxy):
             o = LForm.from_proxy(o)
         if isinstance(o, LForm):
-            return LForm(self.terms + o.terms, self.space, Form._merge_nlset(self.nlset, o.nlset))
+            return LForm(self.terms + o.terms, self.space, Form._merge_nlset(self.nlset, o.nlset), _merge_cf(self.cf, o.cf))
         return NotImplemented
 
     def __mul__(self, o):
@@ -313,10 +377,10 @@ class LForm:
         if isinstance(o, MeshSize):
             o = Scalar(1.0, o.power)
         if isinstance(o, Scalar):
-            return LForm([(a, c * o.c, hp + o.hpow, ex) for a, c, hp, ex in self.terms], self.space, self.nlset)
+            return LForm([(a, c * o.c, hp + o.hpow, ex) for a, c, hp, ex in self.terms], self.space, self.nlset, self.cf)
         if isinstance(o, CoordMonomial):
             return LForm([(a, c * o.coef, hp, tuple(e1 + e2 for e1, e2 in zip(ex, o.expo))) for a, c, hp, ex in self.terms],
-                         self.space, self.nlset)
+                         self.space, self.nlset, self.cf)
         if isinstance(o, CutDifferentialSymbol):
             return Integral(self, o)
         return NotImplemented
@@ -347,8 +411,11 @@ def grad(u):
 class Form:
     """sum of monomials (op_trial, op_test, coef, hpow)"""
 
-    def __init__(self, terms, space, nlset=None):
-        self.terms, self.space, self.nlset = terms, space, nlset
+    def __init__(self, terms, space, nlset=None, cf=None):
+        self.terms, self.space, self.nlset, self.cf = terms, space, nlset, cf
+
+    def _with_cf(self, cf):
+        return Form(self.terms, self.space, self.nlset, cf if self.cf is None else self.cf * cf)
 
     @staticmethod
     def _merge_nlset(a, b):
@@ -374,7 +441,7 @@ class Form:
         if isinstance(o, FacetForm):
             return FacetForm.of(self) + o
         if isinstance(o, Form):
-            return Form(self.terms + o.terms, self.space, Form._merge_nlset(self.nlset, o.nlset))
+            return Form(self.terms + o.terms, self.space, Form._merge_nlset(self.nlset, o.nlset), _merge_cf(self.cf, o.cf))
         return NotImplemented
 
     def __sub__(self, o):
@@ -386,7 +453,7 @@ class Form:
     def __mul__(self, o):
         if isinstance(o, (numbers.Number, Scalar, MeshSize)):
             s = o if isinstance(o, Scalar) else (Scalar(float(o)) if isinstance(o, numbers.Number) else Scalar(1.0, o.power))
-            return Form([(a, b, c * s.c, hp + s.hpow) for a, b, c, hp in self.terms], self.space, self.nlset)
+            return Form([(a, b, c * s.c, hp + s.hpow) for a, b, c, hp in self.terms], self.space, self.nlset, self.cf)
         if isinstance(o, CutDifferentialSymbol) and (o.skeleton or o.element_boundary):
             return Integral(FacetForm.of(self), o)
         if isinstance(o, (CutDifferentialSymbol, FacetPatchDifferentialSymbol)):
@@ -655,6 +722,8 @@ class BilinearForm:
                 # n = Normalize(grad(lset)) of the level set the integrand names (square.GetOuterNormals style forms)
                 phi_n = _lset_vec(integ.form.nlset, mesh) if (has_dn and integ.form.nlset is not None) else phi
                 ctx.raise_on_geometry_error()
+                if w.numel() and integ.form.cf is not None:   # tabulated coefficient folded into the weights
+                    w = w * integ.form.cf.evaluate(dim, mesh, l, off, q, ctx)
                 if w.numel():
                     ops.elmat_rule(dim, p, l, mesh.elements, mesh.points, phi_n, off, q, w, terms, out=m_A, accumulate=True,
                                    slots=slots, ctx=ctx)
@@ -709,8 +778,14 @@ class BilinearForm:
                     if not init_U and not full:
                         m_U.zero_()
                     with ctx.deformation(_eff_def(dx.deformation, mesh)):
-                        ops.elmat_std(dim, p, l, mesh.elements, mesh.points, phi0, order, terms, out=m_U,
-                                      accumulate=init_U or not full, slots=None if full else slot_U[l.long()].contiguous(), ctx=ctx)
+                        if integ.form.cf is None:
+                            ops.elmat_std(dim, p, l, mesh.elements, mesh.points, phi0, order, terms, out=m_U,
+                                          accumulate=init_U or not full, slots=None if full else slot_U[l.long()].contiguous(), ctx=ctx)
+                        else:   # a coefficient varies from point to point: per-element copies of the standard rule, weights scaled
+                            off, q, w = ops.cutquad(dim, l, mesh.elements, mesh.points, phi0, dt, order, ctx=ctx)
+                            w = w * integ.form.cf.evaluate(dim, mesh, l, off, q, ctx)
+                            ops.elmat_rule(dim, p, l, mesh.elements, mesh.points, phi0, off, q, w, terms, out=m_U,
+                                           accumulate=init_U or not full, slots=None if full else slot_U[l.long()].contiguous(), ctx=ctx)
                     init_U = True
             if l_C.numel():
                 sel = Cc.bits if don is None else ops.bitset_op(ops.BIT_AND, Cc.bits, don.bits, ne, ctx=ctx)
@@ -722,6 +797,8 @@ class BilinearForm:
                     with ctx.deformation(_eff_def(dx.deformation, mesh)):
                         off, q, w = ops.cutquad(dim, l, mesh.elements, mesh.points, phi0, dt, order, ctx=ctx)
                         ctx.raise_on_geometry_error()
+                        if integ.form.cf is not None:
+                            w = w * integ.form.cf.evaluate(dim, mesh, l, off, q, ctx)
                         ops.elmat_rule(dim, p, l, mesh.elements, mesh.points, phi0, off, q, w, terms, out=m_C,
                                        accumulate=init_C or not full, slots=None if full else slot_C[l.long()].contiguous(), ctx=ctx)
                     init_C = True
@@ -737,6 +814,10 @@ class BilinearForm:
 
     def Assemble(self):
         sp = self.space
+        unsup = [i for i in self.integrals if getattr(i.form, "cf", None) is not None and
+                 (hasattr(sp, "timeFE") or isinstance(i.dx, FacetPatchDifferentialSymbol) or i.dx.vb == 1)]
+        if unsup:
+            raise XgpuError("coefficient functions: volume cut integrals (dCut, vb=VOL) on H1 spaces only")
         if hasattr(sp, "timeFE"):  # SpaceTimeFESpace
             from . import spacetime
             return spacetime.assemble_bilinear(self)
@@ -890,6 +971,8 @@ class LinearForm:
 
     def Assemble(self):
         sp = self.space
+        if any(getattr(i.form, "cf", None) is not None and (hasattr(sp, "timeFE") or i.dx.vb == 1) for i in self.integrals):
+            raise XgpuError("coefficient functions: volume cut integrals (dCut, vb=VOL) on H1 spaces only")
         if hasattr(sp, "timeFE"):  # SpaceTimeFESpace
             from . import spacetime
             return spacetime.assemble_linear(self)
@@ -943,6 +1026,8 @@ class LinearForm:
                 ctx.raise_on_geometry_error()
                 if has_dn and integ.form.nlset is not None:
                     phi = _lset_vec(integ.form.nlset, mesh)
+                if w.numel() and integ.form.cf is not None:   # f(x_q) folded into the weights (xfem/symboliccutlfi.cpp:96-118)
+                    w = w * integ.form.cf.evaluate(dim, mesh, l, off, q, ctx)
                 if w.numel():
                     ops.elvec_rule(dim, p, l, mesh.elements, mesh.points, phi, off, q, w, integ.form.terms, out=v_A,
                                    accumulate=True, slots=slots, ctx=ctx)
@@ -998,6 +1083,31 @@ def _eff_def(deformation, mesh):
     return deformation if deformation is not None else getattr(mesh, "deformation", None)
 
 
+def _integrate_cf(ld, mesh, cf, order, deformation):
+    """sum_q w_q |det F(xhat_q)| cf(x_q): the weights times the point measures (xgpu_rule_phys), summed in a fixed order"""
+    if ld.get("subdivlvl", 0) != 0:
+        raise XgpuError("subdivlvl != 0: legacy path not provided")
+    if ld.get("vb", 0) == 1:
+        raise XgpuError("Integrate over BND: constants and monomials only")
+    if "order" in ld and ld["order"] is not None and ld["order"] >= 0:
+        order = ld["order"]
+    dim = mesh.dim
+    ctx = default_ctx(mesh.device.index)
+    ls, dt = ld["levelset"], ld["domain_type"]
+    with ctx.deformation(_eff_def(deformation, mesh)):
+        if isinstance(ls, (list, tuple)):
+            phis = torch.stack([_lset_vec(l, mesh) for l in ls]).contiguous()
+            off, p, w = ops.cutquad_ml(dim, None, mesh.elements, mesh.points, phis, _normalize_dtlist(dt, len(ls)), order, ctx=ctx)
+        else:
+            off, p, w = ops.cutquad(dim, None, mesh.elements, mesh.points, _lset_vec(ls, mesh), int(dt), order, ctx=ctx)
+        ctx.raise_on_geometry_error()
+        if not w.numel():
+            return 0.0
+        _, meas = ops.rule_phys(dim, None, mesh.elements, mesh.points, off, p, want_meas=True, ctx=ctx)
+        vals = cf.evaluate(dim, mesh, None, off, p, ctx) * w * meas
+    return ops.sum_f64(vals, ctx=ctx)
+
+
 def Integrate(levelset_domain=None, mesh=None, cf=1.0, order=5, time_order=-1, deformation=None, heapsize=1000000):
     """python/__init__.py:361-439 -> cutint/python_cutint.cpp:21-163: sum_q w_q |det F| cf(x_q)."""
     ld = levelset_domain
@@ -1008,8 +1118,12 @@ def Integrate(levelset_domain=None, mesh=None, cf=1.0, order=5, time_order=-1, d
         return spacetime.integrate(ld, mesh, cf, order, time_order, deformation)
     if isinstance(cf, numbers.Number):
         cf = CoordMonomial((0, 0, 0), cf)
+    if callable(cf) and not isinstance(cf, (CoordMonomial, CoefficientFunction)):
+        cf = CoefficientFunction(cf)
+    if isinstance(cf, CoefficientFunction):
+        return _integrate_cf(ld, mesh, cf, order, deformation)
     if not isinstance(cf, CoordMonomial):
-        raise XgpuError("Integrate: cf must be a constant or a coordinate monomial")
+        raise XgpuError("Integrate: cf is a constant, a coordinate monomial, a CoefficientFunction or a callable of the coordinates")
     ld = levelset_domain
     if ld.get("subdivlvl", 0) != 0:
         raise XgpuError("subdivlvl != 0: legacy path not provided")

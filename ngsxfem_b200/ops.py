@@ -554,6 +554,39 @@ def vec_scatter_mean(plan, batches, out, comp=0):
     return out
 
 
+# ---------------------------------------------------------------- tabulated coefficient functions (csrc/deform.cu)
+def rule_phys(dim, elems, el_vtx, vtx_xyz, off, pts, want_meas=False, ctx=None):
+    """physical coordinates (total x dim) [and measures |det F|] of the points of per-element rules; honours the deformation"""
+    ctx = ctx or default_ctx()
+    n = el_vtx.shape[0] if elems is None else elems.numel()
+    tot = pts.shape[0]
+    xyz = torch.empty((tot, dim), dtype=torch.float64, device=el_vtx.device)
+    meas = torch.empty(tot, dtype=torch.float64, device=el_vtx.device) if want_meas else None
+    if tot:
+        ctx.check(ctx.lib.xgpu_rule_phys(ctx.h, dim, n, ptr(elems), ptr(_i32(el_vtx)), ptr(_f64(vtx_xyz)), ptr(off), ptr(_f64(pts)),
+                                         ptr(xyz), ptr(meas)))
+    return (xyz, meas) if want_meas else xyz
+
+
+def sum_f64(vals, ctx=None):
+    """deterministic sum of a device vector (xgpu_reduce_sum)"""
+    ctx = ctx or default_ctx()
+    r = C.c_double(0.0)
+    ctx.check(ctx.lib.xgpu_reduce_sum(ctx.h, vals.numel(), ptr(_f64(vals)), C.byref(r)))
+    return float(r.value)
+
+
+def h1_eval_rule(dim, fe_order, elems, el_vtx, el_dofs, vals, off, pts, ctx=None):
+    """values of an H1(fe_order) function (coefficient vector `vals`) at the points of per-element rules"""
+    ctx = ctx or default_ctx()
+    n = el_vtx.shape[0] if elems is None else elems.numel()
+    out = torch.empty(pts.shape[0], dtype=torch.float64, device=el_vtx.device)
+    if pts.shape[0]:
+        ctx.check(ctx.lib.xgpu_h1_eval_rule(ctx.h, dim, fe_order, n, ptr(elems), ptr(_i32(el_vtx)), ptr(_i32(el_dofs)), ptr(_f64(vals)),
+                                            ptr(off), ptr(_f64(pts)), ptr(out)))
+    return out
+
+
 # ---------------------------------------------------------------- isoparametric deformation producer (csrc/lsetcurv.cu)
 def band_elements(dim, el_vtx, lset_p1, lower=0.0, upper=0.0, ctx=None):
     """ElementInRelevantBand for every element -> BitArray words (lsetcurving/calcpointshift.cpp:120-141)"""
