@@ -137,6 +137,10 @@ int xgpu_elements_with_neighbor_facets(xgpu_ctx* ctx, int64_t nf, const int32_t*
 /* GetDofsOfElements (cutinfo.cpp:599-622); el_dofs: ne x nd, -1 = no dof */
 int xgpu_dofs_of_elements(xgpu_ctx* ctx, int64_t ne, int nd, const int32_t* el_dofs,
                           const uint32_t* el_bits, int64_t ndof, uint32_t* bits_out);
+/* the converse: elements with at least one marked entry in their row of `table` (ne x nd, -1 = unused).  With the vertex table
+ * and xgpu_dofs_of_elements on it this is GetElementsWithSharedVertex (xfem/cutinfo.cpp:568-597): mark the vertices of the
+ * elements in a, then every element touching a marked vertex. */
+int xgpu_elements_with_marked(xgpu_ctx* ctx, int64_t ne, int nd, const int32_t* table, const uint32_t* marks, uint32_t* bits_out);
 /* RestrictedFESpace / CompressedFESpace numbering (utils/restrictedfespace.cpp:23-51):
  * map[d] = rank of d among the set bits, -1 if unset; *nactive_host = number of set bits */
 int xgpu_bitset_rank(xgpu_ctx* ctx, const uint32_t* bits, int64_t nbits, int32_t* map, int64_t* nactive_host);

@@ -14,7 +14,7 @@ from .meshes import Mesh, MakeStructured1DMesh, MakeStructured2DMesh, MakeStruct
 from .fes import H1, Restrict, Deformation
 from .cutinfo import (NEG, POS, IF, VOL, BND, HAS, BitArray, GridFunction, InterpolateToP1, CutInfo,
                       MultiLevelsetCutInfo, GetFacetsWithNeighborTypes, GetElementsWithNeighborFacets,
-                      GetDofsOfElements, CombinedDomainType)
+                      GetDofsOfElements, GetElementsWithSharedVertex, CombinedDomainType)
 from .cutinfo import C_NO as NO, C_NEG as CDOM_NEG, C_POS as CDOM_POS, C_UNCUT as UNCUT, C_IF as CDOM_IF, \
     C_HASNEG as HASNEG, C_HASPOS as HASPOS, C_ANY as ANY
 from .forms import (dCut, dFacetPatch, grad, Normalize, specialcf, BilinearForm, RestrictedBilinearForm, LinearForm,

@@ -505,6 +505,34 @@ extern "C" int xgpu_dofs_of_elements(xgpu_ctx* ctx, int64_t ne, int nd, const in
   return XGPU_OK;
 }
 
+namespace {
+// elements with at least one marked entry in their table row (vertices / dofs): thread per element, ballot -> words
+__global__ void __launch_bounds__(256) k_els_with_marked(int64_t ne, int nd, const int32_t* __restrict__ table,
+                                                         const uint32_t* __restrict__ marks, uint32_t* __restrict__ bits_out)
+{
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  bool hit = false;
+  if (e < ne) {
+    for (int k = 0; k < nd; k++) {
+      const int32_t d = __ldg(table + e * nd + k);
+      if (d >= 0 && ((__ldg(marks + (d >> 5)) >> (d & 31)) & 1u)) hit = true;
+    }
+  }
+  const unsigned w = __ballot_sync(0xffffffffu, hit);
+  if ((threadIdx.x & 31) == 0 && e < ne) bits_out[e >> 5] = w;
+}
+}  // namespace
+
+extern "C" int xgpu_elements_with_marked(xgpu_ctx* ctx, int64_t ne, int nd, const int32_t* table, const uint32_t* marks,
+                                         uint32_t* bits_out)
+{
+  if (!ctx || ne < 0 || nd < 1 || (ne > 0 && (!table || !marks || !bits_out))) return xgpu_fail(ctx, XGPU_ERR_ARG, "xgpu_elements_with_marked: bad argument");
+  if (ne == 0) return XGPU_OK;
+  k_els_with_marked<<<nblk(ne, 256), 256, 0, ctx->stream>>>(ne, nd, table, marks, bits_out);
+  XGPU_LAUNCH_CHECK(ctx);
+  return XGPU_OK;
+}
+
 extern "C" int xgpu_gather_rows(xgpu_ctx* ctx, int64_t n, const int32_t* list, int width, const int32_t* table,
                                 const int32_t* map, int32_t* out)
 {

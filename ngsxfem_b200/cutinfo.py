@@ -352,6 +352,12 @@ def GetElementsWithNeighborFacets(mesh, a, heapsize=1000000):
     return BitArray(mesh.ne, words=ops.elements_with_neighbor_facets(fe, a.bits, mesh.ne))
 
 
+def GetElementsWithSharedVertex(mesh, a, heapsize=1000000):
+    """xfem/cutinfo.cpp:568-597: the elements that share a vertex with an element of a (a itself included)"""
+    vmarks = ops.dofs_of_elements(mesh.elements, a.bits, mesh.nv)
+    return BitArray(mesh.ne, words=ops.elements_with_marked(mesh.elements, vmarks))
+
+
 def GetDofsOfElements(space, a, heapsize=1000000):
     """xfem/cutinfo.cpp:599-622"""
     return BitArray(space.ndof, words=ops.dofs_of_elements(space.el_dofs, a.bits, space.ndof))

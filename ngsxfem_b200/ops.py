@@ -568,6 +568,15 @@ def rule_phys(dim, elems, el_vtx, vtx_xyz, off, pts, want_meas=False, ctx=None):
     return (xyz, meas) if want_meas else xyz
 
 
+def elements_with_marked(table, marks, ctx=None):
+    """BitArray words of the rows of `table` (ne x nd) that hold at least one marked entry"""
+    ctx = ctx or default_ctx()
+    ne, nd = table.shape
+    out = new_bits(ne, table.device)
+    ctx.check(ctx.lib.xgpu_elements_with_marked(ctx.h, ne, nd, ptr(_i32(table)), ptr(marks), ptr(out)))
+    return out
+
+
 def sum_f64(vals, ctx=None):
     """deterministic sum of a device vector (xgpu_reduce_sum)"""
     ctx = ctx or default_ctx()

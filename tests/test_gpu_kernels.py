@@ -165,6 +165,13 @@ def test_marker_helpers_match_oracle():
     gd = ops.dofs_of_elements(V.el_dofs, ghas, V.ndof)
     od = xo.dofs_of_elements(V.el_dofs.cpu().numpy(), hasneg, V.ndof)
     assert np.array_equal(bits_np(gd)[:len(od)], od)
+    # GetElementsWithSharedVertex (xfem/cutinfo.cpp:568-597) against its definition in numpy
+    import ngsxfem_b200 as xf
+    shared = xf.GetElementsWithSharedVertex(md, xf.BitArray(m.ne, words=gi))
+    in_if = unpack_bits(bits_np(gi), m.ne).astype(bool)
+    vmark = np.zeros(m.nv, dtype=bool); vmark[els[in_if].reshape(-1)] = True
+    assert np.array_equal(unpack_bits(bits_np(shared.bits), m.ne).astype(bool), vmark[els].any(axis=1))
+    assert shared.NumSet() > int(in_if.sum())
     thr = ops.threshold_elements(ops.classify(3, md.elements, torch.from_numpy(phi).to(DEV))[3], NEG, 0.3)
     cr = xo.cutinfo_update(3, els, phi)[3]
     assert np.array_equal(unpack_bits(bits_np(thr), m.ne), cr >= 0.3)

@@ -10,10 +10,13 @@ import subprocess
 import sys
 
 PHASE = [("k_classify", "classify"), ("k_cut_ratio", "classify"),
+         ("k_count_dofs", "restrict_plan"), ("k_active_", "restrict_plan"), ("k_gather_fill", "restrict_plan"), ("k_adj_", "restrict_plan"),
          ("k_dofs_of_els", "restrict"), ("k_bits_rank", "restrict"), ("k_gather_rows", "restrict"),
+         ("k_elmat_cut", "elmat_cut"), ("k_affine_coefs", "affine_coefs"),
          ("k_cq_", "elmat"), ("k_elmat", "elmat"),
-         ("k_adj_", "csr_adjacency"), ("k_pattern", "csr_pattern_pass"), ("k_compact", "csr_pattern"),
-         ("k_scatter", "csr_scatter")]
+         ("k_rows_small_pattern", "csr_count_pass"), ("k_rows_warp_pattern", "csr_count_pass"),
+         ("k_rows_small_values", "csr_rows_fused"), ("k_rows_warp_values", "csr_rows_fused"),
+         ("k_pattern", "csr_pattern_pass"), ("k_compact", "csr_pattern"), ("k_scatter", "csr_scatter")]
 UNIT = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "ns": 1e-6, "us": 1e-3, "ms": 1.0, "s": 1e3,
         "nsecond": 1e-6, "usecond": 1e-3, "msecond": 1.0, "second": 1e3}
 
@@ -47,7 +50,7 @@ def main():
             if pref in short:
                 phases[ph] = phases.get(ph, 0.0) + b
                 break
-    json.dump({"n": n, "source": rep.split("/")[-1], "note": "dram__bytes_read.sum + dram__bytes_write.sum per step, summed over the phase's kernels (ncu --set full, cold cache per replay)",
+    json.dump({"n": n, "source": rep.split("/")[-1], "note": "dram__bytes_read.sum + dram__bytes_write.sum per step, summed over the phase's kernels (cold cache per replay)",
                "phases": {k: int(v) for k, v in phases.items()},
                "kernels": {k: {"launches": v[0], "dram_bytes": int(v[1]), "ms_under_ncu": round(v[2], 4)} for k, v in kernels.items()}},
               open(out, "w"), indent=1)

@@ -1,0 +1,6 @@
+python -m pytest tests -m gpu -x -q > gpurun_out/s13_tests_n2.log 2>&1; tail -n 3 gpurun_out/s13_tests_n2.log
+for sc in weak strong; do
+python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 10 --warmup 3 --scaling $sc > gpurun_out/s13_n2_$sc.json 2> gpurun_out/s13_n2_$sc.err
+tail -n 1 gpurun_out/s13_n2_$sc.json | python -c "
+import json,sys; d=json.loads(sys.stdin.read()); print('$sc', d['n_gpus'], round(d['ms_per_step'],3), round(d['value']/1e6,1), 'e2e', round(d['e2e']['ms_per_step'],2), d.get('check',{}).get('ok')); print(d['config'].get('phases_ms_max_over_ranks'))"
+done
