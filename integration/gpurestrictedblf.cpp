@@ -19,9 +19,9 @@ class GpuRestrictedBilinearForm : public RestrictedBilinearForm<double, double> 
   xgpu_ctx* ctx = nullptr;
   shared_ptr<GridFunction> lsetp1;
   DeviceBuffer<int32_t> d_elvtx, d_eldofs, d_lneg, d_lif, d_tneg, d_tif, d_dofmap, d_col;
-  DeviceBuffer<double> d_xyz, d_phi, d_ratio, d_coefs, d_mif, d_vals, d_pn, d_wn, d_pi, d_wi;
+  DeviceBuffer<double> d_xyz, d_phi, d_ratio, d_coefs, d_mif, d_vals;
   DeviceBuffer<uint32_t> d_neg, d_pos, d_if;
-  DeviceBuffer<int64_t> d_offn, d_offi, d_rowptr;
+  DeviceBuffer<int64_t> d_rowptr;
 public:
   GpuRestrictedBilinearForm(shared_ptr<GridFunction> alset) : lsetp1(alset)
   {
@@ -54,9 +54,10 @@ public:
     d_neg.Resize(nw); d_pos.Resize(nw); d_if.Resize(nw); d_ratio.Resize(ne);
     Check(ctx, xgpu_classify(ctx, dim, ne, d_elvtx, d_phi, d_neg, d_pos, d_if, d_ratio));
     xgpu_adapter::CheckGeometry(ctx);
-    int64_t n_neg = 0, n_if = 0;
-    Check(ctx, xgpu_bitset_count(ctx, d_neg, ne, &n_neg));
-    Check(ctx, xgpu_bitset_count(ctx, d_if, ne, &n_if));
+    int64_t cnt[2] = {0, 0};
+    const uint32_t* sets[2] = {d_neg, d_if};
+    Check(ctx, xgpu_bitset_count_many(ctx, 2, sets, ne, cnt));      // one host wait for both list lengths
+    const int64_t n_neg = cnt[0], n_if = cnt[1];
     d_lneg.Resize(n_neg); d_lif.Resize(n_if);
     Check(ctx, xgpu_bitset_to_list(ctx, d_neg, ne, d_lneg));
     Check(ctx, xgpu_bitset_to_list(ctx, d_if, ne, d_lif));
@@ -71,19 +72,14 @@ public:
     xgpu_plan* plan = nullptr;
     Check(ctx, xgpu_restrict_plan(ctx, (int)nd, d_eldofs, 2, lists, counts, ndof_full, d_dofmap, &ndof, tables, &plan));
     Check(ctx, xgpu_csr_count_rows(ctx, plan, &nnz));
-    // (4) cut quadrature + cut element matrices (NEG volume terms and the IF term in one pass), 7 coefficients per uncut element
+    // (4) cut element matrices, the cut rule made inside the kernel as T_CalcElementMatrixAdd does (NEG volume terms and the IF
+    //     term in one pass; orders > 2 / deformed meshes: xgpu_cutquad_count/_fill + xgpu_elmat_rule_pair), 7 coefficients per
+    //     uncut element
     const xgpu_term vol[2] = {{XGPU_OP_GRAD, XGPU_OP_GRAD, 1.0, 0}, {XGPU_OP_ID, XGPU_OP_ID, 1.0, 0}}, ifc[1] = {{XGPU_OP_ID, XGPU_OP_ID, 1.0, 0}};
     const int order = 2 * p;
-    int64_t npn = 0, npi = 0;
-    d_offn.Resize(n_if + 1); d_offi.Resize(n_if + 1);
-    Check(ctx, xgpu_cutquad_count(ctx, dim, n_if, d_lif, d_elvtx, d_phi, XGPU_NEG, order, d_offn, &npn));
-    Check(ctx, xgpu_cutquad_count(ctx, dim, n_if, d_lif, d_elvtx, d_phi, XGPU_IF, order, d_offi, &npi));
-    d_pn.Resize(3 * npn); d_wn.Resize(npn); d_pi.Resize(3 * npi); d_wi.Resize(npi);
-    Check(ctx, xgpu_cutquad_fill(ctx, dim, n_if, d_lif, d_elvtx, d_xyz, d_phi, XGPU_NEG, order, d_offn, d_pn, d_wn));
-    Check(ctx, xgpu_cutquad_fill(ctx, dim, n_if, d_lif, d_elvtx, d_xyz, d_phi, XGPU_IF, order, d_offi, d_pi, d_wi));
-    xgpu_adapter::CheckGeometry(ctx);
     d_mif.Resize(n_if * nd * nd); d_coefs.Resize(n_neg * 8);
-    Check(ctx, xgpu_elmat_rule_pair(ctx, dim, p, n_if, d_lif, d_elvtx, d_xyz, d_phi, d_offn, d_pn, d_wn, vol, 2, d_offi, d_pi, d_wi, ifc, 1, 0, nullptr, d_mif));
+    Check(ctx, xgpu_elmat_cut_pair(ctx, dim, p, n_if, d_lif, d_elvtx, d_xyz, d_phi, XGPU_NEG, order, vol, 2, XGPU_IF, order, ifc, 1, 0, nullptr, d_mif));
+    xgpu_adapter::CheckGeometry(ctx);
     Check(ctx, xgpu_affine_coefs(ctx, dim, n_neg, d_lneg, d_elvtx, d_xyz, vol, 2, d_coefs));
     const double* tref = nullptr; int ncoef = 0;
     Check(ctx, xgpu_reftensor(ctx, dim, p, order, &tref, &ncoef));

@@ -349,6 +349,28 @@ extern "C" int xgpu_bitset_count(xgpu_ctx* ctx, const uint32_t* bits, int64_t nb
   return XGPU_OK;
 }
 
+extern "C" int xgpu_bitset_count_many(xgpu_ctx* ctx, int k, const uint32_t* const* bits_host, int64_t nbits, int64_t* counts_host)
+{
+  if (!ctx || k < 1 || k > 8 || !bits_host || !counts_host) return xgpu_fail(ctx, XGPU_ERR_ARG, "xgpu_bitset_count_many: bad argument (1..8 bitsets)");
+  const int64_t nwords = (nbits + 31) >> 5;
+  for (int i = 0; i < k; i++) counts_host[i] = 0;
+  if (nwords == 0) return XGPU_OK;
+  void* p;
+  int rc = xgpu_scratch(ctx, 6, 64, &p);
+  if (rc) return rc;
+  XGPU_CUDA(ctx, cudaMemsetAsync(p, 0, 64, ctx->stream));
+  unsigned g = nblk(nwords, 256);
+  if (g > XGPU_NSM * 8) g = XGPU_NSM * 8;
+  for (int i = 0; i < k; i++) {
+    k_popc_total<<<g, 256, 0, ctx->stream>>>(bits_host[i], nwords, (unsigned long long*)p + i);
+    XGPU_LAUNCH_CHECK(ctx);
+  }
+  XGPU_CUDA(ctx, xgpu_d2h_small(ctx->h_pinned, p, 8 * k, ctx->stream));   // ONE read-back and ONE host wait for all of them
+  XGPU_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  for (int i = 0; i < k; i++) counts_host[i] = ctx->h_pinned[i];
+  return XGPU_OK;
+}
+
 static int word_offsets(xgpu_ctx* ctx, const uint32_t* bits, int64_t nwords, int32_t** woff)
 {
   void* p;

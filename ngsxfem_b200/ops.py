@@ -108,6 +108,16 @@ def bitset_count(bits, nbits, ctx=None):
     return c.value
 
 
+def bitset_counts(bitsets, nbits, ctx=None):
+    """numbers of set bits of several bitsets of the same length, one host wait for all (xgpu_bitset_count_many)"""
+    ctx = ctx or default_ctx()
+    k = len(bitsets)
+    ptrs = (_lib.VP * k)(*[_lib.VP(ptr(b)) for b in bitsets])
+    cnt = (C.c_int64 * k)()
+    ctx.check(ctx.lib.xgpu_bitset_count_many(ctx.h, k, ptrs, nbits, cnt))
+    return [int(c) for c in cnt]
+
+
 def bitset_to_list(bits, nbits, ctx=None, count=None):
     ctx = ctx or default_ctx()
     if count is None:

@@ -138,8 +138,9 @@ class CutAssembly:
         if "classified" in hooks:
             hooks["classified"](dict(bits=(bn, bp, bi), cut_ratio=cr))
         has = ops.bitset_op(ops.BIT_OR, bn, bi, ne, ctx=ctx)
-        l_neg = ops.bitset_to_list(bn, ne, ctx=ctx)
-        l_if = ops.bitset_to_list(bi, ne, ctx=ctx)
+        n_neg, n_if = ops.bitset_counts([bn, bi], ne, ctx=ctx)      # one host wait for both list lengths
+        l_neg = ops.bitset_to_list(bn, ne, ctx=ctx, count=n_neg)
+        l_if = ops.bitset_to_list(bi, ne, ctx=ctx, count=n_if)
         t.mark("lists")
         order = 2 * p  # symboliccutbfi.cpp:100-118 (ID*ID present: min diff order 0)
         main = torch.cuda.current_stream(self.dev)
