@@ -110,7 +110,7 @@ class ClockSampler:
                 self.rows.append([x.strip() for x in out.strip().split(",")])
             except Exception:
                 pass
-            time.sleep(0.1)
+            time.sleep(0.02)
 
     def __enter__(self):
         self.th.start()
@@ -316,6 +316,9 @@ def run_gpu(args):
         for k, v in t.result().items():
             phases[k] = phases.get(k, 0.0) + v / nphase
     phases_max = None
+    if os.environ.get("XGPU_DUMP_PHASES"):   # diagnosis: every rank's own phase times
+        with open(os.path.join(ROOT, "gpurun_out", f"phases_rank{rank}_of{world}_{args.scaling}.json"), "w") as f_:
+            json.dump({k: round(v, 4) for k, v in phases.items()}, f_)
     if world > 1:  # the slowest rank per phase (interior ranks have two neighbours)
         keys = sorted(phases)
         pv = torch.tensor([phases[k] for k in keys], device=dev, dtype=torch.float64)
@@ -438,7 +441,7 @@ def run_gpu(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--n", type=int, default=128)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
