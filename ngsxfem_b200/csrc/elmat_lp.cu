@@ -243,17 +243,44 @@ struct CutDesc {
   int cnt;            // points
 };
 
+// rows [R0, R1) of the symmetric matrix of one element: one lane per quadrature point, the entries (a, b >= a) of these rows
+// in registers, partial matrices summed through the shared tile S in fixed order.  The full P2-tet matrix (55 entries) needs
+// ~245 registers = 8 warps per SM; two passes over the points with 27 / 28 entries each need ~150 (12+ warps per SM) and
+// recompute only the point map and the closed-form shapes (~100 of ~500 instructions per round).
+template <int ND>
+__host__ __device__ constexpr int lp_entries(int r0, int r1)
+{
+  int n = 0;
+  for (int a = r0; a < r1; a++) n += ND - a;
+  return n;
+}
+template <int ND>
+__host__ __device__ constexpr int lp_split_row()
+{
+  int r = 0;
+  while (2 * lp_entries<ND>(0, r) < ND * (ND + 1) / 2) r++;
+  return r;
+}
+
+struct CutSeg;
+struct CutDesc;
+template <int D, int P, int R0, int R1>
+__device__ __forceinline__ void cut_pass(const CutDesc& A, const CutDesc& B, const CutSeg& SA, const CutSeg& SB,
+                                         const double* ruleA, const double* ruleB, int npa, int npb, const double* Fi,
+                                         int lane, double* S, double* M, int accumulate);
+
 #define XG_CUT_EB 32  // elements per block and pass
 
-template <int D, int P>
-__global__ void __launch_bounds__(128, 2) k_elmat_cut(
+template <int D, int P, bool SPLIT>
+__global__ void __launch_bounds__(128, SPLIT ? 3 : 2) k_elmat_cut(
     int64_t n, const int32_t* __restrict__ elems, const int32_t* __restrict__ el_vtx,
     const double* __restrict__ vtx_xyz, const double* __restrict__ phi, CutSeg SA, CutSeg SB, int accumulate,
     const int32_t* __restrict__ slots, double* __restrict__ mats, int* status, unsigned long long* status_elem)
 {
   constexpr int ND = (D == 1) ? P + 1 : ((D == 2) ? 3 + 3 * (P - 1) + (P - 1) * (P - 2) / 2
                                                    : 4 + 6 * (P - 1) + 4 * ((P - 1) * (P - 2) / 2) + (P - 1) * (P - 2) * (P - 3) / 6);
-  constexpr int NSYM = ND * (ND + 1) / 2, RS = 34, MAXK = (NSYM + 31) / 32;
+  constexpr int NSYM = ND * (ND + 1) / 2, RS = 34;
+  constexpr int NTILE = SPLIT ? lp_entries<ND>(lp_split_row<ND>(), ND) > lp_entries<ND>(0, lp_split_row<ND>()) ? lp_entries<ND>(lp_split_row<ND>(), ND) : lp_entries<ND>(0, lp_split_row<ND>()) : NSYM;   // rows of the shared tile
   extern __shared__ double smem[];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const int npa = SA.np_sub, npb = SB.dt >= 0 ? SB.np_sub : 0;
@@ -262,7 +289,7 @@ __global__ void __launch_bounds__(128, 2) k_elmat_cut(
   double* geo = ruleB + 4 * ((npb + 1) & ~1);        // XG_CUT_EB x D*D inverse Jacobians
   CutDesc* desc = reinterpret_cast<CutDesc*>(geo + XG_CUT_EB * D * D);   // [2][XG_CUT_EB]
   int* next = reinterpret_cast<int*>(desc + 2 * XG_CUT_EB);   // phase-2 element counter (16 bytes reserved)
-  double* S = reinterpret_cast<double*>(desc + 2 * XG_CUT_EB) + 2 + (size_t)wib * NSYM * RS;
+  double* S = reinterpret_cast<double*>(desc + 2 * XG_CUT_EB) + 2 + (size_t)wib * NTILE * RS;
   {
     const int da = (SA.dt == XGPU_IF) ? D - 1 : D, db = (SB.dt == XGPU_IF) ? D - 1 : D;   // dimension of the sub-simplices
     for (int t = threadIdx.x; t < npa; t += blockDim.x) {
@@ -274,17 +301,6 @@ __global__ void __launch_bounds__(128, 2) k_elmat_cut(
 #pragma unroll
       for (int m = 0; m < 3; m++) ruleB[4 * t + m] = (m < db) ? SB.rs_p[3 * t + m] : 0.0;
       ruleB[4 * t + 3] = SB.rs_w[t];
-    }
-  }
-  int ki_[MAXK], kj_[MAXK];
-#pragma unroll
-  for (int m = 0; m < MAXK; m++) {
-    const int k = lane + 32 * m;
-    ki_[m] = -1; kj_[m] = 0;
-    if (k < NSYM) {
-      int r = 0, rem = k;
-      while (rem >= ND - r) { rem -= ND - r; r++; }
-      ki_[m] = r; kj_[m] = r + rem;
     }
   }
 #pragma unroll 1
@@ -354,89 +370,111 @@ __global__ void __launch_bounds__(128, 2) k_elmat_cut(
       double Fi[D * D];
 #pragma unroll
       for (int a = 0; a < D * D; a++) Fi[a] = geo[k * D * D + a];
-      double acc[NSYM];
+      double* M = mats + (size_t)(slots ? (int64_t)slots[i] : i) * ND * ND;
+      if constexpr (SPLIT) {
+        constexpr int RM = lp_split_row<ND>();
+        cut_pass<D, P, 0, RM>(A, B, SA, SB, ruleA, ruleB, npa, npb, Fi, lane, S, M, accumulate);
+        cut_pass<D, P, RM, ND>(A, B, SA, SB, ruleA, ruleB, npa, npb, Fi, lane, S, M, accumulate);
+      } else {
+        cut_pass<D, P, 0, ND>(A, B, SA, SB, ruleA, ruleB, npa, npb, Fi, lane, S, M, accumulate);
+      }
+    }
+  }
+}
+
+template <int D, int P, int R0, int R1>
+__device__ __forceinline__ void cut_pass(const CutDesc& A, const CutDesc& B, const CutSeg& SA, const CutSeg& SB,
+                                         const double* ruleA, const double* ruleB, int npa, int npb, const double* Fi,
+                                         int lane, double* S, double* M, int accumulate)
+{
+  constexpr int ND = (D == 1) ? P + 1 : ((D == 2) ? 3 + 3 * (P - 1) + (P - 1) * (P - 2) / 2
+                                                   : 4 + 6 * (P - 1) + 4 * ((P - 1) * (P - 2) / 2) + (P - 1) * (P - 2) * (P - 3) / 6);
+  constexpr int NH = lp_entries<ND>(R0, R1), RS = 34, MAXK = (NH + 31) / 32;
+  const int n0 = A.cnt, ntot = n0 + B.cnt;
+  double acc[NH];
 #pragma unroll
-      for (int a = 0; a < NSYM; a++) acc[a] = 0.0;
+  for (int a = 0; a < NH; a++) acc[a] = 0.0;
 #pragma unroll 1
-      for (int qb = 0; qb < ntot; qb += 32) {
-        const int q = qb + lane;
-        if (q < ntot) {
-          const bool second = q >= n0;
-          const CutDesc& Dd = second ? B : A;
-          const int qq = second ? q - n0 : q;
-          double xh[3], w;
-          if (Dd.ns == 0) {
-            const double* rp = second ? SB.rv_p : SA.rv_p;
-            xh[0] = rp[3 * qq]; xh[1] = rp[3 * qq + 1]; xh[2] = rp[3 * qq + 2];
-            w = (second ? SB.rv_w : SA.rv_w)[qq];
-          } else {
-            const int nps = second ? npb : npa;
-            const int s = (qq >= nps) + (qq >= 2 * nps), qi = qq - s * nps;   // <= 3 sub-simplices
-            // branch-free point map: the staged rule has zeros in the coordinates beyond the sub-simplex dimension and
-            // xg_set fills the unused vertices with finite values, so the sum over all three is the sum over sd of them
-            const double* xi = (second ? ruleB : ruleA) + 4 * qi;
-            const double x0 = xi[0], x1 = xi[1], x2 = xi[2];
-            const double ow = ((1.0 - x0) - x1) - x2;
-            const double* pp = &Dd.p[s][0][0];
+  for (int qb = 0; qb < ntot; qb += 32) {
+    const int q = qb + lane;
+    if (q < ntot) {
+      const bool second = q >= n0;
+      const CutDesc& Dd = second ? B : A;
+      const int qq = second ? q - n0 : q;
+      double xh[3], w;
+      if (Dd.ns == 0) {
+        const double* rp = second ? SB.rv_p : SA.rv_p;
+        xh[0] = rp[3 * qq]; xh[1] = rp[3 * qq + 1]; xh[2] = rp[3 * qq + 2];
+        w = (second ? SB.rv_w : SA.rv_w)[qq];
+      } else {
+        const int nps = second ? npb : npa;
+        const int s = (qq >= nps) + (qq >= 2 * nps), qi = qq - s * nps;   // <= 3 sub-simplices
+        // branch-free point map: the staged rule has zeros in the coordinates beyond the sub-simplex dimension and
+        // xg_set fills the unused vertices with finite values, so the sum over all three is the sum over sd of them
+        const double* xi = (second ? ruleB : ruleA) + 4 * qi;
+        const double x0 = xi[0], x1 = xi[1], x2 = xi[2];
+        const double ow = ((1.0 - x0) - x1) - x2;
+        const double* pp = &Dd.p[s][0][0];
 #pragma unroll
-            for (int c = 0; c < 3; c++) xh[c] = ((ow * pp[c] + x0 * pp[3 + c]) + x1 * pp[6 + c]) + x2 * pp[9 + c];
-            w = xi[3] * Dd.vol[s] * Dd.iffac;
-          }
-          const double wm = Dd.cm * w, ws = Dd.cs * w;
-          AD<D> lam[D + 1];
-          double sl = 1.0;
+        for (int c = 0; c < 3; c++) xh[c] = ((ow * pp[c] + x0 * pp[3 + c]) + x1 * pp[6 + c]) + x2 * pp[9 + c];
+        w = xi[3] * Dd.vol[s] * Dd.iffac;
+      }
+      const double wm = Dd.cm * w, ws = Dd.cs * w;
+      AD<D> lam[D + 1];
+      double sl = 1.0;
 #pragma unroll
-          for (int c = 0; c < D; c++) lam[D].d[c] = 0.0;
+      for (int c = 0; c < D; c++) lam[D].d[c] = 0.0;
 #pragma unroll
-          for (int a = 0; a < D; a++) {
-            lam[a].v = xh[a]; sl -= xh[a];
+      for (int a = 0; a < D; a++) {
+        lam[a].v = xh[a]; sl -= xh[a];
 #pragma unroll
-            for (int c = 0; c < D; c++) { lam[a].d[c] = Fi[a * D + c]; lam[D].d[c] -= Fi[a * D + c]; }
-          }
-          lam[D].v = sl;
-          double val[ND], g[D * ND];
-          lp_shapes<D, P, ND>(lam, val, g);
-          {
-            int kk = 0;
+        for (int c = 0; c < D; c++) { lam[a].d[c] = Fi[a * D + c]; lam[D].d[c] -= Fi[a * D + c]; }
+      }
+      lam[D].v = sl;
+      double val[ND], g[D * ND];
+      lp_shapes<D, P, ND>(lam, val, g);
+      {
+        int kk = 0;
 #pragma unroll
-            for (int a = 0; a < ND; a++) {
-              const double ai = wm * val[a];
+        for (int a = R0; a < R1; a++) {
+          const double ai = wm * val[a];
 #pragma unroll
-              for (int b = a; b < ND; b++) acc[kk++] += ai * val[b];
-            }
-          }
-#pragma unroll
-          for (int c = 0; c < D; c++) {
-            int kk = 0;
-#pragma unroll
-            for (int a = 0; a < ND; a++) {
-              const double ai = ws * g[c * ND + a];
-#pragma unroll
-              for (int b = a; b < ND; b++) acc[kk++] += ai * g[c * ND + b];
-            }
-          }
+          for (int b = a; b < ND; b++) acc[kk++] += ai * val[b];
         }
       }
-      __syncwarp();
 #pragma unroll
-      for (int a = 0; a < NSYM; a++) S[a * RS + lane] = acc[a];
-      __syncwarp();
-      double* M = mats + (size_t)(slots ? (int64_t)slots[i] : i) * ND * ND;
+      for (int c = 0; c < D; c++) {
+        int kk = 0;
 #pragma unroll
-      for (int m = 0; m < MAXK; m++) {
-        if (ki_[m] >= 0) {
-          const double2* row = reinterpret_cast<const double2*>(S + (lane + 32 * m) * RS);
-          double r0 = 0.0, r1 = 0.0;
+        for (int a = R0; a < R1; a++) {
+          const double ai = ws * g[c * ND + a];
 #pragma unroll
-          for (int t = 0; t < 16; t++) { const double2 x = row[t]; r0 += x.x; r1 += x.y; }
-          const double r = r0 + r1;
-          const int a = ki_[m], b = kj_[m];
-          if (accumulate) { M[a * ND + b] += r; if (a != b) M[b * ND + a] += r; }
-          else { M[a * ND + b] = r; if (a != b) M[b * ND + a] = r; }
+          for (int b = a; b < ND; b++) acc[kk++] += ai * g[c * ND + b];
         }
       }
     }
   }
+  __syncwarp();
+#pragma unroll
+  for (int a = 0; a < NH; a++) S[a * RS + lane] = acc[a];
+  __syncwarp();
+#pragma unroll
+  for (int m = 0; m < MAXK; m++) {
+    const int kk = lane + 32 * m;
+    if (kk < NH) {
+      const double2* row = reinterpret_cast<const double2*>(S + kk * RS);
+      double r0 = 0.0, r1 = 0.0;
+#pragma unroll
+      for (int t = 0; t < 16; t++) { const double2 x = row[t]; r0 += x.x; r1 += x.y; }
+      const double r = r0 + r1;
+      int a = R0, rem = kk;
+      while (rem >= ND - a) { rem -= ND - a; a++; }
+      const int b = a + rem;
+      if (accumulate) { M[a * ND + b] += r; if (a != b) M[b * ND + a] += r; }
+      else { M[a * ND + b] = r; if (a != b) M[b * ND + a] = r; }
+    }
+  }
+  __syncwarp();
 }
 
 template <int D, int P>
@@ -445,16 +483,23 @@ int launch_cut(xgpu_ctx* ctx, int64_t n, const int32_t* elems, const int32_t* el
 {
   constexpr int ND = (D == 1) ? P + 1 : ((D == 2) ? 3 + 3 * (P - 1) + (P - 1) * (P - 2) / 2 : 4 + 6 * (P - 1));
   constexpr int NSYM = ND * (ND + 1) / 2;
+  // SPLIT = two passes over the points with half of the matrix rows each (167 registers, 12 warps per SM instead of 244 / 8):
+  // measured 0.74 ms against 0.705 ms for the single pass on config 2 — more warps do not pay for the repeated point map and
+  // shapes, so it stays off (profiles/r02_notes.md)
+  constexpr bool SPLIT = false;
+  constexpr int RM = lp_split_row<ND>();
+  constexpr int NTILE = SPLIT ? (lp_entries<ND>(RM, ND) > lp_entries<ND>(0, RM) ? lp_entries<ND>(RM, ND) : lp_entries<ND>(0, RM)) : NSYM;
   const int npb = SB.dt >= 0 ? SB.np_sub : 0;
-  const size_t sm_need = sizeof(double) * (4 * ((SA.np_sub + 1) & ~1) + 4 * ((npb + 1) & ~1) + XG_CUT_EB * D * D + 2 + (size_t)4 * NSYM * 34)
-                    + 2 * XG_CUT_EB * sizeof(CutDesc);
+  const size_t sm_need = sizeof(double) * (4 * ((SA.np_sub + 1) & ~1) + 4 * ((npb + 1) & ~1) + XG_CUT_EB * D * D + 2 + (size_t)4 * NTILE * 34)
+                         + 2 * XG_CUT_EB * sizeof(CutDesc);
   size_t sm = sm_need;
   if (ctx->opt_cut_bpsm == 1 && sm < 116 * 1024) sm = 116 * 1024;   // more than half of an SM's shared memory: one block per SM
+  const int bpsm = ctx->opt_cut_bpsm == 1 ? 1 : (SPLIT ? 3 : 2);
   unsigned grid = nblk(n, XG_CUT_EB);
-  if (grid > XGPU_NSM * 2 * ctx->opt_cut_bpsm && !ctx->opt_short_blocks) grid = XGPU_NSM * 2 * ctx->opt_cut_bpsm;
-  XGPU_CUDA(ctx, cudaFuncSetAttribute(k_elmat_cut<D, P>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-  k_elmat_cut<D, P><<<grid, 128, sm, ctx->stream>>>(n, elems, el_vtx, vtx_xyz, phi, SA, SB, accumulate, slots, mats,
-                                                    ctx->d_status, ctx->d_status_elem);
+  if (grid > (unsigned)(XGPU_NSM * 2 * bpsm) && !ctx->opt_short_blocks) grid = XGPU_NSM * 2 * bpsm;
+  XGPU_CUDA(ctx, cudaFuncSetAttribute(k_elmat_cut<D, P, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+  k_elmat_cut<D, P, SPLIT><<<grid, 128, sm, ctx->stream>>>(n, elems, el_vtx, vtx_xyz, phi, SA, SB, accumulate, slots, mats,
+                                                           ctx->d_status, ctx->d_status_elem);
   XGPU_LAUNCH_CHECK(ctx);
   return XGPU_OK;
 }
