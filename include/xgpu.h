@@ -118,8 +118,10 @@ int xgpu_classify_volumes(xgpu_ctx* ctx, int64_t ne, const double* vol_neg, cons
  * op: 0 OR, 1 AND, 2 ANDNOT (a & ~b), 3 NOT a, 4 COPY a, 5 CLEAR, 6 SET (tail bits stay 0) */
 int xgpu_bitset_op(xgpu_ctx* ctx, int op, const uint32_t* a, const uint32_t* b, uint32_t* out, int64_t nbits);
 int xgpu_bitset_count(xgpu_ctx* ctx, const uint32_t* bits, int64_t nbits, int64_t* count_host);
-/* the counts of k <= 8 bitsets of the same length with ONE host wait (bits_host: host array of device pointers) */
-int xgpu_bitset_count_many(xgpu_ctx* ctx, int k, const uint32_t* const* bits_host, int64_t nbits, int64_t* counts_host);
+/* counts of k <= 8 bitsets with ONE host wait (bits_host: host array of device pointers): counts_host[i] = set bits of
+ * bitset i with index < nbits_host[i] — a prefix of a longer bitset may be counted (own elements before halo elements) */
+int xgpu_bitset_count_many(xgpu_ctx* ctx, int k, const uint32_t* const* bits_host, const int64_t* nbits_host,
+                           int64_t* counts_host);
 /* ascending list of set bits; list must hold xgpu_bitset_count entries */
 int xgpu_bitset_to_list(xgpu_ctx* ctx, const uint32_t* bits, int64_t nbits, int32_t* list);
 /* CutInformation::GetElementsWithThresholdContribution (cutinfo.cpp:263-284) */

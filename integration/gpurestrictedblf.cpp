@@ -56,7 +56,8 @@ public:
     xgpu_adapter::CheckGeometry(ctx);
     int64_t cnt[2] = {0, 0};
     const uint32_t* sets[2] = {d_neg, d_if};
-    Check(ctx, xgpu_bitset_count_many(ctx, 2, sets, ne, cnt));      // one host wait for both list lengths
+    const int64_t lens[2] = {ne, ne};
+    Check(ctx, xgpu_bitset_count_many(ctx, 2, sets, lens, cnt));    // one host wait for both list lengths
     const int64_t n_neg = cnt[0], n_if = cnt[1];
     d_lneg.Resize(n_neg); d_lif.Resize(n_if);
     Check(ctx, xgpu_bitset_to_list(ctx, d_neg, ne, d_lneg));

@@ -123,7 +123,7 @@ _SIGS = {
     "xgpu_h1_eval_rule": (C.c_int, [VP, C.c_int, C.c_int, C.c_int64, VP, VP, VP, VP, VP, VP, VP]),
     "xgpu_reduce_sum": (C.c_int, [VP, C.c_int64, VP, c_f64p]),
     "xgpu_elements_with_marked": (C.c_int, [VP, C.c_int64, C.c_int, VP, VP, VP]),
-    "xgpu_bitset_count_many": (C.c_int, [VP, C.c_int, C.POINTER(VP), C.c_int64, c_i64p]),
+    "xgpu_bitset_count_many": (C.c_int, [VP, C.c_int, C.POINTER(VP), c_i64p, c_i64p]),
     "xgpu_band_elements": (C.c_int, [VP, C.c_int, C.c_int64, VP, VP, C.c_double, C.c_double, VP]),
     "xgpu_rule_points_phys": (C.c_int, [VP, C.c_int, C.c_int, C.c_int64, VP, VP, VP, VP]),
     "xgpu_h1_grad_points": (C.c_int, [VP, C.c_int, C.c_int, C.c_int, C.c_int64, VP, VP, VP, VP, VP, VP]),

@@ -349,22 +349,44 @@ extern "C" int xgpu_bitset_count(xgpu_ctx* ctx, const uint32_t* bits, int64_t nb
   return XGPU_OK;
 }
 
-extern "C" int xgpu_bitset_count_many(xgpu_ctx* ctx, int k, const uint32_t* const* bits_host, int64_t nbits, int64_t* counts_host)
+namespace {
+// set bits with index < nbits (the last word masked: a PREFIX of a longer bitset may be counted)
+__global__ void k_popc_prefix(const uint32_t* __restrict__ bits, int64_t nbits, unsigned long long* total)
 {
-  if (!ctx || k < 1 || k > 8 || !bits_host || !counts_host) return xgpu_fail(ctx, XGPU_ERR_ARG, "xgpu_bitset_count_many: bad argument (1..8 bitsets)");
   const int64_t nwords = (nbits + 31) >> 5;
+  unsigned long long s = 0;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nwords; i += (int64_t)gridDim.x * blockDim.x) {
+    uint32_t w = bits[i];
+    if (i == nwords - 1 && (nbits & 31)) w &= (1u << (nbits & 31)) - 1u;
+    s += __popc(w);
+  }
+  for (int d = 16; d > 0; d >>= 1) s += __shfl_down_sync(0xffffffffu, s, d);
+  if ((threadIdx.x & 31) == 0 && s) atomicAdd(total, s);
+}
+}  // namespace
+
+extern "C" int xgpu_bitset_count_many(xgpu_ctx* ctx, int k, const uint32_t* const* bits_host, const int64_t* nbits_host,
+                                      int64_t* counts_host)
+{
+  if (!ctx || k < 1 || k > 8 || !bits_host || !nbits_host || !counts_host)
+    return xgpu_fail(ctx, XGPU_ERR_ARG, "xgpu_bitset_count_many: bad argument (1..8 bitsets)");
   for (int i = 0; i < k; i++) counts_host[i] = 0;
-  if (nwords == 0) return XGPU_OK;
   void* p;
   int rc = xgpu_scratch(ctx, 6, 64, &p);
   if (rc) return rc;
   XGPU_CUDA(ctx, cudaMemsetAsync(p, 0, 64, ctx->stream));
-  unsigned g = nblk(nwords, 256);
-  if (g > XGPU_NSM * 8) g = XGPU_NSM * 8;
+  bool any = false;
   for (int i = 0; i < k; i++) {
-    k_popc_total<<<g, 256, 0, ctx->stream>>>(bits_host[i], nwords, (unsigned long long*)p + i);
+    if (nbits_host[i] < 0) return xgpu_fail(ctx, XGPU_ERR_ARG, "xgpu_bitset_count_many: negative length");
+    const int64_t nwords = (nbits_host[i] + 31) >> 5;
+    if (nwords == 0) continue;
+    unsigned g = nblk(nwords, 256);
+    if (g > XGPU_NSM * 8) g = XGPU_NSM * 8;
+    k_popc_prefix<<<g, 256, 0, ctx->stream>>>(bits_host[i], nbits_host[i], (unsigned long long*)p + i);
     XGPU_LAUNCH_CHECK(ctx);
+    any = true;
   }
+  if (!any) return XGPU_OK;
   XGPU_CUDA(ctx, xgpu_d2h_small(ctx->h_pinned, p, 8 * k, ctx->stream));   // ONE read-back and ONE host wait for all of them
   XGPU_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   for (int i = 0; i < k; i++) counts_host[i] = ctx->h_pinned[i];

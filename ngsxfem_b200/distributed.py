@@ -262,12 +262,23 @@ class DistributedCutAssembly:
             self._handshake()
         mark("start")
         ne = p.el_vtx.shape[0]
-        l_neg, l_if, cls = be.classify(p.el_vtx, phi)
-        bn, bp, bi, cr = cls
-        has = ops.bitset_op(ops.BIT_OR, bn, bi, ne, ctx=ctx)
+        if type(be) is GpuBackend:
+            # classification + all four list lengths (own elements come first: prefix counts) with ONE host wait; the geometry
+            # status is checked once, inside local_assembly
+            dim = p.el_vtx.shape[1] - 1
+            cls = ops.classify(dim, p.el_vtx, phi, ctx=ctx)
+            bn, bp, bi, cr = cls
+            has = ops.bitset_op(ops.BIT_OR, bn, bi, ne, ctx=ctx)
+            n_neg, n_if, kn, ki = ops.bitset_counts([bn, bi, bn, bi], [ne, ne, p.ne_own, p.ne_own], ctx=ctx)
+            l_neg = ops.bitset_to_list(bn, ne, ctx=ctx, count=n_neg)
+            l_if = ops.bitset_to_list(bi, ne, ctx=ctx, count=n_if)
+        else:
+            l_neg, l_if, cls = be.classify(p.el_vtx, phi)
+            bn, bp, bi, cr = cls
+            has = ops.bitset_op(ops.BIT_OR, bn, bi, ne, ctx=ctx)
+            ne_own = self._ne_own.to(l_neg.dtype)
+            kn, ki = torch.stack([torch.searchsorted(l_neg, ne_own)[0], torch.searchsorted(l_if, ne_own)[0]]).tolist()
         l_has = ops.bitset_to_list(has, ne, ctx=ctx, count=l_neg.numel() + l_if.numel())
-        ne_own = self._ne_own.to(l_neg.dtype)
-        kn, ki = torch.stack([torch.searchsorted(l_neg, ne_own)[0], torch.searchsorted(l_if, ne_own)[0]]).tolist()
         l_neg_own, l_if_own, l_halo = l_neg[:kn], l_if[:ki], l_has[kn + ki:]
         mark("classify")
         a, b = p.range_of[r]

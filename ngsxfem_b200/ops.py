@@ -109,12 +109,15 @@ def bitset_count(bits, nbits, ctx=None):
 
 
 def bitset_counts(bitsets, nbits, ctx=None):
-    """numbers of set bits of several bitsets of the same length, one host wait for all (xgpu_bitset_count_many)"""
+    """numbers of set bits of several bitsets, one host wait for all (xgpu_bitset_count_many); nbits: one length for all or one
+    per bitset — bits with index >= nbits are not counted (a prefix of a longer bitset)"""
     ctx = ctx or default_ctx()
     k = len(bitsets)
+    nb = [int(nbits)] * k if not isinstance(nbits, (list, tuple)) else [int(v) for v in nbits]
     ptrs = (_lib.VP * k)(*[_lib.VP(ptr(b)) for b in bitsets])
+    nba = (C.c_int64 * k)(*nb)
     cnt = (C.c_int64 * k)()
-    ctx.check(ctx.lib.xgpu_bitset_count_many(ctx.h, k, ptrs, nbits, cnt))
+    ctx.check(ctx.lib.xgpu_bitset_count_many(ctx.h, k, ptrs, nba, cnt))
     return [int(c) for c in cnt]
 
 
