@@ -363,6 +363,12 @@ int xgpu_restrict_plan(xgpu_ctx* ctx, int nd, const int32_t* el_dofs, int nlists
                        int32_t* const* tables_host, xgpu_plan** plan_out);
 int xgpu_csr_assemble_fused(xgpu_ctx* ctx, xgpu_plan* plan, const xgpu_batch* batches_host, int nbatches,
                             const double* tref, int ncoef, int64_t* rowptr, int32_t* colidx, double* vals);
+/* the same for the rows [row_lo, row_hi) only (colidx / vals of the other rows are not touched; copy_rowptr != 0 also copies
+ * the row offsets).  An element-partitioned assembly finishes the rows it has to SEND first and lets them travel while the
+ * rows it owns are summed.  XGPU_ERR_UNSUPPORTED when the plan has rows outside the thread-per-row / warp-per-row kernels. */
+int xgpu_csr_assemble_fused_rows(xgpu_ctx* ctx, xgpu_plan* plan, const xgpu_batch* batches_host, int nbatches,
+                                 const double* tref, int ncoef, int64_t* rowptr, int32_t* colidx, double* vals,
+                                 int64_t row_lo, int64_t row_hi, int copy_rowptr);
 void xgpu_plan_destroy(xgpu_plan* plan);
 /* device time of the two halves of xgpu_csr_plan (CUDA events on the plan's stream): ms_host[0] =
  * transposed table (histogram, scan, fill, segment sort), ms_host[1] = pattern pass (bench.py) */

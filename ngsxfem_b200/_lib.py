@@ -135,6 +135,7 @@ _SIGS = {
     "xgpu_restrict_plan": (C.c_int, [VP, C.c_int, VP, C.c_int, C.POINTER(VP), c_i64p, C.c_int64, VP, c_i64p, C.POINTER(VP),
                                     C.POINTER(VP)]),
     "xgpu_csr_assemble_fused": (C.c_int, [VP, VP, C.POINTER(Batch), C.c_int, VP, C.c_int, VP, VP, VP]),
+    "xgpu_csr_assemble_fused_rows": (C.c_int, [VP, VP, C.POINTER(Batch), C.c_int, VP, C.c_int, VP, VP, VP, C.c_int64, C.c_int64, C.c_int]),
     "xgpu_affine_coefs": (C.c_int, [VP, C.c_int, C.c_int64, VP, VP, VP, C.POINTER(Term), C.c_int, VP]),
     "xgpu_reftensor": (C.c_int, [VP, C.c_int, C.c_int, C.c_int, C.POINTER(VP), c_intp]),
     "xgpu_plan_destroy": (None, [VP]),

@@ -57,13 +57,15 @@ int xg_rows_small_na(int width, int64_t ndof);
 int xg_rows_small_supports(int width, int ncoef);
 size_t xg_rows_small_record_bytes(int64_t ndof);
 int xg_rows_small_run(xgpu_ctx* ctx, xgpu_plan* P, const BatchDev& bd, const double* tref, int ncoef, bool pattern,
-                      int32_t* rowcnt, int* stats, int32_t* colidx, double* vals);
+                      int32_t* rowcnt, int* stats, int32_t* colidx, double* vals, int64_t row_lo = 0,
+                      int64_t row_hi = ((int64_t)1 << 40));   // values pass: rows [row_lo, row_hi) only
 
 // csr_rows_warp.cu: warp-per-row kernels (sorting network over the warp) for the other rows with fewer than 256 candidates
 int xg_rows_warp_ok(int width, int64_t ndof);
 size_t xg_rows_warp_record_bytes(int64_t nrows);
 int xg_rows_warp_run(xgpu_ctx* ctx, xgpu_plan* P, const BatchDev& bd, const double* tref, int ncoef, bool pattern, int small_na,
-                     unsigned int* ticket, unsigned int* slotcount, int32_t* rowcnt, int* stats, int32_t* colidx, double* vals);
+                     unsigned int* ticket, unsigned int* slotcount, int32_t* rowcnt, int* stats, int32_t* colidx, double* vals,
+                     int64_t row_lo = 0, int64_t row_hi = ((int64_t)1 << 40));
 
 // elmat.cu: is `tref` the library's own cached reference tensor of H1 order p on the dim-simplex (any integration order)?
 bool xg_reftensor_is(xgpu_ctx* ctx, const double* tref, int dim, int p);

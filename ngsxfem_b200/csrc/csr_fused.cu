@@ -507,10 +507,30 @@ static int count_rows(xgpu_ctx* ctx, xgpu_plan* P, int64_t* nnz_host)
   return XGPU_OK;
 }
 
+static int assemble_fused_rows(xgpu_ctx* ctx, xgpu_plan* P, const xgpu_batch* batches_host, int nbatches,
+                               const double* tref, int ncoef, int64_t* rowptr, int32_t* colidx, double* vals,
+                               int64_t row_lo, int64_t row_hi, bool copy_rowptr);
+
 extern "C" int xgpu_csr_assemble_fused(xgpu_ctx* ctx, xgpu_plan* P, const xgpu_batch* batches_host, int nbatches,
                                        const double* tref, int ncoef, int64_t* rowptr, int32_t* colidx, double* vals)
 {
   XGPU_NVTX(ctx, "xgpu_csr_assemble_fused");
+  return assemble_fused_rows(ctx, P, batches_host, nbatches, tref, ncoef, rowptr, colidx, vals, 0, (int64_t)1 << 40, true);
+}
+
+extern "C" int xgpu_csr_assemble_fused_rows(xgpu_ctx* ctx, xgpu_plan* P, const xgpu_batch* batches_host, int nbatches,
+                                            const double* tref, int ncoef, int64_t* rowptr, int32_t* colidx, double* vals,
+                                            int64_t row_lo, int64_t row_hi, int copy_rowptr)
+{
+  XGPU_NVTX(ctx, "xgpu_csr_assemble_fused_rows");
+  if (row_lo < 0 || row_hi < row_lo) return xgpu_fail(ctx, XGPU_ERR_ARG, "xgpu_csr_assemble_fused_rows: bad row range");
+  return assemble_fused_rows(ctx, P, batches_host, nbatches, tref, ncoef, rowptr, colidx, vals, row_lo, row_hi, copy_rowptr != 0);
+}
+
+static int assemble_fused_rows(xgpu_ctx* ctx, xgpu_plan* P, const xgpu_batch* batches_host, int nbatches,
+                               const double* tref, int ncoef, int64_t* rowptr, int32_t* colidx, double* vals,
+                               int64_t row_lo, int64_t row_hi, bool copy_rowptr)
+{
   if (!ctx || !P || !batches_host || nbatches != P->bd.nb || !rowptr)
     return xgpu_fail(ctx, XGPU_ERR_ARG, "xgpu_csr_assemble_fused: bad argument");
   if (!P->counted) return xgpu_fail(ctx, XGPU_ERR_ARG, "xgpu_csr_assemble_fused: the plan has no row counts (build it with xgpu_csr_plan_rows)");
@@ -534,8 +554,9 @@ extern "C" int xgpu_csr_assemble_fused(xgpu_ctx* ctx, xgpu_plan* P, const xgpu_b
   if (nproc && (!tref || (ncoef != 2 && ncoef != 4 && ncoef != 7)))
     return xgpu_fail(ctx, XGPU_ERR_ARG, "xgpu_csr_assemble_fused: procedural batches need the reference tensors (ncoef 2, 4 or 7)");
   cudaStream_t st = ctx->stream;
-  XGPU_CUDA(ctx, cudaMemcpyAsync(rowptr, P->rowptr, sizeof(long long) * (P->ndof + 1), cudaMemcpyDeviceToDevice, st));
+  if (copy_rowptr) XGPU_CUDA(ctx, cudaMemcpyAsync(rowptr, P->rowptr, sizeof(long long) * (P->ndof + 1), cudaMemcpyDeviceToDevice, st));
   if (P->ndof == 0 || P->nnz == 0) return XGPU_OK;
+  const bool partial = row_lo > 0 || row_hi < P->ndof;
   const bool fast_ok = xg_rows_small_supports(P->wmax, nproc ? ncoef : 0) != 0;
   F.skip_na = (P->small_na > 0 && fast_ok) ? P->small_na : 0;
   F.skip_cand = (P->warp_cand >= 0 && fast_ok) ? P->warp_cand : -1;
@@ -546,15 +567,17 @@ extern "C" int xgpu_csr_assemble_fused(xgpu_ctx* ctx, xgpu_plan* P, const xgpu_b
   const bool fork = ctx->opt_csr_fork && F.skip_cand >= 0 && F.skip_na > 0;
   if (F.skip_cand >= 0) {
     if (fork) XGPU_CUDA(ctx, xgpu_aux_begin(ctx));
-    rc = xg_rows_warp_run(ctx, P, F.bd, tref, nproc ? ncoef : 0, false, F.skip_na, (unsigned int*)sp + 1, nullptr, nullptr, nullptr, colidx, vals);
+    rc = xg_rows_warp_run(ctx, P, F.bd, tref, nproc ? ncoef : 0, false, F.skip_na, (unsigned int*)sp + 1, nullptr, nullptr, nullptr, colidx, vals,
+                          row_lo, row_hi);
     if (fork) { cudaError_t e_ = xgpu_aux_end(ctx, st); if (!rc && e_ != cudaSuccess) rc = xgpu_fail(ctx, XGPU_ERR_CUDA, cudaGetErrorString(e_)); }
     if (rc) return rc;
   }
   if (F.skip_na > 0) {
-    rc = xg_rows_small_run(ctx, P, F.bd, tref, nproc ? ncoef : 0, false, nullptr, nullptr, colidx, vals);
+    rc = xg_rows_small_run(ctx, P, F.bd, tref, nproc ? ncoef : 0, false, nullptr, nullptr, colidx, vals, row_lo, row_hi);
     if (rc) return rc;
   }
   if (P->maxcand <= F.skip_cand && !(F.skip_na > 0 && P->small_overflow)) return XGPU_OK;  // no row left for the lane-group hash kernel
+  if (partial) return xgpu_fail(ctx, XGPU_ERR_UNSUPPORTED, "xgpu_csr_assemble_fused_rows: rows of the lane-group kernel cannot be split by range (assemble all rows at once)");
   int HG = 32;
   while (HG < P->maxnr + (P->maxnr >> 1) + 1) HG <<= 1;
   F.HG = HG;

@@ -15,6 +15,7 @@
 // row by row with contiguous stores.  The same plan can be assembled again with other values (values pass only).
 // The lane-group hash kernels of csr_fused.cu spend ~200 instructions per 30 contributions on per-step bookkeeping
 // (profiles/r02_notes.md); here the bookkeeping is per 32 rows.
+#include <algorithm>
 #include "csr.cuh"
 #include "h1.cuh"
 
@@ -27,6 +28,7 @@ namespace {
 
 struct SmallPar {
   int ndof;
+  int row_lo, row_hi, d0;   // values pass: rows [row_lo, row_hi) only, thread 0 of block 0 is row d0 (multiple of 32)
   const long long* adj_ptr;
   const long long* adj;
   BatchDev bd;
@@ -211,10 +213,10 @@ __global__ void __launch_bounds__(XS_BLOCK, 4) k_rows_small_values(const SmallPa
     }
     __syncthreads();
   }
-  const long long d = (long long)blockIdx.x * XS_BLOCK + tid;
+  const long long d = (long long)P.d0 + (long long)blockIdx.x * XS_BLOCK + tid;
   long long a = 0, rowbase = 0;
   int na = 0, nr = 0;
-  if (d < P.ndof) {
+  if (d >= P.row_lo && d < P.row_hi) {
     a = __ldg(P.adj_ptr + d);
     na = (int)(__ldg(P.adj_ptr + d + 1) - a);
   }
@@ -334,7 +336,7 @@ inline unsigned nblk(int64_t n, int t) { return (unsigned)((n + t - 1) / t); }
 template <int W>
 int launch_small(xgpu_ctx* ctx, const SmallPar& S, int NC, bool pattern, bool closed_form)
 {
-  const unsigned grid = nblk(S.ndof, XS_BLOCK);
+  const unsigned grid = pattern ? nblk(S.ndof, XS_BLOCK) : nblk((int64_t)S.row_hi - S.d0, XS_BLOCK);
   cudaStream_t st = ctx->stream;
   if (pattern) {
     const size_t smem = sizeof(unsigned) * (size_t)(XS_BLOCK / 32) * (64 * XS_LS + 32 * 17);
@@ -381,12 +383,14 @@ int xg_rows_small_na(int width, int64_t ndof)
 size_t xg_rows_small_record_bytes(int64_t ndof) { return (size_t)((ndof + 31) / 32) * XS_CHUNKS * 32 * sizeof(uint4); }
 
 int xg_rows_small_run(xgpu_ctx* ctx, xgpu_plan* P, const BatchDev& bd, const double* tref, int ncoef, bool pattern,
-                      int32_t* rowcnt, int* stats, int32_t* colidx, double* vals)
+                      int32_t* rowcnt, int* stats, int32_t* colidx, double* vals, int64_t row_lo, int64_t row_hi)
 {
   // closed-form rows only when the reference tensors are the library's own P2-tet tensors (the formula is THAT basis)
   const bool cfm = !pattern && ctx->opt_csr_closed_form && tref && xg_reftensor_is(ctx, tref, 3, 2);
   SmallPar S;
   S.ndof = (int)P->ndof;
+  S.row_lo = (int)row_lo; S.row_hi = (int)std::min<int64_t>(row_hi, P->ndof); S.d0 = (int)(row_lo & ~(int64_t)31);
+  if (!pattern && S.row_hi <= S.row_lo) return XGPU_OK;
   S.adj_ptr = P->adj_ptr; S.adj = P->adj; S.bd = bd; S.tref = tref;
   S.rowptr = P->rowptr; S.rowcnt = rowcnt; S.stats = stats; S.records = (uint4*)P->pat_small; S.colidx = colidx; S.vals = vals;
   switch (P->wmax) {

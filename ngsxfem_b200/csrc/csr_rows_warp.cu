@@ -26,6 +26,7 @@ namespace {
 
 struct WarpPar {
   int ndof, small_na;
+  int row_lo, row_hi, tick0;   // values pass: rows [row_lo, row_hi) only; the ticket counter starts at row tick0 (multiple of 32)
   const long long* adj_ptr;
   const long long* adj;
   BatchDev bd;
@@ -216,9 +217,9 @@ __global__ void __launch_bounds__(XW_WARPS * 32) k_rows_warp_values(const WarpPa
   unsigned char* rs_w = sidx_w + NCAND;                                       // 256 run starts
   for (;;) {
     unsigned base = 0;
-    if (lane == 0) base = atomicAdd(P.ticket, 32u);
+    if (lane == 0) base = (unsigned)P.tick0 + atomicAdd(P.ticket, 32u);
     base = __shfl_sync(FULL, base, 0);
-    if (base >= (unsigned)P.ndof) break;
+    if (base >= (unsigned)P.row_hi) break;
     const long long dl = (long long)base + lane;
     long long al = 0, rbl = 0;
     int nal = 0, nrl = 0, sll = -1;
@@ -229,7 +230,7 @@ __global__ void __launch_bounds__(XW_WARPS * 32) k_rows_warp_values(const WarpPa
       nrl = (int)(__ldg(P.rowptr + dl + 1) - rbl);
     }
     const bool small = nal >= 1 && nal <= P.small_na;
-    const bool mine = dl < P.ndof && !small && nal * W < NCAND && nal > 0;
+    const bool mine = dl >= P.row_lo && dl < P.row_hi && !small && nal * W < NCAND && nal > 0;
     if (mine) sll = __ldg(P.bigslot + dl);
     unsigned todo = __ballot_sync(FULL, mine);
     while (todo) {
@@ -343,10 +344,13 @@ int xg_rows_warp_ok(int width, int64_t ndof)
 size_t xg_rows_warp_record_bytes(int64_t nrows) { return (size_t)nrows * XW_RECB; }
 
 int xg_rows_warp_run(xgpu_ctx* ctx, xgpu_plan* P, const BatchDev& bd, const double* tref, int ncoef, bool pattern, int small_na,
-                     unsigned int* ticket, unsigned int* slotcount, int32_t* rowcnt, int* stats, int32_t* colidx, double* vals)
+                     unsigned int* ticket, unsigned int* slotcount, int32_t* rowcnt, int* stats, int32_t* colidx, double* vals,
+                     int64_t row_lo, int64_t row_hi)
 {
   WarpPar S;
   S.ndof = (int)P->ndof; S.small_na = small_na;
+  S.row_lo = (int)row_lo; S.row_hi = (int)std::min<int64_t>(row_hi, P->ndof); S.tick0 = (int)(row_lo & ~(int64_t)31);
+  if (!pattern && S.row_hi <= S.row_lo) return XGPU_OK;
   S.adj_ptr = P->adj_ptr; S.adj = P->adj; S.bd = bd; S.tref = tref;
   S.rowptr = P->rowptr; S.rowcnt = rowcnt; S.stats = stats; S.ticket = ticket; S.colidx = colidx; S.vals = vals;
   S.slotcount = slotcount; S.slotcap = (unsigned)P->nbig_cap; S.bigslot = P->bigslot; S.records = P->pat_big;

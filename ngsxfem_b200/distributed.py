@@ -35,6 +35,8 @@ import os
 import torch
 import torch.distributed as dist
 
+from ._lib import XgpuError
+
 
 # ------------------------------------------------------------------ helpers (torch plumbing, CPU or CUDA)
 def _excl_cumsum(x):
@@ -295,26 +297,15 @@ class DistributedCutAssembly:
                 return (dofmap[:i].max().to(torch.int64) + 1).clamp(min=0)
             self._pin.copy_(torch.stack([below(a), below(b)]), non_blocking=True)
 
-        res = be.local_assembly(p, phi, l_neg_own, l_if_own, l_halo, mark, after_restrict=owned_range if self.world > 1 else None)
-        dofmap, ndof, rowptr, col, vals = res
-        if self.world > 1 and ndof > 0:
-            n_lo, n_hi = self._pin.tolist()
-        else:
-            n_lo, n_hi = 0, ndof
-        n_own = n_hi - n_lo
-        # interface bookkeeping: flags of all candidates, row lists, index messages — three launches for all neighbours
-        counts = torch.zeros(self.world, dtype=torch.int64, device=dev)
-        counts[r] = n_own
-        red = None
-        if self.world > 1:
-            red = dist.all_reduce(counts, group=self.group, async_op=True)
-        msgs, lists = [], []
-        if p.neighbors:
+        state = {}
+
+        def bookkeeping(dofmap, rowptr, vals, n_lo):
+            """interface flags, row lists, index messages of ALL neighbours (three launches), then the packed value messages"""
             flags = ops.iface_marks(has, kt["pair_elem"], kt["pair_gpos"], kt["nflags"], ctx=ctx)
             rows_all = ops.iface_rows(kt["cand_rows"], flags, dofmap, ctx=ctx)
             idx_all = ops.iface_index(kt["cand_seen"], flags[kt["nrows"]:], dofmap, n_lo, ctx=ctx)
             mark("merge_rows")
-            ib = 0
+            msgs, lists, ib = [], [], 0
             for q in p.neighbors:
                 base, nC, nD = kt["views"][q]
                 srows, rrows = rows_all[base:base + nC], rows_all[base + nC:base + nC + nD]
@@ -326,8 +317,62 @@ class DistributedCutAssembly:
                 msgs.append((q, idx_all[ib:ib + nD], torch.empty(qb - qa, dtype=torch.int64, device=dev)))
                 ib += nD
             mark("merge_pack")
-            self._exchange_all(msgs)
-            mark("merge_exchange")
+            return msgs, lists
+
+        def split_values(plan, batches, dofmap, ndof):
+            """the rows this rank SENDS (ghost dofs: the two ends of the (owner, key) numbering) are finished first and travel
+            on a side stream while the rows it owns are summed; the received values are added afterwards"""
+            n_lo, n_hi = self._pin.tolist()      # completed by the count pass's host wait
+            main = torch.cuda.current_stream(dev)
+            try:
+                out = ops.csr_assemble_fused(plan, batches, rows=(0, n_lo))
+                ops.csr_assemble_fused(plan, batches, rows=(n_hi, ndof), out=out)
+            except XgpuError:                     # rows outside the thread- / warp-per-row kernels: one pass, exchange after it
+                out = ops.csr_assemble_fused(plan, batches)
+                state["late"] = True
+                return out
+            rowptr, col, vals = out
+            mark("csr_rows_ghost")
+            msgs, lists = bookkeeping(dofmap, rowptr, vals, n_lo)
+            if not hasattr(self, "_xstream"):
+                self._xstream = torch.cuda.Stream(dev)
+            xs = self._xstream
+            xs.wait_stream(main)
+            with torch.cuda.stream(xs):
+                for _, s_t, r_t in msgs:
+                    s_t.record_stream(xs); r_t.record_stream(xs)
+                self._exchange_all(msgs)
+            ops.csr_assemble_fused(plan, batches, rows=(n_lo, n_hi), out=out)
+            state.update(msgs=msgs, lists=lists, xs=xs)
+            return out
+
+        # opt-in (XGPU_OVERLAP=1): measured at N = 2 the device-resident step is the same within noise (strong 3.91 vs 3.93 ms,
+        # the wait moves into the numbering phase) and the pipelined e2e leg loses 2x (side-stream blocks are not reusable by
+        # the caching allocator until the exchange ends); profiles/r02_notes.md
+        overlap = self.world > 1 and bool(p.neighbors) and type(be) is GpuBackend and os.environ.get("XGPU_OVERLAP", "0") == "1"
+        res = be.local_assembly(p, phi, l_neg_own, l_if_own, l_halo, mark, after_restrict=owned_range if self.world > 1 else None,
+                                values=split_values if overlap else None)
+        dofmap, ndof, rowptr, col, vals = res
+        if self.world > 1 and ndof > 0:
+            n_lo, n_hi = self._pin.tolist()
+        else:
+            n_lo, n_hi = 0, ndof
+        n_own = n_hi - n_lo
+        counts = torch.zeros(self.world, dtype=torch.int64, device=dev)
+        counts[r] = n_own
+        red = None
+        if self.world > 1:
+            red = dist.all_reduce(counts, group=self.group, async_op=True)
+        msgs, lists = [], []
+        if p.neighbors:
+            if "msgs" in state:                                            # the exchange has been running under the own rows
+                msgs, lists = state["msgs"], state["lists"]
+                torch.cuda.current_stream(dev).wait_stream(state["xs"])
+                mark("merge_exchange")
+            else:
+                msgs, lists = bookkeeping(dofmap, rowptr, vals, n_lo)
+                self._exchange_all(msgs)
+                mark("merge_exchange")
             for k, q in enumerate(p.neighbors):                           # neighbours ascending: lower rank first
                 rrows, roff = lists[k]
                 ops.rows_add(rowptr, rrows, roff, msgs[2 * k][2], vals, ctx=ctx)
@@ -532,7 +577,7 @@ class GpuBackend:
         self.ops = ops
         self.ctx = ctx or ops.default_ctx()
 
-    def local_assembly(self, part, phi, l_neg, l_if, l_halo, mark=lambda name: None, after_restrict=None):
+    def local_assembly(self, part, phi, l_neg, l_if, l_halo, mark=lambda name: None, after_restrict=None, values=None):
         """the single-GPU sequence of pipeline.CutAssembly._step over the rank's own batches + the halo batch (sparsity
         only): Restrict + dof rows + transposed table in one sequence (xgpu_restrict_plan), the cut-element branch (cut
         quadrature + cut element matrices) on the side stream, count pass, 7 coefficients per uncut element, one row pass.
@@ -576,7 +621,11 @@ class GpuBackend:
         ctx2.raise_on_geometry_error()
         mark("elmat")
         mats = [m_neg, m_if, None]
-        rowptr, col, vals = ops.csr_assemble_fused(plan, [(tabs[k], mats[i]) for k, i in enumerate(keep)])
+        batches = [(tabs[k], mats[i]) for k, i in enumerate(keep)]
+        if values is None:
+            rowptr, col, vals = ops.csr_assemble_fused(plan, batches)
+        else:   # the caller splits the values pass (rows to send first, exchange under the rows it owns)
+            rowptr, col, vals = values(plan, batches, dofmap, ndof)
         mark("csr_rows_fused")
         return dofmap, ndof, rowptr, col, vals
 

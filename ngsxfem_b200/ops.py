@@ -733,18 +733,26 @@ def restrict_plan(el_dofs, lists, ndof_full, ctx=None):
     return dofmap[:ndof_full], ndof.value, tables, CsrPlan(ctx, h, 0, ndof.value, n)
 
 
-def csr_assemble_fused(plan, batches):
+def csr_assemble_fused(plan, batches, rows=None, out=None):
     """ONE visit per row (xgpu_csr_assemble_fused): pattern + values, `AffineCoefs` in place of the matrices = procedural
-    batch.  plan: csr_plan_rows.  returns rowptr, col, vals"""
+    batch.  plan: csr_plan_rows.  returns rowptr, col, vals.
+    rows=(lo, hi): only these rows are finished (xgpu_csr_assemble_fused_rows) into out=(rowptr, col, vals) of a previous
+    call (None: fresh arrays; the row offsets are copied by the call that allocates)"""
     ctx = plan.ctx
     dev = batches[0][0].device
     arr = _batches(batches)
     proc = [m for _, m in batches if isinstance(m, AffineCoefs)]
     tref, nc = (proc[0].tref_ptr, proc[0].ncoef) if proc else (None, 0)
-    rowptr = torch.empty(plan.ndof + 1, dtype=torch.int64, device=dev)
-    col = torch.empty(plan.nnz, dtype=torch.int32, device=dev)
-    vals = torch.empty(plan.nnz, dtype=torch.float64, device=dev)
-    ctx.check(ctx.lib.xgpu_csr_assemble_fused(ctx.h, plan.h, arr, len(batches), tref, nc, ptr(rowptr), ptr(col), ptr(vals)))
+    fresh = out is None
+    if fresh:
+        out = (torch.empty(plan.ndof + 1, dtype=torch.int64, device=dev), torch.empty(plan.nnz, dtype=torch.int32, device=dev),
+               torch.empty(plan.nnz, dtype=torch.float64, device=dev))
+    rowptr, col, vals = out
+    if rows is None:
+        ctx.check(ctx.lib.xgpu_csr_assemble_fused(ctx.h, plan.h, arr, len(batches), tref, nc, ptr(rowptr), ptr(col), ptr(vals)))
+    else:
+        ctx.check(ctx.lib.xgpu_csr_assemble_fused_rows(ctx.h, plan.h, arr, len(batches), tref, nc, ptr(rowptr), ptr(col), ptr(vals),
+                                                       int(rows[0]), int(rows[1]), int(fresh)))
     return rowptr, col, vals
 
 

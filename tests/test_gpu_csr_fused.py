@@ -172,3 +172,36 @@ def test_restrict_plan_equals_the_separate_calls(n, p):
     e = torch.empty(0, dtype=torch.int32, device=DEV)
     _, nd3, (v_a, v_e), plan3 = ops.restrict_plan(V.el_dofs, [l_a, e], V.ndof)
     assert v_e.shape == (0, nd) and nd3 <= ndof
+
+
+@pytest.mark.parametrize("n,p,proc", [(6, 2, True), (6, 2, False), (7, 1, False)])
+def test_row_ranges_assemble_to_the_same_bits(n, p, proc):
+    """xgpu_csr_assemble_fused_rows: three row ranges finished in any order into the same arrays = one call over all rows
+    (the element-partitioned assembly finishes the rows it sends first); an empty range and a range past the end are no-ops"""
+    mesh = xf.MakeStructured3DMesh(nx=n, device=DEV)
+    V = xf.H1(mesh, order=p)
+    rng = np.random.default_rng(n + p)
+    elems = torch.from_numpy(np.flatnonzero(rng.random(mesh.ne) < 0.7).astype(np.int32)).to(DEV)
+    dofmap, ndof, (table,), plan = ops.restrict_plan(V.el_dofs, [elems], V.ndof)
+    ops.csr_count_rows(plan)
+    if proc:
+        m = ops.affine_coefs(3, p, elems, mesh.elements, mesh.points, 2 * p, [(ops.OP_GRAD, ops.OP_GRAD, 1.0, 0), (ops.OP_ID, ops.OP_ID, 1.0, 0)])
+    else:
+        nd = V.el_dofs.shape[1]
+        m = torch.from_numpy(rng.standard_normal((elems.numel(), nd, nd))).to(DEV)
+    batches = [(table, m)]
+    rp, c, v = ops.csr_assemble_fused(plan, batches)
+    a, b = ndof // 3 + 5, 2 * ndof // 3 - 7          # not multiples of 32
+    out = ops.csr_assemble_fused(plan, batches, rows=(b, ndof))
+    assert torch.equal(out[0], rp)
+    lo, hi = int(rp[b]), int(rp[ndof])
+    assert torch.equal(out[1][lo:hi], c[lo:hi]) and torch.equal(out[2][lo:hi], v[lo:hi])
+    out[2][:lo] = float("nan")                         # rows outside the range must not be read or written
+    ops.csr_assemble_fused(plan, batches, rows=(0, a), out=out)
+    assert torch.isnan(out[2][int(rp[a]):lo]).all()
+    ops.csr_assemble_fused(plan, batches, rows=(a, a), out=out)
+    ops.csr_assemble_fused(plan, batches, rows=(a, b), out=out)
+    ops.csr_assemble_fused(plan, batches, rows=(ndof, ndof + 100), out=out)
+    assert torch.equal(out[1], c) and torch.equal(out[2], v)
+    with pytest.raises(XgpuError):
+        ops.csr_assemble_fused(plan, batches, rows=(5, 2), out=out)
