@@ -295,6 +295,12 @@ int xgpu_facetpatch(xgpu_ctx* ctx, int dim, int fe_order, int64_t n, const int32
                     const int32_t* facet_els, const int32_t* el_vtx, const double* vtx_xyz,
                     int order, double coef, int hpow, double* mats);
 
+/* dFacetPatch(downscale = s): SymbolicFacetPatchBilinearFormIntegrator::SetIRScaling (xfem/python_xfem.cpp:966-967).  State
+ * of the context read by xgpu_facetpatch / xgpu_facetpatch_st: the volume rule of each element of the patch is scaled by s
+ * towards the midpoint of the common facet and its weights by s^2 (ScaleAndMapIntegrationRule, xfem/symboliccutbfi.cpp:
+ * 1849-1885, applied at :2019-2029).  XGPU_ERR_ARG unless 0 < s <= 1 (:2031-2033).  Default 1. */
+int xgpu_facetpatch_set_downscale(xgpu_ctx* ctx, double s);
+
 /* space-time ghost penalty: SymbolicFacetPatchBilinearFormIntegrator with time_order >= 0 (tensor-product rule in time,
  * xfem/symboliccutbfi.cpp:2095-2160) or a fixed reference time (time_order < 0: tref, :2162-2177) on a SpaceTimeFE.  On an
  * undeformed mesh the patch map does not depend on time (:2038-2040), so the matrix is (time matrix) kron (spatial patch

@@ -111,6 +111,7 @@ _SIGS = {
     "xgpu_elvec_st": (C.c_int, [VP, C.c_int, C.c_int, C.c_int, C.c_int64, VP, VP, VP, VP, VP, VP, VP, C.POINTER(StLTerm),
                                 C.c_int, C.c_int, VP, VP]),
     "xgpu_facetpatch": (C.c_int, [VP, C.c_int, C.c_int, C.c_int64, VP, VP, VP, VP, C.c_int, C.c_double, C.c_int, VP]),
+    "xgpu_facetpatch_set_downscale": (C.c_int, [VP, C.c_double]),
     "xgpu_facetpatch_st": (C.c_int, [VP, C.c_int, C.c_int, C.c_int, C.c_int64, VP, VP, VP, VP, C.c_int, C.c_int, C.c_double,
                                      C.c_double, C.c_int, VP]),
     "xgpu_csr_plan": (C.c_int, [VP, C.c_int64, C.POINTER(Batch), C.c_int, C.POINTER(VP), c_i64p]),

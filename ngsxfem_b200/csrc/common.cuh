@@ -58,6 +58,7 @@ struct xgpu_ctx {
   int opt_csr_fork = 1;   // one-pass CSR: the warp-per-row kernel runs on an internal second stream next to the thread-per-row one
   cudaStream_t aux_stream = nullptr;  // created on first use (same priority as `stream` at that time)
   cudaEvent_t aux_fork = nullptr, aux_join = nullptr;
+  double fp_downscale = 1.0;  // dFacetPatch(downscale=): xgpu_facetpatch_set_downscale
   int opt_st_tp = 1;  // space-time element matrices: tensor-structured kernel where instantiated (0: always the generic one)
   int64_t epoch = 0;  // bumped whenever a plan takes over the shared pattern scratch (slot 8)
   int64_t* h_pinned = nullptr;  // 16 x int64 pinned staging for host scalars

@@ -42,11 +42,21 @@ extern "C" int xgpu_facetpatch(xgpu_ctx* ctx, int dim, int fe_order, int64_t n, 
   {                                                                                                                 \
     XGPU_CUDA(ctx, cudaFuncSetAttribute(k_facetpatch<DD, DF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm)); \
     k_facetpatch<DD, DF><<<grid, 128, sm, ctx->stream>>>(n, facets, facet_els, el_vtx, vtx_xyz, r->d_pts, r->d_wts, r->n, \
-                                                         fe_order, nd, CH, coef, hpow, mats, df);                   \
+                                                         fe_order, nd, CH, coef, hpow, ctx->fp_downscale, mats, df);                   \
   }
   if (df.order > 0) { if (dim == 3) XG_FP(3, true) else XG_FP(2, true) }
   else if (dim == 3) XG_FP(3, false) else if (dim == 2) XG_FP(2, false) else XG_FP(1, false)
 #undef XG_FP
   XGPU_LAUNCH_CHECK(ctx);
+  return XGPU_OK;
+}
+
+// SymbolicFacetPatchBilinearFormIntegrator::SetIRScaling (xfem/python_xfem.cpp:966-967, symboliccutbfi.cpp:2020-2033): state
+// of the context, read by xgpu_facetpatch / xgpu_facetpatch_st; only 0 < s <= 1 is valid
+extern "C" int xgpu_facetpatch_set_downscale(xgpu_ctx* ctx, double s)
+{
+  if (!ctx) return XGPU_ERR_ARG;
+  if (!(s > 0.0 && s <= 1.0)) return xgpu_fail(ctx, XGPU_ERR_ARG, "xgpu_facetpatch_set_downscale: only 0 < downscale <= 1 valid");
+  ctx->fp_downscale = s;
   return XGPU_OK;
 }

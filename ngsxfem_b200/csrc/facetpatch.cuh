@@ -64,6 +64,34 @@ __device__ __forceinline__ void map_inv(const double (*vx)[3], const double* Fi,
   for (int i = D; i < 3; i++) xh[i] = 0.0;
 }
 
+// dFacetPatch(downscale = s), ScaleAndMapIntegrationRule (symboliccutbfi.cpp:1849-1885): the volume rule of an element is
+// scaled by s towards the centre of the common facet, xhat <- s xhat + (1 - s) c_facet, and the weight by s^2 (the
+// reference's factor in every dimension).  c_facet = mean of the reference vertices of the facet = of the vertices of `v`
+// that `vo` has too; reference vertex k < D is e_k, vertex D the origin.  s = 1: shift 0, bit-identical points.
+template <int D>
+__device__ __forceinline__ void fp_shift(const int* v, const int* vo, double s, double* sh)
+{
+#pragma unroll
+  for (int k = 0; k < 3; k++) sh[k] = 0.0;
+  if (s == 1.0) return;
+#pragma unroll
+  for (int k = 0; k < D; k++) {
+    bool shared = false;
+#pragma unroll
+    for (int j = 0; j < D + 1; j++) shared |= (v[k] == vo[j]);
+    if (shared) sh[k] = (1.0 - s) / D;
+  }
+}
+
+template <int D>
+__device__ __forceinline__ void fp_point(const double* __restrict__ rp, const double* __restrict__ rw, int q, double s,
+                                         const double* sh, double* x, double* w)
+{
+#pragma unroll
+  for (int c = 0; c < 3; c++) x[c] = (c < D) ? s * rp[3 * q + c] + sh[c] : rp[3 * q + c];
+  *w = rw[q] * s * s;
+}
+
 // x(xhat) and F(xhat) of a (deformed) element: affine part from the vertices + deformation
 template <int D>
 __device__ __forceinline__ void trafo_eval(const double (*vx)[3], const double* Faff, const int* v, int def_order,
@@ -160,7 +188,8 @@ template <int D>
 __device__ __forceinline__ void fp_map_points(int lane, int np, const double* __restrict__ rp, const double* __restrict__ rw,
                                               const double (*vx1)[3], const double* F1, const int* v1, const double* defs1,
                                               const double (*vx2)[3], const double* F2, const int* v2, const double* defs2,
-                                              int def_order, double coef, int hpow, double* pcs, double* mp)
+                                              int def_order, double coef, int hpow, double scale, const double* sh1,
+                                              const double* sh2, double* pcs, double* mp)
 {
   if (lane == 0) patch_consts<D>(vx2, F2, v2, defs2, def_order, pcs);
   if (lane == 1) patch_consts<D>(vx1, F1, v1, defs1, def_order, pcs + 16);
@@ -168,13 +197,12 @@ __device__ __forceinline__ void fp_map_points(int lane, int np, const double* __
   for (int l = lane; l < 2 * np; l += 32) {
     double x1[3], x2[3], x[3], w1, wd;
     if (l < np) {
-      x1[0] = rp[3 * l]; x1[1] = rp[3 * l + 1]; x1[2] = rp[3 * l + 2];
-      w1 = rw[l];
+      fp_point<D>(rp, rw, l, scale, sh1, x1, &w1);
       map_patch_def<D>(vx1, F1, v1, defs1, vx2, F2, v2, defs2, def_order, pcs, x1, w1, x2, &wd);
     } else {
-      const int q = l - np;
-      x2[0] = rp[3 * q]; x2[1] = rp[3 * q + 1]; x2[2] = rp[3 * q + 2];
-      map_patch_def<D>(vx2, F2, v2, defs2, vx1, F1, v1, defs1, def_order, pcs + 16, x2, rw[q], x1, &w1);
+      double w2;
+      fp_point<D>(rp, rw, l - np, scale, sh2, x2, &w2);
+      map_patch_def<D>(vx2, F2, v2, defs2, vx1, F1, v1, defs1, def_order, pcs + 16, x2, w2, x1, &w1);
     }
     double Fq[D * D], Fiq[D * D];
     trafo_eval<D>(vx1, F1, v1, def_order, defs1, x1, Fq, x);
@@ -196,7 +224,7 @@ __global__ void __launch_bounds__(128) k_facetpatch(
     int64_t n, const int32_t* __restrict__ facets, const int32_t* __restrict__ facet_els,
     const int32_t* __restrict__ el_vtx, const double* __restrict__ vtx_xyz,
     const double* __restrict__ rp, const double* __restrict__ rw, int np,
-    int p, int nd, int CH, double coef, int hpow, double* __restrict__ mats, DefDev df)
+    int p, int nd, int CH, double coef, int hpow, double scale, double* __restrict__ mats, DefDev df)
 {
   extern __shared__ double smem[];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
@@ -223,12 +251,15 @@ __global__ void __launch_bounds__(128) k_facetpatch(
     double vx1[D + 1][3], vx2[D + 1][3], F1[D * D], Fi1[D * D], F2[D * D], Fi2[D * D], meas1, meas2;
     load_geom<D>(el_vtx, vtx_xyz, e1, v1, vx1, F1, Fi1, &meas1);
     load_geom<D>(el_vtx, vtx_xyz, e2, v2, vx2, F2, Fi2, &meas2);
+    double sh1[3], sh2[3];
+    fp_shift<D>(v1, v2, scale, sh1);
+    fp_shift<D>(v2, v1, scale, sh2);
     if (DEF) {
       __syncwarp();
       xg_def_gather<D>(df, e1, lane, defs1);
       xg_def_gather<D>(df, e2, lane, defs2);
       __syncwarp();
-      fp_map_points<D>(lane, np, rp, rw, vx1, F1, v1, defs1, vx2, F2, v2, defs2, df.order, coef, hpow, pcs, mp);
+      fp_map_points<D>(lane, np, rp, rw, vx1, F1, v1, defs1, vx2, F2, v2, defs2, df.order, coef, hpow, scale, sh1, sh2, pcs, mp);
     }
     const double h = (D == 1) ? meas1 : ((D == 2) ? sqrt(meas1) : cbrt(meas1));
     double hp = 1.0;
@@ -250,16 +281,15 @@ __global__ void __launch_bounds__(128) k_facetpatch(
             x1[0] = m[0]; x1[1] = m[1]; x1[2] = m[2]; x2[0] = m[3]; x2[1] = m[4]; x2[2] = m[5];
             w = m[6]; cwq = 1.0;
           } else if (l < np) {
-            x1[0] = rp[3 * l]; x1[1] = rp[3 * l + 1]; x1[2] = rp[3 * l + 2];
+            fp_point<D>(rp, rw, l, scale, sh1, x1, &w);
             map_fwd<D>(vx1, x1, x);
             map_inv<D>(vx2, Fi2, x, x2);
-            w = rw[l] * meas1;
+            w = w * meas1;
           } else {
-            const int q = l - np;
-            x2[0] = rp[3 * q]; x2[1] = rp[3 * q + 1]; x2[2] = rp[3 * q + 2];
+            fp_point<D>(rp, rw, l - np, scale, sh2, x2, &w);
             map_fwd<D>(vx2, x2, x);
             map_inv<D>(vx1, Fi1, x, x1);
-            w = rw[q] * meas2;
+            w = w * meas2;
           }
           for (int i = N; i < Np; i++) B[i] = 0.0;
           ValSink s1{B, 1.0}, s2{B + nd, -1.0};
@@ -326,7 +356,7 @@ __global__ void __launch_bounds__(128) k_facetpatch_dmma(
     int64_t n, const int32_t* __restrict__ facets, const int32_t* __restrict__ facet_els,
     const int32_t* __restrict__ el_vtx, const double* __restrict__ vtx_xyz,
     const double* __restrict__ rp, const double* __restrict__ rw, int np,
-    int CH, double coef, int hpow, double* __restrict__ mats, DefDev df)
+    int CH, double coef, int hpow, double scale, double* __restrict__ mats, DefDev df)
 {
   using G = FpGeom<D, P>;
   constexpr int ND = G::ND, N = G::N, NT = G::NT, NDP = G::NDP, PS = G::PS, NPAIR = G::NPAIR;
@@ -353,12 +383,15 @@ __global__ void __launch_bounds__(128) k_facetpatch_dmma(
     double vx1[D + 1][3], vx2[D + 1][3], F1[D * D], Fi1[D * D], F2[D * D], Fi2[D * D], meas1, meas2;
     load_geom<D>(el_vtx, vtx_xyz, e1, v1, vx1, F1, Fi1, &meas1);
     load_geom<D>(el_vtx, vtx_xyz, e2, v2, vx2, F2, Fi2, &meas2);
+    double sh1[3], sh2[3];
+    fp_shift<D>(v1, v2, scale, sh1);
+    fp_shift<D>(v2, v1, scale, sh2);
     if (DEF) {
       __syncwarp();
       xg_def_gather<D>(df, e1, lane, defs1);
       xg_def_gather<D>(df, e2, lane, defs2);
       __syncwarp();
-      fp_map_points<D>(lane, np, rp, rw, vx1, F1, v1, defs1, vx2, F2, v2, defs2, df.order, coef, hpow, pcs, mp);
+      fp_map_points<D>(lane, np, rp, rw, vx1, F1, v1, defs1, vx2, F2, v2, defs2, df.order, coef, hpow, scale, sh1, sh2, pcs, mp);
     }
     const double h = xg_mesh_size<D>(meas1);
     double hp = 1.0;
@@ -381,16 +414,15 @@ __global__ void __launch_bounds__(128) k_facetpatch_dmma(
             x1[0] = m[0]; x1[1] = m[1]; x1[2] = m[2]; x2[0] = m[3]; x2[1] = m[4]; x2[2] = m[5];
             w = m[6];
           } else if (l < np) {
-            x1[0] = rp[3 * l]; x1[1] = rp[3 * l + 1]; x1[2] = rp[3 * l + 2];
+            fp_point<D>(rp, rw, l, scale, sh1, x1, &w);
             map_fwd<D>(vx1, x1, x);
             map_inv<D>(vx2, Fi2, x, x2);
-            w = coef * hp * (rw[l] * meas1);
+            w = coef * hp * (w * meas1);
           } else {
-            const int q = l - np;
-            x2[0] = rp[3 * q]; x2[1] = rp[3 * q + 1]; x2[2] = rp[3 * q + 2];
+            fp_point<D>(rp, rw, l - np, scale, sh2, x2, &w);
             map_fwd<D>(vx2, x2, x);
             map_inv<D>(vx1, Fi1, x, x1);
-            w = coef * hp * (rw[q] * meas2);
+            w = coef * hp * (w * meas2);
           }
 #pragma unroll
           for (int i = N; i < NDP; i++) B[i] = 0.0;
@@ -450,11 +482,11 @@ int launch_fp_dmma(xgpu_ctx* ctx, int64_t n, const int32_t* facets, const int32_
   if (df.order > 0) {
     XGPU_CUDA(ctx, cudaFuncSetAttribute(k_facetpatch_dmma<D, P, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
     k_facetpatch_dmma<D, P, true><<<grid, 128, sm, ctx->stream>>>(n, facets, facet_els, el_vtx, vtx_xyz, r->d_pts, r->d_wts, r->n,
-                                                                  CH, coef, hpow, mats, df);
+                                                                  CH, coef, hpow, ctx->fp_downscale, mats, df);
   } else {
     XGPU_CUDA(ctx, cudaFuncSetAttribute(k_facetpatch_dmma<D, P, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
     k_facetpatch_dmma<D, P, false><<<grid, 128, sm, ctx->stream>>>(n, facets, facet_els, el_vtx, vtx_xyz, r->d_pts, r->d_wts, r->n,
-                                                                   CH, coef, hpow, mats, df);
+                                                                   CH, coef, hpow, ctx->fp_downscale, mats, df);
   }
   XGPU_LAUNCH_CHECK(ctx);
   return XGPU_OK;

@@ -491,8 +491,8 @@ def dCut(levelset, domain_type, order=None, subdivlvl=None, time_order=-1, level
                             "(the codim-2 IF case and deformed facets are not on the accelerated path)")
         if definedonelements is None:
             raise XgpuError("dCut(skeleton / element_boundary) needs definedonelements (facets / elements)")
-    if vb == 1 and (deformation is not None or isinstance(levelset, (list, tuple)) or int(domain_type) == IF):
-        raise XgpuError("dCut(vb=BND): single level set, NEG / POS, no deformation (tests/pytests/test_bndcut.py)")
+    if vb == 1 and (deformation is not None or isinstance(levelset, (list, tuple))):
+        raise XgpuError("dCut(vb=BND): single level set, no deformation (tests/pytests/test_bndcut.py)")
     if kwargs:
         raise XgpuError(f"unsupported dCut arguments: {sorted(kwargs)}")
     if time_order >= 0 or tref is not None:
@@ -504,23 +504,25 @@ def dCut(levelset, domain_type, order=None, subdivlvl=None, time_order=-1, level
 
 
 class FacetPatchDifferentialSymbol:
-    def __init__(self, definedonelements, order, deformation=None, time_order=-1, tref=None):
+    def __init__(self, definedonelements, order, deformation=None, time_order=-1, tref=None, downscale=None):
         self.definedonelements, self.order, self.deformation = definedonelements, order, deformation
-        self.time_order, self.tref = time_order, tref
+        self.time_order, self.tref, self.downscale = time_order, tref, downscale
 
 
 def dFacetPatch(definedonelements=None, deformation=None, time_order=-1, tref=None, downscale=None,
                 bonus_intorder=0, **kwargs):
-    """python/__init__.py:749-778; bonus_intorder is accepted and ignored as in the reference"""
-    if downscale not in (None, 1, 1.0):
-        raise XgpuError("dFacetPatch: downscale is not on the accelerated path yet")
+    """python/__init__.py:749-778; bonus_intorder is accepted and ignored as in the reference.  downscale: the patch rule
+    of each element is scaled towards the common facet (SetIRScaling, symboliccutbfi.cpp:1849-1885, :2019-2033)"""
+    if downscale is not None and not (0.0 < float(downscale) <= 1.0):
+        raise XgpuError("SymbolicFacetPatchBFI: Only 0 < downscale <= 1 valid")
     if kwargs:
         raise XgpuError(f"unsupported dFacetPatch arguments: {sorted(kwargs)}")
     if definedonelements is None:
         raise XgpuError("dFacetPatch needs definedonelements (a BitArray over the facets)")
     if (time_order >= 0 or tref is not None) and deformation is not None:
         raise XgpuError("space-time dFacetPatch does not support a mesh deformation")
-    return FacetPatchDifferentialSymbol(definedonelements, -1, deformation, time_order=int(time_order), tref=tref)
+    return FacetPatchDifferentialSymbol(definedonelements, -1, deformation, time_order=int(time_order), tref=tref,
+                                        downscale=None if downscale is None else float(downscale))
 
 
 class Integral:
@@ -876,7 +878,8 @@ class BilinearForm:
             key = id(integ.dx.definedonelements)
             for (_, _, c, hp) in terms:
                 with ctx.deformation(_eff_def(integ.dx.deformation, mesh)):
-                    mm = ops.facetpatch(dim, p, l_f, fe, mesh.elements, mesh.points, integ.dx.order, c, hp, ctx=ctx)
+                    mm = ops.facetpatch(dim, p, l_f, fe, mesh.elements, mesh.points, integ.dx.order, c, hp,
+                                        downscale=integ.dx.downscale, ctx=ctx)
                 if key in facet_mats:
                     facet_mats[key] = (l_f, facet_mats[key][1] + mm)
                 else:
@@ -912,6 +915,24 @@ class BilinearForm:
         return self
 
 
+def _bnd_cutquad(mesh, bv, phi, dt, order, ctx):
+    """cut rules of the boundary elements bv ((dim-1)-simplices) in their own reference coordinates.  dt = IF on the boundary
+    segments of a 2D mesh is the codim-2 case of cutint/straightcutrule.cpp:646-656: the rule is the cut POINT with the
+    weight w / |segment| (point measure: measure * weight = w).  The segment goes to the 1D interface rule with its arclength
+    as coordinate, whose factor ||F^{-T} n_ref|| (:558-578) is exactly 1 / |segment|."""
+    dim = mesh.dim
+    if int(dt) != IF:
+        return ops.cutquad(dim - 1, None, bv, mesh.points, phi, int(dt), order, ctx=ctx)
+    if dim != 2:
+        raise XgpuError("dCut(IF, vb=BND): boundary segments of 2D meshes only (codim-2 point measure, straightcutrule.cpp:646-656)")
+    nb, dev = bv.shape[0], bv.device
+    P = mesh.points
+    length = (P[bv[:, 0].long()] - P[bv[:, 1].long()]).norm(dim=1)
+    seg = torch.arange(2 * nb, dtype=torch.int32, device=dev).reshape(nb, 2)
+    xs = torch.stack([length, torch.zeros_like(length)], dim=1).reshape(-1, 1).contiguous()   # vertex 0 <-> xi = 1
+    return ops.cutquad(1, None, seg, xs, phi[bv.long()].reshape(-1).contiguous(), IF, order, ctx=ctx)
+
+
 def _bnd_rule_in_volume(mesh, phi, dt, order, ctx, facet_mask=None):
     """dCut(lset, dt, vb=BND): the cut rule of every boundary facet (a (dim-1)-simplex, cutint/straightcutrule.cpp on
     the BND element) carried into the reference coordinates of the adjacent volume element, so that the volume
@@ -926,7 +947,7 @@ def _bnd_rule_in_volume(mesh, phi, dt, order, ctx, facet_mask=None):
     if facet_mask is not None:
         sel = facet_mask.indices()
         bv, vol = bv[sel.long()].contiguous(), vol[sel.long()].contiguous()
-    off, q, w = ops.cutquad(dim - 1, None, bv, mesh.points, phi, dt, order, ctx=ctx)
+    off, q, w = _bnd_cutquad(mesh, bv, phi, dt, order, ctx)
     ctx.raise_on_geometry_error()
     nb = bv.shape[0]
     b_of_pt = torch.repeat_interleave(torch.arange(nb, device=bv.device), off[1:] - off[:-1])
@@ -1133,12 +1154,15 @@ def Integrate(levelset_domain=None, mesh=None, cf=1.0, order=5, time_order=-1, d
     ctx = default_ctx(mesh.device.index)
     ls, dt = ld["levelset"], ld["domain_type"]
     if ld.get("vb", 0) == 1:  # BND: dCut(lset, dt, vb=BND) of tests/pytests/test_bndcut.py — boundary facets as elements
-        if isinstance(ls, (list, tuple)) or deformation is not None or int(dt) == IF:
-            raise XgpuError("Integrate over BND: single level set, NEG / POS, no deformation")
+        if isinstance(ls, (list, tuple)) or deformation is not None:
+            raise XgpuError("Integrate over BND: single level set, no deformation")
         if dim < 2:
             raise XgpuError("Integrate over BND needs dim >= 2")
         bv, _ = mesh.boundary_elements()
-        off, p, w = ops.cutquad(dim - 1, None, bv, mesh.points, _lset_vec(ls, mesh), int(dt), order, ctx=ctx)
+        don = ld.get("definedonelements", None)
+        if don is not None:                       # BitArray over the boundary elements (test_bndcut.py:203-217)
+            bv = bv[don.indices().long()].contiguous()
+        off, p, w = _bnd_cutquad(mesh, bv, _lset_vec(ls, mesh), dt, order, ctx)
         ctx.raise_on_geometry_error()
         return cf.coef * ops.integrate_monomial_bnd(dim - 1, dim, None, bv, mesh.points, off, p, w, cf.expo[:dim], ctx=ctx)
     with ctx.deformation(_eff_def(deformation, mesh)):

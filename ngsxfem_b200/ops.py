@@ -450,26 +450,46 @@ def elvec_std(dim, fe_order, elems, el_vtx, vtx_xyz, phi, order, terms, out=None
     return out
 
 
-def facetpatch(dim, fe_order, facets, facet_els, el_vtx, vtx_xyz, order, coef, hpow, out=None, ctx=None):
+class _Downscale:
+    """dFacetPatch(downscale=s) = SetIRScaling on the integrator (xfem/python_xfem.cpp:966-967): state of the context around
+    one facet-patch call; 0 < s <= 1, else XgpuError (symboliccutbfi.cpp:2031-2033)"""
+
+    def __init__(self, ctx, s):
+        self.ctx, self.s = ctx, 1.0 if s is None else float(s)
+
+    def __enter__(self):
+        if self.s != 1.0:
+            self.ctx.check(self.ctx.lib.xgpu_facetpatch_set_downscale(self.ctx.h, self.s))
+
+    def __exit__(self, *exc):
+        if self.s != 1.0:
+            self.ctx.lib.xgpu_facetpatch_set_downscale(self.ctx.h, 1.0)
+        return False
+
+
+def facetpatch(dim, fe_order, facets, facet_els, el_vtx, vtx_xyz, order, coef, hpow, out=None, downscale=None, ctx=None):
     ctx = ctx or default_ctx()
     n = facet_els.shape[0] if facets is None else facets.numel()
     nd = h1_ndof(dim, fe_order)
     if out is None:
         out = torch.empty((n, 2 * nd, 2 * nd), dtype=torch.float64, device=el_vtx.device)
-    ctx.check(ctx.lib.xgpu_facetpatch(ctx.h, dim, fe_order, n, ptr(facets), ptr(_i32(facet_els)), ptr(_i32(el_vtx)),
-                                      ptr(_f64(vtx_xyz)), order, float(coef), int(hpow), ptr(out)))
+    with _Downscale(ctx, downscale):
+        ctx.check(ctx.lib.xgpu_facetpatch(ctx.h, dim, fe_order, n, ptr(facets), ptr(_i32(facet_els)), ptr(_i32(el_vtx)),
+                                          ptr(_f64(vtx_xyz)), order, float(coef), int(hpow), ptr(out)))
     return out
 
 
-def facetpatch_st(dim, fe_order, time_fe_order, facets, facet_els, el_vtx, vtx_xyz, order, time_order, tref, coef, hpow, ctx=None):
+def facetpatch_st(dim, fe_order, time_fe_order, facets, facet_els, el_vtx, vtx_xyz, order, time_order, tref, coef, hpow,
+                  downscale=None, ctx=None):
     """space-time ghost-penalty patch matrices: n x (2 nd) x (2 nd), nd = nd_s*(time_fe_order+1)"""
     ctx = ctx or default_ctx()
     n = facet_els.shape[0] if facets is None else facets.numel()
     nd = h1_ndof(dim, fe_order) * (time_fe_order + 1)
     out = torch.empty((n, 2 * nd, 2 * nd), dtype=torch.float64, device=el_vtx.device)
-    ctx.check(ctx.lib.xgpu_facetpatch_st(ctx.h, dim, fe_order, time_fe_order, n, ptr(facets), ptr(_i32(facet_els)),
-                                         ptr(_i32(el_vtx)), ptr(_f64(vtx_xyz)), int(order), int(time_order),
-                                         float(0.0 if tref is None else tref), float(coef), int(hpow), ptr(out)))
+    with _Downscale(ctx, downscale):
+        ctx.check(ctx.lib.xgpu_facetpatch_st(ctx.h, dim, fe_order, time_fe_order, n, ptr(facets), ptr(_i32(facet_els)),
+                                             ptr(_i32(el_vtx)), ptr(_f64(vtx_xyz)), int(order), int(time_order),
+                                             float(0.0 if tref is None else tref), float(coef), int(hpow), ptr(out)))
     return out
 
 

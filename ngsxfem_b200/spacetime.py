@@ -399,7 +399,7 @@ def assemble_bilinear(blf):
             mm = None
             for (_, _, c, hp) in terms:
                 m1 = ops.facetpatch_st(dim, p, kt, l_f, fe, mesh.elements, mesh.points, integ.dx.order, integ.dx.time_order, t0,
-                                       c, hp, ctx=ctx)
+                                       c, hp, downscale=integ.dx.downscale, ctx=ctx)
                 mm = m1 if mm is None else mm + m1
             fel = fe[l_f.long()]
             t_f = torch.cat([sp.rows(fel[:, 0].contiguous()), sp.rows(fel[:, 1].contiguous())], dim=1).contiguous()

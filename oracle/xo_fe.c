@@ -441,26 +441,58 @@ static int map_patch_point(const xo_trafo* Tf, const xo_trafo* Tt, const double*
   return failed;
 }
 
-/* T_CalcFacetMatrix: symboliccutbfi.cpp:1982-2377, time_order=-1, downscale=1,
- * form coef*h^hpow*(u-u.Other())*(v-v.Other()).  order<0: 2*fe_order (:2004-2012). */
-int xo_facet_patch_elmat(const xo_trafo* T1, const xo_trafo* T2, int p, int order,
-                         double coef, int hpow, double* elmat)
+/* ScaleAndMapIntegrationRule<D>: symboliccutbfi.cpp:1849-1885.  The rule of element T is scaled towards the midpoint of the
+ * reference facet LocalFacetNr: shift = (1 - s) / nv * sum of the reference vertices of the facet, point <- s * point + shift,
+ * weight <- weight * s * s (in every dimension).  The facet's vertices (ElementTopology::GetFaces / GetEdges / GetVertices
+ * of LocalFacetNr) are the vertices T shares with the neighbour To; reference vertex k < D is e_k, vertex D the origin. */
+static void scale_and_map_rule(const xo_trafo* T, const xo_trafo* To, double s, int n, const double* rp, const double* rw,
+                               double* sp, double* sw)
+{
+  int D = T->dim, nv = 0;
+  double shift[3] = { 0, 0, 0 };
+  for (int k = 0; k < D + 1; k++) {
+    int shared = 0;
+    for (int j = 0; j < D + 1; j++) shared |= (T->vnum[k] == To->vnum[j]);
+    if (!shared) continue;
+    nv++;
+    if (k < D) shift[k] += 1.0;
+  }
+  for (int l = 0; l < D; l++) shift[l] *= (1 - s) / nv;
+  for (int q = 0; q < n; q++) {
+    for (int l = 0; l < 3; l++) sp[3 * q + l] = l < D ? rp[3 * q + l] * s + shift[l] : rp[3 * q + l];
+    sw[q] = rw[q] * s * s;
+  }
+}
+
+/* T_CalcFacetMatrix: symboliccutbfi.cpp:1982-2377, time_order=-1,
+ * form coef*h^hpow*(u-u.Other())*(v-v.Other()).  order<0: 2*fe_order (:2004-2012).  downscale: :2019-2033. */
+int xo_facet_patch_elmat_scaled(const xo_trafo* T1, const xo_trafo* T2, int p, int order,
+                                double coef, int hpow, double downscale, double* elmat)
 {
   int D = T1->dim, nd = xo_h1_ndof(D, p), N = 2 * nd, nfail = 0;
   static __thread double rp[3 * XO_MAXPTS_RULE], rw[XO_MAXPTS_RULE];
+  static __thread double rp1[3 * XO_MAXPTS_RULE], rw1[XO_MAXPTS_RULE], rp2[3 * XO_MAXPTS_RULE], rw2[XO_MAXPTS_RULE];
   if (order < 0) order = 2 * p;
+  if (!(downscale > 0 && downscale <= 1)) return -1; /* "Only 0 < downscale <= 1 valid" (:2031-2033) */
   int n = xo_select_rule(D, order, rp, rw);
+  if (downscale < 1) {
+    scale_and_map_rule(T1, T2, downscale, n, rp, rw, rp1, rw1);
+    scale_and_map_rule(T2, T1, downscale, n, rp, rw, rp2, rw2);
+  } else {
+    memcpy(rp1, rp, sizeof(double) * 3 * n); memcpy(rw1, rw, sizeof(double) * n);
+    memcpy(rp2, rp, sizeof(double) * 3 * n); memcpy(rw2, rw, sizeof(double) * n);
+  }
   memset(elmat, 0, sizeof(double) * N * N);
   for (int l = 0; l < 2 * n; l++) {
     double x1[3], x2[3], w1;
     if (l < n) {
       double wt;
-      for (int k = 0; k < 3; k++) x1[k] = rp[3 * l + k];
-      w1 = rw[l];
+      for (int k = 0; k < 3; k++) x1[k] = rp1[3 * l + k];
+      w1 = rw1[l];
       nfail += map_patch_point(T1, T2, x1, w1, x2, &wt);
     } else {
-      for (int k = 0; k < 3; k++) x2[k] = rp[3 * (l - n) + k];
-      nfail += map_patch_point(T2, T1, x2, rw[l - n], x1, &w1);
+      for (int k = 0; k < 3; k++) x2[k] = rp2[3 * (l - n) + k];
+      nfail += map_patch_point(T2, T1, x2, rw2[l - n], x1, &w1);
     }
     double F[9], Fi[9], x[3], J[128], sh[64];
     xo_trafo_eval(T1, x1, F, x);
@@ -475,4 +507,10 @@ int xo_facet_patch_elmat(const xo_trafo* T1, const xo_trafo* T2, int p, int orde
     for (int i = 0; i < N; i++) for (int j = 0; j < N; j++) elmat[i * N + j] += c * J[i] * J[j];
   }
   return nfail;
+}
+
+int xo_facet_patch_elmat(const xo_trafo* T1, const xo_trafo* T2, int p, int order,
+                         double coef, int hpow, double* elmat)
+{
+  return xo_facet_patch_elmat_scaled(T1, T2, p, order, coef, hpow, 1.0, elmat);
 }

@@ -117,10 +117,22 @@ int xo_batch_cut_elvecs(int dim, int fe_order, int64_t n, const int32_t* elems, 
 }
 
 /* facet patch matrices for a list of facets */
+int xo_batch_facet_patch_scaled(int dim, int fe_order, int64_t n, const int32_t* facets, const int32_t* facet_els,
+                                const int32_t* el_vtx, const double* vtx_xyz, int order, double coef, int hpow,
+                                int def_order, const double* def, double downscale, double* mats);
 int xo_batch_facet_patch(int dim, int fe_order, int64_t n, const int32_t* facets, const int32_t* facet_els,
                          const int32_t* el_vtx, const double* vtx_xyz, int order, double coef, int hpow,
                          int def_order, const double* def, double* mats)
 {
+  return xo_batch_facet_patch_scaled(dim, fe_order, n, facets, facet_els, el_vtx, vtx_xyz, order, coef, hpow, def_order, def, 1.0, mats);
+}
+
+/* the same with dFacetPatch(downscale=) (symboliccutbfi.cpp:2019-2033); -1: downscale outside (0, 1] */
+int xo_batch_facet_patch_scaled(int dim, int fe_order, int64_t n, const int32_t* facets, const int32_t* facet_els,
+                                const int32_t* el_vtx, const double* vtx_xyz, int order, double coef, int hpow,
+                                int def_order, const double* def, double downscale, double* mats)
+{
+  if (!(downscale > 0 && downscale <= 1)) return -1;
   int nv = dim + 1, nd = xo_h1_ndof(dim, fe_order), N = 2 * nd;
   int ndd = def_order > 0 ? xo_h1_ndof(dim, def_order) : 0;
   int nfail = 0;
@@ -131,7 +143,7 @@ int xo_batch_facet_patch(int dim, int fe_order, int64_t n, const int32_t* facets
     xo_trafo T1, T2;
     fill_trafo(&T1, dim, el_vtx + (int64_t)e1 * nv, vtx_xyz, def_order, def ? def + e1 * (int64_t)ndd * dim : 0);
     fill_trafo(&T2, dim, el_vtx + (int64_t)e2 * nv, vtx_xyz, def_order, def ? def + e2 * (int64_t)ndd * dim : 0);
-    nfail += xo_facet_patch_elmat(&T1, &T2, fe_order, order, coef, hpow, mats + i * (int64_t)N * N);
+    nfail += xo_facet_patch_elmat_scaled(&T1, &T2, fe_order, order, coef, hpow, downscale, mats + i * (int64_t)N * N);
   }
   return nfail;
 }

@@ -152,6 +152,9 @@ void xo_elvec_st_from_rule(const xo_trafo* T, int fe_order, int time_fe_order, c
  * returns number of Newton failures. */
 int xo_facet_patch_elmat(const xo_trafo* T1, const xo_trafo* T2, int fe_order, int order,
                          double coef, int hpow, double* elmat);
+/* with dFacetPatch(downscale = s), ScaleAndMapIntegrationRule (symboliccutbfi.cpp:1849-1885, :2019-2033); -1 unless 0 < s <= 1 */
+int xo_facet_patch_elmat_scaled(const xo_trafo* T1, const xo_trafo* T2, int fe_order, int order,
+                                double coef, int hpow, double downscale, double* elmat);
 
 /* SymbolicCutLinearFormIntegrator::T_CalcElementVector (xfem/symboliccutlfi.cpp:51-140) for the closed menu
  *   f(x) * op_test(v),  f = coef * h^hpow * x^e0 y^e1 z^e2,  op_test in {ID, DN}:

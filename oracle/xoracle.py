@@ -367,16 +367,18 @@ def batch_cut_elmats(dim, fe_order, elems, el_vtx, vtx_xyz, phi, dt, order, term
     return mats
 
 
-def batch_facet_patch(dim, fe_order, facets, facet_els, el_vtx, vtx_xyz, order, coef, hpow, def_order=0, deform=None):
+def batch_facet_patch(dim, fe_order, facets, facet_els, el_vtx, vtx_xyz, order, coef, hpow, def_order=0, deform=None, downscale=1.0):
     el_vtx = _i32(el_vtx); vtx_xyz = _f64(vtx_xyz); fe = _i32(facet_els)
     fl = None if facets is None else _i32(facets)
     n = fe.shape[0] if fl is None else len(fl)
     nd = h1_ndof(dim, fe_order)
     mats = np.zeros((n, 2 * nd, 2 * nd))
     d = None if deform is None else _f64(deform)
-    nfail = lib().xo_batch_facet_patch(dim, fe_order, C.c_int64(n), _p(fl, C.c_int32), _p(fe, C.c_int32),
-                                       _p(el_vtx, C.c_int32), _p(vtx_xyz), order, C.c_double(coef), hpow,
-                                       def_order, _p(d), _p(mats))
+    nfail = lib().xo_batch_facet_patch_scaled(dim, fe_order, C.c_int64(n), _p(fl, C.c_int32), _p(fe, C.c_int32),
+                                              _p(el_vtx, C.c_int32), _p(vtx_xyz), order, C.c_double(coef), hpow,
+                                              def_order, _p(d), C.c_double(downscale), _p(mats))
+    if nfail < 0:
+        raise ValueError("Only 0 < downscale <= 1 valid")
     return mats, nfail
 
 

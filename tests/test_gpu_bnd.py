@@ -97,3 +97,69 @@ def test_bnd_bilinear_and_linear_forms(dim, p):
         ex_quad += si.dblquad(lambda t, s_: g(0.0, s_) ** 2, 0, 1, 0, 1)[0]
     assert abs(quad - ex_quad) < 1e-10 * abs(ex_quad)
     assert abs(lin - ex_lin) < 1e-10 * max(1.0, abs(ex_lin))
+
+
+# ---- dCut(lset, IF, vb=BND): the codim-2 point measure on the boundary segments of a 2D mesh
+# (cutint/straightcutrule.cpp:646-656; known answers of tests/pytests/test_bndcut.py:166-217)
+@pytest.mark.parametrize("cut", [0.3, 0.5, 0.7])
+def test_integrate_if_bnd_2d_counts_the_intersections(cut):
+    mesh = xf.MakeStructured2DMesh(nx=7, ny=6, device=DEV)
+    lset = xf.InterpolateToP1(lambda x, y: x - cut, mesh)
+    ld = {"levelset": lset, "domain_type": xf.IF, "vb": xf.BND}
+    assert abs(xf.Integrate(ld, mesh=mesh, cf=1.0, order=0) - 2.0) < 1e-10          # (cut, 0) and (cut, 1)
+    assert abs(xf.Integrate(ld, mesh=mesh, cf=xf.x, order=1) - 2.0 * cut) < 1e-10
+    assert abs(xf.Integrate(ld, mesh=mesh, cf=xf.y, order=1) - 1.0) < 1e-10
+    # definedonelements over the boundary elements (the reference's definedon=mesh.Boundaries("bottom"), :203-217)
+    bv, _ = mesh.boundary_elements()
+    ymid = mesh.points[bv.long()][:, :, 1].mean(dim=1)
+    xmid = mesh.points[bv.long()][:, :, 0].mean(dim=1)
+    for mask, want in ((ymid < 1e-12, 1.0), (xmid < 1e-12, 0.0)):
+        ba = xf.BitArray.from_numpy(mask.cpu().numpy(), DEV)
+        got = xf.Integrate({**ld, "definedonelements": ba}, mesh=mesh, cf=1.0, order=0)
+        assert abs(got - want) < 1e-10
+
+
+def test_if_bnd_2d_against_the_cut_points_in_closed_form():
+    """circle through the boundary of the square: every cut boundary segment contributes f at the zero of the P1 level set"""
+    mesh = xf.MakeStructured2DMesh(nx=9, ny=8, device=DEV)
+    lset = xf.InterpolateToP1(lambda x, y: torch.sqrt((x - .1) ** 2 + (y - .2) ** 2) - 0.62, mesh)
+    bv, _ = mesh.boundary_elements()
+    P, phi, b = mesh.points.cpu().numpy(), lset.vec.cpu().numpy(), bv.cpu().numpy()
+    want1 = wantf = 0.0
+    for s in b:
+        a, c = phi[s[0]], phi[s[1]]
+        if (a < 0) != (c < 0):
+            t = a / (a - c)
+            xs = P[s[0]] + t * (P[s[1]] - P[s[0]])
+            want1 += 1.0
+            wantf += xs[0] ** 2 * xs[1]
+    assert want1 >= 2
+    ld = {"levelset": lset, "domain_type": xf.IF, "vb": xf.BND}
+    assert abs(xf.Integrate(ld, mesh=mesh, cf=1.0, order=0) - want1) < 1e-12
+    assert abs(xf.Integrate(ld, mesh=mesh, cf=xf.x ** 2 * xf.y, order=3) - wantf) < 1e-12
+    # linear / bilinear forms: sum_j v_j = 1 at every cut point; c^T M c = sum g(x*)^2 for a P1 function g
+    V = xf.H1(mesh, order=2)
+    u, v = V.TnT()
+    f = xf.LinearForm(V)
+    f += 1.0 * v * xf.dCut(lset, xf.IF, vb=xf.BND)
+    f.Assemble()
+    assert abs(float(f.vec.sum()) - want1) < 1e-12
+    a = xf.BilinearForm(V)
+    a += u * v * xf.dCut(lset, xf.IF, vb=xf.BND)
+    a.Assemble()
+    c = torch.zeros(V.ndof, dtype=torch.float64, device=DEV)
+    c[:mesh.nv] = 1.0 + 2.0 * mesh.points[:, 0] - mesh.points[:, 1]
+    wantg = 0.0
+    for s in b:
+        p0, p1 = phi[s[0]], phi[s[1]]
+        if (p0 < 0) != (p1 < 0):
+            xs = P[s[0]] + p0 / (p0 - p1) * (P[s[1]] - P[s[0]])
+            wantg += (1.0 + 2.0 * xs[0] - xs[1]) ** 2
+    assert abs(float((c * (a.mat * c)).sum()) - wantg) < 1e-11
+
+
+def test_if_bnd_3d_is_declined():
+    mesh = xf.MakeStructured3DMesh(nx=3, device=DEV)
+    lset = xf.InterpolateToP1(lambda x, y, z: x - 0.4, mesh)
+    with pytest.raises(xf.XgpuError):
+        xf.Integrate({"levelset": lset, "domain_type": xf.IF, "vb": xf.BND}, mesh=mesh, cf=1.0, order=0)

@@ -129,6 +129,14 @@ def test_facet_patch_on_deformed_elements_matches_oracle(dim, p, n):
                                      mesh.points.cpu().numpy(), -1, 0.1, -2, def_order=p, deform=defo.local().cpu().numpy())
     assert nfail == 0
     assert np.linalg.norm(m.cpu().numpy() - mo) <= 1e-12 * np.linalg.norm(mo)
+    # dFacetPatch(downscale=) on curved elements: the scaled points go through the same Newton map
+    with ctx.deformation(defo):
+        ms = ops.facetpatch(dim, p, inner, fe, mesh.elements, mesh.points, -1, 0.1, -2, downscale=0.4)
+    mos, nfail = xo.batch_facet_patch(dim, p, inner.cpu().numpy(), fe.cpu().numpy(), mesh.elements.cpu().numpy(),
+                                      mesh.points.cpu().numpy(), -1, 0.1, -2, def_order=p, deform=defo.local().cpu().numpy(),
+                                      downscale=0.4)
+    assert nfail == 0
+    assert np.linalg.norm(ms.cpu().numpy() - mos) <= 1e-12 * np.linalg.norm(mos)
 
 
 def test_isoparametric_assembly_with_ghost_penalty_matches_oracle():

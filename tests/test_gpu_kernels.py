@@ -7,6 +7,7 @@ import pytest
 import torch
 
 from ngsxfem_b200 import meshes, ops, fes
+from ngsxfem_b200._lib import XgpuError
 from oracle import xoracle as xo
 from util import interpolate_to_p1, mesh_np, unpack_bits
 
@@ -560,3 +561,45 @@ def test_elmat_cut_pair_rules_on_the_fly_equal_stored_rules_and_oracle(dim, n, p
         ops.elmat_cut_pair(dim, 3, lst, m.elements, m.points, phi, ops.NEG, 6, TV)
     with pytest.raises(Exception):
         ops.elmat_cut_pair(dim, p, l_if, m.elements, m.points, phi, ops.IF, order, TERMS_NITSCHE)
+
+
+# ------------------------------------------------------------------ (d) facet patch, dFacetPatch(downscale=)
+@pytest.mark.parametrize("dim,n,p", [(1, 7, 2), (2, 5, 1), (2, 5, 2), (2, 4, 3), (2, 3, 4), (3, 3, 1), (3, 3, 2), (3, 2, 3), (3, 2, 4)])
+@pytest.mark.parametrize("s", [0.5, 0.13])
+def test_facetpatch_downscale_matches_oracle(dim, n, p, s):
+    """xgpu_facetpatch_set_downscale (SetIRScaling; ScaleAndMapIntegrationRule, symboliccutbfi.cpp:1849-1885) on the CUDA-core
+    (p <= 2) and the tensor-tile (p >= 3) kernels; the state is reset after the call"""
+    m = make_mesh(dim, n)
+    pts, els = mesh_np(m)
+    rng = np.random.default_rng(5)
+    pts = pts + 0.1 / n * rng.random(pts.shape)
+    m = meshes.Mesh(torch.from_numpy(pts), m.elements)
+    md = to_dev(m)
+    _, _, fe = md.facets()
+    fe_np = fe.cpu().numpy()
+    inner = np.nonzero(fe_np[:, 1] >= 0)[0].astype(np.int32)
+    sel = inner[:: max(1, len(inner) // 40)]
+    gsel = torch.from_numpy(sel).to(DEV)
+    g1 = ops.facetpatch(dim, p, gsel, fe, md.elements, md.points, -1, 0.37, -2)
+    g = ops.facetpatch(dim, p, gsel, fe, md.elements, md.points, -1, 0.37, -2, downscale=s)
+    o, nfail = xo.batch_facet_patch(dim, p, sel, fe_np, els, pts, -1, 0.37, -2, downscale=s)
+    assert nfail == 0
+    assert rel_err(g.cpu().numpy(), o) < 1e-12
+    assert rel_err(g.cpu().numpy(), g1.cpu().numpy()) > 1e-3           # it is another matrix
+    # u = 1 on element 1, 0 on element 2: coef h^-2 s^2 (|T1| + |T2|) — closed form on the device result
+    gm = g.cpu().numpy()
+    nd = gm.shape[1] // 2
+    one = np.zeros(2 * nd); one[:dim + 1] = 1.0
+    import math
+    for k, f in enumerate(sel):
+        X1, X2 = pts[els[fe_np[f, 0]]], pts[els[fe_np[f, 1]]]
+        v1 = abs(np.linalg.det(X1[:dim] - X1[dim])) / math.factorial(dim)
+        v2 = abs(np.linalg.det(X2[:dim] - X2[dim])) / math.factorial(dim)
+        h1 = (v1 * math.factorial(dim)) ** (1.0 / dim)                    # specialcf.mesh_size of element 1: |det F|^(1/D)
+        want = 0.37 * h1 ** -2 * s * s * (v1 + v2)
+        assert abs(one @ gm[k] @ one - want) < 1e-11 * want
+    # the state does not leak: the next plain call is the unscaled matrix, bit for bit
+    g2 = ops.facetpatch(dim, p, gsel, fe, md.elements, md.points, -1, 0.37, -2)
+    assert torch.equal(g1, g2)
+    with pytest.raises(XgpuError):
+        ops.facetpatch(dim, p, gsel, fe, md.elements, md.points, -1, 0.37, -2, downscale=1.5)

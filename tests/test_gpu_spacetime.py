@@ -354,6 +354,12 @@ def test_spacetime_facet_patch_matches_oracle(dim, n, p, kt, to, tref):
     mo = np.einsum("jl,fhigk->fhjiglk", T, F4).reshape(nf, 2 * nds * nt, 2 * nds * nt)
     assert np.linalg.norm(mo) > 0
     assert np.linalg.norm(m.cpu().numpy() - mo) <= 1e-12 * np.linalg.norm(mo)
+    # downscale: the spatial patch matrix carries the scaling, the time matrix does not
+    ms = ops.facetpatch_st(dim, p, kt, inner, fe, mesh.elements, mesh.points, -1, to, tref, 0.7, -2, downscale=0.5)
+    Fs, nfail = xo.batch_facet_patch(dim, p, inner.cpu().numpy(), fe.cpu().numpy(), mesh.elements.cpu().numpy(),
+                                     mesh.points.cpu().numpy(), -1, 0.7, -2, downscale=0.5)
+    mos = np.einsum("jl,fhigk->fhjiglk", T, Fs.reshape(nf, 2, nds, 2, nds)).reshape(nf, 2 * nds * nt, 2 * nds * nt)
+    assert nfail == 0 and np.linalg.norm(ms.cpu().numpy() - mos) <= 1e-12 * np.linalg.norm(mos)
 
 
 def test_spacetime_ghost_penalty_assembled_kernel_and_definiteness():

@@ -100,3 +100,45 @@ def test_legacy_paths_are_rejected_not_emulated():
     f_def = xf.GetFacetsWithNeighborTypes(mesh, a=ci.GetElementsOfType(xf.HASNEG))
     f_nob = xf.GetFacetsWithNeighborTypes(mesh, a=ci.GetElementsOfType(xf.HASNEG), bnd_val_a=False, bnd_val_b=False)
     assert f_def.NumSet() > f_nob.NumSet() > 0
+
+
+def test_dfacetpatch_downscale_assembles_the_scaled_patch_matrices():
+    """dFacetPatch(definedonelements=..., downscale=s) (python/__init__.py:749-778 -> SetIRScaling): the assembled ghost
+    penalty is the sum of the oracle's scaled patch matrices; the pattern is the one of the unscaled form"""
+    import scipy.sparse as sp
+    mesh = xf.MakeStructured3DMesh(nx=4, device=DEV)
+    lset = sphere(mesh, 0.34)
+    ci = xf.CutInfo(mesh, lset)
+    hasneg, hasif = ci.GetElementsOfType(xf.HASNEG), ci.GetElementsOfType(xf.IF)
+    gpf = xf.GetFacetsWithNeighborTypes(mesh, a=hasneg, b=hasif, use_and=True)
+    V = xf.Restrict(xf.H1(mesh, order=2, dgjumps=True), hasneg)
+    u, v = V.TnT()
+    h = xf.specialcf.mesh_size
+
+    def assemble(s):
+        a = xf.RestrictedBilinearForm(V, element_restriction=hasneg, facet_restriction=gpf)
+        a += (0.1 / h ** 2) * (u - u.Other()) * (v - v.Other()) * xf.dFacetPatch(definedonelements=gpf, downscale=s)
+        a.Assemble()
+        return a.mat
+
+    A1, As = assemble(None), assemble(0.5)
+    assert torch.equal(A1.rowptr, As.rowptr) and torch.equal(A1.col, As.col)
+    assert torch.equal(assemble(1.0).vals, A1.vals)
+    _, _, fe = mesh.facets()
+    l_f = gpf.indices()
+    l_f = l_f[fe[l_f.long(), 1] >= 0].contiguous()
+    fel = fe[l_f.long()]
+    mf, nfail = xo.batch_facet_patch(3, 2, l_f.cpu().numpy(), fe.cpu().numpy(), mesh.elements.cpu().numpy(),
+                                     mesh.points.cpu().numpy(), -1, 0.1, -2, downscale=0.5)
+    assert nfail == 0 and len(mf) > 0
+    t_f = torch.cat([V.rows(fel[:, 0].contiguous()), V.rows(fel[:, 1].contiguous())], dim=1).cpu().numpy()
+    ref = sp.lil_matrix((V.ndof, V.ndof))
+    for r in range(t_f.shape[0]):
+        d = t_f[r]                      # the dofs on the common facet appear in both halves: add entry by entry
+        for i in range(len(d)):
+            for j in range(len(d)):
+                ref[d[i], d[j]] += mf[r, i, j]
+    diff = As.to_scipy() - ref.tocsr()
+    assert np.sqrt(diff.multiply(diff).sum()) <= 1e-12 * np.sqrt(ref.multiply(ref).sum())
+    with pytest.raises(XgpuError):
+        xf.dFacetPatch(definedonelements=gpf, downscale=0.0)

@@ -158,3 +158,48 @@ def test_dg_forms_expand_into_the_term_list():
         xf.dCut(lset, xf.IF, skeleton=True, definedonelements=facets)     # codim-2 case: not provided
     with pytest.raises(xf.XgpuError):
         xf.dn(u, 2)
+
+
+# ---- dFacetPatch(downscale = s): ScaleAndMapIntegrationRule (symboliccutbfi.cpp:1849-1885) pinned by closed forms
+@pytest.mark.parametrize("dim,n", [(1, 5), (2, 3), (3, 2)])
+@pytest.mark.parametrize("p", [1, 2])
+@pytest.mark.parametrize("s", [1.0, 0.5, 0.2])
+def test_downscaled_patch_rule_in_closed_form(dim, n, p, s):
+    """the scaled rule of an element is the rule of its image under the homothety (centre: midpoint of the common facet,
+    ratio s) with weights s^2 |T| w_q.  With u = a polynomial on element 1 and 0 on element 2 the jump is that polynomial
+    on the whole patch: u = 1 gives s^2 (|T1| + |T2|), u = x gives s^(2 - D) times the second moments of the two images"""
+    import math
+    m = {1: lambda: meshes.MakeStructured1DMesh(n), 2: lambda: meshes.MakeStructured2DMesh(nx=n, ny=n + 1),
+         3: lambda: meshes.MakeStructured3DMesh(nx=n)}[dim]()
+    pts, els = mesh_np(m)
+    rng = np.random.default_rng(dim * 10 + p)
+    pts = pts + 0.15 / n * rng.random(pts.shape)
+    ents, _, fe = facet_tables(m)
+    inner = np.nonzero(fe[:, 1] >= 0)[0].astype(np.int32)
+    M, nfail = xo.batch_facet_patch(dim, p, inner, fe, els, pts, -1, 1.0, 0, downscale=s)
+    assert nfail == 0
+    nv, nd = dim + 1, M.shape[1] // 2
+
+    def vol(X):
+        return abs(np.linalg.det(X[:dim] - X[dim])) / math.factorial(dim)
+
+    def moment_x2(X):   # int_T x^2 = |T| / ((D+1)(D+2)) (sum x_i^2 + (sum x_i)^2)
+        x = X[:, 0]
+        return vol(X) / ((dim + 1) * (dim + 2)) * ((x ** 2).sum() + x.sum() ** 2)
+
+    for k, f in enumerate(inner):
+        e1, e2 = fe[f]
+        X1, X2 = pts[els[e1]], pts[els[e2]]
+        mid = pts[np.atleast_1d(ents[f])].reshape(-1, dim).mean(axis=0)
+        one = np.zeros(2 * nd); one[:nv] = 1.0
+        assert abs(one @ M[k] @ one - s * s * (vol(X1) + vol(X2))) < 1e-13
+        cx = np.zeros(2 * nd); cx[:nv] = X1[:, 0]
+        want = s ** (2 - dim) * (moment_x2(mid + s * (X1 - mid)) + moment_x2(mid + s * (X2 - mid)))
+        assert abs(cx @ M[k] @ cx - want) < 1e-13 * max(1.0, abs(want))
+        # the other side: u = x on element 2, 0 on element 1 -> the same moments
+        cy = np.zeros(2 * nd); cy[nd:nd + nv] = X2[:, 0]
+        assert abs(cy @ M[k] @ cy - want) < 1e-13 * max(1.0, abs(want))
+    with pytest.raises(ValueError):
+        xo.batch_facet_patch(dim, p, inner, fe, els, pts, -1, 1.0, 0, downscale=1.5)
+    with pytest.raises(ValueError):
+        xo.batch_facet_patch(dim, p, inner, fe, els, pts, -1, 1.0, 0, downscale=0.0)

@@ -81,7 +81,7 @@ def test_unsupported_requests_raise():
     with pytest.raises(xf.XgpuError):
         xf.dmesh(None, tref=0.0)
     with pytest.raises(xf.XgpuError):
-        xf.dFacetPatch(definedonelements=xf.BitArray(mesh.nfacet, "cpu"), downscale=0.5)
+        xf.dFacetPatch(definedonelements=xf.BitArray(mesh.nfacet, "cpu"), downscale=1.5)   # only 0 < downscale <= 1
     with pytest.raises(xf.XgpuError):
         xf.dCut([xf.GridFunction(mesh), xf.GridFunction(mesh)], (xf.NEG, xf.NEG), time_order=1)   # no multi-level-set slabs
     a = xf.BilinearForm(V)
