@@ -339,10 +339,11 @@ class MultiLevelsetCutInfo:
 
 
 def GetFacetsWithNeighborTypes(mesh, a, b=None, bnd_val_a=True, bnd_val_b=True, use_and=True, heapsize=1000000):
-    """xfem/python_xfem.cpp:346-369 -> xfem/cutinfo.cpp:476-538"""
+    """xfem/python_xfem.cpp:346-369 -> xfem/cutinfo.cpp:476-538.  Periodic meshes (mesh.SetPeriodicFacets /
+    MakeStructured*Mesh(periodic_x=...)): the facet table carries the identified neighbour (:509-518)"""
     if b is None:
         b = a
-    _, _, fe = mesh.facets()
+    fe = mesh.facet_els_periodic()
     return BitArray(mesh.nfacet, words=ops.facets_with_neighbor_types(fe, a.bits, b.bits, bnd_val_a, bnd_val_b, use_and))
 
 

@@ -112,6 +112,58 @@ class Mesh:
             self._topo["facets"] = (ents, el_f, fe)
         return self._topo["facets"]
 
+    # ---- periodic identification (MeshAccess::GetPeriodicFacet; consumed by GetFacetsWithNeighborTypes, cutinfo.cpp:509-518)
+    def SetPeriodicFacets(self, partner):
+        """partner: (nfacet,) int32, the identified facet of every facet, the facet itself where there is none
+        (NGSolve's GetPeriodicFacet convention)"""
+        partner = partner.to(self.device).to(torch.int32).contiguous()
+        assert partner.shape == (self.nfacet,)
+        self._topo["periodic"] = (partner,)
+        self._topo.pop("facet_els_periodic", None)
+
+    def periodic_facets(self):
+        return self._topo["periodic"][0] if "periodic" in self._topo else None
+
+    def IdentifyPeriodic(self, shifts, tol=1e-9):
+        """identify boundary facets whose vertex sets differ by one of the translations `shifts` (set-up code, host side:
+        sorted quantised vertex coordinates as keys)"""
+        import numpy as np
+        ents, _, fe = self.facets()
+        P = self.points.cpu().numpy()
+        E = ents.cpu().numpy().reshape(ents.shape[0], -1)
+        bnd = np.flatnonzero(fe[:, 1].cpu().numpy() < 0)
+        partner = np.arange(E.shape[0], dtype=np.int32)
+
+        def key(X):   # X: (k, dim) vertex coordinates of a facet
+            q = np.round(X / tol).astype(np.int64)
+            return tuple(map(tuple, q[np.lexsort(q.T[::-1])]))
+
+        table = {key(P[E[f]]): f for f in bnd}
+        for sh in shifts:
+            sh = np.asarray(sh, dtype=np.float64)
+            for f in bnd:
+                g = table.get(key(P[E[f]] + sh))
+                if g is not None and g != f:
+                    partner[f], partner[g] = g, f
+        self.SetPeriodicFacets(torch.from_numpy(partner))
+        return self
+
+    def facet_els_periodic(self):
+        """facet_els with the periodic neighbour filled in the way GetFacetsWithNeighborTypes sees it (cutinfo.cpp:509-518):
+        a boundary facet whose identified facet has the LARGER number gets that facet's element as its second element; the
+        facet with the larger number stays a boundary facet.  Without identification: facet_els itself."""
+        _, _, fe = self.facets()
+        partner = self.periodic_facets()
+        if partner is None:
+            return fe
+        if "facet_els_periodic" not in self._topo:
+            idx = torch.arange(fe.shape[0], device=fe.device, dtype=torch.int64)
+            take = (fe[:, 1] < 0) & (partner.to(torch.int64) > idx)
+            fe2 = fe.clone()
+            fe2[take, 1] = fe[partner[take].long(), 0]
+            self._topo["facet_els_periodic"] = (fe2.contiguous(),)
+        return self._topo["facet_els_periodic"][0]
+
     def boundary_elements(self):
         """(bnd_vtx (nbe, dim) int32, facet ids): the boundary facets as surface elements (VorB = BND), ascending facet
         id.  NGSolve's own boundary-element numbering is third party and not needed: the table is an input."""
@@ -134,7 +186,7 @@ class Mesh:
         return self.facets()[0].shape[0]
 
 
-def MakeStructured2DMesh(quads=False, nx=10, ny=10, mapping=None, device="cpu"):
+def MakeStructured2DMesh(quads=False, nx=10, ny=10, mapping=None, device="cpu", periodic_x=False, periodic_y=False):
     """Unit square, nx x ny cells, each split into 2 triangles (lower-right, upper-left);
     element id = 2*(i + nx*j) + t.  (NGSolve's ngsolve.meshes.MakeStructured2DMesh is third party;
     its element ordering is not pinned and not needed: all tables are inputs.)"""
@@ -150,12 +202,16 @@ def MakeStructured2DMesh(quads=False, nx=10, ny=10, mapping=None, device="cpu"):
     t0 = torch.stack([v00, v10, v11], dim=1)
     t1 = torch.stack([v00, v01, v11], dim=1)
     els = torch.stack([t0, t1], dim=1).reshape(-1, 3)
+    m = Mesh(pts, els.to(torch.int32))
+    if periodic_x or periodic_y:   # ngsolve.meshes.MakeStructured2DMesh(periodic_x=, periodic_y=): identified before the mapping
+        m.IdentifyPeriodic([s for s, on in (((1.0, 0.0), periodic_x), ((0.0, 1.0), periodic_y)) if on])
     if mapping is not None:
-        pts = torch.stack(list(mapping(pts[:, 0], pts[:, 1])), dim=1)
-    return Mesh(pts, els.to(torch.int32))
+        m.points = torch.stack(list(mapping(pts[:, 0], pts[:, 1])), dim=1).contiguous()
+    return m
 
 
-def MakeStructured3DMesh(hexes=False, nx=10, ny=None, nz=None, mapping=None, device="cpu"):
+def MakeStructured3DMesh(hexes=False, nx=10, ny=None, nz=None, mapping=None, device="cpu", periodic_x=False, periodic_y=False,
+                        periodic_z=False):
     """Unit cube, nx x ny x nz cells, each split into 6 Kuhn tets (the 6 monotone vertex paths
     (0,0,0)->(1,1,1)); vertex id = i + (nx+1)*(j + (ny+1)*k); element id = 6*cell + path index
     (SURVEY.md §8d C2)."""
@@ -179,9 +235,12 @@ def MakeStructured3DMesh(hexes=False, nx=10, ny=None, nz=None, mapping=None, dev
             v.append(v[-1] + stride[a])
         tets.append(torch.stack(v, dim=1))
     els = torch.stack(tets, dim=1).reshape(-1, 4)
+    m = Mesh(pts, els.to(torch.int32))
+    if periodic_x or periodic_y or periodic_z:
+        m.IdentifyPeriodic([s for s, on in (((1.0, 0, 0), periodic_x), ((0, 1.0, 0), periodic_y), ((0, 0, 1.0), periodic_z)) if on])
     if mapping is not None:
-        pts = torch.stack(list(mapping(pts[:, 0], pts[:, 1], pts[:, 2])), dim=1)
-    return Mesh(pts, els.to(torch.int32))
+        m.points = torch.stack(list(mapping(pts[:, 0], pts[:, 1], pts[:, 2])), dim=1).contiguous()
+    return m
 
 
 def MakeStructured1DMesh(nx=10, device="cpu"):

@@ -118,7 +118,7 @@ int xo_ml_elements_with_contribution(int dim, int64_t ne, const int32_t* el_vtx,
 }
 
 /* GetFacetsWithNeighborTypes: cutinfo.cpp:476-538 (every facet here belongs to an element, so
- * fine_facet is all-true; periodic identification is not restated) */
+ * fine_facet is all-true; periodic identification: xo_facets_with_neighbor_types_periodic) */
 void xo_facets_with_neighbor_types(int64_t nf, const int32_t* facet_els, const uint8_t* a,
                                    const uint8_t* b, int bnd_val_a, int bnd_val_b, int use_and,
                                    uint8_t* out)
@@ -130,6 +130,30 @@ void xo_facets_with_neighbor_types(int64_t nf, const int32_t* facet_els, const u
     int a_right = e1 >= 0 ? testbit(a, e1) : bnd_val_a;
     int b_left = testbit(b, e0);
     int b_right = e1 >= 0 ? testbit(b, e1) : bnd_val_b;
+    if (use_and) { if ((a_left && b_right) || (a_right && b_left)) setbit(out, f); }
+    else { if ((a_left || b_right) || (a_right || b_left)) setbit(out, f); }
+  }
+}
+
+/* the same on a mesh with periodic identification (cutinfo.cpp:509-518): periodic_facet[f] = MeshAccess::GetPeriodicFacet(f)
+ * (f itself where there is none).  A facet with ONE element whose identified facet has the larger number takes that facet's
+ * first element as its second one; the other facet of the pair keeps the boundary values. */
+void xo_facets_with_neighbor_types_periodic(int64_t nf, const int32_t* facet_els, const int32_t* periodic_facet,
+                                            const uint8_t* a, const uint8_t* b, int bnd_val_a, int bnd_val_b, int use_and,
+                                            uint8_t* out)
+{
+  memset(out, 0, (nf + 7) / 8);
+  for (int64_t f = 0; f < nf; f++) {
+    int32_t elnums[2] = { facet_els[2 * f], facet_els[2 * f + 1] };
+    int size = elnums[1] >= 0 ? 2 : 1;
+    if (size < 2) {
+      int32_t facet2 = periodic_facet[f];
+      if (facet2 > f) elnums[size++] = facet_els[2 * (int64_t)facet2];
+    }
+    int a_left = testbit(a, elnums[0]);
+    int a_right = size > 1 ? testbit(a, elnums[1]) : bnd_val_a;
+    int b_left = testbit(b, elnums[0]);
+    int b_right = size > 1 ? testbit(b, elnums[1]) : bnd_val_b;
     if (use_and) { if ((a_left && b_right) || (a_right && b_left)) setbit(out, f); }
     else { if ((a_left || b_right) || (a_right || b_left)) setbit(out, f); }
   }

@@ -106,6 +106,9 @@ int xo_ml_elements_with_contribution(int dim, int64_t ne, const int32_t* el_vtx,
 void xo_facets_with_neighbor_types(int64_t nf, const int32_t* facet_els, const uint8_t* a,
                                    const uint8_t* b, int bnd_val_a, int bnd_val_b, int use_and,
                                    uint8_t* out);
+void xo_facets_with_neighbor_types_periodic(int64_t nf, const int32_t* facet_els, const int32_t* periodic_facet,
+                                            const uint8_t* a, const uint8_t* b, int bnd_val_a, int bnd_val_b, int use_and,
+                                            uint8_t* out);
 /* GetElementsWithNeighborFacets (cutinfo.cpp:540-566) */
 void xo_elements_with_neighbor_facets(int64_t nf, const int32_t* facet_els, const uint8_t* facets,
                                       int64_t ne, uint8_t* out);

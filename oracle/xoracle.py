@@ -169,10 +169,16 @@ def ml_elements_with_contribution(dim, el_vtx, vtx_xyz, phis, dts):
     return bits
 
 
-def facets_with_neighbor_types(facet_els, a, b, bnd_val_a=True, bnd_val_b=True, use_and=True):
+def facets_with_neighbor_types(facet_els, a, b, bnd_val_a=True, bnd_val_b=True, use_and=True, periodic_facet=None):
     fe = _i32(facet_els)
     nf = fe.shape[0]
     out = np.zeros((nf + 7) // 8, np.uint8)
+    if periodic_facet is not None:
+        pf = _i32(periodic_facet)
+        lib().xo_facets_with_neighbor_types_periodic(C.c_int64(nf), _p(fe, C.c_int32), _p(pf, C.c_int32), _p(a, C.c_uint8),
+                                                     _p(b, C.c_uint8), int(bnd_val_a), int(bnd_val_b), int(use_and),
+                                                     _p(out, C.c_uint8))
+        return out
     lib().xo_facets_with_neighbor_types(C.c_int64(nf), _p(fe, C.c_int32), _p(a, C.c_uint8), _p(b, C.c_uint8),
                                         int(bnd_val_a), int(bnd_val_b), int(use_and), _p(out, C.c_uint8))
     return out

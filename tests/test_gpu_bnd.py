@@ -137,25 +137,28 @@ def test_if_bnd_2d_against_the_cut_points_in_closed_form():
     ld = {"levelset": lset, "domain_type": xf.IF, "vb": xf.BND}
     assert abs(xf.Integrate(ld, mesh=mesh, cf=1.0, order=0) - want1) < 1e-12
     assert abs(xf.Integrate(ld, mesh=mesh, cf=xf.x ** 2 * xf.y, order=3) - wantf) < 1e-12
-    # linear / bilinear forms: sum_j v_j = 1 at every cut point; c^T M c = sum g(x*)^2 for a P1 function g
+    # linear / bilinear forms with a P1 function g = 1 + 2x - y (higher-order dofs vanish): f^T c = sum g(x*),
+    # c^T M c = sum g(x*)^2; the vertex functions sum to 1 at every cut point
     V = xf.H1(mesh, order=2)
     u, v = V.TnT()
     f = xf.LinearForm(V)
     f += 1.0 * v * xf.dCut(lset, xf.IF, vb=xf.BND)
     f.Assemble()
-    assert abs(float(f.vec.sum()) - want1) < 1e-12
+    assert abs(float(f.vec[:mesh.nv].sum()) - want1) < 1e-12
     a = xf.BilinearForm(V)
     a += u * v * xf.dCut(lset, xf.IF, vb=xf.BND)
     a.Assemble()
     c = torch.zeros(V.ndof, dtype=torch.float64, device=DEV)
     c[:mesh.nv] = 1.0 + 2.0 * mesh.points[:, 0] - mesh.points[:, 1]
-    wantg = 0.0
+    wantg = wantg2 = 0.0
     for s in b:
         p0, p1 = phi[s[0]], phi[s[1]]
         if (p0 < 0) != (p1 < 0):
             xs = P[s[0]] + p0 / (p0 - p1) * (P[s[1]] - P[s[0]])
-            wantg += (1.0 + 2.0 * xs[0] - xs[1]) ** 2
-    assert abs(float((c * (a.mat * c)).sum()) - wantg) < 1e-11
+            wantg += 1.0 + 2.0 * xs[0] - xs[1]
+            wantg2 += (1.0 + 2.0 * xs[0] - xs[1]) ** 2
+    assert abs(float((f.vec * c).sum()) - wantg) < 1e-11
+    assert abs(float((c * (a.mat * c)).sum()) - wantg2) < 1e-11
 
 
 def test_if_bnd_3d_is_declined():

@@ -181,7 +181,10 @@ def test_row_ranges_assemble_to_the_same_bits(n, p, proc):
     mesh = xf.MakeStructured3DMesh(nx=n, device=DEV)
     V = xf.H1(mesh, order=p)
     rng = np.random.default_rng(n + p)
-    elems = torch.from_numpy(np.flatnonzero(rng.random(mesh.ne) < 0.7).astype(np.int32)).to(DEV)
+    # a ball of elements (the shape of HASNEG): every row goes through the thread-per-row / warp-per-row kernels.  A sparse
+    # random subset has short rows with more than 32 columns, which belong to the lane-group kernel (next test)
+    cen = mesh.points[mesh.elements.long()].mean(dim=1)
+    elems = torch.nonzero(((cen - 0.5) ** 2).sum(dim=1) < 0.42 ** 2).reshape(-1).to(torch.int32)
     dofmap, ndof, (table,), plan = ops.restrict_plan(V.el_dofs, [elems], V.ndof)
     ops.csr_count_rows(plan)
     if proc:
@@ -205,3 +208,24 @@ def test_row_ranges_assemble_to_the_same_bits(n, p, proc):
     assert torch.equal(out[1], c) and torch.equal(out[2], v)
     with pytest.raises(XgpuError):
         ops.csr_assemble_fused(plan, batches, rows=(5, 2), out=out)
+
+
+def test_row_ranges_decline_plans_with_lane_group_rows():
+    """rows outside the thread- / warp-per-row kernels cannot be split by range: XGPU_ERR_UNSUPPORTED (-3), nothing written,
+    and the caller assembles all rows at once (distributed.py falls back to the exchange after the row pass)"""
+    mesh = xf.MakeStructured3DMesh(nx=6, device=DEV)
+    V = xf.H1(mesh, order=2)
+    rng = np.random.default_rng(8)
+    elems = torch.from_numpy(np.flatnonzero(rng.random(mesh.ne) < 0.7).astype(np.int32)).to(DEV)
+    dofmap, ndof, (table,), plan = ops.restrict_plan(V.el_dofs, [elems], V.ndof)
+    ops.csr_count_rows(plan)
+    nd = V.el_dofs.shape[1]
+    m = torch.from_numpy(rng.standard_normal((elems.numel(), nd, nd))).to(DEV)
+    full = ops.csr_assemble_fused(plan, [(table, m)])
+    try:
+        part = ops.csr_assemble_fused(plan, [(table, m)], rows=(0, ndof // 2))
+    except XgpuError as e:
+        assert e.code == -3 and "lane-group" in str(e)
+    else:   # the policy took every row on the fast kernels: then the halves must agree
+        ops.csr_assemble_fused(plan, [(table, m)], rows=(ndof // 2, ndof), out=part)
+        assert torch.equal(part[2], full[2])
