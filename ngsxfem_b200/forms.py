@@ -318,6 +318,8 @@ class CoefficientFunction:
             o = LForm.from_proxy(o)
         if isinstance(o, (Form, LForm)):
             return o._with_cf(self)
+        if hasattr(o, "_st_with_cf"):   # space-time proxies / forms (spacetime.py): fn(x, y[, z], tref)
+            return o._st_with_cf(self)
         if isinstance(o, (FacetForm, FacetExpr)):
             raise XgpuError("coefficient functions on facet integrands are not on the accelerated path (constants and h-powers are)")
         return NotImplemented
@@ -326,6 +328,19 @@ class CoefficientFunction:
 
     def __neg__(self):
         return self * -1.0
+
+    def evaluate_st(self, dim, fe_mesh, elems, off, pts, tv, ctx):
+        """space-time rules: fn(x, y[, z], tref) at the points (x_q, tref_q) — the coordinates are physical, the time is the
+        REFERENCE time of the slab as in ngsxfem (ReferenceTimeVariable, python/__init__.py:86-99; t = told + delta_t * tref
+        is formed by the caller's function).  GridFunction arguments are spatial objects and are not taken here."""
+        xyz = ops.rule_phys(dim, elems, fe_mesh.elements, fe_mesh.points, off, pts, ctx=ctx)
+        args = [xyz[:, c] for c in range(dim)] + [tv]
+        out = torch.full((xyz.shape[0],), self.scale, dtype=torch.float64, device=xyz.device)
+        for fn, gfs in self.factors:
+            if gfs:
+                raise XgpuError("coefficient functions on space-time integrands: functions of (x, y[, z], tref) only")
+            out = out * torch.as_tensor(fn(*args), dtype=torch.float64, device=xyz.device)
+        return out.contiguous()
 
     def evaluate(self, dim, fe_mesh, elems, off, pts, ctx):
         """values at the points of the per-element rules (off, pts) on the listed elements"""
@@ -817,9 +832,9 @@ class BilinearForm:
     def Assemble(self):
         sp = self.space
         unsup = [i for i in self.integrals if getattr(i.form, "cf", None) is not None and
-                 (hasattr(sp, "timeFE") or isinstance(i.dx, FacetPatchDifferentialSymbol) or i.dx.vb == 1)]
+                 (isinstance(i.dx, FacetPatchDifferentialSymbol) or i.dx.vb == 1)]
         if unsup:
-            raise XgpuError("coefficient functions: volume cut integrals (dCut, vb=VOL) on H1 spaces only")
+            raise XgpuError("coefficient functions: volume cut integrals (dCut / dxtref / dmesh, vb=VOL) only")
         if hasattr(sp, "timeFE"):  # SpaceTimeFESpace
             from . import spacetime
             return spacetime.assemble_bilinear(self)
@@ -992,8 +1007,8 @@ class LinearForm:
 
     def Assemble(self):
         sp = self.space
-        if any(getattr(i.form, "cf", None) is not None and (hasattr(sp, "timeFE") or i.dx.vb == 1) for i in self.integrals):
-            raise XgpuError("coefficient functions: volume cut integrals (dCut, vb=VOL) on H1 spaces only")
+        if any(getattr(i.form, "cf", None) is not None and i.dx.vb == 1 for i in self.integrals):
+            raise XgpuError("coefficient functions: volume cut integrals (dCut / dxtref / dmesh, vb=VOL) only")
         if hasattr(sp, "timeFE"):  # SpaceTimeFESpace
             from . import spacetime
             return spacetime.assemble_linear(self)

@@ -188,6 +188,11 @@ class STProxy:
 
     __rmul__ = __mul__
 
+    def _st_with_cf(self, cf):
+        if not self.is_test:
+            raise XgpuError("a coefficient multiplies a whole integrand: cf * (u*v), cf * v")
+        return STLForm.from_proxy(self)._st_with_cf(cf)
+
 
 def dtref(u):
     """python/__init__.py:129-136: derivative w.r.t. the REFERENCE time interval"""
@@ -206,9 +211,21 @@ def fix_tref(u, time):
     return u._with(fixt=float(time))
 
 
+def _merge_st_cf(a, b):
+    if a is b:
+        return a
+    raise XgpuError("integrands with different coefficient functions: add them as separate integrals")
+
+
 class STForm:
-    def __init__(self, terms, space, fixt=None):
-        self.terms, self.space, self.fixt = terms, space, fixt
+    """cf: a CoefficientFunction fn(x, y[, z], tref) multiplying the whole integrand (folded into the rule weights,
+    xfem/symboliccutbfi.cpp:174-193 with the space-time rule's reference times)"""
+
+    def __init__(self, terms, space, fixt=None, cf=None):
+        self.terms, self.space, self.fixt, self.cf = terms, space, fixt, cf
+
+    def _st_with_cf(self, cf):
+        return STForm(self.terms, self.space, self.fixt, cf if self.cf is None else self.cf * cf)
 
     @staticmethod
     def from_pair(a, b):
@@ -228,7 +245,7 @@ class STForm:
         if isinstance(o, STForm):
             if o.fixt != self.fixt:
                 raise XgpuError("one integrand: one fixed reference time (split it into several integrals)")
-            return STForm(self.terms + o.terms, self.space, self.fixt)
+            return STForm(self.terms + o.terms, self.space, self.fixt, _merge_st_cf(self.cf, o.cf))
         return NotImplemented
 
     def __neg__(self):
@@ -240,8 +257,10 @@ class STForm:
     def __mul__(self, o):
         if isinstance(o, (numbers.Number, Scalar, MeshSize)):
             s = _scal(o)
-            return STForm([(a, b, c * s.c, hp + s.hpow) for a, b, c, hp in self.terms], self.space, self.fixt)
+            return STForm([(a, b, c * s.c, hp + s.hpow) for a, b, c, hp in self.terms], self.space, self.fixt, self.cf)
         if isinstance(o, (CutDifferentialSymbol, FacetPatchDifferentialSymbol)):
+            if self.cf is not None and isinstance(o, FacetPatchDifferentialSymbol):
+                raise XgpuError("coefficient functions on facet-patch integrands are not on the accelerated path")
             return Integral(self, o)
         return NotImplemented
 
@@ -251,8 +270,11 @@ class STForm:
 class STLForm:
     """terms: (op_test, coef, hpow, (e0, e1, e2, e_tref))"""
 
-    def __init__(self, terms, space, fixt=None):
-        self.terms, self.space, self.fixt = terms, space, fixt
+    def __init__(self, terms, space, fixt=None, cf=None):
+        self.terms, self.space, self.fixt, self.cf = terms, space, fixt, cf
+
+    def _st_with_cf(self, cf):
+        return STLForm(self.terms, self.space, self.fixt, cf if self.cf is None else self.cf * cf)
 
     @staticmethod
     def from_proxy(v):
@@ -268,18 +290,18 @@ class STLForm:
         if isinstance(o, STLForm):
             if o.fixt != self.fixt:
                 raise XgpuError("one integrand: one fixed reference time")
-            return STLForm(self.terms + o.terms, self.space, self.fixt)
+            return STLForm(self.terms + o.terms, self.space, self.fixt, _merge_st_cf(self.cf, o.cf))
         return NotImplemented
 
     def __mul__(self, o):
         if isinstance(o, (numbers.Number, Scalar, MeshSize)):
             s = _scal(o)
-            return STLForm([(a, c * s.c, hp + s.hpow, ex) for a, c, hp, ex in self.terms], self.space, self.fixt)
+            return STLForm([(a, c * s.c, hp + s.hpow, ex) for a, c, hp, ex in self.terms], self.space, self.fixt, self.cf)
         if isinstance(o, CoordMonomial):
             o = STMonomial(tuple(o.expo) + (0,), o.coef)
         if isinstance(o, STMonomial):
             return STLForm([(a, c * o.coef, hp, tuple(e1 + e2 for e1, e2 in zip(ex, o.expo))) for a, c, hp, ex in self.terms],
-                           self.space, self.fixt)
+                           self.space, self.fixt, self.cf)
         if isinstance(o, CutDifferentialSymbol):
             return Integral(self, o)
         return NotImplemented
@@ -416,6 +438,8 @@ def assemble_bilinear(blf):
         if not l.numel():
             continue
         off, q, tv, w = st_rule(mesh, l, integ.dx, order, integ.form.fixt, ctx)
+        if w.numel() and integ.form.cf is not None:
+            w = w * integ.form.cf.evaluate_st(dim, mesh, l, off, q, tv, ctx)
         if w.numel():
             ops.elmat_st(dim, p, kt, l, mesh.elements, mesh.points, off, q, tv, w, terms, out=m_A, accumulate=True,
                          slots=slots, ctx=ctx)
@@ -445,6 +469,8 @@ def assemble_linear(lf):
         if not l.numel():
             continue
         off, q, tv, w = st_rule(mesh, l, integ.dx, order, integ.form.fixt, ctx)
+        if w.numel() and integ.form.cf is not None:   # f(x_q, tref_q) folded into the weights (xfem/symboliccutlfi.cpp:96-118)
+            w = w * integ.form.cf.evaluate_st(dim, mesh, l, off, q, tv, ctx)
         if w.numel():
             ops.elvec_st(dim, p, kt, l, mesh.elements, mesh.points, off, q, tv, w, integ.form.terms, out=v_A, accumulate=True,
                          slots=slots, ctx=ctx)

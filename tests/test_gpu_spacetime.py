@@ -506,3 +506,51 @@ def test_spacetime_heat_equation_converges():
     e16, _ = _heat_run(16, 4, 0.5)
     assert e16 < 2e-4 * 1.0 and e16 < 0.02 * umax        # the reference's own bound for its sin solution is 2e-4
     assert e8 / e16 > 3.0                                 # second order in h (the solution is linear in time: no time error)
+
+
+# ---------------------------------------------------------------- coefficient functions on space-time integrands
+def test_spacetime_coefficient_functions_fold_into_the_rule_weights():
+    """cf(x, y, tref) * v * dCut(ls, NEG, time_order) and cf * (u*v + grad(u)*grad(v)) * dCut(...): a callable of the physical
+    coordinates and the reference time (xfem/symboliccutlfi.cpp:96-118, symboliccutbfi.cpp:174-193 on space-time rules).
+    A monomial written as a callable gives the vector of the monomial path; M(cf) applied to the dofs of g gives the vector
+    of cf * g; a non-polynomial cf is checked against the rule points themselves."""
+    mesh = xf.MakeStructured2DMesh(nx=5, ny=4, device=DEV)
+    tfe = xf.ScalarTimeFE(1)
+    ls = xf.SpaceTimeInterpolateToP1(lambda x, y, t: torch.sqrt((x - .45 - .1 * t) ** 2 + (y - .5) ** 2) - 0.31, mesh, tfe)
+    V = xf.SpaceTimeFESpace(xf.H1(mesh, order=2), tfe)
+    u, v = V.TnT()
+    dx = xf.dCut(ls, NEG, time_order=2, order=6)
+    f1 = xf.LinearForm(V)
+    f1 += (2.0 * xf.x * xf.y ** 2 * xf.tref) * v * dx
+    f1.Assemble()
+    cf = xf.CoefficientFunction(lambda x, y, t: 2.0 * x * y ** 2 * t)
+    f2 = xf.LinearForm(V)
+    f2 += cf * v * dx
+    f2.Assemble()
+    assert float(f1.vec.abs().max()) > 1e-4
+    assert float((f1.vec - f2.vec).abs().max()) < 1e-14
+    # bilinear: M(cf) g = f(cf g) for g = 1 (vertex dofs 1 at both time nodes)
+    a = xf.BilinearForm(V)
+    a += cf * (u * v) * dx
+    a.Assemble()
+    g = st_coeffs(V, lambda P, t: torch.ones_like(P[:, 0]))
+    assert float((a.mat * g - f1.vec).abs().max()) < 1e-14
+    # a non-polynomial coefficient: sum_j f_j g_j = sum_q w_q |det F| cf(x_q, t_q) g(x_q) with g = 1
+    cfe = xf.CoefficientFunction(lambda x, y, t: torch.exp(x - 0.3 * t) * torch.cos(y))
+    f3 = xf.LinearForm(V)
+    f3 += cfe * v * dx
+    f3.Assemble()
+    off, q, tv, w = ops.cutquad_st(2, None, mesh.elements, mesh.points, ls.vec, 1, NEG, 2, 6)
+    xyz, meas = ops.rule_phys(2, None, mesh.elements, mesh.points, off, q, want_meas=True)
+    want = float((w * meas * torch.exp(xyz[:, 0] - 0.3 * tv) * torch.cos(xyz[:, 1])).sum())
+    assert abs(float((f3.vec * g).sum()) - want) < 1e-13 * max(1.0, abs(want))
+    # fixed reference time: the function sees tref = the fixed time
+    f4 = xf.LinearForm(V)
+    f4 += xf.CoefficientFunction(lambda x, y, t: x * t) * xf.fix_tref(v, 1.0) * xf.dmesh(mesh)
+    f4.Assemble()
+    f5 = xf.LinearForm(V)
+    f5 += xf.x * xf.fix_tref(v, 1.0) * xf.dmesh(mesh)
+    f5.Assemble()
+    assert float((f4.vec - f5.vec).abs().max()) < 1e-14
+    with pytest.raises(xf.XgpuError):
+        cf * u                                      # a coefficient multiplies a whole integrand
