@@ -45,7 +45,7 @@ def oracle_step(dim, el_vtx, vtx_xyz, el_dofs, ndof_full, fe_order, phi, threads
     table = np.concatenate([t_neg, t_if]).astype(np.int32)
     mats = np.concatenate([m_neg, m_if])
     t0 = time.perf_counter()
-    rowptr, col = xo.graph(ndof, table)                                     # restrictedblf.cpp:142-163
+    rowptr, col = xo.graph(ndof, table, once=True)                                     # restrictedblf.cpp:142-163
     t["graph"] = time.perf_counter() - t0
     t0 = time.perf_counter()
     vals = xo.scatter(ndof, table, mats, rowptr, col, threads=threads)      # AddElementMatrix

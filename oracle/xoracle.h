@@ -179,6 +179,9 @@ int xo_batch_cut_elvecs(int dim, int fe_order, int64_t n, const int32_t* elems, 
  * (restrictedblf.cpp:142-163 -> NGSolve MatrixGraph).  Call with colidx==NULL to get nnz via rowptr. */
 int64_t xo_graph(int64_t ndof, int64_t nrows, int width, const int32_t* table,
                  int64_t* rowptr, int32_t* colidx);
+/* timing variant of xo_graph (one sort per row, one call): *colidx_out is malloc'ed, release with xo_free */
+int64_t xo_graph_once(int64_t ndof, int64_t nrows, int width, const int32_t* table, int64_t* rowptr, int32_t** colidx_out);
+void xo_free(void* p);
 /* vals += scatter of `mats` (nrows x width x width) by table rows (AddElementMatrix) */
 void xo_scatter(int64_t ndof, int64_t nrows, int width, const int32_t* table, const double* mats,
                 const int64_t* rowptr, const int32_t* colidx, double* vals);

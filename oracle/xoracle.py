@@ -321,10 +321,20 @@ def set_num_threads(n):
     lib().xo_set_num_threads(int(n))
 
 
-def graph(ndof, table):
+def graph(ndof, table, once=False):
+    """once=True: the one-call / one-sort-per-row variant the CPU baseline times (same result)"""
     t = _i32(table)
     nrows, width = t.shape
     rowptr = np.zeros(ndof + 1, np.int64)
+    if once:
+        L = lib()
+        L.xo_graph_once.restype = C.c_int64
+        L.xo_free.restype = None
+        cp = C.POINTER(C.c_int32)()
+        nnz = L.xo_graph_once(C.c_int64(ndof), C.c_int64(nrows), width, _p(t, C.c_int32), _p(rowptr, C.c_int64), C.byref(cp))
+        col = np.ctypeslib.as_array(cp, shape=(max(nnz, 1),))[:nnz].copy()
+        L.xo_free(cp)
+        return rowptr, col
     nnz = lib().xo_graph(C.c_int64(ndof), C.c_int64(nrows), width, _p(t, C.c_int32), _p(rowptr, C.c_int64), None)
     col = np.zeros(nnz, np.int32)
     lib().xo_graph(C.c_int64(ndof), C.c_int64(nrows), width, _p(t, C.c_int32), _p(rowptr, C.c_int64), _p(col, C.c_int32))

@@ -336,3 +336,22 @@ def test_spacetime_high_order_time_nodes(k):
     neg = st_integrate(m, lsn, k, NEG, k, 1)
     pos = st_integrate(m, lsn, k, POS, k, 1)
     assert abs(neg - 1 / (k + 1)) < 1e-12 and abs(pos - k / (k + 1)) < 1e-12
+
+
+def test_graph_timing_variant_equals_the_two_call_graph():
+    """xo_graph_once (one sort per row, thread-local column buffers; what bench.py's CPU arm times) == xo_graph, for every
+    thread count"""
+    rng = np.random.default_rng(0)
+    nt0 = xo.num_threads()
+    try:
+        for ndof, nr, w in [(500, 700, 10), (50, 0, 4), (64, 40, 3), (3000, 9000, 10)]:
+            t = rng.integers(0, ndof, size=(nr, w)).astype(np.int32)
+            if nr:
+                t[rng.random(t.shape) < 0.05] = -1
+            a = xo.graph(ndof, t)
+            for nt in (1, 3, 8):
+                xo.set_num_threads(nt)
+                b = xo.graph(ndof, t, once=True)
+                assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
+    finally:
+        xo.set_num_threads(nt0)
