@@ -51,6 +51,7 @@ int xgpu_set_stream(xgpu_ctx* ctx, void* cuda_stream);
  * tensor-core tiles: -1 never, 0 (default) at FE order >= 3, 1 also at order 2.  "short_blocks": cut quadrature / cut element matrices with one tile per block
  * instead of a persistent grid (for a low-priority side stream; default 0).  "csr_small": one-pass CSR, rows with few adjacent table rows on the thread-per-row
  * kernels (default 1).  "csr_warp": one-pass CSR, the other rows with at most 256 candidates on the warp-per-row kernels (default 1).
+ * "csr_warp_half": warp-per-row pattern pass, rows with at most 128 candidates on the 4-keys-per-lane sorting network (default 1; same records).
  * "csr_trips": one-pass CSR lane-group kernels, 2 = half-width lane groups with two columns per
  * lane (0 = policy).  "csr_closed_form": one-pass CSR, rows of procedural affine P2-tet batches from the closed-form barycentric
  * expressions instead of the reference tensors (default 1; equal up to rounding).  "csr_fork": one-pass CSR, the warp-per-row kernel runs on an internal second stream next to the

@@ -26,6 +26,7 @@ namespace {
 
 struct WarpPar {
   int ndof, small_na;
+  int half_keys;            // pattern pass: rows with at most 128 candidates on the 4-keys-per-lane network (option "csr_warp_half")
   int row_lo, row_hi, tick0;   // values pass: rows [row_lo, row_hi) only; the ticket counter starts at row tick0 (multiple of 32)
   const long long* adj_ptr;
   const long long* adj;
@@ -51,42 +52,129 @@ __device__ __forceinline__ void ce(unsigned& a, unsigned& b)
   a = lo; b = hi;
 }
 
-// 256 keys, position g = lane * 8 + k, ascending
-__device__ __forceinline__ void sort256(unsigned (&K)[XW_KPL], int lane)
+// bitonic sorting network over the warp: 32 * KPL keys, position g = lane * KPL + k, ascending.  Mirror stage of a merge of
+// `size` keys: g <-> g ^ (size - 1); half cleaners: g <-> g ^ stride.  Partners inside a lane are register pairs, partners in
+// another lane come by shuffle (mirror: lane ^ (size / KPL - 1), register KPL - 1 - k; cleaner: lane ^ (stride / KPL)).
+template <int KPL>
+__device__ __forceinline__ void sort_warp(unsigned (&K)[KPL], int lane)
 {
   const unsigned FULL = 0xffffffffu;
-  // blocks of 2, 4, 8: inside a lane (mirror stage, then half cleaners)
-  ce(K[0], K[1]); ce(K[2], K[3]); ce(K[4], K[5]); ce(K[6], K[7]);
-  ce(K[0], K[3]); ce(K[1], K[2]); ce(K[4], K[7]); ce(K[5], K[6]);
-  ce(K[0], K[1]); ce(K[2], K[3]); ce(K[4], K[5]); ce(K[6], K[7]);
-  ce(K[0], K[7]); ce(K[1], K[6]); ce(K[2], K[5]); ce(K[3], K[4]);
-  ce(K[0], K[2]); ce(K[1], K[3]); ce(K[4], K[6]); ce(K[5], K[7]);
-  ce(K[0], K[1]); ce(K[2], K[3]); ce(K[4], K[5]); ce(K[6], K[7]);
 #pragma unroll
-  for (int size = 16; size <= 256; size <<= 1) {
-    {  // mirror stage: g <-> g ^ (size - 1): lane ^ (size/8 - 1), register 7 - k
-      const int lm = (size >> 3) - 1;
-      const bool lower = (lane & (size >> 4)) == 0;
-      unsigned o[XW_KPL];
+  for (int size = 2; size <= 32 * KPL; size <<= 1) {
+    if (size <= KPL) {
 #pragma unroll
-      for (int k = 0; k < XW_KPL; k++) o[k] = __shfl_xor_sync(FULL, K[XW_KPL - 1 - k], lm);
+      for (int k = 0; k < KPL; k++) {
+        const int o = k ^ (size - 1);
+        if (o > k) ce(K[k], K[o]);
+      }
+    } else {
+      const int lm = size / KPL - 1;
+      const bool lower = (lane & (size / (2 * KPL))) == 0;
+      unsigned o[KPL];
 #pragma unroll
-      for (int k = 0; k < XW_KPL; k++) K[k] = lower ? min(K[k], o[k]) : max(K[k], o[k]);
+      for (int k = 0; k < KPL; k++) o[k] = __shfl_xor_sync(FULL, K[KPL - 1 - k], lm);
+#pragma unroll
+      for (int k = 0; k < KPL; k++) K[k] = lower ? min(K[k], o[k]) : max(K[k], o[k]);
     }
 #pragma unroll
-    for (int stride = size >> 2; stride >= 8; stride >>= 1) {  // half cleaners across lanes
-      const int lm = stride >> 3;
-      const bool lower = (lane & lm) == 0;
+    for (int stride = size >> 2; stride >= 1; stride >>= 1) {
+      if (stride >= KPL) {  // half cleaner across lanes
+        const int lm = stride / KPL;
+        const bool lower = (lane & lm) == 0;
 #pragma unroll
-      for (int k = 0; k < XW_KPL; k++) {
-        const unsigned o = __shfl_xor_sync(FULL, K[k], lm);
-        K[k] = lower ? min(K[k], o) : max(K[k], o);
+        for (int k = 0; k < KPL; k++) {
+          const unsigned o = __shfl_xor_sync(FULL, K[k], lm);
+          K[k] = lower ? min(K[k], o) : max(K[k], o);
+        }
+      } else {
+#pragma unroll
+        for (int k = 0; k < KPL; k++) {
+          const int o = k ^ stride;
+          if (o > k) ce(K[k], K[o]);
+        }
       }
     }
-    ce(K[0], K[4]); ce(K[1], K[5]); ce(K[2], K[6]); ce(K[3], K[7]);
-    ce(K[0], K[2]); ce(K[1], K[3]); ce(K[4], K[6]); ce(K[5], K[7]);
-    ce(K[0], K[1]); ce(K[2], K[3]); ce(K[4], K[5]); ce(K[6], K[7]);
   }
+}
+
+// one row of the pattern pass with 32 * KPL key slots (KPL = 8: up to 255 candidates; KPL = 4: up to 128 — the rows of the
+// axis-parallel edges of a Kuhn mesh have 80 — at less than half the shuffles and compare-exchanges).  The record is the same
+// for both: byte g of the index area = candidate of sorted position g, run starts are sorted positions.  returns the row length
+template <int W, int KPL>
+__device__ __forceinline__ int warp_row_pattern(const WarpPar& P, long long d, long long a, int cand, int lane,
+                                                unsigned char* rs_b, const unsigned int* rs_u, int* __restrict__ cols_s)
+{
+  const unsigned FULL = 0xffffffffu;
+  // candidates: index k * 32 + lane (neighbouring lanes read neighbouring table entries)
+  unsigned K[KPL];
+#pragma unroll
+  for (int k = 0; k < KPL; k++) {
+    const int idx = k * 32 + lane;
+    K[k] = 0xffffffffu;
+    if (idx < cand) {
+      const int t = idx / W, j = idx - t * W;
+      const long long e = __ldg(P.adj + a + t);
+      const int c = __ldg(P.bd.table[XG_ADJ_BATCH(e)] + (size_t)XG_ADJ_ROW(e) * W + j);
+      if (c >= 0) K[k] = ((unsigned)c << 8) | (unsigned)idx;
+    }
+  }
+  sort_warp<KPL>(K, lane);
+  // runs: heads (first key of an equal-column run)
+  const unsigned prevlast = __shfl_up_sync(FULL, K[KPL - 1], 1);
+  unsigned fresh = 0u;
+  int nval = 0;
+#pragma unroll
+  for (int k = 0; k < KPL; k++) {
+    if (K[k] != 0xffffffffu) {
+      nval++;
+      const unsigned pk = (k == 0) ? ((lane == 0) ? 0xffffffffu : prevlast) : K[k - 1];
+      if ((pk >> 8) != (K[k] >> 8) || (k == 0 && lane == 0)) fresh |= 1u << k;
+    }
+  }
+  const int nf = __popc(fresh);
+  int incl = nf;
+#pragma unroll
+  for (int s = 1; s < 32; s <<= 1) {
+    const int y = __shfl_up_sync(FULL, incl, s);
+    if (lane >= s) incl += y;
+  }
+  const int nr = __shfl_sync(FULL, incl, 31);
+  const int nvalid = __reduce_add_sync(FULL, nval);   // the valid keys are the first nvalid of the sorted sequence
+  unsigned slot = 0;
+  if (lane == 0) {
+    slot = atomicAdd(P.slotcount, 1u);
+    P.rowcnt[d] = nr;
+    P.bigslot[d] = (int)slot;
+  }
+  slot = __shfl_sync(FULL, slot, 0);
+  __syncwarp();
+  {
+    int q = incl - nf;  // index of the lane's first head
+#pragma unroll
+    for (int k = 0; k < KPL; k++) {
+      if ((fresh >> k) & 1u) { cols_s[q] = (int)(K[k] >> 8); rs_b[q] = (unsigned char)(lane * KPL + k); q++; }
+    }
+    if (lane == 31) rs_b[nr] = (unsigned char)nvalid;   // nr <= nvalid <= 255
+  }
+  __syncwarp();
+  if (slot < P.slotcap) {
+    unsigned char* __restrict__ rec = P.records + (size_t)slot * XW_RECB;
+    // sorted candidate indices: KPL bytes per lane, straight from the registers (KPL = 4: the upper half of the index area is
+    // not written and never read: the values pass stops at the row's number of valid keys)
+    if constexpr (KPL == 8) {
+      reinterpret_cast<uint2*>(rec)[lane] =
+          make_uint2((K[0] & 255u) | ((K[1] & 255u) << 8) | ((K[2] & 255u) << 16) | ((K[3] & 255u) << 24),
+                     (K[4] & 255u) | ((K[5] & 255u) << 8) | ((K[6] & 255u) << 16) | ((K[7] & 255u) << 24));
+    } else {
+      static_assert(KPL == 4, "record layout: 4 or 8 keys per lane");
+      reinterpret_cast<unsigned*>(rec)[lane] = (K[0] & 255u) | ((K[1] & 255u) << 8) | ((K[2] & 255u) << 16) | ((K[3] & 255u) << 24);
+    }
+    reinterpret_cast<uint2*>(rec + 256)[lane] = make_uint2(rs_u[2 * lane], rs_u[2 * lane + 1]);
+    int* __restrict__ rc = reinterpret_cast<int*>(rec + 512);
+    for (int i = lane; i < nr; i += 32) rc[i] = cols_s[i];
+  }
+  __syncwarp();
+  return nr;
 }
 
 // ---- pattern pass: sort, runs -> row length, columns and the position of every candidate, stored as the row's record
@@ -122,72 +210,10 @@ __global__ void __launch_bounds__(XW_WARPS * 32) k_rows_warp_pattern(const WarpP
       todo &= todo - 1;
       const long long d = (long long)base + src;
       const long long a = __shfl_sync(FULL, al, src);
-      const int na = __shfl_sync(FULL, nal, src);
-      const int cand = na * W;
-      // candidates: index k * 32 + lane (neighbouring lanes read neighbouring table entries)
-      unsigned K[XW_KPL];
-#pragma unroll
-      for (int k = 0; k < XW_KPL; k++) {
-        const int idx = k * 32 + lane;
-        K[k] = 0xffffffffu;
-        if (idx < cand) {
-          const int t = idx / W, j = idx - t * W;
-          const long long e = __ldg(P.adj + a + t);
-          const int c = __ldg(P.bd.table[XG_ADJ_BATCH(e)] + (size_t)XG_ADJ_ROW(e) * W + j);
-          if (c >= 0) K[k] = ((unsigned)c << 8) | (unsigned)idx;
-        }
-      }
-      sort256(K, lane);
-      // runs: heads (first key of an equal-column run)
-      const unsigned prevlast = __shfl_up_sync(FULL, K[XW_KPL - 1], 1);
-      unsigned fresh = 0u;
-      int nval = 0;
-#pragma unroll
-      for (int k = 0; k < XW_KPL; k++) {
-        if (K[k] != 0xffffffffu) {
-          nval++;
-          const unsigned pk = (k == 0) ? ((lane == 0) ? 0xffffffffu : prevlast) : K[k - 1];
-          if ((pk >> 8) != (K[k] >> 8) || (k == 0 && lane == 0)) fresh |= 1u << k;
-        }
-      }
-      const int nf = __popc(fresh);
-      int incl = nf;
-#pragma unroll
-      for (int s = 1; s < 32; s <<= 1) {
-        const int y = __shfl_up_sync(FULL, incl, s);
-        if (lane >= s) incl += y;
-      }
-      const int nr = __shfl_sync(FULL, incl, 31);
-      const int nvalid = __reduce_add_sync(FULL, nval);   // the valid keys are the first nvalid of the sorted sequence
-      unsigned slot = 0;
-      if (lane == 0) {
-        slot = atomicAdd(P.slotcount, 1u);
-        P.rowcnt[d] = nr;
-        P.bigslot[d] = (int)slot;
-      }
-      slot = __shfl_sync(FULL, slot, 0);
+      const int cand = __shfl_sync(FULL, nal, src) * W;
+      const int nr = (cand <= 128 && P.half_keys) ? warp_row_pattern<W, 4>(P, d, a, cand, lane, rs_b, rs_sm[wib], cols_s)
+                                                  : warp_row_pattern<W, XW_KPL>(P, d, a, cand, lane, rs_b, rs_sm[wib], cols_s);
       longest = max(longest, nr);
-      __syncwarp();
-      {
-        int q = incl - nf;  // index of the lane's first head
-#pragma unroll
-        for (int k = 0; k < XW_KPL; k++) {
-          if ((fresh >> k) & 1u) { cols_s[q] = (int)(K[k] >> 8); rs_b[q] = (unsigned char)(lane * XW_KPL + k); q++; }
-        }
-        if (lane == 31) rs_b[nr] = (unsigned char)nvalid;   // nr <= nvalid <= 255
-      }
-      __syncwarp();
-      if (slot < P.slotcap) {
-        unsigned char* __restrict__ rec = P.records + (size_t)slot * XW_RECB;
-        // sorted candidate indices: 8 bytes per lane, straight from the registers
-        reinterpret_cast<uint2*>(rec)[lane] =
-            make_uint2((K[0] & 255u) | ((K[1] & 255u) << 8) | ((K[2] & 255u) << 16) | ((K[3] & 255u) << 24),
-                       (K[4] & 255u) | ((K[5] & 255u) << 8) | ((K[6] & 255u) << 16) | ((K[7] & 255u) << 24));
-        reinterpret_cast<uint2*>(rec + 256)[lane] = make_uint2(rs_sm[wib][2 * lane], rs_sm[wib][2 * lane + 1]);
-        int* __restrict__ rc = reinterpret_cast<int*>(rec + 512);
-        for (int i = lane; i < nr; i += 32) rc[i] = cols_s[i];
-      }
-      __syncwarp();
     }
   }
   longest = __reduce_max_sync(FULL, longest);
@@ -349,6 +375,7 @@ int xg_rows_warp_run(xgpu_ctx* ctx, xgpu_plan* P, const BatchDev& bd, const doub
 {
   WarpPar S;
   S.ndof = (int)P->ndof; S.small_na = small_na;
+  S.half_keys = ctx->opt_csr_warp_half;
   S.row_lo = (int)row_lo; S.row_hi = (int)std::min<int64_t>(row_hi, P->ndof); S.tick0 = (int)(row_lo & ~(int64_t)31);
   if (!pattern && S.row_hi <= S.row_lo) return XGPU_OK;
   S.adj_ptr = P->adj_ptr; S.adj = P->adj; S.bd = bd; S.tref = tref;

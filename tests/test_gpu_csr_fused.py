@@ -229,3 +229,30 @@ def test_row_ranges_decline_plans_with_lane_group_rows():
     else:   # the policy took every row on the fast kernels: then the halves must agree
         ops.csr_assemble_fused(plan, [(table, m)], rows=(ndof // 2, ndof), out=part)
         assert torch.equal(part[2], full[2])
+
+
+@pytest.mark.parametrize("n,p", [(5, 2), (6, 1), (4, 3)])
+def test_half_width_sorting_network_gives_the_same_records(n, p):
+    """warp-per-row pattern pass: rows with at most 128 candidates sort 4 keys per lane ("csr_warp_half", default) — same
+    row lengths, columns and values, bit for bit, as the 8-keys-per-lane network"""
+    mesh = xf.MakeStructured3DMesh(nx=n, device=DEV)
+    V = xf.H1(mesh, order=p)
+    rng = np.random.default_rng(n * 7 + p)
+    cen = mesh.points[mesh.elements.long()].mean(dim=1)
+    elems = torch.nonzero(((cen - 0.5) ** 2).sum(dim=1) < 0.45 ** 2).reshape(-1).to(torch.int32)
+    nd = V.el_dofs.shape[1]
+    m = torch.from_numpy(rng.standard_normal((elems.numel(), nd, nd))).to(DEV)
+    ctx = ops.default_ctx()
+    out = []
+    for half in (1, 0):
+        ctx.set_option("csr_warp_half", half)
+        try:
+            dofmap, ndof, (table,), plan = ops.restrict_plan(V.el_dofs, [elems], V.ndof)
+            ops.csr_count_rows(plan)
+            out.append(ops.csr_assemble_fused(plan, [(table, m)]))
+        finally:
+            ctx.set_option("csr_warp_half", 1)
+    for x, y in zip(*out):
+        assert torch.equal(x, y)
+    ref = ops.csr_assemble(ops.csr_plan(ndof, [table]), [(table, m)])     # the two-pass path
+    assert torch.equal(out[0][0], ref[0]) and torch.equal(out[0][1], ref[1]) and torch.equal(out[0][2], ref[2])
