@@ -53,6 +53,7 @@ struct xgpu_ctx {
   int opt_short_blocks = 0;  // cut quadrature / cut element matrices: one tile per block instead of a persistent grid (a
                              // low-priority side stream then yields the SMs to the main stream block by block)
   int opt_csr_warp = 1;   // one-pass CSR: warp-per-row kernels (sorting network over the warp) for rows with <= 256 candidates
+  int opt_csr_warp_bpsm = 12;  // one-pass CSR, warp-per-row kernels: blocks per SM of the persistent grid
   int opt_csr_warp_half = 1;  // one-pass CSR, warp-per-row pattern pass: rows with <= 128 candidates sort 4 keys per lane instead of 8
   int opt_csr_trips = 0;  // one-pass CSR: columns per lane (0 policy = 1 for rows up to 32 wide; 2: half-width lane groups)
   int opt_csr_closed_form = 1;  // one-pass CSR: rows of affine P2 tets (mass + stiffness) in closed form instead of the reference tensors

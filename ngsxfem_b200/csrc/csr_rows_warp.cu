@@ -337,7 +337,8 @@ int launch_warp(xgpu_ctx* ctx, const WarpPar& S, int NC, bool pattern)
 {
   cudaStream_t st = ctx->stream;
   unsigned grid = nblk(((int64_t)S.ndof + 31) / 32, XW_WARPS);
-  if (grid > XGPU_NSM * 12) grid = XGPU_NSM * 12;
+  const unsigned bpsm = (unsigned)std::max(1, std::min(16, ctx->opt_csr_warp_bpsm));
+  if (grid > XGPU_NSM * bpsm) grid = XGPU_NSM * bpsm;  // persistent grid (row tickets); fewer blocks leave room for the forked thread-per-row kernel
   if (pattern) {
     k_rows_warp_pattern<W><<<grid, XW_WARPS * 32, 0, st>>>(S);
   } else {

@@ -207,6 +207,7 @@ extern "C" int xgpu_set_option(xgpu_ctx* ctx, const char* key, int value)
   if (std::string(key) == "cut_blocks_per_sm") { ctx->opt_cut_bpsm = value <= 1 ? 1 : 2; return XGPU_OK; }
   if (std::string(key) == "short_blocks") { ctx->opt_short_blocks = value != 0; return XGPU_OK; }
   if (std::string(key) == "csr_warp") { ctx->opt_csr_warp = value != 0; return XGPU_OK; }
+  if (std::string(key) == "csr_warp_bpsm") { ctx->opt_csr_warp_bpsm = value; return XGPU_OK; }
   if (std::string(key) == "csr_warp_half") { ctx->opt_csr_warp_half = value != 0; return XGPU_OK; }
   if (std::string(key) == "csr_closed_form") { ctx->opt_csr_closed_form = value != 0; return XGPU_OK; }
   if (std::string(key) == "csr_fork") { ctx->opt_csr_fork = value != 0; return XGPU_OK; }
