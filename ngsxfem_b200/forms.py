@@ -234,16 +234,19 @@ class FacetExpr:
 class FacetForm:
     """bilinear facet integrand: [(trial kind, trial side, test kind, test side, coef, hpow)] (xgpu_fterm)"""
 
-    def __init__(self, terms, space):
-        self.terms, self.space, self.nlset = terms, space, None
+    def __init__(self, terms, space, cf=None):
+        self.terms, self.space, self.nlset, self.cf = terms, space, None, cf
+
+    def _with_cf(self, cf):
+        """cf(x, y[, z]) * integrand: evaluated at the physical points of the cut facet rules and folded into their weights
+        (a coefficient in the integrand of T_CalcFacetMatrix, xfem/symboliccutbfi.cpp:1040-1100)"""
+        return FacetForm(self.terms, self.space, cf if self.cf is None else self.cf * cf)
 
     @staticmethod
     def of(f):
         if isinstance(f, FacetForm):
             return f
         if isinstance(f, Form):   # u*v and (u-u.Other())*(v-v.Other()) written with plain proxies
-            if f.cf is not None:
-                raise XgpuError("coefficient functions on facet integrands are not on the accelerated path")
             out = []
             for a, b, c, hp in f.terms:
                 if a == OP_ID and b == OP_ID:
@@ -252,11 +255,12 @@ class FacetForm:
                     out += [(0, 0, 0, 0, c, hp), (0, 1, 0, 0, -c, hp), (0, 0, 0, 1, -c, hp), (0, 1, 0, 1, c, hp)]
                 else:
                     raise XgpuError("facet integrands: grad(u)*grad(v) / level-set normals are not traces on a facet (menu: values, nF . grad)")
-            return FacetForm(out, f.space)
+            return FacetForm(out, f.space, f.cf)
         raise XgpuError("not a facet integrand")
 
     def __add__(self, o):
-        return FacetForm(self.terms + FacetForm.of(o).terms, self.space)
+        o = FacetForm.of(o)
+        return FacetForm(self.terms + o.terms, self.space, _merge_cf(self.cf, o.cf))
 
     __radd__ = __add__
 
@@ -269,7 +273,7 @@ class FacetForm:
     def __mul__(self, o):
         if isinstance(o, (numbers.Number, Scalar, MeshSize)):
             s = o if isinstance(o, Scalar) else (Scalar(float(o)) if isinstance(o, numbers.Number) else Scalar(1.0, o.power))
-            return FacetForm([(a, b, c_, d, c * s.c, hp + s.hpow) for a, b, c_, d, c, hp in self.terms], self.space)
+            return FacetForm([(a, b, c_, d, c * s.c, hp + s.hpow) for a, b, c_, d, c, hp in self.terms], self.space, self.cf)
         if isinstance(o, CutDifferentialSymbol):
             if not (o.skeleton or o.element_boundary):
                 raise XgpuError("facet integrands need dCut(..., skeleton=True) or dCut(..., element_boundary=True)")
@@ -320,8 +324,10 @@ class CoefficientFunction:
             return o._with_cf(self)
         if hasattr(o, "_st_with_cf"):   # space-time proxies / forms (spacetime.py): fn(x, y[, z], tref)
             return o._st_with_cf(self)
-        if isinstance(o, (FacetForm, FacetExpr)):
-            raise XgpuError("coefficient functions on facet integrands are not on the accelerated path (constants and h-powers are)")
+        if isinstance(o, FacetForm):
+            return o._with_cf(self)
+        if isinstance(o, FacetExpr):
+            raise XgpuError("a coefficient multiplies a whole integrand: cf * (jump(u) * jump(v))")
         return NotImplemented
 
     __rmul__ = __mul__
@@ -340,6 +346,22 @@ class CoefficientFunction:
             if gfs:
                 raise XgpuError("coefficient functions on space-time integrands: functions of (x, y[, z], tref) only")
             out = out * torch.as_tensor(fn(*args), dtype=torch.float64, device=xyz.device)
+        return out.contiguous()
+
+    def evaluate_facets(self, fe_mesh, facet_vtx, off, pts):
+        """cut rules on a table of facets ((dim-1)-simplices in R^dim): fn(x, y[, z]) at x = sum_k lambda_k P[v_k], the
+        barycentric weights of a rule point being (xi_0, .., xi_{dim-2}, 1 - sum xi) (reference vertex k <-> e_k, last <-> 0)"""
+        d1 = facet_vtx.shape[1]                                         # vertices per facet = dim
+        cnt = off[1:] - off[:-1]
+        f_of_pt = torch.repeat_interleave(torch.arange(facet_vtx.shape[0], device=pts.device), cnt)
+        lam = torch.cat([pts[:, :d1 - 1], 1.0 - pts[:, :d1 - 1].sum(dim=1, keepdim=True)], dim=1)
+        X = fe_mesh.points[facet_vtx.long()][f_of_pt]                    # (npts, dim, dim)
+        xyz = (lam.unsqueeze(2) * X).sum(dim=1)
+        out = torch.full((xyz.shape[0],), self.scale, dtype=torch.float64, device=xyz.device)
+        for fn, gfs in self.factors:
+            if gfs:
+                raise XgpuError("coefficient functions on facet integrands: functions of the coordinates only")
+            out = out * torch.as_tensor(fn(*[xyz[:, c] for c in range(xyz.shape[1])]), dtype=torch.float64, device=xyz.device)
         return out.contiguous()
 
     def evaluate(self, dim, fe_mesh, elems, off, pts, ctx):
@@ -634,6 +656,8 @@ class BilinearForm:
                 fel = fe[l_f.long()].contiguous()
                 off, q, w = ops.cutquad(dim - 1, None, fv, mesh.points, phi, int(dx.domain_type), order, ctx=ctx)
                 ctx.raise_on_geometry_error()
+                if form.cf is not None and w.numel():
+                    w = w * form.cf.evaluate_facets(mesh, fv, off, q)
                 mm = ops.facet_elmat(dim, p, fv, fel, mesh.elements, mesh.points, (off, q, w), form.terms, 2, ctx=ctx)
                 t_f = torch.cat([self._rows(fel[:, 0].contiguous()), self._rows(fel[:, 1].contiguous())], dim=1).contiguous()
                 tables.append(t_f); mats.append(mm)
@@ -652,6 +676,8 @@ class BilinearForm:
                 fel = torch.stack([l_e.repeat_interleave(nl), torch.full((l_e.numel() * nl,), -1, dtype=torch.int32, device=dev)], dim=1).contiguous()
                 off, q, w = ops.cutquad(dim - 1, None, fv, mesh.points, phi, int(dx.domain_type), order, ctx=ctx)
                 ctx.raise_on_geometry_error()
+                if form.cf is not None and w.numel():
+                    w = w * form.cf.evaluate_facets(mesh, fv, off, q)
                 mm = ops.facet_elmat(dim, p, fv, fel, mesh.elements, mesh.points, (off, q, w), form.terms, 1, ctx=ctx)
                 nd = sp.nd
                 tables.append(self._rows(l_e.contiguous())); mats.append(mm.reshape(l_e.numel(), nl, nd, nd).sum(dim=1).contiguous())

@@ -142,3 +142,54 @@ def test_unsupported_facet_requests_raise():
         a.Assemble()                      # .Other() on an element boundary
     with pytest.raises(xf.XgpuError):
         xf.dCut(lset, xf.NEG, skeleton=True, definedonelements=els, deformation=object())
+
+
+def test_coefficient_functions_on_cut_facet_integrands():
+    """cf(x, y) * (u*v) * dCut(lset, NEG, skeleton=True | element_boundary=True): the coefficient is tabulated at the physical
+    points of the cut facet rules and folded into their weights.  lset = x - c, cf = x, P1: 1^T A 1 = int_{facets, x < c} x ds
+    in closed form; a constant callable reproduces the constant factor bit for bit"""
+    n, c = 8, 0.41
+    mesh = make(2, n)
+    lset = xf.InterpolateToP1(lambda x, y: x - c, mesh)
+    V = xf.H1(mesh, order=1, dgjumps=True)
+    u, v = V.TnT()
+    allf = xf.BitArray(mesh.nfacet, DEV).Set()
+    alle = xf.BitArray(mesh.ne, DEV).Set()
+    cf = xf.CoefficientFunction(lambda x, y: x)
+    one = torch.ones(V.ndof, dtype=torch.float64, device=DEV)
+    a = xf.BilinearForm(V, check_unused=False)
+    a += cf * (u * v) * xf.dCut(lset, xf.NEG, skeleton=True, definedonelements=allf)
+    a.Assemble()
+    vert = sum(i / n for i in range(1, n) if i / n < c)
+    ref = (n - 1) * c * c / 2 + n * np.sqrt(2) * c * c / 2 + vert
+    assert abs(float((one * (a.mat * one)).sum()) - ref) < 1e-12 * ref
+    b = xf.BilinearForm(V, check_unused=False)
+    b += cf * (u * v) * xf.dCut(lset, xf.NEG, element_boundary=True, definedonelements=alle)
+    b.Assemble()
+    ref_eb = 2 * ref + c * c           # interior facets from both sides + bottom and top edge (the left edge has x = 0)
+    assert abs(float((one * (b.mat * one)).sum()) - ref_eb) < 1e-12 * ref_eb
+    # DG jump term with a constant written as a callable = the constant factor
+    k1 = xf.BilinearForm(V, check_unused=False)
+    k1 += xf.CoefficientFunction(lambda x, y: torch.full_like(x, 2.5)) * ((u - u.Other()) * (v - v.Other())) \
+        * xf.dCut(lset, xf.NEG, skeleton=True, definedonelements=allf)
+    k1.Assemble()
+    k2 = xf.BilinearForm(V, check_unused=False)
+    k2 += 2.5 * ((u - u.Other()) * (v - v.Other())) * xf.dCut(lset, xf.NEG, skeleton=True, definedonelements=allf)
+    k2.Assemble()
+    assert torch.equal(k1.mat.col, k2.mat.col)
+    assert float((k1.mat.vals - k2.mat.vals).abs().max()) <= 1e-15 * float(k2.mat.vals.abs().max())
+    # 3D: cf = z on the cut skeleton of lset = x - c: by symmetry of the Kuhn mesh in z the mean of z is 1/2
+    m3 = make(3, 3)
+    l3 = xf.InterpolateToP1(lambda x, y, z: x - 0.37, m3)
+    V3 = xf.H1(m3, order=1, dgjumps=True)
+    u3, v3 = V3.TnT()
+    f3 = xf.BitArray(m3.nfacet, DEV).Set()
+    o3 = torch.ones(V3.ndof, dtype=torch.float64, device=DEV)
+    az = xf.BilinearForm(V3, check_unused=False)
+    az += xf.CoefficientFunction(lambda x, y, z: z) * (u3 * v3) * xf.dCut(l3, xf.NEG, skeleton=True, definedonelements=f3)
+    az.Assemble()
+    a1 = xf.BilinearForm(V3, check_unused=False)
+    a1 += u3 * v3 * xf.dCut(l3, xf.NEG, skeleton=True, definedonelements=f3)
+    a1.Assemble()
+    tz, t1 = float((o3 * (az.mat * o3)).sum()), float((o3 * (a1.mat * o3)).sum())
+    assert t1 > 1.0 and abs(tz - 0.5 * t1) < 1e-12 * t1
