@@ -178,7 +178,7 @@ def test_coefficient_functions_on_cut_facet_integrands():
     k2.Assemble()
     assert torch.equal(k1.mat.col, k2.mat.col)
     assert float((k1.mat.vals - k2.mat.vals).abs().max()) <= 1e-15 * float(k2.mat.vals.abs().max())
-    # 3D: cf = z on the cut skeleton of lset = x - c: by symmetry of the Kuhn mesh in z the mean of z is 1/2
+    # 3D: cf = z on the cut skeleton of lset = x - c against the facet rules themselves (sum_q w_q |F| z_q)
     m3 = make(3, 3)
     l3 = xf.InterpolateToP1(lambda x, y, z: x - 0.37, m3)
     V3 = xf.H1(m3, order=1, dgjumps=True)
@@ -192,4 +192,14 @@ def test_coefficient_functions_on_cut_facet_integrands():
     a1 += u3 * v3 * xf.dCut(l3, xf.NEG, skeleton=True, definedonelements=f3)
     a1.Assemble()
     tz, t1 = float((o3 * (az.mat * o3)).sum()), float((o3 * (a1.mat * o3)).sum())
-    assert t1 > 1.0 and abs(tz - 0.5 * t1) < 1e-12 * t1
+    ents, _, fe = m3.facets()
+    inner = torch.nonzero(fe[:, 1] >= 0).reshape(-1)
+    fv = ents[inner].to(torch.int32).contiguous()
+    off, q, w = ops.cutquad(2, None, fv, m3.points, l3.vec, NEG, 2)
+    X = m3.points[fv.long()]                                            # (nf, 3, 3)
+    meas = torch.linalg.cross(X[:, 0] - X[:, 2], X[:, 1] - X[:, 2]).norm(dim=1)
+    f_of = torch.repeat_interleave(torch.arange(fv.shape[0], device=DEV), off[1:] - off[:-1])
+    lam = torch.stack([q[:, 0], q[:, 1], 1.0 - q[:, 0] - q[:, 1]], dim=1)
+    zq = (lam * X[f_of][:, :, 2]).sum(dim=1)
+    want1, wantz = float((w * meas[f_of]).sum()), float((w * meas[f_of] * zq).sum())
+    assert t1 > 1.0 and abs(t1 - want1) < 1e-12 * t1 and abs(tz - wantz) < 1e-12 * t1
