@@ -31,7 +31,7 @@ extern "C" int xgpu_facetpatch(xgpu_ctx* ctx, int dim, int fe_order, int64_t n, 
   const int Np = (2 * nd + 1) & ~1, PS = Np + 1;
   const DefDev df = xg_defdev(ctx, dim);
   if (df.order > 0 && dim < 2) return xgpu_fail(ctx, XGPU_ERR_UNSUPPORTED, "xgpu_facetpatch: deformation needs dim >= 2");
-  const size_t extra = df.order > 0 ? (size_t)(2 * XG_DEFS + 32 + 7 * 2 * r->n) : 0;  // doubles per warp
+  const size_t extra = df.order > 0 ? (size_t)(2 * XG_DEFS + 32 + 2 * FP_GEO + 7 * 2 * r->n) : 0;  // doubles per warp
   int CH = 32;  // staged points per pass: the kernels are register limited to 2 blocks / SM, so up to ~100 KB per block is free
   while (CH > 4 && (size_t)4 * (CH * PS + extra) * sizeof(double) > 100 * 1024) CH >>= 1;
   const size_t sm = (size_t)4 * (CH * PS + extra) * sizeof(double);

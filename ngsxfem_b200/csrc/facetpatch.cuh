@@ -103,6 +103,40 @@ __device__ __forceinline__ void trafo_eval(const double (*vx)[3], const double* 
   xg_def_apply<D>(def_order, v, xh, defs, F, x);
 }
 
+// Geometry of the two elements of a facet for the deformed path, per warp in shared memory: the data are the same for all
+// lanes, and a `from` / `to` element chosen by POINTER keeps one copy of the mapping code (each inlined evaluation of a
+// deformed transformation carries the shape functions of all deformation orders: with the elements in registers and the
+// forward / backward cases as two branches the kernels were 20 000 - 25 000 SASS instructions and instruction-fetch bound,
+// profiles/r02_notes.md).  Layout in doubles: vertices [4][3], affine Jacobian [9], vertex numbers (4 ints).
+constexpr int FP_GEO = 24;
+
+template <int D>
+struct FpEl {
+  const double (*vx)[3];
+  const double* F;
+  const int* v;
+  const double* defs;
+};
+
+template <int D>
+__device__ __forceinline__ FpEl<D> fp_el(const double* geo, const double* defs)
+{
+  return FpEl<D>{reinterpret_cast<const double (*)[3]>(geo), geo + 12, reinterpret_cast<const int*>(geo + 21), defs};
+}
+
+template <int D>
+__device__ __forceinline__ void fp_store_geo(double* geo, const double (*vx)[3], const double* F, const int* v)
+{
+#pragma unroll
+  for (int k = 0; k < D + 1; k++) {
+#pragma unroll
+    for (int c = 0; c < 3; c++) geo[3 * k + c] = vx[k][c];
+    reinterpret_cast<int*>(geo + 21)[k] = v[k];
+  }
+#pragma unroll
+  for (int k = 0; k < D * D; k++) geo[12 + k] = F[k];
+}
+
 // MapPatchIntegrationPoint<D> (symboliccutbfi.cpp:1747-1846, non space-time) on deformed elements:
 // (xf, wf) on the `from` element -> xt, wt on the `to` element; affine start value, Newton with the
 // reference's constants (ngsxstd.cpp:66-82: eps 1e-12, 15 iterations, max distance 10), low-order
@@ -110,19 +144,26 @@ __device__ __forceinline__ void trafo_eval(const double (*vx)[3], const double* 
 // the point independent part of the mapping INTO element t: the affine start value uses the images of the
 // reference vertices (out: pc[0..2] = a0, pc[3..3+D*D) = A^{-1}, pc[12] = |det A|)
 template <int D>
-__device__ __forceinline__ void patch_consts(const double (*vxt)[3], const double* Ft, const int* vt, const double* defs_t,
-                                             int def_order, double* pc)
+__device__ __forceinline__ void patch_consts(const FpEl<D>& t, int def_order, double* pc)
 {
   double F[D * D], a0[3] = {0, 0, 0}, A[D * D], Ainv[D * D];
-  const double zero[3] = {0, 0, 0};
-  trafo_eval<D>(vxt, Ft, vt, def_order, defs_t, zero, F, a0);
 #pragma unroll
-  for (int d = 0; d < D; d++) {
-    double e[3] = {0, 0, 0}, ai[3] = {0, 0, 0};
-    e[d] = 1.0;
-    trafo_eval<D>(vxt, Ft, vt, def_order, defs_t, e, F, ai);
+  for (int k = 0; k < D * D; k++) A[k] = 0.0;
+#pragma unroll 1
+  for (int d = -1; d < D; d++) {  // the origin, then the unit points: ONE inlined evaluation
+    double e[3], ai[3] = {0, 0, 0};
+    e[0] = (d == 0) ? 1.0 : 0.0; e[1] = (d == 1) ? 1.0 : 0.0; e[2] = (d == 2) ? 1.0 : 0.0;
+    trafo_eval<D>(t.vx, t.F, t.v, def_order, t.defs, e, F, ai);
+    if (d < 0) {
+      a0[0] = ai[0]; a0[1] = ai[1]; a0[2] = ai[2];
+    } else {
 #pragma unroll
-    for (int i = 0; i < D; i++) A[i * D + d] = ai[i] - a0[i];
+      for (int c = 0; c < D; c++)
+        if (d == c) {
+#pragma unroll
+          for (int i = 0; i < D; i++) A[i * D + c] = ai[i] - a0[i];
+        }
+    }
   }
   const double w00 = fabs(xg_inv<D>(A, Ainv));
   pc[0] = a0[0]; pc[1] = a0[1]; pc[2] = a0[2];
@@ -132,12 +173,11 @@ __device__ __forceinline__ void patch_consts(const double (*vxt)[3], const doubl
 }
 
 template <int D>
-__device__ __forceinline__ void map_patch_def(const double (*vxf)[3], const double* Ff, const int* vf, const double* defs_f,
-                                              const double (*vxt)[3], const double* Ft, const int* vt, const double* defs_t,
-                                              int def_order, const double* pc, const double* xf, double wf, double* xt, double* wt)
+__device__ __forceinline__ void map_patch_def(const FpEl<D>& ef, const FpEl<D>& et, int def_order, const double* pc,
+                                              const double* xf, double wf, double* xt, double* wt)
 {
   double F[D * D], Fi[D * D], vec[3] = {0, 0, 0};
-  trafo_eval<D>(vxf, Ff, vf, def_order, defs_f, xf, F, vec);
+  trafo_eval<D>(ef.vx, ef.F, ef.v, def_order, ef.defs, xf, F, vec);
   const double detf = xg_inv<D>(F, Fi);
   const double h = sqrt(detf);
   const double mipw = wf * fabs(detf);
@@ -154,9 +194,10 @@ __device__ __forceinline__ void map_patch_def(const double (*vxf)[3], const doub
   }
   int its = 0;
   double w = 0.0, diffn = 0.0;
+#pragma unroll 1
   while (its == 0 || (diffn > 1e-12 * h && its < 15)) {
     double xm[3] = {0, 0, 0}, diff[3];
-    trafo_eval<D>(vxt, Ft, vt, def_order, defs_t, x0, F, xm);
+    trafo_eval<D>(et.vx, et.F, et.v, def_order, et.defs, x0, F, xm);
     const double det = xg_inv<D>(F, Fi);
     diffn = 0.0;
 #pragma unroll
@@ -183,29 +224,35 @@ __device__ __forceinline__ void map_patch_def(const double (*vxf)[3], const doub
   }
 }
 
-// all patch points of one facet on deformed elements: (x1, x2, weight) -> mp[7 l ..], once per facet, all lanes busy
+// all patch points of one facet on deformed elements: (x1, x2, weight) -> mp[7 l ..], once per facet, all lanes busy.
+// geo: the two geometry blocks (element 1, element 2); a point of element 1's rule is mapped into element 2 and vice versa
+// through the same code, the elements chosen by pointer
 template <int D>
 __device__ __forceinline__ void fp_map_points(int lane, int np, const double* __restrict__ rp, const double* __restrict__ rw,
-                                              const double (*vx1)[3], const double* F1, const int* v1, const double* defs1,
-                                              const double (*vx2)[3], const double* F2, const int* v2, const double* defs2,
+                                              const double* geo, const double* defs1, const double* defs2,
                                               int def_order, double coef, int hpow, double scale, const double* sh1,
                                               const double* sh2, double* pcs, double* mp)
 {
-  if (lane == 0) patch_consts<D>(vx2, F2, v2, defs2, def_order, pcs);
-  if (lane == 1) patch_consts<D>(vx1, F1, v1, defs1, def_order, pcs + 16);
+  if (lane < 2)  // lane 0: constants of the map INTO element 2, lane 1: into element 1
+    patch_consts<D>(fp_el<D>(geo + (lane == 0 ? FP_GEO : 0), lane == 0 ? defs2 : defs1), def_order, pcs + 16 * lane);
   __syncwarp();
+  const FpEl<D> e1 = fp_el<D>(geo, defs1);
+#pragma unroll 1
   for (int l = lane; l < 2 * np; l += 32) {
-    double x1[3], x2[3], x[3], w1, wd;
-    if (l < np) {
-      fp_point<D>(rp, rw, l, scale, sh1, x1, &w1);
-      map_patch_def<D>(vx1, F1, v1, defs1, vx2, F2, v2, defs2, def_order, pcs, x1, w1, x2, &wd);
-    } else {
-      double w2;
-      fp_point<D>(rp, rw, l - np, scale, sh2, x2, &w2);
-      map_patch_def<D>(vx2, F2, v2, defs2, vx1, F1, v1, defs1, def_order, pcs + 16, x2, w2, x1, &w1);
-    }
+    const bool fwd = l < np;
+    const FpEl<D> ef = fp_el<D>(geo + (fwd ? 0 : FP_GEO), fwd ? defs1 : defs2);
+    const FpEl<D> et = fp_el<D>(geo + (fwd ? FP_GEO : 0), fwd ? defs2 : defs1);
+    double shf[3], xf[3], xt[3], wf, wt;
+#pragma unroll
+    for (int c = 0; c < 3; c++) shf[c] = fwd ? sh1[c] : sh2[c];
+    fp_point<D>(rp, rw, fwd ? l : l - np, scale, shf, xf, &wf);
+    map_patch_def<D>(ef, et, def_order, pcs + (fwd ? 0 : 16), xf, wf, xt, &wt);
+    double x1[3], x2[3], x[3];
+#pragma unroll
+    for (int c = 0; c < 3; c++) { x1[c] = fwd ? xf[c] : xt[c]; x2[c] = fwd ? xt[c] : xf[c]; }
+    const double w1 = fwd ? wf : wt;
     double Fq[D * D], Fiq[D * D];
-    trafo_eval<D>(vx1, F1, v1, def_order, defs1, x1, Fq, x);
+    trafo_eval<D>(e1.vx, e1.F, e1.v, def_order, e1.defs, x1, Fq, x);
     const double measq = fabs(xg_inv<D>(Fq, Fiq));
     const double hq = xg_mesh_size<D>(measq);
     double hpq = 1.0;
@@ -231,11 +278,12 @@ __global__ void __launch_bounds__(128) k_facetpatch(
   const int N = 2 * nd, Np = (N + 1) & ~1, nbk = Np >> 1, nblocks = nbk * nbk;
   const int PS = Np + 1;
   const int npatch_ = 2 * np;
-  double* Bw = smem + (size_t)wib * (CH * PS + (DEF ? 2 * XG_DEFS + 32 + 7 * npatch_ : 0));
+  double* Bw = smem + (size_t)wib * (CH * PS + (DEF ? 2 * XG_DEFS + 32 + 2 * FP_GEO + 7 * npatch_ : 0));
   double* defs1 = Bw + (size_t)CH * PS;
   double* defs2 = defs1 + XG_DEFS;
   double* pcs = defs2 + XG_DEFS;   // mapping constants: [0..15] into element 2, [16..31] into element 1
-  double* mp = pcs + 32;           // mapped patch points: x1[3], x2[3], weight  (DEF: computed ONCE per facet)
+  double* geo = pcs + 32;          // geometry blocks of the two elements (deformed path)
+  double* mp = geo + 2 * FP_GEO;   // mapped patch points: x1[3], x2[3], weight  (DEF: computed ONCE per facet)
   const int64_t warp0 = (int64_t)blockIdx.x * (blockDim.x >> 5) + wib;
   const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
   const int npatch = 2 * np;
@@ -256,10 +304,11 @@ __global__ void __launch_bounds__(128) k_facetpatch(
     fp_shift<D>(v2, v1, scale, sh2);
     if (DEF) {
       __syncwarp();
+      if (lane == 0) { fp_store_geo<D>(geo, vx1, F1, v1); fp_store_geo<D>(geo + FP_GEO, vx2, F2, v2); }
       xg_def_gather<D>(df, e1, lane, defs1);
       xg_def_gather<D>(df, e2, lane, defs2);
       __syncwarp();
-      fp_map_points<D>(lane, np, rp, rw, vx1, F1, v1, defs1, vx2, F2, v2, defs2, df.order, coef, hpow, scale, sh1, sh2, pcs, mp);
+      fp_map_points<D>(lane, np, rp, rw, geo, defs1, defs2, df.order, coef, hpow, scale, sh1, sh2, pcs, mp);
     }
     const double h = (D == 1) ? meas1 : ((D == 2) ? sqrt(meas1) : cbrt(meas1));
     double hp = 1.0;
@@ -364,11 +413,12 @@ __global__ void __launch_bounds__(128) k_facetpatch_dmma(
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const int fr = lane >> 2, fc = lane & 3;
   const int npatch = 2 * np, npad = (npatch + 3) & ~3;
-  double* Bw = smem + (size_t)wib * (CH * PS + (DEF ? 2 * XG_DEFS + 32 + 7 * npatch : 0));
+  double* Bw = smem + (size_t)wib * (CH * PS + (DEF ? 2 * XG_DEFS + 32 + 2 * FP_GEO + 7 * npatch : 0));
   double* defs1 = Bw + (size_t)CH * PS;
   double* defs2 = defs1 + XG_DEFS;
   double* pcs = defs2 + XG_DEFS;
-  double* mp = pcs + 32;
+  double* geo = pcs + 32;
+  double* mp = geo + 2 * FP_GEO;
   const int64_t warp0 = (int64_t)blockIdx.x * (blockDim.x >> 5) + wib;
   const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
   for (int64_t f = warp0; f < n; f += nwarps) {
@@ -388,10 +438,11 @@ __global__ void __launch_bounds__(128) k_facetpatch_dmma(
     fp_shift<D>(v2, v1, scale, sh2);
     if (DEF) {
       __syncwarp();
+      if (lane == 0) { fp_store_geo<D>(geo, vx1, F1, v1); fp_store_geo<D>(geo + FP_GEO, vx2, F2, v2); }
       xg_def_gather<D>(df, e1, lane, defs1);
       xg_def_gather<D>(df, e2, lane, defs2);
       __syncwarp();
-      fp_map_points<D>(lane, np, rp, rw, vx1, F1, v1, defs1, vx2, F2, v2, defs2, df.order, coef, hpow, scale, sh1, sh2, pcs, mp);
+      fp_map_points<D>(lane, np, rp, rw, geo, defs1, defs2, df.order, coef, hpow, scale, sh1, sh2, pcs, mp);
     }
     const double h = xg_mesh_size<D>(meas1);
     double hp = 1.0;
@@ -472,7 +523,7 @@ int launch_fp_dmma(xgpu_ctx* ctx, int64_t n, const int32_t* facets, const int32_
 {
   using G = FpGeom<D, P>;
   const DefDev df = xg_defdev(ctx, D);
-  const size_t extra = df.order > 0 ? (size_t)(2 * XG_DEFS + 32 + 7 * 2 * r->n) : 0;  // doubles per warp
+  const size_t extra = df.order > 0 ? (size_t)(2 * XG_DEFS + 32 + 2 * FP_GEO + 7 * 2 * r->n) : 0;  // doubles per warp
   int CH = 32;
   while (CH > 8 && (size_t)4 * (CH * G::PS + extra) * sizeof(double) > 110 * 1024) CH >>= 1;
   const size_t sm = (size_t)4 * (CH * G::PS + extra) * sizeof(double);
