@@ -93,14 +93,20 @@ __device__ __forceinline__ void fp_point(const double* __restrict__ rp, const do
 }
 
 // x(xhat) and F(xhat) of a (deformed) element: affine part from the vertices + deformation
-template <int D>
+// DO > 0: the deformation order at compile time (one set of shape functions per inlined copy instead of all four)
+template <int D, int DO = 0>
 __device__ __forceinline__ void trafo_eval(const double (*vx)[3], const double* Faff, const int* v, int def_order,
                                            const double* defs, const double* xh, double* F, double* x)
 {
   map_fwd<D>(vx, xh, x);
 #pragma unroll
   for (int k = 0; k < D * D; k++) F[k] = Faff[k];
-  xg_def_apply<D>(def_order, v, xh, defs, F, x);
+  if constexpr (DO > 0) {
+    DefJacSink<D> sink{defs, F, x};
+    xg_h1_shapes<D, DO>(v, xh, sink);
+  } else {
+    xg_def_apply<D>(def_order, v, xh, defs, F, x);
+  }
 }
 
 // Geometry of the two elements of a facet for the deformed path, per warp in shared memory: the data are the same for all
@@ -143,7 +149,7 @@ __device__ __forceinline__ void fp_store_geo(double* geo, const double (*vx)[3],
 // guess kept on failure.
 // the point independent part of the mapping INTO element t: the affine start value uses the images of the
 // reference vertices (out: pc[0..2] = a0, pc[3..3+D*D) = A^{-1}, pc[12] = |det A|)
-template <int D>
+template <int D, int DO>
 __device__ __forceinline__ void patch_consts(const FpEl<D>& t, int def_order, double* pc)
 {
   double F[D * D], a0[3] = {0, 0, 0}, A[D * D], Ainv[D * D];
@@ -153,7 +159,7 @@ __device__ __forceinline__ void patch_consts(const FpEl<D>& t, int def_order, do
   for (int d = -1; d < D; d++) {  // the origin, then the unit points: ONE inlined evaluation
     double e[3], ai[3] = {0, 0, 0};
     e[0] = (d == 0) ? 1.0 : 0.0; e[1] = (d == 1) ? 1.0 : 0.0; e[2] = (d == 2) ? 1.0 : 0.0;
-    trafo_eval<D>(t.vx, t.F, t.v, def_order, t.defs, e, F, ai);
+    trafo_eval<D, DO>(t.vx, t.F, t.v, def_order, t.defs, e, F, ai);
     if (d < 0) {
       a0[0] = ai[0]; a0[1] = ai[1]; a0[2] = ai[2];
     } else {
@@ -172,12 +178,12 @@ __device__ __forceinline__ void patch_consts(const FpEl<D>& t, int def_order, do
   pc[12] = w00;
 }
 
-template <int D>
+template <int D, int DO>
 __device__ __forceinline__ void map_patch_def(const FpEl<D>& ef, const FpEl<D>& et, int def_order, const double* pc,
                                               const double* xf, double wf, double* xt, double* wt)
 {
   double F[D * D], Fi[D * D], vec[3] = {0, 0, 0};
-  trafo_eval<D>(ef.vx, ef.F, ef.v, def_order, ef.defs, xf, F, vec);
+  trafo_eval<D, DO>(ef.vx, ef.F, ef.v, def_order, ef.defs, xf, F, vec);
   const double detf = xg_inv<D>(F, Fi);
   const double h = sqrt(detf);
   const double mipw = wf * fabs(detf);
@@ -197,7 +203,7 @@ __device__ __forceinline__ void map_patch_def(const FpEl<D>& ef, const FpEl<D>& 
 #pragma unroll 1
   while (its == 0 || (diffn > 1e-12 * h && its < 15)) {
     double xm[3] = {0, 0, 0}, diff[3];
-    trafo_eval<D>(et.vx, et.F, et.v, def_order, et.defs, x0, F, xm);
+    trafo_eval<D, DO>(et.vx, et.F, et.v, def_order, et.defs, x0, F, xm);
     const double det = xg_inv<D>(F, Fi);
     diffn = 0.0;
 #pragma unroll
@@ -227,14 +233,14 @@ __device__ __forceinline__ void map_patch_def(const FpEl<D>& ef, const FpEl<D>& 
 // all patch points of one facet on deformed elements: (x1, x2, weight) -> mp[7 l ..], once per facet, all lanes busy.
 // geo: the two geometry blocks (element 1, element 2); a point of element 1's rule is mapped into element 2 and vice versa
 // through the same code, the elements chosen by pointer
-template <int D>
+template <int D, int DO>
 __device__ __forceinline__ void fp_map_points(int lane, int np, const double* __restrict__ rp, const double* __restrict__ rw,
                                               const double* geo, const double* defs1, const double* defs2,
                                               int def_order, double coef, int hpow, double scale, const double* sh1,
                                               const double* sh2, double* pcs, double* mp)
 {
   if (lane < 2)  // lane 0: constants of the map INTO element 2, lane 1: into element 1
-    patch_consts<D>(fp_el<D>(geo + (lane == 0 ? FP_GEO : 0), lane == 0 ? defs2 : defs1), def_order, pcs + 16 * lane);
+    patch_consts<D, DO>(fp_el<D>(geo + (lane == 0 ? FP_GEO : 0), lane == 0 ? defs2 : defs1), def_order, pcs + 16 * lane);
   __syncwarp();
   const FpEl<D> e1 = fp_el<D>(geo, defs1);
 #pragma unroll 1
@@ -246,13 +252,13 @@ __device__ __forceinline__ void fp_map_points(int lane, int np, const double* __
 #pragma unroll
     for (int c = 0; c < 3; c++) shf[c] = fwd ? sh1[c] : sh2[c];
     fp_point<D>(rp, rw, fwd ? l : l - np, scale, shf, xf, &wf);
-    map_patch_def<D>(ef, et, def_order, pcs + (fwd ? 0 : 16), xf, wf, xt, &wt);
+    map_patch_def<D, DO>(ef, et, def_order, pcs + (fwd ? 0 : 16), xf, wf, xt, &wt);
     double x1[3], x2[3], x[3];
 #pragma unroll
     for (int c = 0; c < 3; c++) { x1[c] = fwd ? xf[c] : xt[c]; x2[c] = fwd ? xt[c] : xf[c]; }
     const double w1 = fwd ? wf : wt;
     double Fq[D * D], Fiq[D * D];
-    trafo_eval<D>(e1.vx, e1.F, e1.v, def_order, e1.defs, x1, Fq, x);
+    trafo_eval<D, DO>(e1.vx, e1.F, e1.v, def_order, e1.defs, x1, Fq, x);
     const double measq = fabs(xg_inv<D>(Fq, Fiq));
     const double hq = xg_mesh_size<D>(measq);
     double hpq = 1.0;
@@ -308,7 +314,10 @@ __global__ void __launch_bounds__(128) k_facetpatch(
       xg_def_gather<D>(df, e1, lane, defs1);
       xg_def_gather<D>(df, e2, lane, defs2);
       __syncwarp();
-      fp_map_points<D>(lane, np, rp, rw, geo, defs1, defs2, df.order, coef, hpow, scale, sh1, sh2, pcs, mp);
+      // the usual case (deformation order = 2 or 1 on these kernels' orders) with the order at compile time
+      if (df.order == 2) fp_map_points<D, 2>(lane, np, rp, rw, geo, defs1, defs2, df.order, coef, hpow, scale, sh1, sh2, pcs, mp);
+      else if (df.order == 1) fp_map_points<D, 1>(lane, np, rp, rw, geo, defs1, defs2, df.order, coef, hpow, scale, sh1, sh2, pcs, mp);
+      else fp_map_points<D, 0>(lane, np, rp, rw, geo, defs1, defs2, df.order, coef, hpow, scale, sh1, sh2, pcs, mp);
     }
     const double h = (D == 1) ? meas1 : ((D == 2) ? sqrt(meas1) : cbrt(meas1));
     double hp = 1.0;
@@ -442,7 +451,9 @@ __global__ void __launch_bounds__(128) k_facetpatch_dmma(
       xg_def_gather<D>(df, e1, lane, defs1);
       xg_def_gather<D>(df, e2, lane, defs2);
       __syncwarp();
-      fp_map_points<D>(lane, np, rp, rw, geo, defs1, defs2, df.order, coef, hpow, scale, sh1, sh2, pcs, mp);
+      // the usual case (deformation order = FE order) with the order at compile time
+      if (df.order == P) fp_map_points<D, P>(lane, np, rp, rw, geo, defs1, defs2, df.order, coef, hpow, scale, sh1, sh2, pcs, mp);
+      else fp_map_points<D, 0>(lane, np, rp, rw, geo, defs1, defs2, df.order, coef, hpow, scale, sh1, sh2, pcs, mp);
     }
     const double h = xg_mesh_size<D>(meas1);
     double hp = 1.0;
