@@ -178,55 +178,84 @@ __device__ __forceinline__ void patch_consts(const FpEl<D>& t, int def_order, do
   pc[12] = w00;
 }
 
+// One patch point on deformed elements as a state machine around ONE inlined evaluation of the deformed transformation:
+// stage 0 the point on the `from` element (physical point, measure), stage 1 Newton on the `to` element
+// (MapPatchIntegrationPoint), stage 2 the measure at the point's coordinates on element 1.  The arithmetic and its order are
+// those of the three separate evaluations; the code of the shape functions exists once.
+// out: x1 / x2 = the point in the reference coordinates of element 1 / 2, w1 = its weight on element 1, measq = |det F_1(x1)|
 template <int D, int DO>
-__device__ __forceinline__ void map_patch_def(const FpEl<D>& ef, const FpEl<D>& et, int def_order, const double* pc,
-                                              const double* xf, double wf, double* xt, double* wt)
+__device__ __forceinline__ void fp_map_one(const FpEl<D>& ef, const FpEl<D>& et, const FpEl<D>& e1, bool fwd, int def_order,
+                                           const double* pc, const double* xf, double wf, double* x1, double* x2, double* w1,
+                                           double* measq)
 {
   double F[D * D], Fi[D * D], vec[3] = {0, 0, 0};
-  trafo_eval<D, DO>(ef.vx, ef.F, ef.v, def_order, ef.defs, xf, F, vec);
-  const double detf = xg_inv<D>(F, Fi);
-  const double h = sqrt(detf);
-  const double mipw = wf * fabs(detf);
   double a0[3] = {pc[0], pc[1], pc[2]}, Ainv[D * D], x00[3] = {0, 0, 0}, x0[3] = {0, 0, 0};
 #pragma unroll
   for (int k = 0; k < D * D; k++) Ainv[k] = pc[3 + k];
   const double w00 = pc[12];
+  double h = 0.0, mipw = 0.0, w = 0.0, diffn = 0.0;
+  int its = 0, stage = 0;
 #pragma unroll
-  for (int i = 0; i < D; i++) {
-    double t = 0.0;
-#pragma unroll
-    for (int j = 0; j < D; j++) t += Ainv[i * D + j] * (vec[j] - a0[j]);
-    x00[i] = t; x0[i] = t;
-  }
-  int its = 0;
-  double w = 0.0, diffn = 0.0;
+  for (int c = 0; c < 3; c++) { x1[c] = 0.0; x2[c] = 0.0; }
 #pragma unroll 1
-  while (its == 0 || (diffn > 1e-12 * h && its < 15)) {
-    double xm[3] = {0, 0, 0}, diff[3];
-    trafo_eval<D, DO>(et.vx, et.F, et.v, def_order, et.defs, x0, F, xm);
+  for (;;) {
+    FpEl<D> el;
+    el.vx = (stage == 0) ? ef.vx : ((stage == 1) ? et.vx : e1.vx);
+    el.F = (stage == 0) ? ef.F : ((stage == 1) ? et.F : e1.F);
+    el.v = (stage == 0) ? ef.v : ((stage == 1) ? et.v : e1.v);
+    el.defs = (stage == 0) ? ef.defs : ((stage == 1) ? et.defs : e1.defs);
+    double xe[3], xm[3] = {0, 0, 0};
+#pragma unroll
+    for (int c = 0; c < 3; c++) xe[c] = (stage == 0) ? xf[c] : ((stage == 1) ? x0[c] : x1[c]);
+    trafo_eval<D, DO>(el.vx, el.F, el.v, def_order, el.defs, xe, F, xm);
     const double det = xg_inv<D>(F, Fi);
-    diffn = 0.0;
+    if (stage == 0) {
+      vec[0] = xm[0]; vec[1] = xm[1]; vec[2] = xm[2];
+      h = sqrt(det);
+      mipw = wf * fabs(det);
 #pragma unroll
-    for (int i = 0; i < D; i++) { diff[i] = vec[i] - xm[i]; diffn += diff[i] * diff[i]; }
-    diffn = sqrt(diffn);
+      for (int i = 0; i < D; i++) {
+        double t = 0.0;
 #pragma unroll
-    for (int i = 0; i < D; i++) {
-      double u = 0.0;
+        for (int j = 0; j < D; j++) t += Ainv[i * D + j] * (vec[j] - a0[j]);
+        x00[i] = t; x0[i] = t;
+      }
+      stage = 1;
+    } else if (stage == 1) {
+      double diff[3];
+      diffn = 0.0;
 #pragma unroll
-      for (int j = 0; j < D; j++) u += Fi[i * D + j] * diff[j];
-      x0[i] += u;
+      for (int i = 0; i < D; i++) { diff[i] = vec[i] - xm[i]; diffn += diff[i] * diff[i]; }
+      diffn = sqrt(diffn);
+#pragma unroll
+      for (int i = 0; i < D; i++) {
+        double u = 0.0;
+#pragma unroll
+        for (int j = 0; j < D; j++) u += Fi[i * D + j] * diff[j];
+        x0[i] += u;
+      }
+      its++;
+      w = fabs(det);
+      if (!(diffn > 1e-12 * h && its < 15)) {  // the reference's loop ends here (ngsxstd.cpp:66-82: eps 1e-12, 15 iterations)
+        double dist = 0.0;
+#pragma unroll
+        for (int i = 0; i < D; i++) dist += (x0[i] - x00[i]) * (x0[i] - x00[i]);
+        dist = sqrt(dist);
+        const bool failed = its >= 15 || diffn > 1e-12 * h || dist > 10.0;  // low-order guess kept on failure (max distance 10)
+        const double wt = failed ? mipw / w00 : mipw / w;
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+          const double xtc = failed ? x00[c] : x0[c];
+          x1[c] = fwd ? xf[c] : xtc;
+          x2[c] = fwd ? xtc : xf[c];
+        }
+        *w1 = fwd ? wf : wt;
+        stage = 2;
+      }
+    } else {
+      *measq = fabs(det);
+      break;
     }
-    its++;
-    w = fabs(det);
-  }
-  double dist = 0.0;
-#pragma unroll
-  for (int i = 0; i < D; i++) dist += (x0[i] - x00[i]) * (x0[i] - x00[i]);
-  dist = sqrt(dist);
-  if (its >= 15 || diffn > 1e-12 * h || dist > 10.0) {
-    xt[0] = x00[0]; xt[1] = x00[1]; xt[2] = x00[2]; *wt = mipw / w00;
-  } else {
-    xt[0] = x0[0]; xt[1] = x0[1]; xt[2] = x0[2]; *wt = mipw / w;
   }
 }
 
@@ -248,18 +277,12 @@ __device__ __forceinline__ void fp_map_points(int lane, int np, const double* __
     const bool fwd = l < np;
     const FpEl<D> ef = fp_el<D>(geo + (fwd ? 0 : FP_GEO), fwd ? defs1 : defs2);
     const FpEl<D> et = fp_el<D>(geo + (fwd ? FP_GEO : 0), fwd ? defs2 : defs1);
-    double shf[3], xf[3], xt[3], wf, wt;
+    double shf[3], xf[3], wf;
 #pragma unroll
     for (int c = 0; c < 3; c++) shf[c] = fwd ? sh1[c] : sh2[c];
     fp_point<D>(rp, rw, fwd ? l : l - np, scale, shf, xf, &wf);
-    map_patch_def<D, DO>(ef, et, def_order, pcs + (fwd ? 0 : 16), xf, wf, xt, &wt);
-    double x1[3], x2[3], x[3];
-#pragma unroll
-    for (int c = 0; c < 3; c++) { x1[c] = fwd ? xf[c] : xt[c]; x2[c] = fwd ? xt[c] : xf[c]; }
-    const double w1 = fwd ? wf : wt;
-    double Fq[D * D], Fiq[D * D];
-    trafo_eval<D, DO>(e1.vx, e1.F, e1.v, def_order, e1.defs, x1, Fq, x);
-    const double measq = fabs(xg_inv<D>(Fq, Fiq));
+    double x1[3], x2[3], w1, measq;
+    fp_map_one<D, DO>(ef, et, e1, fwd, def_order, pcs + (fwd ? 0 : 16), xf, wf, x1, x2, &w1, &measq);
     const double hq = xg_mesh_size<D>(measq);
     double hpq = 1.0;
     { const int ap = hpow < 0 ? -hpow : hpow; for (int i = 0; i < ap; i++) hpq *= hq; if (hpow < 0) hpq = 1.0 / hpq; }
