@@ -487,11 +487,17 @@ __global__ void __launch_bounds__(128) k_facetpatch_dmma(
     for (int c0 = 0; c0 < npad; c0 += CH) {
       const int cs = min(CH, npad - c0);  // multiple of 4
       __syncwarp();
-      if (lane < cs) {
-        const int l = c0 + lane;
-        double* B = Bw + (size_t)lane * PS;
+      // staging of the jump vectors: with at most 16 points in the chunk the two bases of a point go to two lanes (lane q and
+      // q + 16: all 32 lanes busy), else one lane evaluates them one after the other; ONE inlined copy of the shape functions
+      const bool split = 2 * cs <= 32;
+      const int q = split ? (lane & 15) : lane;
+      const int half0 = split ? (lane >> 4) : 0, nrep = split ? 1 : 2;
+      if (q < cs) {
+        const int l = c0 + q;
+        double* B = Bw + (size_t)q * PS;
         if (l >= npatch) {
-          for (int i = 0; i <= NDP; i++) B[i] = 0.0;  // padding point: weight 0
+          if (half0 == 0)
+            for (int i = 0; i <= NDP; i++) B[i] = 0.0;  // padding point: weight 0
         } else {
           double x1[3], x2[3], x[3], w;
           if (DEF) {
@@ -509,12 +515,23 @@ __global__ void __launch_bounds__(128) k_facetpatch_dmma(
             map_inv<D>(vx1, Fi1, x, x1);
             w = coef * hp * (w * meas2);
           }
+          if (half0 == 0) {
 #pragma unroll
-          for (int i = N; i < NDP; i++) B[i] = 0.0;
-          ValSink s1{B, 1.0}, s2{B + ND, -1.0};
-          xg_h1_shapes<D, P>(v1, x1, s1);
-          xg_h1_shapes<D, P>(v2, x2, s2);
-          B[NDP] = w;
+            for (int i = N; i < NDP; i++) B[i] = 0.0;
+            B[NDP] = w;
+          }
+#pragma unroll 1
+          for (int rep = 0; rep < nrep; rep++) {
+            const int half = half0 + rep;
+            int vs[D + 1];
+            double xs[3];
+#pragma unroll
+            for (int k = 0; k < D + 1; k++) vs[k] = half ? v2[k] : v1[k];
+#pragma unroll
+            for (int c = 0; c < 3; c++) xs[c] = half ? x2[c] : x1[c];
+            ValSink sk{B + half * ND, half ? -1.0 : 1.0};
+            xg_h1_shapes<D, P>(vs, xs, sk);
+          }
         }
       }
       __syncwarp();
