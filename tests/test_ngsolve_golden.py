@@ -118,3 +118,61 @@ def test_cuda_path_on_the_dumped_inputs(path):
         for key, (p_, w_) in saved.items():
             dim, order = (int(t) for t in key.split("_"))
             ops.set_rule(dim, order, p_, w_, ctx=ctx)
+
+
+def _dump_tool():
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("dump_ngsolve_golden", os.path.join(os.path.dirname(HERE), "tools", "dump_ngsolve_golden.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+@pytest.mark.parametrize("path", FILES, ids=[os.path.basename(p) for p in FILES])
+def test_scalar_integrals_oracle(path):
+    """`integral_cases` of the dump: Integrate(x^a y^b z^c * dCut(lset, dt[, vb=BND])) on meshes whose interface crosses the
+    boundary, against the oracle's cut rules on the DUMPED mesh and level set (volume: xo_integrate_monomial; boundary: the
+    rules of the boundary facets, IF on 2D boundary segments as the point measure of cutint/straightcutrule.cpp:646-656)"""
+    g = load(path)
+    if "integral_cases" not in g:
+        pytest.skip("dump without the integral_cases section (older tools/dump_ngsolve_golden.py)")
+    tool = _dump_tool()
+    n = 0
+    for c in g["integral_cases"]:
+        dim = c["dim"]
+        pts, els, phi = np.array(c["points"])[:, :dim], np.array(c["elements"], dtype=np.int32), np.array(c["lset_p1"])
+        for it in c["integrals"]:
+            got = tool.oracle_integral(xo, dim, pts, els, phi, it["dt"], it["vorb"], it["order"], it["expo"])
+            assert got is not None
+            assert abs(got - it["value"]) <= 1e-12 * max(1.0, abs(it["value"])), (c["name"], it)
+            n += 1
+    assert n > 0
+
+
+def test_boundary_integral_helper_against_the_reference_known_answers():
+    """the boundary part of tools/dump_ngsolve_golden.oracle_integral against tests/pytests/test_bndcut.py of the reference:
+    lset = x - c on the unit square: NEG boundary length 2 c + 1 (:30-47), NEG + POS = 4 (:60-70), two intersection points
+    (:171-183), sum of x = 2 c and of y = 1 over them (:187-200); unit cube: NEG boundary area 1 + 4 c (:73-86)"""
+    tool = _dump_tool()
+    n = 5
+    xs = np.linspace(0.0, 1.0, n + 1)
+    pts = np.array([[xs[i], xs[j]] for j in range(n + 1) for i in range(n + 1)])
+    els = []
+    for j in range(n):
+        for i in range(n):
+            v00 = i + (n + 1) * j
+            els += [[v00, v00 + 1, v00 + n + 2], [v00, v00 + n + 1, v00 + n + 2]]
+    els = np.array(els, dtype=np.int32)
+    for c in (0.3, 0.5, 0.7):
+        phi = pts[:, 0] - c
+        neg = tool.oracle_integral(xo, 2, pts, els, phi, "neg", "bnd", 0, [0, 0, 0])
+        pos = tool.oracle_integral(xo, 2, pts, els, phi, "pos", "bnd", 0, [0, 0, 0])
+        assert abs(neg - (2 * c + 1)) < 1e-12 and abs(neg + pos - 4.0) < 1e-12
+        assert abs(tool.oracle_integral(xo, 2, pts, els, phi, "if", "bnd", 0, [0, 0, 0]) - 2.0) < 1e-12
+        assert abs(tool.oracle_integral(xo, 2, pts, els, phi, "if", "bnd", 1, [1, 0, 0]) - 2 * c) < 1e-12
+        assert abs(tool.oracle_integral(xo, 2, pts, els, phi, "if", "bnd", 1, [0, 1, 0]) - 1.0) < 1e-12
+    from oracle import meshgen
+    p3, e3 = meshgen.structured_tets(3)
+    neg3 = tool.oracle_integral(xo, 3, p3, e3, p3[:, 0] - 0.3, "neg", "bnd", 0, [0, 0, 0])
+    assert abs(neg3 - (1.0 + 4 * 0.3)) < 1e-12
+    assert tool.oracle_integral(xo, 3, p3, e3, p3[:, 0] - 0.3, "if", "bnd", 0, [0, 0, 0]) is None
