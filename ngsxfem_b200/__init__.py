@@ -22,5 +22,7 @@ from .forms import (dCut, dFacetPatch, grad, Normalize, specialcf, BilinearForm,
 from .spacetime import (ScalarTimeFE, SpaceTimeFESpace, SpaceTimeGridFunction, SpaceTimeInterpolateToP1,
                         ReferenceTimeVariable, tref, dtref, dt, fix_tref, dxtref, dmesh)
 from .lsetcurv import LevelSetMeshAdaptation, ProjectShift
+from . import mlset
+from .mlset import DomainTypeArray, TensorUnion, TensorIntersection
 
 __all__ = [n for n in dir() if not n.startswith("_")]

@@ -74,10 +74,14 @@ class Scalar:
 
 
 class Normal:
-    """n = Normalize(grad(lsetp1))"""
+    """n = Normalize(grad(lsetp1)), or its negative (the outward normals of mlset.DomainTypeArray.GetOuterNormals,
+    python/mlset.py:436-440): the sign goes into the coefficient of grad(u) * n"""
 
-    def __init__(self, lset):
-        self.lset = lset
+    def __init__(self, lset, sign=1.0):
+        self.lset, self.sign = lset, float(sign)
+
+    def __neg__(self):
+        return Normal(self.lset, -self.sign)
 
 
 class GradLset:
@@ -133,7 +137,7 @@ class Proxy:
         if isinstance(o, Normal):
             if self.op != OP_GRAD or self.other:
                 raise XgpuError("only grad(u)*n is supported with the level-set normal")
-            return self._with(op=OP_DN, nlset=o.lset)
+            return self._with(op=OP_DN, nlset=o.lset, scal=self.scal * o.sign)
         if isinstance(o, FacetNormal):
             if self.op != OP_GRAD:
                 raise XgpuError("only grad(u)*nF is supported with the facet normal")
