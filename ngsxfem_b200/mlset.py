@@ -9,7 +9,8 @@ the host — it is an input description, not part of the hot path (SURVEY.md §2
 pinned by its own known answers (tests/pytests/test_mlset_module_functionality.py, test_mlset_integration.py:170-253).
 
 Compression needs the measure of a piece: `Integrate(..., order=0)` on the device (cutint/python_cutint.cpp:21-163 through
-xgpu_cutquad_ml_*).  The integrator can be replaced (`integrator=`) — the CPU tests pass the oracle's multi-level-set rule.
+xgpu_cutquad_ml_*).  The integrator can be replaced (`integrator=`: a function (level sets, tuple) -> measure) — the tests on a
+host without a GPU pass their own.
 """
 import itertools
 
