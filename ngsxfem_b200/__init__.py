@@ -24,7 +24,7 @@ from .spacetime import (ScalarTimeFE, SpaceTimeFESpace, SpaceTimeGridFunction, S
 from .lsetcurv import LevelSetMeshAdaptation, ProjectShift
 from . import mlset
 from .mlset import DomainTypeArray, TensorUnion, TensorIntersection
-from . import utils
+from . import utils, lset_smoothblend
 from .compat import SymbolicBFI, SymbolicLFI, NoDeformation, CutRatioGF, kappa, IsCut, fix_t
 
 __all__ = [n for n in dir() if not n.startswith("_")]
