@@ -25,6 +25,7 @@ from .lsetcurv import LevelSetMeshAdaptation, ProjectShift
 from . import mlset
 from .mlset import DomainTypeArray, TensorUnion, TensorIntersection
 from . import utils, lset_smoothblend
-from .compat import SymbolicBFI, SymbolicLFI, NoDeformation, CutRatioGF, kappa, IsCut, fix_t
+from .compat import SymbolicBFI, SymbolicLFI, NoDeformation, IndicatorCF, CutRatioGF, kappa, IsCut, fix_t
+from .forms import ElementCF
 
 __all__ = [n for n in dir() if not n.startswith("_")]

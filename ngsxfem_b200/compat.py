@@ -87,6 +87,17 @@ class NoDeformation:
         return self.deform
 
 
+def IndicatorCF(mesh, ba, facets=False):
+    """1 on the elements marked in the BitArray, 0 on the others (python/__init__.py:441-453; a snapshot of `ba`, as the
+    reference's BitArrayCF(BitArray(ba))).  The facet variant is a facet-wise function and is not provided."""
+    if facets:
+        raise XgpuError("IndicatorCF(facets=True): facet-wise functions are not on the accelerated path")
+    if len(ba) != mesh.ne:
+        raise XgpuError("IndicatorCF: the BitArray is not over the elements of the mesh")
+    from .forms import ElementCF
+    return ElementCF(torch.from_numpy(ba.to_numpy().astype("float64")).to(mesh.device))
+
+
 def CutRatioGF(cutinfo):
     """the ratio |element ∩ NEG| / |element| of every element as a piecewise constant function: one value per element
     (python/__init__.py:455-462; an L2(order=0) GridFunction there, the device vector of CutInfo here)"""

@@ -381,6 +381,54 @@ class CoefficientFunction:
         return out.contiguous()
 
 
+class ElementCF(CoefficientFunction):
+    """a piecewise constant coefficient: one value per mesh element (the reference's BitArrayCF / IndicatorCF(mesh, ba) and
+    L2(order=0) GridFunctions such as CutRatioGF, python/__init__.py:441-462).  At the rule points of an element it is the
+    element's value, so it folds into the weights like any coefficient: cf * (u*v) * dCut(...), cf * v * dCut(...),
+    Integrate(..., cf=cf).  Products: with numbers and with other ElementCFs (pointwise coefficients and element-wise ones do
+    not mix in one product: write two integrals or fold the element values into the callable's GridFunction arguments)."""
+
+    def __init__(self, values, scale=1.0):
+        self.values = torch.as_tensor(values, dtype=torch.float64).contiguous()
+        if self.values.dim() != 1:
+            raise XgpuError("ElementCF: one value per element")
+        self.factors = []
+        self.scale = float(scale)
+
+    def _copy(self, factors=None, scale=None):
+        return ElementCF(self.values, self.scale if scale is None else scale)
+
+    def __mul__(self, o):
+        if isinstance(o, numbers.Number):
+            return ElementCF(self.values, self.scale * float(o))
+        if isinstance(o, ElementCF):
+            if o.values.shape != self.values.shape:
+                raise XgpuError("ElementCF * ElementCF: different numbers of elements")
+            return ElementCF(self.values * o.values.to(self.values.device), self.scale * o.scale)
+        if isinstance(o, CoefficientFunction):
+            raise XgpuError("a pointwise CoefficientFunction and an element-wise one do not mix in one product")
+        return CoefficientFunction.__mul__(self, o)       # integrands: cf * form
+
+    __rmul__ = __mul__
+
+    def _per_point(self, fe_mesh, elems, off):
+        if self.values.numel() != fe_mesh.ne:
+            raise XgpuError("ElementCF: the number of values is not the number of mesh elements")
+        v = self.values.to(off.device)
+        if elems is not None:
+            v = v[elems.long()]
+        return (self.scale * torch.repeat_interleave(v, off[1:] - off[:-1])).contiguous()
+
+    def evaluate(self, dim, fe_mesh, elems, off, pts, ctx):
+        return self._per_point(fe_mesh, elems, off)
+
+    def evaluate_st(self, dim, fe_mesh, elems, off, pts, tv, ctx):
+        return self._per_point(fe_mesh, elems, off)
+
+    def evaluate_facets(self, fe_mesh, facet_vtx, off, pts):
+        raise XgpuError("element-wise coefficients on facet integrands are not on the accelerated path")
+
+
 def _merge_cf(a, b):
     if a is b:
         return a

@@ -110,3 +110,38 @@ def test_fix_t_is_fix_tref(capsys):
     a, b = xf.fix_t(u, 0.0), xf.fix_tref(u, 0.0)
     assert a.fixt == b.fixt == 0.0 and a.op == b.op
     assert "deprecated" in capsys.readouterr().out
+
+
+def test_element_wise_coefficients():
+    """ElementCF / IndicatorCF: the element's value at each of its rule points (offsets of the listed elements), folded into
+    integrands like any coefficient; pure index arithmetic, no kernel"""
+    mesh, lset, V = setup()
+    u, v = V.TnT()
+    mask = torch.zeros(mesh.ne, dtype=torch.bool)
+    mask[[1, 4, 5, 30]] = True
+    ba = xf.BitArray.from_numpy(mask.numpy(), "cpu")
+    ind = xf.IndicatorCF(mesh, ba)
+    assert isinstance(ind, xf.ElementCF) and isinstance(ind, xf.CoefficientFunction) and torch.equal(ind.values, mask.double())
+    # three listed elements with 2, 0 and 3 rule points
+    elems = torch.tensor([4, 7, 30], dtype=torch.int32)
+    off = torch.tensor([0, 2, 2, 5], dtype=torch.int64)
+    pts = torch.zeros((5, 3), dtype=torch.float64)
+    assert ind.evaluate(2, mesh, elems, off, pts, None).tolist() == [1.0, 1.0, 1.0, 1.0, 1.0]
+    assert ind.evaluate(2, mesh, torch.tensor([0, 4, 2], dtype=torch.int32), off, pts, None).tolist() == [0.0, 0.0, 0.0, 0.0, 0.0]
+    cr = xf.ElementCF(torch.arange(mesh.ne, dtype=torch.float64))
+    assert (2.0 * cr).evaluate(2, mesh, elems, off, pts, None).tolist() == [8.0, 8.0, 60.0, 60.0, 60.0]
+    assert (cr * ind * 0.5).evaluate_st(2, mesh, elems, off, pts, torch.zeros(5), None).tolist() == [2.0, 2.0, 15.0, 15.0, 15.0]
+    all_off = torch.arange(mesh.ne + 1, dtype=torch.int64)                        # elems=None: one point per element
+    assert torch.equal(ind.evaluate(2, mesh, None, all_off, None, None), mask.double())
+    # integrands carry it like a pointwise coefficient
+    f = ind * (u * v)
+    assert f.cf is ind and (ind * v).cf is ind and ((u * v) * ind).cf is ind
+    itg = f * xf.dCut(lset, NEG)
+    assert itg.form.cf is ind
+    pointwise = xf.CoefficientFunction(lambda x, y: x)
+    for bad in (lambda: ind * pointwise, lambda: pointwise * ind, lambda: cr * xf.ElementCF(torch.zeros(3)),
+                lambda: xf.ElementCF(torch.zeros(3)).evaluate(2, mesh, None, all_off, None, None),
+                lambda: ind.evaluate_facets(mesh, None, off, pts), lambda: xf.IndicatorCF(mesh, ba, facets=True),
+                lambda: xf.IndicatorCF(mesh, xf.BitArray(mesh.ne + 1, "cpu")), lambda: xf.ElementCF(torch.zeros((2, 2)))):
+        with pytest.raises(xf.XgpuError):
+            bad()
